@@ -1,0 +1,127 @@
+"""ctypes binding of libslb200.so (the C-ABI declared in include/slb200.h).
+
+This is the only place Python touches the kernels. There is no CPU fallback: if the shared library is missing
+or no CUDA device is visible, every entry point raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libslb200.so"
+_lib = None
+
+# enums (mirror include/slb200.h)
+DT_F32, DT_F16, DT_BF16 = 0, 1, 2
+LAYOUT_NCHW, LAYOUT_BTF = 0, 1
+AGG_MEAN, AGG_MAX, AGG_ABSMEAN, AGG_ABSMAX, AGG_TOKEN = 0, 1, 2, 3, 4
+EPI_NONE, EPI_GELU_ERF, EPI_QUICKGELU, EPI_GELU_TANH = 0, 1, 2, 3
+
+_DTYPES = {torch.float32: DT_F32, torch.float16: DT_F16, torch.bfloat16: DT_BF16}
+
+
+class SlbError(RuntimeError):
+    """A libslb200 entry point returned a negative status."""
+
+
+_PROTOS = {
+    "slb_version": (c_int, []),
+    "slb_last_error": (c_char_p, []),
+    "slb_device_info": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "slb_agg_reduce": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int64, c_void_p, c_void_p]),
+    "slb_topk_update": (
+        c_int,
+        [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p],
+    ),
+    "slb_agg_topk_update": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+         c_void_p, c_size_t, c_void_p],
+    ),
+    "slb_topk_merge_lists": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "slb_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "slb_u8_to_f32_norm": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "slb_split_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "slb_gemm_bf16x3": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
+    "slb_layernorm": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
+    "slb_attention_small": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
+    "slb_patchify": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "slb_assemble_tokens": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p],
+    ),
+    "slb_row_inv_norm": (c_int, [c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p]),
+    "slb_clarity": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "slb_polysem_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "slb_polysem_2means": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_double, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load(require_device: bool = False):
+    """Load libslb200.so (once). Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise SlbError(
+                f"{_LIB_PATH} not found: build it with `python -m semanticlens_b200.csrc.build` "
+                "(there is no CPU fallback for the B200 kernels)"
+            )
+        lib = ctypes.CDLL(str(_LIB_PATH))
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(lib, name, None)
+            if fn is None:
+                continue  # checked by tests/test_abi.py against the header
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    if require_device and not torch.cuda.is_available():
+        raise SlbError("no CUDA device visible: the semanticlens_b200 hot path runs on B200 only (no CPU fallback)")
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().slb_last_error()
+        raise SlbError(f"{what or 'libslb200'} failed with status {rc}: {msg.decode() if msg else ''}")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPES[dt]
+    except KeyError as e:
+        raise TypeError(f"unsupported activation dtype {dt} (fp32, fp16, bf16 are supported)") from e
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise SlbError(f"{name} must be a CUDA tensor (got {t.device}); the B200 path has no CPU fallback")

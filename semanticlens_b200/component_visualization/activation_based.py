@@ -1,0 +1,263 @@
+"""Activation-based component visualization — B200 implementation.
+
+Drop-in for ``semanticlens.component_visualization.activation_based.ActivationComponentVisualizer``
+(reference: activation_based.py:41-560): same constructor, ``run`` / ``_run`` / ``_compute_concept_db`` /
+``_embed_vision_dataset`` / ``get_max_reference``, same cache directory grammar (the class name is part of the
+path, :295), same exceptions and warnings.
+
+Differences that are not API-visible:
+
+* the sweep never synchronises the host: hooks enqueue K1+K2 on the model's stream (activation_caching.py), input
+  batches are copied host->device from pinned memory with ``non_blocking=True`` and the logits are not copied back
+  (reference :352 does ``model(images.to(device)).cpu()``);
+* when ``torch.distributed`` is initialised with world_size R > 1, rank r sweeps and embeds the contiguous index
+  range ``[r*ceil(N/R), (r+1)*ceil(N/R))``; the per-rank top-k states are exchanged with ONE all-gather and merged by
+  the K2 list-merge kernel, the embedding shards with one more all-gather (``semanticlens_b200.distributed``);
+* embeddings stay in HBM and ``embeds[sample_ids]`` is the K5 gather kernel; the concept DB is returned on the CPU
+  like the reference unless ``output_device`` is set.
+"""
+
+from __future__ import annotations
+
+import logging
+import warnings
+from pathlib import Path
+
+import torch
+from torch import nn
+from tqdm import tqdm
+
+from .. import distributed as sdist
+from .. import ops
+from ..utils.helper import get_fallback_name
+from . import aggregators
+from .activation_caching import ActMaxCache
+from .base import AbstractComponentVisualizer
+
+logger = logging.getLogger(__name__)
+
+
+class MissingNameWarning(UserWarning):
+    """A model or dataset has no ``.name``; a fallback derived from its ``repr`` names the cache directory."""
+
+
+class ActivationComponentVisualizer(AbstractComponentVisualizer):
+    """Find, per component of the chosen layers, the ``num_samples`` dataset items that activate it most.
+
+    Parameters mirror the reference (activation_based.py:124-134).
+    """
+
+    AGGREGATION_DEFAULTS = {
+        "max": aggregators.aggregate_conv_max,
+        "mean": aggregators.aggregate_conv_mean,
+    }
+
+    def __init__(
+        self,
+        model: nn.Module,
+        dataset_model,
+        dataset_fm,
+        layer_names: list[str],
+        num_samples: int,
+        device=None,
+        aggregate_fn=None,
+        cache_dir: str | None = None,
+    ):
+        self.model = model
+        self.dataset = dataset_model
+        self.dataset_fm = dataset_fm
+        self.output_device = "cpu"  # where _compute_concept_db leaves the (C, k, D) tensors
+        self.show_progress = True
+        self._init_cache_dir(cache_dir)
+        self._validate_args()
+
+        self.layer_names = layer_names
+        self._check_layers()
+
+        device = device or next(model.parameters()).device
+        self.model.to(device)
+
+        if aggregate_fn is None:
+            logger.warning(f"No aggregation_fn provided using default: {aggregators.aggregate_conv_mean.__name__}")
+            aggregate_fn = aggregators.aggregate_conv_mean
+
+        self.actmax_cache = ActMaxCache(self.layer_names, n_collect=num_samples, aggregation_fn=aggregate_fn)
+
+        if self.caching:
+            try:
+                self.actmax_cache.load(self.storage_dir)
+                logger.info(f"Results loaded from {self.storage_dir}")
+            except FileNotFoundError:
+                logger.info(f"Results will be stored in {self.storage_dir}")
+
+    # -- argument checks (reference :187-229) ------------------------------------------------------
+    def _validate_args(self):
+        for obj, what in ((self.model, "Model"), (self.dataset, "Dataset")):
+            if hasattr(obj, "name"):
+                continue
+            fallback = get_fallback_name(obj)
+            if self.caching:
+                warnings.warn(
+                    f"{what} does not have a name attribute, which is required for reliable caching.\n"
+                    f"Using a fallback name: {fallback}.",
+                    MissingNameWarning,
+                    stacklevel=3,
+                )
+            obj.name = fallback
+
+        if len(self.dataset) != len(self.dataset_fm):
+            raise ValueError(
+                "Model and foundation model datasets should have the same length.",
+                (len(self.dataset), len(self.dataset_fm)),
+            )
+
+    def _check_layers(self):
+        modules = dict(self.model.named_modules())
+        for layer in self.layer_names:
+            if layer not in modules:
+                raise ValueError(f"Layer '{layer}' not found in model.")
+
+    def _check_layer_name(self, layer_name):
+        if layer_name not in self.layer_names:
+            raise ValueError(f"Layer '{layer_name}' not found in model layers: {self.layer_names}")
+
+    def _init_cache_dir(self, cache_dir):
+        if cache_dir is None:
+            logger.warning("No cache dir provided. Results will not be cached!")
+            self._cache_root = None
+        else:
+            self._cache_root = Path(cache_dir)
+            self._cache_root.mkdir(parents=True, exist_ok=True)
+
+    # -- plugin properties ---------------------------------------------------------------------------
+    @property
+    def device(self):
+        return next(self.model.parameters()).device
+
+    def to(self, device):
+        return self.model.to(device)
+
+    @property
+    def caching(self) -> bool:
+        return self._cache_root is not None
+
+    @property
+    def storage_dir(self):
+        assert self._cache_root, "No cache dir provided"
+        return self._cache_root / self.__class__.__name__ / self.dataset.name / self.model.name
+
+    @property
+    def metadata(self) -> dict[str, str]:
+        return {**self.actmax_cache.metadata, "dataset": self.dataset.name, "model": self.model.name}
+
+    # -- collect --------------------------------------------------------------------------------------
+    def run(self, batch_size=32, num_workers=0):
+        """Sweep ``dataset_model`` (or load the cached result) -> ``{layer: ActMax}`` (reference :309-339)."""
+        if self._cache_root is None:
+            logger.debug("No cache root provided, running computation...")
+            return self._run(batch_size=batch_size, num_workers=num_workers)
+        try:
+            self.actmax_cache.load(self.storage_dir)
+            return self.actmax_cache.cache
+        except FileNotFoundError:
+            logger.debug(f"Activation maximization cache not found at {self.storage_dir}. Running computation...")
+            return self._run(batch_size=batch_size, num_workers=num_workers)
+
+    @torch.no_grad()
+    def _run(self, batch_size: int = 64, num_workers: int = 0):
+        """The activation sweep (reference :341-358), image-sharded across ranks when distributed."""
+        shard = sdist.image_shard(len(self.dataset))
+        dataset = self.dataset if shard.world == 1 else torch.utils.data.Subset(self.dataset, range(shard.lo, shard.hi))
+        device = self.device
+        dataloader = torch.utils.data.DataLoader(
+            dataset,
+            batch_size=batch_size,
+            shuffle=False,
+            num_workers=num_workers,
+            pin_memory=device.type == "cuda",
+        )
+        if shard.world > 1:
+            # ids are positions in iteration order; a shard starts at its offset, on a fresh state
+            if shard.hi <= shard.lo:
+                raise ValueError("the dataset must have at least one item per rank")
+            for layer in self.layer_names:
+                self.actmax_cache.cache[layer] = type(self.actmax_cache.cache[layer])(self.actmax_cache.n_collect)
+                self.actmax_cache.sample_idx_counter[layer] = shard.lo
+        with self.actmax_cache.hook_context(self.model):
+            for images, _ in tqdm(
+                dataloader, total=len(dataloader), desc="Collecting ActMax", disable=not self.show_progress
+            ):
+                self.model(images.to(device, non_blocking=True))  # hooks enqueue K1+K2; nothing is copied back
+
+        if shard.world > 1:
+            sdist.merge_actmax_across_ranks(self.actmax_cache, device)
+
+        if self._cache_root and shard.rank == 0:
+            self.actmax_cache.store(self.storage_dir)
+            logger.debug(f"Stored activation maximization cache at {self.storage_dir}")
+
+        return self.actmax_cache.cache
+
+    # -- embed + gather -------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _compute_concept_db(self, fm, batch_size=32, **kwargs):
+        """``{layer: embeds[sample_ids]}`` with embeds = fm image embeddings of ``dataset_fm`` (reference :360-390)."""
+        self.run(batch_size=batch_size, **kwargs)
+
+        embeds = self._embed_vision_dataset(fm, batch_size, **kwargs)
+
+        concept_db = dict()
+        for layer_name in self.layer_names:
+            ids = self.get_max_reference(layer_name)
+            if embeds.is_cuda:
+                db = ops.gather_rows(embeds, ids)  # K5; python-negative semantics: id -1 -> last image
+                concept_db[layer_name] = db.to(self.output_device)
+            else:
+                concept_db[layer_name] = embeds[ids]
+        return concept_db
+
+    def _embed_vision_dataset(self, fm, batch_size, **kwargs):
+        """Embed every item of ``dataset_fm`` -> (N, D) fp32 (reference :392-433); stays on the GPU."""
+        fm.to(self.device)
+
+        def item_list_collate(batch):
+            # dataset_fm yields PIL images (or uint8 CHW tensors); fm.preprocess is applied per batch
+            if isinstance(batch[0], (tuple, list)):
+                return [item[0] for item in batch]
+            return list(batch)
+
+        shard = sdist.image_shard(len(self.dataset_fm))
+        dataset = (
+            self.dataset_fm if shard.world == 1 else torch.utils.data.Subset(self.dataset_fm, range(shard.lo, shard.hi))
+        )
+        loader = torch.utils.data.DataLoader(
+            dataset, batch_size=batch_size, shuffle=False, collate_fn=item_list_collate, **kwargs
+        )
+        embeds = []
+        with tqdm(total=len(dataset), desc="Embedding Dataset", disable=not self.show_progress) as pbar:
+            for items in loader:
+                inputs = fm.preprocess(items)
+                embeds.append(fm.encode_image(inputs))
+                pbar.update(len(items))
+        if embeds:
+            embeds = torch.cat(embeds)
+        else:
+            embeds = torch.empty((0, 0), dtype=torch.float32, device=self.device)
+
+        if shard.world > 1:
+            embeds = sdist.all_gather_rows(embeds, shard, len(self.dataset_fm))
+
+        assert embeds.shape[0] == len(self.dataset_fm), "Number of embeddings does not match number of ids!"
+        return embeds
+
+    def get_max_reference(self, layer_name) -> torch.Tensor:
+        """(n_components, n_samples) int64 dataset indices of the top activating samples (reference :435-451)."""
+        self._check_layer_name(layer_name)
+        return self.actmax_cache.cache[layer_name].sample_ids
+
+    def visualize_components(self, *args, **kwargs):
+        """Matplotlib grid plotting (reference :453-543) is outside the concept-DB build path."""
+        raise NotImplementedError(
+            "visualize_components is plotting-only and is not part of the B200 concept-database path; "
+            "use get_max_reference(layer) and plot the dataset items yourself."
+        )
