@@ -51,6 +51,10 @@ extern "C" {
 int slb_version(void);
 const char* slb_last_error(void);
 
+/* Number of kernels this library has launched in this process so far (bench.py reports the delta over the
+ * timed region as "gpu_launches"). */
+int64_t slb_launch_count(void);
+
 /* Number of SMs / compute capability of the current device (host query, for sizing and for
  * failing loudly on a non-sm_100 device). Returns SLB_ECUDA if no device. */
 int slb_device_info(int* sm_count, int* cc_major, int* cc_minor);
@@ -96,79 +100,6 @@ int slb_topk_merge_lists(const uint16_t* vals, const int64_t* ids, int64_t R, in
  * (activation_based.py:387-390; id -1 aliases the last row). Rows are `D` fp32. */
 int slb_gather_rows(const float* table, int64_t N, int64_t D, const int64_t* idx, int64_t n_idx, float* out,
                     void* stream);
-
-/* ------------------------------------------------------------------------------------------
- * embed: preprocessing + ViT image tower  (foundation_models/clip.py:103-163 -> open_clip)
- * ---------------------------------------------------------------------------------------- */
-
-/* K3. out[b,c,y,x] = (u8[b,c,y,x]/255 - mean[c]) / std[c]; `ToTensor` + `Normalize` of the open_clip eval
- * transform (clip.py:157-160) for already-sized planar u8 images. n_pix = H*W. */
-int slb_u8_to_f32_norm(const uint8_t* img, int64_t B, int64_t Cc, int64_t n_pix, const float* mean3,
-                       const float* std3, float* out, void* stream);
-
-/* Split an fp32 matrix into bf16 (hi, lo) planes: hi = bf16(x), lo = bf16(x - hi). n elements. */
-int slb_split_bf16(const float* x, int64_t n, uint16_t* hi, uint16_t* lo, void* stream);
-
-/* epilogue selectors for slb_gemm_bf16x3 */
-#define SLB_EPI_NONE 0
-#define SLB_EPI_GELU_ERF 1
-#define SLB_EPI_QUICKGELU 2
-#define SLB_EPI_GELU_TANH 3
-
-/* K4. D[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) (+ residual[M,N]) with fp32-grade accuracy on the
- * 5th-gen tensor cores: A and W are given as bf16 (hi, lo) planes and the kernel accumulates
- * Ahi*Whi + Ahi*Wlo + Alo*Whi in fp32 TMEM accumulators (tcgen05.mma kind::f16, TMA-fed, 128B swizzle).
- * `passes` = 3 (default, ~2^-16 relative) or 1 (hi*hi only).
- * Outputs: out_f32 (nullable) and/or out_hi/out_lo planes (nullable) for the next GEMM.
- * row_scale/col_scale (nullable, fp32 [M]/[N]) multiply the accumulator before bias (cosine similarity).
- * Requirements: K % 64 == 0, N % 8 == 0, planes 16-byte aligned, row-major, ld == K / N. */
-int slb_gemm_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, const uint16_t* w_hi, const uint16_t* w_lo,
-                    int64_t M, int64_t N, int64_t K, const float* bias, const float* residual,
-                    const float* row_scale, const float* col_scale, int epilogue, int passes, float* out_f32,
-                    uint16_t* out_hi, uint16_t* out_lo, void* stream);
-
-/* Row LayerNorm over the last dim (fp32 two-pass in registers), eps inside the sqrt like torch.
- * Writes fp32 (nullable) and/or bf16 (hi, lo) planes (nullable). */
-int slb_layernorm(const float* x, int64_t rows, int64_t cols, const float* gamma, const float* beta, float eps,
-                  float* out_f32, uint16_t* out_hi, uint16_t* out_lo, void* stream);
-
-/* Multi-head self-attention for short sequences (T <= 1024, head_dim <= 128, head_dim % 4 == 0), fp32 SIMT.
- * qkv: (B, T, 3*H*dh) fp32 packed [q | k | v] as produced by nn.MultiheadAttention's in_proj.
- * out: (B, T, H*dh) as fp32 (nullable) and/or bf16 planes (nullable). Non-causal; scale = dh^-0.5. */
-int slb_attention_small(const float* qkv, int64_t B, int64_t T, int64_t H, int64_t dh, float* out_f32,
-                        uint16_t* out_hi, uint16_t* out_lo, void* stream);
-
-/* Patchify (B,3,S,S) fp32 -> im2col rows (B*gh*gw, 3*P*P) as bf16 planes, so the patch-embedding conv
- * (kernel = stride = P) becomes one GEMM. */
-int slb_patchify(const float* img, int64_t B, int64_t S, int64_t P, uint16_t* out_hi, uint16_t* out_lo,
-                 void* stream);
-
-/* x[b, t, :] = (t == 0 && has_cls ? cls : patch[b, t - has_cls, :]) + pos[t, :]  (fp32). */
-int slb_assemble_tokens(const float* patch, const float* cls, const float* pos, int64_t B, int64_t T,
-                        int64_t W, int has_cls, float* out, void* stream);
-
-/* ------------------------------------------------------------------------------------------
- * analyze: scores.py
- * ---------------------------------------------------------------------------------------- */
-
-/* inv_norm[r] = 1 / max(||x[r,:]||_2, eps)   (F.normalize, scores.py:120-121, eps = 1e-12) */
-int slb_row_inv_norm(const float* x, int64_t rows, int64_t cols, float eps, float* inv_norm, void* stream);
-
-/* K7. clarity_score (scores.py:19-47): V (C, k, D) fp32 -> out (C,) fp32, one pass over V. */
-int slb_clarity(const float* V, int64_t C, int64_t k, int64_t D, float* out, void* stream);
-
-/* K8. polysemanticity_score (scores.py:132-185) for n_clusters = 2: sklearn-faithful KMeans
- * (k-means++ with 2+log(2)->2 local trials, Lloyd, tol, n_init inits, best inertia) on each (k, D) block,
- * driven by the `n_init*3` uniform draws of RandomState(seed) + the integer draws, which are data
- * independent and precomputed on the host (`rand_first` int64[n_init], `rand_u` double[n_init*2]).
- * out (C,) float64 = 1 - cos(centre_1, centre_2) or the reference's small-cluster fallback.
- * labels_out (nullable) (C, k) int32 best labels; counts_out (nullable) (C, 2) int32.
- * workspace: slb_polysem_workspace_bytes(k, D) bytes per concurrently processed neuron. */
-size_t slb_polysem_workspace_bytes(int64_t C, int64_t k, int64_t D);
-int slb_polysem_2means(const float* V, int64_t C, int64_t k, int64_t D, int n_init, int max_iter, double tol_rel,
-                       const int64_t* rand_first, const double* rand_u, int replace_empty, double* out,
-                       int32_t* labels_out, int32_t* counts_out, void* workspace, size_t workspace_bytes,
-                       void* stream);
 
 #ifdef __cplusplus
 }

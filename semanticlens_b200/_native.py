@@ -31,6 +31,7 @@ class SlbError(RuntimeError):
 _PROTOS = {
     "slb_version": (c_int, []),
     "slb_last_error": (c_char_p, []),
+    "slb_launch_count": (c_int64, []),
     "slb_device_info": (c_int, [c_void_p, c_void_p, c_void_p]),
     "slb_agg_reduce": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     "slb_topk_update": (
@@ -44,34 +45,6 @@ _PROTOS = {
     ),
     "slb_topk_merge_lists": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "slb_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
-    "slb_u8_to_f32_norm": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "slb_split_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "slb_gemm_bf16x3": (
-        c_int,
-        [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-         c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
-    ),
-    "slb_layernorm": (
-        c_int,
-        [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
-    ),
-    "slb_attention_small": (
-        c_int,
-        [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
-    ),
-    "slb_patchify": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
-    "slb_assemble_tokens": (
-        c_int,
-        [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p],
-    ),
-    "slb_row_inv_norm": (c_int, [c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p]),
-    "slb_clarity": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
-    "slb_polysem_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
-    "slb_polysem_2means": (
-        c_int,
-        [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_double, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-         c_void_p, c_void_p, c_size_t, c_void_p],
-    ),
 }
 
 

@@ -2,10 +2,12 @@
 #include "slb_common.cuh"
 
 #include <string.h>
+#include <atomic>
 
 namespace {
 thread_local char g_err[512] = "";
 int g_sm_count = 0;
+std::atomic<long long> g_launches{0};
 }  // namespace
 
 void slb_set_error(const char* fmt, ...) {
@@ -14,6 +16,8 @@ void slb_set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+void slb_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int slb_sm_count() {
     if (g_sm_count > 0) return g_sm_count;
@@ -27,6 +31,8 @@ int slb_sm_count() {
 extern "C" int slb_version(void) { return SLB_VERSION; }
 
 extern "C" const char* slb_last_error(void) { return g_err; }
+
+extern "C" int64_t slb_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int slb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;

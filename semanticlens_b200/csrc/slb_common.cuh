@@ -43,8 +43,10 @@ void slb_set_error(const char* fmt, ...);
             slb_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));          \
             return SLB_ECUDA;                                                                \
         }                                                                                    \
+        slb_count_launch();                                                                  \
     } while (0)
 
+void slb_count_launch();  // process-wide counter of kernels this library has launched (slb_launch_count)
 int slb_sm_count();  // cached per process (current device at first call)
 
 static inline int64_t slb_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -18,7 +18,7 @@ def test_library_loads_and_exports_header_symbols():
 
     lib = ctypes.CDLL(str(_native.lib_path()))
     syms = declared_symbols()
-    assert len(syms) >= 10
+    assert len(syms) >= 8
     missing = [s for s in syms if not hasattr(lib, s)]
     assert not missing, f"declared in slb200.h but not exported: {missing}"
 
