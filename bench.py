@@ -1,0 +1,434 @@
+"""bench.py — concept-db images/sec (collect + embed) on N B200s of one node, one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload = BASELINE.json configs[1]: ResNet-50 (torchvision, random init) probed at conv1, layer1..layer4 with
+aggregate_conv_mean, k = 20, OpenCLIP ViT-B/32 image tower (random init) as the foundation model, synthetic
+ImageNet-shaped images, batch 256 per GPU. A *step* is one batch through the hot path:
+probed-model forward under the collect hooks (K1 aggregate + K2 top-k per hooked layer) and, when the embed stage is
+built, FM preprocess + image tower on the same images. The last timed step is followed by the job's closing work
+(cross-rank top-k exchange + merge when N > 1). Scaling is weak: every rank processes its own 256-image batches.
+
+  value      images/s with the inputs already resident in HBM (a ring of distinct device batches larger than L2)
+  e2e        images/s through the public API `Lens.compute_concept_db(cv)` / `cv._compute_concept_db(fm)` on a
+             dataset that lives in pinned HOST memory: per-batch H2D copies and the D2H of the concept DB are inside
+             the timed region
+  roofline   the dominant libslb200 kernel of the step, timed live with CUDA events inside the timed region
+  cpu_baseline / --impl reference   the torch-CPU port of the reference path (oracle/ref_port.py, pinned
+             bit-exactly to fixtures recorded from the imported reference) on the box's host cores
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+LAYERS = ["conv1", "layer1", "layer2", "layer3", "layer4"]
+K_COLLECT = 20
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+COLLECT_BYTES_PER_IMAGE = 4 * (64 * 112 * 112 + 256 * 56 * 56 + 512 * 28 * 28 + 1024 * 14 * 14 + 2048 * 7 * 7)
+
+
+def peaks() -> tuple[dict, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic data: uint8 images = per-image 7x7 colour field upsampled x32 + per-pixel noise (seeded)
+# ---------------------------------------------------------------------------------------------------
+def synth_u8(n: int, seed: int, device) -> torch.Tensor:
+    g = torch.Generator(device=device).manual_seed(seed)
+    field = torch.randint(32, 224, (n, 3, 7, 7), generator=g, device=device, dtype=torch.int16)
+    img = field.repeat_interleave(32, 2).repeat_interleave(32, 3)
+    img += torch.randint(-16, 17, (n, 3, 224, 224), generator=g, device=device, dtype=torch.int16)
+    return img.clamp_(0, 255).to(torch.uint8)
+
+
+def normalise(u8: torch.Tensor) -> torch.Tensor:
+    mean = torch.tensor(IMAGENET_MEAN, device=u8.device).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, device=u8.device).view(1, 3, 1, 1)
+    return (u8.float() / 255.0 - mean) / std
+
+
+class HostImages:
+    """dataset_model / dataset_fm pair over ONE pinned host buffer each; item i of both is the same image.
+    Only the calling rank's shard [lo, hi) of the global index range is materialised."""
+
+    def __init__(self, n_total: int, lo: int, hi: int, seed: int, gen_device, kind: str, store=None):
+        self.n_total, self.lo, self.hi, self.kind = n_total, lo, hi, kind
+        self.name = f"synthetic-{kind}-{n_total}-seed{seed}"
+        if store is not None:
+            self.u8 = store
+        else:
+            chunks = []
+            for a in range(lo, hi, 256):
+                chunks.append(synth_u8(min(256, hi - a), seed * 1_000_003 + a, gen_device).cpu())
+            self.u8 = torch.cat(chunks) if chunks else torch.empty((0, 3, 224, 224), dtype=torch.uint8)
+            if torch.cuda.is_available():
+                self.u8 = self.u8.pin_memory()
+        if kind == "model":
+            self.f32 = torch.empty(self.u8.shape, dtype=torch.float32, pin_memory=torch.cuda.is_available())
+            for a in range(0, self.u8.shape[0], 256):
+                self.f32[a : a + 256] = normalise(self.u8[a : a + 256])
+            self.labels = torch.zeros(self.u8.shape[0], dtype=torch.int64)
+
+    def __len__(self):
+        return self.n_total
+
+    def __getitem__(self, i):
+        j = i - self.lo
+        return (self.f32[j], 0) if self.kind == "model" else self.u8[j]
+
+    def get_batch(self, lo, hi):
+        a, b = lo - self.lo, hi - self.lo
+        assert 0 <= a <= b <= self.u8.shape[0], "index range outside this rank's shard"
+        return (self.f32[a:b], self.labels[a:b]) if self.kind == "model" else self.u8[a:b]
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, exact PID is killed)
+# ---------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows: list[list[str]] = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        self.mark_a = self.mark_b = 0
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def begin(self):
+        self.mark_a = len(self.rows)
+
+    def end(self):
+        self.mark_b = len(self.rows)
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = self.rows[self.mark_a : max(self.mark_b, self.mark_a + 1)] or self.rows
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) >= 6 and r[2 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(rows)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# model / FM construction
+# ---------------------------------------------------------------------------------------------------
+def probed_model():
+    import torchvision
+
+    torch.manual_seed(0)
+    m = torchvision.models.resnet50(weights=None).eval()
+    m.name = "resnet50-random-seed0"
+    return m
+
+
+def foundation_model(device):
+    """The B200 OpenCLIP ViT-B/32 tower when the embed stage is built, else None (collect-only bench)."""
+    try:
+        from semanticlens_b200.foundation_models import OpenClip
+    except ImportError:
+        return None
+    return OpenClip("ViT-B-32", device=device, load_weights=False, seed=1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline: the torch-CPU port of the reference path on a bounded sample
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_step(model_cpu, fm_cpu, batch_f32, batch_u8, sweep_state):
+    """One batch through the reference's op sequence on the host (oracle/ref_port.py)."""
+    with torch.no_grad():
+        model_cpu(batch_f32).cpu()  # hooks of sweep_state fire inside
+        if fm_cpu is not None:
+            fm_cpu.encode_image(fm_cpu.preprocess_u8(batch_u8)).cpu()
+
+
+def make_cpu_reference(with_embed: bool):
+    from oracle import ref_port as rp
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = probed_model()
+    hs = rp.HookSweepPort(LAYERS, rp.aggregate_conv_mean, K_COLLECT)
+    fm = None
+    if with_embed:
+        try:
+            from oracle import vit_port
+
+            fm = vit_port.build("ViT-B-32", seed=1)
+        except ImportError:
+            fm = None
+    return model, hs, fm
+
+
+def run_cpu_sample(n_images: int, batch: int, with_embed: bool) -> dict:
+    model, hs, fm = make_cpu_reference(with_embed)
+    u8 = synth_u8(n_images + batch, 7, "cpu")
+    f32 = normalise(u8)
+    with hs.hooked(model):
+        cpu_reference_step(model, fm, f32[:batch], u8[:batch], hs)  # warm-up (allocator, oneDNN primitives)
+        t0 = time.perf_counter()
+        for a in range(batch, n_images + batch, batch):
+            cpu_reference_step(model, fm, f32[a : a + batch], u8[a : a + batch], hs)
+        dt = time.perf_counter() - t0
+    return {"value": n_images / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_images} images, batch {batch}, torch-CPU port of the reference path "
+                      f"({'collect+embed' if fm is not None else 'collect only'}), {dt:.1f} s"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 32
+    with_embed = foundation_model_available()
+    model, hs, fm = make_cpu_reference(with_embed)
+    n = (args.steps + args.warmup) * batch
+    u8 = synth_u8(n, 7, "cpu")
+    f32 = normalise(u8)
+    with hs.hooked(model):
+        for s in range(args.warmup):
+            cpu_reference_step(model, fm, f32[s * batch : (s + 1) * batch], u8[s * batch : (s + 1) * batch], hs)
+        t0 = time.perf_counter()
+        for s in range(args.warmup, args.warmup + args.steps):
+            cpu_reference_step(model, fm, f32[s * batch : (s + 1) * batch], u8[s * batch : (s + 1) * batch], hs)
+        dt = time.perf_counter() - t0
+    v = args.steps * batch / dt
+    stages = "collect+embed" if fm is not None else "collect"
+    line = {
+        "impl": "reference", "metric": "concept-db images/sec (collect+embed)", "value": v, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(stages, batch),
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"each step = {batch} images on the host cores (torch-CPU port of the reference "
+                                   f"path, oracle/ref_port.py), {stages}"},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def foundation_model_available() -> bool:
+    try:
+        import semanticlens_b200.foundation_models  # noqa: F401
+
+        return True
+    except ImportError:
+        return False
+
+
+def workload_config(stages: str, batch: int) -> dict:
+    return {
+        "workload": "cfg2: ResNet-50 probed at conv1,layer1..layer4 (aggregate_conv_mean, k=20) + OpenCLIP ViT-B/32 "
+                    "image-tower embed, synthetic 224x224 images",
+        "stages": stages, "batch_per_gpu": batch, "layers": LAYERS, "n_collect": K_COLLECT,
+        "l2_policy": "inputs larger than L2: a ring of 4 distinct device batches (154 MB fp32 each) in value mode, "
+                     "fresh host batches in e2e mode",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+
+    from semanticlens_b200 import _native, ops
+    from semanticlens_b200 import distributed as sdist
+    from semanticlens_b200.component_visualization import ActivationComponentVisualizer
+    from semanticlens_b200.component_visualization import aggregators as A
+    from semanticlens_b200.component_visualization.activation_caching import ActMaxCache
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback; use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False  # the probed model runs in plain fp32, like the reference
+    torch.backends.cuda.matmul.allow_tf32 = False
+    lib = _native.load(require_device=True)
+    B, K, W = args.batch, args.steps, args.warmup
+    pk, pk_src = peaks()
+
+    model = probed_model().to(dev)
+    fm = foundation_model(dev)
+    stages = "collect+embed" if fm is not None else "collect"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs --------------------------------------------------------------
+    ring_u8 = [synth_u8(B, 100 + rank * 16 + i, dev) for i in range(4)]
+    ring_f32 = [normalise(u) for u in ring_u8]
+    cache = ActMaxCache(LAYERS, A.aggregate_conv_mean, K_COLLECT)
+    for name in LAYERS:
+        cache.sample_idx_counter[name] = rank * (K + W) * B
+    embeds = []
+
+    def step(i):
+        model(ring_f32[i % 4])
+        if fm is not None:
+            embeds.append(fm.encode_image(fm.preprocess(ring_u8[i % 4])))
+
+    def closing():
+        if world > 1:
+            sdist.merge_actmax_across_ranks(cache, dev)
+
+    clocks = Clocks(local)
+    timer = ops.KernelTimer()
+    with torch.no_grad(), cache.hook_context(model):
+        for i in range(W):
+            step(i)
+        embeds.clear()
+        barrier()
+        ops.set_timer(timer)
+        n0 = lib.slb_launch_count()
+        clocks.begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(W, W + K):
+            step(i)
+        closing()
+        e1.record()
+        barrier()
+        clocks.end()
+        launches = lib.slb_launch_count() - n0
+        ops.set_timer(None)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    value = world * K * B / (ms / 1e3)
+    kt = timer.totals()
+    clk = clocks.stop()
+
+    # ---- e2e: public API, host-resident dataset -----------------------------------------------------
+    def e2e_run(n_steps, seed):
+        n_total = world * n_steps * B
+        lo, hi = rank * n_steps * B, (rank + 1) * n_steps * B
+        ds_model = HostImages(n_total, lo, hi, seed, dev, "model")
+        ds_fm = HostImages(n_total, lo, hi, seed, dev, "fm", store=ds_model.u8)
+        cv = ActivationComponentVisualizer(model, ds_model, ds_fm, LAYERS, K_COLLECT, device=dev,
+                                           aggregate_fn=A.aggregate_conv_mean)
+        cv.show_progress = False
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        if fm is not None:
+            from semanticlens_b200.lens import Lens
+
+            db = Lens(fm, device=dev).compute_concept_db(cv, batch_size=B)
+            d2h = sum(v.numel() * v.element_size() for v in db.values())
+        else:
+            res = cv.run(batch_size=B)
+            d2h = sum(am.activations.numel() * 2 + am.sample_ids.numel() * 8 for am in res.values())
+        b.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([max(a.elapsed_time(b), 0.0), wall], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d = B * 3 * 224 * 224 * 4 + (B * 3 * 224 * 224 if fm is not None else 0)
+        return float(t[0].item()), h2d, d2h / n_steps
+
+    e2e_run(max(W, 1), 11)  # warm-up of the public path
+    e2e_ms, h2d, d2h = e2e_run(K, 12)
+    e2e_value = world * K * B / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant libslb200 kernel --------------------------------------------------
+    roof = None
+    if kt:
+        dom = max(kt, key=lambda k_: kt[k_]["ms"])
+        d = kt[dom]
+        if d["flops"] > 0 and d["flops"] / max(d["bytes"], 1) > 200:
+            ach = d["flops"] / (d["ms"] / 1e3) / 1e12
+            peak = pk["bf16_tflops_sustained"]
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": None}
+        else:
+            ach = d["bytes"] / (d["ms"] / 1e3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                    "traffic": None}
+        roof.update({"kernel": dom, "peak_source": f"{pk_src} (MEASURED_PEAKS.json)", "launches": d["launches"],
+                     "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / ms,
+                     "per_kernel_ms_per_step": {k_: v["ms"] / K for k_, v in kt.items()}})
+
+    if rank == 0:
+        line = {
+            "metric": "concept-db images/sec (collect+embed)", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(stages, B),
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "api": "Lens.compute_concept_db(cv, batch_size=256)"
+                    if fm is not None else "ActivationComponentVisualizer.run(batch_size=256)"},
+            "roofline": roof,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = run_cpu_sample(args.cpu_images, 32, fm is not None)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--cpu-images", type=int, default=256, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,31 @@ from .base import AbstractComponentVisualizer
 logger = logging.getLogger(__name__)
 
 
+class _SlicedBatches:
+    """Batches of a dataset that can hand out a whole index range at once (``dataset.get_batch(lo, hi)``), e.g. one
+    backed by a single pinned host tensor: no per-item ``__getitem__`` + collate copy on the host."""
+
+    def __init__(self, dataset, lo, hi, batch_size):
+        self.dataset, self.lo, self.hi, self.batch_size = dataset, lo, hi, batch_size
+
+    def __len__(self):
+        return -(-(self.hi - self.lo) // self.batch_size) if self.hi > self.lo else 0
+
+    def __iter__(self):
+        for a in range(self.lo, self.hi, self.batch_size):
+            yield self.dataset.get_batch(a, min(a + self.batch_size, self.hi))
+
+
+def _batches(dataset, shard, batch_size, num_workers, device, collate_fn=None):
+    """Iteration order of the reference (DataLoader, shuffle=False, :344-349 / :414-422) over this rank's shard."""
+    if hasattr(dataset, "get_batch"):
+        return _SlicedBatches(dataset, shard.lo, shard.hi, batch_size)
+    if shard.world > 1:
+        dataset = torch.utils.data.Subset(dataset, range(shard.lo, shard.hi))
+    kw = dict(collate_fn=collate_fn) if collate_fn is not None else dict(pin_memory=device.type == "cuda")
+    return torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=False, num_workers=num_workers, **kw)
+
+
 class MissingNameWarning(UserWarning):
     """A model or dataset has no ``.name``; a fallback derived from its ``repr`` names the cache directory."""
 
@@ -167,15 +192,8 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
     def _run(self, batch_size: int = 64, num_workers: int = 0):
         """The activation sweep (reference :341-358), image-sharded across ranks when distributed."""
         shard = sdist.image_shard(len(self.dataset))
-        dataset = self.dataset if shard.world == 1 else torch.utils.data.Subset(self.dataset, range(shard.lo, shard.hi))
         device = self.device
-        dataloader = torch.utils.data.DataLoader(
-            dataset,
-            batch_size=batch_size,
-            shuffle=False,
-            num_workers=num_workers,
-            pin_memory=device.type == "cuda",
-        )
+        dataloader = _batches(self.dataset, shard, batch_size, num_workers, device)
         if shard.world > 1:
             # ids are positions in iteration order; a shard starts at its offset, on a fresh state
             if shard.hi <= shard.lo:
@@ -227,14 +245,10 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
             return list(batch)
 
         shard = sdist.image_shard(len(self.dataset_fm))
-        dataset = (
-            self.dataset_fm if shard.world == 1 else torch.utils.data.Subset(self.dataset_fm, range(shard.lo, shard.hi))
-        )
-        loader = torch.utils.data.DataLoader(
-            dataset, batch_size=batch_size, shuffle=False, collate_fn=item_list_collate, **kwargs
-        )
+        loader = _batches(self.dataset_fm, shard, batch_size, kwargs.get("num_workers", 0), self.device,
+                          collate_fn=item_list_collate)
         embeds = []
-        with tqdm(total=len(dataset), desc="Embedding Dataset", disable=not self.show_progress) as pbar:
+        with tqdm(total=shard.hi - shard.lo, desc="Embedding Dataset", disable=not self.show_progress) as pbar:
             for items in loader:
                 inputs = fm.preprocess(items)
                 embeds.append(fm.encode_image(inputs))

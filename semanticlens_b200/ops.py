@@ -15,6 +15,46 @@ def _dev_guard(t: torch.Tensor):
     return torch.cuda.device(t.device)
 
 
+class KernelTimer:
+    """Optional per-kernel CUDA-event timing on the launching stream (used by bench.py for the roofline line).
+
+    While installed with :func:`set_timer`, every wrapper brackets its kernel with two events on the current
+    stream and records (label, algorithmic bytes, algorithmic flops). Nothing synchronises until :meth:`totals`.
+    """
+
+    def __init__(self):
+        self.records: list[tuple[str, torch.cuda.Event, torch.cuda.Event, int, int]] = []
+
+    def begin(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def end(self, label: str, start, nbytes: int = 0, flops: int = 0):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.records.append((label, start, ev, nbytes, flops))
+
+    def totals(self) -> dict[str, dict[str, float]]:
+        torch.cuda.synchronize()
+        out: dict[str, dict[str, float]] = {}
+        for label, a, b, nbytes, flops in self.records:
+            d = out.setdefault(label, {"ms": 0.0, "launches": 0, "bytes": 0, "flops": 0})
+            d["ms"] += a.elapsed_time(b)
+            d["launches"] += 1
+            d["bytes"] += nbytes
+            d["flops"] += flops
+        return out
+
+
+_timer: KernelTimer | None = None
+
+
+def set_timer(t: KernelTimer | None) -> None:
+    global _timer
+    _timer = t
+
+
 # ------------------------------------------------------------------------------------------------
 # collect
 # ------------------------------------------------------------------------------------------------
@@ -51,10 +91,13 @@ def agg_reduce(t: torch.Tensor, op: int, reduce_kind: str, token_pos: int = 0) -
     if B == 0 or C == 0:
         return out
     with _dev_guard(t):
+        t0 = _timer.begin() if _timer else None
         rc = lib.slb_agg_reduce(
             keep.data_ptr(), N.dtype_code(keep.dtype), layout, B, C, inner, op, token_pos, out.data_ptr(),
             N.stream_ptr(t.device),
         )
+        if _timer:
+            _timer.end("K1 agg_reduce", t0, keep.numel() * keep.element_size())
     N.check(rc, "slb_agg_reduce")
     return out
 
@@ -115,9 +158,12 @@ def agg_topk_update(
     need = B * C
     if scratch is None or scratch.numel() < need or scratch.device != t.device:
         scratch = torch.empty(max(need, 1), dtype=torch.float32, device=t.device)
-    if B + k > 8192:
+    if B + k > 8192 or _timer is not None:
         cand = agg_reduce(t, op, reduce_kind, token_pos)
+        t0 = _timer.begin() if _timer else None
         topk_update(cand, state_vals, state_ids, None, id_base)
+        if _timer:
+            _timer.end("K2 topk_update", t0, cand.numel() * 4)
         return scratch
     with _dev_guard(t):
         rc = lib.slb_agg_topk_update(
