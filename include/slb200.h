@@ -101,6 +101,105 @@ int slb_topk_merge_lists(const uint16_t* vals, const int64_t* ids, int64_t R, in
 int slb_gather_rows(const float* table, int64_t N, int64_t D, const int64_t* idx, int64_t n_idx, float* out,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * embed: the CLIP / SigLIP ViT image tower  (foundation_models/clip.py:103-163 -> open_clip, not vendored)
+ * ---------------------------------------------------------------------------------------- */
+
+/* 16-bit "split plane" formats: x ~= hi + lo, hi = rn16(x), lo = rn16(x - hi).
+ * F16: 22 significant bits, |x| <= 65504 (saturating). BF16: 16 significant bits, fp32 range. */
+#define SLB_PLANE_F16 0
+#define SLB_PLANE_BF16 1
+
+/* x fp32 [n] -> planes [2][n] (hi plane, then lo plane). n % 4 == 0. */
+int slb_split_planes(const float* x, int64_t n, int plane_fmt, uint16_t* planes, void* stream);
+
+/* epilogue selectors for slb_gemm_split */
+#define SLB_EPI_NONE 0
+#define SLB_EPI_GELU_ERF 1  /* nn.GELU()            (open_clip ViT-B-32 / ViT-L-14) */
+#define SLB_EPI_QUICKGELU 2 /* x * sigmoid(1.702 x)  (open_clip *-quickgelu, OpenAI weights) */
+#define SLB_EPI_GELU_TANH 3 /* nn.GELU("tanh")       (SigLIP / timm towers) */
+
+/* K4/K6. D[M,N] = act((A[M,K] * W[N,K]^T) * row_scale[m] * col_scale[n] + bias[n]) + residual[M,N]
+ * on the 5th-gen tensor cores (tcgen05.mma kind::f16, TMA-fed 128B-swizzled stages, fp32 accumulators in TMEM) with
+ * fp32-grade accuracy: operands are split planes a_planes [2,M,K], w_planes [2,N,K] (row-major, K contiguous) and each
+ * tile accumulates Ahi*Whi + Ahi*Wlo + Alo*Whi (passes = 3) or Ahi*Whi only (passes = 1).
+ * Replaces the fp32 GEMMs of open_clip's image tower (clip.py:118) and the cosine matmul of
+ * scores.similarity_score (scores.py:120-125; row_scale/col_scale = inverse row norms).
+ * Outputs: out_f32 [M,N] (nullable) and/or out_planes [2,M,N] (nullable) in the same plane format, ready to be the
+ * A operand of the next GEMM. bias/residual/row_scale/col_scale nullable; residual may alias out_f32.
+ * Requirements: K % 64 == 0, N % 8 == 0, all buffers 16-byte aligned. */
+int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, int plane_fmt, int64_t M, int64_t N, int64_t K,
+                   const float* bias, const float* residual, const float* row_scale, const float* col_scale,
+                   int epilogue, int passes, float* out_f32, uint16_t* out_planes, void* stream);
+
+/* K3. out[b,c,y,x] = (u8[b,c,y,x]/255 - mean[c]) / std[c]  — `ToTensor` + `Normalize` of the open_clip eval transform
+ * (clip.py:157-160) for already-sized planar u8 images, in torch's op order (two IEEE divisions).
+ * mean3/std3 are HOST arrays of Cc floats. n_pix = H*W, a multiple of 16. */
+int slb_u8_to_f32_norm(const uint8_t* img, int64_t B, int64_t Cc, int64_t n_pix, const float* mean3,
+                       const float* std3, float* out, void* stream);
+
+/* (B,3,S,S) fp32 -> im2col rows as split planes [2][B*(S/P)^2][slb_patch_k(P)] (row = (b, gy, gx), col = (c, py, px),
+ * zero padded from 3*P*P up to a multiple of 64), so that the patch-embedding conv (kernel = stride = P, even P) is
+ * one slb_gemm_split against the flattened, equally padded conv weight. */
+int64_t slb_patch_k(int64_t P);
+int slb_patchify(const float* img, int64_t B, int64_t S, int64_t P, int plane_fmt, uint16_t* out_planes, void* stream);
+
+/* x[b,t,:] = (has_cls && t == 0 ? cls : patch[b, t - has_cls, :]) + pos[t,:]   (fp32; pos nullable). */
+int slb_assemble_tokens(const float* patch, const float* cls, const float* pos, int64_t B, int64_t T, int64_t W,
+                        int has_cls, float* out, void* stream);
+
+/* Row LayerNorm over `cols` (fp32, two-pass, biased variance, eps inside the sqrt like torch); input rows are
+ * `row_stride` floats apart (e.g. T*W to normalise only the class tokens). Writes fp32 [rows,cols] (nullable) and/or
+ * split planes [2,rows,cols] (nullable). beta nullable. */
+int slb_layernorm(const float* x, int64_t rows, int64_t cols, int64_t row_stride, const float* gamma, const float* beta,
+                  float eps, int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream);
+
+/* softmax(scale * Q K^T) V per (batch, head) for short sequences (Tk <= 320, head_dim % 4 == 0, <= 128), fp32.
+ * q: row (b, i) at q + b*q_batch_stride + i*q_row_stride, head h at + h*dh; k, v likewise with the kv strides
+ * (packed nn.MultiheadAttention in_proj output: k = q + W, v = q + 2W, row stride 3W).
+ * out [B,Tq,H*dh] as fp32 (nullable) and/or split planes [2, B*Tq, H*dh] (nullable). */
+int slb_attention_small(const float* q, int64_t q_batch_stride, int64_t q_row_stride, const float* k, const float* v,
+                        int64_t kv_batch_stride, int64_t kv_row_stride, int64_t B, int64_t Tq, int64_t Tk, int64_t H,
+                        int64_t dh, float scale, int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream);
+
+/* The whole CLIP ViT image tower in one call (open_clip VisionTransformer.forward behind clip.py:103-118).
+ * Weight matrices are split planes prepared once by the caller (slb_split_planes); vectors are fp32. All pointers are
+ * device pointers except `layer`, a HOST array of `layers` structs. */
+#define SLB_POOL_CLS 0 /* features = ln_post(x)[:, 0] @ proj */
+
+typedef struct {
+    const float* ln1_g; const float* ln1_b;
+    const uint16_t* w_qkv; const float* b_qkv;   /* attn.in_proj: planes [2, 3W, W], [3W] */
+    const uint16_t* w_out; const float* b_out;   /* attn.out_proj: planes [2, W, W], [W] */
+    const float* ln2_g; const float* ln2_b;
+    const uint16_t* w_fc; const float* b_fc;     /* mlp.c_fc: planes [2, mlp, W], [mlp] */
+    const uint16_t* w_proj; const float* b_proj; /* mlp.c_proj: planes [2, W, mlp], [W] */
+} SlbVitLayer;
+
+typedef struct {
+    int32_t image_size, patch, width, layers, heads, mlp, embed_dim;
+    int32_t act;       /* SLB_EPI_* of the MLP */
+    int32_t plane_fmt; /* SLB_PLANE_* of every plane below */
+    int32_t has_cls, pool;
+    float ln_eps;
+    const uint16_t* conv_w; /* planes [2, W, slb_patch_k(patch)] (conv1.weight flattened (c,py,px), zero padded) */
+    const float* conv_b;    /* [W] or NULL (CLIP has no conv bias) */
+    const float* cls;       /* [W] */
+    const float* pos;       /* [T, W] */
+    const float* ln_pre_g; const float* ln_pre_b;   /* NULL: no ln_pre */
+    const float* ln_post_g; const float* ln_post_b;
+    const uint16_t* proj;   /* planes [2, embed_dim, W] (= visual.proj transposed) or NULL */
+    const SlbVitLayer* layer;
+} SlbVitWeights;
+
+/* Bytes of device workspace slb_vit_forward needs for a batch of B images (0 on bad arguments). */
+size_t slb_vit_workspace_bytes(const SlbVitWeights* w, int64_t B);
+
+/* img (B,3,S,S) fp32 preprocessed -> out (B, embed_dim) fp32, un-normalised like open_clip's encode_image.
+ * workspace: 256-byte aligned device memory of at least slb_vit_workspace_bytes(w, B). */
+int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t B, float* out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@ DT_F32, DT_F16, DT_BF16 = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_BTF = 0, 1
 AGG_MEAN, AGG_MAX, AGG_ABSMEAN, AGG_ABSMAX, AGG_TOKEN = 0, 1, 2, 3, 4
 EPI_NONE, EPI_GELU_ERF, EPI_QUICKGELU, EPI_GELU_TANH = 0, 1, 2, 3
+PLANE_F16, PLANE_BF16 = 0, 1
 
 _DTYPES = {torch.float32: DT_F32, torch.float16: DT_F16, torch.bfloat16: DT_BF16}
 
@@ -45,7 +46,44 @@ _PROTOS = {
     ),
     "slb_topk_merge_lists": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "slb_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "slb_split_planes": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "slb_gemm_split": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+         c_void_p, c_void_p, c_void_p],
+    ),
+    "slb_u8_to_f32_norm": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "slb_patchify": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "slb_assemble_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "slb_layernorm": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p],
+    ),
+    "slb_attention_small": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+         c_float, c_int, c_void_p, c_void_p, c_void_p],
+    ),
+    "slb_patch_k": (c_int64, [c_int64]),
+    "slb_vit_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
+    "slb_vit_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
+
+
+class SlbVitLayer(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_out", "b_out", "ln2_g", "ln2_b", "w_fc", "b_fc", "w_proj", "b_proj")]
+
+
+class SlbVitWeights(ctypes.Structure):
+    _fields_ = (
+        [(n, ctypes.c_int32) for n in ("image_size", "patch", "width", "layers", "heads", "mlp", "embed_dim", "act",
+                                       "plane_fmt", "has_cls", "pool")]
+        + [("ln_eps", c_float)]
+        + [(n, c_void_p) for n in ("conv_w", "conv_b", "cls", "pos", "ln_pre_g", "ln_pre_b", "ln_post_g", "ln_post_b",
+                                   "proj")]
+        + [("layer", ctypes.POINTER(SlbVitLayer))]
+    )
 
 
 def lib_path() -> Path:

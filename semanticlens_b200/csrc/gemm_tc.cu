@@ -1,0 +1,379 @@
+// K4/K6 — D[M,N] = epilogue(A[M,K] · W[N,K]^T) on the 5th-generation tensor cores with fp32-grade accuracy.
+//
+// Replaces the fp32 GEMMs the reference reaches through open_clip's image tower (foundation_models/clip.py:118 ->
+// nn.MultiheadAttention in_proj/out_proj, MLP c_fc/c_proj, conv1 patch embed, visual proj) and the cosine matmul of
+// scores.similarity_score (scores.py:120-125).
+//
+// Operands are "split planes": x ~= hi + lo/S, both 16-bit (fp16: 22 significant bits, bf16: 16), lo stored
+// pre-scaled by S so it stays clear of the fp16 subnormals. One output tile keeps TWO fp32 accumulators in tensor
+// memory: main = Ahi·Whi and corr = Ahi·Wlo + Alo·Whi; the epilogue forms main + corr/S (the lo·lo term is below
+// fp32 resolution for fp16 planes). The tensor cores thus deliver fp32-grade results at 1/3 of their 16-bit rate.
+//
+// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0      TMA producer: per k-block ONE 3-D box per operand {64 cols, rows, 2 planes} -> 128B-swizzled smem stage
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16, 12 per k-block; tcgen05.commit frees stages
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> scale/bias/activation/residual -> global
+// Accumulators are double buffered in TMEM (2 x 2 x BN = 512 columns): the epilogue of tile i overlaps the MMAs of
+// tile i+1.
+#include "tc_common.cuh"
+
+#include <algorithm>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 x 2 B = one 128-byte swizzle row
+constexpr int kThreads = 192;
+
+template <int BN>
+struct Cfg {
+    static_assert(BN == 128, "two double-buffered accumulator pairs fill the 512 TMEM columns at BN = 128");
+    static constexpr int kStages = 3;
+    static constexpr int kABytes = 2 * BM * BK * 2;  // both planes
+    static constexpr int kWBytes = 2 * BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kWBytes;
+    static constexpr int kTmemCols = 4 * BN;  // [buffer][main | corr][BN]
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+    int64_t M, N, K;
+    const float* bias;       // [N] or null
+    const float* residual;   // [M,N] or null (may alias out_f32)
+    const float* row_scale;  // [M] or null
+    const float* col_scale;  // [N] or null
+    float* out_f32;          // [M,N] or null
+    uint16_t* out_planes;    // [2,M,N] or null
+    int epilogue;
+    int passes;  // 3 or 1
+    int fmt;     // plane format of A/W and of out_planes
+};
+
+__device__ __forceinline__ float act_apply(float v, int epi) {
+    switch (epi) {
+        case SLB_EPI_GELU_ERF:
+            return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+        case SLB_EPI_QUICKGELU:
+            return v / (1.0f + __expf(-1.702f * v));
+        case SLB_EPI_GELU_TANH: {
+            float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+            return 0.5f * v * (1.0f + tanhf(u));
+        }
+        default:
+            return v;
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmParams p) {
+    using C = Cfg<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::kStages * C::kStageBytes);
+    uint64_t* full = bars;                    // [kStages]  TMA -> MMA
+    uint64_t* empty = bars + C::kStages;      // [kStages]  MMA -> TMA
+    uint64_t* tfull = bars + 2 * C::kStages;  // [2]        MMA -> epilogue
+    uint64_t* tempty = tfull + 2;             // [2]        epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        slb_prefetch_tmap(&tmA);
+        slb_prefetch_tmap(&tmW);
+        for (int s = 0; s < C::kStages; ++s) {
+            slb_mbar_init(&full[s], 1);
+            slb_mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            slb_mbar_init(&tfull[a], 1);
+            slb_mbar_init(&tempty[a], 4);
+        }
+        slb_fence_mbar_init();
+    }
+    if (warp == 1) slb_tmem_alloc<C::kTmemCols>(tmem_slot);
+    slb_tc_fence_before();
+    __syncthreads();
+    slb_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_kb = (int)(p.K / BK);
+    const int tiles_n = (int)((p.N + BN - 1) / BN);
+    const int tiles_m = (int)((p.M + BM - 1) / BM);
+    const int total = tiles_m * tiles_n;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    slb_mbar_wait(&empty[stage], phase ^ 1u);
+                    unsigned char* st = smem + (size_t)stage * C::kStageBytes;
+                    slb_mbar_arrive_expect_tx(&full[stage], (uint32_t)C::kStageBytes);
+                    slb_tma_load_3d(st, &tmA, kb * BK, m0, 0, &full[stage]);
+                    slb_tma_load_3d(st + C::kABytes, &tmW, kb * BK, n0, 0, &full[stage]);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = slb_umma_idesc_f16(p.fmt, BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                slb_mbar_wait(&tempty[acc], acc_phase ^ 1u);
+                slb_tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    slb_mbar_wait(&full[stage], phase);
+                    slb_tc_fence_after();
+                    const uint32_t a0 = slb_smem_u32(smem + (size_t)stage * C::kStageBytes);
+                    const uint32_t w0 = a0 + C::kABytes;
+                    // (A plane, W plane): hi·hi, hi·lo, lo·hi
+#pragma unroll
+                    for (int pr = 0; pr < 3; ++pr) {
+                        if (pr < p.passes) {
+                            const uint32_t ab = a0 + (pr == 2 ? BM * BK * 2 : 0);
+                            const uint32_t wb = w0 + (pr == 1 ? BN * BK * 2 : 0);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                // pr 0 -> main accumulator; pr 1, 2 -> corr accumulator (first write: kb 0, pr 1, k 0)
+                                slb_umma_f16(d_tmem + (pr ? BN : 0), slb_umma_desc_sw128(ab + k * 32),
+                                             slb_umma_desc_sw128(wb + k * 32), idesc,
+                                             pr == 0 ? (kb | k) != 0 : (kb | (pr - 1) | k) != 0);
+                            }
+                        }
+                    }
+                    slb_umma_commit(&empty[stage]);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                }
+                slb_umma_commit(&tfull[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+        __syncwarp();
+    } else {
+        const int quarter = warp & 3;  // TMEM lane group this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int fmt = p.fmt;
+        const float inv_s = 1.0f / slb_plane_lo_scale(fmt);
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+            slb_mbar_wait(&tfull[acc], acc_phase);
+            slb_tc_fence_after();
+            const int64_t m = (int64_t)m0 + quarter * 32 + lane;
+            const bool row_ok = m < p.M;
+            const float rs = (p.row_scale && row_ok) ? p.row_scale[m] : 1.0f;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t raw[32];
+                float v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
+                slb_tmem_ld_32x32(taddr, raw);
+                slb_tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                if (p.passes == 3) {
+                    slb_tmem_ld_32x32(taddr + BN, raw);
+                    slb_tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(raw[j]), inv_s, v[j]);
+                }
+                const int64_t nb = (int64_t)n0 + c * 32;
+                if (row_ok && nb < p.N) {
+                    const int ncols = (int)min((int64_t)32, p.N - nb);  // multiple of 8
+                    if (p.row_scale) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= rs;
+                    }
+                    if (p.col_scale) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) v[j] *= __ldg(p.col_scale + nb + j);
+                    }
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) v[j] += __ldg(p.bias + nb + j);
+                    }
+                    if (p.epilogue != SLB_EPI_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], p.epilogue);
+                    }
+                    if (p.residual) {
+                        const float4* r4 = reinterpret_cast<const float4*>(p.residual + m * p.N + nb);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (4 * j < ncols) {
+                                float4 r = r4[j];
+                                v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+                            }
+                        }
+                    }
+                    if (p.out_f32) {
+                        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + m * p.N + nb);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (4 * j < ncols) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                    if (p.out_planes) {
+                        uint16_t* ph = p.out_planes + m * p.N + nb;
+                        uint16_t* pl = ph + p.M * p.N;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (8 * j < ncols) {
+                                uint32_t h[4], l[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    uint16_t h0, l0, h1, l1;
+                                    slb_split2(v[8 * j + 2 * q], fmt, h0, l0);
+                                    slb_split2(v[8 * j + 2 * q + 1], fmt, h1, l1);
+                                    h[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                                    l[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                                }
+                                *reinterpret_cast<uint4*>(ph + 8 * j) = make_uint4(h[0], h[1], h[2], h[3]);
+                                *reinterpret_cast<uint4*>(pl + 8 * j) = make_uint4(l[0], l[1], l[2], l[3]);
+                            }
+                        }
+                    }
+                }
+            }
+            slb_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) slb_mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    slb_tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        slb_tc_fence_after();
+        slb_tmem_dealloc<C::kTmemCols>(tmem_base);
+    }
+}
+
+// x fp32 -> planes [2][n]
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, int64_t n4, int64_t n, int fmt,
+                                                           uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        uint16_t h[4], l[4];
+        slb_split2(v.x, fmt, h[0], l[0]);
+        slb_split2(v.y, fmt, h[1], l[1]);
+        slb_split2(v.z, fmt, h[2], l[2]);
+        slb_split2(v.w, fmt, h[3], l[3]);
+        reinterpret_cast<uint2*>(hi)[i] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+        reinterpret_cast<uint2*>(lo)[i] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t i = n4 * 4; i < n; ++i) slb_split2(x[i], fmt, hi[i], lo[i]);
+    }
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, cudaStream_t st) {
+    using C = Cfg<BN>;
+    auto kern = gemm_split_kernel<BN>;
+    SLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    const int64_t tiles = slb_ceil_div(p.M, BM) * slb_ceil_div(p.N, BN);
+    const int grid = (int)std::min<int64_t>(tiles, slb_sm_count());
+    kern<<<grid, kThreads, C::kSmem, st>>>(tmA, tmW, p);
+    SLB_LAUNCH_OK("gemm_split");
+    return SLB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------------------------
+slb_tmap_encode_fn slb_get_tmap_encoder() {
+    static slb_tmap_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<slb_tmap_encode_fn>(sym);
+    }
+    if (!fn) slb_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return fn;
+}
+
+int slb_make_plane_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int planes, int box_rows) {
+    slb_tmap_encode_fn enc = slb_get_tmap_encoder();
+    if (!enc) return SLB_ECUDA;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * (cuuint64_t)cols * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)planes};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        slb_set_error("cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld box_rows=%d)", (int)r, (long long)rows,
+                      (long long)cols, box_rows);
+        return SLB_ECUDA;
+    }
+    return SLB_OK;
+}
+
+extern "C" int slb_split_planes(const float* x, int64_t n, int plane_fmt, uint16_t* planes, void* stream) {
+    SLB_REQUIRE(n >= 0, SLB_EINVAL, "slb_split_planes: negative size");
+    if (n == 0) return SLB_OK;
+    SLB_REQUIRE(x && planes, SLB_EINVAL, "slb_split_planes: null pointer");
+    SLB_REQUIRE(plane_fmt == SLB_PLANE_F16 || plane_fmt == SLB_PLANE_BF16, SLB_EINVAL, "slb_split_planes: bad format");
+    SLB_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)planes % 8) == 0 && (n % 4) == 0, SLB_EINVAL,
+                "slb_split_planes: x must be 16-byte aligned, planes 8-byte aligned, n a multiple of 4");
+    const int64_t n4 = n / 4;
+    const int grid = (int)std::min<int64_t>(slb_ceil_div(n4, 256), (int64_t)slb_sm_count() * 8);
+    split_planes_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n4, n, plane_fmt, planes, planes + n);
+    SLB_LAUNCH_OK("split_planes");
+    return SLB_OK;
+}
+
+extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, int plane_fmt, int64_t M, int64_t N,
+                              int64_t K, const float* bias, const float* residual, const float* row_scale,
+                              const float* col_scale, int epilogue, int passes, float* out_f32, uint16_t* out_planes,
+                              void* stream) {
+    SLB_REQUIRE(M >= 0 && N >= 0 && K >= 0, SLB_EINVAL, "slb_gemm_split: negative size");
+    if (M == 0 || N == 0) return SLB_OK;
+    SLB_REQUIRE(a_planes && w_planes, SLB_EINVAL, "slb_gemm_split: null operand");
+    SLB_REQUIRE(out_f32 || out_planes, SLB_EINVAL, "slb_gemm_split: no output requested");
+    SLB_REQUIRE(plane_fmt == SLB_PLANE_F16 || plane_fmt == SLB_PLANE_BF16, SLB_EINVAL, "slb_gemm_split: bad plane format");
+    SLB_REQUIRE(passes == 1 || passes == 3, SLB_EINVAL, "slb_gemm_split: passes must be 1 or 3");
+    SLB_REQUIRE(epilogue >= SLB_EPI_NONE && epilogue <= SLB_EPI_GELU_TANH, SLB_EINVAL, "slb_gemm_split: bad epilogue");
+    SLB_REQUIRE(K >= BK && K % BK == 0, SLB_EUNSUPPORTED, "slb_gemm_split: K must be a positive multiple of 64 (got %lld)",
+                (long long)K);
+    SLB_REQUIRE(N % 8 == 0, SLB_EUNSUPPORTED, "slb_gemm_split: N must be a multiple of 8 (got %lld)", (long long)N);
+    SLB_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), SLB_EUNSUPPORTED, "slb_gemm_split: size too large");
+    SLB_REQUIRE(((uintptr_t)a_planes % 16) == 0 && ((uintptr_t)w_planes % 16) == 0 &&
+                    ((uintptr_t)out_f32 % 16) == 0 && ((uintptr_t)out_planes % 16) == 0 &&
+                    ((uintptr_t)residual % 16) == 0 && ((M * K * 2) % 16) == 0 && ((N * K * 2) % 16) == 0 &&
+                    ((M * N * 2) % 16) == 0,
+                SLB_EINVAL, "slb_gemm_split: operands must be 16-byte aligned");
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K;
+    p.bias = bias; p.residual = residual; p.row_scale = row_scale; p.col_scale = col_scale;
+    p.out_f32 = out_f32; p.out_planes = out_planes;
+    p.epilogue = epilogue; p.passes = passes; p.fmt = plane_fmt;
+    CUtensorMap tmA, tmW;
+    int rc = slb_make_plane_map(&tmA, a_planes, M, K, 2, BM);
+    if (rc != SLB_OK) return rc;
+    rc = slb_make_plane_map(&tmW, w_planes, N, K, 2, 128);
+    if (rc != SLB_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return launch_gemm<128>(tmA, tmW, p, st);
+}

@@ -1,0 +1,132 @@
+// tcgen05 / TMEM / TMA (tensor-map) PTX wrappers for sm_100a. Hand-written: no CUTLASS/CuTe in product code.
+#pragma once
+#include "slb_common.cuh"
+
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor-map encoder without linking libcuda
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*slb_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+slb_tmap_encode_fn slb_get_tmap_encoder();  // nullptr (+ error string) if the driver does not provide it
+
+// 3-D map over 16-bit planes [planes][rows][cols] (cols contiguous); box = {64 cols, box_rows, planes}; 128B swizzle.
+int slb_make_plane_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int planes, int box_rows);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// device: TMA
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void slb_prefetch_tmap(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+
+__device__ __forceinline__ void slb_tma_load_3d(void* smem_dst, const CUtensorMap* m, int c0, int c1, int c2,
+                                                uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(slb_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(slb_smem_u32(bar))
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// device: tcgen05 (cta_group::1)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void slb_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void slb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void slb_tmem_alloc(uint32_t* smem_slot) {  // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slb_smem_u32(smem_slot)),
+                 "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void slb_tmem_dealloc(uint32_t taddr) {  // whole warp (the allocating one)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// K-major operand tile in shared memory, 128-byte swizzle, rows of 64 16-bit elements (128 B), 8-row atoms of 1024 B.
+// Bit layout (PTX "shared memory matrix descriptor", sm_100): [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4,
+// [46,48) version = 1, [49,52) base offset = 0, [61,64) swizzle mode (2 = 128B).
+__device__ __forceinline__ uint64_t slb_umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;              // LBO: unused for K-major swizzled tiles whose K extent is one atom
+    d |= (uint64_t)(1024 >> 4) << 32;    // SBO: 8 rows * 128 B between row groups
+    d |= (uint64_t)1 << 46;              // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+    return d;
+}
+
+// kind::f16 instruction descriptor: D fp32, A/B both `fmt` (0 = fp16, 1 = bf16), both K-major, shape M x N x 16.
+__device__ __forceinline__ uint32_t slb_umma_idesc_f16(int fmt, int M, int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;                        // c_format = F32
+    d |= (uint32_t)fmt << 7;             // a_format
+    d |= (uint32_t)fmt << 10;            // b_format
+    d |= (uint32_t)(N >> 3) << 17;       // n_dim
+    d |= (uint32_t)(M >> 4) << 24;       // m_dim
+    return d;
+}
+
+__device__ __forceinline__ void slb_umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             bool accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
+// arrive on `bar` once every tcgen05 op issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void slb_umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(slb_smem_u32(bar))
+                 : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i), columns [col, col+32)
+__device__ __forceinline__ void slb_tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+__device__ __forceinline__ void slb_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// 16-bit plane formats: 0 = IEEE fp16, 1 = bf16  (same codes as the instruction descriptor)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint16_t slb_to_plane(float v, int fmt) {
+    if (fmt == 0) return __half_as_ushort(__float2half_rn(v));
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float slb_from_plane(uint16_t b, int fmt) {
+    if (fmt == 0) return __half2float(__ushort_as_half(b));
+    return __bfloat162float(__ushort_as_bfloat16(b));
+}
+// x ~= hi + lo / S with hi = rn16(x), lo = rn16((x - hi) * S), S = 2^11 (fp16) or 2^8 (bf16): the remainder is
+// stored pre-scaled so that it never falls into the fp16 subnormal range (weights ~1e-2 would otherwise lose
+// the low bits of lo). 22 (fp16) / 16 (bf16) significant bits in total. fp16 planes saturate at +-65504.
+__host__ __device__ __forceinline__ float slb_plane_lo_scale(int fmt) { return fmt == 0 ? 2048.0f : 256.0f; }
+__device__ __forceinline__ void slb_split2(float v, int fmt, uint16_t& hi, uint16_t& lo) {
+    if (fmt == 0) v = fminf(fmaxf(v, -65504.0f), 65504.0f);
+    hi = slb_to_plane(v, fmt);
+    lo = slb_to_plane((v - slb_from_plane(hi, fmt)) * slb_plane_lo_scale(fmt), fmt);
+}
+#endif  // __CUDACC__

@@ -1,0 +1,117 @@
+// The CLIP ViT image tower as ONE C-ABI call: (B,3,S,S) preprocessed fp32 images -> (B, embed_dim) features.
+//
+// Replaces `self.model.encode_image(img)` of the reference (foundation_models/clip.py:103-118), i.e. open_clip's
+// VisionTransformer.forward: conv1 patch embedding (as a GEMM over im2col planes), class token + positional
+// embedding, ln_pre, `layers` pre-LN residual blocks (nn.MultiheadAttention + MLP), ln_post on the class token, proj.
+// Every dense contraction is slb_gemm_split (tcgen05, split planes, fp32-grade); LayerNorm and attention emit the split
+// planes the next GEMM consumes, bias / activation / residual are GEMM epilogues. The residual stream stays fp32.
+// No allocation: the caller supplies the workspace (slb_vit_workspace_bytes). Nothing synchronises.
+#include "tc_common.cuh"
+
+#include <algorithm>
+
+namespace {
+
+struct WsLayout {
+    size_t x, qkv, planes_a, planes_b, patch_f32, total;
+};
+
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+bool layout_for(const SlbVitWeights* w, int64_t B, WsLayout* L) {
+    if (!w || w->patch <= 0 || w->image_size % w->patch) return false;
+    const int64_t g = w->image_size / w->patch;
+    const int64_t T = g * g + (w->has_cls ? 1 : 0);
+    const int64_t W = w->width, rows = B * T;
+    const int64_t Kc = slb_patch_k(w->patch);
+    size_t o = 0;
+    L->x = o;          o += align_up((size_t)rows * W * 4);
+    L->qkv = o;        o += align_up((size_t)rows * 3 * W * 4);
+    // planes_a: LN output / attention output planes [2, rows, W]  — also holds the im2col planes [2, B*g*g, Kc]
+    size_t pa = std::max<size_t>((size_t)2 * rows * W * 2, (size_t)2 * B * g * g * Kc * 2);
+    L->planes_a = o;   o += align_up(pa);
+    // planes_b: MLP hidden planes [2, rows, mlp] — also the attention output planes
+    size_t pb = std::max<size_t>((size_t)2 * rows * w->mlp * 2, (size_t)2 * rows * W * 2);
+    L->planes_b = o;   o += align_up(pb);
+    L->patch_f32 = o;  o += align_up((size_t)B * g * g * W * 4);
+    L->total = o;
+    return true;
+}
+
+}  // namespace
+
+extern "C" size_t slb_vit_workspace_bytes(const SlbVitWeights* w, int64_t B) {
+    WsLayout L;
+    if (B < 0 || !layout_for(w, B, &L)) return 0;
+    return L.total;
+}
+
+extern "C" int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t B, float* out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    SLB_REQUIRE(w != nullptr && B >= 0, SLB_EINVAL, "slb_vit_forward: bad arguments");
+    if (B == 0) return SLB_OK;
+    SLB_REQUIRE(img && out && workspace, SLB_EINVAL, "slb_vit_forward: null pointer");
+    SLB_REQUIRE(w->layers >= 0 && w->layer && w->conv_w && w->pos && w->ln_post_g, SLB_EINVAL,
+                "slb_vit_forward: incomplete weights");
+    SLB_REQUIRE(w->width % 64 == 0 && w->mlp % 64 == 0 && w->heads > 0 && w->width % w->heads == 0, SLB_EUNSUPPORTED,
+                "slb_vit_forward: width and mlp must be multiples of 64");
+    SLB_REQUIRE(w->patch % 2 == 0, SLB_EUNSUPPORTED, "slb_vit_forward: patch size must be even");
+    SLB_REQUIRE(w->pool == SLB_POOL_CLS && w->has_cls, SLB_EUNSUPPORTED, "slb_vit_forward: only class-token pooling is built");
+    WsLayout L;
+    SLB_REQUIRE(layout_for(w, B, &L), SLB_EINVAL, "slb_vit_forward: image_size must be a multiple of patch");
+    SLB_REQUIRE(((uintptr_t)workspace % 256) == 0, SLB_EINVAL, "slb_vit_forward: workspace must be 256-byte aligned");
+    SLB_REQUIRE(workspace_bytes >= L.total, SLB_EWORKSPACE, "slb_vit_forward: workspace needs %zu bytes, got %zu", L.total,
+                workspace_bytes);
+
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    float* x = reinterpret_cast<float*>(ws + L.x);
+    float* qkv = reinterpret_cast<float*>(ws + L.qkv);
+    uint16_t* pa = reinterpret_cast<uint16_t*>(ws + L.planes_a);
+    uint16_t* pb = reinterpret_cast<uint16_t*>(ws + L.planes_b);
+    float* patch_f32 = reinterpret_cast<float*>(ws + L.patch_f32);
+
+    const int fmt = w->plane_fmt;
+    const int64_t g = w->image_size / w->patch;
+    const int64_t T = g * g + 1, W = w->width, rows = B * T, dh = W / w->heads;
+    const int64_t Kc = slb_patch_k(w->patch);  // conv_w planes are [2, width, Kc], zero padded past 3*P*P
+    int rc;
+#define SLB_TRY(call)            \
+    do {                         \
+        rc = (call);             \
+        if (rc != SLB_OK) return rc; \
+    } while (0)
+
+    // patch embedding: im2col planes -> GEMM (+ conv bias if any) -> tokens
+    SLB_TRY(slb_patchify(img, B, w->image_size, w->patch, fmt, pa, stream));
+    SLB_TRY(slb_gemm_split(pa, w->conv_w, fmt, B * g * g, W, Kc, w->conv_b, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
+                           patch_f32, nullptr, stream));
+    SLB_TRY(slb_assemble_tokens(patch_f32, w->cls, w->pos, B, T, W, 1, x, stream));
+    if (w->ln_pre_g) SLB_TRY(slb_layernorm(x, rows, W, W, w->ln_pre_g, w->ln_pre_b, w->ln_eps, fmt, x, nullptr, stream));
+
+    for (int l = 0; l < w->layers; ++l) {
+        const SlbVitLayer& ly = w->layer[l];
+        SLB_TRY(slb_layernorm(x, rows, W, W, ly.ln1_g, ly.ln1_b, w->ln_eps, fmt, nullptr, pa, stream));
+        SLB_TRY(slb_gemm_split(pa, ly.w_qkv, fmt, rows, 3 * W, W, ly.b_qkv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, qkv,
+                               nullptr, stream));
+        SLB_TRY(slb_attention_small(qkv, T * 3 * W, 3 * W, qkv + W, qkv + 2 * W, T * 3 * W, 3 * W, B, T, T, w->heads, dh,
+                                    1.0f / sqrtf((float)dh), fmt, nullptr, pb, stream));
+        SLB_TRY(slb_gemm_split(pb, ly.w_out, fmt, rows, W, W, ly.b_out, x, nullptr, nullptr, SLB_EPI_NONE, 3, x, nullptr,
+                               stream));
+        SLB_TRY(slb_layernorm(x, rows, W, W, ly.ln2_g, ly.ln2_b, w->ln_eps, fmt, nullptr, pa, stream));
+        SLB_TRY(slb_gemm_split(pa, ly.w_fc, fmt, rows, w->mlp, W, ly.b_fc, nullptr, nullptr, nullptr, w->act, 3, nullptr, pb,
+                               stream));
+        SLB_TRY(slb_gemm_split(pb, ly.w_proj, fmt, rows, W, w->mlp, ly.b_proj, x, nullptr, nullptr, SLB_EPI_NONE, 3, x,
+                               nullptr, stream));
+    }
+
+    // ln_post on the class tokens (rows T*W apart), then the projection
+    if (w->proj) {
+        SLB_TRY(slb_layernorm(x, B, W, T * W, w->ln_post_g, w->ln_post_b, w->ln_eps, fmt, nullptr, pa, stream));
+        SLB_TRY(slb_gemm_split(pa, w->proj, fmt, B, w->embed_dim, W, nullptr, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, out,
+                               nullptr, stream));
+    } else {
+        SLB_TRY(slb_layernorm(x, B, W, T * W, w->ln_post_g, w->ln_post_b, w->ln_eps, fmt, out, nullptr, stream));
+    }
+#undef SLB_TRY
+    return SLB_OK;
+}

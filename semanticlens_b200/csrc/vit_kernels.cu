@@ -1,0 +1,336 @@
+// K3 + the non-GEMM parts of the ViT image tower (preprocess, patchify, token assembly, LayerNorm, attention).
+//
+// Replaces, on the reference's embed path (foundation_models/clip.py:103-163 -> open_clip VisionTransformer):
+//   * `ToTensor` + `Normalize` of the eval transform, applied per PIL image on the host (clip.py:157-160)
+//   * the im2col view of conv1 (kernel = stride = patch), class-token concat + positional embedding
+//   * nn.LayerNorm (ln_pre, ln_1, ln_2, ln_post) and nn.MultiheadAttention's softmax(QK^T)V
+// Everything here is HBM/L2-bound fp32 SIMT work; the dense contractions live in gemm_tc.cu. LayerNorm and attention
+// write their result directly as split planes, the A-operand format of the next GEMM.
+#include "tc_common.cuh"
+
+#include <algorithm>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// K3: u8 planar image -> normalised fp32   out = (u8/255 - mean[c]) / std[c]   (torch's op order)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) u8_norm_kernel(const uint8_t* __restrict__ img, int64_t n16, int64_t plane16, int Cc,
+                                                      float3 mean, float3 stdv, float* __restrict__ out) {
+    // one thread = 16 pixels of one channel plane (planes are multiples of 16 pixels)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)((i / plane16) % Cc);
+        const float m = c == 0 ? mean.x : (c == 1 ? mean.y : mean.z);
+        const float s = c == 0 ? stdv.x : (c == 1 ? stdv.y : stdv.z);
+        const uint4 raw = reinterpret_cast<const uint4*>(img)[i];
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        float4* o = reinterpret_cast<float4*>(out) + i * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 v;
+            v.x = __fdiv_rn(__fdiv_rn((float)(w[q] & 0xFF), 255.0f) - m, s);
+            v.y = __fdiv_rn(__fdiv_rn((float)((w[q] >> 8) & 0xFF), 255.0f) - m, s);
+            v.z = __fdiv_rn(__fdiv_rn((float)((w[q] >> 16) & 0xFF), 255.0f) - m, s);
+            v.w = __fdiv_rn(__fdiv_rn((float)(w[q] >> 24), 255.0f) - m, s);
+            o[q] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// patchify: (B, 3, S, S) fp32 -> planes [2][B*g*g][Kpad], row = (b, gy, gx), col = (c, py, px); cols >= 3*P*P are 0
+// (Kpad = 3*P*P rounded up to 64: patch 14 gives 588 -> 640). One thread = 2 adjacent columns (P is even).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, int64_t B, int S, int P, int Kpad,
+                                                       int fmt, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    const int g = S / P;
+    const int Kc = 3 * P * P;
+    const int K2 = Kpad / 2;
+    const int64_t n2 = B * g * g * (int64_t)K2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(i % K2) * 2;
+        const int64_t row = i / K2;
+        uint32_t h2 = 0, l2 = 0;
+        if (col < Kc) {
+            const int c = col / (P * P), py = (col / P) % P, px = col % P;
+            const int gx = (int)(row % g), gy = (int)((row / g) % g);
+            const int64_t b = row / (g * g);
+            const float2 v = *reinterpret_cast<const float2*>(img + ((b * 3 + c) * S + (gy * P + py)) * (int64_t)S + gx * P + px);
+            uint16_t h0, l0, h1, l1;
+            slb_split2(v.x, fmt, h0, l0);
+            slb_split2(v.y, fmt, h1, l1);
+            h2 = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            l2 = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        }
+        reinterpret_cast<uint32_t*>(hi)[i] = h2;
+        reinterpret_cast<uint32_t*>(lo)[i] = l2;
+    }
+}
+
+// x[b, t, :] = (t < has_cls ? cls : patch[b, t - has_cls, :]) + pos[t, :]
+__global__ void __launch_bounds__(256) assemble_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
+                                                       const float* __restrict__ pos, int64_t B, int T, int W4, int has_cls,
+                                                       float* __restrict__ out) {
+    const int64_t n = B * T * (int64_t)W4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W4);
+        const int t = (int)((i / W4) % T);
+        const int64_t b = i / ((int64_t)W4 * T);
+        float4 a = (has_cls && t == 0) ? reinterpret_cast<const float4*>(cls)[w]
+                                       : reinterpret_cast<const float4*>(patch)[(b * (T - has_cls) + (t - has_cls)) * W4 + w];
+        const float4 p = pos ? reinterpret_cast<const float4*>(pos)[(int64_t)t * W4 + w] : make_float4(0, 0, 0, 0);
+        a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+        reinterpret_cast<float4*>(out)[i] = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, two-pass fp32 (mean, then centred variance), biased variance, eps inside the sqrt
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t rows, int cols,
+                                                        int64_t row_stride, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, int fmt,
+                                                        float* __restrict__ out_f32, uint16_t* __restrict__ out_hi,
+                                                        uint16_t* __restrict__ out_lo) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + r * row_stride);
+    const int c4 = cols >> 2;
+    float s = 0.f;
+    for (int i = lane; i < c4; i += 32) {
+        float4 v = xr[i];
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+    const float mean = slb_warp_sum_butterfly(s) / (float)cols;
+    float q = 0.f;
+    for (int i = lane; i < c4; i += 32) {
+        float4 v = xr[i];
+        float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float var = slb_warp_sum_butterfly(q) / (float)cols;
+    const float rstd = 1.0f / sqrtf(var + eps);
+    for (int i = lane; i < c4; i += 32) {
+        float4 v = xr[i];
+        const float4 g = reinterpret_cast<const float4*>(gamma)[i];
+        const float4 bt = beta ? reinterpret_cast<const float4*>(beta)[i] : make_float4(0, 0, 0, 0);
+        float y[4] = {(v.x - mean) * rstd * g.x + bt.x, (v.y - mean) * rstd * g.y + bt.y, (v.z - mean) * rstd * g.z + bt.z,
+                      (v.w - mean) * rstd * g.w + bt.w};
+        if (out_f32) reinterpret_cast<float4*>(out_f32 + r * cols)[i] = make_float4(y[0], y[1], y[2], y[3]);
+        if (out_hi) {
+            uint16_t h[4], l[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) slb_split2(y[k], fmt, h[k], l[k]);
+            reinterpret_cast<uint2*>(out_hi + r * cols)[i] =
+                make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+            reinterpret_cast<uint2*>(out_lo + r * cols)[i] =
+                make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention for short sequences: one CTA per (batch, head); K and V of the head live in shared memory (fp32),
+// one warp per query row: scores across lanes, softmax by warp shuffles, PV with lanes across head_dim.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAttnWarps = 8;
+constexpr int kAttnMaxChunks = 10;  // Tk <= 320
+
+struct AttnParams {
+    const float* q; int64_t q_bs, q_rs;
+    const float* k; const float* v; int64_t kv_bs, kv_rs;
+    int64_t B; int Tq, Tk, H, dh;
+    float scale;
+    float* out_f32; uint16_t* out_hi; uint16_t* out_lo; int fmt;
+};
+
+__global__ void __launch_bounds__(kAttnWarps * 32) attention_small_kernel(AttnParams p) {
+    extern __shared__ __align__(16) float sm[];
+    const int dh = p.dh, Tk = p.Tk, ldk = dh + 1;
+    float* sK = sm;                         // [Tk][dh+1]
+    float* sV = sK + (((size_t)Tk * ldk + 3) & ~(size_t)3);  // [Tk][dh], 16-byte aligned
+    float* sQ = sV + (size_t)Tk * dh;       // [warps][dh]
+    float* sP = sQ + kAttnWarps * dh;       // [warps][Tk]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b = blockIdx.x / p.H;
+    const int h = (int)(blockIdx.x % p.H);
+
+    const float* kb = p.k + b * p.kv_bs + (int64_t)h * dh;
+    const float* vb = p.v + b * p.kv_bs + (int64_t)h * dh;
+    const int dh4 = dh >> 2;
+    for (int i = threadIdx.x; i < Tk * dh4; i += blockDim.x) {
+        const int j = i / dh4, d4 = i % dh4;
+        const float4 kk = *reinterpret_cast<const float4*>(kb + (int64_t)j * p.kv_rs + 4 * d4);
+        const float4 vv = *reinterpret_cast<const float4*>(vb + (int64_t)j * p.kv_rs + 4 * d4);
+        float* kd = sK + (size_t)j * ldk + 4 * d4;
+        kd[0] = kk.x; kd[1] = kk.y; kd[2] = kk.z; kd[3] = kk.w;
+        *reinterpret_cast<float4*>(sV + (size_t)j * dh + 4 * d4) = vv;
+    }
+    __syncthreads();
+
+    float* myQ = sQ + warp * dh;
+    float* myP = sP + (size_t)warp * Tk;
+    const int nch = (Tk + 31) >> 5;
+    const int Wd = p.H * dh;
+    for (int qi = warp; qi < p.Tq; qi += kAttnWarps) {
+        const float* qr = p.q + b * p.q_bs + (int64_t)qi * p.q_rs + (int64_t)h * dh;
+        for (int d = lane; d < dh; d += 32) myQ[d] = qr[d] * p.scale;
+        __syncwarp();
+        float s[kAttnMaxChunks];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < kAttnMaxChunks; ++c) {
+            s[c] = -INFINITY;
+            if (c < nch) {
+                const int j = c * 32 + lane;
+                if (j < Tk) {
+                    const float* kr = sK + (size_t)j * ldk;
+                    float a0 = 0.f, a1 = 0.f;
+                    for (int d = 0; d < dh; d += 2) {
+                        a0 = fmaf(myQ[d], kr[d], a0);
+                        a1 = fmaf(myQ[d + 1], kr[d + 1], a1);
+                    }
+                    s[c] = a0 + a1;
+                }
+                mx = fmaxf(mx, s[c]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < kAttnMaxChunks; ++c) {
+            if (c < nch) {
+                const int j = c * 32 + lane;
+                const float e = (j < Tk) ? expf(s[c] - mx) : 0.f;
+                s[c] = e;
+                sum += e;
+            }
+        }
+        sum = slb_warp_sum_butterfly(sum);
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int c = 0; c < kAttnMaxChunks; ++c) {
+            if (c < nch) {
+                const int j = c * 32 + lane;
+                if (j < Tk) myP[j] = s[c] * inv;
+            }
+        }
+        __syncwarp();
+        const int64_t orow = b * p.Tq + qi;
+        for (int d = lane; d < dh; d += 32) {
+            float o0 = 0.f, o1 = 0.f;
+            int j = 0;
+            for (; j + 1 < Tk; j += 2) {
+                o0 = fmaf(myP[j], sV[(size_t)j * dh + d], o0);
+                o1 = fmaf(myP[j + 1], sV[(size_t)(j + 1) * dh + d], o1);
+            }
+            if (j < Tk) o0 = fmaf(myP[j], sV[(size_t)j * dh + d], o0);
+            const float o = o0 + o1;
+            const int64_t idx = orow * Wd + (int64_t)h * dh + d;
+            if (p.out_f32) p.out_f32[idx] = o;
+            if (p.out_hi) {
+                uint16_t hh, ll;
+                slb_split2(o, p.fmt, hh, ll);
+                p.out_hi[idx] = hh;
+                p.out_lo[idx] = ll;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+int grid_for(int64_t n, int threads) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>(slb_ceil_div(n, threads), (int64_t)slb_sm_count() * 16));
+}
+
+}  // namespace
+
+extern "C" int slb_u8_to_f32_norm(const uint8_t* img, int64_t B, int64_t Cc, int64_t n_pix, const float* mean3,
+                                  const float* std3, float* out, void* stream) {
+    SLB_REQUIRE(B >= 0 && n_pix >= 0, SLB_EINVAL, "slb_u8_to_f32_norm: negative size");
+    SLB_REQUIRE(Cc >= 1 && Cc <= 3, SLB_EUNSUPPORTED, "slb_u8_to_f32_norm: 1..3 channels supported (got %lld)", (long long)Cc);
+    if (B == 0 || n_pix == 0) return SLB_OK;
+    SLB_REQUIRE(img && out && mean3 && std3, SLB_EINVAL, "slb_u8_to_f32_norm: null pointer (mean3/std3 are HOST arrays)");
+    SLB_REQUIRE(n_pix % 16 == 0 && ((uintptr_t)img % 16) == 0 && ((uintptr_t)out % 16) == 0, SLB_EUNSUPPORTED,
+                "slb_u8_to_f32_norm: planes must be multiples of 16 pixels and 16-byte aligned");
+    const int64_t n16 = B * Cc * n_pix / 16;
+    float3 m = make_float3(mean3[0], Cc > 1 ? mean3[1] : 0.f, Cc > 2 ? mean3[2] : 0.f);
+    float3 s = make_float3(std3[0], Cc > 1 ? std3[1] : 1.f, Cc > 2 ? std3[2] : 1.f);
+    u8_norm_kernel<<<grid_for(n16, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, n16, n_pix / 16, (int)Cc, m, s, out);
+    SLB_LAUNCH_OK("u8_norm");
+    return SLB_OK;
+}
+
+extern "C" int slb_patchify(const float* img, int64_t B, int64_t S, int64_t P, int plane_fmt, uint16_t* out_planes,
+                            void* stream) {
+    SLB_REQUIRE(B >= 0 && S > 0 && P > 0, SLB_EINVAL, "slb_patchify: bad size");
+    if (B == 0) return SLB_OK;
+    SLB_REQUIRE(img && out_planes, SLB_EINVAL, "slb_patchify: null pointer");
+    SLB_REQUIRE(S % P == 0 && P % 2 == 0, SLB_EUNSUPPORTED, "slb_patchify: need S %% P == 0 and an even patch size");
+    SLB_REQUIRE(((uintptr_t)img % 8) == 0 && ((uintptr_t)out_planes % 16) == 0, SLB_EINVAL, "slb_patchify: misaligned");
+    const int64_t g = S / P, Kpad = slb_patch_k(P), n = B * g * g * Kpad;
+    patchify_kernel<<<grid_for(n / 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, B, (int)S, (int)P, (int)Kpad,
+                                                                                        plane_fmt, out_planes, out_planes + n);
+    SLB_LAUNCH_OK("patchify");
+    return SLB_OK;
+}
+
+extern "C" int64_t slb_patch_k(int64_t P) { return (3 * P * P + 63) / 64 * 64; }
+
+extern "C" int slb_assemble_tokens(const float* patch, const float* cls, const float* pos, int64_t B, int64_t T, int64_t W,
+                                   int has_cls, float* out, void* stream) {
+    SLB_REQUIRE(B >= 0 && T > 0 && W > 0, SLB_EINVAL, "slb_assemble_tokens: bad size");
+    if (B == 0) return SLB_OK;
+    SLB_REQUIRE(patch && out && (!has_cls || cls), SLB_EINVAL, "slb_assemble_tokens: null pointer");
+    SLB_REQUIRE(W % 4 == 0, SLB_EUNSUPPORTED, "slb_assemble_tokens: width must be a multiple of 4");
+    assemble_kernel<<<grid_for(B * T * W / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        patch, cls, pos, B, (int)T, (int)(W / 4), has_cls ? 1 : 0, out);
+    SLB_LAUNCH_OK("assemble_tokens");
+    return SLB_OK;
+}
+
+extern "C" int slb_layernorm(const float* x, int64_t rows, int64_t cols, int64_t row_stride, const float* gamma,
+                             const float* beta, float eps, int plane_fmt, float* out_f32, uint16_t* out_planes,
+                             void* stream) {
+    SLB_REQUIRE(rows >= 0 && cols > 0, SLB_EINVAL, "slb_layernorm: bad size");
+    if (rows == 0) return SLB_OK;
+    SLB_REQUIRE(x && gamma && (out_f32 || out_planes), SLB_EINVAL, "slb_layernorm: null pointer");
+    SLB_REQUIRE(cols % 4 == 0 && row_stride % 4 == 0 && row_stride >= cols, SLB_EUNSUPPORTED,
+                "slb_layernorm: cols and row_stride must be multiples of 4");
+    const int threads = 256;
+    layernorm_kernel<<<(unsigned)slb_ceil_div(rows * 32, threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, rows, (int)cols, row_stride, gamma, beta, eps, plane_fmt, out_f32, out_planes,
+        out_planes ? out_planes + rows * cols : nullptr);
+    SLB_LAUNCH_OK("layernorm");
+    return SLB_OK;
+}
+
+extern "C" int slb_attention_small(const float* q, int64_t q_batch_stride, int64_t q_row_stride, const float* k,
+                                   const float* v, int64_t kv_batch_stride, int64_t kv_row_stride, int64_t B, int64_t Tq,
+                                   int64_t Tk, int64_t H, int64_t dh, float scale, int plane_fmt, float* out_f32,
+                                   uint16_t* out_planes, void* stream) {
+    SLB_REQUIRE(B >= 0 && Tq > 0 && Tk > 0 && H > 0 && dh > 0, SLB_EINVAL, "slb_attention_small: bad size");
+    if (B == 0) return SLB_OK;
+    SLB_REQUIRE(q && k && v && (out_f32 || out_planes), SLB_EINVAL, "slb_attention_small: null pointer");
+    SLB_REQUIRE(Tk <= 32 * kAttnMaxChunks, SLB_EUNSUPPORTED, "slb_attention_small: at most %d keys (got %lld)",
+                32 * kAttnMaxChunks, (long long)Tk);
+    SLB_REQUIRE(dh % 4 == 0 && dh <= 128 && kv_row_stride % 4 == 0 && kv_batch_stride % 4 == 0 &&
+                    ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0,
+                SLB_EUNSUPPORTED, "slb_attention_small: head_dim must be a multiple of 4 (<= 128), K/V 16-byte aligned");
+    AttnParams p{};
+    p.q = q; p.q_bs = q_batch_stride; p.q_rs = q_row_stride;
+    p.k = k; p.v = v; p.kv_bs = kv_batch_stride; p.kv_rs = kv_row_stride;
+    p.B = B; p.Tq = (int)Tq; p.Tk = (int)Tk; p.H = (int)H; p.dh = (int)dh;
+    p.scale = scale;
+    p.out_f32 = out_f32; p.out_hi = out_planes; p.out_lo = out_planes ? out_planes + B * Tq * H * dh : nullptr;
+    p.fmt = plane_fmt;
+    const size_t smem = sizeof(float) * ((((size_t)Tk * (dh + 1) + 3) & ~(size_t)3) + (size_t)Tk * dh + (size_t)kAttnWarps * dh + (size_t)kAttnWarps * Tk);
+    SLB_REQUIRE(smem <= 227 * 1024, SLB_EUNSUPPORTED, "slb_attention_small: K/V of one head do not fit shared memory");
+    SLB_CUDA_OK(cudaFuncSetAttribute(attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SLB_REQUIRE(B * H <= 0x7FFFFFFF, SLB_EUNSUPPORTED, "slb_attention_small: grid too large");
+    attention_small_kernel<<<(unsigned)(B * H), kAttnWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    SLB_LAUNCH_OK("attention_small");
+    return SLB_OK;
+}

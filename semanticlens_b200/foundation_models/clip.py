@@ -1,0 +1,152 @@
+"""``OpenClip`` — drop-in for the reference wrapper (semanticlens/foundation_models/clip.py:27-187) whose image
+side runs on the B200 kernels.
+
+The reference delegates to ``open_clip.create_model_and_transforms(url, **kwargs)``; ``open_clip`` is a third-party
+dependency that is not vendored (and there is no network here), so this class restates what that call provides for
+the image path: the model config of ``url``, the eval transform (Resize(bicubic) -> CenterCrop -> RGB -> ToTensor ->
+Normalize with the OpenAI mean/std) and the ``VisionTransformer`` forward. Weights come from ``state_dict=`` /
+``checkpoint_path=`` (open_clip naming, ``visual.*``) or are randomly initialised (``load_weights=False`` in the
+reference's own tests does the same). The text tower (``encode_text`` / ``tokenize``) is not on the concept-DB build
+path and is not built yet.
+"""
+
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from . import vit
+from .base import AbstractVLM
+
+logger = logging.getLogger(__name__)
+
+
+class OpenClip(AbstractVLM):
+    """CLIP image tower on B200.
+
+    Parameters
+    ----------
+    url : str
+        open_clip model name: "ViT-B-32", "ViT-B-32-quickgelu", "ViT-B-16", "ViT-L-14", ... (``vit.CONFIGS``).
+    device : str or torch.device
+        Where the tower lives; kernels need a CUDA device.
+    **kwargs
+        ``load_weights`` / ``pretrained`` (accepted like open_clip's; nothing can be downloaded here),
+        ``state_dict`` or ``checkpoint_path`` (open_clip-named weights), ``seed`` (random init),
+        ``plane_format`` ("f16" default: 22-bit operands, "bf16": 16-bit operands with fp32 range).
+    """
+
+    def __init__(self, url, device="cpu", **kwargs):
+        if url not in vit.CONFIGS:
+            raise ValueError(f"unknown or unsupported open_clip image tower '{url}' (built: {sorted(vit.CONFIGS)})")
+        self.url = url
+        self.cfg = vit.CONFIGS[url]
+        sd = kwargs.pop("state_dict", None)
+        ckpt = kwargs.pop("checkpoint_path", None)
+        seed = kwargs.pop("seed", 1)
+        fmt = {"f16": N.PLANE_F16, "bf16": N.PLANE_BF16}[kwargs.pop("plane_format", "f16")]
+        pretrained = kwargs.pop("pretrained", None)
+        kwargs.pop("load_weights", None)
+        if kwargs:
+            raise TypeError(f"unexpected arguments {sorted(kwargs)}")
+        if sd is None and ckpt is not None:
+            sd = _load_checkpoint(ckpt)
+        if sd is None:
+            if pretrained:
+                logger.warning("pretrained='%s' cannot be downloaded here; using random weights (seed %d)", pretrained, seed)
+            sd = vit.random_state_dict(self.cfg, seed)
+        self.model = vit.VitTower(self.cfg, sd, device, fmt)
+        self._pin: torch.Tensor | None = None
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(url='{self.url}', model=VitTower[B200])"
+
+    @property
+    def device(self):
+        return self.model.device
+
+    def to(self, device):
+        self.model.to(device)
+        return self.model
+
+    # -- image side -------------------------------------------------------------------------------------
+    def encode_image(self, img: torch.Tensor):
+        """(B, 3, S, S) preprocessed images -> (B, D) un-normalised features on the GPU (reference :103-118)."""
+        with torch.no_grad():
+            return self.model.forward(img.to(self.device, non_blocking=True))
+
+    def preprocess(self, img) -> torch.Tensor:
+        """PIL image(s) / uint8 (B,3,H,W) tensor(s) -> normalised fp32 batch on ``device`` (reference :137-163).
+
+        Resize/crop (only needed when the input is not already S x S) use PIL on the host exactly like the
+        reference's transform; ToTensor + Normalize run on the GPU (K3).
+        """
+        from .. import ops
+
+        u8 = self._to_u8_batch(img)
+        dev = self.device
+        if dev.type != "cuda":
+            raise N.SlbError("OpenClip.preprocess runs on the GPU: move the model with .to('cuda') first")
+        if not u8.is_cuda:
+            if not u8.is_pinned():
+                if self._pin is None or self._pin.numel() < u8.numel():
+                    self._pin = torch.empty(u8.numel(), dtype=torch.uint8, pin_memory=True)
+                staged = self._pin[: u8.numel()].view(u8.shape)
+                staged.copy_(u8)
+                u8 = staged
+            u8 = u8.to(dev, non_blocking=True)
+        return ops.u8_to_f32_norm(u8, self.cfg.mean, self.cfg.std)
+
+    def _to_u8_batch(self, img) -> torch.Tensor:
+        S = self.cfg.image_size
+        if isinstance(img, torch.Tensor):
+            t = img if img.ndim == 4 else img.unsqueeze(0)
+            if t.dtype != torch.uint8 or t.shape[1] != 3 or t.shape[2] != S or t.shape[3] != S:
+                raise ValueError(f"tensor inputs must be uint8 (B, 3, {S}, {S}); got {t.dtype} {tuple(t.shape)}")
+            return t.contiguous()
+        items = img if isinstance(img, (list, tuple)) else [img]
+        if items and isinstance(items[0], torch.Tensor):
+            return self._to_u8_batch(torch.stack(list(items)))
+        out = np.empty((len(items), 3, S, S), dtype=np.uint8)
+        for i, im in enumerate(items):
+            out[i] = _pil_to_chw_u8(im, S)
+        return torch.from_numpy(out)
+
+    # -- text side (not on the concept-DB build path) -------------------------------------------------------
+    def encode_text(self, text_input: torch.Tensor):
+        raise NotImplementedError("the CLIP text tower is not built yet (SURVEY.md §8 f2); pass text embeddings to Lens")
+
+    def tokenize(self, txt, context_length=None):
+        raise NotImplementedError("the CLIP tokenizer/text tower is not built yet (SURVEY.md §8 f2)")
+
+
+def _pil_to_chw_u8(im, S: int) -> np.ndarray:
+    """open_clip eval transform up to (not including) ToTensor: Resize(S, bicubic) on the shorter side, CenterCrop(S),
+    convert to RGB."""
+    from PIL import Image
+
+    w, h = im.size
+    if (w, h) != (S, S):
+        if w <= h:
+            nw, nh = S, max(S, int(S * h / w))
+        else:
+            nw, nh = max(S, int(S * w / h)), S
+        if (nw, nh) != (w, h):
+            im = im.resize((nw, nh), Image.BICUBIC)
+        left, top = int(round((nw - S) / 2.0)), int(round((nh - S) / 2.0))
+        im = im.crop((left, top, left + S, top + S))
+    im = im.convert("RGB")
+    return np.asarray(im, dtype=np.uint8).transpose(2, 0, 1)
+
+
+def _load_checkpoint(path) -> dict[str, torch.Tensor]:
+    path = str(path)
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+
+        return load_file(path)
+    sd = torch.load(path, map_location="cpu", weights_only=True)
+    return sd.get("state_dict", sd)

@@ -210,3 +210,127 @@ def gather_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
         )
     N.check(rc, "slb_gather_rows")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# embed: split planes + tensor-core GEMM
+# ------------------------------------------------------------------------------------------------
+PLANE_DTYPES = {N.PLANE_F16: torch.float16, N.PLANE_BF16: torch.bfloat16}
+
+
+def split_planes(x: torch.Tensor, fmt: int = N.PLANE_F16) -> torch.Tensor:
+    """fp32 (..., K) -> (2, ..., K) 16-bit planes: hi = rn16(x), lo = rn16(x - hi)."""
+    lib = N.load(require_device=True)
+    N.require_cuda(x, "x")
+    x = x.detach().to(torch.float32).contiguous()
+    planes = torch.empty((2, *x.shape), dtype=PLANE_DTYPES[fmt], device=x.device)
+    if x.numel():
+        with _dev_guard(x):
+            rc = lib.slb_split_planes(x.data_ptr(), x.numel(), fmt, planes.data_ptr(), N.stream_ptr(x.device))
+        N.check(rc, "slb_split_planes")
+    return planes
+
+
+def gemm_split(
+    a_planes: torch.Tensor,
+    w_planes: torch.Tensor,
+    *,
+    bias: torch.Tensor | None = None,
+    residual: torch.Tensor | None = None,
+    row_scale: torch.Tensor | None = None,
+    col_scale: torch.Tensor | None = None,
+    epilogue: int = N.EPI_NONE,
+    passes: int = 3,
+    out_f32: torch.Tensor | bool = True,
+    out_planes: torch.Tensor | bool = False,
+):
+    """K4: act((A @ W^T) * row_scale * col_scale + bias) + residual from split planes (2, M, K) and (2, N, K).
+
+    ``out_f32`` / ``out_planes``: True = allocate, False = not wanted, or a preallocated tensor.
+    Returns (out_f32 | None, out_planes | None).
+    """
+    lib = N.load(require_device=True)
+    N.require_cuda(a_planes, "a_planes")
+    assert a_planes.ndim == 3 and w_planes.ndim == 3 and a_planes.shape[0] == 2 and w_planes.shape[0] == 2
+    assert a_planes.dtype == w_planes.dtype and a_planes.dtype in (torch.float16, torch.bfloat16)
+    assert a_planes.is_contiguous() and w_planes.is_contiguous()
+    fmt = N.PLANE_F16 if a_planes.dtype == torch.float16 else N.PLANE_BF16
+    _, M, K = a_planes.shape
+    _, Nn, K2 = w_planes.shape
+    assert K == K2, (a_planes.shape, w_planes.shape)
+    dev = a_planes.device
+    if out_f32 is True:
+        out_f32 = torch.empty((M, Nn), dtype=torch.float32, device=dev)
+    elif out_f32 is False:
+        out_f32 = None
+    if out_planes is True:
+        out_planes = torch.empty((2, M, Nn), dtype=a_planes.dtype, device=dev)
+    elif out_planes is False:
+        out_planes = None
+    for t, shape in ((bias, (Nn,)), (residual, (M, Nn)), (row_scale, (M,)), (col_scale, (Nn,)), (out_f32, (M, Nn))):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape, (t.shape, shape)
+    if out_planes is not None:
+        assert tuple(out_planes.shape) == (2, M, Nn) and out_planes.is_contiguous() and out_planes.dtype == a_planes.dtype
+    tm = _timer.begin() if _timer else None
+    with _dev_guard(a_planes):
+        rc = lib.slb_gemm_split(
+            a_planes.data_ptr(), w_planes.data_ptr(), fmt, M, Nn, K, N.ptr(bias), N.ptr(residual), N.ptr(row_scale),
+            N.ptr(col_scale), epilogue, passes, N.ptr(out_f32), N.ptr(out_planes), N.stream_ptr(dev),
+        )
+    if _timer:
+        _timer.end("K4 gemm_split", tm, 2 * 2 * (M * K + Nn * K) + (M * Nn * 4 if out_f32 is not None else 0),
+                   2 * M * Nn * K * passes)
+    N.check(rc, "slb_gemm_split")
+    return out_f32, out_planes
+
+
+def u8_to_f32_norm(u8: torch.Tensor, mean, std) -> torch.Tensor:
+    """K3: uint8 (B, C, H, W) on the GPU -> (x/255 - mean[c]) / std[c] fp32 (ToTensor + Normalize)."""
+    lib = N.load(require_device=True)
+    N.require_cuda(u8, "images")
+    assert u8.dtype == torch.uint8 and u8.ndim == 4
+    u8 = u8.contiguous()
+    B, C, H, W = u8.shape
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=u8.device)
+    import ctypes
+
+    m = (ctypes.c_float * C)(*[float(v) for v in mean][:C])
+    s = (ctypes.c_float * C)(*[float(v) for v in std][:C])
+    with _dev_guard(u8):
+        rc = lib.slb_u8_to_f32_norm(u8.data_ptr(), B, C, H * W, m, s, out.data_ptr(), N.stream_ptr(u8.device))
+    N.check(rc, "slb_u8_to_f32_norm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor | None, eps: float, fmt: int | None = None):
+    """Row LayerNorm of a contiguous (rows, cols) fp32 tensor -> fp32 (fmt None) or split planes (2, rows, cols)."""
+    lib = N.load(require_device=True)
+    N.require_cuda(x, "x")
+    assert x.ndim == 2 and x.dtype == torch.float32 and x.is_contiguous()
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), dtype=torch.float32, device=x.device) if fmt is None else None
+    planes = torch.empty((2, rows, cols), dtype=PLANE_DTYPES[fmt], device=x.device) if fmt is not None else None
+    with _dev_guard(x):
+        rc = lib.slb_layernorm(x.data_ptr(), rows, cols, cols, gamma.data_ptr(), N.ptr(beta), eps, fmt or 0,
+                               N.ptr(out), N.ptr(planes), N.stream_ptr(x.device))
+    N.check(rc, "slb_layernorm")
+    return out if fmt is None else planes
+
+
+def attention_packed(qkv: torch.Tensor, heads: int, fmt: int | None = None):
+    """softmax(QK^T/sqrt(dh))V on a packed (B, T, 3W) in_proj output -> (B, T, W) fp32 or planes (2, B*T, W)."""
+    lib = N.load(require_device=True)
+    N.require_cuda(qkv, "qkv")
+    assert qkv.ndim == 3 and qkv.dtype == torch.float32 and qkv.is_contiguous()
+    B, T, W3 = qkv.shape
+    W = W3 // 3
+    dh = W // heads
+    out = torch.empty((B, T, W), dtype=torch.float32, device=qkv.device) if fmt is None else None
+    planes = torch.empty((2, B * T, W), dtype=PLANE_DTYPES[fmt], device=qkv.device) if fmt is not None else None
+    base = qkv.data_ptr()
+    with _dev_guard(qkv):
+        rc = lib.slb_attention_small(base, T * W3, W3, base + 4 * W, base + 8 * W, T * W3, W3, B, T, T, heads, dh,
+                                     float(dh) ** -0.5, fmt or 0, N.ptr(out), N.ptr(planes), N.stream_ptr(qkv.device))
+    N.check(rc, "slb_attention_small")
+    return out if fmt is None else planes

@@ -1,0 +1,126 @@
+"""Embed stage on the GPU through the C-ABI vs the torch oracle tower (oracle/vit_port.py): K3 preprocess,
+LayerNorm, attention, and the whole ViT image tower. Tolerance for features: 1e-4 relative (max-norm), the bar
+BASELINE.json's north_star states; the achieved error is far below and is asserted at 2e-5."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_port as vp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from semanticlens_b200 import ops
+
+    return ops
+
+
+def rel_max(got, want):
+    return ((got.double().cpu() - want.double().cpu()).abs().max() / want.double().abs().max()).item()
+
+
+def test_k3_u8_norm_bitexact_vs_totensor_normalize(ops):
+    cfg = vp.CONFIGS["ViT-B-32"]
+    u8 = torch.randint(0, 256, (3, 3, 224, 224), dtype=torch.uint8)
+    got = ops.u8_to_f32_norm(u8.cuda(), cfg.mean, cfg.std).cpu()
+    assert torch.equal(got, vp.preprocess_u8(cfg, u8))
+
+
+@pytest.mark.parametrize("rows,cols", [(7, 64), (300, 768), (33, 1024)])
+def test_layernorm_vs_torch(ops, rows, cols):
+    x = torch.randn(rows, cols) * 3 + 0.5
+    g, b = torch.randn(cols), torch.randn(cols)
+    want = torch.nn.functional.layer_norm(x.double(), (cols,), g.double(), b.double(), 1e-5)
+    got = ops.layernorm(x.cuda(), g.cuda(), b.cuda(), 1e-5)
+    assert rel_max(got, want) < 2e-6
+    planes = ops.layernorm(x.cuda(), g.cuda(), b.cuda(), 1e-5, fmt=0)
+    assert rel_max(planes[0].double() + planes[1].double() / 2048, want) < 2e-6
+
+
+@pytest.mark.parametrize("B,T,H,dh", [(2, 50, 12, 64), (1, 257, 4, 64), (3, 17, 2, 32), (2, 197, 3, 64)])
+def test_attention_vs_torch(ops, B, T, H, dh):
+    W = H * dh
+    qkv = torch.randn(B, T, 3 * W)
+    q, k, v = (t.view(B, T, H, dh).transpose(1, 2).double() for t in qkv.split(W, -1))
+    want = (torch.softmax(q @ k.transpose(-1, -2) * dh**-0.5, -1) @ v).transpose(1, 2).reshape(B, T, W)
+    got = ops.attention_packed(qkv.cuda(), H)
+    assert rel_max(got, want) < 2e-6
+    planes = ops.attention_packed(qkv.cuda(), H, fmt=0)
+    assert rel_max((planes[0].double() + planes[1].double() / 2048).view(B, T, W), want) < 2e-6
+
+
+def tower_for(name, seed=3, fmt=0):
+    from semanticlens_b200.foundation_models import vit
+
+    ocfg = vp.CONFIGS[name]
+    cfg = vit.VitConfig(**{f: getattr(ocfg, f) for f in ("name", "image_size", "patch", "width", "layers", "heads", "mlp",
+                                                           "embed_dim", "act", "eps", "mean", "std")})
+    sd = vp.init_weights(ocfg, seed)
+    return ocfg, sd, vit.VitTower(cfg, sd, "cuda", fmt)
+
+
+@pytest.mark.parametrize("name,B", [("ViT-tiny-test", 5), ("ViT-small-test", 9), ("ViT-B-32", 4), ("ViT-B-16", 2)])
+def test_vit_tower_vs_oracle(name, B):
+    ocfg, sd, tower = tower_for(name)
+    img = torch.randn(B, 3, ocfg.image_size, ocfg.image_size, generator=torch.Generator().manual_seed(1))
+    got = tower.forward(img.cuda())
+    truth = vp.encode_image(sd, ocfg, img, dtype=torch.float64)
+    oracle32 = vp.encode_image(sd, ocfg, img)
+    e_kernel, e_oracle = rel_max(got, truth), rel_max(oracle32, truth)
+    print(f"{name}: kernels vs f64 {e_kernel:.2e}, torch-fp32 oracle vs f64 {e_oracle:.2e}")
+    assert got.shape == (B, ocfg.embed_dim)
+    assert rel_max(got, oracle32) < 1e-4  # the north-star tolerance
+    assert e_kernel < 2e-5
+
+
+def test_vit_tower_bf16_planes_are_16bit_grade():
+    ocfg, sd, tower = tower_for("ViT-small-test", fmt=1)
+    img = torch.randn(4, 3, ocfg.image_size, ocfg.image_size)
+    err = rel_max(tower.forward(img.cuda()), vp.encode_image(sd, ocfg, img, dtype=torch.float64))
+    assert err < 5e-4
+
+
+def test_vit_tower_batch_composition_invariance():
+    ocfg, sd, tower = tower_for("ViT-small-test")
+    img = torch.randn(6, 3, ocfg.image_size, ocfg.image_size).cuda()
+    whole = tower.forward(img)
+    parts = torch.cat([tower.forward(img[:1]), tower.forward(img[1:4]), tower.forward(img[4:])])
+    assert torch.equal(whole, parts)
+
+
+def test_openclip_wrapper_api():
+    from PIL import Image
+
+    from semanticlens_b200.foundation_models import OpenClip
+
+    fm = OpenClip("ViT-B-32-quickgelu", device="cuda", load_weights=False)
+    assert fm.device.type == "cuda"
+    x = fm.preprocess(Image.new("RGB", (64, 64), "red"))
+    assert x.shape == (1, 3, 224, 224) and x.is_cuda and x.dtype == torch.float32
+    xs = fm.preprocess([Image.new("RGB", (300, 224), "blue"), Image.new("RGB", (224, 224), "green")])
+    assert xs.shape == (2, 3, 224, 224)
+    e = fm.encode_image(xs)
+    assert e.ndim == 2 and e.shape == (2, 512) and torch.isfinite(e).all()
+    with pytest.raises(ValueError):
+        OpenClip("not-a-model")
+    with pytest.raises(NotImplementedError):
+        fm.encode_text(torch.zeros(1, 77, dtype=torch.long))
+
+
+def test_preprocess_matches_reference_transform_on_pil():
+    """Resize(bicubic)/CenterCrop/ToTensor/Normalize of the open_clip eval transform, restated with torchvision."""
+    import torchvision.transforms as T
+    from PIL import Image
+
+    from semanticlens_b200.foundation_models import OpenClip
+
+    fm = OpenClip("ViT-B-32", device="cuda", load_weights=False)
+    rng = np.random.default_rng(0)
+    ims = [Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)) for h, w in ((224, 224), (260, 300), (500, 230))]
+    tf = T.Compose([T.Resize(224, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(224), T.ToTensor(),
+                    T.Normalize(fm.cfg.mean, fm.cfg.std)])
+    want = torch.stack([tf(im) for im in ims])
+    assert torch.equal(fm.preprocess(ims).cpu(), want)

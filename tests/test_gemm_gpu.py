@@ -1,0 +1,79 @@
+"""K4 tensor-core GEMM (split planes, tcgen05) through the C-ABI vs float64 matmul."""
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from semanticlens_b200 import ops
+
+    return ops
+
+
+def rel_err(got, want):
+    return ((got.double() - want).abs().max() / want.abs().max()).item()
+
+
+SHAPES = [(128, 128, 64), (128, 128, 128), (256, 384, 768), (100, 136, 192), (1000, 768, 768), (12800, 2304, 768),
+          (300, 512, 3072), (5, 8, 64)]
+
+
+@pytest.mark.parametrize("fmt,tol", [(0, 8e-6), (1, 6e-5)])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_split3_accuracy(ops, M, N, K, fmt, tol):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    out, _ = ops.gemm_split(ops.split_planes(a, fmt), ops.split_planes(w, fmt))
+    want = a.double() @ w.double().T
+    assert rel_err(out, want) < tol
+
+
+def test_gemm_single_pass_is_16bit_grade(ops):
+    a = torch.randn(256, 256, device="cuda")
+    w = torch.randn(256, 256, device="cuda")
+    ap, wp = ops.split_planes(a, 1), ops.split_planes(w, 1)
+    out1, _ = ops.gemm_split(ap, wp, passes=1)
+    want1 = ap[0].double() @ wp[0].double().T  # exactly the hi·hi product
+    assert rel_err(out1, want1) < 1e-6
+    assert rel_err(out1, a.double() @ w.double().T) > 1e-4
+
+
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_gemm_epilogues(ops, epi):
+    M, N, K = 300, 264, 128
+    a, w = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda") * 0.1
+    bias, res = torch.randn(N, device="cuda"), torch.randn(M, N, device="cuda")
+    rs, cs = torch.rand(M, device="cuda") + 0.5, torch.rand(N, device="cuda") + 0.5
+    out, planes = ops.gemm_split(ops.split_planes(a), ops.split_planes(w), bias=bias, residual=res, row_scale=rs,
+                                 col_scale=cs, epilogue=epi, out_planes=True)
+    z = (a.double() @ w.double().T) * rs.double()[:, None] * cs.double()[None] + bias.double()
+    act = {0: lambda t: t, 1: lambda t: torch.nn.functional.gelu(t),
+           2: lambda t: t * torch.sigmoid(1.702 * t), 3: lambda t: torch.nn.functional.gelu(t, approximate="tanh")}[epi]
+    want = act(z) + res.double()
+    assert rel_err(out, want) < 3e-6
+    # the planes output is the split of the fp32 output
+    ref_planes = ops.split_planes(out)
+    assert torch.equal(planes, ref_planes)
+    assert rel_err(planes[0].double() + planes[1].double() / 2048, out.double()) < 1e-6
+
+
+def test_gemm_residual_in_place(ops):
+    M, N, K = 200, 128, 64
+    a, w = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
+    x = torch.randn(M, N, device="cuda")
+    want = x.double() + a.double() @ w.double().T
+    ops.gemm_split(ops.split_planes(a), ops.split_planes(w), residual=x, out_f32=x)
+    assert rel_err(x, want) < 2e-6
+
+
+def test_gemm_argument_errors(ops):
+    from semanticlens_b200._native import SlbError
+
+    a = ops.split_planes(torch.randn(8, 48, device="cuda"))
+    w = ops.split_planes(torch.randn(8, 48, device="cuda"))
+    with pytest.raises(SlbError, match="multiple of 64"):
+        ops.gemm_split(a, w)

@@ -1,0 +1,76 @@
+"""Pin the torch restatement of open_clip's VisionTransformer (oracle/vit_port.py) against an independent
+implementation of the same published architecture: HuggingFace transformers' CLIPVisionModelWithProjection,
+weights mapped name by name. (open_clip itself is neither vendored nor installed: parity is otherwise unpinned.)"""
+
+import pytest
+import torch
+
+from oracle import vit_port as vp
+
+
+def hf_model(cfg, sd):
+    transformers = pytest.importorskip("transformers")
+    hc = transformers.CLIPVisionConfig(
+        hidden_size=cfg.width, intermediate_size=cfg.mlp, num_hidden_layers=cfg.layers, num_attention_heads=cfg.heads,
+        image_size=cfg.image_size, patch_size=cfg.patch, projection_dim=cfg.embed_dim,
+        hidden_act={"gelu": "gelu", "quick_gelu": "quick_gelu"}[cfg.act], layer_norm_eps=cfg.eps,
+    )
+    m = transformers.CLIPVisionModelWithProjection(hc).eval()
+    W = cfg.width
+    new = {
+        "vision_model.embeddings.class_embedding": sd["visual.class_embedding"],
+        "vision_model.embeddings.patch_embedding.weight": sd["visual.conv1.weight"],
+        "vision_model.embeddings.position_embedding.weight": sd["visual.positional_embedding"],
+        "vision_model.pre_layrnorm.weight": sd["visual.ln_pre.weight"],
+        "vision_model.pre_layrnorm.bias": sd["visual.ln_pre.bias"],
+        "vision_model.post_layernorm.weight": sd["visual.ln_post.weight"],
+        "vision_model.post_layernorm.bias": sd["visual.ln_post.bias"],
+        "visual_projection.weight": sd["visual.proj"].T.contiguous(),
+    }
+    for i in range(cfg.layers):
+        p, q = f"visual.transformer.resblocks.{i}.", f"vision_model.encoder.layers.{i}."
+        wi, bi = sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"]
+        for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
+            new[q + f"self_attn.{n}.weight"] = wi[j * W : (j + 1) * W]
+            new[q + f"self_attn.{n}.bias"] = bi[j * W : (j + 1) * W]
+        new[q + "self_attn.out_proj.weight"] = sd[p + "attn.out_proj.weight"]
+        new[q + "self_attn.out_proj.bias"] = sd[p + "attn.out_proj.bias"]
+        new[q + "layer_norm1.weight"], new[q + "layer_norm1.bias"] = sd[p + "ln_1.weight"], sd[p + "ln_1.bias"]
+        new[q + "layer_norm2.weight"], new[q + "layer_norm2.bias"] = sd[p + "ln_2.weight"], sd[p + "ln_2.bias"]
+        new[q + "mlp.fc1.weight"], new[q + "mlp.fc1.bias"] = sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"]
+        new[q + "mlp.fc2.weight"], new[q + "mlp.fc2.bias"] = sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"]
+    missing, unexpected = m.load_state_dict(new, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    return m
+
+
+@pytest.mark.parametrize("name", ["ViT-tiny-test", "ViT-small-test"])
+def test_oracle_tower_matches_hf_clip(name):
+    cfg = vp.CONFIGS[name]
+    sd = vp.init_weights(cfg, seed=3)
+    m = hf_model(cfg, sd)
+    img = torch.randn(3, 3, cfg.image_size, cfg.image_size, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        want = m(pixel_values=img).image_embeds
+    got = vp.encode_image(sd, cfg, img)
+    assert got.shape == (3, cfg.embed_dim)
+    assert (got - want).abs().max() <= 2e-5 * want.abs().max()
+    # and fp32 oracle vs its own float64 evaluation
+    hi = vp.encode_image(sd, cfg, img, dtype=torch.float64)
+    assert (got.double() - hi).abs().max() <= 1e-5 * hi.abs().max()
+
+
+def test_preprocess_u8_is_totensor_normalize():
+    cfg = vp.CONFIGS["ViT-tiny-test"]
+    u8 = torch.randint(0, 256, (2, 3, 32, 32), dtype=torch.uint8)
+    import torchvision.transforms as T
+
+    tf = T.Compose([T.ToTensor(), T.Normalize(cfg.mean, cfg.std)])
+    from PIL import Image
+
+    want = torch.stack([tf(Image.fromarray(im.permute(1, 2, 0).numpy())) for im in u8])
+    assert torch.equal(vp.preprocess_u8(cfg, u8), want)
+
+
+def test_flops_model():
+    assert abs(vp.flops_per_image(vp.CONFIGS["ViT-L-14"]) / 1e9 - 162.0) < 3.0
