@@ -372,8 +372,11 @@ def run_b200(args):
         h2d = B * 3 * 224 * 224 * 4 + (B * 3 * 224 * 224 if fm is not None else 0)
         return float(t[0].item()), h2d, d2h / n_steps
 
-    e2e_run(max(W, 1), 11)  # warm-up of the public path
-    e2e_ms, h2d, d2h = e2e_run(K, 12)
+    if args.no_e2e:
+        e2e_ms, h2d, d2h = float("nan"), 0, 0
+    else:
+        e2e_run(max(W, 1), 11)  # warm-up of the public path
+        e2e_ms, h2d, d2h = e2e_run(K, 12)
     e2e_value = world * K * B / (e2e_ms / 1e3)
 
     # ---- roofline of the dominant libslb200 kernel --------------------------------------------------
@@ -422,6 +425,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--cpu-images", type=int, default=256, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -102,6 +102,45 @@ int slb_gather_rows(const float* table, int64_t N, int64_t D, const int64_t* idx
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * analyze: similarity / clarity / polysemanticity  (semanticlens/scores.py)
+ * ---------------------------------------------------------------------------------------- */
+
+/* F.normalize(x, dim=-1, eps) fused with the split-plane conversion: planes [2, rows, Kpad] of x / max(|x|, eps),
+ * Kpad = D rounded up to a multiple of 64 (zero padded), and/or inv_norms [rows] = 1 / max(|x|, eps).
+ * Either output may be NULL. D % 4 == 0, D <= 2048. (scores.py:120-121) */
+int slb_normalize_split_rows(const float* x, int64_t rows, int64_t D, float eps, int plane_fmt, uint16_t* planes,
+                             float* inv_norms, void* stream);
+
+/* K6. out[M,N] = normalize(x)[M,D] . normalize(y)[N,D]^T — scores.similarity_score's matmul branch
+ * (scores.py:119-125, reached from Lens.text_probing / image_probing via lens.py:207-214). fp32 out, fp32-grade
+ * accuracy (3-pass split-fp16 tcgen05 GEMM). N % 8 == 0. workspace: 256-byte aligned, >= the query below. */
+size_t slb_cosine_gemm_workspace_bytes(int64_t M, int64_t N, int64_t D);
+int slb_cosine_gemm(const float* x, int64_t M, const float* y, int64_t N, int64_t D, float* out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* out[r] = F.cosine_similarity(x[r], y[r], eps) — similarity_score's equal-shape branch (scores.py:127). */
+int slb_cosine_rows(const float* x, const float* y, int64_t rows, int64_t D, float eps, float* out, void* stream);
+
+/* K7. out[c] = ((|mean_k normalize(V[c])|^2 - 1/k) / (k-1)) * k — scores.clarity_score (scores.py:19-47), one streaming
+ * pass over V (C, k, D) fp32. D % 4 == 0, D <= 2048. k = 1 gives inf/nan like the reference. */
+int slb_clarity(const float* V, int64_t C, int64_t k, int64_t D, float* out, void* stream);
+
+/* K8. out[c] = polysemanticity of neuron c (float64) — scores.polysemanticity_score (scores.py:132-185): sklearn
+ * KMeans(n_clusters=2, n_init, random_state) per neuron, 1 - cos(centre_1, centre_2); neurons whose smaller cluster has
+ * < 2 members take the fallback of scores.py:173-184 when replace_empty_clusters != 0.
+ * V (C, k, D) fp32 device, k <= 256. first_centers [n_init] / local_trial_uniforms [n_init][2] are HOST arrays: the
+ * data-independent draws of sklearn's RandomState stream (per init `choice(k)` then `uniform(size=2)`, _kmeans.py:231,249).
+ * workspace: 8-byte aligned device memory >= slb_polysem_workspace_bytes(C, k). */
+size_t slb_polysem_workspace_bytes(int64_t C, int64_t k);
+int slb_polysem_2means(const float* V, int64_t C, int64_t k, int64_t D, const int64_t* first_centers,
+                       const double* local_trial_uniforms, int n_init, int replace_empty_clusters, double* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* K9 (part). out[i] = max_j (S[i, j] - 2 * (j == row0 + i)) for a row block S (rows, cols) of the cosine matrix —
+ * scores.redundancy_score's `(sims - 2 I).max(-1)` (scores.py:78-80) without materialising the identity. */
+int slb_rowmax_offdiag(const float* S, int64_t rows, int64_t cols, int64_t row0, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * embed: the CLIP / SigLIP ViT image tower  (foundation_models/clip.py:103-163 -> open_clip, not vendored)
  * ---------------------------------------------------------------------------------------- */
 

@@ -11,6 +11,7 @@ Fixtures (inputs + the reference's outputs):
   collect_edge.npz      N < k, all-negative channel, exact zeros, NaN, k = 0
   actmax_kat.npz        the reference's own known-answer test (tests/component_visualization/test_activation_caching.py:14-30)
   scores.npz            clarity / similarity (all shape branches) / polysemanticity (incl. the small-cluster fallback)
+  scores_poly.npz       reference polysemanticity / clarity of the seeded cases of tests/polysem_cases.py (outputs only)
   cache_format/         one ActMaxCache.store() directory written by the reference (file names, keys, metadata)
 """
 
@@ -185,6 +186,25 @@ def gen_scores():
     np.savez_compressed(GOLD / "scores.npz", **out)
 
 
+def gen_scores_poly():
+    """Larger polysemanticity cases, inputs regenerated from seeds by the tests (only the reference's outputs are
+    stored): see tests/polysem_cases.py for the generators."""
+    import warnings
+
+    from semanticlens import scores as S
+    from tests.polysem_cases import CASES, make_case
+
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name in CASES:
+            V = torch.from_numpy(make_case(name))
+            out[f"{name}.poly"] = S.polysemanticity_score(V).numpy()
+            out[f"{name}.poly_noreplace"] = S.polysemanticity_score(V, replace_empty_clusters=False).numpy()
+            out[f"{name}.clarity"] = S.clarity_score(V).numpy()
+    np.savez_compressed(GOLD / "scores_poly.npz", **out)
+
+
 def main():
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     refshim.import_reference()
@@ -192,6 +212,7 @@ def main():
     gen_collect()
     gen_cache_format()
     gen_scores()
+    gen_scores_poly()
     for f in sorted(GOLD.rglob("*")):
         if f.is_file():
             print(f"{f.relative_to(ROOT)}  {f.stat().st_size} B")

@@ -92,10 +92,78 @@ def bench_collect(batch):
     print(json.dumps({"kernel": "torch.copy", "case": "rn50.layer1", "ms_median": round(med, 4), "GBps_rw": round(2 * by / med / 1e6, 1)}), flush=True)
 
 
+def bench_gemm(batch):
+    """K4 on the GEMM shapes of the ViT towers (rows = batch * tokens) and K6 at cfg-5 size."""
+    pk = peaks()
+    from semanticlens_b200 import _native as N
+
+    cases = {
+        "vitb32.qkv": (batch * 50, 2304, 768), "vitb32.out": (batch * 50, 768, 768),
+        "vitb32.fc": (batch * 50, 3072, 768), "vitb32.proj": (batch * 50, 768, 3072),
+        "vitl14.qkv": (64 * 257, 3072, 1024), "vitl14.fc": (64 * 257, 4096, 1024), "vitl14.proj": (64 * 257, 1024, 4096),
+        "square.8192": (8192, 8192, 8192),
+    }
+    for name, (M, Nn, K) in cases.items():
+        a = ops.split_planes(torch.randn(M, K, device="cuda"))
+        w = ops.split_planes(torch.randn(Nn, K, device="cuda") * 0.02)
+        out = torch.empty(M, Nn, device="cuda")
+        for passes in (3, 1):
+            med, best = time_cuda(lambda: ops.gemm_split(a, w, passes=passes, out_f32=out))
+            tf = 2 * M * Nn * K * passes / med / 1e9
+            print(json.dumps({"kernel": "K4 gemm_split", "case": name, "M": M, "N": Nn, "K": K, "passes": passes,
+                              "ms_median": round(med, 4), "ms_best": round(best, 4), "issued_TFLOPs": round(tf, 1),
+                              "fp32_equiv_TFLOPs": round(tf / passes, 1),
+                              "frac_of_measured_bf16": round(tf / pk["bf16_tflops"], 3)}), flush=True)
+        del a, w, out
+    x, y = torch.randn(10000, 512, device="cuda"), torch.randn(65536, 512, device="cuda")
+    med, best = time_cuda(lambda: ops.cosine_gemm(x, y), warmup=2, iters=5)
+    fl = 2 * 10000 * 65536 * 512 * 3
+    print(json.dumps({"kernel": "K6 cosine_gemm", "case": "cfg5 10000x65536x512", "ms_median": round(med, 3),
+                      "issued_TFLOPs": round(fl / med / 1e9, 1), "out_write_GBps": round(10000 * 65536 * 4 / med / 1e6, 1)}), flush=True)
+
+
+def bench_scores():
+    pk = peaks()
+    V = torch.randn(4096, 256, 512, device="cuda")  # 2.1 GB slab of the cfg-5 concept DB (larger than L2)
+    med, best = time_cuda(lambda: ops.clarity(V), warmup=2, iters=5)
+    by = V.numel() * 4
+    print(json.dumps({"kernel": "K7 clarity", "case": "4096x256x512", "ms_median": round(med, 3), "GBps": round(by / med / 1e6, 1),
+                      "frac_of_measured_hbm": round(by / med / 1e6 / pk["hbm_gbs"], 3)}), flush=True)
+    Vp = V[:1184]
+    med, best = time_cuda(lambda: ops.polysem_2means(Vp), warmup=1, iters=3)
+    by = Vp.numel() * 4
+    print(json.dumps({"kernel": "K8 polysem_2means", "case": "1184x256x512", "ms_median": round(med, 3),
+                      "us_per_neuron": round(med * 1e3 / 1184, 2), "GBps": round(by / med / 1e6, 1),
+                      "frac_of_measured_hbm": round(by / med / 1e6 / pk["hbm_gbs"], 4)}), flush=True)
+    V20 = torch.randn(3904, 20, 512, device="cuda")
+    med, best = time_cuda(lambda: ops.polysem_2means(V20), warmup=1, iters=3)
+    print(json.dumps({"kernel": "K8 polysem_2means", "case": "cfg2 db 3904x20x512", "ms_median": round(med, 3),
+                      "us_per_neuron": round(med * 1e3 / 3904, 2)}), flush=True)
+
+
+def bench_embed(batch):
+    from semanticlens_b200.foundation_models import OpenClip
+
+    for url, B in (("ViT-B-32", batch), ("ViT-B-16", 128), ("ViT-L-14", 64)):
+        fm = OpenClip(url, device="cuda", load_weights=False, seed=1)
+        S = fm.cfg.image_size
+        u8 = torch.randint(0, 255, (B, 3, S, S), dtype=torch.uint8, device="cuda")
+        med, best = time_cuda(lambda: fm.encode_image(fm.preprocess(u8)), warmup=2, iters=5)
+        print(json.dumps({"kernel": "embed tower", "case": url, "batch": B, "ms_median": round(med, 3),
+                          "images_per_s": round(B / med * 1e3, 1)}), flush=True)
+        del fm
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["collect"])
+    ap.add_argument("what", choices=["collect", "gemm", "scores", "embed"])
     ap.add_argument("--batch", type=int, default=256)
     a = ap.parse_args()
     if a.what == "collect":
         bench_collect(a.batch)
+    elif a.what == "gemm":
+        bench_gemm(a.batch)
+    elif a.what == "scores":
+        bench_scores()
+    elif a.what == "embed":
+        bench_embed(a.batch)

@@ -46,6 +46,17 @@ _PROTOS = {
     ),
     "slb_topk_merge_lists": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "slb_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "slb_normalize_split_rows": (c_int, [c_void_p, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "slb_cosine_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "slb_cosine_gemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "slb_cosine_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p]),
+    "slb_clarity": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "slb_polysem_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "slb_polysem_2means": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
+    "slb_rowmax_offdiag": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "slb_split_planes": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "slb_gemm_split": (
         c_int,

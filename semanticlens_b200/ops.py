@@ -334,3 +334,162 @@ def attention_packed(qkv: torch.Tensor, heads: int, fmt: int | None = None):
                                      float(dh) ** -0.5, fmt or 0, N.ptr(out), N.ptr(planes), N.stream_ptr(qkv.device))
     N.check(rc, "slb_attention_small")
     return out if fmt is None else planes
+
+
+# ------------------------------------------------------------------------------------------------
+# analyze: scores
+# ------------------------------------------------------------------------------------------------
+def _pad64(d: int) -> int:
+    return (d + 63) // 64 * 64
+
+
+def normalize_split_rows(x: torch.Tensor, eps: float = 1e-12, fmt: int = N.PLANE_F16) -> torch.Tensor:
+    """F.normalize(x, dim=-1) of a (rows, D) fp32 tensor, emitted as GEMM operand planes (2, rows, pad64(D))."""
+    lib = N.load(require_device=True)
+    N.require_cuda(x, "x")
+    assert x.ndim == 2 and x.dtype == torch.float32
+    x = x.contiguous()
+    rows, D = x.shape
+    planes = torch.empty((2, rows, _pad64(D)), dtype=PLANE_DTYPES[fmt], device=x.device)
+    with _dev_guard(x):
+        rc = lib.slb_normalize_split_rows(x.data_ptr(), rows, D, eps, fmt, planes.data_ptr(), None, N.stream_ptr(x.device))
+    N.check(rc, "slb_normalize_split_rows")
+    return planes
+
+
+def cosine_gemm(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """K6: normalize(x) @ normalize(y).T for (M, D) and (N, D) fp32 CUDA tensors -> (M, N) fp32."""
+    lib = N.load(require_device=True)
+    N.require_cuda(x, "x")
+    N.require_cuda(y, "y")
+    assert x.ndim == 2 and y.ndim == 2 and x.shape[1] == y.shape[1], (x.shape, y.shape)
+    x = x.detach().to(torch.float32).contiguous()
+    y = y.detach().to(torch.float32).contiguous()
+    M, D = x.shape
+    Nn = y.shape[0]
+    n_pad = (Nn + 7) // 8 * 8
+    if n_pad != Nn:  # the GEMM writes 16-byte vectors: pad y with zero rows, slice the result
+        y = torch.cat([y, torch.zeros((n_pad - Nn, D), dtype=y.dtype, device=y.device)])
+    out = torch.empty((M, n_pad), dtype=torch.float32, device=x.device)
+    if M == 0 or Nn == 0:
+        return out[:, :Nn]
+    need = lib.slb_cosine_gemm_workspace_bytes(M, n_pad, D)
+    ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+    tm = _timer.begin() if _timer else None
+    with _dev_guard(x):
+        rc = lib.slb_cosine_gemm(x.data_ptr(), M, y.data_ptr(), n_pad, D, out.data_ptr(), ws.data_ptr(), need,
+                                 N.stream_ptr(x.device))
+    if _timer:
+        _timer.end("K6 cosine_gemm", tm, 4 * (M * D + n_pad * D + M * n_pad), 2 * M * n_pad * _pad64(D) * 3)
+    N.check(rc, "slb_cosine_gemm")
+    return out if n_pad == Nn else out[:, :Nn].contiguous()
+
+
+def cosine_rows(x: torch.Tensor, y: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """F.cosine_similarity(x, y, dim=-1) for equal-shape fp32 CUDA tensors."""
+    lib = N.load(require_device=True)
+    N.require_cuda(x, "x")
+    N.require_cuda(y, "y")
+    assert x.shape == y.shape
+    x = x.detach().to(torch.float32).contiguous()
+    y = y.detach().to(torch.float32).contiguous()
+    D = x.shape[-1]
+    rows = x.numel() // D if D else 0
+    out = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
+    if rows:
+        with _dev_guard(x):
+            rc = lib.slb_cosine_rows(x.data_ptr(), y.data_ptr(), rows, D, eps, out.data_ptr(), N.stream_ptr(x.device))
+        N.check(rc, "slb_cosine_rows")
+    return out
+
+
+def clarity(V: torch.Tensor) -> torch.Tensor:
+    """K7: clarity_score of a (..., k, D) fp32 CUDA tensor -> (...,) fp32."""
+    lib = N.load(require_device=True)
+    N.require_cuda(V, "V")
+    assert V.ndim >= 2
+    V = V.detach().to(torch.float32).contiguous()
+    k, D = V.shape[-2], V.shape[-1]
+    C = V.numel() // (k * D) if k * D else 0
+    out = torch.empty(V.shape[:-2], dtype=torch.float32, device=V.device)
+    if C:
+        tm = _timer.begin() if _timer else None
+        with _dev_guard(V):
+            rc = lib.slb_clarity(V.data_ptr(), C, k, D, out.data_ptr(), N.stream_ptr(V.device))
+        if _timer:
+            _timer.end("K7 clarity", tm, V.numel() * 4)
+        N.check(rc, "slb_clarity")
+    return out
+
+
+def kmeanspp_draws(k: int, seed: int, n_init: int = 10):
+    """The data-independent draws of sklearn's k-means++ for n_clusters=2 (host side of K8): KMeans.fit creates
+    ``RandomState(seed)`` once per fit and every init consumes ``choice(k, p=uniform)`` (first centre) then
+    ``uniform(size=2)`` (the two local trials); nothing else touches the stream."""
+    import numpy as np
+
+    rs = np.random.RandomState(seed)
+    p = np.ones(k, dtype=np.float64)
+    p = p / p.sum()
+    first = np.empty(n_init, dtype=np.int64)
+    rand = np.empty((n_init, 2), dtype=np.float64)
+    for i in range(n_init):
+        first[i] = rs.choice(k, p=p)
+        rand[i] = rs.uniform(size=2)
+    return first, rand
+
+
+def polysem_2means(V: torch.Tensor, random_state: int = 123, replace_empty_clusters: bool = True,
+                   n_init: int = 10) -> torch.Tensor:
+    """K8: polysemanticity of every neuron of a (C, k, D) fp32 CUDA tensor -> (C,) float64."""
+    lib = N.load(require_device=True)
+    N.require_cuda(V, "V")
+    assert V.ndim == 3
+    V = V.detach().to(torch.float32).contiguous()
+    C, k, D = V.shape
+    out = torch.empty((C,), dtype=torch.float64, device=V.device)
+    if C == 0:
+        return out
+    if k == 0 or D == 0:
+        raise ValueError("polysemanticity_score needs at least one sample and one feature per neuron")
+    first, rand = kmeanspp_draws(k, random_state, n_init)
+    need = lib.slb_polysem_workspace_bytes(C, k)
+    if need == 0:
+        raise N.SlbError(f"polysemanticity kernel supports at most 256 examples per neuron (got {k})")
+    ws = torch.empty(need, dtype=torch.uint8, device=V.device)
+    tm = _timer.begin() if _timer else None
+    with _dev_guard(V):
+        rc = lib.slb_polysem_2means(V.data_ptr(), C, k, D, first.ctypes.data, rand.ctypes.data, n_init,
+                                    1 if replace_empty_clusters else 0, out.data_ptr(), ws.data_ptr(), need,
+                                    N.stream_ptr(V.device))
+    if _timer:
+        _timer.end("K8 polysem_2means", tm, V.numel() * 4)
+    N.check(rc, "slb_polysem_2means")
+    return out
+
+
+def redundancy(cones: torch.Tensor, row_block: int = 8192) -> torch.Tensor:
+    """K9: mean_i max_{j != i} cos(cones_i, cones_j) for a (n, D) fp32 CUDA tensor -> 0-d fp32 tensor.
+
+    The n x n cosine matrix is produced in row blocks by the tensor-core GEMM and reduced by a row-max kernel, so at
+    most row_block x n floats exist at a time."""
+    lib = N.load(require_device=True)
+    N.require_cuda(cones, "cones")
+    assert cones.ndim == 2
+    cones = cones.detach().to(torch.float32).contiguous()
+    n, D = cones.shape
+    n_pad = (n + 7) // 8 * 8
+    yp = normalize_split_rows(cones)
+    if n_pad != n:
+        yp = torch.cat([yp, torch.zeros((2, n_pad - n, yp.shape[2]), dtype=yp.dtype, device=yp.device)], 1).contiguous()
+    rowmax = torch.empty((n,), dtype=torch.float32, device=cones.device)
+    for r0 in range(0, n, row_block):
+        r1 = min(n, r0 + row_block)
+        xp = yp[:, r0:r1].contiguous()
+        S, _ = gemm_split(xp, yp, passes=3)
+        with _dev_guard(cones):
+            # padded columns hold cos = 0 and must not take part in the max: pass the true column count via a view
+            Sv = S if n_pad == n else S[:, :n].contiguous()
+            rc = lib.slb_rowmax_offdiag(Sv.data_ptr(), r1 - r0, n, r0, rowmax[r0:r1].data_ptr(), N.stream_ptr(cones.device))
+        N.check(rc, "slb_rowmax_offdiag")
+    return rowmax.mean()
