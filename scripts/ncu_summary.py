@@ -57,8 +57,8 @@ def launches(path: str):
     print("| ms | share | launches | avg us | grid | block | kernel |\n|---:|---:|---:|---:|---|---|---|")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"| {v[1] / 1e6:.3f} | {100 * v[1] / tot:.2f}% | {v[0]} | {v[1] / v[0] / 1e3:.1f} | {v[2]} | {v[3]} | `{k}` |")
-    ours = {k: v for k, v in agg.items() if "unnamed" in k and ("agg_" in k or "topk" in k or "slb" in k or "gather_rows" in k)
-            or "slb_" in k}
+    # every kernel of libslb200 lives in an anonymous namespace; torch's own anonymous kernels carry an `at::` prefix
+    ours = {k: v for k, v in agg.items() if "<unnamed>::" in k and "at::" not in k and "cudnn" not in k}
     if ours:
         t = sum(v[1] for v in ours.values())
         print(f"\nlibslb200 kernels: {t / 1e6:.3f} ms = {100 * t / tot:.2f}% of the listed device time")

@@ -76,8 +76,9 @@ def exchange_states(
     _, R = world()
     shapes = [tuple(v.shape) for v, _ in states]
     mine = pack_states(states)
-    gathered = torch.empty((R, mine.numel()), dtype=torch.uint8, device=mine.device)
-    dist.all_gather_into_tensor(gathered, mine, group=group)
+    flat = torch.empty(R * mine.numel(), dtype=torch.uint8, device=mine.device)  # 1-D: valid for nccl and gloo
+    dist.all_gather_into_tensor(flat, mine, group=group)
+    gathered = flat.view(R, mine.numel())
     per_rank = [unpack_states(gathered[r], shapes) for r in range(R)]
     out = []
     for li in range(len(states)):
@@ -116,6 +117,6 @@ def all_gather_rows(local: torch.Tensor, shard: Shard, n_total: int, group=None)
     if local.shape[0] < per:
         padded = torch.zeros((per, D), dtype=local.dtype, device=local.device)
         padded[: local.shape[0]] = local
-    out = torch.empty((R * per, D), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
-    return out[:n_total]
+    out = torch.empty(R * per * D, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded.contiguous().view(-1), group=group)
+    return out.view(R * per, D)[:n_total]
