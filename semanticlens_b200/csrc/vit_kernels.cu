@@ -8,7 +8,12 @@
 // write their result directly as split planes, the A-operand format of the next GEMM.
 #include "tc_common.cuh"
 
+#include <stdlib.h>
 #include <algorithm>
+
+int slb_attention_mma_dh64(const float* q, int64_t q_bs, int64_t q_rs, const float* k, const float* v, int64_t kv_bs,
+                           int64_t kv_rs, int64_t B, int64_t Tq, int64_t Tk, int64_t H, float scale, int plane_fmt,
+                           float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st);
 
 namespace {
 
@@ -314,11 +319,20 @@ extern "C" int slb_attention_small(const float* q, int64_t q_batch_stride, int64
     SLB_REQUIRE(B >= 0 && Tq > 0 && Tk > 0 && H > 0 && dh > 0, SLB_EINVAL, "slb_attention_small: bad size");
     if (B == 0) return SLB_OK;
     SLB_REQUIRE(q && k && v && (out_f32 || out_planes), SLB_EINVAL, "slb_attention_small: null pointer");
-    SLB_REQUIRE(Tk <= 32 * kAttnMaxChunks, SLB_EUNSUPPORTED, "slb_attention_small: at most %d keys (got %lld)",
-                32 * kAttnMaxChunks, (long long)Tk);
     SLB_REQUIRE(dh % 4 == 0 && dh <= 128 && kv_row_stride % 4 == 0 && kv_batch_stride % 4 == 0 &&
                     ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0,
                 SLB_EUNSUPPORTED, "slb_attention_small: head_dim must be a multiple of 4 (<= 128), K/V 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // head_dim 64 (every CLIP / SigLIP tower): tensor-core path (attention_mma.cu); anything else: the SIMT kernel below
+    static const bool force_simt = [] { const char* e = getenv("SLB_ATTN_SIMT"); return e && e[0] == '1'; }();
+    if (dh == 64 && !force_simt && q_row_stride % 2 == 0 && q_batch_stride % 2 == 0 && ((uintptr_t)q % 8) == 0 &&
+        (Tk + 15) / 16 * 16 <= 400) {
+        uint16_t* lo = out_planes ? out_planes + B * Tq * H * dh : nullptr;
+        return slb_attention_mma_dh64(q, q_batch_stride, q_row_stride, k, v, kv_batch_stride, kv_row_stride, B, Tq, Tk, H,
+                                      scale, plane_fmt, out_f32, out_planes, lo, st);
+    }
+    SLB_REQUIRE(Tk <= 32 * kAttnMaxChunks, SLB_EUNSUPPORTED, "slb_attention_small: at most %d keys (got %lld)",
+                32 * kAttnMaxChunks, (long long)Tk);
     AttnParams p{};
     p.q = q; p.q_bs = q_batch_stride; p.q_rs = q_row_stride;
     p.k = k; p.v = v; p.kv_bs = kv_batch_stride; p.kv_rs = kv_row_stride;
@@ -330,7 +344,7 @@ extern "C" int slb_attention_small(const float* q, int64_t q_batch_stride, int64
     SLB_REQUIRE(smem <= 227 * 1024, SLB_EUNSUPPORTED, "slb_attention_small: K/V of one head do not fit shared memory");
     SLB_CUDA_OK(cudaFuncSetAttribute(attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SLB_REQUIRE(B * H <= 0x7FFFFFFF, SLB_EUNSUPPORTED, "slb_attention_small: grid too large");
-    attention_small_kernel<<<(unsigned)(B * H), kAttnWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    attention_small_kernel<<<(unsigned)(B * H), kAttnWarps * 32, smem, st>>>(p);
     SLB_LAUNCH_OK("attention_small");
     return SLB_OK;
 }

@@ -40,16 +40,19 @@ def test_layernorm_vs_torch(ops, rows, cols):
     assert rel_max(planes[0].double() + planes[1].double() / 2048, want) < 2e-6
 
 
-@pytest.mark.parametrize("B,T,H,dh", [(2, 50, 12, 64), (1, 257, 4, 64), (3, 17, 2, 32), (2, 197, 3, 64)])
-def test_attention_vs_torch(ops, B, T, H, dh):
+@pytest.mark.parametrize("B,T,H,dh,gain", [(2, 50, 12, 64, 1.0), (1, 257, 4, 64, 1.0), (3, 17, 2, 32, 1.0), (2, 197, 3, 64, 1.0),
+                                          (1, 1, 1, 64, 1.0), (2, 64, 2, 64, 1.0), (1, 65, 2, 64, 3.0), (1, 320, 1, 64, 2.0),
+                                          (70, 50, 12, 64, 4.0)])
+def test_attention_vs_torch(ops, B, T, H, dh, gain):
     W = H * dh
-    qkv = torch.randn(B, T, 3 * W)
+    qkv = torch.randn(B, T, 3 * W, generator=torch.Generator().manual_seed(T * 7 + H)) * gain
     q, k, v = (t.view(B, T, H, dh).transpose(1, 2).double() for t in qkv.split(W, -1))
     want = (torch.softmax(q @ k.transpose(-1, -2) * dh**-0.5, -1) @ v).transpose(1, 2).reshape(B, T, W)
     got = ops.attention_packed(qkv.cuda(), H)
-    assert rel_max(got, want) < 2e-6
+    tol = 2e-6 * max(1.0, gain)  # fp32 exp of logits with std ~ gain^2: the error of expf grows with |logit|
+    assert rel_max(got, want) < tol
     planes = ops.attention_packed(qkv.cuda(), H, fmt=0)
-    assert rel_max((planes[0].double() + planes[1].double() / 2048).view(B, T, W), want) < 2e-6
+    assert rel_max((planes[0].double() + planes[1].double() / 2048).view(B, T, W), want) < tol
 
 
 def tower_for(name, seed=3, fmt=0):
