@@ -103,7 +103,15 @@ def bench_gemm(batch):
         "vitl14.qkv": (64 * 257, 3072, 1024), "vitl14.fc": (64 * 257, 4096, 1024), "vitl14.proj": (64 * 257, 1024, 4096),
         "square.8192": (8192, 8192, 8192),
     }
+    import time
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from bench import Clocks
+
+    only = os.environ.get("SLB_BENCH_ONLY")
     for name, (M, Nn, K) in cases.items():
+        if only and only not in name:
+            continue
         a = ops.split_planes(torch.randn(M, K, device="cuda"))
         w = ops.split_planes(torch.randn(Nn, K, device="cuda") * 0.02)
         out = torch.empty(M, Nn, device="cuda")
@@ -114,6 +122,27 @@ def bench_gemm(batch):
                               "ms_median": round(med, 4), "ms_best": round(best, 4), "issued_TFLOPs": round(tf, 1),
                               "fp32_equiv_TFLOPs": round(tf / passes, 1),
                               "frac_of_measured_bf16": round(tf / pk["bf16_tflops"], 3)}), flush=True)
+        if name == "square.8192":
+            # sustained: ~1.5 s back to back with the SM clock sampled, to tell pipe utilisation from power capping
+            clk = Clocks(0)
+            time.sleep(0.3)
+            n = int(1500 / med)
+            torch.cuda.synchronize()
+            clk.begin()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                ops.gemm_split(a, w, passes=3, out_f32=out)
+            e1.record()
+            torch.cuda.synchronize()
+            clk.end()
+            ms = e0.elapsed_time(e1) / n
+            c = clk.stop()
+            tf = 2 * M * Nn * K * 3 / ms / 1e9
+            mhz = c.get("sm_mhz") or 0
+            print(json.dumps({"kernel": "K4 gemm_split", "case": name + " sustained", "ms": round(ms, 4), "issued_TFLOPs": round(tf, 1),
+                              "clocks": c, "tensor_pipe_util_at_clock": round(tf * 1e12 / (148 * 8192 * mhz * 1e6), 3) if mhz else None}),
+                  flush=True)
         del a, w, out
     x, y = torch.randn(10000, 512, device="cuda"), torch.randn(65536, 512, device="cuda")
     med, best = time_cuda(lambda: ops.cosine_gemm(x, y), warmup=2, iters=5)

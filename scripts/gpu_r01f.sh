@@ -1,0 +1,7 @@
+O=gpurun_out; mkdir -p $O
+timeout 400 python scripts/bench_kernels.py gemm > $O/r01f_micro_gemm_pair.jsonl 2> $O/r01f_micro_gemm_pair.err
+SLB_GEMM_SINGLE=1 timeout 400 python scripts/bench_kernels.py gemm > $O/r01f_micro_gemm_single.jsonl 2>&1
+timeout 900 python -m pytest tests/test_embed_gpu.py tests/test_scores_gpu.py -q -p no:cacheprovider > $O/r01f_pytest_embed.log 2>&1; tail -3 $O/r01f_pytest_embed.log
+timeout 300 python scripts/bench_kernels.py embed > $O/r01f_micro_embed.jsonl 2>&1
+cat $O/r01f_micro_gemm_pair.jsonl $O/r01f_micro_embed.jsonl
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r01f_launches_embed.csv python scripts/bench_kernels.py embed --batch 256 > $O/r01f_ncu_embed.log 2>&1

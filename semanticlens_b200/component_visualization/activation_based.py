@@ -62,6 +62,56 @@ def _batches(dataset, shard, batch_size, num_workers, device, collate_fn=None):
     return torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=False, num_workers=num_workers, **kw)
 
 
+class _DevicePrefetcher:
+    """Iterate ``batches`` with the host->device copy of batch i+1 in flight (on a side stream) while batch i is being
+    computed: pinned host tensors are copied with ``non_blocking=True`` on a copy stream and handed over with an event, so
+    the H2D time disappears behind the probed-model forward / the tower. Non-tensor items (lists of PIL images) pass
+    through untouched. Order and contents are exactly those of ``batches``."""
+
+    def __init__(self, batches, device):
+        self.batches, self.device = batches, torch.device(device)
+
+    def __len__(self):
+        return len(self.batches)
+
+    def _stage(self, item, stream):
+        if isinstance(item, torch.Tensor):
+            if item.is_cuda or not item.is_pinned():
+                return item, None
+            with torch.cuda.stream(stream):
+                dev = item.to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+            return dev, ev
+        if isinstance(item, (tuple, list)) and len(item) == 2 and isinstance(item[0], torch.Tensor) and item[0].ndim >= 3:
+            # an (images, labels) batch of dataset_model
+            first, ev = self._stage(item[0], stream)
+            return type(item)((first, *item[1:])), ev
+        return item, None
+
+    def __iter__(self):
+        if self.device.type != "cuda":
+            yield from self.batches
+            return
+        stream = torch.cuda.Stream(self.device)
+        it = iter(self.batches)
+        try:
+            nxt = self._stage(next(it), stream)
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev = nxt
+            try:
+                nxt = self._stage(next(it), stream)  # enqueue the next copy before handing out the current batch
+            except StopIteration:
+                nxt = None
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+                t = cur if isinstance(cur, torch.Tensor) else cur[0]
+                t.record_stream(torch.cuda.current_stream(self.device))
+            yield cur
+
+
 class MissingNameWarning(UserWarning):
     """A model or dataset has no ``.name``; a fallback derived from its ``repr`` names the cache directory."""
 
@@ -203,7 +253,8 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
                 self.actmax_cache.sample_idx_counter[layer] = shard.lo
         with self.actmax_cache.hook_context(self.model):
             for images, _ in tqdm(
-                dataloader, total=len(dataloader), desc="Collecting ActMax", disable=not self.show_progress
+                _DevicePrefetcher(dataloader, device), total=len(dataloader), desc="Collecting ActMax",
+                disable=not self.show_progress,
             ):
                 self.model(images.to(device, non_blocking=True))  # hooks enqueue K1+K2; nothing is copied back
 
@@ -249,7 +300,7 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
                           collate_fn=item_list_collate)
         embeds = []
         with tqdm(total=shard.hi - shard.lo, desc="Embedding Dataset", disable=not self.show_progress) as pbar:
-            for items in loader:
+            for items in _DevicePrefetcher(loader, self.device):
                 inputs = fm.preprocess(items)
                 embeds.append(fm.encode_image(inputs))
                 pbar.update(len(items))

@@ -17,6 +17,7 @@
 // tile i+1.
 #include "tc_common.cuh"
 
+#include <stdlib.h>
 #include <algorithm>
 
 namespace {
@@ -27,12 +28,13 @@ constexpr int kThreads = 192;
 
 template <int BN>
 struct Cfg {
-    static_assert(BN == 128, "two double-buffered accumulator pairs fill the 512 TMEM columns at BN = 128");
-    static constexpr int kStages = 3;
+    static_assert(BN == 128 || BN == 256, "main + correction accumulators: 2 buffers at BN = 128, 1 at BN = 256");
+    static constexpr int kAccBufs = BN == 128 ? 2 : 1;
+    static constexpr int kStages = BN == 128 ? 3 : 2;
     static constexpr int kABytes = 2 * BM * BK * 2;  // both planes
     static constexpr int kWBytes = 2 * BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kWBytes;
-    static constexpr int kTmemCols = 4 * BN;  // [buffer][main | corr][BN]
+    static constexpr int kTmemCols = 512;  // [buffer][main | corr][BN]
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -47,6 +49,7 @@ struct GemmParams {
     int epilogue;
     int passes;  // 3 or 1
     int fmt;     // plane format of A/W and of out_planes
+    unsigned int* dbg;  // SLB_GEMM_DEBUG=1: host-mapped words [cta][16] that a timed-out wait reports into (else null)
 };
 
 __device__ __forceinline__ float act_apply(float v, int epi) {
@@ -61,6 +64,81 @@ __device__ __forceinline__ float act_apply(float v, int epi) {
         }
         default:
             return v;
+    }
+}
+
+// Epilogue of one 32-column chunk of an accumulator row: TMEM -> registers -> scale / bias / activation / residual ->
+// global (fp32 and/or split planes). `taddr` addresses the main accumulator; the correction accumulator sits
+// `corr_off` columns further. Thread = one output row m, columns [nb, nb + 32).
+__device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr, int corr_off, int64_t m, bool row_ok,
+                                            float rs, int64_t nb, int fmt, float inv_s) {
+    uint32_t raw[32];
+    float v[32];
+    slb_tmem_ld_32x32(taddr, raw);
+    slb_tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+    if (p.passes == 3) {
+        slb_tmem_ld_32x32(taddr + corr_off, raw);
+        slb_tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(raw[j]), inv_s, v[j]);
+    }
+    if (!(row_ok && nb < p.N)) return;
+    const int ncols = (int)min((int64_t)32, p.N - nb);  // multiple of 8
+    if (p.row_scale) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= rs;
+    }
+    if (p.col_scale) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < ncols) v[j] *= __ldg(p.col_scale + nb + j);
+    }
+    if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < ncols) v[j] += __ldg(p.bias + nb + j);
+    }
+    if (p.epilogue != SLB_EPI_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], p.epilogue);
+    }
+    if (p.residual) {
+        const float4* r4 = reinterpret_cast<const float4*>(p.residual + m * p.N + nb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (4 * j < ncols) {
+                float4 r = r4[j];
+                v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+            }
+        }
+    }
+    if (p.out_f32) {
+        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + m * p.N + nb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (4 * j < ncols) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    if (p.out_planes) {
+        uint16_t* ph = p.out_planes + m * p.N + nb;
+        uint16_t* pl = ph + p.M * p.N;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (8 * j < ncols) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint16_t h0, l0, h1, l1;
+                    slb_split2(v[8 * j + 2 * q], fmt, h0, l0);
+                    slb_split2(v[8 * j + 2 * q + 1], fmt, h1, l1);
+                    h[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                    l[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                }
+                *reinterpret_cast<uint4*>(ph + 8 * j) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(pl + 8 * j) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+        }
     }
 }
 
@@ -154,8 +232,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
                 slb_umma_commit(&tfull[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
+                if (++acc == C::kAccBufs) { acc = 0; acc_phase ^= 1u; }
             }
         }
         __syncwarp();
@@ -174,83 +251,13 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const float rs = (p.row_scale && row_ok) ? p.row_scale[m] : 1.0f;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
-                uint32_t raw[32];
-                float v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
-                slb_tmem_ld_32x32(taddr, raw);
-                slb_tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                if (p.passes == 3) {
-                    slb_tmem_ld_32x32(taddr + BN, raw);
-                    slb_tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(raw[j]), inv_s, v[j]);
-                }
-                const int64_t nb = (int64_t)n0 + c * 32;
-                if (row_ok && nb < p.N) {
-                    const int ncols = (int)min((int64_t)32, p.N - nb);  // multiple of 8
-                    if (p.row_scale) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= rs;
-                    }
-                    if (p.col_scale) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncols) v[j] *= __ldg(p.col_scale + nb + j);
-                    }
-                    if (p.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncols) v[j] += __ldg(p.bias + nb + j);
-                    }
-                    if (p.epilogue != SLB_EPI_NONE) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], p.epilogue);
-                    }
-                    if (p.residual) {
-                        const float4* r4 = reinterpret_cast<const float4*>(p.residual + m * p.N + nb);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (4 * j < ncols) {
-                                float4 r = r4[j];
-                                v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-                            }
-                        }
-                    }
-                    if (p.out_f32) {
-                        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + m * p.N + nb);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (4 * j < ncols) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
-                    if (p.out_planes) {
-                        uint16_t* ph = p.out_planes + m * p.N + nb;
-                        uint16_t* pl = ph + p.M * p.N;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (8 * j < ncols) {
-                                uint32_t h[4], l[4];
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    uint16_t h0, l0, h1, l1;
-                                    slb_split2(v[8 * j + 2 * q], fmt, h0, l0);
-                                    slb_split2(v[8 * j + 2 * q + 1], fmt, h1, l1);
-                                    h[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                                    l[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                                }
-                                *reinterpret_cast<uint4*>(ph + 8 * j) = make_uint4(h[0], h[1], h[2], h[3]);
-                                *reinterpret_cast<uint4*>(pl + 8 * j) = make_uint4(l[0], l[1], l[2], l[3]);
-                            }
-                        }
-                    }
-                }
+                drain_chunk(p, taddr, BN, m, row_ok, rs, (int64_t)n0 + c * 32, fmt, inv_s);
             }
             slb_tc_fence_before();
             __syncwarp();
             if (lane == 0) slb_mbar_arrive(&tempty[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
+            if (++acc == C::kAccBufs) { acc = 0; acc_phase ^= 1u; }
         }
     }
 
@@ -259,6 +266,184 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1) {
         slb_tc_fence_after();
         slb_tmem_dealloc<C::kTmemCols>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): one 256 x 128 output tile per cluster of two CTAs on neighbouring SMs.
+//
+// Each CTA stages ITS half of both operands per k-block — A rows [m0 + 128 r, +128), W rows [n0 + 64 r, +64), both
+// planes: 48 KB instead of the 64 KB a lone CTA needs for a 128 x 128 tile — so the L2 -> shared-memory feed per MMA
+// cycle drops by 25 % and the ring deepens from 3 to 4 stages; the leader CTA's single MMA thread issues
+// tcgen05.mma.cta_group::2 (M = 256, N = 128, K = 16), which reads A and W from both CTAs' shared memory and writes
+// each CTA's 128 accumulator rows into that CTA's own tensor memory. Barriers:
+//   full[s]    leader only; the leader arms it with the pair's byte count, both CTAs' TMA loads complete on it
+//   empty[s]   in each CTA; tcgen05.commit multicast from the leader frees the stage in both CTAs
+//   tfull[a]   in each CTA; commit multicast after the tile's last k-block
+//   tempty[a]  leader only, 8 arrivals: the 4 epilogue warps of each CTA (the peer's arrive remotely)
+// ---------------------------------------------------------------------------------------------
+struct CfgPair {
+    static constexpr int BN = 128;
+    static constexpr int kStages = 4;
+    static constexpr int kABytes = 2 * BM * BK * 2;        // this CTA's 128 A rows, both planes
+    static constexpr int kWBytes = 2 * (BN / 2) * BK * 2;  // this CTA's 64 W rows, both planes
+    static constexpr int kStageBytes = kABytes + kWBytes;  // 48 KB
+    static constexpr int kTmemCols = 4 * BN;               // [buffer][main | corr][BN]
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 + 256;
+};
+
+// bounded wait: a protocol error must abort the kernel (trap -> CUDA error), never hang the device. On timeout
+// (~2 s) the waiting thread reports (site, tile, k-block, stage, parity) into the host-mapped debug words, if any.
+__device__ __noinline__ void wait_timed_out(unsigned int* dbg, int site, int t, int kb, int stage, uint32_t parity) {
+    if (dbg) {
+        unsigned int* d = dbg + (blockIdx.x & 7) * 32 + site * 6;
+        d[0] = 0xDEAD0000u | (unsigned)site; d[1] = (unsigned)t; d[2] = (unsigned)kb; d[3] = (unsigned)stage; d[4] = parity;
+        d[5] = (unsigned)(threadIdx.x);
+        __threadfence_system();
+    }
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity, unsigned int* dbg, int site, int t, int kb,
+                                                  int stage) {
+    if (slb_mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!slb_mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) wait_timed_out(dbg, site, t, kb, stage, parity);
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmParams p) {
+    using C = CfgPair;
+    constexpr int BN = C::BN;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::kStages * C::kStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + C::kStages;
+    uint64_t* tfull = bars + 2 * C::kStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = slb_cluster_ctarank();  // 0 = leader
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        slb_prefetch_tmap(&tmA);
+        slb_prefetch_tmap(&tmW);
+        for (int s = 0; s < C::kStages; ++s) {
+            slb_mbar_init(&full[s], 1);
+            slb_mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            slb_mbar_init(&tfull[a], 1);
+            slb_mbar_init(&tempty[a], 8);
+        }
+        slb_fence_mbar_init();
+    }
+    __syncwarp();  // barrier.cluster is .aligned: the warp must be converged
+    if (warp == 1) slb_tmem_alloc_pair<C::kTmemCols>(tmem_slot);
+    slb_tc_fence_before();
+    slb_cluster_sync();  // barriers of both CTAs are initialised and both allocations are done
+    slb_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_kb = (int)(p.K / BK);
+    const int tiles_n = (int)((p.N + BN - 1) / BN);
+    const int tiles_m = (int)((p.M + 2 * BM - 1) / (2 * BM));
+    const int total = tiles_m * tiles_n;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < total; t += num_clusters) {
+                const int m0 = (t / tiles_n) * (2 * BM) + (int)rank * BM;
+                const int n0 = (t % tiles_n) * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_bounded(&empty[stage], phase ^ 1u, p.dbg, 1, t, kb, stage);
+                    unsigned char* st = smem + (size_t)stage * C::kStageBytes;
+                    const uint32_t full_leader = slb_mapa(slb_smem_u32(&full[stage]), 0);
+                    if (leader) slb_mbar_arrive_expect_tx(&full[stage], 2u * (uint32_t)C::kStageBytes);
+                    slb_tma_load_3d_pair(st, &tmA, kb * BK, m0, 0, full_leader);
+                    slb_tma_load_3d_pair(st + C::kABytes, &tmW, kb * BK, n0, 0, full_leader);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            const uint32_t idesc = slb_umma_idesc_f16(p.fmt, 2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = cluster_id; t < total; t += num_clusters) {
+                mbar_wait_bounded(&tempty[acc], acc_phase ^ 1u, p.dbg, 2, t, -1, acc);
+                slb_tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_bounded(&full[stage], phase, p.dbg, 3, t, kb, stage);
+                    slb_tc_fence_after();
+                    const uint32_t a0 = slb_smem_u32(smem + (size_t)stage * C::kStageBytes);
+                    const uint32_t w0 = a0 + C::kABytes;
+#pragma unroll
+                    for (int pr = 0; pr < 3; ++pr) {
+                        if (pr < p.passes) {
+                            const uint32_t ab = a0 + (pr == 2 ? BM * BK * 2 : 0);
+                            const uint32_t wb = w0 + (pr == 1 ? (BN / 2) * BK * 2 : 0);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                slb_umma_f16_pair(d_tmem + (pr ? BN : 0), slb_umma_desc_sw128(ab + k * 32),
+                                                  slb_umma_desc_sw128(wb + k * 32), idesc,
+                                                  pr == 0 ? (kb | k) != 0 : (kb | (pr - 1) | k) != 0);
+                            }
+                        }
+                    }
+                    slb_umma_commit_pair(&empty[stage], 0b11);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                }
+                slb_umma_commit_pair(&tfull[acc], 0b11);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+        __syncwarp();
+    } else {
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int fmt = p.fmt;
+        const float inv_s = 1.0f / slb_plane_lo_scale(fmt);
+        for (int t = cluster_id; t < total; t += num_clusters) {
+            const int m0 = (t / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (t % tiles_n) * BN;
+            mbar_wait_bounded(&tfull[acc], acc_phase, p.dbg, 4, t, -1, acc);
+            slb_tc_fence_after();
+            const int64_t m = (int64_t)m0 + quarter * 32 + lane;
+            const bool row_ok = m < p.M;
+            const float rs = (p.row_scale && row_ok) ? p.row_scale[m] : 1.0f;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
+                drain_chunk(p, taddr, BN, m, row_ok, rs, (int64_t)n0 + c * 32, fmt, inv_s);
+            }
+            slb_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) slb_mbar_arrive_cluster(slb_mapa(slb_smem_u32(&tempty[acc]), 0));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    // neither CTA may exit (or free tensor memory) while its partner can still touch its shared / tensor memory
+    slb_tc_fence_before();
+    slb_cluster_sync();
+    if (warp == 1) {
+        slb_tc_fence_after();
+        slb_tmem_dealloc_pair<C::kTmemCols>(tmem_base);
     }
 }
 
@@ -289,6 +474,41 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams
     const int grid = (int)std::min<int64_t>(tiles, slb_sm_count());
     kern<<<grid, kThreads, C::kSmem, st>>>(tmA, tmW, p);
     SLB_LAUNCH_OK("gemm_split");
+    return SLB_OK;
+}
+
+unsigned int* g_dbg_host = nullptr;  // SLB_GEMM_DEBUG=1 only
+unsigned int* g_dbg_dev = nullptr;
+
+int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p_in, cudaStream_t st) {
+    using C = CfgPair;
+    GemmParams p = p_in;
+    static const bool debug = [] { const char* e = getenv("SLB_GEMM_DEBUG"); return e && e[0] == '1'; }();
+    if (debug) {
+        if (!g_dbg_host) {
+            SLB_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&g_dbg_host), 8 * 32 * 4, cudaHostAllocMapped));
+            SLB_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_dbg_dev), g_dbg_host, 0));
+        }
+        for (int i = 0; i < 8 * 32; ++i) g_dbg_host[i] = 0;
+        p.dbg = g_dbg_dev;
+    }
+    SLB_CUDA_OK(cudaFuncSetAttribute(gemm_split_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    const int64_t tiles = slb_ceil_div(p.M, 2 * BM) * slb_ceil_div(p.N, C::BN);
+    const int clusters = (int)std::min<int64_t>(tiles, slb_sm_count() / 2);
+    gemm_split_pair_kernel<<<2 * clusters, kThreads, C::kSmem, st>>>(tmA, tmW, p);
+    SLB_LAUNCH_OK("gemm_split_pair");
+    if (debug) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        fprintf(stderr, "[slb gemm_pair debug] M=%lld N=%lld K=%lld grid=%d sync: %s\n", (long long)p.M, (long long)p.N,
+                (long long)p.K, 2 * clusters, cudaGetErrorString(e));
+        for (int c = 0; c < 8; ++c)
+            for (int site = 1; site <= 4; ++site) {
+                const unsigned int* d = g_dbg_host + c * 32 + site * 6;
+                if (d[0]) fprintf(stderr, "  cta%%8=%d site=%d (1 empty,2 tempty,3 full,4 tfull) tile=%u kb=%d stage=%u parity=%u tid=%u\n", c,
+                                  site, d[1], (int)d[2], d[3], d[4], d[5]);
+            }
+        if (e != cudaSuccess) { slb_set_error("gemm_split_pair failed: %s", cudaGetErrorString(e)); return SLB_ECUDA; }
+    }
     return SLB_OK;
 }
 
@@ -369,11 +589,21 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
     p.bias = bias; p.residual = residual; p.row_scale = row_scale; p.col_scale = col_scale;
     p.out_f32 = out_f32; p.out_planes = out_planes;
     p.epilogue = epilogue; p.passes = passes; p.fmt = plane_fmt;
+    // Kernel choice (measured on B200, profiles/r01_gemm_variants.jsonl): the CTA-pair kernel (256 x 128 tiles, 4-stage
+    // ring) wins when W is large (cosine GEMM N = 65536: 878 vs 781 TFLOP/s; 8192^3: 1108 vs 1092 burst, 959 vs 910
+    // sustained under the power cap), the one-CTA kernel (128 x 128 tiles) on the ViT shapes (N <= 3072: 1083 vs 1050,
+    // N = 768: 913 vs 813). SLB_GEMM_SINGLE=1 / SLB_GEMM_PAIR=1 force one of them (A/B measurements).
+    static const bool force_single = [] { const char* e = getenv("SLB_GEMM_SINGLE"); return e && e[0] == '1'; }();
+    static const bool force_pair = [] { const char* e = getenv("SLB_GEMM_PAIR"); return e && e[0] == '1'; }();
+    const bool pair = !force_single && M > BM && (force_pair || N >= 4096);
     CUtensorMap tmA, tmW;
     int rc = slb_make_plane_map(&tmA, a_planes, M, K, 2, BM);
     if (rc != SLB_OK) return rc;
-    rc = slb_make_plane_map(&tmW, w_planes, N, K, 2, 128);
+    static const bool bn256 = [] { const char* e = getenv("SLB_GEMM_BN256"); return e && e[0] == '1'; }();  // experiment
+    rc = slb_make_plane_map(&tmW, w_planes, N, K, 2, pair ? 64 : (bn256 ? 256 : 128));
     if (rc != SLB_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pair) return launch_gemm_pair(tmA, tmW, p, st);
+    if (bn256) return launch_gemm<256>(tmA, tmW, p, st);
     return launch_gemm<128>(tmA, tmW, p, st);
 }

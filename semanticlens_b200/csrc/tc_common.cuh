@@ -93,6 +93,72 @@ __device__ __forceinline__ void slb_umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// device: thread-block clusters and CTA pairs (cta_group::2)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t slb_cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void slb_cluster_sync() {  // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the location `smem_addr` (a shared::cta address of this CTA) in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t slb_mapa(uint32_t smem_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void slb_mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// TMA tile load issued by either CTA of a pair into ITS OWN shared memory; the bytes are counted on the mbarrier at
+// shared::cluster address `bar_cluster` (the leader CTA's "full" barrier).
+__device__ __forceinline__ void slb_tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, int c0, int c1, int c2,
+                                                     uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(slb_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster)
+        : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void slb_tmem_alloc_pair(uint32_t* smem_slot) {  // the same warp of BOTH CTAs of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slb_smem_u32(smem_slot)),
+                 "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void slb_tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// one MMA across the CTA pair: D (256 x N, rows split over the two CTAs' TMEM) += A (256 x 16) * B (N x 16)^T, issued by
+// one thread of the leader CTA; descriptors are shared::cta offsets valid in both CTAs
+__device__ __forceinline__ void slb_umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                  bool accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in every CTA of `cta_mask` once all prior MMAs completed
+__device__ __forceinline__ void slb_umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     slb_smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i), columns [col, col+32)
 __device__ __forceinline__ void slb_tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(

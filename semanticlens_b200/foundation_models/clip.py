@@ -59,7 +59,8 @@ class OpenClip(AbstractVLM):
                 logger.warning("pretrained='%s' cannot be downloaded here; using random weights (seed %d)", pretrained, seed)
             sd = vit.random_state_dict(self.cfg, seed)
         self.model = vit.VitTower(self.cfg, sd, device, fmt)
-        self._pin: torch.Tensor | None = None
+        self._pin: list = [(None, None), (None, None)]  # (pinned staging buffer, event of its last H2D copy)
+        self._pin_next = 0
 
     def __repr__(self):
         return f"{self.__class__.__name__}(url='{self.url}', model=VitTower[B200])"
@@ -92,12 +93,23 @@ class OpenClip(AbstractVLM):
             raise N.SlbError("OpenClip.preprocess runs on the GPU: move the model with .to('cuda') first")
         if not u8.is_cuda:
             if not u8.is_pinned():
-                if self._pin is None or self._pin.numel() < u8.numel():
-                    self._pin = torch.empty(u8.numel(), dtype=torch.uint8, pin_memory=True)
-                staged = self._pin[: u8.numel()].view(u8.shape)
+                # two pinned staging buffers used alternately: a buffer is rewritten only after the asynchronous copy
+                # that last read it has completed (its event), so the host never races the DMA engine
+                slot = self._pin_next
+                self._pin_next ^= 1
+                buf, ev = self._pin[slot]
+                if ev is not None:
+                    ev.synchronize()
+                if buf is None or buf.numel() < u8.numel():
+                    buf = torch.empty(u8.numel(), dtype=torch.uint8, pin_memory=True)
+                staged = buf[: u8.numel()].view(u8.shape)
                 staged.copy_(u8)
-                u8 = staged
-            u8 = u8.to(dev, non_blocking=True)
+                u8 = staged.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                self._pin[slot] = (buf, ev)
+            else:
+                u8 = u8.to(dev, non_blocking=True)
         return ops.u8_to_f32_norm(u8, self.cfg.mean, self.cfg.std)
 
     def _to_u8_batch(self, img) -> torch.Tensor:

@@ -99,3 +99,12 @@ def test_pack_unpack_roundtrip():
     back = sdist.unpack_states(buf, [tuple(v.shape) for v, _ in states])
     for (v, i), (v2, i2) in zip(states, back):
         assert torch.equal(v.view(torch.int16), v2.view(torch.int16)) and torch.equal(i, i2)
+
+
+def test_prefetcher_is_a_passthrough_without_cuda():
+    from semanticlens_b200.component_visualization.activation_based import _DevicePrefetcher
+
+    batches = [(torch.full((2, 3, 4, 4), float(i)), torch.zeros(2)) for i in range(5)]
+    got = list(_DevicePrefetcher(batches, "cpu"))
+    assert len(got) == 5 and all(torch.equal(a[0], b[0]) for a, b in zip(got, batches))
+    assert list(_DevicePrefetcher([], "cpu")) == []

@@ -127,3 +127,22 @@ def test_preprocess_matches_reference_transform_on_pil():
                     T.Normalize(fm.cfg.mean, fm.cfg.std)])
     want = torch.stack([tf(im) for im in ims])
     assert torch.equal(fm.preprocess(ims).cpu(), want)
+
+
+def test_preprocess_staging_buffers_do_not_race_the_copy_engine():
+    """Unpinned host batches go through pinned staging buffers; with the GPU busy (copies lag behind the host), a reused
+    buffer must not be overwritten before its H2D copy has completed."""
+    from semanticlens_b200.foundation_models import OpenClip
+
+    fm = OpenClip("ViT-B-32", device="cuda", load_weights=False, seed=1)
+    g = torch.Generator().manual_seed(0)
+    batches = [torch.randint(0, 255, (48, 3, 224, 224), generator=g, dtype=torch.uint8) for _ in range(6)]
+    busy = torch.randn(8192, 8192, device="cuda")
+    for _ in range(20):
+        busy = busy @ busy * 1e-4  # keep the stream occupied so that the async copies queue up
+    outs = [fm.preprocess(b) for b in batches]
+    torch.cuda.synchronize()
+    mean = torch.tensor(fm.cfg.mean).view(1, 3, 1, 1)
+    std = torch.tensor(fm.cfg.std).view(1, 3, 1, 1)
+    for b, o in zip(batches, outs):
+        assert torch.equal(o.cpu(), (b.float() / 255.0 - mean) / std)

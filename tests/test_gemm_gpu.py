@@ -18,7 +18,7 @@ def rel_err(got, want):
 
 
 SHAPES = [(128, 128, 64), (128, 128, 128), (256, 384, 768), (100, 136, 192), (1000, 768, 768), (12800, 2304, 768),
-          (300, 512, 3072), (5, 8, 64)]
+          (300, 512, 3072), (5, 8, 64), (129, 72, 64), (257, 128, 64), (512, 1000, 128), (16448, 1024, 256)]
 
 
 @pytest.mark.parametrize("fmt,tol", [(0, 8e-6), (1, 6e-5)])
