@@ -63,10 +63,13 @@ def _batches(dataset, shard, batch_size, num_workers, device, collate_fn=None):
 
 
 class _DevicePrefetcher:
-    """Iterate ``batches`` with the host->device copy of batch i+1 in flight (on a side stream) while batch i is being
-    computed: pinned host tensors are copied with ``non_blocking=True`` on a copy stream and handed over with an event, so
-    the H2D time disappears behind the probed-model forward / the tower. Non-tensor items (lists of PIL images) pass
-    through untouched. Order and contents are exactly those of ``batches``."""
+    """Iterate ``batches`` with the host->device copy of batch i+1 in flight (on a copy stream) while batch i is being
+    computed, so the H2D time disappears behind the probed-model forward / the tower.
+
+    Pinned host tensors are copied into one of TWO device buffers owned by the prefetcher (allocated once: no caching-
+    allocator traffic, no ``cudaMalloc`` in the loop); events order the hand-over in both directions (copy done ->
+    consumer may read; consumer done -> buffer may be overwritten). Unpinned tensors and non-tensor items (lists of PIL
+    images) pass through untouched. Order and contents are exactly those of ``batches``."""
 
     def __init__(self, batches, device):
         self.batches, self.device = batches, torch.device(device)
@@ -74,42 +77,63 @@ class _DevicePrefetcher:
     def __len__(self):
         return len(self.batches)
 
-    def _stage(self, item, stream):
+    @staticmethod
+    def _tensor_of(item):
         if isinstance(item, torch.Tensor):
-            if item.is_cuda or not item.is_pinned():
-                return item, None
-            with torch.cuda.stream(stream):
-                dev = item.to(self.device, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(stream)
-            return dev, ev
+            return item
         if isinstance(item, (tuple, list)) and len(item) == 2 and isinstance(item[0], torch.Tensor) and item[0].ndim >= 3:
-            # an (images, labels) batch of dataset_model
-            first, ev = self._stage(item[0], stream)
-            return type(item)((first, *item[1:])), ev
-        return item, None
+            return item[0]  # an (images, labels) batch of dataset_model
+        return None
 
     def __iter__(self):
         if self.device.type != "cuda":
             yield from self.batches
             return
-        stream = torch.cuda.Stream(self.device)
+        dev = self.device
+        copy_stream = torch.cuda.Stream(dev)
+        bufs: list = [None, None]
+        reusable: list = [None, None]  # event on the compute stream after which buffer k may be overwritten
+
+        def stage(item, k):
+            t = self._tensor_of(item)
+            if t is None or t.is_cuda or not t.is_pinned():
+                return item, None
+            cur_stream = torch.cuda.current_stream(dev)
+            if bufs[k] is None or bufs[k].numel() < t.numel() or bufs[k].dtype != t.dtype:
+                bufs[k] = torch.empty(t.numel(), dtype=t.dtype, device=dev)
+                fresh = torch.cuda.Event()
+                fresh.record(cur_stream)  # the block may have been used by earlier work of the compute stream
+                copy_stream.wait_event(fresh)
+            if reusable[k] is not None:
+                copy_stream.wait_event(reusable[k])
+            dst = bufs[k][: t.numel()].view(t.shape)
+            with torch.cuda.stream(copy_stream):
+                dst.copy_(t, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            out = dst if isinstance(item, torch.Tensor) else type(item)((dst, *item[1:]))
+            return out, ready
+
         it = iter(self.batches)
         try:
-            nxt = self._stage(next(it), stream)
+            nxt = stage(next(it), 0)
         except StopIteration:
             return
+        k = 0
         while nxt is not None:
-            cur, ev = nxt
+            cur, ready = nxt
+            k_cur, k = k, k ^ 1
             try:
-                nxt = self._stage(next(it), stream)  # enqueue the next copy before handing out the current batch
+                nxt = stage(next(it), k)  # enqueue the next copy before handing out the current batch
             except StopIteration:
                 nxt = None
-            if ev is not None:
-                torch.cuda.current_stream(self.device).wait_event(ev)
-                t = cur if isinstance(cur, torch.Tensor) else cur[0]
-                t.record_stream(torch.cuda.current_stream(self.device))
+            if ready is not None:
+                torch.cuda.current_stream(dev).wait_event(ready)
             yield cur
+            if ready is not None:  # the consumer asked for the next batch: everything it enqueued on `cur` is in the stream
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(dev))
+                reusable[k_cur] = done
 
 
 class MissingNameWarning(UserWarning):

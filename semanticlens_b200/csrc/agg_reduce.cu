@@ -245,6 +245,172 @@ __global__ void __launch_bounds__(kThreads, 2) agg_rows_staged_kernel(RowsParams
 }
 
 // ------------------------------------------------------------------------------------------------
+// NCHW, staged, SHORT rows (L <= 128, fp32): G = 8 or 16 lanes fold one row, so a warp folds 32/G rows at a time
+// instead of idling most of its lanes (a 7x7 map is 49 elements). Bit-identical to the canonical order: lane g of a
+// group owns the accumulator slots s = g, g + G, ... of the 32-slot layout; a slot's tree8 over its <= NWS elements
+// (missing ones are the identity, folded at compile time), then the butterfly levels 16, 8 (, ...) >= G are local
+// adds between the lane's own slots and the levels < G are shuffles inside the group.
+// ------------------------------------------------------------------------------------------------
+template <int OP, int G, int NWS>
+__global__ void __launch_bounds__(kThreads, 2) agg_rows_subwarp_kernel(RowsParams p) {
+    using A = Agg<OP>;
+    constexpr int SPL = 32 / G;  // slots per lane
+    constexpr int RPW = 32 / G;  // rows per warp per round
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* stage_base = smem_raw;
+    RowsSmem* ss = reinterpret_cast<RowsSmem*>(smem_raw + kStages * kStageBytes);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane % G, sub = lane / G;
+    const float* x = static_cast<const float*>(p.x);
+    const int L = p.L;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) slb_mbar_init(&ss->full[s], 1);
+        slb_fence_mbar_init();
+    }
+    __syncthreads();
+    const int64_t n_items = (p.n_tiles > blockIdx.x) ? (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    auto issue = [&](int64_t i) {  // thread 0 only; tiles are whole rows and 16-byte multiples except the very last
+        const int s = (int)(i % kStages);
+        unsigned char* dst = stage_base + (size_t)s * kStageBytes;
+        const int64_t t = blockIdx.x + i * (int64_t)gridDim.x;
+        const int64_t r0 = t * p.rows_per_tile;
+        const int64_t nr = min((int64_t)p.rows_per_tile, p.n_rows - r0);
+        const float* src = x + r0 * (int64_t)L;
+        const uint32_t bytes = (uint32_t)(nr * L * sizeof(float));
+        const uint32_t bulk = bytes & ~15u;
+        for (uint32_t o = bulk; o < bytes; o += 4)
+            *reinterpret_cast<float*>(dst + o) = *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(src) + o);
+        if (bulk) {
+            slb_mbar_arrive_expect_tx(&ss->full[s], bulk);
+            slb_bulk_g2s(dst, src, bulk, &ss->full[s]);
+        } else {
+            slb_mbar_arrive(&ss->full[s]);
+        }
+    };
+    if (tid == 0)
+        for (int64_t i = 0; i < kStages && i < n_items; ++i) issue(i);
+
+    for (int64_t i = 0; i < n_items; ++i) {
+        const int s = (int)(i % kStages);
+        slb_mbar_wait(&ss->full[s], (uint32_t)((i / kStages) & 1));
+        const float* tile = reinterpret_cast<const float*>(stage_base + (size_t)s * kStageBytes);
+        const int64_t r0 = (blockIdx.x + i * (int64_t)gridDim.x) * p.rows_per_tile;
+        const int nr = (int)min((int64_t)p.rows_per_tile, p.n_rows - r0);
+        for (int base = warp * RPW; base < nr; base += kWarps * RPW) {  // warp-uniform trip count (shuffles below)
+            const int rr = base + sub;
+            const bool valid = rr < nr;
+            const float* row = tile + (size_t)(valid ? rr : base) * L;
+            float slot[SPL];
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) {
+                const int sl = g + G * q;
+                float a[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    a[j] = A::identity();
+                    if (j < NWS) {
+                        const int e = 32 * j + sl;
+                        if (e < L) a[j] = A::fold(A::identity(), A::pre(row[e]));
+                    }
+                }
+                slot[q] = tree8<OP>(a);
+            }
+            // butterfly levels 16 .. G: between this lane's own slots (slot q <-> slot q + off / G)
+#pragma unroll
+            for (int off = 16; off >= G; off >>= 1) {
+                const int d = off / G;
+#pragma unroll
+                for (int q = 0; q < SPL; ++q)
+                    if ((q & d) == 0 && q + d < SPL) slot[q] = A::fold(slot[q], slot[q + d]);
+            }
+            float v = slot[0];
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1) v = A::fold(v, __shfl_xor_sync(0xffffffffu, v, off));
+            if (valid && g == 0) p.out[r0 + rr] = A::finish(v, L);
+        }
+        __syncthreads();
+        if (tid == 0 && i + kStages < n_items) issue(i + kStages);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCHW, staged, MID rows (one row = 1/RPT of a stage, RPT = 2..4): like LARGE, the 8 warps share a row (warp w folds
+// accumulator column ws = w), but a tile carries RPT whole rows, so the per-tile costs (barrier wait, __syncthreads,
+// refill) are paid once per RPT rows and the bulk copies are RPT times larger.
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) GroupSmem {
+    uint64_t full[kStages];
+    float partial[2][4][kWarps][32];
+};
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(kThreads, 2) agg_rows_group_kernel(RowsParams p) {
+    using A = Agg<OP>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* stage_base = smem_raw;
+    GroupSmem* ss = reinterpret_cast<GroupSmem*>(smem_raw + kStages * kStageBytes);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const T* x = static_cast<const T*>(p.x);
+    const int L = p.L, RPT = p.rows_per_tile;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) slb_mbar_init(&ss->full[s], 1);
+        slb_fence_mbar_init();
+    }
+    __syncthreads();
+    const int64_t n_items = (p.n_tiles > blockIdx.x) ? (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto issue = [&](int64_t i) {  // thread 0; row_bytes % 16 == 0, so every tile is a 16-byte multiple
+        const int s = (int)(i % kStages);
+        const int64_t r0 = (blockIdx.x + i * (int64_t)gridDim.x) * RPT;
+        const int64_t nr = min((int64_t)RPT, p.n_rows - r0);
+        const uint32_t bytes = (uint32_t)(nr * L * sizeof(T));
+        slb_mbar_arrive_expect_tx(&ss->full[s], bytes);
+        slb_bulk_g2s(stage_base + (size_t)s * kStageBytes, x + r0 * (int64_t)L, bytes, &ss->full[s]);
+    };
+    if (tid == 0)
+        for (int64_t i = 0; i < kStages && i < n_items; ++i) issue(i);
+
+    int parity = 0;
+    for (int64_t i = 0; i < n_items; ++i) {
+        const int s = (int)(i % kStages);
+        slb_mbar_wait(&ss->full[s], (uint32_t)((i / kStages) & 1));
+        const T* tile = reinterpret_cast<const T*>(stage_base + (size_t)s * kStageBytes);
+        const int64_t r0 = (blockIdx.x + i * (int64_t)gridDim.x) * RPT;
+        const int nr = (int)min((int64_t)RPT, p.n_rows - r0);
+        for (int rr = 0; rr < nr; ++rr) {
+            const T* row = tile + (size_t)rr * L;
+            float acc = A::identity();
+            for (int e0 = 32 * warp; e0 < L; e0 += 256 * 4) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = e0 + 256 * j + lane;
+                    v[j] = (e < L) ? A::pre(to_f32<T>(row[e])) : A::identity();
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = e0 + 256 * j + lane;
+                    if (e < L) acc = A::fold(acc, v[j]);
+                }
+            }
+            ss->partial[parity][rr][warp][lane] = acc;
+        }
+        __syncthreads();  // the stage is free again; the partials are visible
+        if (tid == 0 && i + kStages < n_items) issue(i + kStages);
+        if (warp < nr) {
+            float a[8];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) a[w] = ss->partial[parity][warp][w][lane];
+            const float rsum = butterfly<OP>(tree8<OP>(a));
+            if (lane == 0) p.out[r0 + warp] = round_to_input<T>(A::finish(rsum, L));
+        }
+        parity ^= 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // NCHW, direct from global (any alignment / row length). Same canonical order.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int OP>
@@ -417,6 +583,47 @@ int launch_rows(const void* x, float* out, int64_t n_rows, int64_t L, cudaStream
     int64_t R = (kStageBytes / row_bytes) / align_r * align_r;
     const size_t smem = (size_t)kStages * kStageBytes + sizeof(RowsSmem);
 
+    if constexpr (sizeof(T) == 4) {
+        // short rows: sub-warp groups (fp32 maps; L <= 128)
+        if (aligned && !force_direct() && R >= kWarps && L <= 128) {
+            RowsParams p{};
+            p.x = x; p.out = out; p.n_rows = n_rows; p.L = (int)L;
+            p.rows_per_tile = (int)R;
+            p.n_tiles = slb_ceil_div(n_rows, R);
+            const int grid = (int)std::min<int64_t>(p.n_tiles, (int64_t)sms * 2);
+            const int nws = (int)slb_ceil_div(L, 32);
+#define SLB_SUBWARP(G_, NWS_)                                                                                         \
+    {                                                                                                                 \
+        auto kern = agg_rows_subwarp_kernel<OP, G_, NWS_>;                                                            \
+        SLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+        kern<<<grid, kThreads, smem, st>>>(p);                                                                        \
+    }
+            if (nws == 1) SLB_SUBWARP(8, 1)
+            else if (nws == 2) SLB_SUBWARP(8, 2)
+            else if (nws == 3) SLB_SUBWARP(16, 3)
+            else SLB_SUBWARP(16, 4)
+#undef SLB_SUBWARP
+            SLB_LAUNCH_OK("agg_rows_subwarp");
+            return SLB_OK;
+        }
+    }
+    {
+        // mid rows: 2..4 whole rows per stage, all 8 warps on each row
+        const int64_t rpt = std::min<int64_t>(4, kStageBytes / row_bytes);
+        if (aligned && !force_direct() && (row_bytes % 16) == 0 && L >= 1024 && rpt >= 2) {
+            RowsParams p{};
+            p.x = x; p.out = out; p.n_rows = n_rows; p.L = (int)L;
+            p.rows_per_tile = (int)rpt;
+            p.n_tiles = slb_ceil_div(n_rows, rpt);
+            auto kern = agg_rows_group_kernel<T, OP>;
+            const size_t gsmem = (size_t)kStages * kStageBytes + sizeof(GroupSmem);
+            SLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+            const int grid = (int)std::min<int64_t>(p.n_tiles, (int64_t)sms * 2);
+            kern<<<grid, kThreads, gsmem, st>>>(p);
+            SLB_LAUNCH_OK("agg_rows_group");
+            return SLB_OK;
+        }
+    }
     if (aligned && !force_direct() && R >= kWarps) {
         RowsParams p{};
         p.x = x; p.out = out; p.n_rows = n_rows; p.L = (int)L;

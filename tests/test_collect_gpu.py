@@ -56,6 +56,14 @@ CONV_SHAPES = [
     (1, 2, 90, 91),  # L = 8190 not a multiple of 4 -> direct CTA path
     (37, 19, 5, 5),
     (300, 64, 7, 7),  # many tiles, tail tile
+    (40, 16, 4, 4),  # L = 16: sub-warp rows, one accumulator column
+    (9, 33, 8, 8),  # L = 64: sub-warp rows, 8 lanes per row, two columns
+    (7, 11, 9, 9),  # L = 81: 16 lanes per row, three columns
+    (5, 13, 10, 10),  # L = 100
+    (6, 10, 8, 16),  # L = 128: the longest sub-warp row
+    (3, 5, 52, 52),  # L = 2704: 3 whole rows per stage, row count not a multiple of 3
+    (2, 7, 32, 64),  # L = 2048: 4 rows per stage
+    (40, 32, 56, 56),  # L = 3136, 1280 rows: more 2-row tiles than resident CTAs
 ]
 
 
@@ -68,6 +76,17 @@ def test_k1_conv_bitexact_vs_canonical_oracle(ops, shape, op):
     assert_f32_bitexact(got, oc.aggregate_canonical(x.numpy(), op, "conv"))
     exact = oc.aggregate_exact(x.numpy(), op, "conv")
     np.testing.assert_allclose(got, exact, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(4, 6, 7, 7), (3, 4, 10, 10), (2, 3, 56, 56)])
+def test_k1_signed_zero_rows_follow_the_canonical_fold(ops, shape):
+    """All-(-0.0) and mixed-zero rows: the identity folds of the canonical order decide the sign of a zero result."""
+    x = torch.zeros(*shape)
+    x[::2] = -0.0
+    x[0, 0].view(-1)[::3] = -0.0
+    for op in ("mean", "max", "absmax"):
+        got = ops.agg_reduce(x.cuda(), OPS[op], "conv").cpu().numpy()
+        assert_f32_bitexact(got, oc.aggregate_canonical(x.numpy(), op, "conv"))
 
 
 def test_k1_conv_staged_equals_direct(ops, monkeypatch):
