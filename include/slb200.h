@@ -55,6 +55,20 @@ const char* slb_last_error(void);
  * timed region as "gpu_launches"). */
 int64_t slb_launch_count(void);
 
+/* Live per-kernel timing for bench.py's roofline line: between slb_profile_begin() and slb_profile_end() every
+ * single-kernel entry point records two CUDA events around its launch, on the stream it launches on, plus its
+ * algorithmic work. slb_profile_summary synchronises those events and returns one entry per kernel name. */
+typedef struct {
+    char name[48];
+    int64_t launches;
+    double ms;    /* sum of event-to-event times */
+    double flops; /* algorithmic flops issued (tensor kernels) */
+    double bytes; /* algorithmic bytes (streaming kernels) */
+} SlbKernelTime;
+int slb_profile_begin(void);
+int slb_profile_end(void);
+int slb_profile_summary(SlbKernelTime* out, int max_entries, int* n_entries);
+
 /* Number of SMs / compute capability of the current device (host query, for sizing and for
  * failing loudly on a non-sm_100 device). Returns SLB_ECUDA if no device. */
 int slb_device_info(int* sm_count, int* cc_major, int* cc_minor);
@@ -200,6 +214,12 @@ int slb_layernorm(const float* x, int64_t rows, int64_t cols, int64_t row_stride
 int slb_attention_small(const float* q, int64_t q_batch_stride, int64_t q_row_stride, const float* k, const float* v,
                         int64_t kv_batch_stride, int64_t kv_row_stride, int64_t B, int64_t Tq, int64_t Tk, int64_t H,
                         int64_t dh, float scale, int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream);
+
+/* The same attention for head_dim 64 reading q, k, v from the fp16 split planes [2][B*T][3*H*64] that the in_proj GEMM emits
+ * (packed nn.MultiheadAttention layout: q | k | v along the last axis): no fp32 round trip, no conversion in the
+ * kernel (cp.async + ldmatrix + mma.sync). out as in slb_attention_small. */
+int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, int64_t dh, float scale,
+                         int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream);
 
 /* The whole CLIP ViT image tower in one call (open_clip VisionTransformer.forward behind clip.py:103-118).
  * Weight matrices are split planes prepared once by the caller (slb_split_planes); vectors are fp32. All pointers are

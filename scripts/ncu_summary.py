@@ -89,8 +89,53 @@ def full(path: str, pat: str | None):
         print()
 
 
+PROFILE_NAMES = [  # kernel function name pattern -> the name the in-library profiler (slb_profile_*) reports
+    (r"gemm_split", "K4 gemm_split (tcgen05)"), (r"attention_", "K4 attention"), (r"layernorm_kernel", "K4 layernorm"),
+    (r"patchify", "K4 patchify"), (r"assemble_kernel", "K4 assemble_tokens"), (r"u8_norm", "K3 u8_to_f32_norm"),
+    (r"agg_rows|agg_btf|token_select", "K1 agg_reduce"), (r"topk_update", "K2 topk_update"),
+    (r"topk_merge_lists", "K2 topk_merge_lists"), (r"gather_rows", "K5 gather_rows"), (r"clarity_kernel", "K7 clarity"),
+    (r"polysem_kernel", "K8 polysem_2means"), (r"normalize_split", "K6 normalize_split_rows"), (r"split_planes", "split_planes"),
+]
+
+
+def traffic(path: str):
+    """ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum CSV -> JSON on stdout:
+    {profile kernel name: {launches, dram_bytes_per_launch, ...}} (what bench.py reports as roofline.traffic)."""
+    import json
+
+    lines = [l for l in open(path) if not l.startswith("==")]
+    per_launch: dict = {}
+    for row in csv.DictReader(lines):
+        name = row["Kernel Name"]
+        if "<unnamed>::" not in name or "at::" in name:
+            continue
+        key = next((pn for pat, pn in PROFILE_NAMES if re.search(pat, name)), None)
+        if key is None:
+            continue
+        d = per_launch.setdefault((key, row["ID"]), {})
+        unit = row["Metric Unit"]
+        val = float(row["Metric Value"].replace(",", ""))
+        if row["Metric Name"].startswith("dram__bytes"):
+            val *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+            d["dram"] = d.get("dram", 0.0) + val
+        elif row["Metric Name"] == "gpu__time_duration.sum":
+            d["ns"] = to_ns(row["Metric Value"], unit)
+    out: dict = {}
+    for (key, _), d in per_launch.items():
+        o = out.setdefault(key, {"launches": 0, "dram_bytes": 0.0, "ns": 0.0})
+        o["launches"] += 1
+        o["dram_bytes"] += d.get("dram", 0.0)
+        o["ns"] += d.get("ns", 0.0)
+    res = {k: {"launches": v["launches"], "dram_bytes_per_launch": v["dram_bytes"] / v["launches"],
+               "us_per_launch_under_ncu": v["ns"] / v["launches"] / 1e3,
+               "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum ({path})"} for k, v in out.items()}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2])
     else:
         full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)

@@ -34,6 +34,9 @@ _PROTOS = {
     "slb_last_error": (c_char_p, []),
     "slb_launch_count": (c_int64, []),
     "slb_device_info": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "slb_profile_begin": (c_int, []),
+    "slb_profile_end": (c_int, []),
+    "slb_profile_summary": (c_int, [c_void_p, c_int, c_void_p]),
     "slb_agg_reduce": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     "slb_topk_update": (
         c_int,
@@ -75,10 +78,33 @@ _PROTOS = {
         [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
          c_float, c_int, c_void_p, c_void_p, c_void_p],
     ),
+    "slb_attention_planes": (
+        c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p]),
     "slb_patch_k": (c_int64, [c_int64]),
     "slb_vit_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "slb_vit_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
+
+
+class SlbKernelTime(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 48), ("launches", c_int64), ("ms", c_double), ("flops", c_double),
+                ("bytes", c_double)]
+
+
+def profile_begin() -> None:
+    check(load().slb_profile_begin(), "slb_profile_begin")
+
+
+def profile_end() -> dict[str, dict[str, float]]:
+    """Stop the live profiling started by :func:`profile_begin` and return {kernel: {launches, ms, flops, bytes}}
+    (synchronises the recorded events)."""
+    lib = load()
+    check(lib.slb_profile_end(), "slb_profile_end")
+    arr = (SlbKernelTime * 64)()
+    n = c_int(0)
+    check(lib.slb_profile_summary(ctypes.byref(arr), 64, ctypes.byref(n)), "slb_profile_summary")
+    return {arr[i].name.decode(): {"launches": int(arr[i].launches), "ms": arr[i].ms, "flops": arr[i].flops,
+                                   "bytes": arr[i].bytes} for i in range(n.value)}
 
 
 class SlbVitLayer(ctypes.Structure):

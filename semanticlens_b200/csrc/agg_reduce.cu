@@ -725,6 +725,8 @@ extern "C" int slb_agg_reduce(const void* x, int dtype, int layout, int64_t B, i
     SLB_REQUIRE(inner >= 1, SLB_EINVAL, "slb_agg_reduce: empty reduction axis");
     SLB_REQUIRE(inner < (1ll << 31) - 4096, SLB_EUNSUPPORTED, "slb_agg_reduce: reduction axis too long");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double esz = dtype == SLB_DT_F32 ? 4.0 : 2.0;
+    SlbProfScope prof("K1 agg_reduce", stream, 0.0, (double)B * (double)C * (double)inner * esz);
     switch (dtype) {
         case SLB_DT_F32:
             return dispatch_op<float>(x, layout, B, C, inner, agg_op, token_pos, out, st);

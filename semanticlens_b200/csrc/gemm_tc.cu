@@ -9,10 +9,11 @@
 // memory: main = Ahi·Whi and corr = Ahi·Wlo + Alo·Whi; the epilogue forms main + corr/S (the lo·lo term is below
 // fp32 resolution for fp16 planes). The tensor cores thus deliver fp32-grade results at 1/3 of their 16-bit rate.
 //
-// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+// Structure (one CTA per SM, persistent over output tiles, 320 threads):
 //   warp 0      TMA producer: per k-block ONE 3-D box per operand {64 cols, rows, 2 planes} -> 128B-swizzled smem stage
 //   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16, 12 per k-block; tcgen05.commit frees stages
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> scale/bias/activation/residual -> global
+//   warps 2..9  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> scale/bias/activation/residual -> global
+//               (two warps per TMEM lane quarter: the GELU / split-plane epilogues are ALU-heavy)
 // Accumulators are double buffered in TMEM (2 x 2 x BN = 512 columns): the epilogue of tile i overlaps the MMAs of
 // tile i+1.
 #include "tc_common.cuh"
@@ -24,7 +25,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 2 B = one 128-byte swizzle row
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;  // two warps per TMEM lane quarter, interleaved over the 32-column chunks
+constexpr int kThreads = (2 + kEpiWarps) * 32;
 
 template <int BN>
 struct Cfg {
@@ -166,7 +168,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             slb_mbar_init(&tfull[a], 1);
-            slb_mbar_init(&tempty[a], 4);
+            slb_mbar_init(&tempty[a], kEpiWarps);
         }
         slb_fence_mbar_init();
     }
@@ -238,6 +240,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
     } else {
         const int quarter = warp & 3;  // TMEM lane group this warp may read
+        const int chunk0 = (warp - 2) >> 2;  // warps 2..5 take the even column chunks, warps 6..9 the odd ones
         int acc = 0;
         uint32_t acc_phase = 0;
         const int fmt = p.fmt;
@@ -250,7 +253,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const bool row_ok = m < p.M;
             const float rs = (p.row_scale && row_ok) ? p.row_scale[m] : 1.0f;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = chunk0; c < BN / 32; c += kEpiWarps / 4) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
                 drain_chunk(p, taddr, BN, m, row_ok, rs, (int64_t)n0 + c * 32, fmt, inv_s);
             }
@@ -280,7 +283,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //   full[s]    leader only; the leader arms it with the pair's byte count, both CTAs' TMA loads complete on it
 //   empty[s]   in each CTA; tcgen05.commit multicast from the leader frees the stage in both CTAs
 //   tfull[a]   in each CTA; commit multicast after the tile's last k-block
-//   tempty[a]  leader only, 8 arrivals: the 4 epilogue warps of each CTA (the peer's arrive remotely)
+//   tempty[a]  leader only, 16 arrivals: the 8 epilogue warps of each CTA (the peer's arrive remotely)
 // ---------------------------------------------------------------------------------------------
 struct CfgPair {
     static constexpr int BN = 128;
@@ -338,7 +341,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         for (int a = 0; a < 2; ++a) {
             slb_mbar_init(&tfull[a], 1);
-            slb_mbar_init(&tempty[a], 8);
+            slb_mbar_init(&tempty[a], 2 * kEpiWarps);
         }
         slb_fence_mbar_init();
     }
@@ -414,6 +417,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         __syncwarp();
     } else {
         const int quarter = warp & 3;
+        const int chunk0 = (warp - 2) >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         const int fmt = p.fmt;
@@ -426,7 +430,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const bool row_ok = m < p.M;
             const float rs = (p.row_scale && row_ok) ? p.row_scale[m] : 1.0f;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = chunk0; c < BN / 32; c += kEpiWarps / 4) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
                 drain_chunk(p, taddr, BN, m, row_ok, rs, (int64_t)n0 + c * 32, fmt, inv_s);
             }
@@ -558,6 +562,7 @@ extern "C" int slb_split_planes(const float* x, int64_t n, int plane_fmt, uint16
     SLB_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)planes % 8) == 0 && (n % 4) == 0, SLB_EINVAL,
                 "slb_split_planes: x must be 16-byte aligned, planes 8-byte aligned, n a multiple of 4");
     const int64_t n4 = n / 4;
+    SlbProfScope prof("split_planes", stream, 0.0, 8.0 * (double)n);
     const int grid = (int)std::min<int64_t>(slb_ceil_div(n4, 256), (int64_t)slb_sm_count() * 8);
     split_planes_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n4, n, plane_fmt, planes, planes + n);
     SLB_LAUNCH_OK("split_planes");
@@ -584,6 +589,8 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
                     ((uintptr_t)residual % 16) == 0 && ((M * K * 2) % 16) == 0 && ((N * K * 2) % 16) == 0 &&
                     ((M * N * 2) % 16) == 0,
                 SLB_EINVAL, "slb_gemm_split: operands must be 16-byte aligned");
+    SlbProfScope prof("K4 gemm_split (tcgen05)", stream, 2.0 * (double)M * (double)N * (double)K * (double)passes,
+                      4.0 * ((double)M * (double)K + (double)N * (double)K) + ((out_f32 ? 4.0 : 0.0) + (out_planes ? 4.0 : 0.0)) * (double)M * (double)N);
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.bias = bias; p.residual = residual; p.row_scale = row_scale; p.col_scale = col_scale;

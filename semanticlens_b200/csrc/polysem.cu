@@ -392,6 +392,7 @@ extern "C" int slb_polysem_2means(const float* V, int64_t C, int64_t k, int64_t 
     const size_t need = slb_polysem_workspace_bytes(C, k);
     SLB_REQUIRE(workspace_bytes >= need, SLB_EWORKSPACE, "slb_polysem_2means: workspace needs %zu bytes, got %zu", need,
                 workspace_bytes);
+    SlbProfScope prof("K8 polysem_2means", stream, 0.0, 4.0 * (double)C * (double)k * (double)D);
     PolyParams p{};
     p.V = V; p.C = C; p.k = (int)k; p.D = (int)D; p.n_init = n_init; p.replace_empty = replace_empty_clusters ? 1 : 0;
     for (int i = 0; i < n_init; ++i) {

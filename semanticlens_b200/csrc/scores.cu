@@ -210,6 +210,7 @@ extern "C" int slb_normalize_split_rows(const float* x, int64_t rows, int64_t D,
                 "slb_normalize_split_rows: D must be a multiple of 4 and <= 2048 (got %lld), x 16-byte aligned", (long long)D);
     const int Kpad = (int)pad64(D);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SlbProfScope prof("K6 normalize_split_rows", stream, 0.0, (double)rows * (4.0 * (double)D + (planes ? 4.0 * Kpad : 0.0)));
     const int nch = (int)slb_ceil_div(Kpad, 128);
     if (nch <= 2) return launch_normalize<2>(x, rows, (int)D, Kpad, eps, plane_fmt, planes, inv_norms, st);
     if (nch <= 4) return launch_normalize<4>(x, rows, (int)D, Kpad, eps, plane_fmt, planes, inv_norms, st);
@@ -266,6 +267,7 @@ extern "C" int slb_clarity(const float* V, int64_t C, int64_t k, int64_t D, floa
     SLB_REQUIRE(D % 4 == 0 && D <= 2048 && k < (1ll << 31) && ((uintptr_t)V % 16) == 0, SLB_EUNSUPPORTED,
                 "slb_clarity: D must be a multiple of 4 and <= 2048 (got %lld), V 16-byte aligned", (long long)D);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SlbProfScope prof("K7 clarity", stream, 0.0, 4.0 * (double)C * (double)k * (double)D);
     const int nch = (int)slb_ceil_div(D, 128);
     const float eps = 1e-12f;  // F.normalize default (scores.py:45)
     if (nch <= 2) return launch_clarity<2>(V, C, (int)k, (int)D, eps, out, st);

@@ -47,6 +47,23 @@ void slb_set_error(const char* fmt, ...);
     } while (0)
 
 void slb_count_launch();  // process-wide counter of kernels this library has launched (slb_launch_count)
+
+// Optional live profiling (slb_profile_begin / slb_profile_end): while enabled, every single-kernel entry point brackets
+// its launch with two CUDA events on the launch stream and notes its algorithmic work; nothing synchronises until
+// slb_profile_summary. Costs one branch when disabled.
+bool slb_profile_enabled();
+void slb_profile_open(const char* name, void* stream, double flops, double bytes, void** token);
+void slb_profile_close(void* token, void* stream);
+struct SlbProfScope {
+    void* token = nullptr;
+    void* stream;
+    SlbProfScope(const char* name, void* st, double flops, double bytes) : stream(st) {
+        if (slb_profile_enabled()) slb_profile_open(name, st, flops, bytes, &token);
+    }
+    ~SlbProfScope() {
+        if (token) slb_profile_close(token, stream);
+    }
+};
 int slb_sm_count();  // cached per process (current device at first call)
 
 static inline int64_t slb_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

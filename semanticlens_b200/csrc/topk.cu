@@ -182,6 +182,8 @@ extern "C" int slb_topk_update(const void* cand, int cand_dtype, int64_t B, int6
     SLB_REQUIRE(ids != nullptr || (id_base >= 0 && id_base + B < (int64_t)SLB_ID_MASK), SLB_EINVAL,
                 "slb_topk_update: sample ids must lie in [0, 2^47-1)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SlbProfScope prof("K2 topk_update", stream, 0.0,
+                      (double)B * (double)C * (cand_dtype == SLB_DT_F32 ? 4.0 : 2.0) + 2.0 * (double)C * (double)k * 10.0);
     const int P = host_next_pow2(k + B);
     size_t smem;
     const int w = pick_warps(P, &smem);
@@ -210,6 +212,7 @@ extern "C" int slb_topk_merge_lists(const uint16_t* vals, const int64_t* ids, in
                 "slb_topk_merge_lists: outputs may not alias inputs");
     SLB_REQUIRE(R * k <= 8192, SLB_EUNSUPPORTED, "slb_topk_merge_lists: R*k = %lld exceeds 8192", (long long)(R * k));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SlbProfScope prof("K2 topk_merge_lists", stream, 0.0, (double)(R + 1) * (double)C * (double)k * 10.0);
     const int P = host_next_pow2(R * k);
     size_t smem;
     const int w = pick_warps(P, &smem);
@@ -240,6 +243,7 @@ extern "C" int slb_gather_rows(const float* table, int64_t N, int64_t D, const i
     SLB_REQUIRE(((uintptr_t)table % 16) == 0 && ((uintptr_t)out % 16) == 0, SLB_EINVAL,
                 "slb_gather_rows: buffers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SlbProfScope prof("K5 gather_rows", stream, 0.0, (double)n_idx * ((double)D * 8.0 + 8.0));
     const int threads = 256;
     gather_rows_kernel<<<(unsigned)slb_ceil_div(n_idx * 32, threads), threads, 0, st>>>(table, N, D, idx, n_idx, out,
                                                                                        nullptr);

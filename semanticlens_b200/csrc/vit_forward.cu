@@ -91,10 +91,18 @@ extern "C" int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t
     for (int l = 0; l < w->layers; ++l) {
         const SlbVitLayer& ly = w->layer[l];
         SLB_TRY(slb_layernorm(x, rows, W, W, ly.ln1_g, ly.ln1_b, w->ln_eps, fmt, nullptr, pa, stream));
-        SLB_TRY(slb_gemm_split(pa, ly.w_qkv, fmt, rows, 3 * W, W, ly.b_qkv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, qkv,
-                               nullptr, stream));
-        SLB_TRY(slb_attention_small(qkv, T * 3 * W, 3 * W, qkv + W, qkv + 2 * W, T * 3 * W, 3 * W, B, T, T, w->heads, dh,
-                                    1.0f / sqrtf((float)dh), fmt, nullptr, pb, stream));
+        if (fmt == SLB_PLANE_F16 && dh == 64) {
+            // in_proj writes q | k | v as split planes (same bytes as fp32) and attention consumes them directly
+            uint16_t* qkv_planes = reinterpret_cast<uint16_t*>(qkv);
+            SLB_TRY(slb_gemm_split(pa, ly.w_qkv, fmt, rows, 3 * W, W, ly.b_qkv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
+                                   nullptr, qkv_planes, stream));
+            SLB_TRY(slb_attention_planes(qkv_planes, B, T, w->heads, dh, 1.0f / sqrtf((float)dh), fmt, nullptr, pb, stream));
+        } else {
+            SLB_TRY(slb_gemm_split(pa, ly.w_qkv, fmt, rows, 3 * W, W, ly.b_qkv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
+                                   qkv, nullptr, stream));
+            SLB_TRY(slb_attention_small(qkv, T * 3 * W, 3 * W, qkv + W, qkv + 2 * W, T * 3 * W, 3 * W, B, T, T, w->heads,
+                                        dh, 1.0f / sqrtf((float)dh), fmt, nullptr, pb, stream));
+        }
         SLB_TRY(slb_gemm_split(pb, ly.w_out, fmt, rows, W, W, ly.b_out, x, nullptr, nullptr, SLB_EPI_NONE, 3, x, nullptr,
                                stream));
         SLB_TRY(slb_layernorm(x, rows, W, W, ly.ln2_g, ly.ln2_b, w->ln_eps, fmt, nullptr, pa, stream));

@@ -261,6 +261,7 @@ extern "C" int slb_u8_to_f32_norm(const uint8_t* img, int64_t B, int64_t Cc, int
     SLB_REQUIRE(n_pix % 16 == 0 && ((uintptr_t)img % 16) == 0 && ((uintptr_t)out % 16) == 0, SLB_EUNSUPPORTED,
                 "slb_u8_to_f32_norm: planes must be multiples of 16 pixels and 16-byte aligned");
     const int64_t n16 = B * Cc * n_pix / 16;
+    SlbProfScope prof("K3 u8_to_f32_norm", stream, 0.0, 5.0 * (double)B * (double)Cc * (double)n_pix);
     float3 m = make_float3(mean3[0], Cc > 1 ? mean3[1] : 0.f, Cc > 2 ? mean3[2] : 0.f);
     float3 s = make_float3(std3[0], Cc > 1 ? std3[1] : 1.f, Cc > 2 ? std3[2] : 1.f);
     u8_norm_kernel<<<grid_for(n16, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, n16, n_pix / 16, (int)Cc, m, s, out);
@@ -276,6 +277,7 @@ extern "C" int slb_patchify(const float* img, int64_t B, int64_t S, int64_t P, i
     SLB_REQUIRE(S % P == 0 && P % 2 == 0, SLB_EUNSUPPORTED, "slb_patchify: need S %% P == 0 and an even patch size");
     SLB_REQUIRE(((uintptr_t)img % 8) == 0 && ((uintptr_t)out_planes % 16) == 0, SLB_EINVAL, "slb_patchify: misaligned");
     const int64_t g = S / P, Kpad = slb_patch_k(P), n = B * g * g * Kpad;
+    SlbProfScope prof("K4 patchify", stream, 0.0, 12.0 * (double)B * (double)S * (double)S + 4.0 * (double)n);
     patchify_kernel<<<grid_for(n / 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, B, (int)S, (int)P, (int)Kpad,
                                                                                         plane_fmt, out_planes, out_planes + n);
     SLB_LAUNCH_OK("patchify");
@@ -290,6 +292,7 @@ extern "C" int slb_assemble_tokens(const float* patch, const float* cls, const f
     if (B == 0) return SLB_OK;
     SLB_REQUIRE(patch && out && (!has_cls || cls), SLB_EINVAL, "slb_assemble_tokens: null pointer");
     SLB_REQUIRE(W % 4 == 0, SLB_EUNSUPPORTED, "slb_assemble_tokens: width must be a multiple of 4");
+    SlbProfScope prof("K4 assemble_tokens", stream, 0.0, 8.0 * (double)B * (double)T * (double)W);
     assemble_kernel<<<grid_for(B * T * W / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         patch, cls, pos, B, (int)T, (int)(W / 4), has_cls ? 1 : 0, out);
     SLB_LAUNCH_OK("assemble_tokens");
@@ -305,6 +308,7 @@ extern "C" int slb_layernorm(const float* x, int64_t rows, int64_t cols, int64_t
     SLB_REQUIRE(cols % 4 == 0 && row_stride % 4 == 0 && row_stride >= cols, SLB_EUNSUPPORTED,
                 "slb_layernorm: cols and row_stride must be multiples of 4");
     const int threads = 256;
+    SlbProfScope prof("K4 layernorm", stream, 0.0, (double)rows * (double)cols * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_planes ? 4.0 : 0.0)));
     layernorm_kernel<<<(unsigned)slb_ceil_div(rows * 32, threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
         x, rows, (int)cols, row_stride, gamma, beta, eps, plane_fmt, out_f32, out_planes,
         out_planes ? out_planes + rows * cols : nullptr);
@@ -323,6 +327,9 @@ extern "C" int slb_attention_small(const float* q, int64_t q_batch_stride, int64
                     ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0,
                 SLB_EUNSUPPORTED, "slb_attention_small: head_dim must be a multiple of 4 (<= 128), K/V 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // QK^T and PV, three plane products each on the tensor-core path
+    SlbProfScope prof("K4 attention", stream, 4.0 * (double)B * (double)H * (double)Tq * (double)Tk * (double)dh * 3.0,
+                      4.0 * (double)B * (double)H * (double)dh * ((double)Tq * 2.0 + (double)Tk * 2.0));
     // head_dim 64 (every CLIP / SigLIP tower): tensor-core path (attention_mma.cu); anything else: the SIMT kernel below
     static const bool force_simt = [] { const char* e = getenv("SLB_ATTN_SIMT"); return e && e[0] == '1'; }();
     if (dh == 64 && !force_simt && q_row_stride % 2 == 0 && q_batch_stride % 2 == 0 && ((uintptr_t)q % 8) == 0 &&

@@ -55,6 +55,25 @@ def test_attention_vs_torch(ops, B, T, H, dh, gain):
     assert rel_max((planes[0].double() + planes[1].double() / 2048).view(B, T, W), want) < tol
 
 
+@pytest.mark.parametrize("B,T,H,gain", [(2, 50, 12, 1.0), (1, 257, 4, 1.0), (2, 197, 3, 1.0), (1, 1, 1, 1.0), (2, 64, 2, 1.0),
+                                       (1, 65, 2, 3.0), (1, 300, 1, 2.0), (70, 50, 12, 4.0), (3, 16, 2, 1.0)])
+def test_attention_from_planes_vs_torch(ops, B, T, H, gain):
+    """The tower's path: attention reads q | k | v from the in_proj GEMM's split planes (cp.async + ldmatrix + mma.sync)."""
+    dh = 64
+    W = H * dh
+    qkv = torch.randn(B, T, 3 * W, generator=torch.Generator().manual_seed(T * 7 + H)) * gain
+    planes_in = ops.split_planes(qkv.view(B * T, 3 * W).cuda(), 0)
+    # reference on the values the planes actually hold (22-bit operands)
+    held = (planes_in[0].double() + planes_in[1].double() / 2048).view(B, T, 3 * W).cpu()
+    q, k, v = (t.view(B, T, H, dh).transpose(1, 2) for t in held.split(W, -1))
+    want = (torch.softmax(q @ k.transpose(-1, -2) * dh**-0.5, -1) @ v).transpose(1, 2).reshape(B, T, W)
+    tol = 2e-6 * max(1.0, gain)
+    got = ops.attention_planes(planes_in, B, H)
+    assert rel_max(got, want) < tol
+    planes = ops.attention_planes(planes_in, B, H, fmt=0)
+    assert rel_max((planes[0].double() + planes[1].double() / 2048).view(B, T, W), want) < tol
+
+
 def tower_for(name, seed=3, fmt=0):
     from semanticlens_b200.foundation_models import vit
 
