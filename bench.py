@@ -305,7 +305,18 @@ def run_b200(args):
         cache.sample_idx_counter[name] = rank * (K + W) * B
     embeds = []
 
+    side = torch.cuda.Stream(dev) if args.overlap else None
+
     def step(i):
+        if side is not None and fm is not None:
+            # the two stages are independent: the tower (tensor cores) runs on a second stream under the probed
+            # model's fp32 convolutions (CUDA cores); both streams join before the next step reuses the ring slot
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                embeds.append(fm.encode_image(fm.preprocess(ring_u8[i % 4])))
+            model(ring_f32[i % 4])
+            torch.cuda.current_stream(dev).wait_stream(side)
+            return
         model(ring_f32[i % 4])
         if fm is not None:
             embeds.append(fm.encode_image(fm.preprocess(ring_u8[i % 4])))
@@ -434,6 +445,7 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=256, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
+    ap.add_argument("--overlap", type=int, default=0, help="1: run the embed tower on a second stream under the sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -384,3 +384,42 @@ def test_store_load_roundtrip_and_reference_cache(tmp_path, golden):
     assert ref.cache["0"].activations.shape == (4, 3) and ref.cache["2"].sample_ids.dtype == torch.int64
     with pytest.raises(FileNotFoundError):
         ActMaxCache(["0"], A.aggregate_conv_max, 3).load(golden / "cache_format")
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE cfg-2 sizes: size-independent properties (the oracle is too slow here)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(256, 64, 112, 112), (256, 256, 56, 56), (256, 512, 28, 28), (256, 1024, 14, 14),
+                                   (256, 2048, 7, 7)])
+def test_full_size_layer_properties(ops, shape):
+    """One ResNet-50 layer of cfg 2 at batch 256, three batches, k = 20:
+    (1) K1 equals a float64 mean to fp32 round-off; (2) the streamed top-k state equals torch.topk over ALL candidates
+    (values bit-exact: the value multiset is well defined); (3) rows are sorted, ids are unique, every id's own
+    aggregate rounds to the stored value; (4) a sweep fed in a different batch split gives the identical state."""
+    from semanticlens_b200.component_visualization.activation_caching import ActMax
+
+    B, C = shape[:2]
+    k = 20
+    g = torch.Generator(device="cuda").manual_seed(C)
+    maps = [torch.relu(torch.randn(*shape, device="cuda", generator=g)) for _ in range(3)]
+    aggs = [ops.agg_reduce(m, 0, "conv") for m in maps]
+    for m, a in zip(maps, aggs):
+        ref = m.double().flatten(2).mean(-1)
+        assert (a.double() - ref).abs().max() <= 2e-7 * ref.abs().max()
+    am = ActMax(k)
+    am2 = ActMax(k)
+    for i, m in enumerate(maps):
+        am.update_from_map(m, 0, "conv", 0, i * B)
+    half = B // 2
+    for i, m in enumerate(maps):  # same data, batches of 128
+        am2.update_from_map(m[:half], 0, "conv", 0, i * B)
+        am2.update_from_map(m[half:], 0, "conv", 0, i * B + half)
+    vals, ids = am.activations, am.sample_ids
+    assert torch.equal(vals.view(torch.int16), am2.activations.view(torch.int16)) and torch.equal(ids, am2.sample_ids)
+    cand = torch.cat(aggs).T.to(torch.bfloat16).cpu()  # (C, 3B)
+    want = torch.topk(cand.float(), k, dim=1).values.to(torch.bfloat16)
+    assert torch.equal(vals.view(torch.int16), want.view(torch.int16))
+    v32 = vals.float()
+    assert (v32[:, :-1] >= v32[:, 1:]).all()
+    assert all(len(set(r.tolist())) == k for r in ids[:64])
+    assert torch.equal(torch.gather(cand, 1, ids).view(torch.int16), vals.view(torch.int16))
