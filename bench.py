@@ -442,7 +442,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--cpu-images", type=int, default=256, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-images", type=int, default=768, help="size of the bounded CPU-baseline sample (~12 s of host work)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     ap.add_argument("--overlap", type=int, default=0, help="1: run the embed tower on a second stream under the sweep")

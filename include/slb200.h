@@ -221,10 +221,12 @@ int slb_attention_small(const float* q, int64_t q_batch_stride, int64_t q_row_st
 int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, int64_t dh, float scale,
                          int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream);
 
-/* The whole CLIP ViT image tower in one call (open_clip VisionTransformer.forward behind clip.py:103-118).
+/* The whole CLIP / SigLIP ViT image tower in one call (open_clip VisionTransformer.forward, or its timm ViT with the
+ * attention-pool head for SigLIP, behind clip.py:103-118).
  * Weight matrices are split planes prepared once by the caller (slb_split_planes); vectors are fp32. All pointers are
  * device pointers except `layer`, a HOST array of `layers` structs. */
-#define SLB_POOL_CLS 0 /* features = ln_post(x)[:, 0] @ proj */
+#define SLB_POOL_CLS 0 /* features = ln_post(x)[:, 0] @ proj                      (CLIP VisionTransformer) */
+#define SLB_POOL_MAP 1 /* features = attention-pool head over ln_post(x) [@ proj]  (SigLIP / timm AttentionPoolLatent) */
 
 typedef struct {
     const float* ln1_g; const float* ln1_b;
@@ -249,6 +251,13 @@ typedef struct {
     const float* ln_post_g; const float* ln_post_b;
     const uint16_t* proj;   /* planes [2, embed_dim, W] (= visual.proj transposed) or NULL */
     const SlbVitLayer* layer;
+    /* SLB_POOL_MAP only: a learned latent query attends over the final tokens, then x + mlp(norm(x)). */
+    const float* map_q;                                /* [W] q-projection of the latent (image independent, incl. bias) */
+    const uint16_t* map_w_kv; const float* map_b_kv;   /* planes [2, 2W, W], [2W]: k | v projections of the tokens */
+    const uint16_t* map_w_out; const float* map_b_out; /* planes [2, W, W], [W] */
+    const float* map_ln_g; const float* map_ln_b;      /* [W] */
+    const uint16_t* map_w_fc; const float* map_b_fc;   /* planes [2, mlp, W], [mlp] */
+    const uint16_t* map_w_proj; const float* map_b_proj; /* planes [2, W, mlp], [W] */
 } SlbVitWeights;
 
 /* Bytes of device workspace slb_vit_forward needs for a batch of B images (0 on bad arguments). */

@@ -185,3 +185,124 @@ def flops_per_image(cfg: VitConfig) -> float:
 
 
 assert math.isclose(flops_per_image(CONFIGS["ViT-B-32"]) / 1e9, 8.8, rel_tol=0.02)
+
+
+# ------------------------------------------------------------------------------------------------
+# SigLIP image tower (reference: foundation_models/clip.py:190-215 `SigLipV2` = open_clip "hf-hub:timm/ViT-B-16-SigLIP2",
+# i.e. a timm VisionTransformer behind open_clip's TimmModel wrapper; timm 1.0.19 / open-clip-torch 3.0.0, neither
+# installed). Restated from the published architecture: biased patch conv, NO class token, learned positional embedding,
+# no pre-norm, pre-LN blocks (eps 1e-6, GELU-tanh), final LayerNorm over all tokens, attention-pool ("MAP") head:
+# a learned latent query attends over the tokens (nn.MultiheadAttention arithmetic), out-projection, then
+# x + mlp(norm(x)); the pooled vector is the feature (no extra projection). Weight names follow the open_clip state
+# dict of such a model (`visual.trunk.*`). Pinned against HF transformers' SiglipVisionModel (tests/test_vit_oracle.py).
+# ------------------------------------------------------------------------------------------------
+SIGLIP_MEAN = (0.5, 0.5, 0.5)
+SIGLIP_STD = (0.5, 0.5, 0.5)
+
+
+@dataclass(frozen=True)
+class SigLipConfig:
+    name: str
+    image_size: int
+    patch: int
+    width: int
+    layers: int
+    heads: int
+    mlp: int
+    act: str = "gelu_tanh"
+    eps: float = 1e-6
+    mean: tuple = SIGLIP_MEAN
+    std: tuple = SIGLIP_STD
+
+    @property
+    def tokens(self):
+        return (self.image_size // self.patch) ** 2
+
+    @property
+    def embed_dim(self):
+        return self.width
+
+
+SIGLIP_CONFIGS = {
+    "ViT-B-16-SigLIP2": SigLipConfig("ViT-B-16-SigLIP2", 224, 16, 768, 12, 12, 3072),
+    "ViT-L-16-SigLIP-256": SigLipConfig("ViT-L-16-SigLIP-256", 256, 16, 1024, 24, 16, 4096),
+    "SigLIP-tiny-test": SigLipConfig("SigLIP-tiny-test", 32, 8, 128, 2, 2, 256),
+}
+
+
+def init_siglip_weights(cfg: SigLipConfig, seed: int = 1) -> dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    W, L = cfg.width, cfg.layers
+    scale = W**-0.5
+    rn = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
+    t = "visual.trunk."
+    sd = {
+        t + "patch_embed.proj.weight": rn(W, 3, cfg.patch, cfg.patch) * (3 * cfg.patch * cfg.patch) ** -0.5,
+        t + "patch_embed.proj.bias": 0.02 * rn(W),
+        t + "pos_embed": rn(1, cfg.tokens, W) * scale,
+        t + "norm.weight": 1 + 0.1 * rn(W),
+        t + "norm.bias": 0.1 * rn(W),
+        t + "attn_pool.latent": rn(1, 1, W) * scale,
+        t + "attn_pool.q.weight": rn(W, W) * scale,
+        t + "attn_pool.q.bias": 0.02 * rn(W),
+        t + "attn_pool.kv.weight": rn(2 * W, W) * scale,
+        t + "attn_pool.kv.bias": 0.02 * rn(2 * W),
+        t + "attn_pool.proj.weight": rn(W, W) * scale,
+        t + "attn_pool.proj.bias": 0.02 * rn(W),
+        t + "attn_pool.norm.weight": 1 + 0.1 * rn(W),
+        t + "attn_pool.norm.bias": 0.1 * rn(W),
+        t + "attn_pool.mlp.fc1.weight": rn(cfg.mlp, W) * (2 * W) ** -0.5,
+        t + "attn_pool.mlp.fc1.bias": 0.02 * rn(cfg.mlp),
+        t + "attn_pool.mlp.fc2.weight": rn(W, cfg.mlp) * scale * 0.5,
+        t + "attn_pool.mlp.fc2.bias": 0.02 * rn(W),
+    }
+    proj_std = scale * (2 * L) ** -0.5
+    for i in range(L):
+        p = f"{t}blocks.{i}."
+        sd[p + "norm1.weight"] = 1 + 0.1 * rn(W)
+        sd[p + "norm1.bias"] = 0.1 * rn(W)
+        sd[p + "attn.qkv.weight"] = rn(3 * W, W) * scale
+        sd[p + "attn.qkv.bias"] = 0.02 * rn(3 * W)
+        sd[p + "attn.proj.weight"] = rn(W, W) * proj_std
+        sd[p + "attn.proj.bias"] = 0.02 * rn(W)
+        sd[p + "norm2.weight"] = 1 + 0.1 * rn(W)
+        sd[p + "norm2.bias"] = 0.1 * rn(W)
+        sd[p + "mlp.fc1.weight"] = rn(cfg.mlp, W) * (2 * W) ** -0.5
+        sd[p + "mlp.fc1.bias"] = 0.02 * rn(cfg.mlp)
+        sd[p + "mlp.fc2.weight"] = rn(W, cfg.mlp) * proj_std
+        sd[p + "mlp.fc2.bias"] = 0.02 * rn(W)
+    return sd
+
+
+@torch.no_grad()
+def encode_image_siglip(sd: dict, cfg: SigLipConfig, img: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    """(B, 3, S, S) preprocessed images -> (B, width) features of the SigLIP tower."""
+    w = {k: v.to(device=img.device, dtype=dtype) for k, v in sd.items()}
+    t = "visual.trunk."
+    W, H = cfg.width, cfg.heads
+    dh = W // H
+    x = F.conv2d(img.to(dtype), w[t + "patch_embed.proj.weight"], w[t + "patch_embed.proj.bias"], stride=cfg.patch)
+    B = x.shape[0]
+    x = x.reshape(B, W, -1).permute(0, 2, 1) + w[t + "pos_embed"]
+    for i in range(cfg.layers):
+        p = f"{t}blocks.{i}."
+        h = F.layer_norm(x, (W,), w[p + "norm1.weight"], w[p + "norm1.bias"], cfg.eps)
+        x = x + mha(h, w[p + "attn.qkv.weight"], w[p + "attn.qkv.bias"], w[p + "attn.proj.weight"], w[p + "attn.proj.bias"], H)
+        h = F.layer_norm(x, (W,), w[p + "norm2.weight"], w[p + "norm2.bias"], cfg.eps)
+        h = _act(F.linear(h, w[p + "mlp.fc1.weight"], w[p + "mlp.fc1.bias"]), cfg.act)
+        x = x + F.linear(h, w[p + "mlp.fc2.weight"], w[p + "mlp.fc2.bias"])
+    x = F.layer_norm(x, (W,), w[t + "norm.weight"], w[t + "norm.bias"], cfg.eps)
+    # attention pool: one latent query per image
+    a = t + "attn_pool."
+    q = F.linear(w[a + "latent"].expand(B, 1, W), w[a + "q.weight"], w[a + "q.bias"]).view(B, 1, H, dh).transpose(1, 2)
+    kv = F.linear(x, w[a + "kv.weight"], w[a + "kv.bias"])
+    k, v = kv.split(W, dim=-1)
+    k = k.view(B, -1, H, dh).transpose(1, 2)
+    v = v.view(B, -1, H, dh).transpose(1, 2)
+    att = torch.softmax((q * dh**-0.5) @ k.transpose(-1, -2), dim=-1)
+    o = (att @ v).transpose(1, 2).reshape(B, 1, W)
+    o = F.linear(o, w[a + "proj.weight"], w[a + "proj.bias"])
+    h = F.layer_norm(o, (W,), w[a + "norm.weight"], w[a + "norm.bias"], cfg.eps)
+    h = _act(F.linear(h, w[a + "mlp.fc1.weight"], w[a + "mlp.fc1.bias"]), cfg.act)
+    o = o + F.linear(h, w[a + "mlp.fc2.weight"], w[a + "mlp.fc2.bias"])
+    return o[:, 0]

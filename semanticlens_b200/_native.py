@@ -20,6 +20,7 @@ DT_F32, DT_F16, DT_BF16 = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_BTF = 0, 1
 AGG_MEAN, AGG_MAX, AGG_ABSMEAN, AGG_ABSMAX, AGG_TOKEN = 0, 1, 2, 3, 4
 EPI_NONE, EPI_GELU_ERF, EPI_QUICKGELU, EPI_GELU_TANH = 0, 1, 2, 3
+POOL_CLS, POOL_MAP = 0, 1
 PLANE_F16, PLANE_BF16 = 0, 1
 
 _DTYPES = {torch.float32: DT_F32, torch.float16: DT_F16, torch.bfloat16: DT_BF16}
@@ -120,6 +121,8 @@ class SlbVitWeights(ctypes.Structure):
         + [(n, c_void_p) for n in ("conv_w", "conv_b", "cls", "pos", "ln_pre_g", "ln_pre_b", "ln_post_g", "ln_post_b",
                                    "proj")]
         + [("layer", ctypes.POINTER(SlbVitLayer))]
+        + [(n, c_void_p) for n in ("map_q", "map_w_kv", "map_b_kv", "map_w_out", "map_b_out", "map_ln_g", "map_ln_b",
+                                   "map_w_fc", "map_b_fc", "map_w_proj", "map_b_proj")]
     )
 
 

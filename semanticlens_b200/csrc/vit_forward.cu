@@ -13,7 +13,7 @@
 namespace {
 
 struct WsLayout {
-    size_t x, qkv, planes_a, planes_b, patch_f32, total;
+    size_t x, qkv, planes_a, planes_b, patch_f32, head_f32, total;
 };
 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -34,6 +34,7 @@ bool layout_for(const SlbVitWeights* w, int64_t B, WsLayout* L) {
     size_t pb = std::max<size_t>((size_t)2 * rows * w->mlp * 2, (size_t)2 * rows * W * 2);
     L->planes_b = o;   o += align_up(pb);
     L->patch_f32 = o;  o += align_up((size_t)B * g * g * W * 4);
+    L->head_f32 = o;   o += align_up((size_t)B * W * 4);  // attention-pool head: pooled vector before its MLP
     L->total = o;
     return true;
 }
@@ -51,12 +52,17 @@ extern "C" int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t
     SLB_REQUIRE(w != nullptr && B >= 0, SLB_EINVAL, "slb_vit_forward: bad arguments");
     if (B == 0) return SLB_OK;
     SLB_REQUIRE(img && out && workspace, SLB_EINVAL, "slb_vit_forward: null pointer");
-    SLB_REQUIRE(w->layers >= 0 && w->layer && w->conv_w && w->pos && w->ln_post_g, SLB_EINVAL,
+    SLB_REQUIRE(w->layers >= 0 && (w->layer || w->layers == 0) && w->conv_w && w->pos && w->ln_post_g, SLB_EINVAL,
                 "slb_vit_forward: incomplete weights");
     SLB_REQUIRE(w->width % 64 == 0 && w->mlp % 64 == 0 && w->heads > 0 && w->width % w->heads == 0, SLB_EUNSUPPORTED,
                 "slb_vit_forward: width and mlp must be multiples of 64");
     SLB_REQUIRE(w->patch % 2 == 0, SLB_EUNSUPPORTED, "slb_vit_forward: patch size must be even");
-    SLB_REQUIRE(w->pool == SLB_POOL_CLS && w->has_cls, SLB_EUNSUPPORTED, "slb_vit_forward: only class-token pooling is built");
+    SLB_REQUIRE((w->pool == SLB_POOL_CLS && w->has_cls) || w->pool == SLB_POOL_MAP, SLB_EUNSUPPORTED,
+                "slb_vit_forward: pooling must be SLB_POOL_CLS (with a class token) or SLB_POOL_MAP");
+    SLB_REQUIRE(!w->has_cls || w->cls, SLB_EINVAL, "slb_vit_forward: class token missing");
+    if (w->pool == SLB_POOL_MAP)
+        SLB_REQUIRE(w->map_q && w->map_w_kv && w->map_w_out && w->map_ln_g && w->map_w_fc && w->map_w_proj, SLB_EINVAL,
+                    "slb_vit_forward: incomplete attention-pool head");
     WsLayout L;
     SLB_REQUIRE(layout_for(w, B, &L), SLB_EINVAL, "slb_vit_forward: image_size must be a multiple of patch");
     SLB_REQUIRE(((uintptr_t)workspace % 256) == 0, SLB_EINVAL, "slb_vit_forward: workspace must be 256-byte aligned");
@@ -69,10 +75,11 @@ extern "C" int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t
     uint16_t* pa = reinterpret_cast<uint16_t*>(ws + L.planes_a);
     uint16_t* pb = reinterpret_cast<uint16_t*>(ws + L.planes_b);
     float* patch_f32 = reinterpret_cast<float*>(ws + L.patch_f32);
+    float* head_f32 = reinterpret_cast<float*>(ws + L.head_f32);
 
     const int fmt = w->plane_fmt;
     const int64_t g = w->image_size / w->patch;
-    const int64_t T = g * g + 1, W = w->width, rows = B * T, dh = W / w->heads;
+    const int64_t T = g * g + (w->has_cls ? 1 : 0), W = w->width, rows = B * T, dh = W / w->heads;
     const int64_t Kc = slb_patch_k(w->patch);  // conv_w planes are [2, width, Kc], zero padded past 3*P*P
     int rc;
 #define SLB_TRY(call)            \
@@ -85,7 +92,7 @@ extern "C" int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t
     SLB_TRY(slb_patchify(img, B, w->image_size, w->patch, fmt, pa, stream));
     SLB_TRY(slb_gemm_split(pa, w->conv_w, fmt, B * g * g, W, Kc, w->conv_b, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
                            patch_f32, nullptr, stream));
-    SLB_TRY(slb_assemble_tokens(patch_f32, w->cls, w->pos, B, T, W, 1, x, stream));
+    SLB_TRY(slb_assemble_tokens(patch_f32, w->cls, w->pos, B, T, W, w->has_cls ? 1 : 0, x, stream));
     if (w->ln_pre_g) SLB_TRY(slb_layernorm(x, rows, W, W, w->ln_pre_g, w->ln_pre_b, w->ln_eps, fmt, x, nullptr, stream));
 
     for (int l = 0; l < w->layers; ++l) {
@@ -112,8 +119,32 @@ extern "C" int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t
                                nullptr, stream));
     }
 
-    // ln_post on the class tokens (rows T*W apart), then the projection
-    if (w->proj) {
+    if (w->pool == SLB_POOL_MAP) {
+        // final LayerNorm over ALL tokens, then the attention-pool head (timm AttentionPoolLatent / HF Siglip "MAP" head)
+        SLB_TRY(slb_layernorm(x, rows, W, W, w->ln_post_g, w->ln_post_b, w->ln_eps, fmt, nullptr, pa, stream));
+        float* kv = qkv;  // [rows, 2W] fp32
+        SLB_TRY(slb_gemm_split(pa, w->map_w_kv, fmt, rows, 2 * W, W, w->map_b_kv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, kv,
+                               nullptr, stream));
+        // one query (the projected latent, shared by every image: batch stride 0) over the T tokens of each image
+        SLB_TRY(slb_attention_small(w->map_q, 0, W, kv, kv + W, T * 2 * W, 2 * W, B, 1, T, w->heads, dh,
+                                    1.0f / sqrtf((float)dh), fmt, nullptr, pb, stream));
+        SLB_TRY(slb_gemm_split(pb, w->map_w_out, fmt, B, W, W, w->map_b_out, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
+                               head_f32, nullptr, stream));
+        SLB_TRY(slb_layernorm(head_f32, B, W, W, w->map_ln_g, w->map_ln_b, w->ln_eps, fmt, nullptr, pa, stream));
+        SLB_TRY(slb_gemm_split(pa, w->map_w_fc, fmt, B, w->mlp, W, w->map_b_fc, nullptr, nullptr, nullptr, w->act, 3, nullptr, pb,
+                               stream));
+        if (w->proj) {
+            SLB_TRY(slb_gemm_split(pb, w->map_w_proj, fmt, B, W, w->mlp, w->map_b_proj, head_f32, nullptr, nullptr, SLB_EPI_NONE,
+                                   3, nullptr, pa, stream));
+            SLB_TRY(slb_gemm_split(pa, w->proj, fmt, B, w->embed_dim, W, nullptr, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, out,
+                                   nullptr, stream));
+        } else {
+            SLB_REQUIRE(w->embed_dim == w->width, SLB_EINVAL, "slb_vit_forward: embed_dim must equal width without a projection");
+            SLB_TRY(slb_gemm_split(pb, w->map_w_proj, fmt, B, W, w->mlp, w->map_b_proj, head_f32, nullptr, nullptr, SLB_EPI_NONE,
+                                   3, out, nullptr, stream));
+        }
+    } else if (w->proj) {
+        // ln_post on the class tokens (rows T*W apart), then the projection
         SLB_TRY(slb_layernorm(x, B, W, T * W, w->ln_post_g, w->ln_post_b, w->ln_eps, fmt, nullptr, pa, stream));
         SLB_TRY(slb_gemm_split(pa, w->proj, fmt, B, w->embed_dim, W, nullptr, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, out,
                                nullptr, stream));

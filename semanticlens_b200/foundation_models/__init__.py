@@ -5,6 +5,6 @@ B200 ViT (``slb_vit_forward``: TMA-fed tcgen05 GEMMs on split planes + fp32 Laye
 """
 
 from .base import AbstractVLM
-from .clip import OpenClip
+from .clip import OpenClip, SigLipV2
 
-__all__ = ["AbstractVLM", "OpenClip"]
+__all__ = ["AbstractVLM", "OpenClip", "SigLipV2"]

@@ -30,7 +30,8 @@ class OpenClip(AbstractVLM):
     Parameters
     ----------
     url : str
-        open_clip model name: "ViT-B-32", "ViT-B-32-quickgelu", "ViT-B-16", "ViT-L-14", ... (``vit.CONFIGS``).
+        open_clip model name: "ViT-B-32", "ViT-B-32-quickgelu", "ViT-B-16", "ViT-L-14", "ViT-B-16-SigLIP2",
+        "ViT-L-16-SigLIP-256", ... (``vit.CONFIGS``).
     device : str or torch.device
         Where the tower lives; kernels need a CUDA device.
     **kwargs
@@ -133,6 +134,17 @@ class OpenClip(AbstractVLM):
 
     def tokenize(self, txt, context_length=None):
         raise NotImplementedError("the CLIP tokenizer/text tower is not built yet (SURVEY.md §8 f2)")
+
+
+class SigLipV2(OpenClip):
+    """SigLIP 2 ViT-B/16 image tower on B200 — drop-in for the reference's ``SigLipV2`` (clip.py:190-215:
+    ``OpenClip("hf-hub:timm/ViT-B-16-SigLIP2")``): biased patch conv, no class token, attention-pool head, mean = std =
+    0.5 preprocessing. Weights: ``state_dict=`` / ``checkpoint_path=`` in open_clip naming (``visual.trunk.*``) or random."""
+
+    URL = "hf-hub:timm/ViT-B-16-SigLIP2"
+
+    def __init__(self, device="cpu", **kwargs):
+        super().__init__(url=self.URL, device=device, **kwargs)
 
 
 def _pil_to_chw_u8(im, S: int) -> np.ndarray:

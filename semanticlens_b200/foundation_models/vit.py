@@ -29,10 +29,15 @@ class VitConfig:
     eps: float = 1e-5
     mean: tuple = OPENAI_MEAN
     std: tuple = OPENAI_STD
+    arch: str = "clip"  # "clip": open_clip VisionTransformer; "siglip": timm ViT with the attention-pool head
+
+    @property
+    def has_cls(self) -> bool:
+        return self.arch == "clip"
 
     @property
     def tokens(self) -> int:
-        return (self.image_size // self.patch) ** 2 + 1
+        return (self.image_size // self.patch) ** 2 + (1 if self.has_cls else 0)
 
 
 # open_clip model configs (model_configs/*.json of open-clip-torch 3.0.0), image tower only
@@ -45,10 +50,81 @@ CONFIGS = {
     "ViT-L-14-quickgelu": VitConfig("ViT-L-14-quickgelu", 224, 14, 1024, 24, 16, 4096, 768, act="quick_gelu"),
 }
 
+SIGLIP_MEAN = (0.5, 0.5, 0.5)
+SIGLIP_STD = (0.5, 0.5, 0.5)
+
+
+def _siglip(name, size, patch, width, layers, heads, mlp):
+    return VitConfig(name, size, patch, width, layers, heads, mlp, width, act="gelu_tanh", eps=1e-6, mean=SIGLIP_MEAN,
+                     std=SIGLIP_STD, arch="siglip")
+
+
+# SigLIP image towers (open_clip wraps timm ViTs: biased patch conv, no class token, attention-pool head, no projection)
+CONFIGS.update({
+    "ViT-B-16-SigLIP2": _siglip("ViT-B-16-SigLIP2", 224, 16, 768, 12, 12, 3072),
+    "hf-hub:timm/ViT-B-16-SigLIP2": _siglip("ViT-B-16-SigLIP2", 224, 16, 768, 12, 12, 3072),
+    "ViT-B-16-SigLIP": _siglip("ViT-B-16-SigLIP", 224, 16, 768, 12, 12, 3072),
+    "ViT-L-16-SigLIP-256": _siglip("ViT-L-16-SigLIP-256", 256, 16, 1024, 24, 16, 4096),
+})
+
 _ACT = {"gelu": N.EPI_GELU_ERF, "quick_gelu": N.EPI_QUICKGELU, "gelu_tanh": N.EPI_GELU_TANH}
 
 
 def random_state_dict(cfg: VitConfig, seed: int = 1) -> dict[str, torch.Tensor]:
+    if cfg.arch == "siglip":
+        return _random_siglip_state_dict(cfg, seed)
+    return _random_clip_state_dict(cfg, seed)
+
+
+def _random_siglip_state_dict(cfg: VitConfig, seed: int) -> dict[str, torch.Tensor]:
+    """Random weights in the naming of an open_clip SigLIP checkpoint (``visual.trunk.*`` = the timm ViT)."""
+    g = torch.Generator().manual_seed(seed)
+    W, L = cfg.width, cfg.layers
+    scale = W**-0.5
+
+    def rn(*s):
+        return torch.randn(*s, generator=g)
+
+    t = "visual.trunk."
+    sd = {
+        t + "patch_embed.proj.weight": rn(W, 3, cfg.patch, cfg.patch) * (3 * cfg.patch * cfg.patch) ** -0.5,
+        t + "patch_embed.proj.bias": 0.02 * rn(W),
+        t + "pos_embed": rn(1, cfg.tokens, W) * scale,
+        t + "norm.weight": 1 + 0.1 * rn(W),
+        t + "norm.bias": 0.1 * rn(W),
+        t + "attn_pool.latent": rn(1, 1, W) * scale,
+        t + "attn_pool.q.weight": rn(W, W) * scale,
+        t + "attn_pool.q.bias": 0.02 * rn(W),
+        t + "attn_pool.kv.weight": rn(2 * W, W) * scale,
+        t + "attn_pool.kv.bias": 0.02 * rn(2 * W),
+        t + "attn_pool.proj.weight": rn(W, W) * scale,
+        t + "attn_pool.proj.bias": 0.02 * rn(W),
+        t + "attn_pool.norm.weight": 1 + 0.1 * rn(W),
+        t + "attn_pool.norm.bias": 0.1 * rn(W),
+        t + "attn_pool.mlp.fc1.weight": rn(cfg.mlp, W) * (2 * W) ** -0.5,
+        t + "attn_pool.mlp.fc1.bias": 0.02 * rn(cfg.mlp),
+        t + "attn_pool.mlp.fc2.weight": rn(W, cfg.mlp) * scale * 0.5,
+        t + "attn_pool.mlp.fc2.bias": 0.02 * rn(W),
+    }
+    proj_std = scale * (2 * L) ** -0.5
+    for i in range(L):
+        p = f"{t}blocks.{i}."
+        sd[p + "norm1.weight"] = 1 + 0.1 * rn(W)
+        sd[p + "norm1.bias"] = 0.1 * rn(W)
+        sd[p + "attn.qkv.weight"] = rn(3 * W, W) * scale
+        sd[p + "attn.qkv.bias"] = 0.02 * rn(3 * W)
+        sd[p + "attn.proj.weight"] = rn(W, W) * proj_std
+        sd[p + "attn.proj.bias"] = 0.02 * rn(W)
+        sd[p + "norm2.weight"] = 1 + 0.1 * rn(W)
+        sd[p + "norm2.bias"] = 0.1 * rn(W)
+        sd[p + "mlp.fc1.weight"] = rn(cfg.mlp, W) * (2 * W) ** -0.5
+        sd[p + "mlp.fc1.bias"] = 0.02 * rn(cfg.mlp)
+        sd[p + "mlp.fc2.weight"] = rn(W, cfg.mlp) * proj_std
+        sd[p + "mlp.fc2.bias"] = 0.02 * rn(W)
+    return sd
+
+
+def _random_clip_state_dict(cfg: VitConfig, seed: int = 1) -> dict[str, torch.Tensor]:
     """Random ``visual.*`` weights (no network here, so no pretrained download): embeddings and proj at
     width**-0.5, attention at width**-0.5, MLP at (2*width)**-0.5, output projections depth-scaled."""
     g = torch.Generator().manual_seed(seed)
@@ -135,27 +211,57 @@ class VitTower:
 
         kc = 3 * cfg.patch * cfg.patch
         kpad = N.load().slb_patch_k(cfg.patch)
+        siglip = cfg.arch == "siglip"
+        t = "visual.trunk." if siglip else "visual."
+        # per-block tensor names: (ln1, qkv, out, ln2, fc, proj) in open_clip's and in timm's naming
+        names = (("norm1", "attn.qkv.weight", "attn.qkv.bias", "attn.proj", "norm2", "mlp.fc1", "mlp.fc2") if siglip else
+                 ("ln_1", "attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj", "ln_2", "mlp.c_fc", "mlp.c_proj"))
         conv = torch.zeros(cfg.width, kpad)
-        conv[:, :kc] = sd["visual.conv1.weight"].reshape(cfg.width, kc)
+        conv[:, :kc] = sd[t + ("patch_embed.proj.weight" if siglip else "conv1.weight")].reshape(cfg.width, kc)
         layers = (N.SlbVitLayer * cfg.layers)()
         for i in range(cfg.layers):
-            p = f"visual.transformer.resblocks.{i}."
+            p = f"{t}blocks.{i}." if siglip else f"{t}transformer.resblocks.{i}."
             ly = layers[i]
-            ly.ln1_g, ly.ln1_b = vec(p + "ln_1.weight"), vec(p + "ln_1.bias")
-            ly.w_qkv, ly.b_qkv = planes(sd[p + "attn.in_proj_weight"]), vec(p + "attn.in_proj_bias")
-            ly.w_out, ly.b_out = planes(sd[p + "attn.out_proj.weight"]), vec(p + "attn.out_proj.bias")
-            ly.ln2_g, ly.ln2_b = vec(p + "ln_2.weight"), vec(p + "ln_2.bias")
-            ly.w_fc, ly.b_fc = planes(sd[p + "mlp.c_fc.weight"]), vec(p + "mlp.c_fc.bias")
-            ly.w_proj, ly.b_proj = planes(sd[p + "mlp.c_proj.weight"]), vec(p + "mlp.c_proj.bias")
+            ln1, wqkv, bqkv, out, ln2, fc, proj = names
+            ly.ln1_g, ly.ln1_b = vec(p + ln1 + ".weight"), vec(p + ln1 + ".bias")
+            ly.w_qkv, ly.b_qkv = planes(sd[p + wqkv]), vec(p + bqkv)
+            ly.w_out, ly.b_out = planes(sd[p + out + ".weight"]), vec(p + out + ".bias")
+            ly.ln2_g, ly.ln2_b = vec(p + ln2 + ".weight"), vec(p + ln2 + ".bias")
+            ly.w_fc, ly.b_fc = planes(sd[p + fc + ".weight"]), vec(p + fc + ".bias")
+            ly.w_proj, ly.b_proj = planes(sd[p + proj + ".weight"]), vec(p + proj + ".bias")
         w = N.SlbVitWeights()
         w.image_size, w.patch, w.width, w.layers = cfg.image_size, cfg.patch, cfg.width, cfg.layers
         w.heads, w.mlp, w.embed_dim = cfg.heads, cfg.mlp, cfg.embed_dim
-        w.act, w.plane_fmt, w.has_cls, w.pool, w.ln_eps = _ACT[cfg.act], fmt, 1, 0, cfg.eps
-        w.conv_w, w.conv_b = planes(conv), None
-        w.cls, w.pos = vec("visual.class_embedding"), vec("visual.positional_embedding")
-        w.ln_pre_g, w.ln_pre_b = vec("visual.ln_pre.weight"), vec("visual.ln_pre.bias")
-        w.ln_post_g, w.ln_post_b = vec("visual.ln_post.weight"), vec("visual.ln_post.bias")
-        w.proj = planes(sd["visual.proj"].T.contiguous())
+        w.act, w.plane_fmt, w.ln_eps = _ACT[cfg.act], fmt, cfg.eps
+        w.conv_w = planes(conv)
+        if siglip:
+            w.has_cls, w.pool = 0, N.POOL_MAP
+            w.conv_b = vec(t + "patch_embed.proj.bias")
+            w.cls = None
+            pos = sd[t + "pos_embed"].reshape(cfg.tokens, cfg.width).to(dev).contiguous()
+            keep.append(pos)
+            w.pos = pos.data_ptr()
+            w.ln_pre_g = w.ln_pre_b = None
+            w.ln_post_g, w.ln_post_b = vec(t + "norm.weight"), vec(t + "norm.bias")
+            w.proj = None
+            a = t + "attn_pool."
+            # the latent's q projection does not depend on the image: one tiny host-side matvec at load time
+            mq = (sd[a + "latent"].reshape(1, cfg.width).double() @ sd[a + "q.weight"].double().T + sd[a + "q.bias"].double())
+            mq = mq.float().reshape(cfg.width).to(dev).contiguous()
+            keep.append(mq)
+            w.map_q = mq.data_ptr()
+            w.map_w_kv, w.map_b_kv = planes(sd[a + "kv.weight"]), vec(a + "kv.bias")
+            w.map_w_out, w.map_b_out = planes(sd[a + "proj.weight"]), vec(a + "proj.bias")
+            w.map_ln_g, w.map_ln_b = vec(a + "norm.weight"), vec(a + "norm.bias")
+            w.map_w_fc, w.map_b_fc = planes(sd[a + "mlp.fc1.weight"]), vec(a + "mlp.fc1.bias")
+            w.map_w_proj, w.map_b_proj = planes(sd[a + "mlp.fc2.weight"]), vec(a + "mlp.fc2.bias")
+        else:
+            w.has_cls, w.pool = 1, N.POOL_CLS
+            w.conv_b = None
+            w.cls, w.pos = vec("visual.class_embedding"), vec("visual.positional_embedding")
+            w.ln_pre_g, w.ln_pre_b = vec("visual.ln_pre.weight"), vec("visual.ln_pre.bias")
+            w.ln_post_g, w.ln_post_b = vec("visual.ln_post.weight"), vec("visual.ln_post.bias")
+            w.proj = planes(sd["visual.proj"].T.contiguous())
         w.layer = layers
         keep.append(layers)
         self._struct = w
@@ -192,6 +298,8 @@ class VitTower:
 
 
 def random_state_dict_keys(cfg: VitConfig) -> list[str]:
+    if cfg.arch == "siglip":
+        return list(_random_siglip_state_dict(VitConfig(cfg.name, cfg.patch, cfg.patch, 8, cfg.layers, 1, 8, 8, arch="siglip"), 0))
     keys = ["visual.conv1.weight", "visual.class_embedding", "visual.positional_embedding", "visual.ln_pre.weight",
             "visual.ln_pre.bias", "visual.ln_post.weight", "visual.ln_post.bias", "visual.proj"]
     for i in range(cfg.layers):
@@ -206,4 +314,5 @@ def flops_per_image(cfg: VitConfig) -> float:
     """2*MAC of the GEMMs and attention of one image (algorithmic, single pass)."""
     T, W = cfg.tokens, cfg.width
     per_layer = 2 * T * W * (3 * W + W + 2 * cfg.mlp) + 2 * 2 * T * T * W
-    return (T - 1) * 2 * W * 3 * cfg.patch**2 + cfg.layers * per_layer + 2 * W * cfg.embed_dim
+    tail = 2 * W * cfg.embed_dim if cfg.arch == "clip" else 2 * T * W * 2 * W + 2 * 2 * T * W + 2 * W * W + 4 * W * cfg.mlp
+    return (T - cfg.has_cls) * 2 * W * 3 * cfg.patch**2 + cfg.layers * per_layer + tail

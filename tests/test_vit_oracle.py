@@ -60,6 +60,63 @@ def test_oracle_tower_matches_hf_clip(name):
     assert (got.double() - hi).abs().max() <= 1e-5 * hi.abs().max()
 
 
+def hf_siglip(cfg, sd):
+    transformers = pytest.importorskip("transformers")
+    hc = transformers.SiglipVisionConfig(
+        hidden_size=cfg.width, intermediate_size=cfg.mlp, num_hidden_layers=cfg.layers, num_attention_heads=cfg.heads,
+        image_size=cfg.image_size, patch_size=cfg.patch, hidden_act="gelu_pytorch_tanh", layer_norm_eps=cfg.eps,
+    )
+    m = transformers.SiglipVisionModel(hc).eval()
+    W, t = cfg.width, "visual.trunk."
+    new = {
+        "vision_model.embeddings.patch_embedding.weight": sd[t + "patch_embed.proj.weight"],
+        "vision_model.embeddings.patch_embedding.bias": sd[t + "patch_embed.proj.bias"],
+        "vision_model.embeddings.position_embedding.weight": sd[t + "pos_embed"][0],
+        "vision_model.post_layernorm.weight": sd[t + "norm.weight"],
+        "vision_model.post_layernorm.bias": sd[t + "norm.bias"],
+        "vision_model.head.probe": sd[t + "attn_pool.latent"],
+        # HF packs the head's projections like nn.MultiheadAttention: [q; k; v]
+        "vision_model.head.attention.in_proj_weight": torch.cat([sd[t + "attn_pool.q.weight"], sd[t + "attn_pool.kv.weight"]]),
+        "vision_model.head.attention.in_proj_bias": torch.cat([sd[t + "attn_pool.q.bias"], sd[t + "attn_pool.kv.bias"]]),
+        "vision_model.head.attention.out_proj.weight": sd[t + "attn_pool.proj.weight"],
+        "vision_model.head.attention.out_proj.bias": sd[t + "attn_pool.proj.bias"],
+        "vision_model.head.layernorm.weight": sd[t + "attn_pool.norm.weight"],
+        "vision_model.head.layernorm.bias": sd[t + "attn_pool.norm.bias"],
+        "vision_model.head.mlp.fc1.weight": sd[t + "attn_pool.mlp.fc1.weight"],
+        "vision_model.head.mlp.fc1.bias": sd[t + "attn_pool.mlp.fc1.bias"],
+        "vision_model.head.mlp.fc2.weight": sd[t + "attn_pool.mlp.fc2.weight"],
+        "vision_model.head.mlp.fc2.bias": sd[t + "attn_pool.mlp.fc2.bias"],
+    }
+    for i in range(cfg.layers):
+        p, q = f"{t}blocks.{i}.", f"vision_model.encoder.layers.{i}."
+        wi, bi = sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"]
+        for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
+            new[q + f"self_attn.{n}.weight"] = wi[j * W : (j + 1) * W]
+            new[q + f"self_attn.{n}.bias"] = bi[j * W : (j + 1) * W]
+        new[q + "self_attn.out_proj.weight"], new[q + "self_attn.out_proj.bias"] = sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"]
+        new[q + "layer_norm1.weight"], new[q + "layer_norm1.bias"] = sd[p + "norm1.weight"], sd[p + "norm1.bias"]
+        new[q + "layer_norm2.weight"], new[q + "layer_norm2.bias"] = sd[p + "norm2.weight"], sd[p + "norm2.bias"]
+        new[q + "mlp.fc1.weight"], new[q + "mlp.fc1.bias"] = sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]
+        new[q + "mlp.fc2.weight"], new[q + "mlp.fc2.bias"] = sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"]
+    missing, unexpected = m.load_state_dict(new, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    return m
+
+
+def test_oracle_siglip_tower_matches_hf_siglip():
+    cfg = vp.SIGLIP_CONFIGS["SigLIP-tiny-test"]
+    sd = vp.init_siglip_weights(cfg, seed=4)
+    m = hf_siglip(cfg, sd)
+    img = torch.randn(3, 3, cfg.image_size, cfg.image_size, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        want = m(pixel_values=img).pooler_output
+    got = vp.encode_image_siglip(sd, cfg, img)
+    assert got.shape == (3, cfg.width)
+    assert (got - want).abs().max() <= 2e-5 * want.abs().max()
+    hi = vp.encode_image_siglip(sd, cfg, img, dtype=torch.float64)
+    assert (got.double() - hi).abs().max() <= 1e-5 * hi.abs().max()
+
+
 def test_preprocess_u8_is_totensor_normalize():
     cfg = vp.CONFIGS["ViT-tiny-test"]
     u8 = torch.randint(0, 256, (2, 3, 32, 32), dtype=torch.uint8)
