@@ -219,7 +219,8 @@ int slb_attention_small(const float* q, int64_t q_batch_stride, int64_t q_row_st
  * (packed nn.MultiheadAttention layout: q | k | v along the last axis): no fp32 round trip, no conversion in the
  * kernel (cp.async + ldmatrix + mma.sync). out as in slb_attention_small. */
 int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, int64_t dh, float scale,
-                         int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream);
+                         int causal /* 1: key j visible to query i only if j <= i */, int plane_fmt, float* out_f32,
+                         uint16_t* out_planes, void* stream);
 
 /* The whole CLIP / SigLIP ViT image tower in one call (open_clip VisionTransformer.forward, or its timm ViT with the
  * attention-pool head for SigLIP, behind clip.py:103-118).
@@ -267,6 +268,27 @@ size_t slb_vit_workspace_bytes(const SlbVitWeights* w, int64_t B);
  * workspace: 256-byte aligned device memory of at least slb_vit_workspace_bytes(w, B). */
 int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t B, float* out, void* workspace,
                     size_t workspace_bytes, void* stream);
+
+/* The CLIP text tower in one call (open_clip CLIP.encode_text behind clip.py:120-135; reached from Lens.text_probing,
+ * lens.py:166-203): token + positional embedding, `layers` pre-LN blocks with a causal mask, ln_final, the end-of-text
+ * token's feature times text_projection; un-normalised. head_dim must be 64 and plane_fmt fp16 (tensor-core attention). */
+typedef struct {
+    int32_t context, vocab, width, layers, heads, mlp, embed_dim;
+    int32_t act, plane_fmt;
+    float ln_eps;
+    const float* tok_emb;  /* [vocab, W] */
+    const float* pos;      /* [context, W] */
+    const float* ln_final_g; const float* ln_final_b;
+    const uint16_t* proj;  /* planes [2, embed_dim, W] (= text_projection transposed) */
+    const SlbVitLayer* layer; /* HOST array */
+} SlbTextWeights;
+
+size_t slb_text_workspace_bytes(const SlbTextWeights* w, int64_t B);
+
+/* tokens (B, context) int64 device; eot_rows (B,) int64 device = b * context + argmax_t tokens[b, t] (computed by the
+ * caller); out (B, embed_dim) fp32. workspace: 256-byte aligned, >= slb_text_workspace_bytes(w, B). */
+int slb_text_forward(const SlbTextWeights* w, const int64_t* tokens, const int64_t* eot_rows, int64_t B, float* out,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

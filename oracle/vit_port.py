@@ -306,3 +306,87 @@ def encode_image_siglip(sd: dict, cfg: SigLipConfig, img: torch.Tensor, dtype=to
     h = _act(F.linear(h, w[a + "mlp.fc1.weight"], w[a + "mlp.fc1.bias"]), cfg.act)
     o = o + F.linear(h, w[a + "mlp.fc2.weight"], w[a + "mlp.fc2.bias"])
     return o[:, 0]
+
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP text tower (reference: foundation_models/clip.py:120-135 -> open_clip CLIP.encode_text, third-party): token
+# embedding + positional embedding, pre-LN blocks with a CAUSAL attention mask, ln_final, the feature of the end-of-text
+# token (the position of the largest token id) times text_projection; un-normalised. Pinned against HF transformers'
+# CLIPTextModelWithProjection (tests/test_vit_oracle.py).
+# ------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class TextConfig:
+    name: str
+    context: int
+    vocab: int
+    width: int
+    layers: int
+    heads: int
+    embed_dim: int
+    act: str = "gelu"
+    eps: float = 1e-5
+
+    @property
+    def mlp(self):
+        return 4 * self.width
+
+
+TEXT_CONFIGS = {
+    "ViT-B-32": TextConfig("ViT-B-32", 77, 49408, 512, 12, 8, 512),
+    "ViT-L-14": TextConfig("ViT-L-14", 77, 49408, 768, 12, 12, 768),
+    "text-tiny-test": TextConfig("text-tiny-test", 12, 100, 128, 2, 2, 32),
+}
+
+
+def init_text_weights(cfg: TextConfig, seed: int = 1) -> dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    W, L = cfg.width, cfg.layers
+    rn = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
+    sd = {
+        "token_embedding.weight": rn(cfg.vocab, W) * 0.02,
+        "positional_embedding": rn(cfg.context, W) * 0.01,
+        "ln_final.weight": 1 + 0.1 * rn(W),
+        "ln_final.bias": 0.1 * rn(W),
+        "text_projection": rn(W, cfg.embed_dim) * W**-0.5,
+    }
+    proj_std = W**-0.5 * (2 * L) ** -0.5
+    for i in range(L):
+        p = f"transformer.resblocks.{i}."
+        sd[p + "ln_1.weight"] = 1 + 0.1 * rn(W)
+        sd[p + "ln_1.bias"] = 0.1 * rn(W)
+        sd[p + "attn.in_proj_weight"] = rn(3 * W, W) * W**-0.5
+        sd[p + "attn.in_proj_bias"] = 0.02 * rn(3 * W)
+        sd[p + "attn.out_proj.weight"] = rn(W, W) * proj_std
+        sd[p + "attn.out_proj.bias"] = 0.02 * rn(W)
+        sd[p + "ln_2.weight"] = 1 + 0.1 * rn(W)
+        sd[p + "ln_2.bias"] = 0.1 * rn(W)
+        sd[p + "mlp.c_fc.weight"] = rn(cfg.mlp, W) * (2 * W) ** -0.5
+        sd[p + "mlp.c_fc.bias"] = 0.02 * rn(cfg.mlp)
+        sd[p + "mlp.c_proj.weight"] = rn(W, cfg.mlp) * proj_std
+        sd[p + "mlp.c_proj.bias"] = 0.02 * rn(W)
+    return sd
+
+
+@torch.no_grad()
+def encode_text(sd: dict, cfg: TextConfig, tokens: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    """(B, context) int64 token ids -> (B, embed_dim) un-normalised text features."""
+    w = {k: v.to(device=tokens.device, dtype=dtype) for k, v in sd.items()}
+    B, T = tokens.shape
+    W, H = cfg.width, cfg.heads
+    dh = W // H
+    x = w["token_embedding.weight"][tokens] + w["positional_embedding"][:T]
+    mask = torch.full((T, T), float("-inf"), dtype=dtype, device=tokens.device).triu(1)
+    for i in range(cfg.layers):
+        p = f"transformer.resblocks.{i}."
+        h = F.layer_norm(x, (W,), w[p + "ln_1.weight"], w[p + "ln_1.bias"], cfg.eps)
+        qkv = F.linear(h, w[p + "attn.in_proj_weight"], w[p + "attn.in_proj_bias"])
+        q, k, v = (t.view(B, T, H, dh).transpose(1, 2) for t in qkv.split(W, dim=-1))
+        att = torch.softmax((q * dh**-0.5) @ k.transpose(-1, -2) + mask, dim=-1)
+        o = (att @ v).transpose(1, 2).reshape(B, T, W)
+        x = x + F.linear(o, w[p + "attn.out_proj.weight"], w[p + "attn.out_proj.bias"])
+        h = F.layer_norm(x, (W,), w[p + "ln_2.weight"], w[p + "ln_2.bias"], cfg.eps)
+        h = _act(F.linear(h, w[p + "mlp.c_fc.weight"], w[p + "mlp.c_fc.bias"]), cfg.act)
+        x = x + F.linear(h, w[p + "mlp.c_proj.weight"], w[p + "mlp.c_proj.bias"])
+    x = F.layer_norm(x, (W,), w["ln_final.weight"], w["ln_final.bias"], cfg.eps)
+    return x[torch.arange(B, device=tokens.device), tokens.argmax(dim=-1)] @ w["text_projection"]

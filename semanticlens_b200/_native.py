@@ -80,7 +80,9 @@ _PROTOS = {
          c_float, c_int, c_void_p, c_void_p, c_void_p],
     ),
     "slb_attention_planes": (
-        c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p]),
+        c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "slb_text_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
+    "slb_text_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "slb_patch_k": (c_int64, [c_int64]),
     "slb_vit_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "slb_vit_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -123,6 +125,15 @@ class SlbVitWeights(ctypes.Structure):
         + [("layer", ctypes.POINTER(SlbVitLayer))]
         + [(n, c_void_p) for n in ("map_q", "map_w_kv", "map_b_kv", "map_w_out", "map_b_out", "map_ln_g", "map_ln_b",
                                    "map_w_fc", "map_b_fc", "map_w_proj", "map_b_proj")]
+    )
+
+
+class SlbTextWeights(ctypes.Structure):
+    _fields_ = (
+        [(n, ctypes.c_int32) for n in ("context", "vocab", "width", "layers", "heads", "mlp", "embed_dim", "act", "plane_fmt")]
+        + [("ln_eps", c_float)]
+        + [(n, c_void_p) for n in ("tok_emb", "pos", "ln_final_g", "ln_final_b", "proj")]
+        + [("layer", ctypes.POINTER(SlbVitLayer))]
     )
 
 

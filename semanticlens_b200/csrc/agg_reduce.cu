@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, 2) agg_rows_staged_kernel(RowsParams
 }
 
 // ------------------------------------------------------------------------------------------------
-// NCHW, staged, SHORT rows (L <= 128, fp32): G = 8 or 16 lanes fold one row, so a warp folds 32/G rows at a time
+// NCHW, staged, SHORT rows (L <= 256, fp32): G = 8 or 16 lanes fold one row, so a warp folds 32/G rows at a time
 // instead of idling most of its lanes (a 7x7 map is 49 elements). Bit-identical to the canonical order: lane g of a
 // group owns the accumulator slots s = g, g + G, ... of the 32-slot layout; a slot's tree8 over its <= NWS elements
 // (missing ones are the identity, folded at compile time), then the butterfly levels 16, 8 (, ...) >= G are local
@@ -584,8 +584,8 @@ int launch_rows(const void* x, float* out, int64_t n_rows, int64_t L, cudaStream
     const size_t smem = (size_t)kStages * kStageBytes + sizeof(RowsSmem);
 
     if constexpr (sizeof(T) == 4) {
-        // short rows: sub-warp groups (fp32 maps; L <= 128)
-        if (aligned && !force_direct() && R >= kWarps && L <= 128) {
+        // short rows: sub-warp groups (fp32 maps; L <= 256: one 256-element block of the canonical order)
+        if (aligned && !force_direct() && R >= kWarps && L <= 256) {
             RowsParams p{};
             p.x = x; p.out = out; p.n_rows = n_rows; p.L = (int)L;
             p.rows_per_tile = (int)R;
@@ -601,7 +601,11 @@ int launch_rows(const void* x, float* out, int64_t n_rows, int64_t L, cudaStream
             if (nws == 1) SLB_SUBWARP(8, 1)
             else if (nws == 2) SLB_SUBWARP(8, 2)
             else if (nws == 3) SLB_SUBWARP(16, 3)
-            else SLB_SUBWARP(16, 4)
+            else if (nws == 4) SLB_SUBWARP(16, 4)
+            else if (nws == 5) SLB_SUBWARP(16, 5)
+            else if (nws == 6) SLB_SUBWARP(16, 6)
+            else if (nws == 7) SLB_SUBWARP(16, 7)
+            else SLB_SUBWARP(16, 8)
 #undef SLB_SUBWARP
             SLB_LAUNCH_OK("agg_rows_subwarp");
             return SLB_OK;

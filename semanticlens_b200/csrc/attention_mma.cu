@@ -253,6 +253,7 @@ struct AttnPlanesParams {
     const __half* hi;  // [rows][3W]
     const __half* lo;
     int T, Tkp, H, W;
+    int causal;  // 1: key j is visible to query i only if j <= i (CLIP text tower)
     float scale;
     float* out_f32; uint16_t* out_hi; uint16_t* out_lo; int fmt;
 };
@@ -361,7 +362,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
             const int col = kb0 + nt * 8 + t4 * 2;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const bool ok = nt < nkt && (col + (j & 1)) < p.T;
+                const int c = col + (j & 1);
+                const bool ok = nt < nkt && c < p.T && (!p.causal || c <= r0 + g + (j >> 1) * 8);
                 s[nt][j] = ok ? fmaf(sc_[j], sc_corr, sm_[j] * sc_main) : -INFINITY;
             }
         }
@@ -498,7 +500,7 @@ int slb_attention_mma_dh64(const float* q, int64_t q_bs, int64_t q_rs, const flo
 }
 
 extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, int64_t dh, float scale,
-                                    int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream) {
+                                    int causal, int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream) {
     SLB_REQUIRE(B >= 0 && T > 0 && H > 0, SLB_EINVAL, "slb_attention_planes: bad size");
     if (B == 0) return SLB_OK;
     SLB_REQUIRE(qkv_planes && (out_f32 || out_planes), SLB_EINVAL, "slb_attention_planes: null pointer");
@@ -514,6 +516,7 @@ extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64
     p.lo = p.hi + rows * 3 * W;
     p.T = (int)T; p.Tkp = (int)((T + 15) / 16 * 16); p.H = (int)H; p.W = (int)W;
     p.scale = scale;
+    p.causal = causal ? 1 : 0;
     p.out_f32 = out_f32; p.out_hi = out_planes; p.out_lo = out_planes ? out_planes + rows * W : nullptr; p.fmt = plane_fmt;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (T <= 64) return launch_attn_planes<4, 3>(p, B, st);

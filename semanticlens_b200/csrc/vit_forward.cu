@@ -39,6 +39,44 @@ bool layout_for(const SlbVitWeights* w, int64_t B, WsLayout* L) {
     return true;
 }
 
+// `layers` pre-LN residual blocks on x (rows = B*T, fp32 residual stream): x += attn(ln_1(x)); x += mlp(ln_2(x)).
+// Shared by the image towers (causal = 0) and the CLIP text tower (causal = 1).
+int run_blocks(const SlbVitLayer* layer, int n_layers, float* x, float* qkv, uint16_t* pa, uint16_t* pb, int64_t B, int64_t T,
+               int64_t W, int heads, int64_t mlp, int act, int fmt, float eps, int causal, void* stream) {
+    const int64_t rows = B * T, dh = W / heads;
+    int rc;
+#define SLB_TRY(call)            \
+    do {                         \
+        rc = (call);             \
+        if (rc != SLB_OK) return rc; \
+    } while (0)
+    for (int l = 0; l < n_layers; ++l) {
+        const SlbVitLayer& ly = layer[l];
+        SLB_TRY(slb_layernorm(x, rows, W, W, ly.ln1_g, ly.ln1_b, eps, fmt, nullptr, pa, stream));
+        if (fmt == SLB_PLANE_F16 && dh == 64) {
+            // in_proj writes q | k | v as split planes (same bytes as fp32) and attention consumes them directly
+            uint16_t* qkv_planes = reinterpret_cast<uint16_t*>(qkv);
+            SLB_TRY(slb_gemm_split(pa, ly.w_qkv, fmt, rows, 3 * W, W, ly.b_qkv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
+                                   nullptr, qkv_planes, stream));
+            SLB_TRY(slb_attention_planes(qkv_planes, B, T, heads, dh, 1.0f / sqrtf((float)dh), causal, fmt, nullptr, pb, stream));
+        } else {
+            SLB_REQUIRE(!causal, SLB_EUNSUPPORTED, "causal attention needs head_dim 64 and fp16 planes");
+            SLB_TRY(slb_gemm_split(pa, ly.w_qkv, fmt, rows, 3 * W, W, ly.b_qkv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
+                                   qkv, nullptr, stream));
+            SLB_TRY(slb_attention_small(qkv, T * 3 * W, 3 * W, qkv + W, qkv + 2 * W, T * 3 * W, 3 * W, B, T, T, heads, dh,
+                                        1.0f / sqrtf((float)dh), fmt, nullptr, pb, stream));
+        }
+        SLB_TRY(slb_gemm_split(pb, ly.w_out, fmt, rows, W, W, ly.b_out, x, nullptr, nullptr, SLB_EPI_NONE, 3, x, nullptr,
+                               stream));
+        SLB_TRY(slb_layernorm(x, rows, W, W, ly.ln2_g, ly.ln2_b, eps, fmt, nullptr, pa, stream));
+        SLB_TRY(slb_gemm_split(pa, ly.w_fc, fmt, rows, mlp, W, ly.b_fc, nullptr, nullptr, nullptr, act, 3, nullptr, pb, stream));
+        SLB_TRY(slb_gemm_split(pb, ly.w_proj, fmt, rows, W, mlp, ly.b_proj, x, nullptr, nullptr, SLB_EPI_NONE, 3, x, nullptr,
+                               stream));
+    }
+#undef SLB_TRY
+    return SLB_OK;
+}
+
 }  // namespace
 
 extern "C" size_t slb_vit_workspace_bytes(const SlbVitWeights* w, int64_t B) {
@@ -95,29 +133,7 @@ extern "C" int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t
     SLB_TRY(slb_assemble_tokens(patch_f32, w->cls, w->pos, B, T, W, w->has_cls ? 1 : 0, x, stream));
     if (w->ln_pre_g) SLB_TRY(slb_layernorm(x, rows, W, W, w->ln_pre_g, w->ln_pre_b, w->ln_eps, fmt, x, nullptr, stream));
 
-    for (int l = 0; l < w->layers; ++l) {
-        const SlbVitLayer& ly = w->layer[l];
-        SLB_TRY(slb_layernorm(x, rows, W, W, ly.ln1_g, ly.ln1_b, w->ln_eps, fmt, nullptr, pa, stream));
-        if (fmt == SLB_PLANE_F16 && dh == 64) {
-            // in_proj writes q | k | v as split planes (same bytes as fp32) and attention consumes them directly
-            uint16_t* qkv_planes = reinterpret_cast<uint16_t*>(qkv);
-            SLB_TRY(slb_gemm_split(pa, ly.w_qkv, fmt, rows, 3 * W, W, ly.b_qkv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
-                                   nullptr, qkv_planes, stream));
-            SLB_TRY(slb_attention_planes(qkv_planes, B, T, w->heads, dh, 1.0f / sqrtf((float)dh), fmt, nullptr, pb, stream));
-        } else {
-            SLB_TRY(slb_gemm_split(pa, ly.w_qkv, fmt, rows, 3 * W, W, ly.b_qkv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
-                                   qkv, nullptr, stream));
-            SLB_TRY(slb_attention_small(qkv, T * 3 * W, 3 * W, qkv + W, qkv + 2 * W, T * 3 * W, 3 * W, B, T, T, w->heads,
-                                        dh, 1.0f / sqrtf((float)dh), fmt, nullptr, pb, stream));
-        }
-        SLB_TRY(slb_gemm_split(pb, ly.w_out, fmt, rows, W, W, ly.b_out, x, nullptr, nullptr, SLB_EPI_NONE, 3, x, nullptr,
-                               stream));
-        SLB_TRY(slb_layernorm(x, rows, W, W, ly.ln2_g, ly.ln2_b, w->ln_eps, fmt, nullptr, pa, stream));
-        SLB_TRY(slb_gemm_split(pa, ly.w_fc, fmt, rows, w->mlp, W, ly.b_fc, nullptr, nullptr, nullptr, w->act, 3, nullptr, pb,
-                               stream));
-        SLB_TRY(slb_gemm_split(pb, ly.w_proj, fmt, rows, W, w->mlp, ly.b_proj, x, nullptr, nullptr, SLB_EPI_NONE, 3, x,
-                               nullptr, stream));
-    }
+    SLB_TRY(run_blocks(w->layer, w->layers, x, qkv, pa, pb, B, T, W, w->heads, w->mlp, w->act, fmt, w->ln_eps, 0, stream));
 
     if (w->pool == SLB_POOL_MAP) {
         // final LayerNorm over ALL tokens, then the attention-pool head (timm AttentionPoolLatent / HF Siglip "MAP" head)
@@ -153,4 +169,72 @@ extern "C" int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t
     }
 #undef SLB_TRY
     return SLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CLIP text tower
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct TextLayout {
+    size_t x, qkv, planes_a, planes_b, emb, head, total;
+};
+bool text_layout(const SlbTextWeights* w, int64_t B, TextLayout* L) {
+    if (!w || w->context <= 0 || w->width <= 0) return false;
+    const int64_t rows = B * w->context, W = w->width;
+    size_t o = 0;
+    L->x = o;         o += align_up((size_t)rows * W * 4);
+    L->qkv = o;       o += align_up((size_t)rows * 3 * W * 4);
+    L->planes_a = o;  o += align_up((size_t)2 * rows * W * 2);
+    L->planes_b = o;  o += align_up(std::max<size_t>((size_t)2 * rows * w->mlp * 2, (size_t)2 * rows * W * 2));
+    L->emb = o;       o += align_up((size_t)rows * W * 4);
+    L->head = o;      o += align_up((size_t)B * W * 4);
+    L->total = o;
+    return true;
+}
+}  // namespace
+
+extern "C" size_t slb_text_workspace_bytes(const SlbTextWeights* w, int64_t B) {
+    TextLayout L;
+    if (B < 0 || !text_layout(w, B, &L)) return 0;
+    return L.total;
+}
+
+extern "C" int slb_text_forward(const SlbTextWeights* w, const int64_t* tokens, const int64_t* eot_rows, int64_t B, float* out,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    SLB_REQUIRE(w != nullptr && B >= 0, SLB_EINVAL, "slb_text_forward: bad arguments");
+    if (B == 0) return SLB_OK;
+    SLB_REQUIRE(tokens && eot_rows && out && workspace, SLB_EINVAL, "slb_text_forward: null pointer");
+    SLB_REQUIRE(w->tok_emb && w->pos && w->ln_final_g && w->proj && (w->layer || w->layers == 0), SLB_EINVAL,
+                "slb_text_forward: incomplete weights");
+    SLB_REQUIRE(w->width % 64 == 0 && w->mlp % 64 == 0 && w->heads > 0 && w->width == 64 * w->heads, SLB_EUNSUPPORTED,
+                "slb_text_forward: width must be 64 * heads");
+    SLB_REQUIRE(w->plane_fmt == SLB_PLANE_F16, SLB_EUNSUPPORTED, "slb_text_forward: fp16 planes only");
+    TextLayout L;
+    SLB_REQUIRE(text_layout(w, B, &L), SLB_EINVAL, "slb_text_forward: bad configuration");
+    SLB_REQUIRE(((uintptr_t)workspace % 256) == 0, SLB_EINVAL, "slb_text_forward: workspace must be 256-byte aligned");
+    SLB_REQUIRE(workspace_bytes >= L.total, SLB_EWORKSPACE, "slb_text_forward: workspace needs %zu bytes, got %zu", L.total,
+                workspace_bytes);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    float* x = reinterpret_cast<float*>(ws + L.x);
+    float* qkv = reinterpret_cast<float*>(ws + L.qkv);
+    uint16_t* pa = reinterpret_cast<uint16_t*>(ws + L.planes_a);
+    uint16_t* pb = reinterpret_cast<uint16_t*>(ws + L.planes_b);
+    float* emb = reinterpret_cast<float*>(ws + L.emb);
+    float* head = reinterpret_cast<float*>(ws + L.head);
+    const int64_t T = w->context, W = w->width;
+    int rc;
+    // x = token_embedding[tokens] + positional_embedding
+    rc = slb_gather_rows(w->tok_emb, w->vocab, W, tokens, B * T, emb, stream);
+    if (rc != SLB_OK) return rc;
+    rc = slb_assemble_tokens(emb, nullptr, w->pos, B, T, W, 0, x, stream);
+    if (rc != SLB_OK) return rc;
+    rc = run_blocks(w->layer, w->layers, x, qkv, pa, pb, B, T, W, w->heads, w->mlp, w->act, w->plane_fmt, w->ln_eps, 1, stream);
+    if (rc != SLB_OK) return rc;
+    // ln_final acts per token, so it commutes with picking the end-of-text rows: gather first, normalise B rows
+    rc = slb_gather_rows(x, B * T, W, eot_rows, B, head, stream);
+    if (rc != SLB_OK) return rc;
+    rc = slb_layernorm(head, B, W, W, w->ln_final_g, w->ln_final_b, w->ln_eps, w->plane_fmt, nullptr, pa, stream);
+    if (rc != SLB_OK) return rc;
+    return slb_gemm_split(pa, w->proj, w->plane_fmt, B, w->embed_dim, W, nullptr, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, out,
+                          nullptr, stream);
 }

@@ -6,8 +6,9 @@ dependency that is not vendored (and there is no network here), so this class re
 the image path: the model config of ``url``, the eval transform (Resize(bicubic) -> CenterCrop -> RGB -> ToTensor ->
 Normalize with the OpenAI mean/std) and the ``VisionTransformer`` forward. Weights come from ``state_dict=`` /
 ``checkpoint_path=`` (open_clip naming, ``visual.*``) or are randomly initialised (``load_weights=False`` in the
-reference's own tests does the same). The text tower (``encode_text`` / ``tokenize``) is not on the concept-DB build
-path and is not built yet.
+reference's own tests does the same). The CLIP text tower (``encode_text``, causal transformer on the same kernels) and
+a BPE tokenizer in open_clip's scheme (``tokenize``; needs CLIP's merges file, ``bpe_path=``) serve
+``Lens.text_probing``.
 """
 
 from __future__ import annotations
@@ -18,6 +19,7 @@ import numpy as np
 import torch
 
 from .. import _native as N
+from . import text as text_mod
 from . import vit
 from .base import AbstractVLM
 
@@ -46,6 +48,8 @@ class OpenClip(AbstractVLM):
         self.url = url
         self.cfg = vit.CONFIGS[url]
         sd = kwargs.pop("state_dict", None)
+        given_sd = sd is not None
+        bpe_path = kwargs.pop("bpe_path", None)
         ckpt = kwargs.pop("checkpoint_path", None)
         seed = kwargs.pop("seed", 1)
         fmt = {"f16": N.PLANE_F16, "bf16": N.PLANE_BF16}[kwargs.pop("plane_format", "f16")]
@@ -60,6 +64,12 @@ class OpenClip(AbstractVLM):
                 logger.warning("pretrained='%s' cannot be downloaded here; using random weights (seed %d)", pretrained, seed)
             sd = vit.random_state_dict(self.cfg, seed)
         self.model = vit.VitTower(self.cfg, sd, device, fmt)
+        # text side: built lazily (encode_text / tokenize), only for the CLIP towers
+        self._text_sd = {k: v for k, v in sd.items() if not k.startswith("visual.")} if ckpt or given_sd else None
+        self._text_seed = seed
+        self._bpe_path = bpe_path
+        self._text: text_mod.TextTower | None = None
+        self._tokenizer: text_mod.SimpleTokenizer | None = None
         self._pin: list = [(None, None), (None, None)]  # (pinned staging buffer, event of its last H2D copy)
         self._pin_next = 0
 
@@ -128,12 +138,32 @@ class OpenClip(AbstractVLM):
             out[i] = _pil_to_chw_u8(im, S)
         return torch.from_numpy(out)
 
-    # -- text side (not on the concept-DB build path) -------------------------------------------------------
+    # -- text side (Lens.text_probing) --------------------------------------------------------
+    def _text_tower(self) -> "text_mod.TextTower":
+        if self._text is None:
+            tcfg = text_mod.TEXT_CONFIGS.get(self.url)
+            if tcfg is None:
+                raise NotImplementedError(f"no CLIP text tower is built for '{self.url}' (SigLIP text towers are not built)")
+            sd = self._text_sd
+            if not sd or "token_embedding.weight" not in sd:
+                sd = text_mod.random_text_state_dict(tcfg, self._text_seed)
+            self._text = text_mod.TextTower(tcfg, sd, self.device)
+        return self._text.to(self.device)
+
     def encode_text(self, text_input: torch.Tensor):
-        raise NotImplementedError("the CLIP text tower is not built yet (SURVEY.md §8 f2); pass text embeddings to Lens")
+        """(B, context_length) token ids -> (B, D) un-normalised text features on the GPU (reference :120-135)."""
+        with torch.no_grad():
+            return self._text_tower().forward(text_input)
 
     def tokenize(self, txt, context_length=None):
-        raise NotImplementedError("the CLIP tokenizer/text tower is not built yet (SURVEY.md §8 f2)")
+        """str or list[str] -> (n, context_length) int64 token ids on ``device`` (reference :165-187). Needs CLIP's BPE
+        merges file: ``OpenClip(..., bpe_path=...)`` or ``SLB_CLIP_BPE``."""
+        if self._tokenizer is None:
+            tcfg = text_mod.TEXT_CONFIGS.get(self.url)
+            if tcfg is None:
+                raise NotImplementedError(f"no tokenizer is built for '{self.url}'")
+            self._tokenizer = text_mod.SimpleTokenizer(self._bpe_path, context_length=tcfg.context)
+        return self._tokenizer(txt, context_length).to(self.device)
 
 
 class SigLipV2(OpenClip):

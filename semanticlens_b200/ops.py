@@ -336,7 +336,7 @@ def attention_packed(qkv: torch.Tensor, heads: int, fmt: int | None = None):
     return out if fmt is None else planes
 
 
-def attention_planes(qkv_planes: torch.Tensor, B: int, heads: int, fmt: int | None = None):
+def attention_planes(qkv_planes: torch.Tensor, B: int, heads: int, fmt: int | None = None, causal: bool = False):
     """Attention straight from the in_proj GEMM's split planes (2, B*T, 3W) fp16 -> (B, T, W) fp32 or planes (2, B*T, W)."""
     lib = N.load(require_device=True)
     N.require_cuda(qkv_planes, "qkv_planes")
@@ -347,7 +347,8 @@ def attention_planes(qkv_planes: torch.Tensor, B: int, heads: int, fmt: int | No
     out = torch.empty((B, T, W), dtype=torch.float32, device=qkv_planes.device) if fmt is None else None
     planes = torch.empty((2, rows, W), dtype=PLANE_DTYPES[fmt], device=qkv_planes.device) if fmt is not None else None
     with _dev_guard(qkv_planes):
-        rc = lib.slb_attention_planes(qkv_planes.data_ptr(), B, T, heads, dh, float(dh) ** -0.5, N.PLANE_F16, N.ptr(out),
+        rc = lib.slb_attention_planes(qkv_planes.data_ptr(), B, T, heads, dh, float(dh) ** -0.5, 1 if causal else 0,
+                                      N.PLANE_F16, N.ptr(out),
                                       N.ptr(planes), N.stream_ptr(qkv_planes.device))
     N.check(rc, "slb_attention_planes")
     return out if fmt is None else planes

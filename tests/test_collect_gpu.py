@@ -60,7 +60,11 @@ CONV_SHAPES = [
     (9, 33, 8, 8),  # L = 64: sub-warp rows, 8 lanes per row, two columns
     (7, 11, 9, 9),  # L = 81: 16 lanes per row, three columns
     (5, 13, 10, 10),  # L = 100
-    (6, 10, 8, 16),  # L = 128: the longest sub-warp row
+    (6, 10, 8, 16),  # L = 128
+    (5, 9, 12, 12),  # L = 144: five columns
+    (3, 17, 13, 13),  # L = 169
+    (4, 6, 15, 15),  # L = 225
+    (2, 8, 16, 16),  # L = 256: the longest sub-warp row
     (3, 5, 52, 52),  # L = 2704: 3 whole rows per stage, row count not a multiple of 3
     (2, 7, 32, 64),  # L = 2048: 4 rows per stage
     (40, 32, 56, 56),  # L = 3136, 1280 rows: more 2-row tiles than resident CTAs

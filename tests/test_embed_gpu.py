@@ -157,8 +157,12 @@ def test_openclip_wrapper_api():
     assert e.ndim == 2 and e.shape == (2, 512) and torch.isfinite(e).all()
     with pytest.raises(ValueError):
         OpenClip("not-a-model")
+    t = fm.encode_text(torch.zeros(1, 77, dtype=torch.long))  # image and text features share the embedding dimension
+    assert t.shape == (1, 512) and torch.isfinite(t).all()
+    from semanticlens_b200.foundation_models import SigLipV2
+
     with pytest.raises(NotImplementedError):
-        fm.encode_text(torch.zeros(1, 77, dtype=torch.long))
+        SigLipV2(device="cuda", load_weights=False).encode_text(torch.zeros(1, 64, dtype=torch.long))
 
 
 def test_preprocess_matches_reference_transform_on_pil():
@@ -194,3 +198,62 @@ def test_preprocess_staging_buffers_do_not_race_the_copy_engine():
     std = torch.tensor(fm.cfg.std).view(1, 3, 1, 1)
     for b, o in zip(batches, outs):
         assert torch.equal(o.cpu(), (b.float() / 255.0 - mean) / std)
+
+
+@pytest.mark.parametrize("B,T,H", [(3, 77, 8), (2, 12, 2), (1, 64, 1), (2, 130, 2)])
+def test_causal_attention_from_planes_vs_torch(ops, B, T, H):
+    dh = 64
+    W = H * dh
+    qkv = torch.randn(B, T, 3 * W, generator=torch.Generator().manual_seed(T + H))
+    planes_in = ops.split_planes(qkv.view(B * T, 3 * W).cuda(), 0)
+    held = (planes_in[0].double() + planes_in[1].double() / 2048).view(B, T, 3 * W).cpu()
+    q, k, v = (t.view(B, T, H, dh).transpose(1, 2) for t in held.split(W, -1))
+    mask = torch.full((T, T), float("-inf"), dtype=torch.float64).triu(1)
+    want = (torch.softmax(q @ k.transpose(-1, -2) * dh**-0.5 + mask, -1) @ v).transpose(1, 2).reshape(B, T, W)
+    got = ops.attention_planes(planes_in, B, H, causal=True)
+    assert rel_max(got, want) < 2e-6
+
+
+@pytest.mark.parametrize("name,B", [("text-tiny-test", 5), ("ViT-B-32", 3)])
+def test_text_tower_vs_oracle(name, B):
+    """CLIP text tower (token + positional embedding, causal blocks, ln_final, EOT pooling, text_projection) against the
+    torch oracle pinned to HF CLIPTextModelWithProjection."""
+    from semanticlens_b200.foundation_models import text as T
+
+    ocfg = vp.TEXT_CONFIGS[name]
+    cfg = T.TextConfig(ocfg.name, ocfg.context, ocfg.vocab, ocfg.width, ocfg.layers, ocfg.heads, ocfg.embed_dim, ocfg.act, ocfg.eps)
+    sd = vp.init_text_weights(ocfg, seed=5)
+    tower = T.TextTower(cfg, sd, "cuda")
+    g = torch.Generator().manual_seed(9)
+    tokens = torch.zeros(B, cfg.context, dtype=torch.int64)
+    for b in range(B):
+        n = int(torch.randint(1, cfg.context - 2, (1,), generator=g))
+        tokens[b, 0] = cfg.vocab - 2
+        tokens[b, 1 : 1 + n] = torch.randint(1, cfg.vocab - 2, (n,), generator=g)
+        tokens[b, 1 + n] = cfg.vocab - 1
+    want = vp.encode_text(sd, ocfg, tokens, dtype=torch.float64)
+    got = tower.forward(tokens)
+    assert got.shape == (B, cfg.embed_dim) and got.is_cuda
+    assert rel_max(got, want) < 2e-5
+    with pytest.raises(IndexError):
+        tower.forward(torch.full((1, cfg.context), cfg.vocab, dtype=torch.int64))
+
+
+def test_text_probing_end_to_end_with_token_ids():
+    """Lens.text_probing's arithmetic from token ids: encode_text -> similarity_score against an aggregated concept DB."""
+    from semanticlens_b200.foundation_models import OpenClip
+    from semanticlens_b200.lens import _probe
+
+    fm = OpenClip("ViT-B-32", device="cuda", load_weights=False, seed=1)
+    tokens = torch.zeros(4, 77, dtype=torch.int64)
+    tokens[:, 0] = 49406
+    tokens[:, 1:4] = torch.arange(12).view(4, 3) + 1000
+    tokens[:, 4] = 49407
+    emb = fm.encode_text(tokens)
+    assert emb.shape == (4, 512) and torch.isfinite(emb).all()
+    db = torch.randn(40, 512)
+    sim = _probe(emb.cpu(), db)
+    ref = torch.nn.functional.normalize(emb.cpu(), dim=-1) @ torch.nn.functional.normalize(db, dim=-1).T
+    assert (sim - ref).abs().max() < 1e-5
+    with pytest.raises(FileNotFoundError, match="BPE"):
+        fm.tokenize(["a photo of a dog"])

@@ -117,6 +117,51 @@ def test_oracle_siglip_tower_matches_hf_siglip():
     assert (got.double() - hi).abs().max() <= 1e-5 * hi.abs().max()
 
 
+def test_oracle_text_tower_matches_hf_clip_text():
+    transformers = pytest.importorskip("transformers")
+    cfg = vp.TEXT_CONFIGS["text-tiny-test"]
+    sd = vp.init_text_weights(cfg, seed=5)
+    hc = transformers.CLIPTextConfig(
+        vocab_size=cfg.vocab, hidden_size=cfg.width, intermediate_size=cfg.mlp, num_hidden_layers=cfg.layers,
+        num_attention_heads=cfg.heads, max_position_embeddings=cfg.context, projection_dim=cfg.embed_dim, hidden_act="gelu",
+        layer_norm_eps=cfg.eps, eos_token_id=cfg.vocab - 1, bos_token_id=cfg.vocab - 2, pad_token_id=0,
+    )
+    m = transformers.CLIPTextModelWithProjection(hc).eval()
+    W = cfg.width
+    new = {
+        "text_model.embeddings.token_embedding.weight": sd["token_embedding.weight"],
+        "text_model.embeddings.position_embedding.weight": sd["positional_embedding"],
+        "text_model.final_layer_norm.weight": sd["ln_final.weight"],
+        "text_model.final_layer_norm.bias": sd["ln_final.bias"],
+        "text_projection.weight": sd["text_projection"].T.contiguous(),
+    }
+    for i in range(cfg.layers):
+        p, q = f"transformer.resblocks.{i}.", f"text_model.encoder.layers.{i}."
+        wi, bi = sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"]
+        for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
+            new[q + f"self_attn.{n}.weight"] = wi[j * W : (j + 1) * W]
+            new[q + f"self_attn.{n}.bias"] = bi[j * W : (j + 1) * W]
+        new[q + "self_attn.out_proj.weight"], new[q + "self_attn.out_proj.bias"] = sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"]
+        new[q + "layer_norm1.weight"], new[q + "layer_norm1.bias"] = sd[p + "ln_1.weight"], sd[p + "ln_1.bias"]
+        new[q + "layer_norm2.weight"], new[q + "layer_norm2.bias"] = sd[p + "ln_2.weight"], sd[p + "ln_2.bias"]
+        new[q + "mlp.fc1.weight"], new[q + "mlp.fc1.bias"] = sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"]
+        new[q + "mlp.fc2.weight"], new[q + "mlp.fc2.bias"] = sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"]
+    missing, unexpected = m.load_state_dict(new, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    # sequences: <bos> words... <eot = largest id> then padding zeros, like the CLIP tokenizer emits them
+    g = torch.Generator().manual_seed(2)
+    tokens = torch.zeros(4, cfg.context, dtype=torch.int64)
+    for b, n in enumerate((3, 7, 10, 1)):
+        tokens[b, 0] = cfg.vocab - 2
+        tokens[b, 1 : 1 + n] = torch.randint(1, cfg.vocab - 2, (n,), generator=g)
+        tokens[b, 1 + n] = cfg.vocab - 1
+    with torch.no_grad():
+        want = m(input_ids=tokens).text_embeds
+    got = vp.encode_text(sd, cfg, tokens)
+    assert got.shape == (4, cfg.embed_dim)
+    assert (got - want).abs().max() <= 2e-5 * want.abs().max()
+
+
 def test_preprocess_u8_is_totensor_normalize():
     cfg = vp.CONFIGS["ViT-tiny-test"]
     u8 = torch.randint(0, 256, (2, 3, 32, 32), dtype=torch.uint8)
