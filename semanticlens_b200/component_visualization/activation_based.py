@@ -300,13 +300,22 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
         embeds = self._embed_vision_dataset(fm, batch_size, **kwargs)
 
         concept_db = dict()
+        to_host = torch.device(self.output_device).type == "cpu"
         for layer_name in self.layer_names:
             ids = self.get_max_reference(layer_name)
             if embeds.is_cuda:
                 db = ops.gather_rows(embeds, ids)  # K5; python-negative semantics: id -1 -> last image
-                concept_db[layer_name] = db.to(self.output_device)
+                if to_host:
+                    # asynchronous D2H into pinned memory (the next layer's gather runs meanwhile); one sync below
+                    host = torch.empty(db.shape, dtype=db.dtype, pin_memory=True)
+                    host.copy_(db, non_blocking=True)
+                    concept_db[layer_name] = host
+                else:
+                    concept_db[layer_name] = db.to(self.output_device)
             else:
                 concept_db[layer_name] = embeds[ids]
+        if embeds.is_cuda and to_host:
+            torch.cuda.current_stream(embeds.device).synchronize()
         return concept_db
 
     def _embed_vision_dataset(self, fm, batch_size, **kwargs):
