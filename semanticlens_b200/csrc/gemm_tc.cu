@@ -240,7 +240,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
     } else {
         const int quarter = warp & 3;  // TMEM lane group this warp may read
-        const int chunk0 = (warp - 2) >> 2;  // warps 2..5 take the even column chunks, warps 6..9 the odd ones
+        const int chunk0 = (warp - 2) >> 2;  // epilogue warps 2-5 take the even 32-column chunks, warps 6-9 the odd ones
         int acc = 0;
         uint32_t acc_phase = 0;
         const int fmt = p.fmt;

@@ -285,14 +285,11 @@ class VitTower:
         need = lib.slb_vit_workspace_bytes(ctypes.byref(self._struct), B)
         if self._ws is None or self._ws.numel() < need or self._ws.device != img.device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=img.device)
-        tm = ops._timer.begin() if ops._timer else None
         with torch.cuda.device(img.device):
             rc = lib.slb_vit_forward(
                 ctypes.byref(self._struct), img.data_ptr(), B, out.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
                 N.stream_ptr(img.device),
             )
-        if ops._timer:
-            ops._timer.end("K4 vit_forward", tm, 0, int(3 * flops_per_image(cfg) * B))
         N.check(rc, "slb_vit_forward")
         return out
 

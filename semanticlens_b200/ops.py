@@ -15,46 +15,6 @@ def _dev_guard(t: torch.Tensor):
     return torch.cuda.device(t.device)
 
 
-class KernelTimer:
-    """Optional per-kernel CUDA-event timing on the launching stream (used by bench.py for the roofline line).
-
-    While installed with :func:`set_timer`, every wrapper brackets its kernel with two events on the current
-    stream and records (label, algorithmic bytes, algorithmic flops). Nothing synchronises until :meth:`totals`.
-    """
-
-    def __init__(self):
-        self.records: list[tuple[str, torch.cuda.Event, torch.cuda.Event, int, int]] = []
-
-    def begin(self):
-        ev = torch.cuda.Event(enable_timing=True)
-        ev.record()
-        return ev
-
-    def end(self, label: str, start, nbytes: int = 0, flops: int = 0):
-        ev = torch.cuda.Event(enable_timing=True)
-        ev.record()
-        self.records.append((label, start, ev, nbytes, flops))
-
-    def totals(self) -> dict[str, dict[str, float]]:
-        torch.cuda.synchronize()
-        out: dict[str, dict[str, float]] = {}
-        for label, a, b, nbytes, flops in self.records:
-            d = out.setdefault(label, {"ms": 0.0, "launches": 0, "bytes": 0, "flops": 0})
-            d["ms"] += a.elapsed_time(b)
-            d["launches"] += 1
-            d["bytes"] += nbytes
-            d["flops"] += flops
-        return out
-
-
-_timer: KernelTimer | None = None
-
-
-def set_timer(t: KernelTimer | None) -> None:
-    global _timer
-    _timer = t
-
-
 # ------------------------------------------------------------------------------------------------
 # collect
 # ------------------------------------------------------------------------------------------------
@@ -91,13 +51,10 @@ def agg_reduce(t: torch.Tensor, op: int, reduce_kind: str, token_pos: int = 0) -
     if B == 0 or C == 0:
         return out
     with _dev_guard(t):
-        t0 = _timer.begin() if _timer else None
         rc = lib.slb_agg_reduce(
             keep.data_ptr(), N.dtype_code(keep.dtype), layout, B, C, inner, op, token_pos, out.data_ptr(),
             N.stream_ptr(t.device),
         )
-        if _timer:
-            _timer.end("K1 agg_reduce", t0, keep.numel() * keep.element_size())
     N.check(rc, "slb_agg_reduce")
     return out
 
@@ -158,12 +115,9 @@ def agg_topk_update(
     need = B * C
     if scratch is None or scratch.numel() < need or scratch.device != t.device:
         scratch = torch.empty(max(need, 1), dtype=torch.float32, device=t.device)
-    if B + k > 8192 or _timer is not None:
+    if B + k > 8192:
         cand = agg_reduce(t, op, reduce_kind, token_pos)
-        t0 = _timer.begin() if _timer else None
         topk_update(cand, state_vals, state_ids, None, id_base)
-        if _timer:
-            _timer.end("K2 topk_update", t0, cand.numel() * 4)
         return scratch
     with _dev_guard(t):
         rc = lib.slb_agg_topk_update(
@@ -272,15 +226,11 @@ def gemm_split(
             assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape, (t.shape, shape)
     if out_planes is not None:
         assert tuple(out_planes.shape) == (2, M, Nn) and out_planes.is_contiguous() and out_planes.dtype == a_planes.dtype
-    tm = _timer.begin() if _timer else None
     with _dev_guard(a_planes):
         rc = lib.slb_gemm_split(
             a_planes.data_ptr(), w_planes.data_ptr(), fmt, M, Nn, K, N.ptr(bias), N.ptr(residual), N.ptr(row_scale),
             N.ptr(col_scale), epilogue, passes, N.ptr(out_f32), N.ptr(out_planes), N.stream_ptr(dev),
         )
-    if _timer:
-        _timer.end("K4 gemm_split", tm, 2 * 2 * (M * K + Nn * K) + (M * Nn * 4 if out_f32 is not None else 0),
-                   2 * M * Nn * K * passes)
     N.check(rc, "slb_gemm_split")
     return out_f32, out_planes
 
@@ -393,12 +343,9 @@ def cosine_gemm(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         return out[:, :Nn]
     need = lib.slb_cosine_gemm_workspace_bytes(M, n_pad, D)
     ws = torch.empty(need, dtype=torch.uint8, device=x.device)
-    tm = _timer.begin() if _timer else None
     with _dev_guard(x):
         rc = lib.slb_cosine_gemm(x.data_ptr(), M, y.data_ptr(), n_pad, D, out.data_ptr(), ws.data_ptr(), need,
                                  N.stream_ptr(x.device))
-    if _timer:
-        _timer.end("K6 cosine_gemm", tm, 4 * (M * D + n_pad * D + M * n_pad), 2 * M * n_pad * _pad64(D) * 3)
     N.check(rc, "slb_cosine_gemm")
     return out if n_pad == Nn else out[:, :Nn].contiguous()
 
@@ -431,11 +378,8 @@ def clarity(V: torch.Tensor) -> torch.Tensor:
     C = V.numel() // (k * D) if k * D else 0
     out = torch.empty(V.shape[:-2], dtype=torch.float32, device=V.device)
     if C:
-        tm = _timer.begin() if _timer else None
         with _dev_guard(V):
             rc = lib.slb_clarity(V.data_ptr(), C, k, D, out.data_ptr(), N.stream_ptr(V.device))
-        if _timer:
-            _timer.end("K7 clarity", tm, V.numel() * 4)
         N.check(rc, "slb_clarity")
     return out
 
@@ -475,13 +419,10 @@ def polysem_2means(V: torch.Tensor, random_state: int = 123, replace_empty_clust
     if need == 0:
         raise N.SlbError(f"polysemanticity kernel supports at most 256 examples per neuron (got {k})")
     ws = torch.empty(need, dtype=torch.uint8, device=V.device)
-    tm = _timer.begin() if _timer else None
     with _dev_guard(V):
         rc = lib.slb_polysem_2means(V.data_ptr(), C, k, D, first.ctypes.data, rand.ctypes.data, n_init,
                                     1 if replace_empty_clusters else 0, out.data_ptr(), ws.data_ptr(), need,
                                     N.stream_ptr(V.device))
-    if _timer:
-        _timer.end("K8 polysem_2means", tm, V.numel() * 4)
     N.check(rc, "slb_polysem_2means")
     return out
 
