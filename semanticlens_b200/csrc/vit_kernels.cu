@@ -135,6 +135,64 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
+// Register-resident variant for cols <= 128 * NCH: the row is read from global memory ONCE (the generic kernel above
+// re-reads it for the variance and the normalisation). Same accumulation order as the generic kernel, so the results
+// are bit-identical.
+template <int NCH>
+__global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* __restrict__ x, int64_t rows, int cols,
+                                                            int64_t row_stride, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, int fmt,
+                                                            float* __restrict__ out_f32, uint16_t* __restrict__ out_hi,
+                                                            uint16_t* __restrict__ out_lo) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + r * row_stride);
+    const int c4 = cols >> 2;
+    float4 v[NCH];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int i = c * 32 + lane;
+        if (i < c4) {
+            v[c] = xr[i];
+            s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+        }
+    }
+    const float mean = slb_warp_sum_butterfly(s) / (float)cols;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int i = c * 32 + lane;
+        if (i < c4) {
+            const float a = v[c].x - mean, b = v[c].y - mean, cc = v[c].z - mean, d = v[c].w - mean;
+            q += (a * a + b * b) + (cc * cc + d * d);
+        }
+    }
+    const float var = slb_warp_sum_butterfly(q) / (float)cols;
+    const float rstd = 1.0f / sqrtf(var + eps);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int i = c * 32 + lane;
+        if (i < c4) {
+            const float4 g = reinterpret_cast<const float4*>(gamma)[i];
+            const float4 bt = beta ? reinterpret_cast<const float4*>(beta)[i] : make_float4(0, 0, 0, 0);
+            float y[4] = {(v[c].x - mean) * rstd * g.x + bt.x, (v[c].y - mean) * rstd * g.y + bt.y,
+                          (v[c].z - mean) * rstd * g.z + bt.z, (v[c].w - mean) * rstd * g.w + bt.w};
+            if (out_f32) reinterpret_cast<float4*>(out_f32 + r * cols)[i] = make_float4(y[0], y[1], y[2], y[3]);
+            if (out_hi) {
+                uint16_t h[4], l[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) slb_split2(y[k], fmt, h[k], l[k]);
+                reinterpret_cast<uint2*>(out_hi + r * cols)[i] =
+                    make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+                reinterpret_cast<uint2*>(out_lo + r * cols)[i] =
+                    make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // attention for short sequences: one CTA per (batch, head); K and V of the head live in shared memory (fp32),
 // one warp per query row: scores across lanes, softmax by warp shuffles, PV with lanes across head_dim.
@@ -309,9 +367,19 @@ extern "C" int slb_layernorm(const float* x, int64_t rows, int64_t cols, int64_t
                 "slb_layernorm: cols and row_stride must be multiples of 4");
     const int threads = 256;
     SlbProfScope prof("K4 layernorm", stream, 0.0, (double)rows * (double)cols * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_planes ? 4.0 : 0.0)));
-    layernorm_kernel<<<(unsigned)slb_ceil_div(rows * 32, threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, rows, (int)cols, row_stride, gamma, beta, eps, plane_fmt, out_f32, out_planes,
-        out_planes ? out_planes + rows * cols : nullptr);
+    const unsigned grid = (unsigned)slb_ceil_div(rows * 32, threads);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint16_t* lo = out_planes ? out_planes + rows * cols : nullptr;
+    // in-place use (ln_pre: out_f32 == x) is safe in both kernels: a warp owns its row
+    if (cols <= 768)
+        layernorm_reg_kernel<6><<<grid, threads, 0, st>>>(x, rows, (int)cols, row_stride, gamma, beta, eps, plane_fmt, out_f32,
+                                                         out_planes, lo);
+    else if (cols <= 1024)
+        layernorm_reg_kernel<8><<<grid, threads, 0, st>>>(x, rows, (int)cols, row_stride, gamma, beta, eps, plane_fmt, out_f32,
+                                                         out_planes, lo);
+    else
+        layernorm_kernel<<<grid, threads, 0, st>>>(x, rows, (int)cols, row_stride, gamma, beta, eps, plane_fmt, out_f32,
+                                                   out_planes, lo);
     SLB_LAUNCH_OK("layernorm");
     return SLB_OK;
 }

@@ -29,7 +29,7 @@ def test_k3_u8_norm_bitexact_vs_totensor_normalize(ops):
     assert torch.equal(got, vp.preprocess_u8(cfg, u8))
 
 
-@pytest.mark.parametrize("rows,cols", [(7, 64), (300, 768), (33, 1024)])
+@pytest.mark.parametrize("rows,cols", [(7, 64), (300, 768), (33, 1024), (5, 1280), (4, 2048), (9, 512)])
 def test_layernorm_vs_torch(ops, rows, cols):
     x = torch.randn(rows, cols) * 3 + 0.5
     g, b = torch.randn(cols), torch.randn(cols)
