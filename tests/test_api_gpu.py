@@ -1,0 +1,173 @@
+"""Public-API behaviour of the drop-in classes, mirroring what the reference's own tests pin for this path
+(reference tests/component_visualization/test_activation_based.py:26-161 and tests/test_lens.py:35-97: constructor,
+bad layer, MissingNameWarning, cache hit / miss control flow, empty layer list, num_samples = 0, Lens cache file), plus the
+end-to-end concept DB (`Lens.compute_concept_db`) against the torch-CPU port of the reference path on the same weights."""
+
+from unittest import mock
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+from torch.utils.data import TensorDataset
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def model():
+    torch.manual_seed(0)
+    m = nn.Sequential(nn.Conv2d(3, 8, 3), nn.ReLU(), nn.Conv2d(8, 16, 3)).cuda()
+    m.name = "mock_model"
+    return m
+
+
+@pytest.fixture
+def dataset():
+    ds = TensorDataset(torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(1)), torch.zeros(4))
+    ds.name = "mock_dataset"
+    return ds
+
+
+def make_cv(model, dataset, layers, k, **kw):
+    from semanticlens_b200.component_visualization import ActivationComponentVisualizer
+
+    return ActivationComponentVisualizer(model=model, dataset_model=dataset, dataset_fm=dataset, layer_names=layers,
+                                         num_samples=k, **kw)
+
+
+def test_initialization_and_errors(model, dataset, tmp_path):
+    from semanticlens_b200.component_visualization import MissingNameWarning
+
+    cv = make_cv(model, dataset, ["0"], 10, cache_dir=None)
+    assert cv.model is model and cv.layer_names == ["0"] and not cv.caching
+    with pytest.raises(ValueError, match="Layer 'bad_layer' not found in model"):
+        make_cv(model, dataset, ["bad_layer"], 10)
+    del model.name
+    with pytest.warns(MissingNameWarning, match="Model does not have a name attribute"):
+        make_cv(model, dataset, ["0"], 10, cache_dir=str(tmp_path))
+    short = TensorDataset(torch.randn(3, 3, 32, 32), torch.zeros(3))
+    short.name = "short"
+    from semanticlens_b200.component_visualization import ActivationComponentVisualizer
+
+    with pytest.raises(ValueError, match="same length"):
+        ActivationComponentVisualizer(model, dataset, short, ["0"], 4)
+
+
+def test_run_loads_from_cache_if_available(model, dataset, tmp_path):
+    target = "semanticlens_b200.component_visualization.activation_caching.ActMaxCache.load"
+    with mock.patch(target, return_value={}) as load, mock.patch(
+            "semanticlens_b200.component_visualization.activation_based.ActivationComponentVisualizer._run") as run:
+        cv = make_cv(model, dataset, ["0"], 10, cache_dir=str(tmp_path))
+        cv.run()
+        assert load.call_count == 2  # once in the constructor, once in run()
+        run.assert_not_called()
+
+
+def test_run_computes_and_stores_on_cache_miss(model, dataset, tmp_path):
+    base = "semanticlens_b200.component_visualization.activation_caching.ActMaxCache."
+    with mock.patch(base + "load", side_effect=FileNotFoundError), mock.patch(base + "store") as store:
+        cv = make_cv(model, dataset, ["0"], 10, cache_dir=str(tmp_path))
+        cv.show_progress = False
+        cv.run(batch_size=2)
+        store.assert_called_once()
+
+
+def test_empty_layer_names_and_zero_samples(model, dataset, tmp_path):
+    cv = make_cv(model, dataset, [], 10)
+    cv.show_progress = False
+    assert cv.layer_names == [] and cv.run() == {}
+    cv = make_cv(model, dataset, ["0"], 0, cache_dir=str(tmp_path))
+    cv.show_progress = False
+    cv.run(batch_size=2)
+    am = cv.actmax_cache.cache["0"]
+    assert am.n_collect == 0 and am.sample_ids.shape == (8, 0) and am.activations.shape == (8, 0)
+
+
+def test_real_cache_roundtrip_skips_the_second_sweep(model, dataset, tmp_path):
+    cv = make_cv(model, dataset, ["0", "2"], 3, cache_dir=str(tmp_path))
+    cv.show_progress = False
+    first = cv.run(batch_size=2)
+    ids = {k: v.sample_ids.clone() for k, v in first.items()}
+    files = sorted(p.name for p in cv.storage_dir.glob("*.safetensors"))
+    assert files == ["aggregate_conv_mean-3-0.safetensors", "aggregate_conv_mean-3-2.safetensors"]  # reference grammar
+    with mock.patch("semanticlens_b200.component_visualization.activation_based.ActivationComponentVisualizer._run") as run:
+        cv2 = make_cv(model, dataset, ["0", "2"], 3, cache_dir=str(tmp_path))
+        again = cv2.run(batch_size=2)
+        run.assert_not_called()
+    for k in ids:
+        assert torch.equal(again[k].sample_ids, ids[k])
+
+
+class _Images(torch.utils.data.Dataset):
+    def __init__(self, n, kind, size):
+        self.u8 = torch.randint(0, 255, (n, 3, size, size), generator=torch.Generator().manual_seed(5), dtype=torch.uint8)
+        self.kind, self.name = kind, f"img-{kind}-{n}"
+
+    def __len__(self):
+        return self.u8.shape[0]
+
+    def __getitem__(self, i):
+        return ((self.u8[i].float() / 255 - 0.45) / 0.23, 0) if self.kind == "model" else self.u8[i]
+
+
+def test_concept_db_end_to_end_vs_reference_port(tmp_path):
+    """Lens.compute_concept_db on the GPU vs the torch-CPU port of the reference path (oracle/ref_port.py + the oracle
+    tower) with the same model weights, the same images and the same FM weights. The probed model's activations differ
+    between cuDNN and oneDNN at the 1e-6 level, so ids are compared with the tie-aware contract through the value
+    multiset (bit-exact here unless a bf16 rounding flips: none with this seed) and the DB rows wherever ids agree."""
+    from oracle import ref_port as rp
+    from oracle import vit_port as vp
+    from semanticlens_b200.component_visualization import ActivationComponentVisualizer, aggregators
+    from semanticlens_b200.foundation_models import OpenClip, vit
+    from semanticlens_b200.lens import Lens
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Conv2d(3, 8, 5, stride=2), nn.ReLU(), nn.Conv2d(8, 16, 3), nn.ReLU()).eval()
+    net.name = "net"
+    layers, k, n, S = ["1", "3"], 4, 21, 32
+    ds_m, ds_f = _Images(n, "model", S), _Images(n, "fm", S)
+    ocfg = vp.CONFIGS["ViT-tiny-test"]
+    sd = vp.init_weights(ocfg, seed=3)
+    # reference path on the CPU
+    ref_states = rp.sweep(net, torch.utils.data.DataLoader(ds_m, batch_size=5), layers, rp.aggregate_conv_mean, k)
+    ref_embeds = torch.cat([vp.encode_image(sd, ocfg, vp.preprocess_u8(ocfg, ds_f.u8[i : i + 5])) for i in range(0, n, 5)])
+    ref_db = rp.concept_db(ref_states, ref_embeds)
+    # B200 path through the public API
+    cfg = vit.VitConfig(**{f: getattr(ocfg, f) for f in ("name", "image_size", "patch", "width", "layers", "heads", "mlp",
+                                                          "embed_dim", "act", "eps", "mean", "std")})
+    vit.CONFIGS[cfg.name] = cfg
+    try:
+        fm = OpenClip(cfg.name, device="cuda", state_dict=sd)
+    finally:
+        vit.CONFIGS.pop(cfg.name, None)
+    fm.name = "tiny-fm"
+    cv = ActivationComponentVisualizer(net.cuda(), ds_m, ds_f, layers, k, aggregate_fn=aggregators.aggregate_conv_mean,
+                                       cache_dir=str(tmp_path))
+    cv.show_progress = False
+    lens = Lens(fm, device="cuda")
+    db = lens.compute_concept_db(cv, batch_size=6)
+    assert set(db) == set(layers)
+    cache_file = cv.storage_dir / "concept_database" / "tiny-fm" / "concept_db-aggregate_conv_mean-4-['1', '3'].safetensors"
+    assert cache_file.exists()  # file grammar of reference lens.py:308-316
+    for name in layers:
+        am = cv.actmax_cache.cache[name]
+        rv, ri = ref_states[name].activations, ref_states[name].sample_ids
+        assert db[name].shape == (rv.shape[0], k, ocfg.embed_dim) and db[name].device.type == "cpu"
+        same_vals = (am.activations.view(torch.int16) == rv.view(torch.int16)) | ((am.activations == 0) & (rv == 0))
+        assert same_vals.float().mean() > 0.98  # cuDNN vs oneDNN activations: at most a stray bf16 rounding flip
+        agree = am.sample_ids == ri
+        assert agree.float().mean() > 0.9
+        err = (db[name][agree] - ref_db[name][agree]).abs().max() / ref_db[name].abs().max()
+        assert err < 1e-4
+        # id -1 placeholders (dead channels) alias the LAST image, like `embeds[-1]` upstream
+        dead = am.sample_ids == -1
+        if dead.any():
+            assert torch.allclose(db[name][dead], db[name][dead][0])
+    # second call: served from the concept-DB cache file
+    with mock.patch.object(ActivationComponentVisualizer, "_compute_concept_db") as comp:
+        again = lens.compute_concept_db(cv, batch_size=6)
+        comp.assert_not_called()
+    for name in layers:
+        assert torch.equal(again[name], db[name])
