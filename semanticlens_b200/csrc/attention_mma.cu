@@ -14,6 +14,8 @@
 //   V^T [dim][Tkp+8] fp16 (row = dim, keys contiguous)       -> b = V^T[d0 + lane/4][key0 + 2*(lane%4) .. +1]
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int kDh = 64;
@@ -40,6 +42,15 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
     x0 = fminf(fmaxf(x0, -65504.0f), 65504.0f);
     x1 = fminf(fmaxf(x1, -65504.0f), 65504.0f);
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// the same for values known to lie in [0, 1] (softmax numerators): no saturation needed
+__device__ __forceinline__ void split_pair_unit(float x0, float x1, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(x0, x1);
     const float2 hf = __half22float2(h);
     const __half2 l = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
@@ -253,6 +264,7 @@ struct AttnPlanesParams {
     const __half* hi;  // [rows][3W]
     const __half* lo;
     int T, Tkp, H, W;
+    int q_row0;  // first query row handled by this launch (rows below it belong to the tcgen05 tiles)
     int causal;  // 1: key j is visible to query i only if j <= i (CLIP text tower)
     float scale;
     float* out_f32; uint16_t* out_hi; uint16_t* out_lo; int fmt;
@@ -276,32 +288,37 @@ template <int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPlanesParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Tkp = p.Tkp;
-    __half* Kh = reinterpret_cast<__half*>(smem_raw);  // four [Tkp][72] tiles
-    __half* Kl = Kh + (size_t)Tkp * kKPad;
-    __half* Vh = Kl + (size_t)Tkp * kKPad;
-    __half* Vl = Vh + (size_t)Tkp * kKPad;
+    // one stage = a 64-key block of Kh, Kl, Vh, Vl ([64][72] halves each); two stages when the sequence has several blocks:
+    // block j + 1 streams in (cp.async) while block j is being multiplied
+    constexpr int kTileHalves = kKeyBlock * kKPad;
+    constexpr int kStageHalves = 4 * kTileHalves;
+    __half* smem = reinterpret_cast<__half*>(smem_raw);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t b = blockIdx.x / p.H;
     const int h = (int)(blockIdx.x % p.H);
     const int64_t ld = 3 * (int64_t)p.W;
     const int64_t row0 = b * p.T;
+    const int nblk = (Tkp + kKeyBlock - 1) / kKeyBlock;
 
-    // ---- stage K and V (hi and lo) with 16-byte async copies; keys >= T are zero ----
-    for (int i = tid; i < Tkp * 32; i += NW * 32) {
-        const int key = i >> 5, which = (i >> 3) & 3, chunk = i & 7;  // which: 0 Kh, 1 Kl, 2 Vh, 3 Vl
-        __half* dst = Kh + (size_t)which * Tkp * kKPad + (size_t)key * kKPad + chunk * 8;
-        if (key < p.T) {
-            const __half* plane = (which & 1) ? p.lo : p.hi;
-            const __half* src = plane + (row0 + key) * ld + ((which >> 1) ? 2 : 1) * p.W + h * kDh + chunk * 8;
-            cp_async16(dst, src);
-        } else {
-            *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    auto stage = [&](int blk) {  // 16-byte async copies; keys >= T are zero
+        __half* base = smem + (size_t)(blk & 1) * kStageHalves;
+        for (int i = tid; i < kKeyBlock * 32; i += NW * 32) {
+            const int kl = i >> 5, which = (i >> 3) & 3, chunk = i & 7;  // which: 0 Kh, 1 Kl, 2 Vh, 3 Vl
+            const int key = blk * kKeyBlock + kl;
+            __half* dst = base + (size_t)which * kTileHalves + (size_t)kl * kKPad + chunk * 8;
+            if (key < p.T) {
+                const __half* plane = (which & 1) ? p.lo : p.hi;
+                cp_async16(dst, plane + (row0 + key) * ld + ((which >> 1) ? 2 : 1) * p.W + h * kDh + chunk * 8);
+            } else if (key < Tkp) {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0);
 
-    const int r0 = blockIdx.y * (16 * NW) + warp * 16;
+    const int r0 = p.q_row0 + blockIdx.y * (16 * NW) + warp * 16;
     const int g = lane >> 2, t4 = lane & 3;
     // ---- Q fragments straight from the planes (overlaps the copies above) ----
     uint32_t qh[4][4], ql[4][4];
@@ -321,9 +338,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
             ql[ks][i] = vl;
         }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    if (r0 >= p.T) return;
+    const bool active = r0 < p.T;  // warps past the last query row still help to stage K / V
 
     float om[8][4], oc[8][4];
 #pragma unroll
@@ -333,19 +348,34 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
     float m_run[2] = {-INFINITY, -INFINITY};
     float l_run[2] = {0.f, 0.f};
     constexpr float kInvS = 1.0f / 2048.0f;
-    const float sc_main = p.scale, sc_corr = p.scale * kInvS;
+    // logits are kept in the log2 domain (scale * log2 e folded in) so that the exponentials are single ex2 instructions
+    const float sc_main = p.scale * 1.4426950408889634f, sc_corr = sc_main * kInvS;
     // ldmatrix row addresses: lane -> (matrix j = lane / 8, row r = lane % 8)
     const int lm_j = lane >> 3, lm_r = lane & 7;
 
-    for (int kb0 = 0; kb0 < Tkp; kb0 += kKeyBlock) {
+    for (int blk = 0; blk < nblk; ++blk) {
+        const int kb0 = blk * kKeyBlock;
+        if (blk + 1 < nblk) {
+            stage(blk + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();  // block `blk` has landed for every thread's copies
+        const __half* Kh = smem + (size_t)(blk & 1) * kStageHalves;
+        const __half* Kl = Kh + kTileHalves;
+        const __half* Vh = Kl + kTileHalves;
+        const __half* Vl = Vh + kTileHalves;
+        if (active) {
         const int nkt = min(kKeyBlock, Tkp - kb0) >> 3;
+        const bool need_mask = (kb0 + kKeyBlock > p.T) || (p.causal && kb0 + kKeyBlock > r0);
         float s[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             float sm_[4] = {0.f, 0.f, 0.f, 0.f}, sc_[4] = {0.f, 0.f, 0.f, 0.f};
             if (nt < nkt) {
                 // matrices: (keys nt*8.., d = ks2*32 + j*8 ..): j = 0,1 -> k-step 2*ks2 (b0, b1); j = 2,3 -> k-step 2*ks2 + 1
-                const size_t roff = (size_t)(kb0 + nt * 8 + lm_r) * kKPad + lm_j * 8;
+                const size_t roff = (size_t)(nt * 8 + lm_r) * kKPad + lm_j * 8;
 #pragma unroll
                 for (int ks2 = 0; ks2 < 2; ++ks2) {
                     uint32_t bh[4], bl[4];
@@ -359,12 +389,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
                     mma16816(sc_, ql[2 * ks2 + 1], bh[2], bh[3]);
                 }
             }
-            const int col = kb0 + nt * 8 + t4 * 2;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = col + (j & 1);
-                const bool ok = nt < nkt && c < p.T && (!p.causal || c <= r0 + g + (j >> 1) * 8);
-                s[nt][j] = ok ? fmaf(sc_[j], sc_corr, sm_[j] * sc_main) : -INFINITY;
+            for (int j = 0; j < 4; ++j) s[nt][j] = fmaf(sc_[j], sc_corr, sm_[j] * sc_main);
+            if (need_mask) {  // block-uniform: only the last key block (padding) and causal blocks on / above the diagonal
+                const int col = kb0 + nt * 8 + t4 * 2;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = col + (j & 1);
+                    const bool ok = nt < nkt && c < p.T && (!p.causal || c <= r0 + g + (j >> 1) * 8);
+                    if (!ok) s[nt][j] = -INFINITY;
+                }
             }
         }
         float mx[2] = {-INFINITY, -INFINITY};
@@ -382,7 +416,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const float m_new = fmaxf(m_run[r], mx[r]);
-            alpha[r] = (m_run[r] == -INFINITY) ? 0.f : expf(m_run[r] - m_new);
+            alpha[r] = (m_run[r] == -INFINITY) ? 0.f : exp2f(m_run[r] - m_new);
             m_run[r] = m_new;
         }
         float rs[2] = {0.f, 0.f};
@@ -390,7 +424,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float e = expf(s[nt][j] - m_run[j >> 1]);
+                const float e = exp2f(s[nt][j] - m_run[j >> 1]);
                 s[nt][j] = e;
                 rs[j >> 1] += e;
             }
@@ -408,12 +442,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
         for (int kt = 0; kt < 4; ++kt) {
             if (2 * kt < nkt) {
                 uint32_t ph[4], pl[4];
-                split_pair(s[2 * kt][0], s[2 * kt][1], ph[0], pl[0]);
-                split_pair(s[2 * kt][2], s[2 * kt][3], ph[1], pl[1]);
-                split_pair(s[2 * kt + 1][0], s[2 * kt + 1][1], ph[2], pl[2]);
-                split_pair(s[2 * kt + 1][2], s[2 * kt + 1][3], ph[3], pl[3]);
+                split_pair_unit(s[2 * kt][0], s[2 * kt][1], ph[0], pl[0]);
+                split_pair_unit(s[2 * kt][2], s[2 * kt][3], ph[1], pl[1]);
+                split_pair_unit(s[2 * kt + 1][0], s[2 * kt + 1][1], ph[2], pl[2]);
+                split_pair_unit(s[2 * kt + 1][2], s[2 * kt + 1][3], ph[3], pl[3]);
                 // matrices: j & 1 -> keys +8 (b1), j >> 1 -> next 8 dims (n-tile dt + 1)
-                const size_t roff = (size_t)(kb0 + kt * 16 + (lm_j & 1) * 8 + lm_r) * kKPad + (lm_j >> 1) * 8;
+                const size_t roff = (size_t)(kt * 16 + (lm_j & 1) * 8 + lm_r) * kKPad + (lm_j >> 1) * 8;
 #pragma unroll
                 for (int dt2 = 0; dt2 < 4; ++dt2) {
                     uint32_t bh[4], bl[4];
@@ -428,7 +462,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
                 }
             }
         }
+        }  // active
+        if (blk + 2 < nblk) __syncthreads();  // everyone is done with this stage before block blk + 2 overwrites it
     }
+    if (!active) return;
 
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -459,11 +496,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
 
 template <int NW, int MINB>
 int launch_attn_planes(const AttnPlanesParams& p, int64_t B, cudaStream_t st) {
-    const size_t smem = (size_t)4 * p.Tkp * kKPad * sizeof(__half);
-    SLB_REQUIRE(smem <= 227 * 1024, SLB_EUNSUPPORTED, "slb_attention_planes: K/V of one head do not fit shared memory");
+    const size_t smem = (size_t)(p.Tkp > kKeyBlock ? 2 : 1) * 4 * kKeyBlock * kKPad * sizeof(__half);
     if (smem > 48 * 1024)
         SLB_CUDA_OK(cudaFuncSetAttribute(attention_planes_kernel<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)(B * p.H), (unsigned)slb_ceil_div(p.T, 16 * NW));
+    dim3 grid((unsigned)(B * p.H), (unsigned)slb_ceil_div(p.T - p.q_row0, 16 * NW));
     attention_planes_kernel<NW, MINB><<<grid, NW * 32, smem, st>>>(p);
     SLB_LAUNCH_OK("attention_planes");
     return SLB_OK;
@@ -499,6 +535,9 @@ int slb_attention_mma_dh64(const float* q, int64_t q_bs, int64_t q_rs, const flo
     return launch_attn<8>(p, B, st);
 }
 
+int slb_attention_tc_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles,
+                           int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st);
+
 extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, int64_t dh, float scale,
                                     int causal, int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream) {
     SLB_REQUIRE(B >= 0 && T > 0 && H > 0, SLB_EINVAL, "slb_attention_planes: bad size");
@@ -507,7 +546,7 @@ extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64
     SLB_REQUIRE(dh == kDh, SLB_EUNSUPPORTED, "slb_attention_planes: head_dim must be 64 (got %lld)", (long long)dh);
     SLB_REQUIRE(plane_fmt == SLB_PLANE_F16, SLB_EUNSUPPORTED, "slb_attention_planes: fp16 planes only");
     SLB_REQUIRE(((uintptr_t)qkv_planes % 16) == 0, SLB_EINVAL, "slb_attention_planes: planes must be 16-byte aligned");
-    SLB_REQUIRE(B * H <= 0x7FFFFFFF && T <= 4096, SLB_EUNSUPPORTED, "slb_attention_planes: problem too large");
+    SLB_REQUIRE(B * H <= 0x7FFFFFFF && T <= 64 * 65535, SLB_EUNSUPPORTED, "slb_attention_planes: problem too large");
     const int64_t W = H * dh, rows = B * T;
     SlbProfScope prof("K4 attention", stream, 4.0 * (double)B * (double)H * (double)T * (double)T * (double)dh * 3.0,
                       4.0 * (double)rows * (double)W * 4.0);
@@ -519,6 +558,322 @@ extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64
     p.causal = causal ? 1 : 0;
     p.out_f32 = out_f32; p.out_hi = out_planes; p.out_lo = out_planes ? out_planes + rows * W : nullptr; p.fmt = plane_fmt;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (T <= 64) return launch_attn_planes<4, 3>(p, B, st);
-    return launch_attn_planes<8, 1>(p, B, st);
+    // Long sequences: full 128-query tiles run on tcgen05 (attention_tc_kernel); a tail of fewer than 64 rows (the class
+    // token of a 257-token tower) and short / causal sequences stay on the mma.sync kernel.
+    static const bool no_tc = [] { const char* e = getenv("SLB_ATTN_TC"); return e && e[0] == '0'; }();
+    if (!causal && !no_tc && T >= 128) {
+        int n_tiles = (int)(T / 128);
+        const int64_t rem = T - 128 * (int64_t)n_tiles;
+        if (rem >= 64) n_tiles += 1;
+        int rc = slb_attention_tc_tiles(qkv_planes, B, T, H, scale, n_tiles, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
+        if (rc != SLB_OK) return rc;
+        if ((int64_t)n_tiles * 128 >= T) return SLB_OK;
+        p.q_row0 = n_tiles * 128;
+    }
+    return launch_attn_planes<4, 3>(p, B, st);  // 64 query rows per CTA, 3 CTAs / SM (168 registers, <= 72 KB smem)
+}
+
+// =================================================================================================
+// tcgen05 attention for full 128-row query tiles (T >= 128: ViT-B/16, ViT-L/14, SigLIP towers).
+//
+// One CTA = one (image, head, 128-query tile); 192 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax
+// (thread = query row = TMEM lane). Operands come from the in_proj GEMM's split planes through ONE 3-D tensor map
+// (box 64 cols x 128 rows x 2 planes, 128B swizzle): Q, K blocks and V blocks of 128 tokens. Two sweeps over the keys
+// avoid rescaling the output accumulator: sweep 1 computes S = Q K^T block by block for the row maxima only, sweep 2
+// recomputes S, writes P = exp2(S - max) as split planes into shared memory (K-major, swizzled by hand) and accumulates
+// O += P V with V consumed straight from its row-major tile as an MN-major operand (no transpose anywhere).
+// Accumulators (TMEM): S main | S corr (2 x 128 columns), O main | O corr (2 x 64 columns); every product is the
+// usual three plane products. Rows of the tile beyond T and keys beyond T are masked / never stored.
+// =================================================================================================
+namespace {
+
+constexpr int kTcSoftmaxWarps = 8;                // two warps per TMEM lane quarter: each takes 64 of a block's 128 keys
+constexpr int kTcThreads = (2 + kTcSoftmaxWarps) * 32;
+constexpr int kTcTile = 128;                      // queries per CTA and keys per block
+constexpr int kTcPlane = kTcTile * 64 * 2;        // one 128 x 64 fp16 plane tile: 16 KB
+constexpr int kTcQ = 0;                           // Q  hi | lo            32 KB
+constexpr int kTcKV = 2 * kTcPlane;               // 2 stages x (K hi|lo, V hi|lo) = 2 x 64 KB
+constexpr int kTcP = kTcKV + 2 * 4 * kTcPlane;    // P  hi | lo, each 128 x 128 fp16 = 2 x 32 KB
+constexpr int kTcBars = kTcP + 4 * kTcPlane;
+constexpr size_t kTcSmem = (size_t)kTcBars + 1024 /*align*/ + 128 /*barriers*/ + 2 * 128 * 4 /*row max / row sum exchange*/;
+
+struct AttnTcParams {
+    int T, H, W;
+    float scale_log2;  // scale * log2(e)
+    float* out_f32; uint16_t* out_hi; uint16_t* out_lo; int fmt;
+    unsigned int* dbg;
+};
+
+__device__ __noinline__ void tc_timeout(unsigned int* dbg, int site) {
+    if (dbg) { dbg[(blockIdx.x & 7) * 8 + (site & 7)] = 0xDEAD0000u | (unsigned)site; __threadfence_system(); }
+    __trap();
+}
+__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, int site) {
+    if (slb_mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!slb_mbar_try_wait(bar, parity))
+        if (clock64() - t0 > 4000000000ll) tc_timeout(dbg, site);
+}
+
+// MN-major operand tile (rows = K index, 128 B per row = 64 contiguous MN elements), 128-byte swizzle:
+// SBO = 1024 B between 8-row groups along K; LBO (between 64-element MN atoms) unused for N = 64.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 16;    // LBO (not used: a single MN atom)
+    d |= (uint64_t)(1024 >> 4) << 32;    // SBO
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcBars);
+    uint64_t* q_full = bars;        // TMA -> MMA
+    uint64_t* kv_full = bars + 1;   // [2]
+    uint64_t* kv_empty = bars + 3;  // [2] MMA -> TMA
+    uint64_t* s_full = bars + 5;    // MMA -> softmax
+    uint64_t* s_free = bars + 6;    // softmax (4 warps) -> MMA
+    uint64_t* p_full = bars + 7;    // softmax (4 warps) -> MMA
+    uint64_t* p_free = bars + 8;    // MMA -> softmax
+    uint64_t* o_full = bars + 9;    // MMA -> softmax
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    float* xch = reinterpret_cast<float*>(bars + 16);  // [2][128]: partial row max / row sum of the second column half
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int q0 = blockIdx.y * kTcTile;
+    const int row_base = b * p.T;                       // first token row of this image in the planes
+    const int nblk = (p.T + kTcTile - 1) / kTcTile;
+    const int n_iter = 2 * nblk;                        // sweep 1 (max) then sweep 2 (P V)
+
+    if (warp == 0 && lane == 0) {
+        slb_prefetch_tmap(&tm);
+        slb_mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) { slb_mbar_init(&kv_full[s], 1); slb_mbar_init(&kv_empty[s], 1); }
+        slb_mbar_init(s_full, 1);
+        slb_mbar_init(s_free, kTcSoftmaxWarps);
+        slb_mbar_init(p_full, kTcSoftmaxWarps);
+        slb_mbar_init(p_free, 1);
+        slb_mbar_init(o_full, 1);
+        slb_fence_mbar_init();
+    }
+    if (warp == 1) slb_tmem_alloc<512>(tmem_slot);
+    slb_tc_fence_before();
+    __syncthreads();
+    slb_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_s = tmem_base;            // S main [0,128), S corr [128,256)
+    const uint32_t t_o = tmem_base + 256;      // O main [256,320), O corr [320,384)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            slb_mbar_arrive_expect_tx(q_full, 2u * kTcPlane);
+            slb_tma_load_3d(smem + kTcQ, &tm, h * 64, row_base + q0, 0, q_full);
+            for (int it = 0; it < n_iter; ++it) {
+                const int st = it & 1, blk = it % nblk;
+                const bool with_v = it >= nblk;
+                tc_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1u, p.dbg, 1);
+                unsigned char* dst = smem + kTcKV + (size_t)st * 4 * kTcPlane;
+                slb_mbar_arrive_expect_tx(&kv_full[st], (with_v ? 4u : 2u) * kTcPlane);
+                slb_tma_load_3d(dst, &tm, p.W + h * 64, row_base + blk * kTcTile, 0, &kv_full[st]);
+                if (with_v) slb_tma_load_3d(dst + 2 * kTcPlane, &tm, 2 * p.W + h * 64, row_base + blk * kTcTile, 0, &kv_full[st]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t qa = slb_smem_u32(smem + kTcQ);
+            const uint32_t pa = slb_smem_u32(smem + kTcP);
+            tc_wait(q_full, 0, p.dbg, 2);
+            for (int it = 0; it < n_iter; ++it) {
+                const int st = it & 1, blk = it % nblk;
+                const bool sweep2 = it >= nblk;
+                const int nk = min(kTcTile, (p.T - blk * kTcTile + 15) & ~15);  // keys of this block, padded to the MMA N step
+                const uint32_t ka = slb_smem_u32(smem + kTcKV + (size_t)st * 4 * kTcPlane);
+                const uint32_t va = ka + 2 * kTcPlane;
+                tc_wait(&kv_full[st], (it >> 1) & 1, p.dbg, 3);
+                tc_wait(s_free, (it & 1) ^ 1u, p.dbg, 4);  // the softmax warps have read the previous S
+                slb_tc_fence_after();
+                // S = Q K^T: hi.hi -> main, hi.lo + lo.hi -> corr
+                const uint32_t idesc_s = slb_umma_idesc_f16(0, kTcTile, nk);
+#pragma unroll
+                for (int pr = 0; pr < 3; ++pr) {
+                    const uint32_t ab = qa + (pr == 2 ? kTcPlane : 0);
+                    const uint32_t bb = ka + (pr == 1 ? kTcPlane : 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        slb_umma_f16(t_s + (pr ? 128 : 0), slb_umma_desc_sw128(ab + k * 32), slb_umma_desc_sw128(bb + k * 32),
+                                     idesc_s, pr == 0 ? k != 0 : ((pr - 1) | k) != 0);
+                }
+                slb_umma_commit(s_full);
+                if (!sweep2) {
+                    slb_umma_commit(&kv_empty[st]);
+                    continue;
+                }
+                // O += P V once the softmax warps have written P for this block
+                tc_wait(p_full, (uint32_t)((it - nblk) & 1), p.dbg, 5);
+                slb_tc_fence_after();
+                const uint32_t idesc_o = slb_umma_idesc_f16(0, kTcTile, 64) | (1u << 16);  // B (= V) is MN-major
+                const int ksteps = nk >> 4;
+#pragma unroll
+                for (int pr = 0; pr < 3; ++pr) {
+                    const uint32_t ab = pa + (pr == 2 ? 2 * kTcPlane : 0);   // P hi / lo (each 2 atoms of 64 keys)
+                    const uint32_t bb = va + (pr == 1 ? kTcPlane : 0);       // V hi / lo
+                    for (int k = 0; k < ksteps; ++k) {
+                        const bool acc = pr == 0 ? (blk | k) != 0 : (blk | (pr - 1) | k) != 0;
+                        slb_umma_f16(t_o + (pr ? 64 : 0), slb_umma_desc_sw128(ab + (k >> 2) * kTcPlane + (k & 3) * 32),
+                                     umma_desc_mn_sw128(bb + k * 2048), idesc_o, acc);
+                    }
+                }
+                slb_umma_commit(p_free);
+                slb_umma_commit(&kv_empty[st]);
+            }
+            slb_umma_commit(o_full);
+        }
+        __syncwarp();
+    } else {
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;            // which 64 keys of every 128-key block (= which swizzle atom of P)
+        const int r = quarter * 32 + lane;           // row of the tile = TMEM lane
+        const int row = q0 + r;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        constexpr float kInvS = 1.0f / 2048.0f;
+        const float c_main = p.scale_log2, c_corr = p.scale_log2 * kInvS;
+        float m_row = -INFINITY, l_row = 0.f;
+        unsigned char* p_hi = smem + kTcP;
+        unsigned char* p_lo = p_hi + 2 * kTcPlane;
+        for (int it = 0; it < n_iter; ++it) {
+            const int blk = it % nblk;
+            const bool sweep2 = it >= nblk;
+            const int nk = min(kTcTile, (p.T - blk * kTcTile + 15) & ~15);
+            if (it == nblk) {
+                // end of sweep 1: the two warps of a row exchange their partial maxima (named barrier 1: softmax warps only)
+                if (half) xch[r] = m_row;
+                asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
+                if (!half) m_row = fmaxf(m_row, xch[r]);
+                asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
+                if (!half) xch[r] = m_row;
+                asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
+                m_row = xch[r];
+            }
+            tc_wait(s_full, (uint32_t)(it & 1), p.dbg, 6);
+            slb_tc_fence_after();
+            if (sweep2) tc_wait(p_free, (uint32_t)((it - nblk) & 1) ^ 1u, p.dbg, 7);  // previous P consumed by its MMAs
+            for (int c = half * 64; c < min(nk, half * 64 + 64); c += 32) {
+                uint32_t a[32], cr[32];
+                slb_tmem_ld_32x32(t_s + lane_addr + c, a);
+                slb_tmem_ld_32x32(t_s + lane_addr + 128 + c, cr);
+                slb_tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float sv = fmaf(__uint_as_float(cr[j]), c_corr, __uint_as_float(a[j]) * c_main);
+                    v[j] = (blk * kTcTile + c + j < p.T) ? sv : -INFINITY;
+                }
+                if (!sweep2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) m_row = fmaxf(m_row, v[j]);
+                } else {
+                    // p = exp2(s - max); 16-byte chunks of hi and of lo per 8 keys, swizzled like TMA would write them
+#pragma unroll
+                    for (int q8 = 0; q8 < 4; ++q8) {
+                        uint32_t hh[4], ll[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float p0 = exp2f(v[q8 * 8 + 2 * e] - m_row), p1 = exp2f(v[q8 * 8 + 2 * e + 1] - m_row);
+                            l_row += p0 + p1;
+                            split_pair_unit(p0, p1, hh[e], ll[e]);
+                        }
+                        const int key = c + q8 * 8;                    // first key of this 16-byte chunk
+                        const int atom = key >> 6, chunk = (key & 63) >> 3;
+                        const size_t off = (size_t)atom * kTcPlane + (size_t)r * 128 + (size_t)((chunk ^ (r & 7)) << 4);
+                        *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                        *reinterpret_cast<uint4*>(p_lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                    }
+                }
+            }
+            slb_tc_fence_before();
+            if (sweep2) slb_fence_proxy_async();  // the P tile was written through the generic proxy; the MMA reads it through the async proxy
+            __syncwarp();
+            if (lane == 0) {
+                if (sweep2) slb_mbar_arrive(p_full);
+                slb_mbar_arrive(s_free);
+            }
+        }
+        // ---- row sums of the two column halves, then O = (main + corr / 2^11) / l; each warp stores 32 of the 64 dims ----
+        if (half) xch[128 + r] = l_row;
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
+        if (!half) xch[128 + r] += l_row;
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
+        l_row = xch[128 + r];
+        tc_wait(o_full, 0, p.dbg, 0);
+        slb_tc_fence_after();
+        const float inv = 1.0f / l_row;
+        const bool ok = row < p.T;
+        const int64_t base = ((int64_t)row_base + row) * p.W + (int64_t)h * 64;
+        {
+            const int c = half * 32;
+            uint32_t a[32], cr[32];
+            slb_tmem_ld_32x32(t_o + lane_addr + c, a);
+            slb_tmem_ld_32x32(t_o + lane_addr + 64 + c, cr);
+            slb_tmem_ld_wait();
+            if (ok) {
+                float o[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = fmaf(__uint_as_float(cr[j]), kInvS, __uint_as_float(a[j])) * inv;
+                if (p.out_f32) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        reinterpret_cast<float4*>(p.out_f32 + base + c)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                }
+                if (p.out_hi) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t hh[4], ll[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            uint16_t h0, l0, h1, l1;
+                            slb_split2(o[8 * j + 2 * e], p.fmt, h0, l0);
+                            slb_split2(o[8 * j + 2 * e + 1], p.fmt, h1, l1);
+                            hh[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                            ll[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                        }
+                        *reinterpret_cast<uint4*>(p.out_hi + base + c + 8 * j) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                        *reinterpret_cast<uint4*>(p.out_lo + base + c + 8 * j) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                    }
+                }
+            }
+        }
+    }
+
+    slb_tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        slb_tc_fence_after();
+        slb_tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace
+
+// Full 128-row query tiles of every (image, head) on the tcgen05 path; the caller handles the remaining rows.
+int slb_attention_tc_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles,
+                           int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
+    const int64_t W = H * 64, rows = B * T;
+    CUtensorMap tm;
+    int rc = slb_make_plane_map(&tm, qkv_planes, rows, 3 * W, 2, kTcTile);
+    if (rc != SLB_OK) return rc;
+    AttnTcParams p{};
+    p.T = (int)T; p.H = (int)H; p.W = (int)W;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.out_f32 = out_f32; p.out_hi = out_hi; p.out_lo = out_lo; p.fmt = plane_fmt;
+    p.dbg = nullptr;
+    SLB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+    dim3 grid((unsigned)(B * H), (unsigned)n_tiles);
+    attention_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(tm, p);
+    SLB_LAUNCH_OK("attention_tc");
+    return SLB_OK;
 }

@@ -56,7 +56,11 @@ def test_attention_vs_torch(ops, B, T, H, dh, gain):
 
 
 @pytest.mark.parametrize("B,T,H,gain", [(2, 50, 12, 1.0), (1, 257, 4, 1.0), (2, 197, 3, 1.0), (1, 1, 1, 1.0), (2, 64, 2, 1.0),
-                                       (1, 65, 2, 3.0), (1, 300, 1, 2.0), (70, 50, 12, 4.0), (3, 16, 2, 1.0)])
+                                       (1, 65, 2, 3.0), (1, 300, 1, 2.0), (70, 50, 12, 4.0), (3, 16, 2, 1.0),
+                                       # tcgen05 tiles: exactly one tile, tile + 1-row tail, tile + 64-row second tile,
+                                       # three key blocks, many (image, head) pairs
+                                       (2, 128, 2, 1.0), (2, 129, 2, 1.0), (1, 192, 3, 2.0), (1, 255, 1, 1.0), (1, 256, 2, 1.0),
+                                       (1, 320, 2, 1.0), (9, 257, 16, 1.0), (2, 577, 2, 1.0)])
 def test_attention_from_planes_vs_torch(ops, B, T, H, gain):
     """The tower's path: attention reads q | k | v from the in_proj GEMM's split planes (cp.async + ldmatrix + mma.sync)."""
     dh = 64
