@@ -578,23 +578,26 @@ extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64
 //
 // One CTA = one (image, head, 128-query tile); 192 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax
 // (thread = query row = TMEM lane). Operands come from the in_proj GEMM's split planes through ONE 3-D tensor map
-// (box 64 cols x 128 rows x 2 planes, 128B swizzle): Q, K blocks and V blocks of 128 tokens. Two sweeps over the keys
+// (boxes of 64 cols x 128 / 64 rows x 2 planes, 128B swizzle): the Q tile, K blocks and V blocks of 64 tokens. The tiles
+// take 96 KB and the accumulators 256 TMEM columns, so TWO CTAs share an SM and fill each other's hand-off bubbles. Two sweeps over the keys
 // avoid rescaling the output accumulator: sweep 1 computes S = Q K^T block by block for the row maxima only, sweep 2
 // recomputes S, writes P = exp2(S - max) as split planes into shared memory (K-major, swizzled by hand) and accumulates
 // O += P V with V consumed straight from its row-major tile as an MN-major operand (no transpose anywhere).
-// Accumulators (TMEM): S main | S corr (2 x 128 columns), O main | O corr (2 x 64 columns); every product is the
+// Accumulators (TMEM): S main | S corr (2 x 64 columns), O main | O corr (2 x 64 columns); every product is the
 // usual three plane products. Rows of the tile beyond T and keys beyond T are masked / never stored.
 // =================================================================================================
 namespace {
 
-constexpr int kTcSoftmaxWarps = 8;                // two warps per TMEM lane quarter: each takes 64 of a block's 128 keys
+constexpr int kTcSoftmaxWarps = 8;                // two warps per TMEM lane quarter: each takes 32 of a block's 64 keys
 constexpr int kTcThreads = (2 + kTcSoftmaxWarps) * 32;
-constexpr int kTcTile = 128;                      // queries per CTA and keys per block
-constexpr int kTcPlane = kTcTile * 64 * 2;        // one 128 x 64 fp16 plane tile: 16 KB
-constexpr int kTcQ = 0;                           // Q  hi | lo            32 KB
-constexpr int kTcKV = 2 * kTcPlane;               // 2 stages x (K hi|lo, V hi|lo) = 2 x 64 KB
-constexpr int kTcP = kTcKV + 2 * 4 * kTcPlane;    // P  hi | lo, each 128 x 128 fp16 = 2 x 32 KB
-constexpr int kTcBars = kTcP + 4 * kTcPlane;
+constexpr int kTcTile = 128;                      // queries per CTA
+constexpr int kTcKeys = 64;                       // keys per block
+constexpr int kTcPlaneQ = kTcTile * 64 * 2;       // one 128 x 64 fp16 plane tile (Q, P): 16 KB
+constexpr int kTcPlaneK = kTcKeys * 64 * 2;       // one 64 x 64 fp16 plane tile (K, V): 8 KB
+constexpr int kTcQ = 0;                           // Q  hi | lo                       32 KB
+constexpr int kTcKV = 2 * kTcPlaneQ;              // K hi | lo, V hi | lo (one stage)  32 KB
+constexpr int kTcP = kTcKV + 4 * kTcPlaneK;       // P  hi | lo (128 x 64 each)        32 KB
+constexpr int kTcBars = kTcP + 2 * kTcPlaneQ;     // 96 KB of tiles: two CTAs per SM hide each other's hand-off latencies
 constexpr size_t kTcSmem = (size_t)kTcBars + 1024 /*align*/ + 128 /*barriers*/ + 2 * 128 * 4 /*row max / row sum exchange*/;
 
 struct AttnTcParams {
@@ -627,13 +630,14 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
     return d;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap tm, AttnTcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv, AttnTcParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcBars);
     uint64_t* q_full = bars;        // TMA -> MMA
-    uint64_t* kv_full = bars + 1;   // [2]
-    uint64_t* kv_empty = bars + 3;  // [2] MMA -> TMA
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = bars + 3;  // MMA -> TMA
     uint64_t* s_full = bars + 5;    // MMA -> softmax
     uint64_t* s_free = bars + 6;    // softmax (4 warps) -> MMA
     uint64_t* p_full = bars + 7;    // softmax (4 warps) -> MMA
@@ -646,13 +650,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
     const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int q0 = blockIdx.y * kTcTile;
     const int row_base = b * p.T;                       // first token row of this image in the planes
-    const int nblk = (p.T + kTcTile - 1) / kTcTile;
+    const int nblk = (p.T + kTcKeys - 1) / kTcKeys;
     const int n_iter = 2 * nblk;                        // sweep 1 (max) then sweep 2 (P V)
 
     if (warp == 0 && lane == 0) {
-        slb_prefetch_tmap(&tm);
+        slb_prefetch_tmap(&tmq);
+        slb_prefetch_tmap(&tmkv);
         slb_mbar_init(q_full, 1);
-        for (int s = 0; s < 2; ++s) { slb_mbar_init(&kv_full[s], 1); slb_mbar_init(&kv_empty[s], 1); }
+        slb_mbar_init(kv_full, 1);
+        slb_mbar_init(kv_empty, 1);
         slb_mbar_init(s_full, 1);
         slb_mbar_init(s_free, kTcSoftmaxWarps);
         slb_mbar_init(p_full, kTcSoftmaxWarps);
@@ -660,26 +666,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         slb_mbar_init(o_full, 1);
         slb_fence_mbar_init();
     }
-    if (warp == 1) slb_tmem_alloc<512>(tmem_slot);
+    if (warp == 1) slb_tmem_alloc<256>(tmem_slot);
     slb_tc_fence_before();
     __syncthreads();
     slb_tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t t_s = tmem_base;            // S main [0,128), S corr [128,256)
-    const uint32_t t_o = tmem_base + 256;      // O main [256,320), O corr [320,384)
+    const uint32_t t_s = tmem_base;            // S main [0,64), S corr [64,128)
+    const uint32_t t_o = tmem_base + 128;      // O main [128,192), O corr [192,256)
 
     if (warp == 0) {
         if (lane == 0) {
-            slb_mbar_arrive_expect_tx(q_full, 2u * kTcPlane);
-            slb_tma_load_3d(smem + kTcQ, &tm, h * 64, row_base + q0, 0, q_full);
+            slb_mbar_arrive_expect_tx(q_full, 2u * kTcPlaneQ);
+            slb_tma_load_3d(smem + kTcQ, &tmq, h * 64, row_base + q0, 0, q_full);
             for (int it = 0; it < n_iter; ++it) {
-                const int st = it & 1, blk = it % nblk;
+                const int blk = it % nblk;
                 const bool with_v = it >= nblk;
-                tc_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1u, p.dbg, 1);
-                unsigned char* dst = smem + kTcKV + (size_t)st * 4 * kTcPlane;
-                slb_mbar_arrive_expect_tx(&kv_full[st], (with_v ? 4u : 2u) * kTcPlane);
-                slb_tma_load_3d(dst, &tm, p.W + h * 64, row_base + blk * kTcTile, 0, &kv_full[st]);
-                if (with_v) slb_tma_load_3d(dst + 2 * kTcPlane, &tm, 2 * p.W + h * 64, row_base + blk * kTcTile, 0, &kv_full[st]);
+                tc_wait(kv_empty, (uint32_t)(it & 1) ^ 1u, p.dbg, 1);
+                unsigned char* dst = smem + kTcKV;
+                slb_mbar_arrive_expect_tx(kv_full, (with_v ? 4u : 2u) * kTcPlaneK);
+                slb_tma_load_3d(dst, &tmkv, p.W + h * 64, row_base + blk * kTcKeys, 0, kv_full);
+                if (with_v) slb_tma_load_3d(dst + 2 * kTcPlaneK, &tmkv, 2 * p.W + h * 64, row_base + blk * kTcKeys, 0, kv_full);
             }
         }
         __syncwarp();
@@ -689,28 +695,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
             const uint32_t pa = slb_smem_u32(smem + kTcP);
             tc_wait(q_full, 0, p.dbg, 2);
             for (int it = 0; it < n_iter; ++it) {
-                const int st = it & 1, blk = it % nblk;
+                const int blk = it % nblk;
                 const bool sweep2 = it >= nblk;
-                const int nk = min(kTcTile, (p.T - blk * kTcTile + 15) & ~15);  // keys of this block, padded to the MMA N step
-                const uint32_t ka = slb_smem_u32(smem + kTcKV + (size_t)st * 4 * kTcPlane);
-                const uint32_t va = ka + 2 * kTcPlane;
-                tc_wait(&kv_full[st], (it >> 1) & 1, p.dbg, 3);
+                const int nk = min(kTcKeys, (p.T - blk * kTcKeys + 15) & ~15);  // keys of this block, padded to the MMA N step
+                const uint32_t ka = slb_smem_u32(smem + kTcKV);
+                const uint32_t va = ka + 2 * kTcPlaneK;
+                tc_wait(kv_full, (uint32_t)(it & 1), p.dbg, 3);
                 tc_wait(s_free, (it & 1) ^ 1u, p.dbg, 4);  // the softmax warps have read the previous S
                 slb_tc_fence_after();
                 // S = Q K^T: hi.hi -> main, hi.lo + lo.hi -> corr
                 const uint32_t idesc_s = slb_umma_idesc_f16(0, kTcTile, nk);
 #pragma unroll
                 for (int pr = 0; pr < 3; ++pr) {
-                    const uint32_t ab = qa + (pr == 2 ? kTcPlane : 0);
-                    const uint32_t bb = ka + (pr == 1 ? kTcPlane : 0);
+                    const uint32_t ab = qa + (pr == 2 ? kTcPlaneQ : 0);
+                    const uint32_t bb = ka + (pr == 1 ? kTcPlaneK : 0);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        slb_umma_f16(t_s + (pr ? 128 : 0), slb_umma_desc_sw128(ab + k * 32), slb_umma_desc_sw128(bb + k * 32),
+                        slb_umma_f16(t_s + (pr ? 64 : 0), slb_umma_desc_sw128(ab + k * 32), slb_umma_desc_sw128(bb + k * 32),
                                      idesc_s, pr == 0 ? k != 0 : ((pr - 1) | k) != 0);
                 }
                 slb_umma_commit(s_full);
                 if (!sweep2) {
-                    slb_umma_commit(&kv_empty[st]);
+                    slb_umma_commit(kv_empty);
                     continue;
                 }
                 // O += P V once the softmax warps have written P for this block
@@ -720,23 +726,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
                 const int ksteps = nk >> 4;
 #pragma unroll
                 for (int pr = 0; pr < 3; ++pr) {
-                    const uint32_t ab = pa + (pr == 2 ? 2 * kTcPlane : 0);   // P hi / lo (each 2 atoms of 64 keys)
-                    const uint32_t bb = va + (pr == 1 ? kTcPlane : 0);       // V hi / lo
+                    const uint32_t ab = pa + (pr == 2 ? kTcPlaneQ : 0);   // P hi / lo
+                    const uint32_t bb = va + (pr == 1 ? kTcPlaneK : 0);   // V hi / lo
                     for (int k = 0; k < ksteps; ++k) {
                         const bool acc = pr == 0 ? (blk | k) != 0 : (blk | (pr - 1) | k) != 0;
-                        slb_umma_f16(t_o + (pr ? 64 : 0), slb_umma_desc_sw128(ab + (k >> 2) * kTcPlane + (k & 3) * 32),
-                                     umma_desc_mn_sw128(bb + k * 2048), idesc_o, acc);
+                        slb_umma_f16(t_o + (pr ? 64 : 0), slb_umma_desc_sw128(ab + k * 32), umma_desc_mn_sw128(bb + k * 2048),
+                                     idesc_o, acc);
                     }
                 }
                 slb_umma_commit(p_free);
-                slb_umma_commit(&kv_empty[st]);
+                slb_umma_commit(kv_empty);
             }
             slb_umma_commit(o_full);
         }
         __syncwarp();
     } else {
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;            // which 64 keys of every 128-key block (= which swizzle atom of P)
+        const int half = (warp - 2) >> 2;            // which 32 keys of every 64-key block
         const int r = quarter * 32 + lane;           // row of the tile = TMEM lane
         const int row = q0 + r;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -744,11 +750,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         const float c_main = p.scale_log2, c_corr = p.scale_log2 * kInvS;
         float m_row = -INFINITY, l_row = 0.f;
         unsigned char* p_hi = smem + kTcP;
-        unsigned char* p_lo = p_hi + 2 * kTcPlane;
+        unsigned char* p_lo = p_hi + kTcPlaneQ;
         for (int it = 0; it < n_iter; ++it) {
             const int blk = it % nblk;
             const bool sweep2 = it >= nblk;
-            const int nk = min(kTcTile, (p.T - blk * kTcTile + 15) & ~15);
+            const int nk = min(kTcKeys, (p.T - blk * kTcKeys + 15) & ~15);
             if (it == nblk) {
                 // end of sweep 1: the two warps of a row exchange their partial maxima (named barrier 1: softmax warps only)
                 if (half) xch[r] = m_row;
@@ -762,16 +768,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
             tc_wait(s_full, (uint32_t)(it & 1), p.dbg, 6);
             slb_tc_fence_after();
             if (sweep2) tc_wait(p_free, (uint32_t)((it - nblk) & 1) ^ 1u, p.dbg, 7);  // previous P consumed by its MMAs
-            for (int c = half * 64; c < min(nk, half * 64 + 64); c += 32) {
+            for (int c = half * 32; c < min(nk, half * 32 + 32); c += 32) {
                 uint32_t a[32], cr[32];
                 slb_tmem_ld_32x32(t_s + lane_addr + c, a);
-                slb_tmem_ld_32x32(t_s + lane_addr + 128 + c, cr);
+                slb_tmem_ld_32x32(t_s + lane_addr + 64 + c, cr);
                 slb_tmem_ld_wait();
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float sv = fmaf(__uint_as_float(cr[j]), c_corr, __uint_as_float(a[j]) * c_main);
-                    v[j] = (blk * kTcTile + c + j < p.T) ? sv : -INFINITY;
+                    v[j] = (blk * kTcKeys + c + j < p.T) ? sv : -INFINITY;
                 }
                 if (!sweep2) {
 #pragma unroll
@@ -788,8 +794,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
                             split_pair_unit(p0, p1, hh[e], ll[e]);
                         }
                         const int key = c + q8 * 8;                    // first key of this 16-byte chunk
-                        const int atom = key >> 6, chunk = (key & 63) >> 3;
-                        const size_t off = (size_t)atom * kTcPlane + (size_t)r * 128 + (size_t)((chunk ^ (r & 7)) << 4);
+                        const int chunk = key >> 3;
+                        const size_t off = (size_t)r * 128 + (size_t)((chunk ^ (r & 7)) << 4);
                         *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
                         *reinterpret_cast<uint4*>(p_lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
                     }
@@ -853,7 +859,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
     __syncthreads();
     if (warp == 1) {
         slb_tc_fence_after();
-        slb_tmem_dealloc<512>(tmem_base);
+        slb_tmem_dealloc<256>(tmem_base);
     }
 }
 
@@ -863,8 +869,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
 int slb_attention_tc_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles,
                            int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
     const int64_t W = H * 64, rows = B * T;
-    CUtensorMap tm;
-    int rc = slb_make_plane_map(&tm, qkv_planes, rows, 3 * W, 2, kTcTile);
+    CUtensorMap tmq, tmkv;
+    int rc = slb_make_plane_map(&tmq, qkv_planes, rows, 3 * W, 2, kTcTile);
+    if (rc != SLB_OK) return rc;
+    rc = slb_make_plane_map(&tmkv, qkv_planes, rows, 3 * W, 2, kTcKeys);
     if (rc != SLB_OK) return rc;
     AttnTcParams p{};
     p.T = (int)T; p.H = (int)H; p.W = (int)W;
@@ -873,7 +881,7 @@ int slb_attention_tc_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int
     p.dbg = nullptr;
     SLB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
     dim3 grid((unsigned)(B * H), (unsigned)n_tiles);
-    attention_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(tm, p);
+    attention_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(tmq, tmkv, p);
     SLB_LAUNCH_OK("attention_tc");
     return SLB_OK;
 }
