@@ -19,6 +19,7 @@
 #include "tc_common.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 #include <algorithm>
 
 namespace {
@@ -285,13 +286,20 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //   tfull[a]   in each CTA; commit multicast after the tile's last k-block
 //   tempty[a]  leader only, 16 arrivals: the 8 epilogue warps of each CTA (the peer's arrive remotely)
 // ---------------------------------------------------------------------------------------------
+// PBN = 128: 256 x 128 pair tile, accumulators double-buffered (2 x 2 x 128 TMEM columns), 4 stages of 48 KB.
+// PBN = 256: 256 x 256 pair tile — per MMA cycle each CTA reads half as much shared memory (its 128 A rows and HALF of W
+//            serve a 256-wide MMA; one-CTA 128 x 128 tiles read 128 B/clk, the shared-memory limit) and half as much L2;
+//            main + corr fill all 512 TMEM columns, so the epilogue of a tile is NOT overlapped with the next main loop:
+//            worth it when K is long.
+template <int PBN>
 struct CfgPair {
-    static constexpr int BN = 128;
-    static constexpr int kStages = 4;
+    static constexpr int BN = PBN;
+    static constexpr int kAccBufs = PBN == 128 ? 2 : 1;
+    static constexpr int kStages = PBN == 128 ? 4 : 3;
     static constexpr int kABytes = 2 * BM * BK * 2;        // this CTA's 128 A rows, both planes
-    static constexpr int kWBytes = 2 * (BN / 2) * BK * 2;  // this CTA's 64 W rows, both planes
-    static constexpr int kStageBytes = kABytes + kWBytes;  // 48 KB
-    static constexpr int kTmemCols = 4 * BN;               // [buffer][main | corr][BN]
+    static constexpr int kWBytes = 2 * (BN / 2) * BK * 2;  // this CTA's half of the W rows, both planes
+    static constexpr int kStageBytes = kABytes + kWBytes;  // 48 / 64 KB
+    static constexpr int kTmemCols = 512;                  // [buffer][main | corr][BN]
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 + 256;
 };
 
@@ -315,9 +323,10 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
     }
 }
 
+template <int PBN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmParams p) {
-    using C = CfgPair;
+    using C = CfgPair<PBN>;
     constexpr int BN = C::BN;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -410,8 +419,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
                 slb_umma_commit_pair(&tfull[acc], 0b11);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
+                if (++acc == C::kAccBufs) { acc = 0; acc_phase ^= 1u; }
             }
         }
         __syncwarp();
@@ -437,8 +445,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             slb_tc_fence_before();
             __syncwarp();
             if (lane == 0) slb_mbar_arrive_cluster(slb_mapa(slb_smem_u32(&tempty[acc]), 0));
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
+            if (++acc == C::kAccBufs) { acc = 0; acc_phase ^= 1u; }
         }
     }
 
@@ -484,8 +491,9 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams
 unsigned int* g_dbg_host = nullptr;  // SLB_GEMM_DEBUG=1 only
 unsigned int* g_dbg_dev = nullptr;
 
+template <int PBN>
 int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p_in, cudaStream_t st) {
-    using C = CfgPair;
+    using C = CfgPair<PBN>;
     GemmParams p = p_in;
     static const bool debug = [] { const char* e = getenv("SLB_GEMM_DEBUG"); return e && e[0] == '1'; }();
     if (debug) {
@@ -496,10 +504,10 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmP
         for (int i = 0; i < 8 * 32; ++i) g_dbg_host[i] = 0;
         p.dbg = g_dbg_dev;
     }
-    SLB_CUDA_OK(cudaFuncSetAttribute(gemm_split_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    SLB_CUDA_OK(cudaFuncSetAttribute(gemm_split_pair_kernel<PBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
     const int64_t tiles = slb_ceil_div(p.M, 2 * BM) * slb_ceil_div(p.N, C::BN);
     const int clusters = (int)std::min<int64_t>(tiles, slb_sm_count() / 2);
-    gemm_split_pair_kernel<<<2 * clusters, kThreads, C::kSmem, st>>>(tmA, tmW, p);
+    gemm_split_pair_kernel<PBN><<<2 * clusters, kThreads, C::kSmem, st>>>(tmA, tmW, p);
     SLB_LAUNCH_OK("gemm_split_pair");
     if (debug) {
         cudaError_t e = cudaStreamSynchronize(st);
@@ -596,21 +604,35 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
     p.bias = bias; p.residual = residual; p.row_scale = row_scale; p.col_scale = col_scale;
     p.out_f32 = out_f32; p.out_planes = out_planes;
     p.epilogue = epilogue; p.passes = passes; p.fmt = plane_fmt;
-    // Kernel choice (measured on B200, profiles/r01_gemm_variants.jsonl): the CTA-pair kernel (256 x 128 tiles, 4-stage
-    // ring) wins when W is large (cosine GEMM N = 65536: 878 vs 781 TFLOP/s; 8192^3: 1108 vs 1092 burst, 959 vs 910
-    // sustained under the power cap), the one-CTA kernel (128 x 128 tiles) on the ViT shapes (N <= 3072: 1083 vs 1050,
-    // N = 768: 913 vs 813). SLB_GEMM_SINGLE=1 / SLB_GEMM_PAIR=1 force one of them (A/B measurements).
-    static const bool force_single = [] { const char* e = getenv("SLB_GEMM_SINGLE"); return e && e[0] == '1'; }();
-    static const bool force_pair = [] { const char* e = getenv("SLB_GEMM_PAIR"); return e && e[0] == '1'; }();
-    const bool pair = !force_single && M > BM && (force_pair || N >= 4096);
+    // Kernel choice (measured on B200, profiles/r01_gemm_variants.jsonl). One-CTA 128 x 128 tiles read 128 B/clk of shared
+    // memory per MMA cycle (the limit); CTA pairs share W: 256 x 128 pair tiles (double-buffered accumulators) win when W
+    // is large (cosine GEMM), 256 x 256 pair tiles (single-buffered) when K is long and the tile count fills the machine
+    // without a short last wave (8192^3: 1440 vs 1055 TFLOP/s burst, 1193 vs 882 sustained at 89 % vs 72 % pipe
+    // utilisation; ViT-L/14 c_proj K = 4096: 1382 vs 1294). SLB_GEMM_KERNEL = single | pair128 | pair256 forces one.
+    static const int forced = [] {
+        const char* e = getenv("SLB_GEMM_KERNEL");
+        if (!e) return 0;
+        return !strcmp(e, "single") ? 1 : (!strcmp(e, "pair128") ? 2 : (!strcmp(e, "pair256") ? 3 : 0));
+    }();
+    int kind = 1;  // 1 single, 2 pair128, 3 pair256
+    if (M > BM) {
+        const int64_t pairs = slb_sm_count() / 2;
+        const int64_t t256 = slb_ceil_div(M, 2 * BM) * slb_ceil_div(N, 256);
+        const double waves256 = (double)t256 / (double)pairs;
+        const double eff256 = waves256 / (double)slb_ceil_div(t256, pairs);  // last-wave utilisation
+        if (N >= 4096) kind = 2;
+        if (K >= 2048 && N >= 256 && eff256 >= 0.85) kind = 3;  // K = 1024: the exposed epilogue still costs more than it saves
+    }
+    if (forced) kind = (M > BM || forced == 1) ? forced : 1;
     CUtensorMap tmA, tmW;
     int rc = slb_make_plane_map(&tmA, a_planes, M, K, 2, BM);
     if (rc != SLB_OK) return rc;
     static const bool bn256 = [] { const char* e = getenv("SLB_GEMM_BN256"); return e && e[0] == '1'; }();  // experiment
-    rc = slb_make_plane_map(&tmW, w_planes, N, K, 2, pair ? 64 : (bn256 ? 256 : 128));
+    rc = slb_make_plane_map(&tmW, w_planes, N, K, 2, kind == 3 ? 128 : (kind == 2 ? 64 : (bn256 ? 256 : 128)));
     if (rc != SLB_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (pair) return launch_gemm_pair(tmA, tmW, p, st);
+    if (kind == 3) return launch_gemm_pair<256>(tmA, tmW, p, st);
+    if (kind == 2) return launch_gemm_pair<128>(tmA, tmW, p, st);
     if (bn256) return launch_gemm<256>(tmA, tmW, p, st);
     return launch_gemm<128>(tmA, tmW, p, st);
 }
