@@ -93,7 +93,8 @@ def bench_collect(batch):
 
 
 def bench_gemm(batch):
-    """K4 on the GEMM shapes of the ViT towers (rows = batch * tokens) and K6 at cfg-5 size."""
+    """K4 on the GEMM shapes of the ViT towers (rows = batch * tokens) and K6 at cfg-5 size.
+    SLB_GEMM_KERNEL=single|pair128|pair256 forces a kernel variant, SLB_BENCH_ONLY=<substring> selects cases."""
     pk = peaks()
     from semanticlens_b200 import _native as N
 

@@ -31,9 +31,9 @@ constexpr int kThreads = (2 + kEpiWarps) * 32;
 
 template <int BN>
 struct Cfg {
-    static_assert(BN == 128 || BN == 256, "main + correction accumulators: 2 buffers at BN = 128, 1 at BN = 256");
-    static constexpr int kAccBufs = BN == 128 ? 2 : 1;
-    static constexpr int kStages = BN == 128 ? 3 : 2;
+    static_assert(BN == 128, "two double-buffered accumulator pairs fill the 512 TMEM columns at BN = 128");
+    static constexpr int kAccBufs = 2;
+    static constexpr int kStages = 3;
     static constexpr int kABytes = 2 * BM * BK * 2;  // both planes
     static constexpr int kWBytes = 2 * BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kWBytes;
@@ -627,12 +627,10 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
     CUtensorMap tmA, tmW;
     int rc = slb_make_plane_map(&tmA, a_planes, M, K, 2, BM);
     if (rc != SLB_OK) return rc;
-    static const bool bn256 = [] { const char* e = getenv("SLB_GEMM_BN256"); return e && e[0] == '1'; }();  // experiment
-    rc = slb_make_plane_map(&tmW, w_planes, N, K, 2, kind == 3 ? 128 : (kind == 2 ? 64 : (bn256 ? 256 : 128)));
+    rc = slb_make_plane_map(&tmW, w_planes, N, K, 2, kind == 2 ? 64 : 128);  // W rows staged per CTA
     if (rc != SLB_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (kind == 3) return launch_gemm_pair<256>(tmA, tmW, p, st);
     if (kind == 2) return launch_gemm_pair<128>(tmA, tmW, p, st);
-    if (bn256) return launch_gemm<256>(tmA, tmW, p, st);
     return launch_gemm<128>(tmA, tmW, p, st);
 }
