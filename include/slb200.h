@@ -121,9 +121,9 @@ int slb_gather_rows(const float* table, int64_t N, int64_t D, const int64_t* idx
 
 /* F.normalize(x, dim=-1, eps) fused with the split-plane conversion: planes [2, rows, Kpad] of x / max(|x|, eps),
  * Kpad = D rounded up to a multiple of 64 (zero padded), and/or inv_norms [rows] = 1 / max(|x|, eps).
- * Either output may be NULL. D % 4 == 0, D <= 2048. (scores.py:120-121) */
-int slb_normalize_split_rows(const float* x, int64_t rows, int64_t D, float eps, int plane_fmt, uint16_t* planes,
-                             float* inv_norms, void* stream);
+ * The planes hold plane_scale * x / max(|x|, eps). Either output may be NULL. D % 4 == 0, D <= 2048. (scores.py:120-121) */
+int slb_normalize_split_rows(const float* x, int64_t rows, int64_t D, float eps, int plane_fmt, float plane_scale,
+                             uint16_t* planes, float* inv_norms, void* stream);
 
 /* K6. out[M,N] = normalize(x)[M,D] . normalize(y)[N,D]^T — scores.similarity_score's matmul branch
  * (scores.py:119-125, reached from Lens.text_probing / image_probing via lens.py:207-214). fp32 out, fp32-grade
@@ -158,13 +158,18 @@ int slb_rowmax_offdiag(const float* S, int64_t rows, int64_t cols, int64_t row0,
  * embed: the CLIP / SigLIP ViT image tower  (foundation_models/clip.py:103-163 -> open_clip, not vendored)
  * ---------------------------------------------------------------------------------------- */
 
-/* 16-bit "split plane" formats: x ~= hi + lo, hi = rn16(x), lo = rn16(x - hi).
- * F16: 22 significant bits, |x| <= 65504 (saturating). BF16: 16 significant bits, fp32 range. */
+/* 16-bit "split plane" operands: s * x ~= hi + lo with hi = rn16(s * x), lo = rn16(s * x - hi), s a power of two chosen
+ * per tensor so that typical magnitudes sit well inside the fp16 normal range (the lo plane then keeps its 11 bits; a lo
+ * that underflows costs at most 2^-25 absolute). Because hi and lo share ONE scale, all three plane products of a GEMM
+ * (hi.hi, hi.lo, lo.hi) accumulate in a single tensor-memory accumulator.
+ * F16: 22 significant bits, |s * x| <= 65504 (saturating). BF16: 16 significant bits, fp32 range. */
 #define SLB_PLANE_F16 0
 #define SLB_PLANE_BF16 1
+#define SLB_ACT_PLANE_SCALE 16.0f      /* every plane WRITTEN by a kernel (LayerNorm, attention, GEMM epilogue, patchify) */
+#define SLB_WEIGHT_PLANE_SCALE 1024.0f /* what the towers expect of their weight planes (slb_split_planes(..., 1024, ...)) */
 
-/* x fp32 [n] -> planes [2][n] (hi plane, then lo plane). n % 4 == 0. */
-int slb_split_planes(const float* x, int64_t n, int plane_fmt, uint16_t* planes, void* stream);
+/* x fp32 [n] -> planes [2][n] (hi plane, then lo plane) of scale * x. n % 4 == 0. */
+int slb_split_planes(const float* x, int64_t n, int plane_fmt, float scale, uint16_t* planes, void* stream);
 
 /* epilogue selectors for slb_gemm_split */
 #define SLB_EPI_NONE 0
@@ -172,18 +177,19 @@ int slb_split_planes(const float* x, int64_t n, int plane_fmt, uint16_t* planes,
 #define SLB_EPI_QUICKGELU 2 /* x * sigmoid(1.702 x)  (open_clip *-quickgelu, OpenAI weights) */
 #define SLB_EPI_GELU_TANH 3 /* nn.GELU("tanh")       (SigLIP / timm towers) */
 
-/* K4/K6. D[M,N] = act((A[M,K] * W[N,K]^T) * row_scale[m] * col_scale[n] + bias[n]) + residual[M,N]
+/* K4/K6. D[M,N] = act(alpha * (A[M,K] * W[N,K]^T) * row_scale[m] * col_scale[n] + bias[n]) + residual[M,N]
  * on the 5th-gen tensor cores (tcgen05.mma kind::f16, TMA-fed 128B-swizzled stages, fp32 accumulators in TMEM) with
  * fp32-grade accuracy: operands are split planes a_planes [2,M,K], w_planes [2,N,K] (row-major, K contiguous) and each
- * tile accumulates Ahi*Whi + Ahi*Wlo + Alo*Whi (passes = 3) or Ahi*Whi only (passes = 1).
+ * tile accumulates Ahi*Whi + Ahi*Wlo + Alo*Whi (passes = 3) or Ahi*Whi only (passes = 1) in ONE accumulator.
  * Replaces the fp32 GEMMs of open_clip's image tower (clip.py:118) and the cosine matmul of
  * scores.similarity_score (scores.py:120-125; row_scale/col_scale = inverse row norms).
  * Outputs: out_f32 [M,N] (nullable) and/or out_planes [2,M,N] (nullable) in the same plane format, ready to be the
  * A operand of the next GEMM. bias/residual/row_scale/col_scale nullable; residual may alias out_f32.
  * Requirements: K % 64 == 0, N % 8 == 0, all buffers 16-byte aligned. */
 int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, int plane_fmt, int64_t M, int64_t N, int64_t K,
-                   const float* bias, const float* residual, const float* row_scale, const float* col_scale,
-                   int epilogue, int passes, float* out_f32, uint16_t* out_planes, void* stream);
+                   float alpha /* 1 / (scale of A planes * scale of W planes) */, const float* bias, const float* residual,
+                   const float* row_scale, const float* col_scale, int epilogue, int passes, float* out_f32,
+                   uint16_t* out_planes /* written at SLB_ACT_PLANE_SCALE */, void* stream);
 
 /* K3. out[b,c,y,x] = (u8[b,c,y,x]/255 - mean[c]) / std[c]  — `ToTensor` + `Normalize` of the open_clip eval transform
  * (clip.py:157-160) for already-sized planar u8 images, in torch's op order (two IEEE divisions).
@@ -215,7 +221,8 @@ int slb_attention_small(const float* q, int64_t q_batch_stride, int64_t q_row_st
                         int64_t kv_batch_stride, int64_t kv_row_stride, int64_t B, int64_t Tq, int64_t Tk, int64_t H,
                         int64_t dh, float scale, int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream);
 
-/* The same attention for head_dim 64 reading q, k, v from the fp16 split planes [2][B*T][3*H*64] that the in_proj GEMM emits
+/* The same attention for head_dim 64 reading q, k, v from the fp16 split planes [2][B*T][3*H*64] (at SLB_ACT_PLANE_SCALE)
+ * that the in_proj GEMM emits
  * (packed nn.MultiheadAttention layout: q | k | v along the last axis): no fp32 round trip, no conversion in the
  * kernel (cp.async + ldmatrix + mma.sync). out as in slb_attention_small. */
 int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, int64_t dh, float scale,

@@ -113,8 +113,8 @@ def bench_gemm(batch):
     for name, (M, Nn, K) in cases.items():
         if only and only not in name:
             continue
-        a = ops.split_planes(torch.randn(M, K, device="cuda"))
-        w = ops.split_planes(torch.randn(Nn, K, device="cuda") * 0.02)
+        a = ops.split_planes(torch.randn(M, K, device="cuda"), scale=16.0)
+        w = ops.split_planes(torch.randn(Nn, K, device="cuda") * 0.02, scale=1024.0)
         out = torch.empty(M, Nn, device="cuda")
         for passes in (3, 1):
             med, best = time_cuda(lambda: ops.gemm_split(a, w, passes=passes, out_f32=out))

@@ -22,6 +22,7 @@ AGG_MEAN, AGG_MAX, AGG_ABSMEAN, AGG_ABSMAX, AGG_TOKEN = 0, 1, 2, 3, 4
 EPI_NONE, EPI_GELU_ERF, EPI_QUICKGELU, EPI_GELU_TANH = 0, 1, 2, 3
 POOL_CLS, POOL_MAP = 0, 1
 PLANE_F16, PLANE_BF16 = 0, 1
+ACT_PLANE_SCALE, WEIGHT_PLANE_SCALE = 16.0, 1024.0  # SLB_ACT_PLANE_SCALE / SLB_WEIGHT_PLANE_SCALE
 
 _DTYPES = {torch.float32: DT_F32, torch.float16: DT_F16, torch.bfloat16: DT_BF16}
 
@@ -50,7 +51,7 @@ _PROTOS = {
     ),
     "slb_topk_merge_lists": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "slb_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
-    "slb_normalize_split_rows": (c_int, [c_void_p, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "slb_normalize_split_rows": (c_int, [c_void_p, c_int64, c_int64, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "slb_cosine_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "slb_cosine_gemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "slb_cosine_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p]),
@@ -61,10 +62,10 @@ _PROTOS = {
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
     "slb_rowmax_offdiag": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
-    "slb_split_planes": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "slb_split_planes": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
     "slb_gemm_split": (
         c_int,
-        [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+        [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
          c_void_p, c_void_p, c_void_p],
     ),
     "slb_u8_to_f32_norm": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -5,9 +5,9 @@
 // Sequences here are short (50 / 197 / 257 tokens) and heads are 64 wide, so one (image, head) is far below a tcgen05
 // tile; this kernel uses warp-level mma.sync m16n8k16 (fp16 x fp16 -> fp32) in the FlashAttention-2 arrangement: a warp
 // owns 16 query rows, the head's K and V live in shared memory for the whole CTA, scores never leave registers.
-// fp32-grade: every operand is split x = hi + lo/2^11 (two fp16, 22 significant bits) and each product is three MMAs
-// (hi·hi into the main accumulator; hi·lo and lo·hi into a correction accumulator that is added back /2^11), for both
-// S = Q Kᵀ and O = P V; the softmax itself (max, exp, sum) is fp32.
+// fp32-grade: every operand is split x·s = hi + lo (two fp16, 22 significant bits, s = SLB_ACT_PLANE_SCALE shared by q, k
+// and v) and each product is three MMAs hi·hi + hi·lo + lo·hi, for both S = Q Kᵀ and O = P V (P planes carry 2^10); the
+// cross terms accumulate apart from hi·hi and are added in fp32 at the end; the softmax itself (max, exp, sum) is fp32.
 //
 // Shared-memory layouts are chosen so that every B-fragment register is ONE conflict-free 32-bit load:
 //   K   [key][72]  fp16 (row = key, 64 dims + 8 pad)        -> b = K[key0 + lane/4][d0 + 2*(lane%4) .. +1]
@@ -50,10 +50,15 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
 }
 
 // the same for values known to lie in [0, 1] (softmax numerators): no saturation needed
+// Probabilities p in [0, 1] as split planes with the scale kPScale (hi + lo = p * 2^10; lo stays a normal fp16 down to
+// p ~ 2^-14 and is exact to 2^-34 below that), the same format as the GEMM operands.
+constexpr float kPScale = 1024.0f;
 __device__ __forceinline__ void split_pair_unit(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    x0 *= kPScale;
+    x1 *= kPScale;
     const __half2 h = __floats2half2_rn(x0, x1);
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -245,8 +250,8 @@ __global__ void __launch_bounds__(NW * 32) attention_mma_kernel(AttnMmaParams p)
             if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + base + dt * 8) = make_float2(o0, o1);
             if (p.out_hi) {
                 uint16_t h0, l0, h1, l1;
-                slb_split2(o0, p.fmt, h0, l0);
-                slb_split2(o1, p.fmt, h1, l1);
+                slb_split2_act(o0, p.fmt, h0, l0);
+                slb_split2_act(o1, p.fmt, h1, l1);
                 *reinterpret_cast<uint32_t*>(p.out_hi + base + dt * 8) = (uint32_t)h0 | ((uint32_t)h1 << 16);
                 *reinterpret_cast<uint32_t*>(p.out_lo + base + dt * 8) = (uint32_t)l0 | ((uint32_t)l1 << 16);
             }
@@ -347,9 +352,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
         for (int j = 0; j < 4; ++j) { om[dt][j] = 0.f; oc[dt][j] = 0.f; }
     float m_run[2] = {-INFINITY, -INFINITY};
     float l_run[2] = {0.f, 0.f};
-    constexpr float kInvS = 1.0f / 2048.0f;
-    // logits are kept in the log2 domain (scale * log2 e folded in) so that the exponentials are single ex2 instructions
-    const float sc_main = p.scale * 1.4426950408889634f, sc_corr = sc_main * kInvS;
+    // q, k, v planes carry SLB_ACT_PLANE_SCALE with unscaled lo planes: the three products of Q K^T share one accumulator.
+    // Logits are kept in the log2 domain (scale * log2 e folded in) so that the exponentials are single ex2 instructions.
+    constexpr float kInvAct = 1.0f / SLB_ACT_PLANE_SCALE;
+    const float sc_main = p.scale * 1.4426950408889634f * kInvAct * kInvAct;
     // ldmatrix row addresses: lane -> (matrix j = lane / 8, row r = lane % 8)
     const int lm_j = lane >> 3, lm_r = lane & 7;
 
@@ -372,7 +378,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
         float s[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            float sm_[4] = {0.f, 0.f, 0.f, 0.f}, sc_[4] = {0.f, 0.f, 0.f, 0.f};
+            float sm_[4] = {0.f, 0.f, 0.f, 0.f};
             if (nt < nkt) {
                 // matrices: (keys nt*8.., d = ks2*32 + j*8 ..): j = 0,1 -> k-step 2*ks2 (b0, b1); j = 2,3 -> k-step 2*ks2 + 1
                 const size_t roff = (size_t)(nt * 8 + lm_r) * kKPad + lm_j * 8;
@@ -382,15 +388,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
                     ldmatrix_x4(bh, Kh + roff + ks2 * 32);
                     ldmatrix_x4(bl, Kl + roff + ks2 * 32);
                     mma16816(sm_, qh[2 * ks2], bh[0], bh[1]);
-                    mma16816(sc_, qh[2 * ks2], bl[0], bl[1]);
-                    mma16816(sc_, ql[2 * ks2], bh[0], bh[1]);
+                    mma16816(sm_, qh[2 * ks2], bl[0], bl[1]);
+                    mma16816(sm_, ql[2 * ks2], bh[0], bh[1]);
                     mma16816(sm_, qh[2 * ks2 + 1], bh[2], bh[3]);
-                    mma16816(sc_, qh[2 * ks2 + 1], bl[2], bl[3]);
-                    mma16816(sc_, ql[2 * ks2 + 1], bh[2], bh[3]);
+                    mma16816(sm_, qh[2 * ks2 + 1], bl[2], bl[3]);
+                    mma16816(sm_, ql[2 * ks2 + 1], bh[2], bh[3]);
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) s[nt][j] = fmaf(sc_[j], sc_corr, sm_[j] * sc_main);
+            for (int j = 0; j < 4; ++j) s[nt][j] = sm_[j] * sc_main;
             if (need_mask) {  // block-uniform: only the last key block (padding) and causal blocks on / above the diagonal
                 const int col = kb0 + nt * 8 + t4 * 2;
 #pragma unroll
@@ -454,8 +460,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
                     ldmatrix_x4_trans(bh, Vh + roff + dt2 * 16);
                     ldmatrix_x4_trans(bl, Vl + roff + dt2 * 16);
                     mma16816(om[2 * dt2], ph, bh[0], bh[1]);
-                    mma16816(oc[2 * dt2], ph, bl[0], bl[1]);
-                    mma16816(oc[2 * dt2], pl, bh[0], bh[1]);
+                    mma16816(oc[2 * dt2], ph, bl[0], bl[1]);      // the two cross terms (same scale as hi . hi) are kept
+                    mma16816(oc[2 * dt2], pl, bh[0], bh[1]);      // apart and added in fp32 at the end
                     mma16816(om[2 * dt2 + 1], ph, bh[2], bh[3]);
                     mma16816(oc[2 * dt2 + 1], ph, bl[2], bl[3]);
                     mma16816(oc[2 * dt2 + 1], pl, bh[2], bh[3]);
@@ -476,17 +482,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
     for (int r = 0; r < 2; ++r) {
         const int row = r0 + g + r * 8;
         if (row >= p.T) continue;
-        const float inv = 1.0f / l_run[r];
+        const float inv = kInvAct / (kPScale * l_run[r]);  // V planes carry the activation scale, P planes kPScale
         const int64_t base = (row0 + row) * p.W + (int64_t)h * kDh + t4 * 2;
 #pragma unroll
         for (int dt = 0; dt < 8; ++dt) {
-            const float o0 = fmaf(oc[dt][2 * r], kInvS, om[dt][2 * r]) * inv;
-            const float o1 = fmaf(oc[dt][2 * r + 1], kInvS, om[dt][2 * r + 1]) * inv;
+            const float o0 = (om[dt][2 * r] + oc[dt][2 * r]) * inv;
+            const float o1 = (om[dt][2 * r + 1] + oc[dt][2 * r + 1]) * inv;
             if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + base + dt * 8) = make_float2(o0, o1);
             if (p.out_hi) {
                 uint16_t h0, l0, h1, l1;
-                slb_split2(o0, p.fmt, h0, l0);
-                slb_split2(o1, p.fmt, h1, l1);
+                slb_split2_act(o0, p.fmt, h0, l0);
+                slb_split2_act(o1, p.fmt, h1, l1);
                 *reinterpret_cast<uint32_t*>(p.out_hi + base + dt * 8) = (uint32_t)h0 | ((uint32_t)h1 << 16);
                 *reinterpret_cast<uint32_t*>(p.out_lo + base + dt * 8) = (uint32_t)l0 | ((uint32_t)l1 << 16);
             }
@@ -583,8 +589,8 @@ extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64
 // avoid rescaling the output accumulator: sweep 1 computes S = Q K^T block by block for the row maxima only, sweep 2
 // recomputes S, writes P = exp2(S - max) as split planes into shared memory (K-major, swizzled by hand) and accumulates
 // O += P V with V consumed straight from its row-major tile as an MN-major operand (no transpose anywhere).
-// Accumulators (TMEM): S main | S corr (2 x 64 columns), O main | O corr (2 x 64 columns); every product is the
-// usual three plane products. Rows of the tile beyond T and keys beyond T are masked / never stored.
+// Accumulators (TMEM): S main | S corr (2 x 64 columns), O main | O corr (2 x 64 columns); every product is the usual three
+// plane products, hi.hi into main and the two cross terms into corr (q, k, v planes share one scale, P planes carry 2^10). Rows of the tile beyond T and keys beyond T are masked / never stored.
 // =================================================================================================
 namespace {
 
@@ -703,7 +709,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                 tc_wait(kv_full, (uint32_t)(it & 1), p.dbg, 3);
                 tc_wait(s_free, (it & 1) ^ 1u, p.dbg, 4);  // the softmax warps have read the previous S
                 slb_tc_fence_after();
-                // S = Q K^T: hi.hi -> main, hi.lo + lo.hi -> corr
+                // S = Q K^T: hi.hi -> S main; hi.lo + lo.hi -> S corr (same scale; summed in fp32 by the softmax warps, so
+                // the small terms are not truncated against the large accumulator: the logits feed an exponential)
                 const uint32_t idesc_s = slb_umma_idesc_f16(0, kTcTile, nk);
 #pragma unroll
                 for (int pr = 0; pr < 3; ++pr) {
@@ -712,7 +719,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         slb_umma_f16(t_s + (pr ? 64 : 0), slb_umma_desc_sw128(ab + k * 32), slb_umma_desc_sw128(bb + k * 32),
-                                     idesc_s, pr == 0 ? k != 0 : ((pr - 1) | k) != 0);
+                                     idesc_s, pr == 2 ? true : k != 0);
                 }
                 slb_umma_commit(s_full);
                 if (!sweep2) {
@@ -729,7 +736,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                     const uint32_t ab = pa + (pr == 2 ? kTcPlaneQ : 0);   // P hi / lo
                     const uint32_t bb = va + (pr == 1 ? kTcPlaneK : 0);   // V hi / lo
                     for (int k = 0; k < ksteps; ++k) {
-                        const bool acc = pr == 0 ? (blk | k) != 0 : (blk | (pr - 1) | k) != 0;
+                        // P hi . V hi -> main; the cross terms P hi . V lo + P lo . V hi -> corr (same scale, added in fp32)
+                        const bool acc = pr == 2 ? true : (blk | k) != 0;
                         slb_umma_f16(t_o + (pr ? 64 : 0), slb_umma_desc_sw128(ab + k * 32), umma_desc_mn_sw128(bb + k * 2048),
                                      idesc_o, acc);
                     }
@@ -746,8 +754,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         const int r = quarter * 32 + lane;           // row of the tile = TMEM lane
         const int row = q0 + r;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        constexpr float kInvS = 1.0f / 2048.0f;
-        const float c_main = p.scale_log2, c_corr = p.scale_log2 * kInvS;
+        constexpr float kInvAct = 1.0f / SLB_ACT_PLANE_SCALE;
+        const float c_main = p.scale_log2 * kInvAct * kInvAct;
         float m_row = -INFINITY, l_row = 0.f;
         unsigned char* p_hi = smem + kTcP;
         unsigned char* p_lo = p_hi + kTcPlaneQ;
@@ -769,16 +777,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             slb_tc_fence_after();
             if (sweep2) tc_wait(p_free, (uint32_t)((it - nblk) & 1) ^ 1u, p.dbg, 7);  // previous P consumed by its MMAs
             for (int c = half * 32; c < min(nk, half * 32 + 32); c += 32) {
-                uint32_t a[32], cr[32];
+                uint32_t a[32], sc[32];
                 slb_tmem_ld_32x32(t_s + lane_addr + c, a);
-                slb_tmem_ld_32x32(t_s + lane_addr + 64 + c, cr);
+                slb_tmem_ld_32x32(t_s + lane_addr + 64 + c, sc);
                 slb_tmem_ld_wait();
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float sv = fmaf(__uint_as_float(cr[j]), c_corr, __uint_as_float(a[j]) * c_main);
-                    v[j] = (blk * kTcKeys + c + j < p.T) ? sv : -INFINITY;
-                }
+                for (int j = 0; j < 32; ++j)
+                    v[j] = (blk * kTcKeys + c + j < p.T) ? (__uint_as_float(a[j]) + __uint_as_float(sc[j])) * c_main : -INFINITY;
                 if (!sweep2) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) m_row = fmaxf(m_row, v[j]);
@@ -809,7 +815,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                 slb_mbar_arrive(s_free);
             }
         }
-        // ---- row sums of the two column halves, then O = (main + corr / 2^11) / l; each warp stores 32 of the 64 dims ----
+        // ---- row sums of the two column halves, then O = (main + corr) / (scales * l); each warp stores 32 of the 64 dims ----
         if (half) xch[128 + r] = l_row;
         asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
         if (!half) xch[128 + r] += l_row;
@@ -817,7 +823,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         l_row = xch[128 + r];
         tc_wait(o_full, 0, p.dbg, 0);
         slb_tc_fence_after();
-        const float inv = 1.0f / l_row;
+        const float inv = kInvAct / (kPScale * l_row);  // V planes carry the activation scale, P planes kPScale
         const bool ok = row < p.T;
         const int64_t base = ((int64_t)row_base + row) * p.W + (int64_t)h * 64;
         {
@@ -829,7 +835,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             if (ok) {
                 float o[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = fmaf(__uint_as_float(cr[j]), kInvS, __uint_as_float(a[j])) * inv;
+                for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(a[j]) + __uint_as_float(cr[j])) * inv;
                 if (p.out_f32) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -842,8 +848,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             uint16_t h0, l0, h1, l1;
-                            slb_split2(o[8 * j + 2 * e], p.fmt, h0, l0);
-                            slb_split2(o[8 * j + 2 * e + 1], p.fmt, h1, l1);
+                            slb_split2_act(o[8 * j + 2 * e], p.fmt, h0, l0);
+                            slb_split2_act(o[8 * j + 2 * e + 1], p.fmt, h1, l1);
                             hh[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
                             ll[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
                         }

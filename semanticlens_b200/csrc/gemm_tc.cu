@@ -4,18 +4,18 @@
 // nn.MultiheadAttention in_proj/out_proj, MLP c_fc/c_proj, conv1 patch embed, visual proj) and the cosine matmul of
 // scores.similarity_score (scores.py:120-125).
 //
-// Operands are "split planes": x ~= hi + lo/S, both 16-bit (fp16: 22 significant bits, bf16: 16), lo stored
-// pre-scaled by S so it stays clear of the fp16 subnormals. One output tile keeps TWO fp32 accumulators in tensor
-// memory: main = Ahi·Whi and corr = Ahi·Wlo + Alo·Whi; the epilogue forms main + corr/S (the lo·lo term is below
-// fp32 resolution for fp16 planes). The tensor cores thus deliver fp32-grade results at 1/3 of their 16-bit rate.
+// Operands are "split planes": s·x ~= hi + lo, both 16-bit (fp16: 22 significant bits, bf16: 16) at one per-tensor
+// power-of-two scale s (slb200.h), so the three plane products Ahi·Whi + Ahi·Wlo + Alo·Whi accumulate in ONE fp32
+// accumulator in tensor memory (the lo·lo term is below fp32 resolution for fp16 planes) and the epilogue multiplies by
+// alpha = 1 / (s_A · s_W). The tensor cores thus deliver fp32-grade results at 1/3 of their 16-bit rate.
 //
 // Structure (one CTA per SM, persistent over output tiles, 320 threads):
 //   warp 0      TMA producer: per k-block ONE 3-D box per operand {64 cols, rows, 2 planes} -> 128B-swizzled smem stage
-//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16, 12 per k-block; tcgen05.commit frees stages
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16, 12 per k-block (3 plane products x 4
+//               k-steps, one accumulator); tcgen05.commit frees stages
 //   warps 2..9  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> scale/bias/activation/residual -> global
 //               (two warps per TMEM lane quarter: the GELU / split-plane epilogues are ALU-heavy)
-// Accumulators are double buffered in TMEM (2 x 2 x BN = 512 columns): the epilogue of tile i overlaps the MMAs of
-// tile i+1.
+// Accumulators are double buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "tc_common.cuh"
 
 #include <stdlib.h>
@@ -31,18 +31,19 @@ constexpr int kThreads = (2 + kEpiWarps) * 32;
 
 template <int BN>
 struct Cfg {
-    static_assert(BN == 128, "two double-buffered accumulator pairs fill the 512 TMEM columns at BN = 128");
+    static_assert(BN == 128, "one-CTA tiles are 128 x 128");
     static constexpr int kAccBufs = 2;
     static constexpr int kStages = 3;
     static constexpr int kABytes = 2 * BM * BK * 2;  // both planes
     static constexpr int kWBytes = 2 * BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kWBytes;
-    static constexpr int kTmemCols = 512;  // [buffer][main | corr][BN]
+    static constexpr int kTmemCols = 2 * BN;  // [buffer][BN]
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
     int64_t M, N, K;
+    float alpha;             // 1 / (scale of the A planes * scale of the W planes)
     const float* bias;       // [N] or null
     const float* residual;   // [M,N] or null (may alias out_f32)
     const float* row_scale;  // [M] or null
@@ -70,23 +71,16 @@ __device__ __forceinline__ float act_apply(float v, int epi) {
     }
 }
 
-// Epilogue of one 32-column chunk of an accumulator row: TMEM -> registers -> scale / bias / activation / residual ->
-// global (fp32 and/or split planes). `taddr` addresses the main accumulator; the correction accumulator sits
-// `corr_off` columns further. Thread = one output row m, columns [nb, nb + 32).
-__device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr, int corr_off, int64_t m, bool row_ok,
-                                            float rs, int64_t nb, int fmt, float inv_s) {
+// Epilogue of one 32-column chunk of an accumulator row: TMEM -> registers -> alpha / scale / bias / activation /
+// residual -> global (fp32 and/or split planes at the activation scale). Thread = one output row m, columns [nb, nb + 32).
+__device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr, int64_t m, bool row_ok, float rs, int64_t nb,
+                                            int fmt) {
     uint32_t raw[32];
     float v[32];
     slb_tmem_ld_32x32(taddr, raw);
     slb_tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-    if (p.passes == 3) {
-        slb_tmem_ld_32x32(taddr + corr_off, raw);
-        slb_tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(raw[j]), inv_s, v[j]);
-    }
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
     if (!(row_ok && nb < p.N)) return;
     const int ncols = (int)min((int64_t)32, p.N - nb);  // multiple of 8
     if (p.row_scale) {
@@ -133,8 +127,8 @@ __device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr,
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint16_t h0, l0, h1, l1;
-                    slb_split2(v[8 * j + 2 * q], fmt, h0, l0);
-                    slb_split2(v[8 * j + 2 * q + 1], fmt, h1, l1);
+                    slb_split2_act(v[8 * j + 2 * q], fmt, h0, l0);
+                    slb_split2_act(v[8 * j + 2 * q + 1], fmt, h1, l1);
                     h[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
                     l[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
                 }
@@ -210,7 +204,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 slb_mbar_wait(&tempty[acc], acc_phase ^ 1u);
                 slb_tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     slb_mbar_wait(&full[stage], phase);
                     slb_tc_fence_after();
@@ -224,10 +218,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             const uint32_t wb = w0 + (pr == 1 ? BN * BK * 2 : 0);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k) {
-                                // pr 0 -> main accumulator; pr 1, 2 -> corr accumulator (first write: kb 0, pr 1, k 0)
-                                slb_umma_f16(d_tmem + (pr ? BN : 0), slb_umma_desc_sw128(ab + k * 32),
-                                             slb_umma_desc_sw128(wb + k * 32), idesc,
-                                             pr == 0 ? (kb | k) != 0 : (kb | (pr - 1) | k) != 0);
+                                slb_umma_f16(d_tmem, slb_umma_desc_sw128(ab + k * 32), slb_umma_desc_sw128(wb + k * 32), idesc,
+                                             (kb | pr | k) != 0);
                             }
                         }
                     }
@@ -245,7 +237,6 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int acc = 0;
         uint32_t acc_phase = 0;
         const int fmt = p.fmt;
-        const float inv_s = 1.0f / slb_plane_lo_scale(fmt);
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
             slb_mbar_wait(&tfull[acc], acc_phase);
@@ -255,8 +246,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const float rs = (p.row_scale && row_ok) ? p.row_scale[m] : 1.0f;
 #pragma unroll 1
             for (int c = chunk0; c < BN / 32; c += kEpiWarps / 4) {
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
-                drain_chunk(p, taddr, BN, m, row_ok, rs, (int64_t)n0 + c * 32, fmt, inv_s);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+                drain_chunk(p, taddr, m, row_ok, rs, (int64_t)n0 + c * 32, fmt);
             }
             slb_tc_fence_before();
             __syncwarp();
@@ -278,7 +269,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //
 // Each CTA stages ITS half of both operands per k-block — A rows [m0 + 128 r, +128), W rows [n0 + 64 r, +64), both
 // planes: 48 KB instead of the 64 KB a lone CTA needs for a 128 x 128 tile — so the L2 -> shared-memory feed per MMA
-// cycle drops by 25 % and the ring deepens from 3 to 4 stages; the leader CTA's single MMA thread issues
+// cycle drops and the ring deepens; the leader CTA's single MMA thread issues
 // tcgen05.mma.cta_group::2 (M = 256, N = 128, K = 16), which reads A and W from both CTAs' shared memory and writes
 // each CTA's 128 accumulator rows into that CTA's own tensor memory. Barriers:
 //   full[s]    leader only; the leader arms it with the pair's byte count, both CTAs' TMA loads complete on it
@@ -286,20 +277,19 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //   tfull[a]   in each CTA; commit multicast after the tile's last k-block
 //   tempty[a]  leader only, 16 arrivals: the 8 epilogue warps of each CTA (the peer's arrive remotely)
 // ---------------------------------------------------------------------------------------------
-// PBN = 128: 256 x 128 pair tile, accumulators double-buffered (2 x 2 x 128 TMEM columns), 4 stages of 48 KB.
-// PBN = 256: 256 x 256 pair tile — per MMA cycle each CTA reads half as much shared memory (its 128 A rows and HALF of W
-//            serve a 256-wide MMA; one-CTA 128 x 128 tiles read 128 B/clk, the shared-memory limit) and half as much L2;
-//            main + corr fill all 512 TMEM columns, so the epilogue of a tile is NOT overlapped with the next main loop:
-//            worth it when K is long.
+// PBN = 128: 256 x 128 pair tile, 4 stages of 48 KB. PBN = 256: 256 x 256 pair tile, 3 stages of 64 KB — per MMA cycle
+// each CTA reads half as much shared memory (its 128 A rows and HALF of W serve a 256-wide MMA; one-CTA 128 x 128 tiles
+// read 128 B/clk, the shared-memory limit) and half as much L2. Accumulators are double-buffered in both (2 x PBN TMEM
+// columns: the single accumulator per tile is what lets the 256-wide tile fit twice).
 template <int PBN>
 struct CfgPair {
     static constexpr int BN = PBN;
-    static constexpr int kAccBufs = PBN == 128 ? 2 : 1;
+    static constexpr int kAccBufs = 2;
     static constexpr int kStages = PBN == 128 ? 4 : 3;
     static constexpr int kABytes = 2 * BM * BK * 2;        // this CTA's 128 A rows, both planes
     static constexpr int kWBytes = 2 * (BN / 2) * BK * 2;  // this CTA's half of the W rows, both planes
     static constexpr int kStageBytes = kABytes + kWBytes;  // 48 / 64 KB
-    static constexpr int kTmemCols = 512;                  // [buffer][main | corr][BN]
+    static constexpr int kTmemCols = 2 * PBN;              // [buffer][BN]
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 + 256;
 };
 
@@ -396,7 +386,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             for (int t = cluster_id; t < total; t += num_clusters) {
                 mbar_wait_bounded(&tempty[acc], acc_phase ^ 1u, p.dbg, 2, t, -1, acc);
                 slb_tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait_bounded(&full[stage], phase, p.dbg, 3, t, kb, stage);
                     slb_tc_fence_after();
@@ -409,9 +399,8 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             const uint32_t wb = w0 + (pr == 1 ? (BN / 2) * BK * 2 : 0);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k) {
-                                slb_umma_f16_pair(d_tmem + (pr ? BN : 0), slb_umma_desc_sw128(ab + k * 32),
-                                                  slb_umma_desc_sw128(wb + k * 32), idesc,
-                                                  pr == 0 ? (kb | k) != 0 : (kb | (pr - 1) | k) != 0);
+                                slb_umma_f16_pair(d_tmem, slb_umma_desc_sw128(ab + k * 32), slb_umma_desc_sw128(wb + k * 32),
+                                                  idesc, (kb | pr | k) != 0);
                             }
                         }
                     }
@@ -429,7 +418,6 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int acc = 0;
         uint32_t acc_phase = 0;
         const int fmt = p.fmt;
-        const float inv_s = 1.0f / slb_plane_lo_scale(fmt);
         for (int t = cluster_id; t < total; t += num_clusters) {
             const int m0 = (t / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (t % tiles_n) * BN;
             mbar_wait_bounded(&tfull[acc], acc_phase, p.dbg, 4, t, -1, acc);
@@ -439,8 +427,8 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const float rs = (p.row_scale && row_ok) ? p.row_scale[m] : 1.0f;
 #pragma unroll 1
             for (int c = chunk0; c < BN / 32; c += kEpiWarps / 4) {
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
-                drain_chunk(p, taddr, BN, m, row_ok, rs, (int64_t)n0 + c * 32, fmt, inv_s);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+                drain_chunk(p, taddr, m, row_ok, rs, (int64_t)n0 + c * 32, fmt);
             }
             slb_tc_fence_before();
             __syncwarp();
@@ -460,19 +448,19 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
 // x fp32 -> planes [2][n]
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, int64_t n4, int64_t n, int fmt,
-                                                           uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+                                                           float scale, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 v = reinterpret_cast<const float4*>(x)[i];
         uint16_t h[4], l[4];
-        slb_split2(v.x, fmt, h[0], l[0]);
-        slb_split2(v.y, fmt, h[1], l[1]);
-        slb_split2(v.z, fmt, h[2], l[2]);
-        slb_split2(v.w, fmt, h[3], l[3]);
+        slb_split2(v.x * scale, fmt, h[0], l[0]);
+        slb_split2(v.y * scale, fmt, h[1], l[1]);
+        slb_split2(v.z * scale, fmt, h[2], l[2]);
+        slb_split2(v.w * scale, fmt, h[3], l[3]);
         reinterpret_cast<uint2*>(hi)[i] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
         reinterpret_cast<uint2*>(lo)[i] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int64_t i = n4 * 4; i < n; ++i) slb_split2(x[i], fmt, hi[i], lo[i]);
+        for (int64_t i = n4 * 4; i < n; ++i) slb_split2(x[i] * scale, fmt, hi[i], lo[i]);
     }
 }
 
@@ -562,7 +550,8 @@ int slb_make_plane_map(CUtensorMap* out, const void* base, int64_t rows, int64_t
     return SLB_OK;
 }
 
-extern "C" int slb_split_planes(const float* x, int64_t n, int plane_fmt, uint16_t* planes, void* stream) {
+extern "C" int slb_split_planes(const float* x, int64_t n, int plane_fmt, float scale, uint16_t* planes, void* stream) {
+    SLB_REQUIRE(scale > 0.0f, SLB_EINVAL, "slb_split_planes: scale must be positive");
     SLB_REQUIRE(n >= 0, SLB_EINVAL, "slb_split_planes: negative size");
     if (n == 0) return SLB_OK;
     SLB_REQUIRE(x && planes, SLB_EINVAL, "slb_split_planes: null pointer");
@@ -572,13 +561,13 @@ extern "C" int slb_split_planes(const float* x, int64_t n, int plane_fmt, uint16
     const int64_t n4 = n / 4;
     SlbProfScope prof("split_planes", stream, 0.0, 8.0 * (double)n);
     const int grid = (int)std::min<int64_t>(slb_ceil_div(n4, 256), (int64_t)slb_sm_count() * 8);
-    split_planes_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n4, n, plane_fmt, planes, planes + n);
+    split_planes_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n4, n, plane_fmt, scale, planes, planes + n);
     SLB_LAUNCH_OK("split_planes");
     return SLB_OK;
 }
 
 extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, int plane_fmt, int64_t M, int64_t N,
-                              int64_t K, const float* bias, const float* residual, const float* row_scale,
+                              int64_t K, float alpha, const float* bias, const float* residual, const float* row_scale,
                               const float* col_scale, int epilogue, int passes, float* out_f32, uint16_t* out_planes,
                               void* stream) {
     SLB_REQUIRE(M >= 0 && N >= 0 && K >= 0, SLB_EINVAL, "slb_gemm_split: negative size");
@@ -601,6 +590,7 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
                       4.0 * ((double)M * (double)K + (double)N * (double)K) + ((out_f32 ? 4.0 : 0.0) + (out_planes ? 4.0 : 0.0)) * (double)M * (double)N);
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
+    p.alpha = alpha;
     p.bias = bias; p.residual = residual; p.row_scale = row_scale; p.col_scale = col_scale;
     p.out_f32 = out_f32; p.out_planes = out_planes;
     p.epilogue = epilogue; p.passes = passes; p.fmt = plane_fmt;
@@ -621,7 +611,7 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
         const double waves256 = (double)t256 / (double)pairs;
         const double eff256 = waves256 / (double)slb_ceil_div(t256, pairs);  // last-wave utilisation
         if (N >= 4096) kind = 2;
-        if (K >= 2048 && N >= 256 && eff256 >= 0.85) kind = 3;  // K = 1024: the exposed epilogue still costs more than it saves
+        if (K >= 512 && N >= 256 && eff256 >= 0.85) kind = 3;
     }
     if (forced) kind = (M > BM || forced == 1) ? forced : 1;
     CUtensorMap tmA, tmW;

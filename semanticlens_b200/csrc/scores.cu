@@ -26,7 +26,7 @@ __device__ __forceinline__ float inv_norm(float ss, float eps) { return 1.0f / f
 // ------------------------------------------------------------------------------------------------
 template <int NCH>  // row chunks of 128 floats kept in registers (D <= 128 * NCH)
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-normalize_split_kernel(const float* __restrict__ x, int64_t rows, int D, int Kpad, float eps, int fmt,
+normalize_split_kernel(const float* __restrict__ x, int64_t rows, int D, int Kpad, float eps, int fmt, float plane_scale,
                        uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, float* __restrict__ inv_out) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
@@ -44,6 +44,7 @@ normalize_split_kernel(const float* __restrict__ x, int64_t rows, int D, int Kpa
     const float inv = inv_norm(slb_warp_sum_butterfly(ss), eps);
     if (inv_out && lane == 0) inv_out[r] = inv;
     if (!hi) return;
+    const float sc = inv * plane_scale;
     const int k4 = Kpad >> 2;
     uint2* h2 = reinterpret_cast<uint2*>(hi + r * (int64_t)Kpad);
     uint2* l2 = reinterpret_cast<uint2*>(lo + r * (int64_t)Kpad);
@@ -52,10 +53,10 @@ normalize_split_kernel(const float* __restrict__ x, int64_t rows, int D, int Kpa
         const int i = c * 32 + lane;
         if (i < k4) {
             uint16_t h[4], l[4];
-            slb_split2(v[c].x * inv, fmt, h[0], l[0]);
-            slb_split2(v[c].y * inv, fmt, h[1], l[1]);
-            slb_split2(v[c].z * inv, fmt, h[2], l[2]);
-            slb_split2(v[c].w * inv, fmt, h[3], l[3]);
+            slb_split2(v[c].x * sc, fmt, h[0], l[0]);
+            slb_split2(v[c].y * sc, fmt, h[1], l[1]);
+            slb_split2(v[c].z * sc, fmt, h[2], l[2]);
+            slb_split2(v[c].w * sc, fmt, h[3], l[3]);
             h2[i] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
             l2[i] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
         }
@@ -176,10 +177,10 @@ rowmax_offdiag_kernel(const float* __restrict__ S, int64_t rows, int64_t cols, i
 }
 
 template <int NCH>
-int launch_normalize(const float* x, int64_t rows, int D, int Kpad, float eps, int fmt, uint16_t* planes, float* inv,
-                     cudaStream_t st) {
+int launch_normalize(const float* x, int64_t rows, int D, int Kpad, float eps, int fmt, float plane_scale, uint16_t* planes,
+                     float* inv, cudaStream_t st) {
     const unsigned grid = (unsigned)slb_ceil_div(rows, kWarpsPerCta);
-    normalize_split_kernel<NCH><<<grid, kWarpsPerCta * 32, 0, st>>>(x, rows, D, Kpad, eps, fmt, planes,
+    normalize_split_kernel<NCH><<<grid, kWarpsPerCta * 32, 0, st>>>(x, rows, D, Kpad, eps, fmt, plane_scale, planes,
                                                                    planes ? planes + rows * (int64_t)Kpad : nullptr, inv);
     SLB_LAUNCH_OK("normalize_split");
     return SLB_OK;
@@ -200,8 +201,9 @@ int64_t pad64(int64_t d) { return (d + 63) / 64 * 64; }
 
 }  // namespace
 
-extern "C" int slb_normalize_split_rows(const float* x, int64_t rows, int64_t D, float eps, int plane_fmt,
+extern "C" int slb_normalize_split_rows(const float* x, int64_t rows, int64_t D, float eps, int plane_fmt, float plane_scale,
                                         uint16_t* planes, float* inv_norms, void* stream) {
+    SLB_REQUIRE(plane_scale > 0.0f, SLB_EINVAL, "slb_normalize_split_rows: plane_scale must be positive");
     SLB_REQUIRE(rows >= 0 && D > 0, SLB_EINVAL, "slb_normalize_split_rows: bad size");
     if (rows == 0) return SLB_OK;
     SLB_REQUIRE(x && (planes || inv_norms), SLB_EINVAL, "slb_normalize_split_rows: null pointer");
@@ -212,10 +214,10 @@ extern "C" int slb_normalize_split_rows(const float* x, int64_t rows, int64_t D,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SlbProfScope prof("K6 normalize_split_rows", stream, 0.0, (double)rows * (4.0 * (double)D + (planes ? 4.0 * Kpad : 0.0)));
     const int nch = (int)slb_ceil_div(Kpad, 128);
-    if (nch <= 2) return launch_normalize<2>(x, rows, (int)D, Kpad, eps, plane_fmt, planes, inv_norms, st);
-    if (nch <= 4) return launch_normalize<4>(x, rows, (int)D, Kpad, eps, plane_fmt, planes, inv_norms, st);
-    if (nch <= 8) return launch_normalize<8>(x, rows, (int)D, Kpad, eps, plane_fmt, planes, inv_norms, st);
-    return launch_normalize<16>(x, rows, (int)D, Kpad, eps, plane_fmt, planes, inv_norms, st);
+    if (nch <= 2) return launch_normalize<2>(x, rows, (int)D, Kpad, eps, plane_fmt, plane_scale, planes, inv_norms, st);
+    if (nch <= 4) return launch_normalize<4>(x, rows, (int)D, Kpad, eps, plane_fmt, plane_scale, planes, inv_norms, st);
+    if (nch <= 8) return launch_normalize<8>(x, rows, (int)D, Kpad, eps, plane_fmt, plane_scale, planes, inv_norms, st);
+    return launch_normalize<16>(x, rows, (int)D, Kpad, eps, plane_fmt, plane_scale, planes, inv_norms, st);
 }
 
 extern "C" size_t slb_cosine_gemm_workspace_bytes(int64_t M, int64_t N, int64_t D) {
@@ -241,12 +243,14 @@ extern "C" int slb_cosine_gemm(const float* x, int64_t M, const float* y, int64_
     uint16_t* py = reinterpret_cast<uint16_t*>(static_cast<unsigned char*>(workspace) +
                                                (((size_t)2 * M * Kpad * 2 + 255) & ~(size_t)255));
     // F.normalize default eps = 1e-12 (scores.py:120-121)
-    int rc = slb_normalize_split_rows(x, M, D, 1e-12f, SLB_PLANE_F16, px, nullptr, stream);
+    // unit rows: elements ~ 1/sqrt(D), scaled by 2^10 into the fp16 normal range on both sides
+    const float sc = 1024.0f;
+    int rc = slb_normalize_split_rows(x, M, D, 1e-12f, SLB_PLANE_F16, sc, px, nullptr, stream);
     if (rc != SLB_OK) return rc;
-    rc = slb_normalize_split_rows(y, N, D, 1e-12f, SLB_PLANE_F16, py, nullptr, stream);
+    rc = slb_normalize_split_rows(y, N, D, 1e-12f, SLB_PLANE_F16, sc, py, nullptr, stream);
     if (rc != SLB_OK) return rc;
-    return slb_gemm_split(px, py, SLB_PLANE_F16, M, N, Kpad, nullptr, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, out,
-                          nullptr, stream);
+    return slb_gemm_split(px, py, SLB_PLANE_F16, M, N, Kpad, 1.0f / (sc * sc), nullptr, nullptr, nullptr, nullptr,
+                          SLB_EPI_NONE, 3, out, nullptr, stream);
 }
 
 extern "C" int slb_cosine_rows(const float* x, const float* y, int64_t rows, int64_t D, float eps, float* out,

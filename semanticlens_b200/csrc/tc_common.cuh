@@ -186,13 +186,15 @@ __device__ __forceinline__ float slb_from_plane(uint16_t b, int fmt) {
     if (fmt == 0) return __half2float(__ushort_as_half(b));
     return __bfloat162float(__ushort_as_bfloat16(b));
 }
-// x ~= hi + lo / S with hi = rn16(x), lo = rn16((x - hi) * S), S = 2^11 (fp16) or 2^8 (bf16): the remainder is
-// stored pre-scaled so that it never falls into the fp16 subnormal range (weights ~1e-2 would otherwise lose
-// the low bits of lo). 22 (fp16) / 16 (bf16) significant bits in total. fp16 planes saturate at +-65504.
-__host__ __device__ __forceinline__ float slb_plane_lo_scale(int fmt) { return fmt == 0 ? 2048.0f : 256.0f; }
+// s * x ~= hi + lo with hi = rn16(s * x), lo = rn16(s * x - hi); the caller applies the tensor's power-of-two scale s
+// (see slb200.h). 22 (fp16) / 16 (bf16) significant bits in total. fp16 planes saturate at +-65504.
 __device__ __forceinline__ void slb_split2(float v, int fmt, uint16_t& hi, uint16_t& lo) {
     if (fmt == 0) v = fminf(fmaxf(v, -65504.0f), 65504.0f);
     hi = slb_to_plane(v, fmt);
-    lo = slb_to_plane((v - slb_from_plane(hi, fmt)) * slb_plane_lo_scale(fmt), fmt);
+    lo = slb_to_plane(v - slb_from_plane(hi, fmt), fmt);
+}
+// planes written by a kernel (activations) carry SLB_ACT_PLANE_SCALE
+__device__ __forceinline__ void slb_split2_act(float v, int fmt, uint16_t& hi, uint16_t& lo) {
+    slb_split2(v * SLB_ACT_PLANE_SCALE, fmt, hi, lo);
 }
 #endif  // __CUDACC__

@@ -12,6 +12,9 @@
 
 namespace {
 
+// every GEMM of the towers multiplies activation planes (SLB_ACT_PLANE_SCALE) with weight planes (SLB_WEIGHT_PLANE_SCALE)
+constexpr float kAlpha = 1.0f / (SLB_ACT_PLANE_SCALE * SLB_WEIGHT_PLANE_SCALE);
+
 struct WsLayout {
     size_t x, qkv, planes_a, planes_b, patch_f32, head_f32, total;
 };
@@ -56,21 +59,21 @@ int run_blocks(const SlbVitLayer* layer, int n_layers, float* x, float* qkv, uin
         if (fmt == SLB_PLANE_F16 && dh == 64) {
             // in_proj writes q | k | v as split planes (same bytes as fp32) and attention consumes them directly
             uint16_t* qkv_planes = reinterpret_cast<uint16_t*>(qkv);
-            SLB_TRY(slb_gemm_split(pa, ly.w_qkv, fmt, rows, 3 * W, W, ly.b_qkv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
+            SLB_TRY(slb_gemm_split(pa, ly.w_qkv, fmt, rows, 3 * W, W, kAlpha, ly.b_qkv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
                                    nullptr, qkv_planes, stream));
             SLB_TRY(slb_attention_planes(qkv_planes, B, T, heads, dh, 1.0f / sqrtf((float)dh), causal, fmt, nullptr, pb, stream));
         } else {
             SLB_REQUIRE(!causal, SLB_EUNSUPPORTED, "causal attention needs head_dim 64 and fp16 planes");
-            SLB_TRY(slb_gemm_split(pa, ly.w_qkv, fmt, rows, 3 * W, W, ly.b_qkv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
+            SLB_TRY(slb_gemm_split(pa, ly.w_qkv, fmt, rows, 3 * W, W, kAlpha, ly.b_qkv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
                                    qkv, nullptr, stream));
             SLB_TRY(slb_attention_small(qkv, T * 3 * W, 3 * W, qkv + W, qkv + 2 * W, T * 3 * W, 3 * W, B, T, T, heads, dh,
                                         1.0f / sqrtf((float)dh), fmt, nullptr, pb, stream));
         }
-        SLB_TRY(slb_gemm_split(pb, ly.w_out, fmt, rows, W, W, ly.b_out, x, nullptr, nullptr, SLB_EPI_NONE, 3, x, nullptr,
+        SLB_TRY(slb_gemm_split(pb, ly.w_out, fmt, rows, W, W, kAlpha, ly.b_out, x, nullptr, nullptr, SLB_EPI_NONE, 3, x, nullptr,
                                stream));
         SLB_TRY(slb_layernorm(x, rows, W, W, ly.ln2_g, ly.ln2_b, eps, fmt, nullptr, pa, stream));
-        SLB_TRY(slb_gemm_split(pa, ly.w_fc, fmt, rows, mlp, W, ly.b_fc, nullptr, nullptr, nullptr, act, 3, nullptr, pb, stream));
-        SLB_TRY(slb_gemm_split(pb, ly.w_proj, fmt, rows, W, mlp, ly.b_proj, x, nullptr, nullptr, SLB_EPI_NONE, 3, x, nullptr,
+        SLB_TRY(slb_gemm_split(pa, ly.w_fc, fmt, rows, mlp, W, kAlpha, ly.b_fc, nullptr, nullptr, nullptr, act, 3, nullptr, pb, stream));
+        SLB_TRY(slb_gemm_split(pb, ly.w_proj, fmt, rows, W, mlp, kAlpha, ly.b_proj, x, nullptr, nullptr, SLB_EPI_NONE, 3, x, nullptr,
                                stream));
     }
 #undef SLB_TRY
@@ -128,7 +131,7 @@ extern "C" int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t
 
     // patch embedding: im2col planes -> GEMM (+ conv bias if any) -> tokens
     SLB_TRY(slb_patchify(img, B, w->image_size, w->patch, fmt, pa, stream));
-    SLB_TRY(slb_gemm_split(pa, w->conv_w, fmt, B * g * g, W, Kc, w->conv_b, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
+    SLB_TRY(slb_gemm_split(pa, w->conv_w, fmt, B * g * g, W, Kc, kAlpha, w->conv_b, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
                            patch_f32, nullptr, stream));
     SLB_TRY(slb_assemble_tokens(patch_f32, w->cls, w->pos, B, T, W, w->has_cls ? 1 : 0, x, stream));
     if (w->ln_pre_g) SLB_TRY(slb_layernorm(x, rows, W, W, w->ln_pre_g, w->ln_pre_b, w->ln_eps, fmt, x, nullptr, stream));
@@ -139,30 +142,30 @@ extern "C" int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t
         // final LayerNorm over ALL tokens, then the attention-pool head (timm AttentionPoolLatent / HF Siglip "MAP" head)
         SLB_TRY(slb_layernorm(x, rows, W, W, w->ln_post_g, w->ln_post_b, w->ln_eps, fmt, nullptr, pa, stream));
         float* kv = qkv;  // [rows, 2W] fp32
-        SLB_TRY(slb_gemm_split(pa, w->map_w_kv, fmt, rows, 2 * W, W, w->map_b_kv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, kv,
+        SLB_TRY(slb_gemm_split(pa, w->map_w_kv, fmt, rows, 2 * W, W, kAlpha, w->map_b_kv, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, kv,
                                nullptr, stream));
         // one query (the projected latent, shared by every image: batch stride 0) over the T tokens of each image
         SLB_TRY(slb_attention_small(w->map_q, 0, W, kv, kv + W, T * 2 * W, 2 * W, B, 1, T, w->heads, dh,
                                     1.0f / sqrtf((float)dh), fmt, nullptr, pb, stream));
-        SLB_TRY(slb_gemm_split(pb, w->map_w_out, fmt, B, W, W, w->map_b_out, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
+        SLB_TRY(slb_gemm_split(pb, w->map_w_out, fmt, B, W, W, kAlpha, w->map_b_out, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
                                head_f32, nullptr, stream));
         SLB_TRY(slb_layernorm(head_f32, B, W, W, w->map_ln_g, w->map_ln_b, w->ln_eps, fmt, nullptr, pa, stream));
-        SLB_TRY(slb_gemm_split(pa, w->map_w_fc, fmt, B, w->mlp, W, w->map_b_fc, nullptr, nullptr, nullptr, w->act, 3, nullptr, pb,
+        SLB_TRY(slb_gemm_split(pa, w->map_w_fc, fmt, B, w->mlp, W, kAlpha, w->map_b_fc, nullptr, nullptr, nullptr, w->act, 3, nullptr, pb,
                                stream));
         if (w->proj) {
-            SLB_TRY(slb_gemm_split(pb, w->map_w_proj, fmt, B, W, w->mlp, w->map_b_proj, head_f32, nullptr, nullptr, SLB_EPI_NONE,
+            SLB_TRY(slb_gemm_split(pb, w->map_w_proj, fmt, B, W, w->mlp, kAlpha, w->map_b_proj, head_f32, nullptr, nullptr, SLB_EPI_NONE,
                                    3, nullptr, pa, stream));
-            SLB_TRY(slb_gemm_split(pa, w->proj, fmt, B, w->embed_dim, W, nullptr, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, out,
+            SLB_TRY(slb_gemm_split(pa, w->proj, fmt, B, w->embed_dim, W, kAlpha, nullptr, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, out,
                                    nullptr, stream));
         } else {
             SLB_REQUIRE(w->embed_dim == w->width, SLB_EINVAL, "slb_vit_forward: embed_dim must equal width without a projection");
-            SLB_TRY(slb_gemm_split(pb, w->map_w_proj, fmt, B, W, w->mlp, w->map_b_proj, head_f32, nullptr, nullptr, SLB_EPI_NONE,
+            SLB_TRY(slb_gemm_split(pb, w->map_w_proj, fmt, B, W, w->mlp, kAlpha, w->map_b_proj, head_f32, nullptr, nullptr, SLB_EPI_NONE,
                                    3, out, nullptr, stream));
         }
     } else if (w->proj) {
         // ln_post on the class tokens (rows T*W apart), then the projection
         SLB_TRY(slb_layernorm(x, B, W, T * W, w->ln_post_g, w->ln_post_b, w->ln_eps, fmt, nullptr, pa, stream));
-        SLB_TRY(slb_gemm_split(pa, w->proj, fmt, B, w->embed_dim, W, nullptr, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, out,
+        SLB_TRY(slb_gemm_split(pa, w->proj, fmt, B, w->embed_dim, W, kAlpha, nullptr, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, out,
                                nullptr, stream));
     } else {
         SLB_TRY(slb_layernorm(x, B, W, T * W, w->ln_post_g, w->ln_post_b, w->ln_eps, fmt, out, nullptr, stream));
@@ -235,6 +238,6 @@ extern "C" int slb_text_forward(const SlbTextWeights* w, const int64_t* tokens, 
     if (rc != SLB_OK) return rc;
     rc = slb_layernorm(head, B, W, W, w->ln_final_g, w->ln_final_b, w->ln_eps, w->plane_fmt, nullptr, pa, stream);
     if (rc != SLB_OK) return rc;
-    return slb_gemm_split(pa, w->proj, w->plane_fmt, B, w->embed_dim, W, nullptr, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, out,
+    return slb_gemm_split(pa, w->proj, w->plane_fmt, B, w->embed_dim, W, kAlpha, nullptr, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, out,
                           nullptr, stream);
 }

@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
             const int64_t b = row / (g * g);
             const float2 v = *reinterpret_cast<const float2*>(img + ((b * 3 + c) * S + (gy * P + py)) * (int64_t)S + gx * P + px);
             uint16_t h0, l0, h1, l1;
-            slb_split2(v.x, fmt, h0, l0);
-            slb_split2(v.y, fmt, h1, l1);
+            slb_split2_act(v.x, fmt, h0, l0);
+            slb_split2_act(v.y, fmt, h1, l1);
             h2 = (uint32_t)h0 | ((uint32_t)h1 << 16);
             l2 = (uint32_t)l0 | ((uint32_t)l1 << 16);
         }
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         if (out_hi) {
             uint16_t h[4], l[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) slb_split2(y[k], fmt, h[k], l[k]);
+            for (int k = 0; k < 4; ++k) slb_split2_act(y[k], fmt, h[k], l[k]);
             reinterpret_cast<uint2*>(out_hi + r * cols)[i] =
                 make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
             reinterpret_cast<uint2*>(out_lo + r * cols)[i] =
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* __restr
             if (out_hi) {
                 uint16_t h[4], l[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) slb_split2(y[k], fmt, h[k], l[k]);
+                for (int k = 0; k < 4; ++k) slb_split2_act(y[k], fmt, h[k], l[k]);
                 reinterpret_cast<uint2*>(out_hi + r * cols)[i] =
                     make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
                 reinterpret_cast<uint2*>(out_lo + r * cols)[i] =
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_small_kernel(AttnPa
             if (p.out_f32) p.out_f32[idx] = o;
             if (p.out_hi) {
                 uint16_t hh, ll;
-                slb_split2(o, p.fmt, hh, ll);
+                slb_split2_act(o, p.fmt, hh, ll);
                 p.out_hi[idx] = hh;
                 p.out_lo[idx] = ll;
             }

@@ -133,7 +133,7 @@ class TextTower:
             return t.data_ptr()
 
         def planes(mat):
-            t = ops.split_planes(mat.to(dev), N.PLANE_F16)
+            t = ops.split_planes(mat.to(dev), N.PLANE_F16, N.WEIGHT_PLANE_SCALE)
             keep.append(t)
             return t.data_ptr()
 

@@ -205,7 +205,7 @@ class VitTower:
             return t.data_ptr()
 
         def planes(mat: torch.Tensor):
-            t = ops.split_planes(mat.to(dev), fmt)
+            t = ops.split_planes(mat.to(dev), fmt, N.WEIGHT_PLANE_SCALE)
             keep.append(t)
             return t.data_ptr()
 

@@ -172,15 +172,16 @@ def gather_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 PLANE_DTYPES = {N.PLANE_F16: torch.float16, N.PLANE_BF16: torch.bfloat16}
 
 
-def split_planes(x: torch.Tensor, fmt: int = N.PLANE_F16) -> torch.Tensor:
-    """fp32 (..., K) -> (2, ..., K) 16-bit planes: hi = rn16(x), lo = rn16(x - hi)."""
+def split_planes(x: torch.Tensor, fmt: int = N.PLANE_F16, scale: float = 1.0) -> torch.Tensor:
+    """fp32 (..., K) -> (2, ..., K) 16-bit planes of ``scale * x``: hi = rn16(scale * x), lo = rn16(scale * x - hi).
+    ``scale`` is a power of two that lifts the tensor into the fp16 normal range (weights: N.WEIGHT_PLANE_SCALE)."""
     lib = N.load(require_device=True)
     N.require_cuda(x, "x")
     x = x.detach().to(torch.float32).contiguous()
     planes = torch.empty((2, *x.shape), dtype=PLANE_DTYPES[fmt], device=x.device)
     if x.numel():
         with _dev_guard(x):
-            rc = lib.slb_split_planes(x.data_ptr(), x.numel(), fmt, planes.data_ptr(), N.stream_ptr(x.device))
+            rc = lib.slb_split_planes(x.data_ptr(), x.numel(), fmt, float(scale), planes.data_ptr(), N.stream_ptr(x.device))
         N.check(rc, "slb_split_planes")
     return planes
 
@@ -195,10 +196,13 @@ def gemm_split(
     col_scale: torch.Tensor | None = None,
     epilogue: int = N.EPI_NONE,
     passes: int = 3,
+    alpha: float = 1.0,
     out_f32: torch.Tensor | bool = True,
     out_planes: torch.Tensor | bool = False,
 ):
-    """K4: act((A @ W^T) * row_scale * col_scale + bias) + residual from split planes (2, M, K) and (2, N, K).
+    """K4: act(alpha * (A @ W^T) * row_scale * col_scale + bias) + residual from split planes (2, M, K) and (2, N, K).
+
+    ``alpha`` = 1 / (scale of the A planes * scale of the W planes). ``out_planes`` are written at N.ACT_PLANE_SCALE.
 
     ``out_f32`` / ``out_planes``: True = allocate, False = not wanted, or a preallocated tensor.
     Returns (out_f32 | None, out_planes | None).
@@ -228,7 +232,7 @@ def gemm_split(
         assert tuple(out_planes.shape) == (2, M, Nn) and out_planes.is_contiguous() and out_planes.dtype == a_planes.dtype
     with _dev_guard(a_planes):
         rc = lib.slb_gemm_split(
-            a_planes.data_ptr(), w_planes.data_ptr(), fmt, M, Nn, K, N.ptr(bias), N.ptr(residual), N.ptr(row_scale),
+            a_planes.data_ptr(), w_planes.data_ptr(), fmt, M, Nn, K, float(alpha), N.ptr(bias), N.ptr(residual), N.ptr(row_scale),
             N.ptr(col_scale), epilogue, passes, N.ptr(out_f32), N.ptr(out_planes), N.stream_ptr(dev),
         )
     N.check(rc, "slb_gemm_split")
@@ -254,7 +258,8 @@ def u8_to_f32_norm(u8: torch.Tensor, mean, std) -> torch.Tensor:
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor | None, eps: float, fmt: int | None = None):
-    """Row LayerNorm of a contiguous (rows, cols) fp32 tensor -> fp32 (fmt None) or split planes (2, rows, cols)."""
+    """Row LayerNorm of a contiguous (rows, cols) fp32 tensor -> fp32 (fmt None) or split planes (2, rows, cols) at
+    N.ACT_PLANE_SCALE."""
     lib = N.load(require_device=True)
     N.require_cuda(x, "x")
     assert x.ndim == 2 and x.dtype == torch.float32 and x.is_contiguous()
@@ -311,8 +316,12 @@ def _pad64(d: int) -> int:
     return (d + 63) // 64 * 64
 
 
-def normalize_split_rows(x: torch.Tensor, eps: float = 1e-12, fmt: int = N.PLANE_F16) -> torch.Tensor:
-    """F.normalize(x, dim=-1) of a (rows, D) fp32 tensor, emitted as GEMM operand planes (2, rows, pad64(D))."""
+UNIT_ROW_PLANE_SCALE = 1024.0  # unit-norm rows: elements ~ 1/sqrt(D)
+
+
+def normalize_split_rows(x: torch.Tensor, eps: float = 1e-12, fmt: int = N.PLANE_F16,
+                         scale: float = UNIT_ROW_PLANE_SCALE) -> torch.Tensor:
+    """F.normalize(x, dim=-1) of a (rows, D) fp32 tensor, emitted as GEMM operand planes (2, rows, pad64(D)) at ``scale``."""
     lib = N.load(require_device=True)
     N.require_cuda(x, "x")
     assert x.ndim == 2 and x.dtype == torch.float32
@@ -320,7 +329,8 @@ def normalize_split_rows(x: torch.Tensor, eps: float = 1e-12, fmt: int = N.PLANE
     rows, D = x.shape
     planes = torch.empty((2, rows, _pad64(D)), dtype=PLANE_DTYPES[fmt], device=x.device)
     with _dev_guard(x):
-        rc = lib.slb_normalize_split_rows(x.data_ptr(), rows, D, eps, fmt, planes.data_ptr(), None, N.stream_ptr(x.device))
+        rc = lib.slb_normalize_split_rows(x.data_ptr(), rows, D, eps, fmt, float(scale), planes.data_ptr(), None,
+                                          N.stream_ptr(x.device))
     N.check(rc, "slb_normalize_split_rows")
     return planes
 
@@ -445,7 +455,7 @@ def redundancy(cones: torch.Tensor, row_block: int = 8192) -> torch.Tensor:
     for r0 in range(0, n, row_block):
         r1 = min(n, r0 + row_block)
         xp = yp[:, r0:r1].contiguous()
-        S, _ = gemm_split(xp, yp, passes=3)
+        S, _ = gemm_split(xp, yp, passes=3, alpha=1.0 / (UNIT_ROW_PLANE_SCALE * UNIT_ROW_PLANE_SCALE))
         with _dev_guard(cones):
             # padded columns hold cos = 0 and must not take part in the max: pass the true column count via a view
             Sv = S if n_pad == n else S[:, :n].contiguous()

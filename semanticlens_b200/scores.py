@@ -59,11 +59,11 @@ def similarity_score(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
             # normalize(x) (Q, D) @ normalize(y) (D, C): y is normalised along ITS rows, then used untransposed
             yn = torch.nn.functional.normalize(yg.float(), dim=-1).t().contiguous()  # layout plumbing, (C, D)
             xp = ops.normalize_split_rows(xg.float())
-            yp = ops.split_planes(_pad_cols(yn, xp.shape[2]))
+            yp = ops.split_planes(_pad_cols(yn, xp.shape[2]), scale=ops.UNIT_ROW_PLANE_SCALE)
             n_pad = (yn.shape[0] + 7) // 8 * 8
             if n_pad != yn.shape[0]:
                 yp = torch.cat([yp, torch.zeros((2, n_pad - yn.shape[0], yp.shape[2]), dtype=yp.dtype, device=yp.device)], 1)
-            out, _ = ops.gemm_split(xp, yp.contiguous(), passes=3)
+            out, _ = ops.gemm_split(xp, yp.contiguous(), passes=3, alpha=1.0 / ops.UNIT_ROW_PLANE_SCALE**2)
             out = out[:, : yn.shape[0]]
         elif x.shape[1] == y.shape[1]:
             out = ops.cosine_gemm(xg, yg)

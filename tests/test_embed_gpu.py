@@ -18,6 +18,9 @@ def ops():
     return ops
 
 
+ACT = 16.0  # SLB_ACT_PLANE_SCALE: planes written by kernels hold 16 * x as hi + lo
+
+
 def rel_max(got, want):
     return ((got.double().cpu() - want.double().cpu()).abs().max() / want.double().abs().max()).item()
 
@@ -37,7 +40,7 @@ def test_layernorm_vs_torch(ops, rows, cols):
     got = ops.layernorm(x.cuda(), g.cuda(), b.cuda(), 1e-5)
     assert rel_max(got, want) < 2e-6
     planes = ops.layernorm(x.cuda(), g.cuda(), b.cuda(), 1e-5, fmt=0)
-    assert rel_max(planes[0].double() + planes[1].double() / 2048, want) < 2e-6
+    assert rel_max((planes[0].double() + planes[1].double()) / ACT, want) < 2e-6
 
 
 @pytest.mark.parametrize("B,T,H,dh,gain", [(2, 50, 12, 64, 1.0), (1, 257, 4, 64, 1.0), (3, 17, 2, 32, 1.0), (2, 197, 3, 64, 1.0),
@@ -52,7 +55,7 @@ def test_attention_vs_torch(ops, B, T, H, dh, gain):
     tol = 2e-6 * max(1.0, gain)  # fp32 exp of logits with std ~ gain^2: the error of expf grows with |logit|
     assert rel_max(got, want) < tol
     planes = ops.attention_packed(qkv.cuda(), H, fmt=0)
-    assert rel_max((planes[0].double() + planes[1].double() / 2048).view(B, T, W), want) < tol
+    assert rel_max(((planes[0].double() + planes[1].double()) / ACT).view(B, T, W), want) < tol
 
 
 @pytest.mark.parametrize("B,T,H,gain", [(2, 50, 12, 1.0), (1, 257, 4, 1.0), (2, 197, 3, 1.0), (1, 1, 1, 1.0), (2, 64, 2, 1.0),
@@ -66,16 +69,16 @@ def test_attention_from_planes_vs_torch(ops, B, T, H, gain):
     dh = 64
     W = H * dh
     qkv = torch.randn(B, T, 3 * W, generator=torch.Generator().manual_seed(T * 7 + H)) * gain
-    planes_in = ops.split_planes(qkv.view(B * T, 3 * W).cuda(), 0)
+    planes_in = ops.split_planes(qkv.view(B * T, 3 * W).cuda(), 0, ACT)
     # reference on the values the planes actually hold (22-bit operands)
-    held = (planes_in[0].double() + planes_in[1].double() / 2048).view(B, T, 3 * W).cpu()
+    held = ((planes_in[0].double() + planes_in[1].double()) / ACT).view(B, T, 3 * W).cpu()
     q, k, v = (t.view(B, T, H, dh).transpose(1, 2) for t in held.split(W, -1))
     want = (torch.softmax(q @ k.transpose(-1, -2) * dh**-0.5, -1) @ v).transpose(1, 2).reshape(B, T, W)
     tol = 2e-6 * max(1.0, gain)
     got = ops.attention_planes(planes_in, B, H)
     assert rel_max(got, want) < tol
     planes = ops.attention_planes(planes_in, B, H, fmt=0)
-    assert rel_max((planes[0].double() + planes[1].double() / 2048).view(B, T, W), want) < tol
+    assert rel_max(((planes[0].double() + planes[1].double()) / ACT).view(B, T, W), want) < tol
 
 
 def tower_for(name, seed=3, fmt=0):
@@ -209,8 +212,8 @@ def test_causal_attention_from_planes_vs_torch(ops, B, T, H):
     dh = 64
     W = H * dh
     qkv = torch.randn(B, T, 3 * W, generator=torch.Generator().manual_seed(T + H))
-    planes_in = ops.split_planes(qkv.view(B * T, 3 * W).cuda(), 0)
-    held = (planes_in[0].double() + planes_in[1].double() / 2048).view(B, T, 3 * W).cpu()
+    planes_in = ops.split_planes(qkv.view(B * T, 3 * W).cuda(), 0, ACT)
+    held = ((planes_in[0].double() + planes_in[1].double()) / ACT).view(B, T, 3 * W).cpu()
     q, k, v = (t.view(B, T, H, dh).transpose(1, 2) for t in held.split(W, -1))
     mask = torch.full((T, T), float("-inf"), dtype=torch.float64).triu(1)
     want = (torch.softmax(q @ k.transpose(-1, -2) * dh**-0.5 + mask, -1) @ v).transpose(1, 2).reshape(B, T, W)
