@@ -176,11 +176,21 @@ int slb_split_planes(const float* x, int64_t n, int plane_fmt, float scale, uint
 #define SLB_EPI_GELU_ERF 1  /* nn.GELU()            (open_clip ViT-B-32 / ViT-L-14) */
 #define SLB_EPI_QUICKGELU 2 /* x * sigmoid(1.702 x)  (open_clip *-quickgelu, OpenAI weights) */
 #define SLB_EPI_GELU_TANH 3 /* nn.GELU("tanh")       (SigLIP / timm towers) */
+#define SLB_EPI_RELU 4      /* max(z, 0)             (conv + BatchNorm + ReLU of the CLIP ModifiedResNet) */
+#define SLB_EPI_ADD_RELU 5  /* max(z + residual, 0)  (the tail of a ResNet bottleneck: the ReLU follows the shortcut add) */
+
+#define SLB_PASSES_SPLIT_ACC 4 /* `passes` selector of slb_gemm_split, see below */
 
 /* K4/K6. D[M,N] = act(alpha * (A[M,K] * W[N,K]^T) * row_scale[m] * col_scale[n] + bias[n]) + residual[M,N]
+ * (SLB_EPI_ADD_RELU applies its max after the residual instead)
  * on the 5th-gen tensor cores (tcgen05.mma kind::f16, TMA-fed 128B-swizzled stages, fp32 accumulators in TMEM) with
  * fp32-grade accuracy: operands are split planes a_planes [2,M,K], w_planes [2,N,K] (row-major, K contiguous) and each
  * tile accumulates Ahi*Whi + Ahi*Wlo + Alo*Whi (passes = 3) or Ahi*Whi only (passes = 1) in ONE accumulator.
+ * passes = SLB_PASSES_SPLIT_ACC computes the same three products but keeps the two cross terms in a second
+ * accumulator that the epilogue adds in fp32: the tensor core truncates at every accumulate, so a third of the adds
+ * into the large accumulator means a third of the (systematic) error — measured 2e-6 instead of 6e-6 of the largest
+ * output at K = 1152. It runs on the one-CTA 128 x 128 tile only (no 256 x 256 pair tile: TMEM is full), so it is
+ * for long chains of GEMMs without a normalisation in between (the ModifiedResNet), not for the ViT towers.
  * Replaces the fp32 GEMMs of open_clip's image tower (clip.py:118) and the cosine matmul of
  * scores.similarity_score (scores.py:120-125; row_scale/col_scale = inverse row norms).
  * Outputs: out_f32 [M,N] (nullable) and/or out_planes [2,M,N] (nullable) in the same plane format, ready to be the
@@ -296,6 +306,61 @@ size_t slb_text_workspace_bytes(const SlbTextWeights* w, int64_t B);
  * caller); out (B, embed_dim) fp32. workspace: 256-byte aligned, >= slb_text_workspace_bytes(w, B). */
 int slb_text_forward(const SlbTextWeights* w, const int64_t* tokens, const int64_t* eot_rows, int64_t B, float* out,
                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- CLIP ModifiedResNet image tower (open_clip "RN50" / "RN101" behind clip.py:103-118; BASELINE configs[0]) ----
+ * Activations are channels-last split planes [2, B*H*W, C] at SLB_ACT_PLANE_SCALE, so every 1x1 convolution IS a
+ * slb_gemm_split over them and a 3x3 convolution is the same GEMM over im2col planes; eval-mode BatchNorm rides in the
+ * GEMM epilogue as col_scale = gamma / sqrt(var + eps), bias = beta - mean * col_scale, followed by the ReLU. */
+
+/* Columns of the im2col matrix of a k x k convolution over cin channels: cin*k*k rounded up to a multiple of 64. */
+int64_t slb_conv_k(int64_t cin, int64_t ksize);
+
+/* im2col of the stem's first convolution (3x3, stride 2, pad 1) straight from the preprocessed images:
+ * img (B,3,S,S) fp32 NCHW -> planes [2, B*(S/2)^2, 64], column (ky*3 + kx)*3 + c, zero past 27. S must be even. */
+int slb_im2col_stem(const float* img, int64_t B, int64_t S, int plane_fmt, uint16_t* out_planes, void* stream);
+
+/* im2col of a 3x3, stride 1, pad 1 convolution over channels-last planes: in [2, B*H*W, C] ->
+ * out [2, B*H*W, slb_conv_k(C, 3)], column (ky*3 + kx)*C + c (weights are laid out (cout, ky, kx, cin) to match),
+ * zero outside the image and past 9C. C must be a multiple of 8. Plane bits are moved untouched. */
+int slb_im2col3x3(const uint16_t* in_planes, int64_t B, int64_t H, int64_t W, int64_t C, uint16_t* out_planes, void* stream);
+
+/* nn.AvgPool2d(2) over channels-last planes: in [2, B*H*W, C] -> out [2, B*(H/2)*(W/2), C]; H, W even, C % 8 == 0.
+ * The four values are summed in fp32 from hi + lo and re-split. */
+int slb_avgpool2_planes(const uint16_t* in_planes, int64_t B, int64_t H, int64_t W, int64_t C, int plane_fmt,
+                        uint16_t* out_planes, void* stream);
+
+/* Tokens of open_clip's AttentionPool2d: x (B, HW, C) fp32 channels-last feature map, pos (HW+1, C) ->
+ * tok_planes [2, B*(HW+1), C] = [mean over positions; positions] + pos, and query_planes [2, B, C] = token 0 of
+ * every image (the only query whose output is kept). */
+int slb_pool_tokens(const float* x, const float* pos, int64_t B, int64_t HW, int64_t C, int plane_fmt, uint16_t* tok_planes,
+                    uint16_t* query_planes, void* stream);
+
+typedef struct {
+    const uint16_t* w;  /* planes [2, cout, slb_conv_k(cin, ksize)]: conv weight permuted to (cout, ky, kx, cin), zero padded */
+    const float* scale; /* [cout] gamma / sqrt(running_var + eps) */
+    const float* shift; /* [cout] beta - running_mean * scale */
+    int32_t cin, cout, ksize, reserved;
+} SlbConvBn;
+
+typedef struct {
+    int32_t image_size, width, heads, out_dim;
+    int32_t blocks[4]; /* bottlenecks per stage, e.g. {3, 4, 6, 3} */
+    int32_t plane_fmt, n_convs;
+    /* HOST array in execution order: stem conv1, conv2, conv3; then per bottleneck conv1, conv2, conv3 and, for the first
+     * bottleneck of every stage, its downsample convolution. n_convs = 3 + sum(3 * blocks[i] + 1). */
+    const SlbConvBn* convs;
+    const float* pos;                          /* [(S/32)^2 + 1, 32 * width] attnpool.positional_embedding */
+    const uint16_t* w_q; const float* b_q;     /* planes [2, E, E], [E]       (E = 32 * width) */
+    const uint16_t* w_kv; const float* b_kv;   /* planes [2, 2E, E], [2E]: k_proj | v_proj */
+    const uint16_t* w_c; const float* b_c;     /* planes [2, out_dim, E], [out_dim] */
+} SlbRnWeights;
+
+size_t slb_rn_workspace_bytes(const SlbRnWeights* w, int64_t B);
+
+/* img (B,3,S,S) fp32 preprocessed -> out (B, out_dim) fp32, un-normalised like open_clip's encode_image.
+ * width must be a multiple of 64 and S of 32. workspace: 256-byte aligned, >= slb_rn_workspace_bytes(w, B). */
+int slb_rn_forward(const SlbRnWeights* w, const float* img, int64_t B, float* out, void* workspace, size_t workspace_bytes,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -174,7 +174,10 @@ def bench_scores():
 def bench_embed(batch):
     from semanticlens_b200.foundation_models import OpenClip
 
-    for url, B in (("ViT-B-32", batch), ("ViT-B-16", 128), ("ViT-L-14", 64), ("ViT-B-16-SigLIP2", 128), ("ViT-L-16-SigLIP-256", 64)):
+    for url, B in (("ViT-B-32", batch), ("ViT-B-16", 128), ("ViT-L-14", 64), ("ViT-B-16-SigLIP2", 128), ("ViT-L-16-SigLIP-256", 64),
+                   ("RN50", 128)):
+        if os.environ.get("SLB_BENCH_ONLY") and os.environ["SLB_BENCH_ONLY"] not in url:
+            continue
         fm = OpenClip(url, device="cuda", load_weights=False, seed=1)
         S = fm.cfg.image_size
         u8 = torch.randint(0, 255, (B, 3, S, S), dtype=torch.uint8, device="cuda")

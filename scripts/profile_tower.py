@@ -7,7 +7,7 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from semanticlens_b200 import _native  # noqa: E402
-from semanticlens_b200.foundation_models import OpenClip, vit  # noqa: E402
+from semanticlens_b200.foundation_models import OpenClip, rn, vit  # noqa: E402
 
 url, B = sys.argv[1], int(sys.argv[2])
 fm = OpenClip(url, device="cuda", load_weights=False, seed=1)
@@ -27,7 +27,7 @@ torch.cuda.synchronize()
 kt = _native.profile_end()
 ms = a.elapsed_time(b) / n
 out = {"tower": url, "batch": B, "ms": round(ms, 3), "images_per_s": round(B / ms * 1e3, 1),
-       "issued_TFLOPs_overall": round(3 * vit.flops_per_image(fm.cfg) * B / ms / 1e9, 1), "kernels": {}}
+       "issued_TFLOPs_overall": round(3 * (rn if fm.url in rn.CONFIGS else vit).flops_per_image(fm.cfg) * B / ms / 1e9, 1), "kernels": {}}
 for k, d in sorted(kt.items(), key=lambda kv: -kv[1]["ms"]):
     e = {"ms": round(d["ms"] / n, 3), "share": round(d["ms"] / n / ms, 3), "launches": d["launches"] // n}
     if d["flops"]:

@@ -19,8 +19,9 @@ _lib = None
 DT_F32, DT_F16, DT_BF16 = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_BTF = 0, 1
 AGG_MEAN, AGG_MAX, AGG_ABSMEAN, AGG_ABSMAX, AGG_TOKEN = 0, 1, 2, 3, 4
-EPI_NONE, EPI_GELU_ERF, EPI_QUICKGELU, EPI_GELU_TANH = 0, 1, 2, 3
+EPI_NONE, EPI_GELU_ERF, EPI_QUICKGELU, EPI_GELU_TANH, EPI_RELU, EPI_ADD_RELU = 0, 1, 2, 3, 4, 5
 POOL_CLS, POOL_MAP = 0, 1
+PASSES_SPLIT_ACC = 4  # SLB_PASSES_SPLIT_ACC
 PLANE_F16, PLANE_BF16 = 0, 1
 ACT_PLANE_SCALE, WEIGHT_PLANE_SCALE = 16.0, 1024.0  # SLB_ACT_PLANE_SCALE / SLB_WEIGHT_PLANE_SCALE
 
@@ -85,6 +86,13 @@ _PROTOS = {
     "slb_text_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "slb_text_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "slb_patch_k": (c_int64, [c_int64]),
+    "slb_conv_k": (c_int64, [c_int64, c_int64]),
+    "slb_im2col_stem": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "slb_im2col3x3": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "slb_avgpool2_planes": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "slb_pool_tokens": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "slb_rn_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
+    "slb_rn_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "slb_vit_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "slb_vit_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
@@ -126,6 +134,20 @@ class SlbVitWeights(ctypes.Structure):
         + [("layer", ctypes.POINTER(SlbVitLayer))]
         + [(n, c_void_p) for n in ("map_q", "map_w_kv", "map_b_kv", "map_w_out", "map_b_out", "map_ln_g", "map_ln_b",
                                    "map_w_fc", "map_b_fc", "map_w_proj", "map_b_proj")]
+    )
+
+
+class SlbConvBn(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("w", "scale", "shift")] + [(n, ctypes.c_int32) for n in ("cin", "cout", "ksize", "reserved")]
+
+
+class SlbRnWeights(ctypes.Structure):
+    _fields_ = (
+        [(n, ctypes.c_int32) for n in ("image_size", "width", "heads", "out_dim")]
+        + [("blocks", ctypes.c_int32 * 4)]
+        + [(n, ctypes.c_int32) for n in ("plane_fmt", "n_convs")]
+        + [("convs", ctypes.POINTER(SlbConvBn))]
+        + [(n, c_void_p) for n in ("pos", "w_q", "b_q", "w_kv", "b_kv", "w_c", "b_c")]
     )
 
 

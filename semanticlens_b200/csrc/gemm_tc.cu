@@ -37,7 +37,7 @@ struct Cfg {
     static constexpr int kABytes = 2 * BM * BK * 2;  // both planes
     static constexpr int kWBytes = 2 * BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kWBytes;
-    static constexpr int kTmemCols = 2 * BN;  // [buffer][BN]
+    static constexpr int kTmemCols = 4 * BN;  // [buffer][main | cross][BN]: the cross half is used by SLB_PASSES_SPLIT_ACC only
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -52,6 +52,7 @@ struct GemmParams {
     uint16_t* out_planes;    // [2,M,N] or null
     int epilogue;
     int passes;  // 3 or 1
+    int split_acc;  // 1: hi·lo + lo·hi accumulate in their own TMEM columns and meet hi·hi in the epilogue (fp32 add)
     int fmt;     // plane format of A/W and of out_planes
     unsigned int* dbg;  // SLB_GEMM_DEBUG=1: host-mapped words [cta][16] that a timed-out wait reports into (else null)
 };
@@ -66,21 +67,31 @@ __device__ __forceinline__ float act_apply(float v, int epi) {
             float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
             return 0.5f * v * (1.0f + tanhf(u));
         }
+        case SLB_EPI_RELU:
+            return fmaxf(v, 0.0f);
         default:
-            return v;
+            return v;  // SLB_EPI_NONE; SLB_EPI_ADD_RELU acts after the residual
     }
 }
 
 // Epilogue of one 32-column chunk of an accumulator row: TMEM -> registers -> alpha / scale / bias / activation /
 // residual -> global (fp32 and/or split planes at the activation scale). Thread = one output row m, columns [nb, nb + 32).
 __device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr, int64_t m, bool row_ok, float rs, int64_t nb,
-                                            int fmt) {
+                                            int fmt, uint32_t cross_off = 0) {
     uint32_t raw[32];
     float v[32];
     slb_tmem_ld_32x32(taddr, raw);
-    slb_tmem_ld_wait();
+    if (cross_off) {
+        uint32_t cr[32];
+        slb_tmem_ld_32x32(taddr + cross_off, cr);
+        slb_tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+        for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(raw[j]) + __uint_as_float(cr[j])) * p.alpha;
+    } else {
+        slb_tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+    }
     if (!(row_ok && nb < p.N)) return;
     const int ncols = (int)min((int64_t)32, p.N - nb);  // multiple of 8
     if (p.row_scale) {
@@ -97,7 +108,7 @@ __device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr,
         for (int j = 0; j < 32; ++j)
             if (j < ncols) v[j] += __ldg(p.bias + nb + j);
     }
-    if (p.epilogue != SLB_EPI_NONE) {
+    if (p.epilogue != SLB_EPI_NONE && p.epilogue != SLB_EPI_ADD_RELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], p.epilogue);
     }
@@ -110,6 +121,10 @@ __device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr,
                 v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
             }
         }
+    }
+    if (p.epilogue == SLB_EPI_ADD_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
     }
     if (p.out_f32) {
         float4* o4 = reinterpret_cast<float4*>(p.out_f32 + m * p.N + nb);
@@ -204,7 +219,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 slb_mbar_wait(&tempty[acc], acc_phase ^ 1u);
                 slb_tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BN);
+                const uint32_t d_cross = d_tmem + (p.split_acc ? BN : 0);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     slb_mbar_wait(&full[stage], phase);
                     slb_tc_fence_after();
@@ -216,10 +232,12 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         if (pr < p.passes) {
                             const uint32_t ab = a0 + (pr == 2 ? BM * BK * 2 : 0);
                             const uint32_t wb = w0 + (pr == 1 ? BN * BK * 2 : 0);
+                            // first write of an accumulator overwrites: main at (kb, pr, k) = 0, the cross columns at pr = 1
+                            const int first = p.split_acc ? (pr == 2 ? 1 : kb) : (kb | pr);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k) {
-                                slb_umma_f16(d_tmem, slb_umma_desc_sw128(ab + k * 32), slb_umma_desc_sw128(wb + k * 32), idesc,
-                                             (kb | pr | k) != 0);
+                                slb_umma_f16(pr ? d_cross : d_tmem, slb_umma_desc_sw128(ab + k * 32), slb_umma_desc_sw128(wb + k * 32),
+                                             idesc, (first | k) != 0);
                             }
                         }
                     }
@@ -246,8 +264,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const float rs = (p.row_scale && row_ok) ? p.row_scale[m] : 1.0f;
 #pragma unroll 1
             for (int c = chunk0; c < BN / 32; c += kEpiWarps / 4) {
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32);
-                drain_chunk(p, taddr, m, row_ok, rs, (int64_t)n0 + c * 32, fmt);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
+                drain_chunk(p, taddr, m, row_ok, rs, (int64_t)n0 + c * 32, fmt, p.split_acc ? BN : 0);
             }
             slb_tc_fence_before();
             __syncwarp();
@@ -575,8 +593,11 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
     SLB_REQUIRE(a_planes && w_planes, SLB_EINVAL, "slb_gemm_split: null operand");
     SLB_REQUIRE(out_f32 || out_planes, SLB_EINVAL, "slb_gemm_split: no output requested");
     SLB_REQUIRE(plane_fmt == SLB_PLANE_F16 || plane_fmt == SLB_PLANE_BF16, SLB_EINVAL, "slb_gemm_split: bad plane format");
-    SLB_REQUIRE(passes == 1 || passes == 3, SLB_EINVAL, "slb_gemm_split: passes must be 1 or 3");
-    SLB_REQUIRE(epilogue >= SLB_EPI_NONE && epilogue <= SLB_EPI_GELU_TANH, SLB_EINVAL, "slb_gemm_split: bad epilogue");
+    SLB_REQUIRE(passes == 1 || passes == 3 || passes == SLB_PASSES_SPLIT_ACC, SLB_EINVAL,
+                "slb_gemm_split: passes must be 1, 3 or SLB_PASSES_SPLIT_ACC");
+    const int split_acc = passes == SLB_PASSES_SPLIT_ACC;
+    if (split_acc) passes = 3;
+    SLB_REQUIRE(epilogue >= SLB_EPI_NONE && epilogue <= SLB_EPI_ADD_RELU, SLB_EINVAL, "slb_gemm_split: bad epilogue");
     SLB_REQUIRE(K >= BK && K % BK == 0, SLB_EUNSUPPORTED, "slb_gemm_split: K must be a positive multiple of 64 (got %lld)",
                 (long long)K);
     SLB_REQUIRE(N % 8 == 0, SLB_EUNSUPPORTED, "slb_gemm_split: N must be a multiple of 8 (got %lld)", (long long)N);
@@ -593,7 +614,7 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
     p.alpha = alpha;
     p.bias = bias; p.residual = residual; p.row_scale = row_scale; p.col_scale = col_scale;
     p.out_f32 = out_f32; p.out_planes = out_planes;
-    p.epilogue = epilogue; p.passes = passes; p.fmt = plane_fmt;
+    p.epilogue = epilogue; p.passes = passes; p.fmt = plane_fmt; p.split_acc = split_acc;
     // Kernel choice (measured on B200, profiles/r01_gemm_variants.jsonl). One-CTA 128 x 128 tiles read 128 B/clk of shared
     // memory per MMA cycle (the limit); CTA pairs share W: 256 x 128 pair tiles (double-buffered accumulators) win when W
     // is large (cosine GEMM), 256 x 256 pair tiles (single-buffered) when K is long and the tile count fills the machine
@@ -614,6 +635,7 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
         if (K >= 512 && N >= 256 && eff256 >= 0.85) kind = 3;
     }
     if (forced) kind = (M > BM || forced == 1) ? forced : 1;
+    if (split_acc) kind = 1;  // the second accumulator fits the one-CTA tile only (4 x 128 TMEM columns)
     CUtensorMap tmA, tmW;
     int rc = slb_make_plane_map(&tmA, a_planes, M, K, 2, BM);
     if (rc != SLB_OK) return rc;

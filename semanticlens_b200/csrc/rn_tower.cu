@@ -1,0 +1,402 @@
+// The CLIP ModifiedResNet image tower ("RN50" / "RN101") as ONE C-ABI call: (B,3,S,S) fp32 -> (B, out_dim) features.
+//
+// Replaces `self.model.encode_image(img)` of the reference (foundation_models/clip.py:103-118) for open_clip's
+// ModifiedResNet (the embed model of BASELINE.json configs[0]): 3-convolution stem + AvgPool2d(2),
+// bottlenecks whose stride is an average pool (anti-aliasing), AttentionPool2d head.
+//
+// Data layout: activations are channels-last split planes [2, B*H*W, C] at SLB_ACT_PLANE_SCALE. That makes every 1x1
+// convolution (two thirds of the convolutions, 60 % of the flops) exactly slb_gemm_split over the activation planes —
+// TMA-fed tcgen05 tiles, no data movement — and a 3x3 convolution the same GEMM over im2col planes written by a
+// 16-byte gather kernel (the im2col matrix is 9x the activation but only the narrow bottleneck channels go through it).
+// Eval-mode BatchNorm, ReLU and the shortcut add are GEMM epilogues (col_scale / bias / SLB_EPI_RELU / SLB_EPI_ADD_RELU);
+// the block output is written both as planes (operand of the next block) and fp32 (its shortcut).
+// No allocation: caller-supplied workspace (slb_rn_workspace_bytes). Nothing synchronises.
+#include "tc_common.cuh"
+
+#include <stdlib.h>
+#include <algorithm>
+
+namespace {
+
+constexpr float kAlpha = 1.0f / (SLB_ACT_PLANE_SCALE * SLB_WEIGHT_PLANE_SCALE);
+// 50+ convolutions in sequence with no normalisation between them: the truncation bias of the tensor-core accumulate adds
+// up coherently, so the cross terms get their own accumulator (slb200.h, SLB_PASSES_SPLIT_ACC). SLB_RN_FAST=1 trades that
+// for the faster single-accumulator tiles (measured 5e-5 instead of ~2e-5 of the largest feature on RN50).
+int rn_passes() {
+    static const int v = [] {
+        const char* e = getenv("SLB_RN_FAST");
+        return (e && e[0] == '1') ? 3 : SLB_PASSES_SPLIT_ACC;
+    }();
+    return v;
+}
+
+int grid_for(int64_t n, int threads) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>(slb_ceil_div(n, threads), (int64_t)slb_sm_count() * 16));
+}
+
+// ---- stem im2col: one thread = one 16-byte chunk (8 columns) of one output row, both planes --------------------------
+__global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ img, int64_t n_chunks, int S, int fmt,
+                                                          uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    const int Ho = S >> 1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_chunks; i += (int64_t)gridDim.x * blockDim.x) {
+        const int kc = (int)(i & 7);
+        const int64_t m = i >> 3;
+        const int x = (int)(m % Ho);
+        const int y = (int)((m / Ho) % Ho);
+        const int64_t b = m / ((int64_t)Ho * Ho);
+        uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+        if (kc < 4) {
+            const float* base = img + b * 3 * (int64_t)S * S;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = kc * 8 + j;
+                float v = 0.f;
+                if (k < 27) {
+                    const int tap = k / 3, c = k - tap * 3;
+                    const int yy = 2 * y + tap / 3 - 1, xx = 2 * x + tap % 3 - 1;
+                    if (yy >= 0 && yy < S && xx >= 0 && xx < S) v = __ldg(base + ((int64_t)c * S + yy) * S + xx);
+                }
+                uint16_t hh, ll;
+                slb_split2_act(v, fmt, hh, ll);
+                h[j >> 1] |= (uint32_t)hh << ((j & 1) * 16);
+                l[j >> 1] |= (uint32_t)ll << ((j & 1) * 16);
+            }
+        }
+        *reinterpret_cast<uint4*>(hi + m * 64 + kc * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(lo + m * 64 + kc * 8) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// ---- 3x3 / stride 1 / pad 1 im2col over channels-last planes: pure 16-byte moves ------------------------------------
+// grid.y = plane; one thread = one chunk of 8 channels of one tap of one output pixel.
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const uint16_t* __restrict__ in, int64_t M, int H, int W, int C8, int K8,
+                                                        uint16_t* __restrict__ out) {
+    const uint4* src = reinterpret_cast<const uint4*>(in) + (int64_t)blockIdx.y * M * C8;
+    uint4* dst = reinterpret_cast<uint4*>(out) + (int64_t)blockIdx.y * M * K8;
+    const int64_t n = M * K8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int kc = (int)(i % K8);
+        const int64_t m = i / K8;
+        const int tap = kc / C8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (tap < 9) {
+            const int c8 = kc - tap * C8;
+            const int x = (int)(m % W);
+            const int y = (int)((m / W) % H);
+            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(src + (m + (int64_t)(yy - y) * W + (xx - x)) * C8 + c8);
+        }
+        dst[i] = v;
+    }
+}
+
+// ---- AvgPool2d(2) over channels-last planes ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) avgpool2_kernel(const uint16_t* __restrict__ in, int64_t M_in, int64_t n_chunks, int Ho,
+                                                       int Wo, int C8, int fmt, uint16_t* __restrict__ out, int64_t M_out) {
+    const uint4* sh = reinterpret_cast<const uint4*>(in);
+    const uint4* sl = sh + M_in * C8;
+    uint4* dh = reinterpret_cast<uint4*>(out);
+    uint4* dl = dh + M_out * C8;
+    const int W = 2 * Wo;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_chunks; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        const int64_t mo = i / C8;
+        const int xo = (int)(mo % Wo);
+        const int yo = (int)((mo / Wo) % Ho);
+        const int64_t b = mo / ((int64_t)Wo * Ho);
+        const int64_t m00 = (b * 2 * Ho + 2 * yo) * W + 2 * xo;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int64_t m = m00 + (t >> 1) * W + (t & 1);
+            const uint4 a = __ldg(sh + m * C8 + c8), c = __ldg(sl + m * C8 + c8);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint16_t hb = (uint16_t)(aw[j >> 1] >> ((j & 1) * 16)), lb = (uint16_t)(cw[j >> 1] >> ((j & 1) * 16));
+                acc[j] += slb_from_plane(hb, fmt) + slb_from_plane(lb, fmt);
+            }
+        }
+        uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint16_t hh, ll;
+            slb_split2(acc[j] * 0.25f, fmt, hh, ll);  // the sum is already at the activation scale
+            h[j >> 1] |= (uint32_t)hh << ((j & 1) * 16);
+            l[j >> 1] |= (uint32_t)ll << ((j & 1) * 16);
+        }
+        dh[i] = make_uint4(h[0], h[1], h[2], h[3]);
+        dl[i] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// ---- attention-pool tokens: thread = (image, channel); positions are walked with coalesced loads ------------------------
+__global__ void __launch_bounds__(256) pool_tokens_kernel(const float* __restrict__ x, const float* __restrict__ pos, int64_t B,
+                                                          int HW, int C, int fmt, uint16_t* __restrict__ tok, uint16_t* __restrict__ qry) {
+    const int64_t n = B * C;
+    const int T = HW + 1;
+    uint16_t* tok_lo = tok + B * T * (int64_t)C;
+    uint16_t* qry_lo = qry + n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t b = i / C;
+        const float* xb = x + b * HW * (int64_t)C + c;
+        float sum = 0.f;
+        for (int t = 0; t < HW; ++t) {
+            const float v = xb[(int64_t)t * C];
+            sum += v;
+            uint16_t hh, ll;
+            slb_split2_act(v + __ldg(pos + (int64_t)(t + 1) * C + c), fmt, hh, ll);
+            const int64_t o = (b * T + t + 1) * C + c;
+            tok[o] = hh;
+            tok_lo[o] = ll;
+        }
+        uint16_t hh, ll;
+        slb_split2_act(sum / (float)HW + __ldg(pos + c), fmt, hh, ll);
+        tok[b * T * C + c] = hh;
+        tok_lo[b * T * C + c] = ll;
+        qry[i] = hh;
+        qry_lo[i] = ll;
+    }
+}
+
+// ---- workspace ---------------------------------------------------------------------------------------------------------
+struct RnLayout {
+    size_t xa, xb, t1, t2, t3, xp, f, col, head, total;
+};
+
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int n_convs_of(const SlbRnWeights* w) {
+    int n = 3;
+    for (int i = 0; i < 4; ++i) n += 3 * w->blocks[i] + 1;
+    return n;
+}
+
+bool rn_layout(const SlbRnWeights* w, int64_t B, RnLayout* L) {
+    if (!w || w->width <= 0 || w->width % 64 || w->image_size <= 0 || w->image_size % 32) return false;
+    for (int i = 0; i < 4; ++i)
+        if (w->blocks[i] < 1) return false;
+    const int64_t wd = w->width, S = w->image_size;
+    int64_t M = B * (S / 2) * (S / 2);
+    // element counts (per plane); byte sizes are 4x for planes (2 planes x 2 bytes) and for fp32
+    int64_t x_max = M * wd, t_max = M * (wd / 2), t3_max = 0, xp_max = 0, f_max = 0;
+    int64_t col_max = std::max<int64_t>(M * 64, M * slb_conv_k(wd / 2, 3));
+    M /= 4;  // after the stem's pool
+    int64_t inpl = wd;
+    for (int li = 0; li < 4; ++li) {
+        const int64_t pl = wd << li;
+        for (int bi = 0; bi < w->blocks[li]; ++bi) {
+            const int stride = (bi == 0 && li > 0) ? 2 : 1;
+            x_max = std::max(x_max, M * inpl);
+            t_max = std::max(t_max, M * pl);
+            col_max = std::max(col_max, M * slb_conv_k(pl, 3));
+            if (stride == 2) {
+                xp_max = std::max(xp_max, M / 4 * inpl);
+                t3_max = std::max(t3_max, M / 4 * pl);
+                M /= 4;
+            }
+            x_max = std::max(x_max, M * 4 * pl);
+            f_max = std::max(f_max, M * 4 * pl);
+            inpl = 4 * pl;
+        }
+    }
+    const int64_t E = 32 * wd, T = (S / 32) * (S / 32) + 1;
+    col_max = std::max(col_max, B * T * 2 * E);  // the k | v projections (fp32) reuse the im2col region
+    x_max = std::max(x_max, B * T * E);          // the attention-pool tokens reuse an activation buffer
+    size_t o = 0;
+    L->xa = o;   o += align_up((size_t)x_max * 4);
+    L->xb = o;   o += align_up((size_t)x_max * 4);
+    L->t1 = o;   o += align_up((size_t)t_max * 4);
+    L->t2 = o;   o += align_up((size_t)t_max * 4);
+    L->t3 = o;   o += align_up((size_t)t3_max * 4);
+    L->xp = o;   o += align_up((size_t)xp_max * 4);
+    L->f = o;    o += align_up((size_t)f_max * 4);
+    L->col = o;  o += align_up((size_t)col_max * 4);
+    L->head = o; o += 3 * align_up((size_t)B * E * 4);  // query planes | projected query fp32 | pooled planes
+    L->total = o;
+    return true;
+}
+
+}  // namespace
+
+extern "C" int64_t slb_conv_k(int64_t cin, int64_t ksize) { return (cin * ksize * ksize + 63) / 64 * 64; }
+
+extern "C" int slb_im2col_stem(const float* img, int64_t B, int64_t S, int plane_fmt, uint16_t* out_planes, void* stream) {
+    SLB_REQUIRE(B >= 0 && S > 0, SLB_EINVAL, "slb_im2col_stem: bad size");
+    if (B == 0) return SLB_OK;
+    SLB_REQUIRE(img && out_planes, SLB_EINVAL, "slb_im2col_stem: null pointer");
+    SLB_REQUIRE(S % 2 == 0, SLB_EUNSUPPORTED, "slb_im2col_stem: the image size must be even");
+    SLB_REQUIRE(((uintptr_t)out_planes % 16) == 0, SLB_EINVAL, "slb_im2col_stem: misaligned output");
+    const int64_t M = B * (S / 2) * (S / 2);
+    SlbProfScope prof("K4 im2col", stream, 0.0, 12.0 * (double)B * (double)S * (double)S + 4.0 * 64.0 * (double)M);
+    im2col_stem_kernel<<<grid_for(M * 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, M * 8, (int)S, plane_fmt, out_planes,
+                                                                                           out_planes + M * 64);
+    SLB_LAUNCH_OK("im2col_stem");
+    return SLB_OK;
+}
+
+extern "C" int slb_im2col3x3(const uint16_t* in_planes, int64_t B, int64_t H, int64_t W, int64_t C, uint16_t* out_planes,
+                             void* stream) {
+    SLB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0, SLB_EINVAL, "slb_im2col3x3: bad size");
+    if (B == 0) return SLB_OK;
+    SLB_REQUIRE(in_planes && out_planes, SLB_EINVAL, "slb_im2col3x3: null pointer");
+    SLB_REQUIRE(C % 8 == 0, SLB_EUNSUPPORTED, "slb_im2col3x3: channels must be a multiple of 8 (got %lld)", (long long)C);
+    SLB_REQUIRE(((uintptr_t)in_planes % 16) == 0 && ((uintptr_t)out_planes % 16) == 0, SLB_EINVAL, "slb_im2col3x3: misaligned");
+    const int64_t M = B * H * W, K = slb_conv_k(C, 3);
+    SlbProfScope prof("K4 im2col", stream, 0.0, 4.0 * (double)M * (double)(K + C));
+    dim3 grid(grid_for(M * (K / 8), 256), 2);
+    im2col3x3_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_planes, M, (int)H, (int)W, (int)(C / 8), (int)(K / 8),
+                                                                         out_planes);
+    SLB_LAUNCH_OK("im2col3x3");
+    return SLB_OK;
+}
+
+extern "C" int slb_avgpool2_planes(const uint16_t* in_planes, int64_t B, int64_t H, int64_t W, int64_t C, int plane_fmt,
+                                   uint16_t* out_planes, void* stream) {
+    SLB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0, SLB_EINVAL, "slb_avgpool2_planes: bad size");
+    if (B == 0) return SLB_OK;
+    SLB_REQUIRE(in_planes && out_planes, SLB_EINVAL, "slb_avgpool2_planes: null pointer");
+    SLB_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, SLB_EUNSUPPORTED,
+                "slb_avgpool2_planes: H and W must be even and C a multiple of 8");
+    SLB_REQUIRE(((uintptr_t)in_planes % 16) == 0 && ((uintptr_t)out_planes % 16) == 0, SLB_EINVAL, "slb_avgpool2_planes: misaligned");
+    const int64_t Mo = B * (H / 2) * (W / 2), n = Mo * (C / 8);
+    SlbProfScope prof("K4 avgpool", stream, 0.0, 4.0 * 5.0 * (double)Mo * (double)C);
+    avgpool2_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in_planes, B * H * W, n, (int)(H / 2), (int)(W / 2),
+                                                                                    (int)(C / 8), plane_fmt, out_planes, Mo);
+    SLB_LAUNCH_OK("avgpool2");
+    return SLB_OK;
+}
+
+extern "C" int slb_pool_tokens(const float* x, const float* pos, int64_t B, int64_t HW, int64_t C, int plane_fmt,
+                               uint16_t* tok_planes, uint16_t* query_planes, void* stream) {
+    SLB_REQUIRE(B >= 0 && HW > 0 && C > 0, SLB_EINVAL, "slb_pool_tokens: bad size");
+    if (B == 0) return SLB_OK;
+    SLB_REQUIRE(x && pos && tok_planes && query_planes, SLB_EINVAL, "slb_pool_tokens: null pointer");
+    SlbProfScope prof("K4 pool_tokens", stream, 0.0, 8.0 * (double)B * (double)(HW + 1) * (double)C);
+    pool_tokens_kernel<<<grid_for(B * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, pos, B, (int)HW, (int)C, plane_fmt,
+                                                                                           tok_planes, query_planes);
+    SLB_LAUNCH_OK("pool_tokens");
+    return SLB_OK;
+}
+
+extern "C" size_t slb_rn_workspace_bytes(const SlbRnWeights* w, int64_t B) {
+    RnLayout L;
+    if (B < 0 || !rn_layout(w, B, &L)) return 0;
+    return L.total;
+}
+
+extern "C" int slb_rn_forward(const SlbRnWeights* w, const float* img, int64_t B, float* out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    SLB_REQUIRE(w != nullptr && B >= 0, SLB_EINVAL, "slb_rn_forward: bad arguments");
+    if (B == 0) return SLB_OK;
+    SLB_REQUIRE(img && out && workspace, SLB_EINVAL, "slb_rn_forward: null pointer");
+    RnLayout L;
+    SLB_REQUIRE(rn_layout(w, B, &L), SLB_EUNSUPPORTED,
+                "slb_rn_forward: width must be a multiple of 64, image_size of 32, every stage needs a bottleneck");
+    SLB_REQUIRE(w->convs && w->n_convs == n_convs_of(w), SLB_EINVAL, "slb_rn_forward: expected %d convolutions, got %d",
+                n_convs_of(w), w->n_convs);
+    SLB_REQUIRE(w->pos && w->w_q && w->b_q && w->w_kv && w->b_kv && w->w_c && w->b_c, SLB_EINVAL,
+                "slb_rn_forward: incomplete attention pool");
+    const int64_t wd = w->width, S = w->image_size, E = 32 * wd;
+    SLB_REQUIRE(w->heads > 0 && E % w->heads == 0 && (E / w->heads) % 4 == 0 && E / w->heads <= 128, SLB_EUNSUPPORTED,
+                "slb_rn_forward: unsupported head count");
+    SLB_REQUIRE(w->out_dim > 0 && w->out_dim % 8 == 0, SLB_EUNSUPPORTED, "slb_rn_forward: out_dim must be a multiple of 8");
+    SLB_REQUIRE(((uintptr_t)workspace % 256) == 0, SLB_EINVAL, "slb_rn_forward: workspace must be 256-byte aligned");
+    SLB_REQUIRE(workspace_bytes >= L.total, SLB_EWORKSPACE, "slb_rn_forward: workspace needs %zu bytes, got %zu", L.total,
+                workspace_bytes);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    uint16_t* x_cur = reinterpret_cast<uint16_t*>(ws + L.xa);
+    uint16_t* x_nxt = reinterpret_cast<uint16_t*>(ws + L.xb);
+    uint16_t* t1 = reinterpret_cast<uint16_t*>(ws + L.t1);
+    uint16_t* t2 = reinterpret_cast<uint16_t*>(ws + L.t2);
+    uint16_t* t3 = reinterpret_cast<uint16_t*>(ws + L.t3);
+    uint16_t* xp = reinterpret_cast<uint16_t*>(ws + L.xp);
+    float* f = reinterpret_cast<float*>(ws + L.f);
+    uint16_t* col = reinterpret_cast<uint16_t*>(ws + L.col);
+    const int fmt = w->plane_fmt;
+    const int kPasses = rn_passes();
+    int rc;
+#define SLB_TRY(call)                \
+    do {                             \
+        rc = (call);                 \
+        if (rc != SLB_OK) return rc; \
+    } while (0)
+    // conv (as a GEMM over planes `a` with M rows) + BatchNorm + epilogue
+    auto conv = [&](const SlbConvBn& c, const uint16_t* a, int64_t M, int epi, const float* residual, float* o32, uint16_t* opl) {
+        return slb_gemm_split(a, c.w, fmt, M, c.cout, slb_conv_k(c.cin, c.ksize), kAlpha, c.shift, residual, nullptr, c.scale, epi,
+                              kPasses, o32, opl, stream);
+    };
+    for (int i = 0; i < w->n_convs; ++i)
+        SLB_REQUIRE(w->convs[i].w && w->convs[i].scale && w->convs[i].shift, SLB_EINVAL, "slb_rn_forward: convolution %d is incomplete", i);
+    const SlbConvBn* cv = w->convs;
+    SLB_REQUIRE(cv[0].cin == 3 && cv[0].ksize == 3 && cv[0].cout == wd / 2 && cv[2].cout == wd, SLB_EINVAL,
+                "slb_rn_forward: the stem does not match width %lld", (long long)wd);
+
+    // ---- stem ----
+    int64_t H = S / 2, M = B * H * H;
+    SLB_TRY(slb_im2col_stem(img, B, S, fmt, col, stream));
+    SLB_TRY(conv(cv[0], col, M, SLB_EPI_RELU, nullptr, nullptr, t1));
+    SLB_TRY(slb_im2col3x3(t1, B, H, H, wd / 2, col, stream));
+    SLB_TRY(conv(cv[1], col, M, SLB_EPI_RELU, nullptr, nullptr, t2));
+    SLB_TRY(slb_im2col3x3(t2, B, H, H, wd / 2, col, stream));
+    SLB_TRY(conv(cv[2], col, M, SLB_EPI_RELU, nullptr, nullptr, x_nxt));
+    SLB_TRY(slb_avgpool2_planes(x_nxt, B, H, H, wd, fmt, x_cur, stream));
+    H /= 2;
+    M /= 4;
+    cv += 3;
+
+    // ---- bottlenecks ----
+    int64_t inpl = wd;
+    for (int li = 0; li < 4; ++li) {
+        const int64_t pl = wd << li;
+        for (int bi = 0; bi < w->blocks[li]; ++bi) {
+            const bool ds = bi == 0;
+            const int stride = (bi == 0 && li > 0) ? 2 : 1;
+            SLB_REQUIRE(cv[0].cin == inpl && cv[0].cout == pl && cv[0].ksize == 1 && cv[1].cin == pl && cv[1].cout == pl &&
+                            cv[1].ksize == 3 && cv[2].cin == pl && cv[2].cout == 4 * pl && cv[2].ksize == 1 &&
+                            (!ds || (cv[3].cin == inpl && cv[3].cout == 4 * pl && cv[3].ksize == 1)),
+                        SLB_EINVAL, "slb_rn_forward: stage %d bottleneck %d has unexpected convolution shapes", li + 1, bi);
+            SLB_TRY(conv(cv[0], x_cur, M, SLB_EPI_RELU, nullptr, nullptr, t1));
+            SLB_TRY(slb_im2col3x3(t1, B, H, H, pl, col, stream));
+            SLB_TRY(conv(cv[1], col, M, SLB_EPI_RELU, nullptr, nullptr, t2));
+            const uint16_t* main_in = t2;
+            const uint16_t* short_in = x_cur;
+            if (stride == 2) {
+                SLB_TRY(slb_avgpool2_planes(t2, B, H, H, pl, fmt, t3, stream));
+                SLB_TRY(slb_avgpool2_planes(x_cur, B, H, H, inpl, fmt, xp, stream));
+                main_in = t3;
+                short_in = xp;
+                H /= 2;
+                M /= 4;
+            }
+            if (ds) SLB_TRY(conv(cv[3], short_in, M, SLB_EPI_NONE, nullptr, f, nullptr));
+            // main + shortcut, ReLU: the shortcut is read from and the fp32 output written to the same buffer
+            SLB_TRY(conv(cv[2], main_in, M, SLB_EPI_ADD_RELU, f, f, x_nxt));
+            std::swap(x_cur, x_nxt);
+            cv += ds ? 4 : 3;
+            inpl = 4 * pl;
+        }
+    }
+
+    // ---- attention pool ----
+    const int64_t HW = H * H, T = HW + 1, dh = E / w->heads;
+    unsigned char* head = ws + L.head;
+    const size_t hs = align_up((size_t)B * E * 4);
+    uint16_t* q_planes = reinterpret_cast<uint16_t*>(head);
+    float* q32 = reinterpret_cast<float*>(head + hs);
+    uint16_t* pooled = reinterpret_cast<uint16_t*>(head + 2 * hs);
+    float* kv = reinterpret_cast<float*>(col);
+    uint16_t* tok = x_nxt;
+    SLB_TRY(slb_pool_tokens(f, w->pos, B, HW, E, fmt, tok, q_planes, stream));
+    SLB_TRY(slb_gemm_split(tok, w->w_kv, fmt, B * T, 2 * E, E, kAlpha, w->b_kv, nullptr, nullptr, nullptr, SLB_EPI_NONE, kPasses, kv, nullptr,
+                           stream));
+    SLB_TRY(slb_gemm_split(q_planes, w->w_q, fmt, B, E, E, kAlpha, w->b_q, nullptr, nullptr, nullptr, SLB_EPI_NONE, kPasses, q32, nullptr,
+                           stream));
+    SLB_TRY(slb_attention_small(q32, E, E, kv, kv + E, T * 2 * E, 2 * E, B, 1, T, w->heads, dh, 1.0f / sqrtf((float)dh), fmt, nullptr,
+                                pooled, stream));
+    SLB_TRY(slb_gemm_split(pooled, w->w_c, fmt, B, w->out_dim, E, kAlpha, w->b_c, nullptr, nullptr, nullptr, SLB_EPI_NONE, kPasses, out,
+                           nullptr, stream));
+#undef SLB_TRY
+    return SLB_OK;
+}

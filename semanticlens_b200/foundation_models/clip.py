@@ -4,7 +4,7 @@ side runs on the B200 kernels.
 The reference delegates to ``open_clip.create_model_and_transforms(url, **kwargs)``; ``open_clip`` is a third-party
 dependency that is not vendored (and there is no network here), so this class restates what that call provides for
 the image path: the model config of ``url``, the eval transform (Resize(bicubic) -> CenterCrop -> RGB -> ToTensor ->
-Normalize with the OpenAI mean/std) and the ``VisionTransformer`` forward. Weights come from ``state_dict=`` /
+Normalize with the OpenAI mean/std) and the ``VisionTransformer`` / ``ModifiedResNet`` forward. Weights come from ``state_dict=`` /
 ``checkpoint_path=`` (open_clip naming, ``visual.*``) or are randomly initialised (``load_weights=False`` in the
 reference's own tests does the same). The CLIP text tower (``encode_text``, causal transformer on the same kernels) and
 a BPE tokenizer in open_clip's scheme (``tokenize``; needs CLIP's merges file, ``bpe_path=``) serve
@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from .. import _native as N
+from . import rn
 from . import text as text_mod
 from . import vit
 from .base import AbstractVLM
@@ -33,7 +34,7 @@ class OpenClip(AbstractVLM):
     ----------
     url : str
         open_clip model name: "ViT-B-32", "ViT-B-32-quickgelu", "ViT-B-16", "ViT-L-14", "ViT-B-16-SigLIP2",
-        "ViT-L-16-SigLIP-256", ... (``vit.CONFIGS``).
+        "ViT-L-16-SigLIP-256", ... (``vit.CONFIGS``) or a ModifiedResNet "RN50", "RN101" (``rn.CONFIGS``).
     device : str or torch.device
         Where the tower lives; kernels need a CUDA device.
     **kwargs
@@ -43,10 +44,12 @@ class OpenClip(AbstractVLM):
     """
 
     def __init__(self, url, device="cpu", **kwargs):
-        if url not in vit.CONFIGS:
-            raise ValueError(f"unknown or unsupported open_clip image tower '{url}' (built: {sorted(vit.CONFIGS)})")
+        if url not in vit.CONFIGS and url not in rn.CONFIGS:
+            raise ValueError(f"unknown or unsupported open_clip image tower '{url}' "
+                             f"(built: {sorted(vit.CONFIGS) + sorted(rn.CONFIGS)})")
         self.url = url
-        self.cfg = vit.CONFIGS[url]
+        is_rn = url in rn.CONFIGS
+        self.cfg = rn.CONFIGS[url] if is_rn else vit.CONFIGS[url]
         sd = kwargs.pop("state_dict", None)
         given_sd = sd is not None
         bpe_path = kwargs.pop("bpe_path", None)
@@ -62,8 +65,8 @@ class OpenClip(AbstractVLM):
         if sd is None:
             if pretrained:
                 logger.warning("pretrained='%s' cannot be downloaded here; using random weights (seed %d)", pretrained, seed)
-            sd = vit.random_state_dict(self.cfg, seed)
-        self.model = vit.VitTower(self.cfg, sd, device, fmt)
+            sd = rn.random_state_dict(self.cfg, seed) if is_rn else vit.random_state_dict(self.cfg, seed)
+        self.model = rn.RnTower(self.cfg, sd, device, fmt) if is_rn else vit.VitTower(self.cfg, sd, device, fmt)
         # text side: built lazily (encode_text / tokenize), only for the CLIP towers
         self._text_sd = {k: v for k, v in sd.items() if not k.startswith("visual.")} if ckpt or given_sd else None
         self._text_seed = seed
@@ -74,7 +77,7 @@ class OpenClip(AbstractVLM):
         self._pin_next = 0
 
     def __repr__(self):
-        return f"{self.__class__.__name__}(url='{self.url}', model=VitTower[B200])"
+        return f"{self.__class__.__name__}(url='{self.url}', model={type(self.model).__name__}[B200])"
 
     @property
     def device(self):

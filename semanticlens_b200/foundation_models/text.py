@@ -47,6 +47,10 @@ TEXT_CONFIGS = {
     "ViT-B-16-quickgelu": TextConfig("ViT-B-16-quickgelu", 77, 49408, 512, 12, 8, 512, act="quick_gelu"),
     "ViT-L-14": TextConfig("ViT-L-14", 77, 49408, 768, 12, 12, 768),
     "ViT-L-14-quickgelu": TextConfig("ViT-L-14-quickgelu", 77, 49408, 768, 12, 12, 768, act="quick_gelu"),
+    "RN50": TextConfig("RN50", 77, 49408, 512, 12, 8, 1024),
+    "RN50-quickgelu": TextConfig("RN50-quickgelu", 77, 49408, 512, 12, 8, 1024, act="quick_gelu"),
+    "RN101": TextConfig("RN101", 77, 49408, 512, 12, 8, 512),
+    "RN101-quickgelu": TextConfig("RN101-quickgelu", 77, 49408, 512, 12, 8, 512, act="quick_gelu"),
 }
 
 

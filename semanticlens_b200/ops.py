@@ -312,6 +312,63 @@ def attention_planes(qkv_planes: torch.Tensor, B: int, heads: int, fmt: int | No
 # ------------------------------------------------------------------------------------------------
 # analyze: scores
 # ------------------------------------------------------------------------------------------------
+# ---- CLIP ModifiedResNet pieces (channels-last split planes) ---------------------------------------------------------
+def conv_k(cin: int, ksize: int) -> int:
+    return int(N.load().slb_conv_k(cin, ksize))
+
+
+def im2col_stem(img: torch.Tensor, fmt: int = N.PLANE_F16) -> torch.Tensor:
+    """(B,3,S,S) fp32 -> planes (2, B*(S/2)^2, 64) of the stem's 3x3 / stride 2 / pad 1 convolution."""
+    lib = N.load(require_device=True)
+    N.require_cuda(img, "img")
+    img = img.float().contiguous()
+    B, _, S, _ = img.shape
+    out = torch.empty((2, B * (S // 2) ** 2, 64), dtype=PLANE_DTYPES[fmt], device=img.device)
+    with _dev_guard(img):
+        N.check(lib.slb_im2col_stem(img.data_ptr(), B, S, fmt, out.data_ptr(), N.stream_ptr(img.device)), "slb_im2col_stem")
+    return out
+
+
+def im2col3x3(planes: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+    """channels-last planes (2, B*H*W, C) -> (2, B*H*W, conv_k(C, 3)) of a 3x3 / stride 1 / pad 1 convolution."""
+    lib = N.load(require_device=True)
+    N.require_cuda(planes, "planes")
+    assert planes.ndim == 3 and planes.shape[0] == 2 and planes.shape[1] == B * H * W and planes.is_contiguous()
+    C = planes.shape[2]
+    out = torch.empty((2, B * H * W, conv_k(C, 3)), dtype=planes.dtype, device=planes.device)
+    with _dev_guard(planes):
+        N.check(lib.slb_im2col3x3(planes.data_ptr(), B, H, W, C, out.data_ptr(), N.stream_ptr(planes.device)), "slb_im2col3x3")
+    return out
+
+
+def avgpool2_planes(planes: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+    lib = N.load(require_device=True)
+    N.require_cuda(planes, "planes")
+    assert planes.ndim == 3 and planes.shape[0] == 2 and planes.shape[1] == B * H * W and planes.is_contiguous()
+    C = planes.shape[2]
+    fmt = N.PLANE_F16 if planes.dtype == torch.float16 else N.PLANE_BF16
+    out = torch.empty((2, B * (H // 2) * (W // 2), C), dtype=planes.dtype, device=planes.device)
+    with _dev_guard(planes):
+        N.check(lib.slb_avgpool2_planes(planes.data_ptr(), B, H, W, C, fmt, out.data_ptr(), N.stream_ptr(planes.device)),
+                "slb_avgpool2_planes")
+    return out
+
+
+def pool_tokens(x: torch.Tensor, pos: torch.Tensor, fmt: int = N.PLANE_F16):
+    """x (B, HW, C) fp32, pos (HW+1, C) -> (token planes (2, B*(HW+1), C), query planes (2, B, C))."""
+    lib = N.load(require_device=True)
+    N.require_cuda(x, "x")
+    x, pos = x.float().contiguous(), pos.float().contiguous()
+    B, HW, C = x.shape
+    assert tuple(pos.shape) == (HW + 1, C)
+    tok = torch.empty((2, B * (HW + 1), C), dtype=PLANE_DTYPES[fmt], device=x.device)
+    qry = torch.empty((2, B, C), dtype=PLANE_DTYPES[fmt], device=x.device)
+    with _dev_guard(x):
+        N.check(lib.slb_pool_tokens(x.data_ptr(), pos.data_ptr(), B, HW, C, fmt, tok.data_ptr(), qry.data_ptr(),
+                                    N.stream_ptr(x.device)), "slb_pool_tokens")
+    return tok, qry
+
+
 def _pad64(d: int) -> int:
     return (d + 63) // 64 * 64
 

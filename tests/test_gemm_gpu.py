@@ -37,6 +37,23 @@ def test_gemm_split3_accuracy(ops, M, N, K, fmt, tol):
     assert rel_err(out, want) < tol
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 512, 3072), (98, 128, 1152), (1000, 768, 768), (129, 72, 64), (16448, 1024, 256)])
+def test_gemm_split_accumulator_mode(ops, M, N, K):
+    """SLB_PASSES_SPLIT_ACC: cross terms in their own accumulator -> a third of the truncating adds into the large one."""
+    from semanticlens_b200._native import PASSES_SPLIT_ACC
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    ap, wp = ops.split_planes(a, 0, SA), ops.split_planes(w, 0, SW)
+    want = a.double() @ w.double().T
+    fast, _ = ops.gemm_split(ap, wp, alpha=1 / (SA * SW))
+    acc, _ = ops.gemm_split(ap, wp, alpha=1 / (SA * SW), passes=PASSES_SPLIT_ACC)
+    assert rel_err(acc, want) < 8e-6
+    if K >= 1024:
+        assert rel_err(acc, want) < 0.6 * rel_err(fast, want)
+
+
 def test_gemm_unscaled_planes_lose_only_subnormal_bits(ops):
     """Without the per-tensor scale the lo plane of small weights underflows into fp16 subnormals: still < 1e-5."""
     a = torch.randn(300, 256, device="cuda")

@@ -1,0 +1,74 @@
+"""CPU checks of the ModifiedResNet oracle (oracle/rn_port.py) and of the host-side weight layout the B200 tower uses."""
+
+import torch
+import torch.nn.functional as F
+
+from oracle import rn_port as rp
+
+
+def test_block_plan_matches_open_clip_rn50():
+    plan = rp.block_plan(rp.CONFIGS["RN50"])
+    assert len(plan) == 16
+    assert [p for p, *_ in plan][:4] == ["visual.layer1.0.", "visual.layer1.1.", "visual.layer1.2.", "visual.layer2.0."]
+    # only the first bottleneck of a stage changes resolution / width and carries a downsample branch
+    assert [(s, ds) for _p, _i, _pl, s, ds in plan if ds] == [(1, True), (2, True), (2, True), (2, True)]
+    assert plan[-1][1:3] == (2048, 512)
+    sd = rp.init_weights(rp.CONFIGS["RN50"])
+    assert sd["visual.layer4.0.downsample.0.weight"].shape == (2048, 1024, 1, 1)
+    assert sd["visual.attnpool.positional_embedding"].shape == (50, 2048)
+    assert sd["visual.attnpool.c_proj.weight"].shape == (1024, 2048)
+
+
+def test_attention_pool_equals_explicit_softmax():
+    cfg = rp.CONFIGS["RN-tiny-test"]
+    sd = {k: v.double() for k, v in rp.init_weights(cfg).items()}
+    x = torch.randn(2, 2048, 2, 2, dtype=torch.float64)
+    got = rp.attnpool(sd, cfg, x)
+    a = "visual.attnpool."
+    tok = x.reshape(2, 2048, 4).permute(0, 2, 1)
+    tok = torch.cat([tok.mean(1, keepdim=True), tok], 1) + sd[a + "positional_embedding"]
+    q = tok[:, :1] @ sd[a + "q_proj.weight"].T + sd[a + "q_proj.bias"]
+    k = tok @ sd[a + "k_proj.weight"].T + sd[a + "k_proj.bias"]
+    v = tok @ sd[a + "v_proj.weight"].T + sd[a + "v_proj.bias"]
+    H, dh = cfg.heads, 2048 // cfg.heads
+    qh, kh, vh = (t.view(2, -1, H, dh).transpose(1, 2) for t in (q, k, v))
+    o = (torch.softmax(qh @ kh.transpose(-1, -2) * dh**-0.5, -1) @ vh).transpose(1, 2).reshape(2, 2048)
+    want = o @ sd[a + "c_proj.weight"].T + sd[a + "c_proj.bias"]
+    assert torch.allclose(got, want, rtol=1e-10, atol=1e-12)
+
+
+def test_fp32_port_tracks_fp64():
+    cfg = rp.CONFIGS["RN-small-test"]
+    sd = rp.init_weights(cfg)
+    img = torch.randn(2, 3, cfg.image_size, cfg.image_size, generator=torch.Generator().manual_seed(1))
+    o32, o64 = rp.encode_image(sd, cfg, img), rp.encode_image(sd, cfg, img, dtype=torch.float64)
+    assert o32.shape == (2, cfg.embed_dim)
+    assert ((o32.double() - o64).abs().max() / o64.abs().max()).item() < 5e-6
+
+
+def test_channels_last_im2col_layout_reproduces_conv2d():
+    """The tower multiplies im2col rows, column (ky*3 + kx)*C + c, with weights permuted to (cout, ky, kx, cin), and
+    folds BatchNorm into a scale and shift: restated with torch on the CPU, that equals conv2d + batch_norm."""
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 8, 6, 5, generator=g, dtype=torch.float64)
+    wt = torch.randn(16, 8, 3, 3, generator=g, dtype=torch.float64)
+    gamma, beta, mean, var = (torch.randn(16, generator=g, dtype=torch.float64) for _ in range(4))
+    var = var.abs() + 0.5
+    cols = F.unfold(x, 3, padding=1).view(2, 8, 9, 30).permute(0, 3, 2, 1).reshape(60, 72)
+    mat = wt.permute(0, 2, 3, 1).reshape(16, 72)
+    scale = gamma / torch.sqrt(var + rp.BN_EPS)
+    got = (cols @ mat.T) * scale + (beta - mean * scale)
+    want = F.batch_norm(F.conv2d(x, wt, padding=1), mean, var, gamma, beta, False, 0.0, rp.BN_EPS)
+    assert torch.allclose(got, want.permute(0, 2, 3, 1).reshape(60, 16), rtol=1e-10, atol=1e-10)
+
+
+def test_tower_host_config_matches_oracle_config():
+    from semanticlens_b200.foundation_models import rn
+
+    for name in ("RN50", "RN101"):
+        o, c = rp.CONFIGS[name], rn.CONFIGS[name]
+        assert (o.image_size, o.width, o.layers, o.heads, o.embed_dim) == (c.image_size, c.width, c.layers, c.heads, c.embed_dim)
+        assert sorted(rn.state_dict_keys(c)) == sorted(rp.init_weights(o))
+        assert rn.block_plan(c) == rp.block_plan(o)
+        assert abs(rn.flops_per_image(c) - rp.flops_per_image(o)) < 1
+    assert len(rn.conv_names(rn.CONFIGS["RN50"])) == 3 + sum(3 * n + 1 for n in (3, 4, 6, 3))
