@@ -207,6 +207,18 @@ int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, int plane
 int slb_u8_to_f32_norm(const uint8_t* img, int64_t B, int64_t Cc, int64_t n_pix, const float* mean3,
                        const float* std3, float* out, void* stream);
 
+/* Bicubic resize + crop of one RGB image, bit-exact with Pillow's ImagingResample (what torchvision
+ * Resize(S, BICUBIC) + CenterCrop(S) of the open_clip eval transform run per PIL image; clip.py:157-160):
+ * src_hwc (h, w, 3) u8 is resampled to out_w x out_h (Keys a = -0.5 kernel, support scaled when shrinking, 22-bit
+ * fixed-point coefficients, horizontal pass into an 8-bit intermediate, then vertical), of which only the window
+ * [crop_top, +crop_h) x [crop_left, +crop_w) is produced, channels first: dst_chw (3, crop_h, crop_w) u8.
+ * workspace: 256-byte aligned, >= slb_resize_workspace_bytes(...) (0 on bad sizes). */
+size_t slb_resize_workspace_bytes(int64_t h, int64_t w, int64_t out_w, int64_t out_h, int64_t crop_left, int64_t crop_top,
+                                  int64_t crop_w, int64_t crop_h);
+int slb_resize_bicubic_u8(const uint8_t* src_hwc, int64_t h, int64_t w, int64_t out_w, int64_t out_h, int64_t crop_left,
+                          int64_t crop_top, int64_t crop_w, int64_t crop_h, uint8_t* dst_chw, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* (B,3,S,S) fp32 -> im2col rows as split planes [2][B*(S/P)^2][slb_patch_k(P)] (row = (b, gy, gx), col = (c, py, px),
  * zero padded from 3*P*P up to a multiple of 64), so that the patch-embedding conv (kernel = stride = P, even P) is
  * one slb_gemm_split against the flattened, equally padded conv weight. */

@@ -68,25 +68,32 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restric
 }
 
 // ---- 3x3 / stride 1 / pad 1 im2col over channels-last planes: pure 16-byte moves ------------------------------------
-// grid.y = plane; one thread = one chunk of 8 channels of one tap of one output pixel.
-__global__ void __launch_bounds__(256) im2col3x3_kernel(const uint16_t* __restrict__ in, int64_t M, int H, int W, int C8, int K8,
-                                                        uint16_t* __restrict__ out) {
+// grid.y = plane. One warp owns an output pixel (row of the im2col matrix) at a time: the pixel is decoded once, the
+// lanes sweep the row's 16-byte chunks (tap-major, channels contiguous), so stores are fully coalesced and loads are
+// contiguous within a tap.
+template <bool kPow2>
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const uint16_t* __restrict__ in, int M, int H, int W, int C8, int c8_shift,
+                                                        int K8, uint16_t* __restrict__ out) {
     const uint4* src = reinterpret_cast<const uint4*>(in) + (int64_t)blockIdx.y * M * C8;
     uint4* dst = reinterpret_cast<uint4*>(out) + (int64_t)blockIdx.y * M * K8;
-    const int64_t n = M * K8;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int kc = (int)(i % K8);
-        const int64_t m = i / K8;
-        const int tap = kc / C8;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (tap < 9) {
-            const int c8 = kc - tap * C8;
-            const int x = (int)(m % W);
-            const int y = (int)((m / W) % H);
-            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(src + (m + (int64_t)(yy - y) * W + (xx - x)) * C8 + c8);
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
+        const int x = m % W;
+        const int y = (m / W) % H;
+        const uint4* row_src = src + (int64_t)m * C8;
+        uint4* row_dst = dst + (int64_t)m * K8;
+        for (int kc = lane; kc < K8; kc += 32) {
+            const int tap = kPow2 ? (kc >> c8_shift) : (kc / C8);
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (tap < 9) {
+                const int c8 = kc - tap * C8;
+                const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                if ((unsigned)(y + dy) < (unsigned)H && (unsigned)(x + dx) < (unsigned)W)
+                    v = __ldg(row_src + (dy * W + dx) * C8 + c8);
+            }
+            row_dst[kc] = v;
         }
-        dst[i] = v;
     }
 }
 
@@ -245,9 +252,18 @@ extern "C" int slb_im2col3x3(const uint16_t* in_planes, int64_t B, int64_t H, in
     SLB_REQUIRE(((uintptr_t)in_planes % 16) == 0 && ((uintptr_t)out_planes % 16) == 0, SLB_EINVAL, "slb_im2col3x3: misaligned");
     const int64_t M = B * H * W, K = slb_conv_k(C, 3);
     SlbProfScope prof("K4 im2col", stream, 0.0, 4.0 * (double)M * (double)(K + C));
-    dim3 grid(grid_for(M * (K / 8), 256), 2);
-    im2col3x3_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_planes, M, (int)H, (int)W, (int)(C / 8), (int)(K / 8),
-                                                                         out_planes);
+    SLB_REQUIRE(M < (1ll << 31) / 8, SLB_EUNSUPPORTED, "slb_im2col3x3: too many pixels (%lld)", (long long)M);
+    const int C8 = (int)(C / 8);
+    const bool pow2 = (C8 & (C8 - 1)) == 0;
+    int shift = 0;
+    while ((1 << shift) < C8) ++shift;
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(slb_ceil_div(M, 8), (int64_t)slb_sm_count() * 32)), 2);
+    if (pow2)
+        im2col3x3_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_planes, (int)M, (int)H, (int)W, C8, shift,
+                                                                                   (int)(K / 8), out_planes);
+    else
+        im2col3x3_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_planes, (int)M, (int)H, (int)W, C8, shift,
+                                                                                    (int)(K / 8), out_planes);
     SLB_LAUNCH_OK("im2col3x3");
     return SLB_OK;
 }

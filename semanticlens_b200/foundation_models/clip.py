@@ -14,6 +14,7 @@ a BPE tokenizer in open_clip's scheme (``tokenize``; needs CLIP's merges file, `
 from __future__ import annotations
 
 import logging
+import os
 
 import numpy as np
 import torch
@@ -96,15 +97,19 @@ class OpenClip(AbstractVLM):
     def preprocess(self, img) -> torch.Tensor:
         """PIL image(s) / uint8 (B,3,H,W) tensor(s) -> normalised fp32 batch on ``device`` (reference :137-163).
 
-        Resize/crop (only needed when the input is not already S x S) use PIL on the host exactly like the
-        reference's transform; ToTensor + Normalize run on the GPU (K3).
+        RGB PIL images are uploaded as they are and resized / centre-cropped on the GPU (slb_resize_bicubic_u8: Pillow's
+        bicubic resample byte for byte); other PIL modes are resized in their own mode by PIL on the host like the
+        reference's transform does, then converted. ToTensor + Normalize run on the GPU (K3).
         """
         from .. import ops
 
-        u8 = self._to_u8_batch(img)
         dev = self.device
         if dev.type != "cuda":
             raise N.SlbError("OpenClip.preprocess runs on the GPU: move the model with .to('cuda') first")
+        items = img if isinstance(img, (list, tuple)) else [img]
+        if items and not isinstance(items[0], torch.Tensor) and os.environ.get("SLB_HOST_RESIZE") != "1":
+            return ops.u8_to_f32_norm(self._pil_batch_on_device(items), self.cfg.mean, self.cfg.std)
+        u8 = self._to_u8_batch(img)
         if not u8.is_cuda:
             if not u8.is_pinned():
                 # two pinned staging buffers used alternately: a buffer is rewritten only after the asynchronous copy
@@ -125,6 +130,23 @@ class OpenClip(AbstractVLM):
             else:
                 u8 = u8.to(dev, non_blocking=True)
         return ops.u8_to_f32_norm(u8, self.cfg.mean, self.cfg.std)
+
+    def _pil_batch_on_device(self, items) -> torch.Tensor:
+        """PIL images -> (n, 3, S, S) u8 on the GPU; Resize(S, bicubic) + CenterCrop(S) of RGB images run there."""
+        from .. import ops
+
+        S, dev = self.cfg.image_size, self.device
+        out = torch.empty((len(items), 3, S, S), dtype=torch.uint8, device=dev)
+        for i, im in enumerate(items):
+            if im.mode != "RGB":
+                out[i].copy_(torch.from_numpy(_pil_to_chw_u8(im, S)), non_blocking=True)
+                continue
+            hwc = torch.from_numpy(np.array(im, dtype=np.uint8)).to(dev, non_blocking=True)
+            if im.size == (S, S):
+                out[i].copy_(hwc.permute(2, 0, 1))
+            else:
+                ops.resize_center_crop_u8(hwc, S, out=out[i])
+        return out
 
     def _to_u8_batch(self, img) -> torch.Tensor:
         S = self.cfg.image_size

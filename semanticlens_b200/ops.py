@@ -257,6 +257,34 @@ def u8_to_f32_norm(u8: torch.Tensor, mean, std) -> torch.Tensor:
     return out
 
 
+def resized_size(w: int, h: int, S: int) -> tuple[int, int]:
+    """torchvision ``Resize(S)``: the shorter side becomes S, the longer ``int(S * long / short)``."""
+    if w <= h:
+        return S, max(S, int(S * h / w))
+    return max(S, int(S * w / h)), S
+
+
+def resize_center_crop_u8(img_hwc: torch.Tensor, S: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(h, w, 3) u8 CUDA -> (3, S, S) u8: Resize(S, bicubic) + CenterCrop(S), byte-identical to Pillow / torchvision."""
+    lib = N.load(require_device=True)
+    N.require_cuda(img_hwc, "img_hwc")
+    assert img_hwc.dtype == torch.uint8 and img_hwc.ndim == 3 and img_hwc.shape[2] == 3
+    img_hwc = img_hwc.contiguous()
+    h, w = int(img_hwc.shape[0]), int(img_hwc.shape[1])
+    nw, nh = resized_size(w, h, S)
+    left, top = int(round((nw - S) / 2.0)), int(round((nh - S) / 2.0))
+    if out is None:
+        out = torch.empty((3, S, S), dtype=torch.uint8, device=img_hwc.device)
+    assert out.is_contiguous() and tuple(out.shape) == (3, S, S) and out.device == img_hwc.device
+    need = lib.slb_resize_workspace_bytes(h, w, nw, nh, left, top, S, S)
+    ws = torch.empty(max(need, 1), dtype=torch.uint8, device=img_hwc.device)
+    with _dev_guard(img_hwc):
+        rc = lib.slb_resize_bicubic_u8(img_hwc.data_ptr(), h, w, nw, nh, left, top, S, S, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       N.stream_ptr(img_hwc.device))
+    N.check(rc, "slb_resize_bicubic_u8")
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor | None, eps: float, fmt: int | None = None):
     """Row LayerNorm of a contiguous (rows, cols) fp32 tensor -> fp32 (fmt None) or split planes (2, rows, cols) at
     N.ACT_PLANE_SCALE."""
