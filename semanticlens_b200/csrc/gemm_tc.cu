@@ -28,6 +28,10 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 2 B = one 128-byte swizzle row
 constexpr int kEpiWarps = 8;  // two warps per TMEM lane quarter, interleaved over the 32-column chunks
 constexpr int kThreads = (2 + kEpiWarps) * 32;
+// per-warp transpose tile of the epilogue (see drain_chunk)
+constexpr int kTileStride = 20;                // floats per tile row: 16 columns + 4 pad (float4-aligned, conflict-free writes)
+constexpr int kTileFloats = 32 * kTileStride;  // per epilogue warp
+constexpr int kEpiTileBytes = kEpiWarps * kTileFloats * 4;
 
 template <int BN>
 struct Cfg {
@@ -38,7 +42,7 @@ struct Cfg {
     static constexpr int kWBytes = 2 * BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kWBytes;
     static constexpr int kTmemCols = 4 * BN;  // [buffer][main | cross][BN]: the cross half is used by SLB_PASSES_SPLIT_ACC only
-    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiTileBytes;
 };
 
 struct GemmParams {
@@ -74,10 +78,28 @@ __device__ __forceinline__ float act_apply(float v, int epi) {
     }
 }
 
-// Epilogue of one 32-column chunk of an accumulator row: TMEM -> registers -> alpha / scale / bias / activation /
-// residual -> global (fp32 and/or split planes at the activation scale). Thread = one output row m, columns [nb, nb + 32).
-__device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr, int64_t m, bool row_ok, float rs, int64_t nb,
-                                            int fmt, uint32_t cross_off = 0) {
+// Epilogue of one 32 x 32 chunk of an accumulator (a warp's 32 TMEM lanes = 32 output rows, 32 columns):
+// TMEM -> registers (thread = row) -> alpha / row scale -> per-warp shared-memory tile -> registers (4 lanes = 16
+// consecutive columns of a row, 8 rows per pass) -> column scale / bias / activation / residual -> global. The transpose
+// makes every global access of the warp cover 64 contiguous bytes per row instead of one 128-byte line per THREAD
+// (32 lines per instruction): the short-K GEMMs are pure epilogue and were LSU-bound at ~2.5 TB/s before it.
+__device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr, int64_t m_warp, int lane, float rs, int64_t nb,
+                                            int fmt, float* tile, uint32_t cross_off = 0) {
+    const int c4 = (lane & 3) * 4;  // this lane's 4 columns within a 16-column half
+    const int r8 = lane >> 2;       // its row within a pass of 8 rows
+    // the shortcut values are fetched first (8 independent 16-byte loads per lane): their latency hides behind the
+    // TMEM load and the transpose, and no store of this chunk can be ordered before them (residual may alias out_f32)
+    float4 res[2][4];
+    if (p.residual && nb < p.N) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int64_t m = m_warp + it * 8 + r8, n = nb + half * 16 + c4;
+                res[half][it] = (m < p.M && n < p.N) ? *reinterpret_cast<const float4*>(p.residual + m * p.N + n)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+    }
     uint32_t raw[32];
     float v[32];
     slb_tmem_ld_32x32(taddr, raw);
@@ -92,63 +114,54 @@ __device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr,
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
     }
-    if (!(row_ok && nb < p.N)) return;
-    const int ncols = (int)min((int64_t)32, p.N - nb);  // multiple of 8
+    if (nb >= p.N) return;  // warp-uniform
     if (p.row_scale) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= rs;
     }
-    if (p.col_scale) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < ncols) v[j] *= __ldg(p.col_scale + nb + j);
-    }
-    if (p.bias) {
+    for (int half = 0; half < 2; ++half) {
+        __syncwarp();  // the previous half has been read
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < ncols) v[j] += __ldg(p.bias + nb + j);
-    }
-    if (p.epilogue != SLB_EPI_NONE && p.epilogue != SLB_EPI_ADD_RELU) {
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(tile + lane * kTileStride + 4 * q) =
+                make_float4(v[half * 16 + 4 * q], v[half * 16 + 4 * q + 1], v[half * 16 + 4 * q + 2], v[half * 16 + 4 * q + 3]);
+        __syncwarp();
+        const int64_t n = nb + half * 16 + c4;  // N % 8 == 0 and n % 4 == 0: the 4 columns are valid together
+        if (n >= p.N) continue;
+        float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.col_scale) cs = __ldg(reinterpret_cast<const float4*>(p.col_scale + n));
+        if (p.bias) bs = __ldg(reinterpret_cast<const float4*>(p.bias + n));
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], p.epilogue);
-    }
-    if (p.residual) {
-        const float4* r4 = reinterpret_cast<const float4*>(p.residual + m * p.N + nb);
+        for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + r8;
+            const int64_t m = m_warp + rr;
+            if (m >= p.M) continue;
+            const float4 x = *reinterpret_cast<const float4*>(tile + rr * kTileStride + c4);
+            float o[4] = {x.x, x.y, x.z, x.w};
+            if (p.col_scale) { o[0] *= cs.x; o[1] *= cs.y; o[2] *= cs.z; o[3] *= cs.w; }
+            o[0] += bs.x; o[1] += bs.y; o[2] += bs.z; o[3] += bs.w;
+            if (p.epilogue != SLB_EPI_NONE && p.epilogue != SLB_EPI_ADD_RELU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (4 * j < ncols) {
-                float4 r = r4[j];
-                v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+                for (int j = 0; j < 4; ++j) o[j] = act_apply(o[j], p.epilogue);
             }
-        }
-    }
-    if (p.epilogue == SLB_EPI_ADD_RELU) {
+            const int64_t off = m * p.N + n;
+            if (p.residual) {
+                const float4 r = res[half][it];
+                o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+            }
+            if (p.epilogue == SLB_EPI_ADD_RELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-    }
-    if (p.out_f32) {
-        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + m * p.N + nb);
+                for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.0f);
+            }
+            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
+            if (p.out_planes) {
+                uint16_t h[4], l[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (4 * j < ncols) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
-    if (p.out_planes) {
-        uint16_t* ph = p.out_planes + m * p.N + nb;
-        uint16_t* pl = ph + p.M * p.N;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (8 * j < ncols) {
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint16_t h0, l0, h1, l1;
-                    slb_split2_act(v[8 * j + 2 * q], fmt, h0, l0);
-                    slb_split2_act(v[8 * j + 2 * q + 1], fmt, h1, l1);
-                    h[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                    l[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                }
-                *reinterpret_cast<uint4*>(ph + 8 * j) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(pl + 8 * j) = make_uint4(l[0], l[1], l[2], l[3]);
+                for (int j = 0; j < 4; ++j) slb_split2_act(o[j], fmt, h[j], l[j]);
+                *reinterpret_cast<uint2*>(p.out_planes + off) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+                *reinterpret_cast<uint2*>(p.out_planes + p.M * p.N + off) =
+                    make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
             }
         }
     }
@@ -255,6 +268,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int acc = 0;
         uint32_t acc_phase = 0;
         const int fmt = p.fmt;
+        float* tile = reinterpret_cast<float*>(smem + (size_t)C::kStages * C::kStageBytes + 256) + (warp - 2) * kTileFloats;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
             slb_mbar_wait(&tfull[acc], acc_phase);
@@ -265,7 +279,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll 1
             for (int c = chunk0; c < BN / 32; c += kEpiWarps / 4) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
-                drain_chunk(p, taddr, m, row_ok, rs, (int64_t)n0 + c * 32, fmt, p.split_acc ? BN : 0);
+                drain_chunk(p, taddr, (int64_t)m0 + quarter * 32, lane, rs, (int64_t)n0 + c * 32, fmt, tile, p.split_acc ? BN : 0);
             }
             slb_tc_fence_before();
             __syncwarp();
@@ -308,7 +322,7 @@ struct CfgPair {
     static constexpr int kWBytes = 2 * (BN / 2) * BK * 2;  // this CTA's half of the W rows, both planes
     static constexpr int kStageBytes = kABytes + kWBytes;  // 48 / 64 KB
     static constexpr int kTmemCols = 2 * PBN;              // [buffer][BN]
-    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 + 256;
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 + 256 + kEpiTileBytes;
 };
 
 // bounded wait: a protocol error must abort the kernel (trap -> CUDA error), never hang the device. On timeout
@@ -436,6 +450,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int acc = 0;
         uint32_t acc_phase = 0;
         const int fmt = p.fmt;
+        float* tile = reinterpret_cast<float*>(smem + (size_t)C::kStages * C::kStageBytes + 256) + (warp - 2) * kTileFloats;
         for (int t = cluster_id; t < total; t += num_clusters) {
             const int m0 = (t / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (t % tiles_n) * BN;
             mbar_wait_bounded(&tfull[acc], acc_phase, p.dbg, 4, t, -1, acc);
@@ -446,7 +461,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll 1
             for (int c = chunk0; c < BN / 32; c += kEpiWarps / 4) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32);
-                drain_chunk(p, taddr, m, row_ok, rs, (int64_t)n0 + c * 32, fmt);
+                drain_chunk(p, taddr, (int64_t)m0 + quarter * 32, lane, rs, (int64_t)n0 + c * 32, fmt, tile);
             }
             slb_tc_fence_before();
             __syncwarp();
