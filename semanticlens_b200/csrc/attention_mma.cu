@@ -289,8 +289,12 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                  : "r"(slb_smem_u32(smem_row)));
 }
 
-template <int NW, int MINB>
+// kSplit (a tail of <= 16 query rows, e.g. the class token left over by the tcgen05 tiles of a 257-token tower): the NW
+// warps share the one 16-row query tile and split every 64-key block four ways (warp w takes keys [16w, 16w + 16) of
+// each block), then merge their (max, sum, O) through shared memory — the serial chain per CTA is a quarter as long.
+template <int NW, int MINB, bool kSplit = false>
 __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPlanesParams p) {
+    static_assert(!kSplit || NW == 4, "key splitting assumes 4 warps x 16 keys per block");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Tkp = p.Tkp;
     // one stage = a 64-key block of Kh, Kl, Vh, Vl ([64][72] halves each); two stages when the sequence has several blocks:
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
     };
     stage(0);
 
-    const int r0 = p.q_row0 + blockIdx.y * (16 * NW) + warp * 16;
+    const int r0 = kSplit ? p.q_row0 : p.q_row0 + blockIdx.y * (16 * NW) + warp * 16;
     const int g = lane >> 2, t4 = lane & 3;
     // ---- Q fragments straight from the planes (overlaps the copies above) ----
     uint32_t qh[4][4], ql[4][4];
@@ -379,7 +383,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             float sm_[4] = {0.f, 0.f, 0.f, 0.f};
-            if (nt < nkt) {
+            const bool mine = !kSplit || (nt >> 1) == warp;
+            if (nt < nkt && mine) {
                 // matrices: (keys nt*8.., d = ks2*32 + j*8 ..): j = 0,1 -> k-step 2*ks2 (b0, b1); j = 2,3 -> k-step 2*ks2 + 1
                 const size_t roff = (size_t)(nt * 8 + lm_r) * kKPad + lm_j * 8;
 #pragma unroll
@@ -397,12 +402,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) s[nt][j] = sm_[j] * sc_main;
-            if (need_mask) {  // block-uniform: only the last key block (padding) and causal blocks on / above the diagonal
+            if (need_mask || kSplit) {  // block-uniform: the last key block (padding), causal blocks on / above the diagonal
                 const int col = kb0 + nt * 8 + t4 * 2;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int c = col + (j & 1);
-                    const bool ok = nt < nkt && c < p.T && (!p.causal || c <= r0 + g + (j >> 1) * 8);
+                    const bool ok = mine && nt < nkt && c < p.T && (!p.causal || c <= r0 + g + (j >> 1) * 8);
                     if (!ok) s[nt][j] = -INFINITY;
                 }
             }
@@ -430,7 +435,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float e = exp2f(s[nt][j] - m_run[j >> 1]);
+                // (a warp of the split variant may not have seen a valid key yet: keep exp2(-inf - -inf) out)
+                const float mr = kSplit && m_run[j >> 1] == -INFINITY ? 0.f : m_run[j >> 1];
+                const float e = exp2f(s[nt][j] - mr);
                 s[nt][j] = e;
                 rs[j >> 1] += e;
             }
@@ -446,7 +453,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
         }
 #pragma unroll
         for (int kt = 0; kt < 4; ++kt) {
-            if (2 * kt < nkt) {
+            if (2 * kt < nkt && (!kSplit || kt == warp)) {
                 uint32_t ph[4], pl[4];
                 split_pair_unit(s[2 * kt][0], s[2 * kt][1], ph[0], pl[0]);
                 split_pair_unit(s[2 * kt][2], s[2 * kt][3], ph[1], pl[1]);
@@ -478,6 +485,58 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
     }
+    if constexpr (kSplit) {
+        // merge the four key quarters: xm / xl [warp][16 rows], xo [warp][16][64] in the (now idle) staging memory
+        __syncthreads();
+        float* xm = reinterpret_cast<float*>(smem_raw);
+        float* xl = xm + NW * 16;
+        float* xo = xl + NW * 16;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = g + r * 8;
+            if (t4 == 0) { xm[warp * 16 + row] = m_run[r]; xl[warp * 16 + row] = l_run[r]; }
+#pragma unroll
+            for (int dt = 0; dt < 8; ++dt)
+                *reinterpret_cast<float2*>(xo + ((size_t)warp * 16 + row) * 64 + dt * 8 + t4 * 2) =
+                    make_float2(om[dt][2 * r] + oc[dt][2 * r], om[dt][2 * r + 1] + oc[dt][2 * r + 1]);
+        }
+        __syncthreads();
+        const int row = tid >> 3, c0 = (tid & 7) * 8;  // 128 threads x 8 columns = the 16 x 64 tile
+        if (r0 + row >= p.T) return;
+        float mw[NW], mmax = -INFINITY, lsum = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { mw[w] = xm[w * 16 + row]; mmax = fmaxf(mmax, mw[w]); }
+        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const float sc = mw[w] == -INFINITY ? 0.f : exp2f(mw[w] - mmax);
+            lsum += xl[w * 16 + row] * sc;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += xo[((size_t)w * 16 + row) * 64 + c0 + j] * sc;
+        }
+        const float inv = kInvAct / (kPScale * lsum);
+        const int64_t base = (row0 + r0 + row) * p.W + (int64_t)h * kDh + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] *= inv;
+        if (p.out_f32) {
+            *reinterpret_cast<float4*>(p.out_f32 + base) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(p.out_f32 + base + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (p.out_hi) {
+            uint32_t hh[4], ll[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint16_t h0, l0, h1, l1;
+                slb_split2_act(o[2 * e], p.fmt, h0, l0);
+                slb_split2_act(o[2 * e + 1], p.fmt, h1, l1);
+                hh[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                ll[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+            *reinterpret_cast<uint4*>(p.out_hi + base) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(p.out_lo + base) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+        }
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int row = r0 + g + r * 8;
@@ -500,13 +559,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
     }
 }
 
-template <int NW, int MINB>
+template <int NW, int MINB, bool kSplit = false>
 int launch_attn_planes(const AttnPlanesParams& p, int64_t B, cudaStream_t st) {
     const size_t smem = (size_t)(p.Tkp > kKeyBlock ? 2 : 1) * 4 * kKeyBlock * kKPad * sizeof(__half);
     if (smem > 48 * 1024)
-        SLB_CUDA_OK(cudaFuncSetAttribute(attention_planes_kernel<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)(B * p.H), (unsigned)slb_ceil_div(p.T - p.q_row0, 16 * NW));
-    attention_planes_kernel<NW, MINB><<<grid, NW * 32, smem, st>>>(p);
+        SLB_CUDA_OK(cudaFuncSetAttribute(attention_planes_kernel<NW, MINB, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+    dim3 grid((unsigned)(B * p.H), kSplit ? 1u : (unsigned)slb_ceil_div(p.T - p.q_row0, 16 * NW));
+    attention_planes_kernel<NW, MINB, kSplit><<<grid, NW * 32, smem, st>>>(p);
     SLB_LAUNCH_OK("attention_planes");
     return SLB_OK;
 }
@@ -575,6 +635,7 @@ extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64
         if (rc != SLB_OK) return rc;
         if ((int64_t)n_tiles * 128 >= T) return SLB_OK;
         p.q_row0 = n_tiles * 128;
+        if (T - p.q_row0 <= 16) return launch_attn_planes<4, 3, true>(p, B, st);  // the class-token row: split the keys
     }
     return launch_attn_planes<4, 3>(p, B, st);  // 64 query rows per CTA, 3 CTAs / SM (168 registers, <= 72 KB smem)
 }

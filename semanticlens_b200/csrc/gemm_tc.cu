@@ -317,11 +317,12 @@ template <int PBN>
 struct CfgPair {
     static constexpr int BN = PBN;
     static constexpr int kAccBufs = 2;
+    static_assert(PBN == 128 || PBN == 192 || PBN == 256, "pair tiles are 256 x 128 / 192 / 256");
     static constexpr int kStages = PBN == 128 ? 4 : 3;
     static constexpr int kABytes = 2 * BM * BK * 2;        // this CTA's 128 A rows, both planes
     static constexpr int kWBytes = 2 * (BN / 2) * BK * 2;  // this CTA's half of the W rows, both planes
-    static constexpr int kStageBytes = kABytes + kWBytes;  // 48 / 64 KB
-    static constexpr int kTmemCols = 2 * PBN;              // [buffer][BN]
+    static constexpr int kStageBytes = kABytes + kWBytes;  // 48 / 56 / 64 KB
+    static constexpr int kTmemCols = PBN == 192 ? 512 : 2 * PBN;  // [buffer][BN]; allocations are powers of two
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 + 256 + kEpiTileBytes;
 };
 
@@ -638,9 +639,9 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
     static const int forced = [] {
         const char* e = getenv("SLB_GEMM_KERNEL");
         if (!e) return 0;
-        return !strcmp(e, "single") ? 1 : (!strcmp(e, "pair128") ? 2 : (!strcmp(e, "pair256") ? 3 : 0));
+        return !strcmp(e, "single") ? 1 : (!strcmp(e, "pair128") ? 2 : (!strcmp(e, "pair256") ? 3 : (!strcmp(e, "pair192") ? 4 : 0)));
     }();
-    int kind = 1;  // 1 single, 2 pair128, 3 pair256
+    int kind = 1;  // 1 single, 2 pair128, 3 pair256, 4 pair192
     if (M > BM) {
         const int64_t pairs = slb_sm_count() / 2;
         const int64_t t256 = slb_ceil_div(M, 2 * BM) * slb_ceil_div(N, 256);
@@ -648,15 +649,23 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
         const double eff256 = waves256 / (double)slb_ceil_div(t256, pairs);  // last-wave utilisation
         if (N >= 4096) kind = 2;
         if (K >= 512 && N >= 256 && eff256 >= 0.85) kind = 3;
+        // 256 x 192 pair tiles when they cut the number of waves: N = 768 at 12800 rows is 600 one-CTA tiles = 4.05 waves
+        // (5 rounds) but 200 pair tiles = 2.7 waves (3 rounds of 1.5 x the work per SM at the pair tile's better efficiency)
+        if (kind == 1 && K >= 512 && N >= 192) {
+            const int64_t r1 = slb_ceil_div(slb_ceil_div(M, BM) * slb_ceil_div(N, 128), slb_sm_count());
+            const int64_t r192 = slb_ceil_div(slb_ceil_div(M, 2 * BM) * slb_ceil_div(N, 192), pairs);
+            if ((double)r192 * 1.5 / 1.12 < 0.95 * (double)r1) kind = 4;
+        }
     }
     if (forced) kind = (M > BM || forced == 1) ? forced : 1;
     if (split_acc) kind = 1;  // the second accumulator fits the one-CTA tile only (4 x 128 TMEM columns)
     CUtensorMap tmA, tmW;
     int rc = slb_make_plane_map(&tmA, a_planes, M, K, 2, BM);
     if (rc != SLB_OK) return rc;
-    rc = slb_make_plane_map(&tmW, w_planes, N, K, 2, kind == 2 ? 64 : 128);  // W rows staged per CTA
+    rc = slb_make_plane_map(&tmW, w_planes, N, K, 2, kind == 2 ? 64 : (kind == 4 ? 96 : 128));  // W rows staged per CTA
     if (rc != SLB_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (kind == 4) return launch_gemm_pair<192>(tmA, tmW, p, st);
     if (kind == 3) return launch_gemm_pair<256>(tmA, tmW, p, st);
     if (kind == 2) return launch_gemm_pair<128>(tmA, tmW, p, st);
     return launch_gemm<128>(tmA, tmW, p, st);

@@ -63,7 +63,9 @@ def test_attention_vs_torch(ops, B, T, H, dh, gain):
                                        # tcgen05 tiles: exactly one tile, tile + 1-row tail, tile + 64-row second tile,
                                        # three key blocks, many (image, head) pairs
                                        (2, 128, 2, 1.0), (2, 129, 2, 1.0), (1, 192, 3, 2.0), (1, 255, 1, 1.0), (1, 256, 2, 1.0),
-                                       (1, 320, 2, 1.0), (9, 257, 16, 1.0), (2, 577, 2, 1.0)])
+                                       (1, 320, 2, 1.0), (9, 257, 16, 1.0), (2, 577, 2, 1.0),
+                                       # tails of <= 16 rows split the keys over the warps; 17 rows do not
+                                       (2, 140, 2, 1.0), (3, 144, 1, 2.0), (1, 145, 2, 1.0), (2, 263, 3, 1.0)])
 def test_attention_from_planes_vs_torch(ops, B, T, H, gain):
     """The tower's path: attention reads q | k | v from the in_proj GEMM's split planes (cp.async + ldmatrix + mma.sync)."""
     dh = 64
