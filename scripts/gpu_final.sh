@@ -14,4 +14,7 @@ PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > $O/${TAG}_ncu_launches.log 2>&1
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'gemm_split|attention_|layernorm|patchify|assemble|u8_norm|agg_rows|agg_btf|topk_' -c 1200 --csv --log-file $O/${TAG}_traffic.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > $O/${TAG}_ncu_traffic.log 2>&1
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:'gemm_split_pair|attention_tc|attention_planes|layernorm_reg' -s 20 -c 8 -f -o $O/${TAG}_prof_towers python scripts/profile_tower.py ViT-L-14 16 > $O/${TAG}_ncu_towers.log 2>&1
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:'im2col3x3|avgpool2|gemm_split_kernel|pool_tokens|im2col_stem' -s 6 -c 8 -f -o $O/${TAG}_prof_rn python scripts/profile_tower.py RN50 32 > $O/${TAG}_ncu_rn.log 2>&1
+timeout 600 python scripts/bench_kernels.py embed > $O/${TAG}_embed.jsonl 2>&1
+for t in "ViT-B-32 256" "ViT-L-14 64" "RN50 128"; do timeout 300 python scripts/profile_tower.py $t > "$O/${TAG}_tower_${t%% *}.json" 2>&1; done
 ls $O | grep ${TAG}

@@ -340,6 +340,18 @@ def attention_planes(qkv_planes: torch.Tensor, B: int, heads: int, fmt: int | No
 # ------------------------------------------------------------------------------------------------
 # analyze: scores
 # ------------------------------------------------------------------------------------------------
+def patchify(img: torch.Tensor, patch: int, fmt: int = N.PLANE_F16) -> torch.Tensor:
+    """(B,3,S,S) fp32 -> im2col planes (2, B*(S/P)^2, patch_k(P)) of the ViT patch-embedding convolution, column (c, py, px)."""
+    lib = N.load(require_device=True)
+    N.require_cuda(img, "img")
+    img = img.float().contiguous()
+    B, _, S, _ = img.shape
+    out = torch.empty((2, B * (S // patch) ** 2, int(lib.slb_patch_k(patch))), dtype=PLANE_DTYPES[fmt], device=img.device)
+    with _dev_guard(img):
+        N.check(lib.slb_patchify(img.data_ptr(), B, S, patch, fmt, out.data_ptr(), N.stream_ptr(img.device)), "slb_patchify")
+    return out
+
+
 # ---- CLIP ModifiedResNet pieces (channels-last split planes) ---------------------------------------------------------
 def conv_k(cin: int, ksize: int) -> int:
     return int(N.load().slb_conv_k(cin, ksize))

@@ -32,6 +32,17 @@ def test_k3_u8_norm_bitexact_vs_totensor_normalize(ops):
     assert torch.equal(got, vp.preprocess_u8(cfg, u8))
 
 
+@pytest.mark.parametrize("B,S,P", [(2, 64, 32), (3, 48, 16), (2, 28, 14), (1, 32, 8), (2, 12, 4), (1, 224, 32)])
+def test_patchify_bitexact_vs_unfold(ops, B, S, P):
+    """The patch-embedding im2col (8 pixels per thread when P % 8 == 0, 2 otherwise) against F.unfold, bit for bit."""
+    img = torch.randn(B, 3, S, S, generator=torch.Generator().manual_seed(S + P))
+    cols = torch.nn.functional.unfold(img, P, stride=P).transpose(1, 2).reshape(-1, 3 * P * P)  # (B*g*g, (c, py, px))
+    got = ops.patchify(img.cuda(), P)
+    want = torch.zeros(cols.shape[0], got.shape[2])
+    want[:, : 3 * P * P] = cols
+    assert torch.equal(got.cpu(), ops.split_planes(want.cuda(), 0, ACT).cpu())
+
+
 @pytest.mark.parametrize("rows,cols", [(7, 64), (300, 768), (33, 1024), (5, 1280), (4, 2048), (9, 512)])
 def test_layernorm_vs_torch(ops, rows, cols):
     x = torch.randn(rows, cols) * 3 + 0.5
