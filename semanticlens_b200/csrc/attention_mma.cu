@@ -703,8 +703,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcBars);
     uint64_t* q_full = bars;        // TMA -> MMA
-    uint64_t* kv_full = bars + 1;
-    uint64_t* kv_empty = bars + 3;  // MMA -> TMA
+    uint64_t* kv_full = bars + 1;   // [2] TMA -> MMA, one per K / V slot
+    uint64_t* kv_empty = bars + 3;  // [2] MMA -> TMA
     uint64_t* s_full = bars + 5;    // MMA -> softmax
     uint64_t* s_free = bars + 6;    // softmax (4 warps) -> MMA
     uint64_t* p_full = bars + 7;    // softmax (4 warps) -> MMA
@@ -724,8 +724,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         slb_prefetch_tmap(&tmq);
         slb_prefetch_tmap(&tmkv);
         slb_mbar_init(q_full, 1);
-        slb_mbar_init(kv_full, 1);
-        slb_mbar_init(kv_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            slb_mbar_init(&kv_full[i], 1);
+            slb_mbar_init(&kv_empty[i], 1);
+        }
         slb_mbar_init(s_full, 1);
         slb_mbar_init(s_free, kTcSoftmaxWarps);
         slb_mbar_init(p_full, kTcSoftmaxWarps);
@@ -745,14 +747,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         if (lane == 0) {
             slb_mbar_arrive_expect_tx(q_full, 2u * kTcPlaneQ);
             slb_tma_load_3d(smem + kTcQ, &tmq, h * 64, row_base + q0, 0, q_full);
+            // K / V blocks travel through a ring of two 16 KB slots (hi | lo planes of 64 tokens); item t uses slot t & 1.
+            // Sweep 1 streams K_0, K_1, ... (double-buffered); sweep 2 alternates K_j, V_j: K_{j+1} lands while the softmax
+            // warps work on block j (its slot is released by the S MMAs), V_{j+1} while S_{j+1} is computed.
+            int t = 0;
+            auto load_item = [&](int col, int row) {
+                const int slot = t & 1;
+                tc_wait(&kv_empty[slot], (uint32_t)((t >> 1) & 1) ^ 1u, p.dbg, 1);
+                slb_mbar_arrive_expect_tx(&kv_full[slot], 2u * kTcPlaneK);
+                slb_tma_load_3d(smem + kTcKV + slot * 2 * kTcPlaneK, &tmkv, col, row, 0, &kv_full[slot]);
+                ++t;
+            };
             for (int it = 0; it < n_iter; ++it) {
                 const int blk = it % nblk;
-                const bool with_v = it >= nblk;
-                tc_wait(kv_empty, (uint32_t)(it & 1) ^ 1u, p.dbg, 1);
-                unsigned char* dst = smem + kTcKV;
-                slb_mbar_arrive_expect_tx(kv_full, (with_v ? 4u : 2u) * kTcPlaneK);
-                slb_tma_load_3d(dst, &tmkv, p.W + h * 64, row_base + blk * kTcKeys, 0, kv_full);
-                if (with_v) slb_tma_load_3d(dst + 2 * kTcPlaneK, &tmkv, 2 * p.W + h * 64, row_base + blk * kTcKeys, 0, kv_full);
+                load_item(p.W + h * 64, row_base + blk * kTcKeys);
+                if (it >= nblk) load_item(2 * p.W + h * 64, row_base + blk * kTcKeys);
             }
         }
         __syncwarp();
@@ -761,13 +770,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             const uint32_t qa = slb_smem_u32(smem + kTcQ);
             const uint32_t pa = slb_smem_u32(smem + kTcP);
             tc_wait(q_full, 0, p.dbg, 2);
+            int t = 0;  // item counter of the K / V slot ring (same sequence as the producer's)
             for (int it = 0; it < n_iter; ++it) {
                 const int blk = it % nblk;
                 const bool sweep2 = it >= nblk;
                 const int nk = min(kTcKeys, (p.T - blk * kTcKeys + 15) & ~15);  // keys of this block, padded to the MMA N step
-                const uint32_t ka = slb_smem_u32(smem + kTcKV);
-                const uint32_t va = ka + 2 * kTcPlaneK;
-                tc_wait(kv_full, (uint32_t)(it & 1), p.dbg, 3);
+                const int slot_k = t & 1;
+                tc_wait(&kv_full[slot_k], (uint32_t)((t >> 1) & 1), p.dbg, 3);
+                ++t;
+                const uint32_t ka = slb_smem_u32(smem + kTcKV + slot_k * 2 * kTcPlaneK);
                 tc_wait(s_free, (it & 1) ^ 1u, p.dbg, 4);  // the softmax warps have read the previous S
                 slb_tc_fence_after();
                 // S = Q K^T: hi.hi -> S main; hi.lo + lo.hi -> S corr (same scale; summed in fp32 by the softmax warps, so
@@ -783,11 +794,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                                      idesc_s, pr == 2 ? true : k != 0);
                 }
                 slb_umma_commit(s_full);
-                if (!sweep2) {
-                    slb_umma_commit(kv_empty);
-                    continue;
-                }
-                // O += P V once the softmax warps have written P for this block
+                slb_umma_commit(&kv_empty[slot_k]);  // the K slot is free as soon as these MMAs have read it
+                if (!sweep2) continue;
+                // O += P V once V has landed and the softmax warps have written P for this block
+                const int slot_v = t & 1;
+                tc_wait(&kv_full[slot_v], (uint32_t)((t >> 1) & 1), p.dbg, 8);
+                ++t;
+                const uint32_t va = slb_smem_u32(smem + kTcKV + slot_v * 2 * kTcPlaneK);
                 tc_wait(p_full, (uint32_t)((it - nblk) & 1), p.dbg, 5);
                 slb_tc_fence_after();
                 const uint32_t idesc_o = slb_umma_idesc_f16(0, kTcTile, 64) | (1u << 16);  // B (= V) is MN-major
@@ -804,7 +817,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                     }
                 }
                 slb_umma_commit(p_free);
-                slb_umma_commit(kv_empty);
+                slb_umma_commit(&kv_empty[slot_v]);
             }
             slb_umma_commit(o_full);
         }

@@ -80,3 +80,62 @@ def test_vit_l14_tower_vs_oracle():
     got = tower.forward(img.cuda()).cpu()
     err = ((got.double() - want).abs().max() / want.abs().max()).item()
     assert err < 1e-4, err
+
+
+class _Cfg1Images(torch.utils.data.Dataset):
+    def __init__(self, n, kind):
+        g = torch.Generator().manual_seed(11)
+        # per-image contrast so that channel means differ between images by far more than a bf16 ulp (pure noise images
+        # give near-ties everywhere, and cuDNN / oneDNN then order them differently)
+        gain = torch.linspace(0.15, 1.0, n)[torch.randperm(n, generator=g)].view(n, 1, 1, 1)
+        self.u8 = (torch.randint(0, 255, (n, 3, 224, 224), generator=g).float() * gain).to(torch.uint8)
+        self.kind, self.name = kind, f"cfg1-{kind}-{n}"
+
+    def __len__(self):
+        return self.u8.shape[0]
+
+    def __getitem__(self, i):
+        return ((self.u8[i].float() / 255 - 0.45) / 0.23, 0) if self.kind == "model" else self.u8[i]
+
+
+def test_cfg1_resnet18_layer4_rn50_embed_end_to_end(tmp_path):
+    """BASELINE configs[0] at a small image count: ResNet-18 (random init) probed at layer4, OpenClip RN50 embed, through
+    Lens.compute_concept_db — against the torch-CPU port of the reference path with the oracle ModifiedResNet."""
+    import torchvision
+
+    from oracle import ref_port as rp
+    from oracle import rn_port as rnp
+    from semanticlens_b200.component_visualization import ActivationComponentVisualizer, aggregators
+    from semanticlens_b200.foundation_models import OpenClip
+    from semanticlens_b200.lens import Lens
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    net = torchvision.models.resnet18(weights=None).eval()
+    net.name = "resnet18"
+    n, k = 20, 5
+    ds_m, ds_f = _Cfg1Images(n, "model"), _Cfg1Images(n, "fm")
+    ocfg = rnp.CONFIGS["RN50"]
+    sd = rnp.init_weights(ocfg, seed=9)
+    mean = torch.tensor(ocfg.mean).view(1, 3, 1, 1)
+    std = torch.tensor(ocfg.std).view(1, 3, 1, 1)
+    ref_states = rp.sweep(net, torch.utils.data.DataLoader(ds_m, batch_size=5), ["layer4"], rp.aggregate_conv_mean, k)
+    ref_embeds = torch.cat([rnp.encode_image(sd, ocfg, (ds_f.u8[i:i + 5].float() / 255.0 - mean) / std) for i in range(0, n, 5)])
+    ref_db = rp.concept_db(ref_states, ref_embeds)
+
+    fm = OpenClip("RN50", device="cuda", state_dict=sd)
+    fm.name = "rn50-fm"
+    cv = ActivationComponentVisualizer(net.cuda(), ds_m, ds_f, ["layer4"], k, aggregate_fn=aggregators.aggregate_conv_mean,
+                                       cache_dir=str(tmp_path))
+    cv.show_progress = False
+    db = Lens(fm, device="cuda").compute_concept_db(cv, batch_size=8)
+    am = cv.actmax_cache.cache["layer4"]
+    rv, ri = ref_states["layer4"].activations, ref_states["layer4"].sample_ids
+    assert db["layer4"].shape == (512, k, 1024)
+    same_vals = (am.activations.view(torch.int16) == rv.view(torch.int16)) | ((am.activations == 0) & (rv == 0))
+    assert same_vals.float().mean() > 0.97  # cuDNN vs oneDNN activations: stray bf16 rounding flips only
+    agree = am.sample_ids == ri
+    assert agree.float().mean() > 0.9
+    err = (db["layer4"][agree] - ref_db["layer4"][agree]).abs().max() / ref_db["layer4"].abs().max()
+    assert err < 1e-4
