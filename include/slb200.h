@@ -251,6 +251,11 @@ int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64_t T, int64
                          int causal /* 1: key j visible to query i only if j <= i */, int plane_fmt, float* out_f32,
                          uint16_t* out_planes, void* stream);
 
+/* Debug aid: with SLB_ATTN_TRACE=1 in the environment, CTA (0, 0) of the last tcgen05 attention launch records the SM-clock
+ * offsets of its producer / MMA / softmax hand-offs into 256 host-mapped words (event type t, index i at [64 + 16 t + i]);
+ * NULL otherwise. Read after synchronising the stream (scripts/trace_attention.py). */
+const unsigned int* slb_attention_trace(void);
+
 /* The whole CLIP / SigLIP ViT image tower in one call (open_clip VisionTransformer.forward, or its timm ViT with the
  * attention-pool head for SigLIP, behind clip.py:103-118).
  * Weight matrices are split planes prepared once by the caller (slb_split_planes); vectors are fp32. All pointers are

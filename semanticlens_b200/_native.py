@@ -86,6 +86,7 @@ _PROTOS = {
     "slb_text_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "slb_text_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "slb_patch_k": (c_int64, [c_int64]),
+    "slb_attention_trace": (c_void_p, []),
     "slb_resize_workspace_bytes": (c_size_t, [c_int64] * 8),
     "slb_resize_bicubic_u8": (c_int, [c_void_p] + [c_int64] * 8 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     "slb_conv_k": (c_int64, [c_int64, c_int64]),

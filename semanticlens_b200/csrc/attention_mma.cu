@@ -643,15 +643,23 @@ extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64
 // =================================================================================================
 // tcgen05 attention for full 128-row query tiles (T >= 128: ViT-B/16, ViT-L/14, SigLIP towers).
 //
-// One CTA = one (image, head, 128-query tile); 192 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax
-// (thread = query row = TMEM lane). Operands come from the in_proj GEMM's split planes through ONE 3-D tensor map
-// (boxes of 64 cols x 128 / 64 rows x 2 planes, 128B swizzle): the Q tile, K blocks and V blocks of 64 tokens. The tiles
-// take 96 KB and the accumulators 256 TMEM columns, so TWO CTAs share an SM and fill each other's hand-off bubbles. Two sweeps over the keys
-// avoid rescaling the output accumulator: sweep 1 computes S = Q K^T block by block for the row maxima only, sweep 2
-// recomputes S, writes P = exp2(S - max) as split planes into shared memory (K-major, swizzled by hand) and accumulates
-// O += P V with V consumed straight from its row-major tile as an MN-major operand (no transpose anywhere).
-// Accumulators (TMEM): S main | S corr (2 x 64 columns), O main | O corr (2 x 64 columns); every product is the usual three
-// plane products, hi.hi into main and the two cross terms into corr (q, k, v planes share one scale, P planes carry 2^10). Rows of the tile beyond T and keys beyond T are masked / never stored.
+// One CTA = one (image, head, 128-query tile); 320 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 softmax
+// (thread = query row = TMEM lane, two warps per lane quarter, each on 32 of a block's 64 keys). Operands come from the
+// in_proj GEMM's split planes through ONE 3-D tensor map (boxes of 64 cols x 128 / 64 rows x 2 planes, 128B swizzle):
+// the Q tile, and K / V blocks of 64 tokens that travel through one ring of three 16 KB slots. The tiles take 112 KB
+// and the accumulators 256 TMEM columns, so TWO CTAs share an SM and fill each other's hand-off bubbles.
+// Two sweeps over the keys avoid rescaling the output accumulator: sweep 1 computes S = Q K^T (hi.hi only: the row
+// maximum is just the softmax's stabiliser) block by block, sweep 2 recomputes S with all three plane products, writes
+// P = exp2(S - max) as split planes into shared memory (K-major, swizzled by hand) and accumulates O += P V with V
+// consumed straight from its row-major tile as an MN-major operand (no transpose anywhere).
+// Software pipeline: the softmax warps release S as soon as it is in registers and the MMA warp issues S of block j + 1
+// BEFORE P V of block j, so the tensor core computes the next logits under this block's exponentials; V_{j+1} is
+// requested when the S MMAs release K_j's slot (early), K_{j+2} when P V releases V_j's.
+// Accumulators (TMEM): S main | S corr (2 x 64 columns), O main | O corr (2 x 64 columns); hi.hi goes into main and the
+// two cross terms into corr (q, k, v planes share one scale, P planes carry 2^10). Rows of the tile beyond T and keys
+// beyond T are masked / never stored. SLB_ATTN_TRACE=1 records one CTA's hand-off timeline (scripts/trace_attention.py):
+// what remains is the serial chain tmem-load -> exp -> P store -> P V per block (~3500 SM clocks, MUFU- and
+// latency-bound) against ~770 clocks of tensor work; a ping-pong over two query tiles per CTA is the next step.
 // =================================================================================================
 namespace {
 
@@ -662,10 +670,11 @@ constexpr int kTcKeys = 64;                       // keys per block
 constexpr int kTcPlaneQ = kTcTile * 64 * 2;       // one 128 x 64 fp16 plane tile (Q, P): 16 KB
 constexpr int kTcPlaneK = kTcKeys * 64 * 2;       // one 64 x 64 fp16 plane tile (K, V): 8 KB
 constexpr int kTcQ = 0;                           // Q  hi | lo                       32 KB
-constexpr int kTcKV = 2 * kTcPlaneQ;              // K hi | lo, V hi | lo (one stage)  32 KB
-constexpr int kTcP = kTcKV + 4 * kTcPlaneK;       // P  hi | lo (128 x 64 each)        32 KB
-constexpr int kTcBars = kTcP + 2 * kTcPlaneQ;     // 96 KB of tiles: two CTAs per SM hide each other's hand-off latencies
-constexpr size_t kTcSmem = (size_t)kTcBars + 1024 /*align*/ + 128 /*barriers*/ + 2 * 128 * 4 /*row max / row sum exchange*/;
+constexpr int kTcKV = 2 * kTcPlaneQ;              // ring of three 16 KB slots (hi | lo planes of 64 tokens) for K and V blocks
+constexpr int kTcSlots = 3;
+constexpr int kTcP = kTcKV + 6 * kTcPlaneK;       // P  hi | lo (128 x 64 each)        32 KB (also the row max / sum exchange)
+constexpr int kTcBars = kTcP + 2 * kTcPlaneQ;     // 112 KB of tiles: two CTAs per SM (2 x (112.1 KB + 1 KB reserved) <= 228 KB)
+constexpr size_t kTcSmem = (size_t)kTcBars + 128 /*barriers*/;
 
 struct AttnTcParams {
     int T, H, W;
@@ -685,6 +694,12 @@ __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, unsigned
         if (clock64() - t0 > 4000000000ll) tc_timeout(dbg, site);
 }
 
+// SLB_ATTN_TRACE=1: CTA (0, 0) records SM-clock offsets of its hand-offs into host-mapped words (scripts/trace_attention.py)
+#define TC_TRACE(type, idx)                                                                                  \
+    do {                                                                                                     \
+        if (trace_on && (idx) < 16) p.dbg[64 + (type) * 16 + (idx)] = (unsigned int)(clock64() - t_start);   \
+    } while (0)
+
 // MN-major operand tile (rows = K index, 128 B per row = 64 contiguous MN elements), 128-byte swizzle:
 // SBO = 1024 B between 8-row groups along K; LBO (between 64-element MN atoms) unused for N = 64.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
@@ -699,19 +714,23 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
 
 __global__ void __launch_bounds__(kTcThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv, AttnTcParams p) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // no alignment slack: two CTAs must fit an SM. The declared alignment is honoured for dynamic shared memory (no static
+    // shared memory in this kernel); checked below, a misaligned base traps instead of corrupting swizzled tiles.
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcBars);
     uint64_t* q_full = bars;        // TMA -> MMA
-    uint64_t* kv_full = bars + 1;   // [2] TMA -> MMA, one per K / V slot
-    uint64_t* kv_empty = bars + 3;  // [2] MMA -> TMA
-    uint64_t* s_full = bars + 5;    // MMA -> softmax
-    uint64_t* s_free = bars + 6;    // softmax (4 warps) -> MMA
-    uint64_t* p_full = bars + 7;    // softmax (4 warps) -> MMA
-    uint64_t* p_free = bars + 8;    // MMA -> softmax
-    uint64_t* o_full = bars + 9;    // MMA -> softmax
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-    float* xch = reinterpret_cast<float*>(bars + 16);  // [2][128]: partial row max / row sum of the second column half
+    uint64_t* kv_full = bars + 1;   // [3] TMA -> MMA, one per slot of the K / V ring
+    uint64_t* kv_empty = bars + 4;  // [3] MMA -> TMA
+    uint64_t* s_full = bars + 7;    // MMA -> softmax
+    uint64_t* s_free = bars + 8;    // softmax (8 warps) -> MMA
+    uint64_t* p_full = bars + 9;    // softmax (8 warps) -> MMA
+    uint64_t* p_free = bars + 10;   // MMA -> softmax
+    uint64_t* o_full = bars + 11;   // MMA -> softmax
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    // [2][128] partial row max / row sum of the second column half; aliases the P tile, which is idle at both exchanges
+    // (before the first P is written, and after the last P V has completed)
+    float* xch = reinterpret_cast<float*>(smem + kTcP);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
@@ -724,7 +743,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         slb_prefetch_tmap(&tmq);
         slb_prefetch_tmap(&tmkv);
         slb_mbar_init(q_full, 1);
-        for (int i = 0; i < 2; ++i) {
+        if ((slb_smem_u32(smem) & 1023u) != 0) tc_timeout(p.dbg, 15);
+        for (int i = 0; i < kTcSlots; ++i) {
             slb_mbar_init(&kv_full[i], 1);
             slb_mbar_init(&kv_empty[i], 1);
         }
@@ -740,6 +760,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     __syncthreads();
     slb_tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const bool trace_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+    const long long t_start = clock64();
     const uint32_t t_s = tmem_base;            // S main [0,64), S corr [64,128)
     const uint32_t t_o = tmem_base + 128;      // O main [128,192), O corr [192,256)
 
@@ -747,15 +769,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         if (lane == 0) {
             slb_mbar_arrive_expect_tx(q_full, 2u * kTcPlaneQ);
             slb_tma_load_3d(smem + kTcQ, &tmq, h * 64, row_base + q0, 0, q_full);
-            // K / V blocks travel through a ring of two 16 KB slots (hi | lo planes of 64 tokens); item t uses slot t & 1.
-            // Sweep 1 streams K_0, K_1, ... (double-buffered); sweep 2 alternates K_j, V_j: K_{j+1} lands while the softmax
-            // warps work on block j (its slot is released by the S MMAs), V_{j+1} while S_{j+1} is computed.
+            // K and V blocks travel through ONE ring of three slots in the order the sweeps consume them: K_0 .. K_{n-1}
+            // (sweep 1, triple-buffered), then K_0, V_0, K_1, V_1, ... Item t may be requested once item t - 3 has been read:
+            // V_{j+1} follows K_j (released by the S MMAs, early), so it lands while the softmax warps still work on block j;
+            // K_{j+2} follows V_j (released by the P V MMAs) and has the whole softmax of block j + 1 to arrive.
             int t = 0;
             auto load_item = [&](int col, int row) {
-                const int slot = t & 1;
-                tc_wait(&kv_empty[slot], (uint32_t)((t >> 1) & 1) ^ 1u, p.dbg, 1);
+                const int slot = t % kTcSlots;
+                tc_wait(&kv_empty[slot], (uint32_t)((t / kTcSlots) & 1) ^ 1u, p.dbg, 1);
                 slb_mbar_arrive_expect_tx(&kv_full[slot], 2u * kTcPlaneK);
                 slb_tma_load_3d(smem + kTcKV + slot * 2 * kTcPlaneK, &tmkv, col, row, 0, &kv_full[slot]);
+                TC_TRACE(0, t);
                 ++t;
             };
             for (int it = 0; it < n_iter; ++it) {
@@ -770,39 +794,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             const uint32_t qa = slb_smem_u32(smem + kTcQ);
             const uint32_t pa = slb_smem_u32(smem + kTcP);
             tc_wait(q_full, 0, p.dbg, 2);
-            int t = 0;  // item counter of the K / V slot ring (same sequence as the producer's)
-            for (int it = 0; it < n_iter; ++it) {
+            // S(it) = Q K^T. Sweep 1 only needs row maxima as a softmax stabiliser: hi.hi alone (|error| ~ 2^-11 |s|) is
+            // enough, the exponentials of sweep 2 use the full three products.
+            // item index of block it's K in the ring (the producer's sequence); its V, in sweep 2, is the next item
+            auto item_k = [&](int it) { return it < nblk ? it : nblk + 2 * (it - nblk); };
+            auto issue_s = [&](int it) {
                 const int blk = it % nblk;
                 const bool sweep2 = it >= nblk;
                 const int nk = min(kTcKeys, (p.T - blk * kTcKeys + 15) & ~15);  // keys of this block, padded to the MMA N step
-                const int slot_k = t & 1;
-                tc_wait(&kv_full[slot_k], (uint32_t)((t >> 1) & 1), p.dbg, 3);
-                ++t;
-                const uint32_t ka = slb_smem_u32(smem + kTcKV + slot_k * 2 * kTcPlaneK);
-                tc_wait(s_free, (it & 1) ^ 1u, p.dbg, 4);  // the softmax warps have read the previous S
+                const int t = item_k(it), slot = t % kTcSlots;
+                tc_wait(&kv_full[slot], (uint32_t)((t / kTcSlots) & 1), p.dbg, 3);
+                TC_TRACE(1, it);  // K landed
+                tc_wait(s_free, (it & 1) ^ 1u, p.dbg, 4);  // the softmax warps have loaded the previous S into registers
                 slb_tc_fence_after();
-                // S = Q K^T: hi.hi -> S main; hi.lo + lo.hi -> S corr (same scale; summed in fp32 by the softmax warps, so
-                // the small terms are not truncated against the large accumulator: the logits feed an exponential)
+                TC_TRACE(2, it);  // S MMAs issued from here
+                const uint32_t ka = slb_smem_u32(smem + kTcKV + slot * 2 * kTcPlaneK);
                 const uint32_t idesc_s = slb_umma_idesc_f16(0, kTcTile, nk);
+                // hi.hi -> S main; hi.lo + lo.hi -> S corr (same scale; summed in fp32 by the softmax warps, so the small
+                // terms are not truncated against the large accumulator: the logits feed an exponential)
 #pragma unroll
                 for (int pr = 0; pr < 3; ++pr) {
-                    const uint32_t ab = qa + (pr == 2 ? kTcPlaneQ : 0);
-                    const uint32_t bb = ka + (pr == 1 ? kTcPlaneK : 0);
+                    if (pr == 0 || sweep2) {
+                        const uint32_t ab = qa + (pr == 2 ? kTcPlaneQ : 0);
+                        const uint32_t bb = ka + (pr == 1 ? kTcPlaneK : 0);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        slb_umma_f16(t_s + (pr ? 64 : 0), slb_umma_desc_sw128(ab + k * 32), slb_umma_desc_sw128(bb + k * 32),
-                                     idesc_s, pr == 2 ? true : k != 0);
+                        for (int k = 0; k < 4; ++k)
+                            slb_umma_f16(t_s + (pr ? 64 : 0), slb_umma_desc_sw128(ab + k * 32), slb_umma_desc_sw128(bb + k * 32),
+                                         idesc_s, pr == 2 ? true : k != 0);
+                    }
                 }
                 slb_umma_commit(s_full);
-                slb_umma_commit(&kv_empty[slot_k]);  // the K slot is free as soon as these MMAs have read it
-                if (!sweep2) continue;
-                // O += P V once V has landed and the softmax warps have written P for this block
-                const int slot_v = t & 1;
-                tc_wait(&kv_full[slot_v], (uint32_t)((t >> 1) & 1), p.dbg, 8);
-                ++t;
-                const uint32_t va = slb_smem_u32(smem + kTcKV + slot_v * 2 * kTcPlaneK);
-                tc_wait(p_full, (uint32_t)((it - nblk) & 1), p.dbg, 5);
+                slb_umma_commit(&kv_empty[slot]);  // the K slot is free as soon as these MMAs have read it
+            };
+            // O += P V for block it of sweep 2, once V has landed and the softmax warps have written P
+            auto issue_pv = [&](int it) {
+                const int blk = it - nblk;
+                const int nk = min(kTcKeys, (p.T - blk * kTcKeys + 15) & ~15);
+                const int t = item_k(it) + 1, slot = t % kTcSlots;
+                tc_wait(&kv_full[slot], (uint32_t)((t / kTcSlots) & 1), p.dbg, 8);
+                tc_wait(p_full, (uint32_t)(blk & 1), p.dbg, 5);
                 slb_tc_fence_after();
+                TC_TRACE(3, blk);  // P V MMAs issued from here
+                const uint32_t va = slb_smem_u32(smem + kTcKV + slot * 2 * kTcPlaneK);
                 const uint32_t idesc_o = slb_umma_idesc_f16(0, kTcTile, 64) | (1u << 16);  // B (= V) is MN-major
                 const int ksteps = nk >> 4;
 #pragma unroll
@@ -817,7 +850,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                     }
                 }
                 slb_umma_commit(p_free);
-                slb_umma_commit(&kv_empty[slot_v]);
+                slb_umma_commit(&kv_empty[slot]);
+            };
+            // software pipeline: S of the next block is issued BEFORE P V of the current one, so the tensor core works on
+            // S(it + 1) while the softmax warps turn S(it) into P(it) (they release S as soon as it is in registers)
+            for (int it = 0; it <= nblk; ++it) issue_s(it);  // sweep 1 and the first block of sweep 2
+            for (int it = nblk; it < n_iter; ++it) {
+                if (it + 1 < n_iter) issue_s(it + 1);
+                issue_pv(it);
             }
             slb_umma_commit(o_full);
         }
@@ -849,54 +889,77 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             }
             tc_wait(s_full, (uint32_t)(it & 1), p.dbg, 6);
             slb_tc_fence_after();
-            if (sweep2) tc_wait(p_free, (uint32_t)((it - nblk) & 1) ^ 1u, p.dbg, 7);  // previous P consumed by its MMAs
-            for (int c = half * 32; c < min(nk, half * 32 + 32); c += 32) {
-                uint32_t a[32], sc[32];
+            if (warp == 2) TC_TRACE(4, it);    // S visible to the softmax warps
+            const int c = half * 32;           // this warp's 32 keys of the block
+            const bool has_cols = c < nk;      // warp-uniform
+            float v[32];
+            if (has_cols) {
+                uint32_t a[32];
                 slb_tmem_ld_32x32(t_s + lane_addr + c, a);
-                slb_tmem_ld_32x32(t_s + lane_addr + 64 + c, sc);
-                slb_tmem_ld_wait();
-                float v[32];
+                if (sweep2) {
+                    uint32_t sc[32];
+                    slb_tmem_ld_32x32(t_s + lane_addr + 64 + c, sc);
+                    slb_tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    v[j] = (blk * kTcKeys + c + j < p.T) ? (__uint_as_float(a[j]) + __uint_as_float(sc[j])) * c_main : -INFINITY;
-                if (!sweep2) {
+                    for (int j = 0; j < 32; ++j)
+                        v[j] = (blk * kTcKeys + c + j < p.T) ? (__uint_as_float(a[j]) + __uint_as_float(sc[j])) * c_main : -INFINITY;
+                } else {
+                    slb_tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (blk * kTcKeys + c + j < p.T) ? __uint_as_float(a[j]) * c_main : -INFINITY;
+                }
+            }
+            // S is in registers: hand the accumulator back so that the next S is computed under this block's exponentials
+            slb_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) slb_mbar_arrive(s_free);
+            if (warp == 2) TC_TRACE(5, it);    // S in registers
+            if (!sweep2) {
+                if (has_cols) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) m_row = fmaxf(m_row, v[j]);
-                } else {
-                    // p = exp2(s - max); 16-byte chunks of hi and of lo per 8 keys, swizzled like TMA would write them
+                }
+                continue;
+            }
+            // p = exp2(s - max) as split planes: 16-byte chunks of hi and of lo per 8 keys, swizzled like TMA would write them
+            uint32_t hh[4][4], ll[4][4];
+            if (has_cols) {
 #pragma unroll
-                    for (int q8 = 0; q8 < 4; ++q8) {
-                        uint32_t hh[4], ll[4];
+                for (int q8 = 0; q8 < 4; ++q8) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float p0 = exp2f(v[q8 * 8 + 2 * e] - m_row), p1 = exp2f(v[q8 * 8 + 2 * e + 1] - m_row);
-                            l_row += p0 + p1;
-                            split_pair_unit(p0, p1, hh[e], ll[e]);
-                        }
-                        const int key = c + q8 * 8;                    // first key of this 16-byte chunk
-                        const int chunk = key >> 3;
-                        const size_t off = (size_t)r * 128 + (size_t)((chunk ^ (r & 7)) << 4);
-                        *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-                        *reinterpret_cast<uint4*>(p_lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                    for (int e = 0; e < 4; ++e) {
+                        const float p0 = exp2f(v[q8 * 8 + 2 * e] - m_row), p1 = exp2f(v[q8 * 8 + 2 * e + 1] - m_row);
+                        l_row += p0 + p1;
+                        split_pair_unit(p0, p1, hh[q8][e], ll[q8][e]);
                     }
                 }
             }
-            slb_tc_fence_before();
-            if (sweep2) slb_fence_proxy_async();  // the P tile was written through the generic proxy; the MMA reads it through the async proxy
-            __syncwarp();
-            if (lane == 0) {
-                if (sweep2) slb_mbar_arrive(p_full);
-                slb_mbar_arrive(s_free);
+            if (warp == 2) TC_TRACE(6, it - nblk);  // exponentials done
+            tc_wait(p_free, (uint32_t)((it - nblk) & 1) ^ 1u, p.dbg, 7);  // the previous P has been consumed by its MMAs
+            if (warp == 2) TC_TRACE(7, it - nblk);  // P buffer free
+            if (has_cols) {
+#pragma unroll
+                for (int q8 = 0; q8 < 4; ++q8) {
+                    const int chunk = (c + q8 * 8) >> 3;  // 16-byte chunk of the row holding these 8 keys
+                    const size_t off = (size_t)r * 128 + (size_t)((chunk ^ (r & 7)) << 4);
+                    *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(hh[q8][0], hh[q8][1], hh[q8][2], hh[q8][3]);
+                    *reinterpret_cast<uint4*>(p_lo + off) = make_uint4(ll[q8][0], ll[q8][1], ll[q8][2], ll[q8][3]);
+                }
             }
+            slb_fence_proxy_async();  // the P tile was written through the generic proxy; the MMA reads it through the async proxy
+            __syncwarp();
+            if (lane == 0) slb_mbar_arrive(p_full);
+            if (warp == 2) TC_TRACE(8, it - nblk);  // P written and published
         }
         // ---- row sums of the two column halves, then O = (main + corr) / (scales * l); each warp stores 32 of the 64 dims ----
+        tc_wait(o_full, 0, p.dbg, 0);  // every P V has completed: the P tile is idle and can carry the exchange
+        slb_tc_fence_after();
+        if (warp == 2) TC_TRACE(9, 0);  // O complete
         if (half) xch[128 + r] = l_row;
         asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
         if (!half) xch[128 + r] += l_row;
         asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
         l_row = xch[128 + r];
-        tc_wait(o_full, 0, p.dbg, 0);
-        slb_tc_fence_after();
         const float inv = kInvAct / (kPScale * l_row);  // V planes carry the activation scale, P planes kPScale
         const bool ok = row < p.T;
         const int64_t base = ((int64_t)row_base + row) * p.W + (int64_t)h * 64;
@@ -940,10 +1003,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     if (warp == 1) {
         slb_tc_fence_after();
         slb_tmem_dealloc<256>(tmem_base);
+        TC_TRACE(9, 1);  // CTA done
     }
 }
 
+unsigned int* g_attn_trace_host = nullptr;  // SLB_ATTN_TRACE=1 only
+unsigned int* g_attn_trace_dev = nullptr;
+
 }  // namespace
+
+// the trace words of the last tcgen05 attention launch (null unless SLB_ATTN_TRACE=1): [64 + type * 16 + index] SM clocks
+extern "C" const unsigned int* slb_attention_trace() { return g_attn_trace_host; }
 
 // Full 128-row query tiles of every (image, head) on the tcgen05 path; the caller handles the remaining rows.
 int slb_attention_tc_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles,
@@ -959,6 +1029,15 @@ int slb_attention_tc_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out_f32 = out_f32; p.out_hi = out_hi; p.out_lo = out_lo; p.fmt = plane_fmt;
     p.dbg = nullptr;
+    static const bool trace = [] { const char* e = getenv("SLB_ATTN_TRACE"); return e && e[0] == '1'; }();
+    if (trace) {
+        if (!g_attn_trace_host) {
+            SLB_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&g_attn_trace_host), 256 * 4, cudaHostAllocMapped));
+            SLB_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_attn_trace_dev), g_attn_trace_host, 0));
+        }
+        for (int i = 0; i < 256; ++i) g_attn_trace_host[i] = 0;
+        p.dbg = g_attn_trace_dev;
+    }
     SLB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
     dim3 grid((unsigned)(B * H), (unsigned)n_tiles);
     attention_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(tmq, tmkv, p);
