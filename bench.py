@@ -240,7 +240,7 @@ def run_reference_arm(args):
                                    f"path, oracle/ref_port.py), {stages}"},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def foundation_model_available() -> bool:
@@ -438,12 +438,31 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = run_cpu_sample(args.cpu_images, 32, fm is not None)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None  # the process's real stdout, kept for the ONE JSON line
+
+
+def _claim_stdout():
+    """The contract is one JSON line on stdout. Libraries write there too (NCCL prints its version banner to fd 1 when
+    NCCL_DEBUG is set), so fd 1 is pointed at stderr for the whole run and the result line goes to a saved duplicate."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

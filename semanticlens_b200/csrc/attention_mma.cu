@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(NW * 32) attention_mma_kernel(AttnMmaParams p)
 
 // ------------------------------------------------------------------------------------------------
 // Same algorithm, operands already split: q, k, v are read from the fp16 split planes [2][rows][3W] that the in_proj
-// GEMM emits (hi, lo * 2^11), so nothing is converted here — K and V go to shared memory with 16-byte cp.async copies,
+// GEMM emits (hi, lo at SLB_ACT_PLANE_SCALE), so nothing is converted here — K and V go to shared memory with 16-byte cp.async copies,
 // B fragments come from ldmatrix (.trans for V, which stays row-major), Q fragments are 32-bit global loads. The softmax
 // scale multiplies the fp32 logits.
 // ------------------------------------------------------------------------------------------------

@@ -13,9 +13,12 @@
 //   warp 0      TMA producer: per k-block ONE 3-D box per operand {64 cols, rows, 2 planes} -> 128B-swizzled smem stage
 //   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16, 12 per k-block (3 plane products x 4
 //               k-steps, one accumulator); tcgen05.commit frees stages
-//   warps 2..9  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> scale/bias/activation/residual -> global
-//               (two warps per TMEM lane quarter: the GELU / split-plane epilogues are ALU-heavy)
-// Accumulators are double buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warps 2..9  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> per-warp shared-memory transpose ->
+//               scale/bias/activation/residual -> row-contiguous global stores (two warps per TMEM lane quarter: the
+//               GELU / split-plane epilogues are ALU-heavy)
+// Accumulators are double buffered in TMEM: the epilogue of tile i overlaps the MMAs of tile i+1. CTA-pair variants
+// (cta_group::2, tiles 256 x 128 / 192 / 256) follow below; SLB_PASSES_SPLIT_ACC keeps the cross terms in a second
+// accumulator (one-CTA tile).
 #include "tc_common.cuh"
 
 #include <stdlib.h>
