@@ -793,6 +793,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         if (lane == 0) {
             const uint32_t qa = slb_smem_u32(smem + kTcQ);
             const uint32_t pa = slb_smem_u32(smem + kTcP);
+            // loop-invariant operand descriptors (slot 0 of the ring for K / V) and the P V instruction descriptor
+            const uint64_t dq_hi = slb_umma_desc_sw128(qa), dq_lo = slb_umma_desc_sw128(qa + kTcPlaneQ);
+            const uint64_t dp_hi = slb_umma_desc_sw128(pa), dp_lo = slb_umma_desc_sw128(pa + kTcPlaneQ);
+            const uint64_t dk0 = slb_umma_desc_sw128(slb_smem_u32(smem + kTcKV));
+            const uint64_t dv0 = umma_desc_mn_sw128(slb_smem_u32(smem + kTcKV));
+            const uint32_t idesc_o = slb_umma_idesc_f16(0, kTcTile, 64) | (1u << 16);  // B (= V) is MN-major
             tc_wait(q_full, 0, p.dbg, 2);
             // S(it) = Q K^T. Sweep 1 only needs row maxima as a softmax stabiliser: hi.hi alone (|error| ~ 2^-11 |s|) is
             // enough, the exponentials of sweep 2 use the full three products.
@@ -808,19 +814,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                 tc_wait(s_free, (it & 1) ^ 1u, p.dbg, 4);  // the softmax warps have loaded the previous S into registers
                 slb_tc_fence_after();
                 TC_TRACE(2, it);  // S MMAs issued from here
-                const uint32_t ka = slb_smem_u32(smem + kTcKV + slot * 2 * kTcPlaneK);
+                const uint64_t dk_hi = dk0 + (uint64_t)(slot * (2 * kTcPlaneK >> 4)), dk_lo = dk_hi + (kTcPlaneK >> 4);
                 const uint32_t idesc_s = slb_umma_idesc_f16(0, kTcTile, nk);
                 // hi.hi -> S main; hi.lo + lo.hi -> S corr (same scale; summed in fp32 by the softmax warps, so the small
-                // terms are not truncated against the large accumulator: the logits feed an exponential)
+                // terms are not truncated against the large accumulator: the logits feed an exponential).
+                // One thread issues every MMA: descriptors are base + constant (a descriptor is linear in the address), so
+                // that the issue rate (not ~90 clocks of address arithmetic per MMA) stays below the 32-clock N = 64 MMA.
 #pragma unroll
                 for (int pr = 0; pr < 3; ++pr) {
                     if (pr == 0 || sweep2) {
-                        const uint32_t ab = qa + (pr == 2 ? kTcPlaneQ : 0);
-                        const uint32_t bb = ka + (pr == 1 ? kTcPlaneK : 0);
+                        const uint64_t da = pr == 2 ? dq_lo : dq_hi, db = pr == 1 ? dk_lo : dk_hi;
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            slb_umma_f16(t_s + (pr ? 64 : 0), slb_umma_desc_sw128(ab + k * 32), slb_umma_desc_sw128(bb + k * 32),
-                                         idesc_s, pr == 2 ? true : k != 0);
+                            slb_umma_f16(t_s + (pr ? 64 : 0), da + 2 * k, db + 2 * k, idesc_s, pr == 2 ? true : k != 0);
                     }
                 }
                 slb_umma_commit(s_full);
@@ -835,18 +841,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                 tc_wait(p_full, (uint32_t)(blk & 1), p.dbg, 5);
                 slb_tc_fence_after();
                 TC_TRACE(3, blk);  // P V MMAs issued from here
-                const uint32_t va = slb_smem_u32(smem + kTcKV + slot * 2 * kTcPlaneK);
-                const uint32_t idesc_o = slb_umma_idesc_f16(0, kTcTile, 64) | (1u << 16);  // B (= V) is MN-major
+                const uint64_t dv_hi = dv0 + (uint64_t)(slot * (2 * kTcPlaneK >> 4)), dv_lo = dv_hi + (kTcPlaneK >> 4);
                 const int ksteps = nk >> 4;
 #pragma unroll
                 for (int pr = 0; pr < 3; ++pr) {
-                    const uint32_t ab = pa + (pr == 2 ? kTcPlaneQ : 0);   // P hi / lo
-                    const uint32_t bb = va + (pr == 1 ? kTcPlaneK : 0);   // V hi / lo
-                    for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t da = pr == 2 ? dp_lo : dp_hi;   // P hi / lo
+                    const uint64_t db = pr == 1 ? dv_lo : dv_hi;   // V hi / lo
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
                         // P hi . V hi -> main; the cross terms P hi . V lo + P lo . V hi -> corr (same scale, added in fp32)
-                        const bool acc = pr == 2 ? true : (blk | k) != 0;
-                        slb_umma_f16(t_o + (pr ? 64 : 0), slb_umma_desc_sw128(ab + k * 32), umma_desc_mn_sw128(bb + k * 2048),
-                                     idesc_o, acc);
+                        if (k < ksteps)
+                            slb_umma_f16(t_o + (pr ? 64 : 0), da + 2 * k, db + (2048 >> 4) * k, idesc_o,
+                                         pr == 2 ? true : (blk | k) != 0);
                     }
                 }
                 slb_umma_commit(p_free);
