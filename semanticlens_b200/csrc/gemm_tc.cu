@@ -228,6 +228,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = slb_umma_idesc_f16(p.fmt, BM, BN);
+            const uint64_t desc0 = slb_umma_desc_sw128(slb_smem_u32(smem));  // stage 0, A hi plane
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -240,21 +241,21 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int kb = 0; kb < num_kb; ++kb) {
                     slb_mbar_wait(&full[stage], phase);
                     slb_tc_fence_after();
-                    const uint32_t a0 = slb_smem_u32(smem + (size_t)stage * C::kStageBytes);
-                    const uint32_t w0 = a0 + C::kABytes;
+                    // operand descriptors are linear in the shared-memory address: stage base + constants, so the single
+                    // issuing thread spends a couple of adds per MMA, not a descriptor build
+                    const uint64_t da0 = desc0 + (uint64_t)(stage * (C::kStageBytes >> 4));
+                    const uint64_t dw0 = da0 + (C::kABytes >> 4);
                     // (A plane, W plane): hi·hi, hi·lo, lo·hi
 #pragma unroll
                     for (int pr = 0; pr < 3; ++pr) {
                         if (pr < p.passes) {
-                            const uint32_t ab = a0 + (pr == 2 ? BM * BK * 2 : 0);
-                            const uint32_t wb = w0 + (pr == 1 ? BN * BK * 2 : 0);
+                            const uint64_t da = da0 + (pr == 2 ? (BM * BK * 2) >> 4 : 0);
+                            const uint64_t dw = dw0 + (pr == 1 ? (BN * BK * 2) >> 4 : 0);
                             // first write of an accumulator overwrites: main at (kb, pr, k) = 0, the cross columns at pr = 1
                             const int first = p.split_acc ? (pr == 2 ? 1 : kb) : (kb | pr);
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k) {
-                                slb_umma_f16(pr ? d_cross : d_tmem, slb_umma_desc_sw128(ab + k * 32), slb_umma_desc_sw128(wb + k * 32),
-                                             idesc, (first | k) != 0);
-                            }
+                            for (int k = 0; k < BK / 16; ++k)
+                                slb_umma_f16(pr ? d_cross : d_tmem, da + 2 * k, dw + 2 * k, idesc, (first | k) != 0);
                         }
                     }
                     slb_umma_commit(&empty[stage]);
@@ -415,6 +416,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     } else if (warp == 1) {
         if (leader && lane == 0) {
             const uint32_t idesc = slb_umma_idesc_f16(p.fmt, 2 * BM, BN);
+            const uint64_t desc0 = slb_umma_desc_sw128(slb_smem_u32(smem));  // stage 0, A hi plane
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -426,18 +428,16 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait_bounded(&full[stage], phase, p.dbg, 3, t, kb, stage);
                     slb_tc_fence_after();
-                    const uint32_t a0 = slb_smem_u32(smem + (size_t)stage * C::kStageBytes);
-                    const uint32_t w0 = a0 + C::kABytes;
+                    const uint64_t da0 = desc0 + (uint64_t)(stage * (C::kStageBytes >> 4));  // descriptors: base + constants
+                    const uint64_t dw0 = da0 + (C::kABytes >> 4);
 #pragma unroll
                     for (int pr = 0; pr < 3; ++pr) {
                         if (pr < p.passes) {
-                            const uint32_t ab = a0 + (pr == 2 ? BM * BK * 2 : 0);
-                            const uint32_t wb = w0 + (pr == 1 ? (BN / 2) * BK * 2 : 0);
+                            const uint64_t da = da0 + (pr == 2 ? (BM * BK * 2) >> 4 : 0);
+                            const uint64_t dw = dw0 + (pr == 1 ? ((BN / 2) * BK * 2) >> 4 : 0);
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k) {
-                                slb_umma_f16_pair(d_tmem, slb_umma_desc_sw128(ab + k * 32), slb_umma_desc_sw128(wb + k * 32),
-                                                  idesc, (kb | pr | k) != 0);
-                            }
+                            for (int k = 0; k < BK / 16; ++k)
+                                slb_umma_f16_pair(d_tmem, da + 2 * k, dw + 2 * k, idesc, (kb | pr | k) != 0);
                         }
                     }
                     slb_umma_commit_pair(&empty[stage], 0b11);
