@@ -277,9 +277,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
             slb_mbar_wait(&tfull[acc], acc_phase);
             slb_tc_fence_after();
-            const int64_t m = (int64_t)m0 + quarter * 32 + lane;
-            const bool row_ok = m < p.M;
-            const float rs = (p.row_scale && row_ok) ? p.row_scale[m] : 1.0f;
+            const int64_t m = (int64_t)m0 + quarter * 32 + lane;  // the TMEM lane (= output row) this thread drains
+            const float rs = (p.row_scale && m < p.M) ? p.row_scale[m] : 1.0f;
 #pragma unroll 1
             for (int c = chunk0; c < BN / 32; c += kEpiWarps / 4) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
@@ -459,9 +458,8 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const int m0 = (t / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (t % tiles_n) * BN;
             mbar_wait_bounded(&tfull[acc], acc_phase, p.dbg, 4, t, -1, acc);
             slb_tc_fence_after();
-            const int64_t m = (int64_t)m0 + quarter * 32 + lane;
-            const bool row_ok = m < p.M;
-            const float rs = (p.row_scale && row_ok) ? p.row_scale[m] : 1.0f;
+            const int64_t m = (int64_t)m0 + quarter * 32 + lane;  // the TMEM lane (= output row) this thread drains
+            const float rs = (p.row_scale && m < p.M) ? p.row_scale[m] : 1.0f;
 #pragma unroll 1
             for (int c = chunk0; c < BN / 32; c += kEpiWarps / 4) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32);
