@@ -19,6 +19,8 @@ State-dict names follow open_clip (``visual.conv1.weight``, ``visual.bn1.running
 
 PARITY UNPINNED for the wiring: no golden vector of this tower exists in the reference (its tests construct
 ``OpenClip`` with ViT names only) and open_clip cannot be imported here; every arithmetic step is torch's own operator.
+Partial pins (tests/test_oracle_rn.py): the stride-1 bottleneck equals torchvision's ``Bottleneck`` with the same weights,
+the attention pool an explicit softmax restatement.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline may import this module.
 """

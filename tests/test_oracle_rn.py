@@ -72,3 +72,32 @@ def test_tower_host_config_matches_oracle_config():
         assert rn.block_plan(c) == rp.block_plan(o)
         assert abs(rn.flops_per_image(c) - rp.flops_per_image(o)) < 1
     assert len(rn.conv_names(rn.CONFIGS["RN50"])) == 3 + sum(3 * n + 1 for n in (3, 4, 6, 3))
+
+
+def test_stride1_bottleneck_matches_torchvision_bottleneck():
+    """Partial pin of the wiring on an independent implementation: for stride 1, open_clip's Bottleneck (no pooling) is
+    torchvision's (conv1x1-BN-ReLU, conv3x3-BN-ReLU, conv1x1-BN, + shortcut [conv1x1-BN when the width changes], ReLU).
+    The stride-2 blocks differ by design (average pool instead of a strided convolution) and stay unpinned."""
+    import torchvision
+
+    cfg = rp.CONFIGS["RN-tiny-test"]
+    sd = {k: v.double() for k, v in rp.init_weights(cfg).items()}
+    for prefix, inpl, pl, stride, ds in rp.block_plan(cfg)[:1]:  # layer1.0: 64 -> 256 channels, stride 1, with downsample
+        assert stride == 1 and ds
+        tv = torchvision.models.resnet.Bottleneck(
+            inpl, pl, stride=1,
+            downsample=torch.nn.Sequential(torch.nn.Conv2d(inpl, 4 * pl, 1, bias=False), torch.nn.BatchNorm2d(4 * pl))).double().eval()
+        tsd = {}
+        for i in (1, 2, 3):
+            tsd[f"conv{i}.weight"] = sd[f"{prefix}conv{i}.weight"]
+            for s in ("weight", "bias", "running_mean", "running_var"):
+                tsd[f"bn{i}.{s}"] = sd[f"{prefix}bn{i}.{s}"]
+        tsd["downsample.0.weight"] = sd[prefix + "downsample.0.weight"]
+        for s in ("weight", "bias", "running_mean", "running_var"):
+            tsd[f"downsample.1.{s}"] = sd[f"{prefix}downsample.1.{s}"]
+        missing = tv.load_state_dict(tsd, strict=False)
+        assert all(k.endswith("num_batches_tracked") for k in missing.missing_keys) and not missing.unexpected_keys
+        x = torch.randn(2, inpl, 9, 9, dtype=torch.float64)
+        with torch.no_grad():
+            want = tv(x)
+        assert torch.allclose(rp._bottleneck(x, sd, prefix, stride, ds), want, rtol=1e-12, atol=1e-12)
