@@ -892,6 +892,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                 if (!half) xch[r] = m_row;
                 asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
                 m_row = xch[r];
+                // xch aliases the P tile: nobody may start writing P before every row has read its maximum
+                asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
             }
             tc_wait(s_full, (uint32_t)(it & 1), p.dbg, 6);
             slb_tc_fence_after();
@@ -958,7 +960,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             if (warp == 2) TC_TRACE(8, it - nblk);  // P written and published
         }
         // ---- row sums of the two column halves, then O = (main + corr) / (scales * l); each warp stores 32 of the 64 dims ----
-        tc_wait(o_full, 0, p.dbg, 0);  // every P V has completed: the P tile is idle and can carry the exchange
+        // every P V has completed, hence every warp's P store before it (store -> fence.proxy.async -> p_full -> MMA -> commit
+        // -> o_full): the P tile is idle and can carry the exchange. (compute-sanitizer racecheck does not follow ordering
+        // through mbarriers / tcgen05.commit and reports the store below against the P stores.)
+        tc_wait(o_full, 0, p.dbg, 0);
         slb_tc_fence_after();
         if (warp == 2) TC_TRACE(9, 0);  // O complete
         if (half) xch[128 + r] = l_row;
