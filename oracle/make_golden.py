@@ -13,6 +13,10 @@ Fixtures (inputs + the reference's outputs):
   scores.npz            clarity / similarity (all shape branches) / polysemanticity (incl. the small-cluster fallback)
   scores_poly.npz       reference polysemanticity / clarity of the seeded cases of tests/polysem_cases.py (outputs only)
   cache_format/         one ActMaxCache.store() directory written by the reference (file names, keys, metadata)
+  collect_large.npz     full-size hook fixture: 3 batches of (256, 2048, 7, 7) post-ReLU maps (regenerated from a seed by
+                        tests/collect_cases.py; only a checksum of the inputs and the reference's outputs are stored), k = 20
+  text_probe.npz        lens._embed_text_probes with and without templates over a deterministic stand-in FM
+                        (tests/collect_cases.py:FakeTextFM): pins the template-major / (q t) regrouping
 """
 
 from __future__ import annotations
@@ -205,6 +209,32 @@ def gen_scores_poly():
     np.savez_compressed(GOLD / "scores_poly.npz", **out)
 
 
+def gen_collect_large():
+    """k = 20, batch 256, C = 2048 (ResNet-50 layer4 geometry) through the reference's hooks."""
+    from semanticlens.component_visualization import aggregators as A
+    from tests.collect_cases import LARGE, large_maps
+
+    maps = [torch.from_numpy(m) for m in large_maps()]
+    am = run_reference_hooks(maps, A.aggregate_conv_mean, LARGE["k"])
+    np.savez_compressed(
+        GOLD / "collect_large.npz",
+        checksum=np.array([float(m.double().sum()) for m in maps]),
+        ref_bits=bits_of(am.activations),
+        ref_ids=am.sample_ids.numpy().astype(np.int32),
+    )
+
+
+def gen_text_probe():
+    from semanticlens import lens as L
+    from tests.collect_cases import TEXT_PROBE, FakeTextFM
+
+    fm = FakeTextFM()
+    out = {}
+    for name, (queries, templates, bs) in TEXT_PROBE.items():
+        out[name] = L._embed_text_probes(fm, list(queries), list(templates) if templates else None, bs).numpy()
+    np.savez_compressed(GOLD / "text_probe.npz", **out)
+
+
 def main():
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     refshim.import_reference()
@@ -213,6 +243,8 @@ def main():
     gen_cache_format()
     gen_scores()
     gen_scores_poly()
+    gen_collect_large()
+    gen_text_probe()
     for f in sorted(GOLD.rglob("*")):
         if f.is_file():
             print(f"{f.relative_to(ROOT)}  {f.stat().st_size} B")

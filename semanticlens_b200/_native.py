@@ -177,10 +177,12 @@ def load(require_device: bool = False):
                 "(there is no CPU fallback for the B200 kernels)"
             )
         lib = ctypes.CDLL(str(_LIB_PATH))
+        absent = [name for name in _PROTOS if not hasattr(lib, name)]
+        if absent:
+            raise SlbError(f"{_LIB_PATH} is stale: it does not export {absent[:4]}{' ...' if len(absent) > 4 else ''}; "
+                           "rebuild it with `python -m semanticlens_b200.csrc.build --force`")
         for name, (res, args) in _PROTOS.items():
-            fn = getattr(lib, name, None)
-            if fn is None:
-                continue  # checked by tests/test_abi.py against the header
+            fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
         _lib = lib

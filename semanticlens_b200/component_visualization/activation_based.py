@@ -11,8 +11,9 @@ Differences that are not API-visible:
   batches are copied host->device from pinned memory with ``non_blocking=True`` and the logits are not copied back
   (reference :352 does ``model(images.to(device)).cpu()``);
 * when ``torch.distributed`` is initialised with world_size R > 1, rank r sweeps and embeds the contiguous index
-  range ``[r*ceil(N/R), (r+1)*ceil(N/R))``; the per-rank top-k states are exchanged with ONE all-gather and merged by
-  the K2 list-merge kernel, the embedding shards with one more all-gather (``semanticlens_b200.distributed``);
+  balanced shard of the index range; the per-rank top-k states are exchanged with ONE all-gather and merged by the K2
+  list-merge kernel, then one more all-gather moves only the embedding rows the merged top-k refers to
+  (``semanticlens_b200.distributed``);
 * embeddings stay in HBM and ``embeds[sample_ids]`` is the K5 gather kernel; the concept DB is returned on the CPU
   like the reference unless ``output_device`` is set.
 """
@@ -166,6 +167,7 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
         self.dataset = dataset_model
         self.dataset_fm = dataset_fm
         self.output_device = "cpu"  # where _compute_concept_db leaves the (C, k, D) tensors
+        self.exchange = "winners"  # distributed embed exchange: "winners" (rows the top-k refers to) or "all"
         self.show_progress = True
         self._init_cache_dir(cache_dir)
         self._validate_args()
@@ -251,27 +253,38 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
 
     # -- collect --------------------------------------------------------------------------------------
     def run(self, batch_size=32, num_workers=0):
-        """Sweep ``dataset_model`` (or load the cached result) -> ``{layer: ActMax}`` (reference :309-339)."""
-        if self._cache_root is None:
+        """Sweep ``dataset_model`` (or load the cached result) -> ``{layer: ActMax}`` (reference :309-339).
+
+        Distributed: whether the cache is warm is decided by rank 0 alone and its states are sent to the other ranks, so
+        a cache directory only rank 0 can see cannot make the ranks disagree about entering the sweep's collectives."""
+        if not self.caching:
             logger.debug("No cache root provided, running computation...")
             return self._run(batch_size=batch_size, num_workers=num_workers)
-        try:
-            self.actmax_cache.load(self.storage_dir)
+        rank, world_size = sdist.world()
+        hit = False
+        if rank == 0:
+            try:
+                self.actmax_cache.load(self.storage_dir)
+                hit = True
+            except FileNotFoundError:
+                logger.debug(f"Activation maximization cache not found at {self.storage_dir}. Running computation...")
+        if world_size > 1:
+            hit = sdist.agree(hit, self.device)
+            if hit:
+                sdist.share_actmax_from_rank0(self.actmax_cache)
+        if hit:
             return self.actmax_cache.cache
-        except FileNotFoundError:
-            logger.debug(f"Activation maximization cache not found at {self.storage_dir}. Running computation...")
-            return self._run(batch_size=batch_size, num_workers=num_workers)
+        return self._run(batch_size=batch_size, num_workers=num_workers)
 
     @torch.no_grad()
     def _run(self, batch_size: int = 64, num_workers: int = 0):
         """The activation sweep (reference :341-358), image-sharded across ranks when distributed."""
+        sdist.require_items_per_rank(len(self.dataset))
         shard = sdist.image_shard(len(self.dataset))
         device = self.device
         dataloader = _batches(self.dataset, shard, batch_size, num_workers, device)
         if shard.world > 1:
             # ids are positions in iteration order; a shard starts at its offset, on a fresh state
-            if shard.hi <= shard.lo:
-                raise ValueError("the dataset must have at least one item per rank")
             for layer in self.layer_names:
                 self.actmax_cache.cache[layer] = type(self.actmax_cache.cache[layer])(self.actmax_cache.n_collect)
                 self.actmax_cache.sample_idx_counter[layer] = shard.lo
@@ -294,17 +307,28 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
     # -- embed + gather -------------------------------------------------------------------------------
     @torch.no_grad()
     def _compute_concept_db(self, fm, batch_size=32, **kwargs):
-        """``{layer: embeds[sample_ids]}`` with embeds = fm image embeddings of ``dataset_fm`` (reference :360-390)."""
-        self.run(batch_size=batch_size, **kwargs)
+        """``{layer: embeds[sample_ids]}`` with embeds = fm image embeddings of ``dataset_fm`` (reference :360-390).
 
-        embeds = self._embed_vision_dataset(fm, batch_size, **kwargs)
+        Distributed: each rank embeds its shard and only the rows the merged top-k refers to are exchanged
+        (``sdist.exchange_winner_rows``); set ``exchange = "all"`` to all-gather the whole table instead."""
+        self.run(batch_size=batch_size, **kwargs)
+        rank, world_size = sdist.world()
+        ids = {name: self.get_max_reference(name) for name in self.layer_names}
+
+        if world_size > 1 and self.exchange == "winners":
+            local, shard = self._embed_vision_dataset(fm, batch_size, _gather=False, **kwargs)
+            dev_ids = [ids[name].to(local.device) for name in self.layer_names]
+            embeds, remapped = sdist.exchange_winner_rows(local, shard, dev_ids)
+            ids = dict(zip(self.layer_names, remapped))
+        else:
+            embeds = self._embed_vision_dataset(fm, batch_size, **kwargs)
 
         concept_db = dict()
         to_host = torch.device(self.output_device).type == "cpu"
         for layer_name in self.layer_names:
-            ids = self.get_max_reference(layer_name)
             if embeds.is_cuda:
-                db = ops.gather_rows(embeds, ids)  # K5; python-negative semantics: id -1 -> last image
+                table = embeds if embeds.dtype == torch.float32 else embeds.float()
+                db = ops.gather_rows(table, ids[layer_name])  # K5; python-negative semantics: id -1 -> last image
                 if to_host:
                     # asynchronous D2H into pinned memory (the next layer's gather runs meanwhile); one sync below
                     host = torch.empty(db.shape, dtype=db.dtype, pin_memory=True)
@@ -313,13 +337,15 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
                 else:
                     concept_db[layer_name] = db.to(self.output_device)
             else:
-                concept_db[layer_name] = embeds[ids]
+                concept_db[layer_name] = embeds[ids[layer_name]]
         if embeds.is_cuda and to_host:
             torch.cuda.current_stream(embeds.device).synchronize()
         return concept_db
 
-    def _embed_vision_dataset(self, fm, batch_size, **kwargs):
-        """Embed every item of ``dataset_fm`` -> (N, D) fp32 (reference :392-433); stays on the GPU."""
+    def _embed_vision_dataset(self, fm, batch_size, _gather=True, **kwargs):
+        """Embed every item of ``dataset_fm`` -> (N, D) fp32 (reference :392-433); stays on the GPU.
+
+        ``_gather=False`` (distributed, internal) returns ``(this rank's rows, shard)`` without the all-gather."""
         fm.to(self.device)
 
         def item_list_collate(batch):
@@ -328,6 +354,7 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
                 return [item[0] for item in batch]
             return list(batch)
 
+        sdist.require_items_per_rank(len(self.dataset_fm), "foundation-model dataset")
         shard = sdist.image_shard(len(self.dataset_fm))
         loader = _batches(self.dataset_fm, shard, batch_size, kwargs.get("num_workers", 0), self.device,
                           collate_fn=item_list_collate)
@@ -341,7 +368,10 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
             embeds = torch.cat(embeds)
         else:
             embeds = torch.empty((0, 0), dtype=torch.float32, device=self.device)
+        assert embeds.shape[0] == shard.hi - shard.lo, "Number of embeddings does not match number of ids!"
 
+        if not _gather:
+            return embeds, shard
         if shard.world > 1:
             embeds = sdist.all_gather_rows(embeds, shard, len(self.dataset_fm))
 

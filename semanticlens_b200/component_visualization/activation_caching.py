@@ -150,33 +150,42 @@ class ActMax:
             return torch.tensor([], dtype=torch.int64)
         return torch.where(self.activations.abs().sum(dim=1) > 0)[0]
 
-    # -- persistence (byte-compatible with the reference, :158-216) -------------------------------
+    # -- persistence ---------------------------------------------------------------------------
+    # On-disk contract shared with the reference (activation_caching.py:158-216) so caches interchange: one safetensors
+    # file with tensors "activations" (bf16) and "sample_ids" (int64) and string metadata carrying at least
+    # n_collect and n_latents. Everything else about how the file is produced / parsed is this module's own.
     def store(self, file_path: str | Path, metadata: dict[str, str] | None = None):
         if not self.is_setup:
-            logger.warning("Attempted to store an un-initialized ActMax instance; skipping.")
+            logger.warning("ActMax.store: nothing collected yet, %s not written", file_path)
             return
-        tensors = {
-            "activations": self.activations,
-            "sample_ids": self.sample_ids,
-        }
-        safetensors.torch.save_file(tensors, file_path, metadata=metadata)
-        logger.debug(f"Stored ActMax data to {file_path}")
+        _write_state_file(Path(file_path), self.activations, self.sample_ids, metadata)
 
     @classmethod
     def load(cls, file_path: str | Path) -> ActMax:
-        with safetensors.safe_open(file_path, framework="pt") as f:
-            metadata = f.metadata()
-            if metadata is None:
-                raise ValueError(f"File {file_path} is missing required metadata for loading.")
-            tensors = {k: f.get_tensor(k) for k in f.keys()}
+        meta, vals, ids = _read_state_file(Path(file_path))
+        if meta is None or "n_collect" not in meta or "n_latents" not in meta:
+            raise ValueError(f"{file_path} carries no n_collect / n_latents metadata: not an ActMax file")
+        state = cls(n_collect=int(meta["n_collect"]), n_latents=int(meta["n_latents"]))
+        state._cpu_vals = vals.to(torch.bfloat16).contiguous()
+        state._cpu_ids = ids.to(torch.int64).contiguous()
+        state._dev_vals = state._dev_ids = None
+        return state
 
-        n_collect = int(metadata["n_collect"])
-        n_latents = int(metadata["n_latents"])
 
-        instance = cls(n_collect=n_collect, n_latents=n_latents)
-        instance.activations = tensors["activations"]
-        instance.sample_ids = tensors["sample_ids"]
-        return instance
+def _write_state_file(path: Path, vals: torch.Tensor, ids: torch.Tensor, metadata: dict[str, str] | None) -> None:
+    """Write to a sibling temporary name and rename, so a reader (another rank, a resumed run) never sees half a file."""
+    tmp = path.with_name(path.name + ".partial")
+    safetensors.torch.save_file({"activations": vals, "sample_ids": ids}, str(tmp), metadata=metadata)
+    tmp.replace(path)
+    logger.debug("wrote %s", path)
+
+
+def _read_state_file(path: Path, header_only: bool = False):
+    with safetensors.safe_open(str(path), framework="pt") as f:
+        meta = f.metadata()
+        if header_only:
+            return meta, None, None
+        return meta, f.get_tensor("activations"), f.get_tensor("sample_ids")
 
 
 class ActCache:
@@ -246,6 +255,8 @@ class ActMaxCache(ActCache):
                 want = 4 if fn._slb_kind == "conv" else 3
                 if outs.ndim != want:
                     fn(outs)  # raises the reference's ValueError for a wrong rank
+                if fn._slb_op == _native.AGG_TOKEN and not -outs.shape[1] <= fn._slb_token < outs.shape[1]:
+                    fn(outs)  # raises the IndexError python indexing gives the reference
                 batch_size = outs.shape[0]
                 self.cache[layer_name].update_from_map(
                     outs, fn._slb_op, fn._slb_kind, fn._slb_token, self.sample_idx_counter[layer_name]
@@ -278,73 +289,60 @@ class ActMaxCache(ActCache):
 
     @property
     def metadata(self) -> dict[str, str]:
-        return dict(
-            aggregation_fn_name=self.agg_fn_name,
-            n_collect=str(self.n_collect),
-            layer_names=str(list(self.cache.keys())),
-        )
+        """Key order matters: Lens joins the values into the concept-DB file name (reference lens.py:308-316)."""
+        return {
+            "aggregation_fn_name": self.agg_fn_name,
+            "n_collect": str(self.n_collect),
+            "layer_names": str(list(self.cache)),
+        }
+
+    # File grammar shared with the reference (:434-465, :495-503): "<agg fn>-<n_collect>-<layer>.safetensors", metadata
+    # keys aggregation_fn_name / n_collect / n_latents / layer_name.
+    def _layer_path(self, directory: Path, layer_name: str) -> Path:
+        return directory / f"{self.agg_fn_name}-{self.n_collect}-{layer_name}.safetensors"
 
     def store(self, directory: Path | str):
-        """One ``{agg_fn}-{n_collect}-{layer}.safetensors`` per layer (reference :434-465)."""
         directory = Path(directory)
         directory.mkdir(parents=True, exist_ok=True)
-
-        for layer_name, act_max_instance in self.cache.items():
-            if not act_max_instance.is_setup:
-                logger.warning(f"Skipping layer '{layer_name}' as it has no data.")
+        written = 0
+        for layer_name, state in self.cache.items():
+            if not state.is_setup:
+                logger.warning("layer '%s' saw no batch; no file written for it", layer_name)
                 continue
-
-            metadata = {
+            state.store(self._layer_path(directory, layer_name), metadata={
                 "aggregation_fn_name": self.agg_fn_name,
                 "n_collect": str(self.n_collect),
-                "n_latents": str(act_max_instance.n_latents),
+                "n_latents": str(state.n_latents),
                 "layer_name": layer_name,
-            }
-            fname = "-".join([str(v) for k, v in metadata.items() if k not in ["n_latents"]]) + ".safetensors"
-            act_max_instance.store(directory / fname, metadata=metadata)
-
-        logger.info(f"Cache saved successfully to {directory}")
+            })
+            written += 1
+        logger.info("act-max cache: %d layer file(s) written to %s", written, directory)
 
     def load(self, directory: Path | str):
-        """Load every layer's file; any miss or metadata mismatch is a FileNotFoundError (reference :467-534)."""
+        """All layers or nothing: every file is located and its header validated before any state is replaced. A missing
+        directory / file or a header written for another aggregation function or n_collect is reported as
+        ``FileNotFoundError`` — the signal ``run()`` and the constructor treat as "cache miss" (reference :467-534)."""
         directory = Path(directory)
         if not directory.is_dir():
-            raise FileNotFoundError(f"Cache directory not found: {directory}")
-
-        expected_agg_fn_name = self.aggregation_fn.__name__
-        logger.info(f"Loading cache for aggregation fn: '{expected_agg_fn_name}'")
-
-        loaded_count = 0
+            raise FileNotFoundError(f"no act-max cache at {directory}")
+        paths = {}
         for layer_name in self.layer_names:
-            fname = "-".join([self.agg_fn_name, str(self.n_collect), layer_name]) + ".safetensors"
-            fpath = directory / fname
-
-            if not fpath.exists():
-                logger.warning(f"File not found for layer '{layer_name}': {fpath}")
-                raise FileNotFoundError(f"Expected file not found: {fpath}")
-
-            try:
-                with safetensors.safe_open(fpath, framework="pt") as f:
-                    metadata = f.metadata()
-
-                    if metadata.get("aggregation_fn_name") != expected_agg_fn_name:
-                        raise ValueError(
-                            f"Mismatch in aggregation function for layer '{layer_name}'. "
-                            f"Expected '{expected_agg_fn_name}', but file has '{metadata.get('aggregation_fn_name')}'."
-                        )
-                    if int(metadata.get("n_collect")) != self.n_collect:
-                        raise ValueError(
-                            f"Mismatch in n_collect for layer '{layer_name}'. "
-                            f"Expected '{self.n_collect}', but file has '{metadata.get('n_collect')}'."
-                        )
-            except ValueError as e:
-                logger.warning(f"Validation failed for layer '{layer_name}': {e}")
-                raise FileNotFoundError(f"Expected file not found: {fpath}")
-
-            self.cache[layer_name] = ActMax.load(fpath)
-            loaded_count += 1
-
-        if loaded_count == 0:
-            logger.warning(f"No matching cache files were found and loaded from {directory}")
+            path = self._layer_path(directory, layer_name)
+            if not path.is_file():
+                raise FileNotFoundError(f"act-max cache has no file for layer '{layer_name}': {path}")
+            meta = _read_state_file(path, header_only=True)[0] or {}
+            problems = []
+            if meta.get("aggregation_fn_name") != self.agg_fn_name:
+                problems.append(f"aggregation_fn_name={meta.get('aggregation_fn_name')!r}, wanted {self.agg_fn_name!r}")
+            if str(meta.get("n_collect")) != str(self.n_collect):
+                problems.append(f"n_collect={meta.get('n_collect')!r}, wanted {self.n_collect}")
+            if problems:
+                logger.warning("ignoring %s: %s", path, "; ".join(problems))
+                raise FileNotFoundError(f"act-max cache file does not match this configuration: {path}")
+            paths[layer_name] = path
+        loaded = {layer_name: ActMax.load(path) for layer_name, path in paths.items()}
+        self.cache.update(loaded)
+        if loaded:
+            logger.info("act-max cache: %d layer(s) loaded from %s", len(loaded), directory)
         else:
-            logger.info(f"Successfully loaded data for {loaded_count} layer(s) from {directory}")
+            logger.warning("act-max cache: no layers requested, nothing loaded from %s", directory)

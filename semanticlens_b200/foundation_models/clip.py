@@ -58,14 +58,23 @@ class OpenClip(AbstractVLM):
         seed = kwargs.pop("seed", 1)
         fmt = {"f16": N.PLANE_F16, "bf16": N.PLANE_BF16}[kwargs.pop("plane_format", "f16")]
         pretrained = kwargs.pop("pretrained", None)
-        kwargs.pop("load_weights", None)
+        load_weights = kwargs.pop("load_weights", True)
         if kwargs:
             raise TypeError(f"unexpected arguments {sorted(kwargs)}")
         if sd is None and ckpt is not None:
             sd = _load_checkpoint(ckpt)
         if sd is None:
-            if pretrained:
-                logger.warning("pretrained='%s' cannot be downloaded here; using random weights (seed %d)", pretrained, seed)
+            # open_clip would download here (pretrained=<tag>, or an hf-hub: model id). Nothing can be fetched by this
+            # package, and a silently random tower yields a meaningless concept DB: random init must be asked for, the
+            # way the reference's own tests do (load_weights=False).
+            wants_pretrained = bool(pretrained) or str(url).startswith("hf-hub:")
+            if wants_pretrained and load_weights:
+                raise ValueError(
+                    f"OpenClip('{url}'" + (f", pretrained='{pretrained}'" if pretrained else "") + ") names pretrained "
+                    "weights, which this package cannot download: pass state_dict= or checkpoint_path= (open_clip "
+                    "naming), or load_weights=False for a randomly initialised tower")
+            if not wants_pretrained:
+                logger.warning("OpenClip('%s') without pretrained weights: randomly initialised tower (seed %d)", url, seed)
             sd = rn.random_state_dict(self.cfg, seed) if is_rn else vit.random_state_dict(self.cfg, seed)
         self.model = rn.RnTower(self.cfg, sd, device, fmt) if is_rn else vit.VitTower(self.cfg, sd, device, fmt)
         # text side: built lazily (encode_text / tokenize), only for the CLIP towers
@@ -79,6 +88,12 @@ class OpenClip(AbstractVLM):
 
     def __repr__(self):
         return f"{self.__class__.__name__}(url='{self.url}', model={type(self.model).__name__}[B200])"
+
+    @property
+    def resize_mode(self) -> str:
+        """open_clip's ``preprocess_cfg["resize_mode"]``: "shortest" for the CLIP towers, "squash" for SigLIP (its
+        ``_slpcfg`` / the model configs' preprocess_cfg: Resize((S, S), bicubic) without a crop)."""
+        return getattr(self.cfg, "resize_mode", "shortest")
 
     @property
     def device(self):
@@ -139,13 +154,13 @@ class OpenClip(AbstractVLM):
         out = torch.empty((len(items), 3, S, S), dtype=torch.uint8, device=dev)
         for i, im in enumerate(items):
             if im.mode != "RGB":
-                out[i].copy_(torch.from_numpy(_pil_to_chw_u8(im, S)), non_blocking=True)
+                out[i].copy_(torch.from_numpy(_pil_to_chw_u8(im, S, self.resize_mode)), non_blocking=True)
                 continue
             hwc = torch.from_numpy(np.array(im, dtype=np.uint8)).to(dev, non_blocking=True)
             if im.size == (S, S):
                 out[i].copy_(hwc.permute(2, 0, 1))
             else:
-                ops.resize_center_crop_u8(hwc, S, out=out[i])
+                ops.resize_center_crop_u8(hwc, S, out=out[i], squash=self.resize_mode == "squash")
         return out
 
     def _to_u8_batch(self, img) -> torch.Tensor:
@@ -160,7 +175,7 @@ class OpenClip(AbstractVLM):
             return self._to_u8_batch(torch.stack(list(items)))
         out = np.empty((len(items), 3, S, S), dtype=np.uint8)
         for i, im in enumerate(items):
-            out[i] = _pil_to_chw_u8(im, S)
+            out[i] = _pil_to_chw_u8(im, S, self.resize_mode)
         return torch.from_numpy(out)
 
     # -- text side (Lens.text_probing) --------------------------------------------------------
@@ -202,13 +217,15 @@ class SigLipV2(OpenClip):
         super().__init__(url=self.URL, device=device, **kwargs)
 
 
-def _pil_to_chw_u8(im, S: int) -> np.ndarray:
-    """open_clip eval transform up to (not including) ToTensor: Resize(S, bicubic) on the shorter side, CenterCrop(S),
-    convert to RGB."""
+def _pil_to_chw_u8(im, S: int, resize_mode: str = "shortest") -> np.ndarray:
+    """open_clip eval transform up to (not including) ToTensor. resize_mode "shortest" (CLIP): Resize(S, bicubic) on the
+    shorter side, CenterCrop(S); "squash" (SigLIP): Resize((S, S), bicubic), aspect ratio not kept, no crop. Then RGB."""
     from PIL import Image
 
     w, h = im.size
-    if (w, h) != (S, S):
+    if (w, h) != (S, S) and resize_mode == "squash":
+        im = im.resize((S, S), Image.BICUBIC)
+    elif (w, h) != (S, S):
         if w <= h:
             nw, nh = S, max(S, int(S * h / w))
         else:

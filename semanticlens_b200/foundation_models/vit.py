@@ -36,6 +36,12 @@ class VitConfig:
         return self.arch == "clip"
 
     @property
+    def resize_mode(self) -> str:
+        """Eval-transform geometry of open_clip's preprocess_cfg: CLIP resizes the shorter side and centre-crops,
+        SigLIP squashes the whole image to (S, S)."""
+        return "squash" if self.arch == "siglip" else "shortest"
+
+    @property
     def tokens(self) -> int:
         return (self.image_size // self.patch) ** 2 + (1 if self.has_cls else 0)
 
@@ -169,9 +175,16 @@ class VitTower:
         self.cfg = cfg
         self.plane_format = plane_format
         self.state_dict = {k: v.detach().to(torch.float32).cpu() for k, v in state_dict.items() if k.startswith("visual.")}
-        missing = [k for k in random_state_dict_keys(cfg) if k not in self.state_dict]
+        want = expected_shapes(cfg)
+        missing = [k for k in want if k not in self.state_dict]
         if missing:
             raise KeyError(f"state dict is missing {len(missing)} image-tower tensors, e.g. {missing[:3]}")
+        # a checkpoint of another architecture must fail here, not as an out-of-bounds read inside a GEMM
+        wrong = [(k, tuple(self.state_dict[k].shape), shp) for k, shp in want.items() if tuple(self.state_dict[k].shape) != shp]
+        if wrong:
+            k, got, shp = wrong[0]
+            raise ValueError(f"state dict does not fit '{cfg.name}': {len(wrong)} tensor(s) have the wrong shape, e.g. "
+                             f"{k} is {got}, expected {shp}")
         self._device = torch.device("cpu")
         self._struct = None
         self._keep: list = []
@@ -294,17 +307,43 @@ class VitTower:
         return out
 
 
-def random_state_dict_keys(cfg: VitConfig) -> list[str]:
+def expected_shapes(cfg: VitConfig) -> dict[str, tuple]:
+    """Name -> shape of every image-tower tensor of an open_clip checkpoint for ``cfg`` (what ``_upload`` indexes)."""
+    W, M, P, T, L = cfg.width, cfg.mlp, cfg.patch, cfg.tokens, cfg.layers
     if cfg.arch == "siglip":
-        return list(_random_siglip_state_dict(VitConfig(cfg.name, cfg.patch, cfg.patch, 8, cfg.layers, 1, 8, 8, arch="siglip"), 0))
-    keys = ["visual.conv1.weight", "visual.class_embedding", "visual.positional_embedding", "visual.ln_pre.weight",
-            "visual.ln_pre.bias", "visual.ln_post.weight", "visual.ln_post.bias", "visual.proj"]
-    for i in range(cfg.layers):
-        p = f"visual.transformer.resblocks.{i}."
-        keys += [p + s for s in ("ln_1.weight", "ln_1.bias", "attn.in_proj_weight", "attn.in_proj_bias",
-                                 "attn.out_proj.weight", "attn.out_proj.bias", "ln_2.weight", "ln_2.bias",
-                                 "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias")]
-    return keys
+        t = "visual.trunk."
+        shapes = {
+            t + "patch_embed.proj.weight": (W, 3, P, P), t + "patch_embed.proj.bias": (W,), t + "pos_embed": (1, T, W),
+            t + "norm.weight": (W,), t + "norm.bias": (W,), t + "attn_pool.latent": (1, 1, W),
+            t + "attn_pool.q.weight": (W, W), t + "attn_pool.q.bias": (W,),
+            t + "attn_pool.kv.weight": (2 * W, W), t + "attn_pool.kv.bias": (2 * W,),
+            t + "attn_pool.proj.weight": (W, W), t + "attn_pool.proj.bias": (W,),
+            t + "attn_pool.norm.weight": (W,), t + "attn_pool.norm.bias": (W,),
+            t + "attn_pool.mlp.fc1.weight": (M, W), t + "attn_pool.mlp.fc1.bias": (M,),
+            t + "attn_pool.mlp.fc2.weight": (W, M), t + "attn_pool.mlp.fc2.bias": (W,),
+        }
+        block = {"norm1.weight": (W,), "norm1.bias": (W,), "attn.qkv.weight": (3 * W, W), "attn.qkv.bias": (3 * W,),
+                 "attn.proj.weight": (W, W), "attn.proj.bias": (W,), "norm2.weight": (W,), "norm2.bias": (W,),
+                 "mlp.fc1.weight": (M, W), "mlp.fc1.bias": (M,), "mlp.fc2.weight": (W, M), "mlp.fc2.bias": (W,)}
+        prefix = t + "blocks.{}."
+    else:
+        shapes = {
+            "visual.conv1.weight": (W, 3, P, P), "visual.class_embedding": (W,), "visual.positional_embedding": (T, W),
+            "visual.ln_pre.weight": (W,), "visual.ln_pre.bias": (W,), "visual.ln_post.weight": (W,),
+            "visual.ln_post.bias": (W,), "visual.proj": (W, cfg.embed_dim),
+        }
+        block = {"ln_1.weight": (W,), "ln_1.bias": (W,), "attn.in_proj_weight": (3 * W, W), "attn.in_proj_bias": (3 * W,),
+                 "attn.out_proj.weight": (W, W), "attn.out_proj.bias": (W,), "ln_2.weight": (W,), "ln_2.bias": (W,),
+                 "mlp.c_fc.weight": (M, W), "mlp.c_fc.bias": (M,), "mlp.c_proj.weight": (W, M), "mlp.c_proj.bias": (W,)}
+        prefix = "visual.transformer.resblocks.{}."
+    for i in range(L):
+        for name, shape in block.items():
+            shapes[prefix.format(i) + name] = shape
+    return shapes
+
+
+def random_state_dict_keys(cfg: VitConfig) -> list[str]:
+    return list(expected_shapes(cfg))
 
 
 def flops_per_image(cfg: VitConfig) -> float:

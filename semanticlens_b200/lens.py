@@ -1,6 +1,6 @@
 """``Lens`` — orchestrator of the concept-database path; drop-in for ``semanticlens.lens`` (reference lens.py:27-480).
 
-Same functions, signatures, cache-file grammar and control flow as the reference. What changes underneath:
+Same functions, signatures and cache-file grammar as the reference. What changes underneath:
 ``cv._compute_concept_db(fm)`` is the B200 sweep + embed + gather, and ``_probe`` / ``eval_*`` call the libslb200 score
 kernels (``semanticlens_b200.scores``).
 """
@@ -13,6 +13,7 @@ import torch
 from safetensors.torch import load_file, save_file
 from tqdm.auto import tqdm
 
+from . import distributed as sdist
 from .component_visualization.base import AbstractComponentVisualizer
 from .foundation_models.base import AbstractVLM
 from .scores import clarity_score, polysemanticity_score, redundancy_score, similarity_score
@@ -45,30 +46,47 @@ def image_probing(fm, query, aggregated_concept_db):
 
 @torch.no_grad()
 def _embed_text_probes(fm, query: list[str], templates, batch_size):
-    """Reference lens.py:166-203, including its template layout: the templated list is built template-major
-    (``for t in templates for q in query``) but regrouped as ``(q t)`` — kept as is."""
-    if templates:
-        query_templated = [t.format(q) for t in templates for q in query]
-        empty_templates = [t.format("") for t in templates]
-        batch_size = batch_size or len(query_templated)
-        chunks = []
-        for b0 in tqdm(range(0, len(query_templated), batch_size), desc="text embedding ...", leave=False,
-                       disable=batch_size == len(query_templated)):
-            batch = query_templated[b0 : b0 + batch_size]
-            chunks.append(fm.encode_text(fm.tokenize(batch).to(fm.device)).cpu())
-        templated = torch.cat(chunks, dim=0)
-        empty = fm.encode_text(fm.tokenize(empty_templates).to(fm.device)).cpu()
-        q, t = len(query), len(templates)
-        return (templated.reshape(q, t, -1) - empty.reshape(1, t, -1)).mean(1)
-    return fm.encode_text(fm.tokenize(query).to(fm.device)).cpu()
+    """Text-query embeddings (reference lens.py:166-203).
+
+    Without templates: one embedding per query. With templates: every (template, query) prompt is embedded, the
+    embedding of the same template formatted with "" is subtracted, and the result is averaged per query. The prompt
+    list is built template-major (all queries under template 0, then template 1, ...) while the regrouping reads it as
+    ``(query, template)`` blocks — the reference's behaviour (lens.py:174 vs :196-199), which mixes queries unless one
+    of the two lists has a single entry. It is reproduced on purpose so results stay comparable."""
+
+    def embed(prompts):
+        return fm.encode_text(fm.tokenize(prompts).to(fm.device)).cpu()
+
+    if not templates:
+        return embed(query)
+    prompts = [template.format(q) for template in templates for q in query]
+    step = batch_size or len(prompts)
+    starts = range(0, len(prompts), step)
+    if len(starts) > 1:
+        starts = tqdm(starts, desc="text embedding ...", leave=False)
+    rows = torch.cat([embed(prompts[b0 : b0 + step]) for b0 in starts], dim=0)
+    baseline = embed([template.format("") for template in templates])
+    n_q, n_t = len(query), len(templates)
+    return (rows.view(n_q, n_t, rows.shape[-1]) - baseline.view(1, n_t, baseline.shape[-1])).mean(dim=1)
 
 
 @torch.no_grad()
 def _probe(query: torch.Tensor, aggregated_concept_db):
-    """K6 behind the reference's tensor-or-dict dispatch (lens.py:207-214)."""
-    if isinstance(aggregated_concept_db, torch.Tensor):
-        return similarity_score(query.to(aggregated_concept_db.device), aggregated_concept_db)
-    return {key: similarity_score(query.to(value.device), value) for key, value in aggregated_concept_db.items()}
+    """K6 (``similarity_score``) for one aggregated concept DB or a dict of them (reference lens.py:207-214)."""
+
+    def one(db):
+        return similarity_score(query.to(db.device), db)
+
+    if isinstance(aggregated_concept_db, dict):
+        return {layer: one(db) for layer, db in aggregated_concept_db.items()}
+    return one(aggregated_concept_db)
+
+
+def _per_layer(score_fn, db):
+    """The reference's eval_* dispatch (lens.py:391-480): a tensor is scored directly, a dict layer by layer."""
+    if isinstance(db, dict):
+        return {layer: score_fn(t) for layer, t in db.items()}
+    return score_fn(db)
 
 
 class Lens:
@@ -76,34 +94,40 @@ class Lens:
 
     def __init__(self, fm, device=None):
         self.fm = fm
-        self.device = device or self.fm.device
-        self.fm.to(self.device)
-        if not hasattr(self.fm, "name"):
-            self.fm.name = get_fallback_name(self.fm)
-            logger.debug(f"Assigned fallback name to foundation model: {self.fm.name}")
+        self.device = device if device is not None else fm.device
+        fm.to(self.device)
+        if not hasattr(fm, "name"):
+            fm.name = get_fallback_name(fm)  # names the concept-DB cache directory
+            logger.debug("foundation model has no .name; using %s", fm.name)
+
+    def concept_db_path(self, cv: AbstractComponentVisualizer):
+        """Cache file of ``cv``'s concept DB under this foundation model — the reference's grammar (lens.py:308-316):
+        ``<storage_dir>/concept_database/<fm.name>/concept_db-<agg fn>-<n_collect>-<layer list>.safetensors``."""
+        tags = [value for key, value in cv.metadata.items() if key not in ("dataset", "model")]
+        return cv.storage_dir / "concept_database" / self.fm.name / ("concept_db-" + "-".join(tags) + ".safetensors")
 
     def compute_concept_db(self, cv: AbstractComponentVisualizer, **kwargs) -> dict[str, torch.Tensor]:
-        """Concept DB of ``cv`` under ``self.fm``, cached as safetensors next to the act-max cache when ``cv.caching``
-        (file grammar of reference lens.py:308-316)."""
-        if cv.caching:
-            fdir = cv.storage_dir / "concept_database" / self.fm.name
-            fdir.mkdir(parents=True, exist_ok=True)
-            fname = (
-                "concept_db-"
-                + "-".join([v for k, v in cv.metadata.items() if k not in ["dataset", "model"]])
-                + ".safetensors"
-            )
-            fpath = fdir / fname
-            if fpath.exists():
-                logger.debug("Loading concept DB from cache")
-                return load_file(filename=fpath)
-            logger.debug("Computing concept DB and saving to cache")
-            concept_db = cv._compute_concept_db(self.fm, **kwargs)
-            save_file(tensors={k: v.cpu().contiguous() for k, v in concept_db.items()}, filename=fpath)
-            logger.debug(f"Saved concept DB to cache {fpath}")
-            return concept_db
-        logger.debug("Caching is not enabled. Computing Concept DB")
-        return cv._compute_concept_db(self.fm, **kwargs)
+        """Concept DB of ``cv`` under ``self.fm``; with ``cv.caching`` it is read from / written to
+        :meth:`concept_db_path`.
+
+        Under ``torch.distributed`` rank 0 decides hit or miss for everyone and is the only writer, and a barrier
+        follows the write, so no rank reads a half-written file or skips the collectives of
+        ``cv._compute_concept_db``. The cache directory must be visible to every rank that wants to read it."""
+        if not cv.caching:
+            logger.debug("Caching is not enabled. Computing Concept DB")
+            return cv._compute_concept_db(self.fm, **kwargs)
+        rank, _ = sdist.world()
+        path = self.concept_db_path(cv)
+        if sdist.agree(path.exists() if rank == 0 else False, getattr(cv, "device", None)):
+            logger.debug("Loading concept DB from cache %s", path)
+            return load_file(filename=path)
+        concept_db = cv._compute_concept_db(self.fm, **kwargs)
+        if rank == 0:
+            path.parent.mkdir(parents=True, exist_ok=True)
+            save_file(tensors={layer: t.cpu().contiguous() for layer, t in concept_db.items()}, filename=path)
+            logger.debug("Saved concept DB to cache %s", path)
+        sdist.barrier()
+        return concept_db
 
     def text_probing(self, query, aggregated_concept_db, templates=None, batch_size=None):
         return text_probing(self.fm, query, aggregated_concept_db, templates, batch_size)
@@ -112,16 +136,10 @@ class Lens:
         return image_probing(self.fm, query, aggregated_concept_db)
 
     def eval_clarity(self, concept_db):
-        if isinstance(concept_db, torch.Tensor):
-            return clarity_score(concept_db)
-        return {key: clarity_score(value) for key, value in concept_db.items()}
+        return _per_layer(clarity_score, concept_db)
 
     def eval_redundancy(self, aggregated_concept_db):
-        if isinstance(aggregated_concept_db, torch.Tensor):
-            return redundancy_score(aggregated_concept_db)
-        return {key: redundancy_score(value) for key, value in aggregated_concept_db.items()}
+        return _per_layer(redundancy_score, aggregated_concept_db)
 
     def eval_polysemanticity(self, concept_db):
-        if isinstance(concept_db, torch.Tensor):
-            return polysemanticity_score(concept_db)
-        return {key: polysemanticity_score(value) for key, value in concept_db.items()}
+        return _per_layer(polysemanticity_score, concept_db)

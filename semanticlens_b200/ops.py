@@ -18,12 +18,16 @@ def _dev_guard(t: torch.Tensor):
 # ------------------------------------------------------------------------------------------------
 # collect
 # ------------------------------------------------------------------------------------------------
-def describe_map(t: torch.Tensor, reduce_kind: str):
+def describe_map(t: torch.Tensor, reduce_kind: str, op: int | None = None):
     """Classify a hooked activation map for K1 without copying when possible.
 
     reduce_kind: "conv" (4-D, reduce H*W) or "tokens" (3-D, reduce dim 1).
     Returns (tensor_to_keep_alive, layout, B, C, inner).
     """
+    if t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        t = t.float()  # float64 / integer maps: the kernels read fp32, fp16, bf16
+    if reduce_kind != "conv" and op == N.AGG_TOKEN and not t.is_contiguous():
+        t = t.contiguous()  # the token select reads one (B, T, F) row per image: a permuted view is copied once
     if reduce_kind == "conv":
         B, C, H, W = t.shape
         if t.is_contiguous():
@@ -46,7 +50,7 @@ def agg_reduce(t: torch.Tensor, op: int, reduce_kind: str, token_pos: int = 0) -
     lib = N.load(require_device=True)
     N.require_cuda(t, "activation map")
     t = t.detach()
-    keep, layout, B, C, inner = describe_map(t, reduce_kind)
+    keep, layout, B, C, inner = describe_map(t, reduce_kind, op)
     out = torch.empty((B, C), dtype=torch.float32, device=t.device)
     if B == 0 or C == 0:
         return out
@@ -110,7 +114,7 @@ def agg_topk_update(
     lib = N.load(require_device=True)
     N.require_cuda(t, "activation map")
     t = t.detach()
-    keep, layout, B, C, inner = describe_map(t, reduce_kind)
+    keep, layout, B, C, inner = describe_map(t, reduce_kind, op)
     k = state_vals.shape[1]
     need = B * C
     if scratch is None or scratch.numel() < need or scratch.device != t.device:
@@ -151,8 +155,8 @@ def gather_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """K5: table[idx] for a 2-D fp32 table and an integer index tensor of any shape (python negatives wrap)."""
     lib = N.load(require_device=True)
     N.require_cuda(table, "table")
-    assert table.ndim == 2 and table.dtype == torch.float32
-    table = table.contiguous()
+    assert table.ndim == 2
+    table = table.detach().to(torch.float32).contiguous()  # a custom FM may hand over fp16 / bf16 embeddings
     idx_d = idx.to(device=table.device, dtype=torch.int64).contiguous()
     n, D = table.shape
     out = torch.empty((*idx.shape, D), dtype=torch.float32, device=table.device)
@@ -264,15 +268,20 @@ def resized_size(w: int, h: int, S: int) -> tuple[int, int]:
     return max(S, int(S * w / h)), S
 
 
-def resize_center_crop_u8(img_hwc: torch.Tensor, S: int, out: torch.Tensor | None = None) -> torch.Tensor:
-    """(h, w, 3) u8 CUDA -> (3, S, S) u8: Resize(S, bicubic) + CenterCrop(S), byte-identical to Pillow / torchvision."""
+def resize_center_crop_u8(img_hwc: torch.Tensor, S: int, out: torch.Tensor | None = None,
+                          squash: bool = False) -> torch.Tensor:
+    """(h, w, 3) u8 CUDA -> (3, S, S) u8: Resize(S, bicubic) + CenterCrop(S), or with ``squash`` Resize((S, S), bicubic)
+    without a crop; byte-identical to Pillow / torchvision."""
     lib = N.load(require_device=True)
     N.require_cuda(img_hwc, "img_hwc")
     assert img_hwc.dtype == torch.uint8 and img_hwc.ndim == 3 and img_hwc.shape[2] == 3
     img_hwc = img_hwc.contiguous()
     h, w = int(img_hwc.shape[0]), int(img_hwc.shape[1])
-    nw, nh = resized_size(w, h, S)
-    left, top = int(round((nw - S) / 2.0)), int(round((nh - S) / 2.0))
+    if squash:
+        nw, nh, left, top = S, S, 0, 0
+    else:
+        nw, nh = resized_size(w, h, S)
+        left, top = int(round((nw - S) / 2.0)), int(round((nh - S) / 2.0))
     if out is None:
         out = torch.empty((3, S, S), dtype=torch.uint8, device=img_hwc.device)
     assert out.is_contiguous() and tuple(out.shape) == (3, S, S) and out.device == img_hwc.device
@@ -413,6 +422,20 @@ def _pad64(d: int) -> int:
     return (d + 63) // 64 * 64
 
 
+MAX_FEATURES = 2048  # the score kernels keep one row in registers: 16 x 128 floats per warp
+
+
+def _pad_features(x: torch.Tensor) -> torch.Tensor:
+    """Zero-pad the last dimension to a multiple of 4 (the kernels read 16-byte vectors); zero columns change neither
+    norms nor dot products. Embedding widths above MAX_FEATURES are rejected with a plain ValueError."""
+    D = x.shape[-1]
+    if D > MAX_FEATURES:
+        raise ValueError(f"the B200 score kernels support at most {MAX_FEATURES} features per row (got {D})")
+    if D % 4 == 0:
+        return x
+    return torch.nn.functional.pad(x, (0, 4 - D % 4))
+
+
 UNIT_ROW_PLANE_SCALE = 1024.0  # unit-norm rows: elements ~ 1/sqrt(D)
 
 
@@ -422,7 +445,7 @@ def normalize_split_rows(x: torch.Tensor, eps: float = 1e-12, fmt: int = N.PLANE
     lib = N.load(require_device=True)
     N.require_cuda(x, "x")
     assert x.ndim == 2 and x.dtype == torch.float32
-    x = x.contiguous()
+    x = _pad_features(x).contiguous()
     rows, D = x.shape
     planes = torch.empty((2, rows, _pad64(D)), dtype=PLANE_DTYPES[fmt], device=x.device)
     with _dev_guard(x):
@@ -438,8 +461,8 @@ def cosine_gemm(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     N.require_cuda(x, "x")
     N.require_cuda(y, "y")
     assert x.ndim == 2 and y.ndim == 2 and x.shape[1] == y.shape[1], (x.shape, y.shape)
-    x = x.detach().to(torch.float32).contiguous()
-    y = y.detach().to(torch.float32).contiguous()
+    x = _pad_features(x.detach().to(torch.float32)).contiguous()
+    y = _pad_features(y.detach().to(torch.float32)).contiguous()
     M, D = x.shape
     Nn = y.shape[0]
     n_pad = (Nn + 7) // 8 * 8
@@ -480,7 +503,7 @@ def clarity(V: torch.Tensor) -> torch.Tensor:
     lib = N.load(require_device=True)
     N.require_cuda(V, "V")
     assert V.ndim >= 2
-    V = V.detach().to(torch.float32).contiguous()
+    V = _pad_features(V.detach().to(torch.float32)).contiguous()
     k, D = V.shape[-2], V.shape[-1]
     C = V.numel() // (k * D) if k * D else 0
     out = torch.empty(V.shape[:-2], dtype=torch.float32, device=V.device)

@@ -49,16 +49,20 @@ def similarity_score(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """
     dev = x.device
     if x.shape != y.shape:
-        if x.ndim != 2 or y.ndim != 2:
-            # the reference indexes shape[1] / shape[0] and would matmul-broadcast; only matrices are supported here
+        if x.ndim < 2 or y.ndim != 2:
+            # the reference indexes x.shape[1] / y.shape[0] and lets matmul broadcast; matrices on the right only here
             raise ValueError("x and y must have the same shape")
         xg, yg = _to_gpu(x), _to_gpu(y)
         if yg.device != xg.device:
             yg = yg.to(xg.device)
+        lead = xg.shape[:-1]  # (Q,) or, for a batched x, (A, Q): matmul broadcasting = flatten the rows, reshape back
+        x2 = xg.reshape(-1, xg.shape[-1])
         if x.shape[1] == y.shape[0]:
             # normalize(x) (Q, D) @ normalize(y) (D, C): y is normalised along ITS rows, then used untransposed
+            if xg.shape[-1] != y.shape[0]:
+                raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({tuple(x2.shape)} and {tuple(y.shape)})")
             yn = torch.nn.functional.normalize(yg.float(), dim=-1).t().contiguous()  # layout plumbing, (C, D)
-            xp = ops.normalize_split_rows(xg.float())
+            xp = ops.normalize_split_rows(x2.float())
             yp = ops.split_planes(_pad_cols(yn, xp.shape[2]), scale=ops.UNIT_ROW_PLANE_SCALE)
             n_pad = (yn.shape[0] + 7) // 8 * 8
             if n_pad != yn.shape[0]:
@@ -66,9 +70,12 @@ def similarity_score(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
             out, _ = ops.gemm_split(xp, yp.contiguous(), passes=3, alpha=1.0 / ops.UNIT_ROW_PLANE_SCALE**2)
             out = out[:, : yn.shape[0]]
         elif x.shape[1] == y.shape[1]:
-            out = ops.cosine_gemm(xg, yg)
+            if xg.shape[-1] != y.shape[1]:
+                raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({tuple(x2.shape)} and {tuple(y.T.shape)})")
+            out = ops.cosine_gemm(x2, yg)
         else:
             raise ValueError("x and y must have the same shape")
+        out = out.reshape(*lead, out.shape[-1])
         return out.to(dev) if out.device != dev else out
     out = ops.cosine_rows(_to_gpu(x), _to_gpu(y).to(_to_gpu(x).device))
     return out.to(dev) if out.device != dev else out

@@ -57,6 +57,31 @@ def _worker(rank, world, port, out):
         emb_local = torch.arange(shard.lo, shard.hi, dtype=torch.float32).unsqueeze(1).repeat(1, 6)
         table = sdist.all_gather_rows(emb_local, shard, N_IMAGES)
         assert table.shape == (N_IMAGES, 6) and torch.equal(table[:, 0], torch.arange(N_IMAGES, dtype=torch.float32))
+        # winners-only exchange: only the rows the merged top-k refers to travel; indexing the compact table with the
+        # remapped ids must equal indexing the full table with the original ids (id -1 = last item, like python)
+        id_tensors = [torch.from_numpy(mi.copy()) for _, mi in merged]
+        id_tensors[0][0, -1] = -1
+        compact, remapped = sdist.exchange_winner_rows(emb_local, shard, id_tensors)
+        winners, starts = sdist.winner_plan(id_tensors, N_IMAGES, world)
+        assert compact.shape[0] == winners.numel() < N_IMAGES and starts[0] == 0 and starts[-1] == winners.numel()
+        for ids, rm in zip(id_tensors, remapped):
+            assert torch.equal(compact[rm], table[ids])
+        # rank 0's filesystem view decides for everyone
+        assert sdist.agree(rank == 0) is True and sdist.agree(rank != 0) is False
+        # a cache only rank 0 could read reaches the other ranks
+        from semanticlens_b200.component_visualization import aggregators as A
+        from semanticlens_b200.component_visualization.activation_caching import ActMax, ActMaxCache
+
+        cache = ActMaxCache([n for n, _, _ in LAYERS], A.aggregate_conv_mean, 4)
+        if rank == 0:
+            for (name, C, k), (mb, mi) in zip(LAYERS, merged):
+                am = ActMax(n_collect=k, n_latents=C)
+                am.activations = torch.from_numpy(mb.view(np.int16).copy()).view(torch.bfloat16)
+                am.sample_ids = torch.from_numpy(mi.copy())
+                cache.cache[name] = am
+        sdist.share_actmax_from_rank0(cache)
+        for (name, C, k), (mb, mi) in zip(LAYERS, merged):
+            assert (_bits(cache.cache[name].activations) == mb).all() and (cache.cache[name].sample_ids.numpy() == mi).all()
         out[rank] = merged
         dist.barrier()
     finally:
@@ -88,6 +113,18 @@ def test_image_shard_partition():
             for a, b in zip(shards, shards[1:]):
                 assert a.hi == b.lo and a.lo <= a.hi
             assert all(s.hi - s.lo <= s.per for s in shards)
+            sizes = [s.hi - s.lo for s in shards]
+            assert max(sizes) - min(sizes) <= 1  # balanced: no rank is empty unless n < world
+            assert all(s.bounds(r) == (shards[r].lo, shards[r].hi) for s in shards for r in range(world))
+
+
+def test_too_few_items_is_the_same_error_on_every_rank(monkeypatch):
+    monkeypatch.setattr(sdist, "world", lambda: (3, 4))
+    with pytest.raises(ValueError, match="at least one item"):
+        sdist.require_items_per_rank(3)
+    sdist.require_items_per_rank(4)
+    monkeypatch.setattr(sdist, "world", lambda: (0, 1))
+    sdist.require_items_per_rank(0)
 
 
 def test_pack_unpack_roundtrip():

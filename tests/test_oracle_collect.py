@@ -112,3 +112,18 @@ def test_merge_lists_equals_single_sweep():
         parts.append(p)
     bits, ids = oc.merge_lists(np.stack([p.bits for p in parts]), np.stack([p.ids for p in parts]))
     assert (bits == whole.bits).all() and (ids == whole.ids).all()
+
+
+def test_full_size_reference_fixture(golden):
+    """k = 20, batch 256, C = 2048 (ResNet-50 layer4 geometry): the reference's hooks ran over tests/collect_cases.py's
+    seeded maps (oracle/make_golden.py:gen_collect_large); the oracle must meet the tie-aware contract against it."""
+    from tests.collect_cases import LARGE, large_maps
+
+    z = np.load(golden / "collect_large.npz")
+    maps = large_maps()
+    np.testing.assert_allclose([float(m.astype(np.float64).sum()) for m in maps], z["checksum"], rtol=1e-12)
+    st = oc.sweep(maps, "mean", "conv", LARGE["k"], exact=True)
+    cand = np.concatenate([oc.f32_to_bf16_bits(oc.aggregate_exact(m, "mean", "conv")) for m in maps]).T
+    errs = oc.check_tie_aware(st.bits, st.ids, z["ref_bits"], z["ref_ids"].astype(np.int64), cand)
+    assert not errs, errs[:5]
+    assert (st.ids >= 0).all() and ((st.bits & 0x7FFF) == 0).any()  # dead channels: real ids on zero values
