@@ -114,8 +114,8 @@ class _Images(torch.utils.data.Dataset):
 def test_concept_db_end_to_end_vs_reference_port(tmp_path):
     """Lens.compute_concept_db on the GPU vs the torch-CPU port of the reference path (oracle/ref_port.py + the oracle
     tower) with the same model weights, the same images and the same FM weights. The probed model's activations differ
-    between cuDNN and oneDNN at the 1e-6 level, so ids are compared with the tie-aware contract through the value
-    multiset (bit-exact here unless a bf16 rounding flips: none with this seed) and the DB rows wherever ids agree."""
+    between cuDNN and oneDNN at the 1e-6 level, so the collect state is held to the end-to-end contract of SURVEY §8(c)
+    (tests/e2e_contract.py: exact except for enumerated near-midpoint elements) and the DB rows wherever ids agree."""
     from oracle import ref_port as rp
     from oracle import vit_port as vp
     from semanticlens_b200.component_visualization import ActivationComponentVisualizer, aggregators
@@ -131,7 +131,7 @@ def test_concept_db_end_to_end_vs_reference_port(tmp_path):
     ocfg = vp.CONFIGS["ViT-tiny-test"]
     sd = vp.init_weights(ocfg, seed=3)
     # reference path on the CPU
-    ref_states = rp.sweep(net, torch.utils.data.DataLoader(ds_m, batch_size=5), layers, rp.aggregate_conv_mean, k)
+    ref_states = rp.sweep(net, torch.utils.data.DataLoader(ds_m, batch_size=6), layers, rp.aggregate_conv_mean, k)
     ref_embeds = torch.cat([vp.encode_image(sd, ocfg, vp.preprocess_u8(ocfg, ds_f.u8[i : i + 5])) for i in range(0, n, 5)])
     ref_db = rp.concept_db(ref_states, ref_embeds)
     # B200 path through the public API
@@ -151,14 +151,23 @@ def test_concept_db_end_to_end_vs_reference_port(tmp_path):
     assert set(db) == set(layers)
     cache_file = cv.storage_dir / "concept_database" / "tiny-fm" / "concept_db-aggregate_conv_mean-4-['1', '3'].safetensors"
     assert cache_file.exists()  # file grammar of reference lens.py:308-316
+    # collect: SURVEY §8(c) end-to-end contract — exact everywhere except the enumerated near-midpoint elements
+    from tests.e2e_contract import check_collect_contract
+
+    def bits(t):
+        return t.view(torch.int16).numpy().view(np.uint16)
+
+    batches = [torch.stack([ds_m[i][0] for i in range(a, min(a + 6, n))]) for a in range(0, n, 6)]
+    gpu_state = {name: (bits(cv.actmax_cache.cache[name].activations), cv.actmax_cache.cache[name].sample_ids.numpy()) for name in layers}
+    ref_state = {name: (bits(ref_states[name].activations), ref_states[name].sample_ids.numpy()) for name in layers}
+    report = check_collect_contract(net.cpu(), layers, batches, "mean", "conv", k, gpu_state, ref_state)
+    print(report)
     for name in layers:
         am = cv.actmax_cache.cache[name]
-        rv, ri = ref_states[name].activations, ref_states[name].sample_ids
-        assert db[name].shape == (rv.shape[0], k, ocfg.embed_dim) and db[name].device.type == "cpu"
-        same_vals = (am.activations.view(torch.int16) == rv.view(torch.int16)) | ((am.activations == 0) & (rv == 0))
-        assert same_vals.float().mean() > 0.98  # cuDNN vs oneDNN activations: at most a stray bf16 rounding flip
+        ri = ref_states[name].sample_ids
+        assert db[name].shape == (ri.shape[0], k, ocfg.embed_dim) and db[name].device.type == "cpu"
+        assert report[name]["rows_checked_exactly"] >= 0.75 * report[name]["rows"]  # the excused set stays small
         agree = am.sample_ids == ri
-        assert agree.float().mean() > 0.9
         err = (db[name][agree] - ref_db[name][agree]).abs().max() / ref_db[name].abs().max()
         assert err < 1e-4
         # id -1 placeholders (dead channels) alias the LAST image, like `embeds[-1]` upstream

@@ -330,6 +330,52 @@ def test_hook_path_vs_reference_fixture(golden, name):
     assert not errs, errs
 
 
+def test_hook_path_full_size_reference_fixture(golden):
+    """k = 20, batch 256, C = 2048 (ResNet-50 layer4 geometry), 3 batches: the reference's hooks ran over the same seeded
+    maps (oracle/make_golden.py:gen_collect_large). Values bit-exact, ids under the tie-aware contract, and exact against
+    the canonical oracle."""
+    from tests.collect_cases import LARGE, large_maps
+
+    z = np.load(golden / "collect_large.npz")
+    maps = large_maps()
+    np.testing.assert_allclose([float(m.astype(np.float64).sum()) for m in maps], z["checksum"], rtol=1e-12)
+    am = run_hooks(maps, get_agg("aggregate_conv_mean"), LARGE["k"])
+    got_bits, got_ids = bits_of(am.activations), am.sample_ids.numpy()
+    assert oc.values_equal(got_bits, z["ref_bits"]).all()  # bit-exact bf16 values against the reference
+    cand = np.concatenate([oc.f32_to_bf16_bits(oc.aggregate_canonical(m, "mean", "conv")) for m in maps]).T
+    errs = oc.check_tie_aware(got_bits, got_ids, z["ref_bits"], z["ref_ids"].astype(np.int64), cand)
+    assert not errs, errs[:5]
+    st = oc.sweep(maps, "mean", "conv", LARGE["k"])
+    assert (got_bits == st.bits).all() and (got_ids == st.ids).all()
+
+
+def test_hook_path_special_token_on_a_permuted_map():
+    """A (B, T, F) map whose memory is (B, F, T) (e.g. the output of a permute): the reference indexes it like any other
+    tensor; the token select copies it once instead of failing."""
+    from semanticlens_b200.component_visualization import aggregators as A
+    from semanticlens_b200.component_visualization.activation_caching import ActMaxCache
+
+    class Perm(torch.nn.Module):
+        def forward(self, x):
+            return x.permute(0, 2, 1)
+
+    model = torch.nn.Sequential()
+    model.add_module("probe", Perm())
+    x = torch.randn(6, 24, 9, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))  # (B, F, T)
+    cache = ActMaxCache(["probe"], A.get_aggregate_transformer_special_token(-2), 4)
+    with cache.hook_context(model):
+        model(x)
+    st = oc.sweep([x.permute(0, 2, 1).cpu().numpy()], "token", "tokens", 4, token=7)
+    assert (bits_of(cache.cache["probe"].activations) == st.bits).all()
+    assert (cache.cache["probe"].sample_ids.numpy() == st.ids).all()
+    bad = ActMaxCache(["probe"], A.get_aggregate_transformer_special_token(9), 4)
+    with pytest.raises(IndexError), bad.hook_context(model):
+        model(x)
+    # float64 maps are cast, not rejected
+    out = A.aggregate_conv_mean(torch.randn(2, 3, 4, 4, dtype=torch.float64).cuda())
+    assert out.shape == (2, 3)
+
+
 def test_hook_path_tiefree_ids_exact(golden):
     z = np.load(golden / "collect_tiefree.npz")
     maps = [z[f"map{i}"] for i in range(int(z["n_batches"]))]

@@ -136,6 +136,28 @@ def test_siglip_tower_vs_oracle(name, B):
     assert rel_max(got, want) < 2e-5  # 22-bit operands through 12 blocks: measured 5.5e-6 on ViT-B/16-SigLIP2
 
 
+def test_siglip_l16_256_tower_vs_oracle():
+    """cfg 3's foundation model at full size (T = 256: the pure tcgen05 attention path, no mma.sync tail), two images
+    against the float64 oracle tower."""
+    from semanticlens_b200.foundation_models import vit
+
+    ocfg = vp.SIGLIP_CONFIGS["ViT-L-16-SigLIP-256"]
+    cfg = vit.CONFIGS["ViT-L-16-SigLIP-256"]
+    sd = vp.init_siglip_weights(ocfg, seed=6)
+    tower = vit.VitTower(cfg, sd, "cuda")
+    img = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(3))
+    want = vp.encode_image_siglip(sd, ocfg, img, dtype=torch.float64)
+    got = tower.forward(img.cuda())
+    assert got.shape == (2, 1024)
+    err = rel_max(got, want)
+    print(f"ViT-L-16-SigLIP-256: kernels vs f64 {err:.2e}")
+    assert err < 1e-4
+    # batch composition must not matter (the 128-row query tiles straddle images differently at B = 3)
+    img3 = torch.cat([img, img[:1]])
+    got3 = tower.forward(img3.cuda())
+    assert torch.equal(got3[:2], got) and torch.equal(got3[2], got[0])
+
+
 def test_siglipv2_wrapper():
     from semanticlens_b200.foundation_models import SigLipV2
 

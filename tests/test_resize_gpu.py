@@ -79,3 +79,28 @@ def test_openclip_preprocess_device_resize_matches_reference_transform():
                     T.ToTensor(), T.Normalize(fm.cfg.mean, fm.cfg.std)])
     want = torch.stack([tf(im) for im in ims])
     assert torch.equal(fm.preprocess(ims).cpu(), want)
+
+
+@pytest.mark.parametrize("w,h,S", [(300, 260, 224), (230, 500, 224), (97, 131, 64), (640, 480, 256), (100, 80, 224)])
+def test_squash_resize_is_pillow_exact(ops, w, h, S):
+    """open_clip's resize_mode="squash" (SigLIP preprocess): Resize((S, S), bicubic), aspect ratio not kept, no crop."""
+    rng = np.random.default_rng(w * 3 + h)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    got = ops.resize_center_crop_u8(torch.from_numpy(img).cuda(), S, squash=True).cpu().numpy()
+    want = np.asarray(Image.fromarray(img).resize((S, S), Image.BICUBIC)).transpose(2, 0, 1)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, rz.resize_bicubic(img, S, S).transpose(2, 0, 1))
+
+
+def test_siglip_preprocess_squashes_like_the_open_clip_transform():
+    import torchvision.transforms as T
+
+    from semanticlens_b200.foundation_models import SigLipV2
+
+    fm = SigLipV2(device="cuda", load_weights=False)
+    rng = np.random.default_rng(1)
+    ims = [Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)) for h, w in ((224, 224), (260, 300), (500, 230))]
+    ims.append(Image.fromarray(rng.integers(0, 256, (240, 250), dtype=np.uint8)))  # mode "L": host path
+    tf = T.Compose([T.Resize((224, 224), interpolation=T.InterpolationMode.BICUBIC), lambda im: im.convert("RGB"),
+                    T.ToTensor(), T.Normalize(fm.cfg.mean, fm.cfg.std)])
+    assert torch.equal(fm.preprocess(ims).cpu(), torch.stack([tf(im) for im in ims]))

@@ -43,6 +43,40 @@ def test_golden_similarity_all_branches(golden, S):
         S.similarity_score(torch.randn(4, 8), torch.randn(5, 9))
 
 
+def test_feature_widths_that_are_not_multiples_of_four(S):
+    """The reference takes any D; the kernels read 16-byte vectors, so the wrappers zero-pad."""
+    g = torch.Generator().manual_seed(4)
+    for D in (5, 30, 511):
+        V = torch.randn(7, 6, D, generator=g)
+        maxnorm_close(S.clarity_score(V).numpy(), rp.clarity_score(V).numpy())
+        x, y = torch.randn(3, D, generator=g), torch.randn(9, D, generator=g)
+        maxnorm_close(S.similarity_score(x, y).numpy(), rp.similarity_score(x, y).numpy())
+        maxnorm_close(S.redundancy_score(y).numpy(), rp.redundancy_score(y).numpy())
+    with pytest.raises(ValueError, match="at most 2048"):
+        S.clarity_score(torch.randn(2, 3, 2052))
+
+
+def test_similarity_with_a_batched_left_operand(S):
+    """x (A, Q, D) against y (C, D): the reference's second branch fires when x.shape[1] == y.shape[1] and matmul
+    broadcasts over the leading dimension."""
+    g = torch.Generator().manual_seed(5)
+    x, y = torch.randn(3, 16, 16, generator=g), torch.randn(9, 16, generator=g)
+    want = rp.similarity_score(x, y)
+    got = S.similarity_score(x, y)
+    assert got.shape == want.shape == (3, 16, 9)
+    maxnorm_close(got.numpy(), want.numpy())
+    with pytest.raises(ValueError, match="same shape"):
+        S.similarity_score(torch.randn(3, 16, 16), torch.randn(2, 9, 16))
+
+
+def test_embeddings_in_half_precision_are_gathered(S):
+    from semanticlens_b200 import ops
+
+    table = torch.randn(11, 32, device="cuda").half()
+    idx = torch.tensor([[0, 5, -1], [10, 2, 2]])
+    assert torch.equal(ops.gather_rows(table, idx).cpu(), table.float().cpu()[idx])
+
+
 def test_golden_clarity_redundancy(golden, S):
     z = np.load(golden / "scores.npz")
     maxnorm_close(S.clarity_score(torch.from_numpy(z["V"]).cuda()).cpu().numpy(), z["clarity"])
