@@ -473,12 +473,12 @@ STEP_CONFIGS = {
         workload="cfg3: torchvision ViT-B/16 probed at its 12 encoder-block outputs (aggregate_transformer_mean, k=20) "
                  "+ SigLIP ViT-L/16-256 image-tower embed, synthetic 224x224 / 256x256 images",
         probed="vit_b_16", agg="aggregate_transformer_mean", fm="ViT-L-16-SigLIP-256", batch=128, steps=6, warmup=3,
-        cpu_images=24, cpu_batch=8),
+        cpu_images=64, cpu_batch=16),
     "cfg4_step": dict(
         workload="cfg4: ResNet-50 probed at all 53 nn.Conv2d outputs (aggregate_conv_mean, k=20) + OpenCLIP ViT-L/14 "
                  "image-tower embed, synthetic 224x224 images",
         probed="resnet50_all_convs", agg="aggregate_conv_mean", fm="ViT-L-14", batch=128, steps=6, warmup=3,
-        cpu_images=24, cpu_batch=8),
+        cpu_images=64, cpu_batch=16),
 }
 
 

@@ -11,8 +11,12 @@
 // O(k * moved points) instead of O(k D). The rows of Gc sum to zero, so the second cluster's sums are minus the first's.
 //
 // Phase A  G0 = X X^T in float64 (products of fp32 values are exact in f64, so assignments match sklearn's f64 fit
-//          except at true f64 near-ties), 64x64 blocks of the upper triangle, 4x4 register tiles, written to the CTA's
-//          own k*k slot of the workspace (stays L2 resident: one slot per resident CTA).
+//          except at true f64 near-ties) on the FP64 tensor cores: mma.sync.m8n8k4.f64 (DMMA.884). The 36 32x32 tiles
+//          of the upper triangle go to the CTA's 9 warps in 4 passes (one tile = 32 f64 accumulators per lane); the
+//          examples arrive as raw fp32 rows through a 2-stage ring of 1-D bulk async copies (one 128-byte row piece per
+//          thread and stage, evict-first in L2 so the Gram slots stay resident) and are widened to f64 when a fragment
+//          is loaded (row pitch 36 floats: conflict-free). Because A and B^T are the same matrix, both fragments
+//          are the same access pattern. Results go to the CTA's own k*k slot of the workspace, mirrored.
 // Phase B  thread i = example i: k-means++ with sklearn's RandomState stream (data independent: the first-centre
 //          index and the two local-trial uniforms per init are precomputed on the host), Lloyd to strict convergence or
 //          tolerance, empty-cluster relocation, best of n_init by inertia with sklearn's _is_same_clustering guard.
@@ -23,7 +27,12 @@
 
 namespace {
 
-constexpr int kT = 256;     // threads per CTA = max examples per neuron
+constexpr int kT = 256;     // max examples per neuron (thread i < kT owns example i in phase B)
+constexpr int kWarps = 9;   // 36 upper-triangle tiles of 32x32 = 4 passes x 9 warps
+constexpr int kThreads = kWarps * 32;
+constexpr int kStageCols = 32;  // features per pipeline stage
+constexpr int kPitch = 36;      // floats per staged row: bank = (4*row + col) mod 32 -> conflict-free fragment loads
+constexpr int kStages = 2;
 constexpr int kMaxInit = 16;
 constexpr int kMaxIter = 300;  // sklearn default max_iter
 
@@ -40,19 +49,20 @@ struct PolyParams {
 };
 
 struct Smem {
-    double tileA[64][33];
-    double tileB[64][33];
-    double r[kT];
-    double diag[kT];
-    double red[8 * 4];
-    double scan[8];
-    int ired[8 * 2];
-    signed char delta[kT];
-    unsigned char best_lab[kT];
-    unsigned char best_mask[kT];
+    float stage[kStages][kT][kPitch];  // fp32 examples, kStageCols features per stage
+    uint64_t full[kStages];
+    double r[kThreads];
+    double diag[kThreads];
+    double red[kWarps * 4];
+    double scan[kWarps];
+    int ired[kWarps * 2];
+    short moved[kT];   // examples that changed side this iteration, ascending; ~j encodes "left cluster 0"
+    int wcnt[kWarps];
+    unsigned char best_lab[kThreads];
+    unsigned char best_mask[kThreads];
 };
 
-// ---- block primitives (256 threads, every thread must call) ----------------------------------------
+// ---- block primitives (kThreads threads, every thread must call) ----------------------------------------
 template <int N>
 __device__ __forceinline__ void block_sum(double (&v)[N], Smem& sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -71,7 +81,7 @@ __device__ __forceinline__ void block_sum(double (&v)[N], Smem& sm) {
     for (int n = 0; n < N; ++n) {
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += sm.red[w * 4 + n];
+        for (int w = 0; w < kWarps; ++w) t += sm.red[w * 4 + n];
         v[n] = t;
     }
 }
@@ -97,12 +107,12 @@ __device__ __forceinline__ void block_count(int (&v)[N], Smem& sm) {
     for (int n = 0; n < N; ++n) {
         int t = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += sm.ired[w * 2 + n];
+        for (int w = 0; w < kWarps; ++w) t += sm.ired[w * 2 + n];
         v[n] = t;
     }
 }
 
-// inclusive prefix sum over threads 0..255 (np.cumsum)
+// inclusive prefix sum over the threads (np.cumsum)
 __device__ __forceinline__ double block_scan(double x, Smem& sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -132,59 +142,135 @@ __device__ __forceinline__ void block_argmax(double& val, int& idx, Smem& sm) {
     __syncthreads();
     val = sm.red[0];
     idx = sm.ired[0];
-    for (int w = 1; w < 8; ++w) {
+    for (int w = 1; w < kWarps; ++w) {
         const double v2 = sm.red[w * 4];
         const int i2 = sm.ired[w * 2];
         if (v2 > val || (v2 == val && i2 < idx)) { val = v2; idx = i2; }
     }
 }
 
-// ---- phase A: G0 = X X^T (float64) ---------------------------------------------------------------
-__device__ void gram_f64(const float* __restrict__ X, int k, int D, double* __restrict__ G, Smem& sm) {
-    const int tid = threadIdx.x;
-    const int ty = tid >> 4, tx = tid & 15;
-    const int nb = (k + 63) >> 6;
-    for (int bi = 0; bi < nb; ++bi) {
-        for (int bj = bi; bj < nb; ++bj) {
-            double acc[4][4];
+// ---- phase A: G0 = X X^T (float64, DMMA) -----------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint64_t evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            slb_smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(slb_smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+
+// upper-triangle 32x32 tiles in row-major order: tile t of pass p belongs to warp t - 9 p
+__constant__ unsigned char kTileRow[36] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 6, 6, 7};
+__constant__ unsigned char kTileCol[36] = {0, 1, 2, 3, 4, 5, 6, 7, 1, 2, 3, 4, 5, 6, 7, 2, 3, 4, 5, 6, 7, 3, 4, 5, 6, 7, 4, 5, 6, 7, 5, 6, 7, 6, 7, 7};
+
+struct Ring {
+    uint32_t issued = 0;    // stages requested so far (all threads agree)
+    uint32_t consumed = 0;  // stages waited for so far
+};
+
+// Thread i (< kT) requests columns [d0, d0 + 32) of example row i into ring slot issued % kStages. `bulk`: X and D allow
+// 16-byte async copies; otherwise the row piece is copied with plain loads. Every row thread arrives once per stage, so a
+// consumer's wait also orders the plain stores (tail zeroes, fallback copies) before its reads.
+__device__ __forceinline__ void request_stage(Smem& sm, Ring& ring, const float* __restrict__ X, int k, int D, int d0, bool bulk,
+                                              uint64_t pol) {
+    const int i = threadIdx.x;
+    const int slot = ring.issued % kStages;
+    ring.issued++;
+    if (i >= kT) return;
+    uint64_t* bar = &sm.full[slot];
+    float* dst = sm.stage[slot][i];
+    const int valid = min(kStageCols, D - d0);
+    if (i >= k) {  // rows past the last example stay zero (zeroed once at kernel start)
+        slb_mbar_arrive(bar);
+        return;
+    }
+    const float* src = X + (int64_t)i * D + d0;
+    if (valid < kStageCols)
+        for (int c = valid; c < kStageCols; ++c) dst[c] = 0.f;
+    if (bulk) {
+        slb_mbar_arrive_expect_tx(bar, (uint32_t)valid * 4u);
+        bulk_g2s_hint(dst, src, (uint32_t)valid * 4u, bar, pol);
+    } else {
+        for (int c = 0; c < valid; ++c) dst[c] = __ldg(src + c);
+        slb_mbar_arrive(bar);
+    }
+}
+
+__device__ void gram_f64(const float* __restrict__ X, int k, int D, double* __restrict__ G, Smem& sm, Ring& ring, bool bulk,
+                         uint64_t pol) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int n_stage = (D + kStageCols - 1) / kStageCols;
+    const int nb = (k + 31) >> 5;  // 32-row blocks that hold examples
+    const bool vec2 = (k & 1) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int tile = pass * kWarps + warp;
+        const int bi = kTileRow[tile], bj = kTileCol[tile];
+        const bool live = bj < nb;  // bi <= bj: the tile touches real examples
+        bool any = false;  // uniform over the CTA: a pass whose nine tiles are all past the last example is skipped
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+        for (int w = 0; w < kWarps; ++w) any |= kTileCol[pass * kWarps + w] < nb;
+        if (!any) continue;
+        double acc[4][4][2];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-            for (int d0 = 0; d0 < D; d0 += 32) {
-                __syncthreads();
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int e = tid + q * kT;
-                    const int row = e >> 5, col = e & 31;
-                    const int d = d0 + col;
-                    const int ra = bi * 64 + row, rb = bj * 64 + row;
-                    sm.tileA[row][col] = (ra < k && d < D) ? (double)__ldg(X + (int64_t)ra * D + d) : 0.0;
-                    if (bj != bi) sm.tileB[row][col] = (rb < k && d < D) ? (double)__ldg(X + (int64_t)rb * D + d) : 0.0;
-                }
-                __syncthreads();
-                const double(*tb)[33] = (bj != bi) ? sm.tileB : sm.tileA;
-#pragma unroll 8
-                for (int d = 0; d < 32; ++d) {
+            for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        // prologue: fill the ring
+        __syncthreads();  // every reader of the previous pass / phase B is done with the ring slots
+        const int pre = min(kStages, n_stage);
+        for (int s = 0; s < pre; ++s) request_stage(sm, ring, X, k, D, s * kStageCols, bulk, pol);
+        for (int s = 0; s < n_stage; ++s) {
+            const int slot = ring.consumed % kStages;
+            slb_mbar_wait(&sm.full[slot], (ring.consumed / kStages) & 1u);
+            ring.consumed++;
+            if (live) {
+                const float* ra = &sm.stage[slot][bi * 32 + g][t];
+                const float* rb = &sm.stage[slot][bj * 32 + g][t];
+#pragma unroll
+                for (int kk = 0; kk < kStageCols / 4; ++kk) {
                     double av[4], bv[4];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) av[a] = sm.tileA[ty + 16 * a][d];
+                    for (int a = 0; a < 4; ++a) av[a] = (double)ra[a * 8 * kPitch + kk * 4];
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) bv[b] = tb[tx + 16 * b][d];
+                    for (int b = 0; b < 4; ++b) bv[b] = (double)rb[b * 8 * kPitch + kk * 4];
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+                        for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], av[a], bv[b]);
                 }
             }
+            __syncthreads();  // the slot is free again
+            if (s + kStages < n_stage) request_stage(sm, ring, X, k, D, (s + kStages) * kStageCols, bulk, pol);
+        }
+        if (live) {
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    const int i = bi * 64 + ty + 16 * a, j = bj * 64 + tx + 16 * b;
-                    if (i < k && j < k) {
-                        G[(int64_t)i * k + j] = acc[a][b];
-                        if (bj != bi) G[(int64_t)j * k + i] = acc[a][b];
+                    const int i = bi * 32 + a * 8 + g, j = bj * 32 + b * 8 + 2 * t;
+                    if (i < k) {
+                        if (j + 1 < k) {
+                            if (vec2) *reinterpret_cast<double2*>(G + (int64_t)i * k + j) = make_double2(acc[a][b][0], acc[a][b][1]);
+                            else { G[(int64_t)i * k + j] = acc[a][b][0]; G[(int64_t)i * k + j + 1] = acc[a][b][1]; }
+                        } else if (j < k) {
+                            G[(int64_t)i * k + j] = acc[a][b][0];
+                        }
+                        if (bi != bj) {
+                            if (j < k) G[(int64_t)j * k + i] = acc[a][b][0];
+                            if (j + 1 < k) G[(int64_t)(j + 1) * k + i] = acc[a][b][1];
+                        }
                     }
                 }
             }
@@ -194,21 +280,31 @@ __device__ void gram_f64(const float* __restrict__ X, int k, int D, double* __re
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kT) polysem_kernel(PolyParams p) {
+__global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int i = threadIdx.x;
     const int k = p.k;
     const bool on = i < k;
     double* G = p.G + (int64_t)blockIdx.x * k * k;
+    for (int e = i; e < kStages * kT * kPitch; e += kThreads) (&sm.stage[0][0][0])[e] = 0.f;
+    if (i == 0) {
+        for (int s = 0; s < kStages; ++s) slb_mbar_init(&sm.full[s], kT);
+        slb_fence_mbar_init();
+    }
+    __syncthreads();
+    Ring ring;
+    const uint64_t pol = evict_first_policy();
+    const bool bulk = (p.D % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.V) & 15) == 0);
 
     for (int64_t neuron = blockIdx.x; neuron < p.C; neuron += gridDim.x) {
-        gram_f64(p.V + neuron * (int64_t)k * p.D, k, p.D, G, sm);
+        gram_f64(p.V + neuron * (int64_t)k * p.D, k, p.D, G, sm, ring, bulk, pol);
         __threadfence_block();
 
         // row means, grand mean, centred diagonal, tolerance
         double ri = 0.0;
         if (on) {
+#pragma unroll 8
             for (int j = 0; j < k; ++j) ri += __ldcg(G + (int64_t)j * k + i);
             ri /= (double)k;
         }
@@ -268,14 +364,43 @@ __global__ void __launch_bounds__(kT) polysem_kernel(PolyParams p) {
                     }
                 }
                 double s0n, s1n, n0n, n1n, cross0, cross1;
-                // incremental update of tA with the examples that changed side
+                // incremental update of tA with the examples that changed side: the movers are compacted into an
+                // ascending list (ballot + per-warp offsets) so that every thread walks only them, eight independent
+                // L2 loads in flight at a time; the additions keep the ascending order (same bits as a full scan)
+                const int dj = on ? (mk == 0) - (cur == 0) : 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, dj != 0);
+                __syncthreads();  // previous readers of sm.moved / sm.wcnt are done
+                if ((i & 31) == 0) sm.wcnt[i >> 5] = __popc(bal);
                 __syncthreads();
-                sm.delta[i] = on ? (signed char)((mk == 0) - (cur == 0)) : 0;
+                int base = 0, n_moved = 0;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) {
+                    const int c = sm.wcnt[w];
+                    if (w < (i >> 5)) base += c;
+                    n_moved += c;
+                }
+                if (dj != 0) sm.moved[base + __popc(bal & ((1u << (i & 31)) - 1u))] = (short)(dj > 0 ? i : ~i);
                 __syncthreads();
                 if (on) {
-                    for (int j = 0; j < k; ++j) {
-                        const int dj = sm.delta[j];
-                        if (dj != 0) tA += (double)dj * gc(j);
+                    for (int e0 = 0; e0 < n_moved; e0 += 8) {
+                        double gv[8];
+                        int jj[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int e = min(e0 + u, n_moved - 1);
+                            const int code = sm.moved[e];
+                            jj[u] = code;
+                            const int j = code >= 0 ? code : ~code;
+                            gv[u] = __ldcg(G + (int64_t)j * k + i);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (e0 + u < n_moved) {
+                                const int j = jj[u] >= 0 ? jj[u] : ~jj[u];
+                                const double gcj = gv[u] - ri - sm.r[j] + m;
+                                tA += jj[u] >= 0 ? gcj : -gcj;
+                            }
+                        }
                     }
                 }
                 cur = mk;
@@ -343,6 +468,7 @@ __global__ void __launch_bounds__(kT) polysem_kernel(PolyParams p) {
         } else {
             double wa = 0.0, wb = 0.0;
             if (on) {
+#pragma unroll 8
                 for (int j = 0; j < k; ++j) {
                     const double g = __ldcg(G + (int64_t)j * k + i);
                     if (sm.best_mask[j] == 0) wa += g; else wb += g;
@@ -405,7 +531,7 @@ extern "C" int slb_polysem_2means(const float* V, int64_t C, int64_t k, int64_t 
     p.out = out;
     const size_t smem = sizeof(Smem);
     SLB_CUDA_OK(cudaFuncSetAttribute(polysem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    polysem_kernel<<<poly_grid(C), kT, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    polysem_kernel<<<poly_grid(C), kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     SLB_LAUNCH_OK("polysem_2means");
     return SLB_OK;
 }
