@@ -144,8 +144,12 @@ int slb_clarity(const float* V, int64_t C, int64_t k, int64_t D, float* out, voi
  * < 2 members take the fallback of scores.py:173-184 when replace_empty_clusters != 0.
  * V (C, k, D) fp32 device, k <= 256. first_centers [n_init] / local_trial_uniforms [n_init][2] are HOST arrays: the
  * data-independent draws of sklearn's RandomState stream (per init `choice(k)` then `uniform(size=2)`, _kmeans.py:231,249).
- * workspace: 8-byte aligned device memory >= slb_polysem_workspace_bytes(C, k). */
+ * workspace: 16-byte aligned device memory >= slb_polysem_workspace_bytes(C, k). */
 size_t slb_polysem_workspace_bytes(int64_t C, int64_t k);
+/* Diagnostic: SM clocks that thread 0 of every polysemanticity CTA spent per phase since the last reset, summed over CTAs
+ * (synchronises the device): [0] Gram matrix, [1] row means, [2] k-means++ and first assignments, [3] first-iteration
+ * sums, [4] Lloyd restarts, [5] score, [6] neurons processed. */
+int slb_polysem_phase_clocks(uint64_t* out7, int reset);
 int slb_polysem_2means(const float* V, int64_t C, int64_t k, int64_t D, const int64_t* first_centers,
                        const double* local_trial_uniforms, int n_init, int replace_empty_clusters, double* out,
                        void* workspace, size_t workspace_bytes, void* stream);

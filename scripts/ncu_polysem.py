@@ -1,0 +1,9 @@
+import sys, torch
+sys.path.insert(0, "/root/repo")
+from semanticlens_b200 import ops
+C = 296 * 8
+g = torch.Generator(device="cuda").manual_seed(2)
+V = torch.randn(C, 256, 512, device="cuda", generator=g)
+V[:, ::2] += 2 * torch.randn(C, 1, 512, device="cuda", generator=g)
+ops.polysem_2means(V); torch.cuda.synchronize()
+ops.polysem_2means(V); torch.cuda.synchronize()

@@ -16,11 +16,18 @@ for kind, X in (("planted", V), ("gaussian", torch.randn(C, 256, 512, device="cu
     for n_init in (1, 10):
         ops.polysem_2means(X, n_init=n_init)
         torch.cuda.synchronize()
+        import ctypes
+        from semanticlens_b200 import _native as N
+        clk = (ctypes.c_uint64 * 7)()
+        N.load().slb_polysem_phase_clocks(clk, 1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         ops.polysem_2means(X, n_init=n_init)
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
+        N.load().slb_polysem_phase_clocks(clk, 1)
+        per = [round(clk[c] / max(clk[6], 1) / 1.965e3, 1) for c in range(6)]  # us per neuron per CTA at 1.965 GHz
         print(json.dumps({"data": kind, "neurons": C, "n_init": n_init, "ms": round(ms, 2), "us_per_neuron": round(ms * 1e3 / C, 3),
-                          "ms_at_65536": round(ms * 65536 / C, 1)}), flush=True)
+                          "ms_at_65536": round(ms * 65536 / C, 1),
+                          "us_per_neuron_per_cta": dict(zip(["gram", "means", "seed+assign", "first_sums", "lloyd", "score"], per))}), flush=True)

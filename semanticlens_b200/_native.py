@@ -58,6 +58,7 @@ _PROTOS = {
     "slb_cosine_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p]),
     "slb_clarity": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "slb_polysem_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "slb_polysem_phase_clocks": (c_int, [c_void_p, c_int]),
     "slb_polysem_2means": (
         c_int,
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p],

@@ -33,7 +33,7 @@ constexpr int kThreads = kWarps * 32;
 constexpr int kStageCols = 32;  // features per pipeline stage
 constexpr int kPitch = 36;      // floats per staged row: bank = (4*row + col) mod 32 -> conflict-free fragment loads
 constexpr int kStages = 2;
-constexpr int kMaxInit = 16;
+constexpr int kMaxInit = 10;  // sklearn's n_init of the reference call (scores.py:167)
 constexpr int kMaxIter = 300;  // sklearn default max_iter
 
 struct PolyParams {
@@ -44,19 +44,24 @@ struct PolyParams {
     int replace_empty;
     int first[kMaxInit];
     double rand[2 * kMaxInit];
-    double* G;  // workspace: gridDim.x slots of k*k doubles
+    double* G;  // workspace: gridDim.x slots of k(k+1)/2 doubles (packed upper triangle)
     double* out;
 };
 
 struct Smem {
     float stage[kStages][kT][kPitch];  // fp32 examples, kStageCols features per stage
     uint64_t full[kStages];
+    double tA0[kMaxInit][kT];      // first-iteration sums of every restart
     double r[kThreads];
     double diag[kThreads];
     double red[kWarps * 4];
     double scan[kWarps];
     int ired[kWarps * 2];
     short moved[kT];   // examples that changed side this iteration, ascending; ~j encodes "left cluster 0"
+    unsigned short in0[kThreads];  // bit `it`: the example starts restart `it` in cluster 0
+    int trow[kT];                  // row offsets of the packed upper triangle
+    int seed0[kMaxInit];           // second seed of every restart (the first is PolyParams::first)
+    int cnt0[kMaxInit];            // size of cluster 0 after the first assignment
     int wcnt[kWarps];
     unsigned char best_lab[kThreads];
     unsigned char best_mask[kThreads];
@@ -149,6 +154,43 @@ __device__ __forceinline__ void block_argmax(double& val, int& idx, Smem& sm) {
     }
 }
 
+// ---- Gram storage: packed upper triangle -----------------------------------------------------------
+// G0 is symmetric; a slot keeps rows a = 0..k-1 of the upper triangle back to back (row a holds columns a..k-1), i.e.
+// k(k+1)/2 doubles = 263 KB at k = 256. Two CTAs per SM keep 296 slots live: 78 MB, which stays inside the 126 MB L2 —
+// the full mirrored matrix (152 MB) did not, and every phase-B read went to DRAM (ncu: 30 % L2 hit rate, 7x the
+// algorithmic DRAM traffic). Thread i reads "column i": entries above the diagonal come from row j (coalesced over i),
+// entries below it from the thread's own row i (consecutive j -> consecutive addresses, served by L1 after the first touch).
+__host__ __device__ __forceinline__ int64_t slot_doubles(int64_t k) { return (k * (k + 1) / 2 + 1) & ~(int64_t)1; }  // even
+__device__ __forceinline__ int tri_row(int a, int k) { return a * k - (a * (a - 1)) / 2 - a; }  // + column; k <= 256: fits int
+// trow = the k row offsets, precomputed in shared memory: phase B is a latency-bound scalar loop at two warps per scheduler,
+// so every instruction saved per element shortens it (an on-the-fly tri_row cost ~10 integer instructions per load)
+__device__ __forceinline__ double gsym(const double* __restrict__ U, const int* __restrict__ trow, int i, int j) {
+    const int lo = min(i, j), hi = max(i, j);
+    return U[trow[lo] + hi];
+}
+
+// Sweep over "column i" of the symmetric Gram matrix by thread i, eight independent loads in flight (a load block
+// followed by a use block: left to itself the compiler interleaves one load with the arithmetic of the previous
+// element and every load pays the full L2 latency). f(j, G0[i][j]) is called in ascending j.
+// Two alternatives were measured and were slower at two warps per scheduler (scripts/time_polysem.py, r02 notes in
+// DESIGN.md): warp-cooperative row sums (more sequential round trips) and streaming the triangle through shared memory
+// with bulk copies (the CTA waits on the copies, 8 chunk hand-offs per sweep).
+template <typename F>
+__device__ __forceinline__ void sweep_column(const double* __restrict__ U, const int* __restrict__ trow, int i, int k, F&& f) {
+    const double* own = U + trow[i];  // row i of the packed triangle (+ column)
+    for (int j0 = 0; j0 < k; j0 += 8) {
+        double gv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = min(j0 + u, k - 1);
+            gv[u] = j < i ? U[trow[j] + i] : own[j];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (j0 + u < k) f(j0 + u, gv[u]);
+    }
+}
+
 // ---- phase A: G0 = X X^T (float64, DMMA) -----------------------------------------------------------
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -191,7 +233,7 @@ __device__ __forceinline__ void request_stage(Smem& sm, Ring& ring, const float*
     uint64_t* bar = &sm.full[slot];
     float* dst = sm.stage[slot][i];
     const int valid = min(kStageCols, D - d0);
-    if (i >= k) {  // rows past the last example stay zero (zeroed once at kernel start)
+    if (i >= k) {  // rows past the last example stay zero (zeroed once at kernel start; nothing else writes the ring)
         slb_mbar_arrive(bar);
         return;
     }
@@ -213,7 +255,6 @@ __device__ void gram_f64(const float* __restrict__ X, int k, int D, double* __re
     const int g = lane >> 2, t = lane & 3;
     const int n_stage = (D + kStageCols - 1) / kStageCols;
     const int nb = (k + 31) >> 5;  // 32-row blocks that hold examples
-    const bool vec2 = (k & 1) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0;
     for (int pass = 0; pass < 4; ++pass) {
         const int tile = pass * kWarps + warp;
         const int bi = kTileRow[tile], bj = kTileCol[tile];
@@ -228,7 +269,7 @@ __device__ void gram_f64(const float* __restrict__ X, int k, int D, double* __re
 #pragma unroll
             for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
         // prologue: fill the ring
-        __syncthreads();  // every reader of the previous pass / phase B is done with the ring slots
+        __syncthreads();  // every reader of the previous pass is done with the ring slots
         const int pre = min(kStages, n_stage);
         for (int s = 0; s < pre; ++s) request_stage(sm, ring, X, k, D, s * kStageCols, bulk, pol);
         for (int s = 0; s < n_stage; ++s) {
@@ -261,16 +302,9 @@ __device__ void gram_f64(const float* __restrict__ X, int k, int D, double* __re
                 for (int b = 0; b < 4; ++b) {
                     const int i = bi * 32 + a * 8 + g, j = bj * 32 + b * 8 + 2 * t;
                     if (i < k) {
-                        if (j + 1 < k) {
-                            if (vec2) *reinterpret_cast<double2*>(G + (int64_t)i * k + j) = make_double2(acc[a][b][0], acc[a][b][1]);
-                            else { G[(int64_t)i * k + j] = acc[a][b][0]; G[(int64_t)i * k + j + 1] = acc[a][b][1]; }
-                        } else if (j < k) {
-                            G[(int64_t)i * k + j] = acc[a][b][0];
-                        }
-                        if (bi != bj) {
-                            if (j < k) G[(int64_t)j * k + i] = acc[a][b][0];
-                            if (j + 1 < k) G[(int64_t)(j + 1) * k + i] = acc[a][b][1];
-                        }
+                        double* row = G + tri_row(i, k);  // (phase A: once per tile row, not worth a table lookup)
+                        if (j >= i && j < k) row[j] = acc[a][b][0];
+                        if (j + 1 >= i && j + 1 < k) row[j + 1] = acc[a][b][1];
                     }
                 }
             }
@@ -280,14 +314,19 @@ __device__ void gram_f64(const float* __restrict__ X, int k, int D, double* __re
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
+// SM-clock totals of thread 0 of every CTA per phase (slb_polysem_phase_clocks): Gram, row means, k-means++ and first
+// assignments, first-iteration sums, Lloyd restarts, score. A handful of clock reads per neuron.
+__device__ unsigned long long g_phase_clk[8];
+
 __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int i = threadIdx.x;
     const int k = p.k;
     const bool on = i < k;
-    double* G = p.G + (int64_t)blockIdx.x * k * k;
+    double* G = p.G + (int64_t)blockIdx.x * slot_doubles(k);
     for (int e = i; e < kStages * kT * kPitch; e += kThreads) (&sm.stage[0][0][0])[e] = 0.f;
+    if (i < kT) sm.trow[i] = tri_row(min(i, k - 1), k);
     if (i == 0) {
         for (int s = 0; s < kStages; ++s) slb_mbar_init(&sm.full[s], kT);
         slb_fence_mbar_init();
@@ -297,33 +336,41 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
     const uint64_t pol = evict_first_policy();
     const bool bulk = (p.D % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.V) & 15) == 0);
 
+    unsigned long long clk[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int64_t neuron = blockIdx.x; neuron < p.C; neuron += gridDim.x) {
+        long long t0 = clock64(), t1;
         gram_f64(p.V + neuron * (int64_t)k * p.D, k, p.D, G, sm, ring, bulk, pol);
         __threadfence_block();
+        t1 = clock64(); clk[0] += t1 - t0; t0 = t1;
 
         // row means, grand mean, centred diagonal, tolerance
         double ri = 0.0;
         if (on) {
-#pragma unroll 8
-            for (int j = 0; j < k; ++j) ri += __ldcg(G + (int64_t)j * k + i);
+            sweep_column(G, sm.trow, i, k, [&](int, double g) { ri += g; });
             ri /= (double)k;
         }
         const double m = block_sum1(on ? ri : 0.0, sm) / (double)k;
-        const double g_ii = on ? __ldcg(G + (int64_t)i * k + i) : 0.0;
+        const double g_ii = on ? gsym(G, sm.trow, i, i) : 0.0;
         const double di = on ? g_ii - 2.0 * ri + m : 0.0;
         sm.r[i] = ri;
         sm.diag[i] = di;
         const double tol = block_sum1(di, sm) / ((double)k * (double)p.D) * 1e-4;  // also publishes sm.r / sm.diag
 
-        auto gc = [&](int j) -> double {  // Gc[i][j], read down column i of the symmetric G0 (coalesced over i)
-            return __ldcg(G + (int64_t)j * k + i) - ri - sm.r[j] + m;
+        t1 = clock64(); clk[1] += t1 - t0; t0 = t1;
+        auto gc = [&](int j) -> double {  // Gc[i][j] from the packed upper triangle
+            return gsym(G, sm.trow, i, j) - ri - sm.r[j] + m;
         };
 
         double best_inertia = 0.0;
         bool have_best = false;
 
+        // ---- pass 1 over the restarts: k-means++ and the FIRST assignment of every restart -------------------------
+        // In the first Lloyd iteration about half of the examples enter cluster 0, so updating tA costs ~k/2 row reads per
+        // restart. The first assignments only depend on the seeds, so they are all taken first and ONE sweep over the
+        // Gram matrix then serves every restart (each entry is loaded once and added into up to n_init independent sums).
+        unsigned labw = 0, in0w = 0;  // bit `it`: first label of example i / example i starts in cluster 0 (after relocation)
         for (int it = 0; it < p.n_init; ++it) {
-            // ---- k-means++ (sklearn _kmeans_plusplus, n_local_trials = 2) ----
+            // k-means++ (sklearn _kmeans_plusplus, n_local_trials = 2)
             const int i0 = p.first[it];
             const double gi0 = on ? gc(i0) : 0.0;
             const double closest = on ? fmax(di - 2.0 * gi0 + sm.diag[i0], 0.0) : 0.0;
@@ -337,72 +384,128 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
                               on ? fmin(closest, fmax(di - 2.0 * gc1 + sm.diag[cand1], 0.0)) : 0.0};
             block_sum<2>(pots, sm);
             const int i1 = (pots[1] < pots[0]) ? cand1 : cand0;
-
-            // ---- Lloyd ----
-            double s0 = gi0, s1 = (i1 == cand1) ? gc1 : gc0;
+            // first E-step (+ empty-cluster relocation) from the two seeds
+            const double s0 = gi0, s1 = (i1 == cand1) ? gc1 : gc0;
+            const double n0 = sm.diag[i0], n1 = sm.diag[i1];
+            const int lab = (on && (n1 - 2.0 * s1) < (n0 - 2.0 * s0)) ? 1 : 0;
+            int mk = lab;
+            int c1[1] = {(on && lab == 0) ? 1 : 0};
+            block_count<1>(c1, sm);
+            int cnt0 = c1[0], cnt1 = k - cnt0;
+            if (cnt0 == 0 || cnt1 == 0) {
+                const int o = (cnt1 == 0) ? 0 : 1;
+                double dist = on ? di - 2.0 * (o ? s1 : s0) + (o ? n1 : n0) : -1.0;
+                int far = i;
+                block_argmax(dist, far, sm);
+                if (dist > 0.0) {
+                    if (i == far) mk = 1 - o;
+                    if (o == 0) { cnt0 -= 1; } else { cnt0 = 1; }
+                }
+            }
+            labw |= (unsigned)lab << it;
+            in0w |= (unsigned)(on && mk == 0) << it;
+            if (i == 0) { sm.seed0[it] = i1; sm.cnt0[it] = cnt0; }
+        }
+        __syncthreads();
+        sm.in0[i] = (unsigned short)in0w;
+        __syncthreads();
+        t1 = clock64(); clk[2] += t1 - t0; t0 = t1;
+        // groups of 5 restarts: the default n_init = 10 is two sweeps with no idle accumulator
+        for (int q0 = 0; q0 < p.n_init; q0 += 5) {
+            double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            if (on) {
+                sweep_column(G, sm.trow, i, k, [&](int j, double g) {
+                    const double gcj = g - ri - sm.r[j] + m;
+                    const unsigned w = (unsigned)sm.in0[j] >> q0;  // the same j for the whole warp: no divergence
+#pragma unroll
+                    for (int q = 0; q < 5; ++q)
+                        if ((w >> q) & 1u) acc[q] += gcj;
+                });
+            }
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+                if (q0 + q < p.n_init && i < kT) sm.tA0[q0 + q][i] = acc[q];
+        }
+        __syncthreads();
+        t1 = clock64(); clk[3] += t1 - t0; t0 = t1;
+        // ---- pass 2: the Lloyd iterations of every restart, best of n_init ------------------------------------
+        for (int it = 0; it < p.n_init; ++it) {
+            const int i0 = p.first[it], i1 = sm.seed0[it];
+            double s0 = on ? gc(i0) : 0.0, s1 = on ? gc(i1) : 0.0;
             double n0 = sm.diag[i0], n1 = sm.diag[i1];
-            double tA = 0.0;   // sum over members of cluster 0 of Gc[i][j]
-            int cur = 1;       // current M-step membership of example i (nothing is in cluster 0 yet)
+            double tA = on ? sm.tA0[it][i] : 0.0;  // sum over members of cluster 0 of Gc[i][j]
+            int cur = 1;       // current M-step membership of example i
             int lab = 0, lab_old = -1;
             bool strict = false;
             for (int iter = 0; iter < kMaxIter; ++iter) {
-                lab = (on && (n1 - 2.0 * s1) < (n0 - 2.0 * s0)) ? 1 : 0;
-                int mk = lab;
-                int c2[2] = {(on && lab == 0) ? 1 : 0, (on && lab != lab_old) ? 1 : 0};
-                block_count<2>(c2, sm);
-                int cnt0 = c2[0], cnt1 = k - cnt0;
-                const bool same = c2[1] == 0;
-                if (cnt0 == 0 || cnt1 == 0) {
-                    // _relocate_empty_clusters_dense: the point farthest from its centre founds the empty cluster
-                    const int o = (cnt1 == 0) ? 0 : 1;
-                    double dist = on ? di - 2.0 * (o ? s1 : s0) + (o ? n1 : n0) : -1.0;
-                    int far = i;
-                    block_argmax(dist, far, sm);
-                    if (dist > 0.0) {
-                        if (i == far) mk = 1 - o;
-                        if (o == 0) { cnt0 -= 1; cnt1 = 1; } else { cnt1 -= 1; cnt0 = 1; }
-                    }
-                }
-                double s0n, s1n, n0n, n1n, cross0, cross1;
-                // incremental update of tA with the examples that changed side: the movers are compacted into an
-                // ascending list (ballot + per-warp offsets) so that every thread walks only them, eight independent
-                // L2 loads in flight at a time; the additions keep the ascending order (same bits as a full scan)
-                const int dj = on ? (mk == 0) - (cur == 0) : 0;
-                const unsigned bal = __ballot_sync(0xffffffffu, dj != 0);
-                __syncthreads();  // previous readers of sm.moved / sm.wcnt are done
-                if ((i & 31) == 0) sm.wcnt[i >> 5] = __popc(bal);
-                __syncthreads();
-                int base = 0, n_moved = 0;
-#pragma unroll
-                for (int w = 0; w < kWarps; ++w) {
-                    const int c = sm.wcnt[w];
-                    if (w < (i >> 5)) base += c;
-                    n_moved += c;
-                }
-                if (dj != 0) sm.moved[base + __popc(bal & ((1u << (i & 31)) - 1u))] = (short)(dj > 0 ? i : ~i);
-                __syncthreads();
-                if (on) {
-                    for (int e0 = 0; e0 < n_moved; e0 += 8) {
-                        double gv[8];
-                        int jj[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int e = min(e0 + u, n_moved - 1);
-                            const int code = sm.moved[e];
-                            jj[u] = code;
-                            const int j = code >= 0 ? code : ~code;
-                            gv[u] = __ldcg(G + (int64_t)j * k + i);
+                int mk, cnt0, cnt1;
+                bool same;
+                if (iter == 0) {  // taken in pass 1
+                    lab = (labw >> it) & 1u;
+                    mk = on ? (((in0w >> it) & 1u) ? 0 : 1) : 0;
+                    cnt0 = sm.cnt0[it];
+                    cnt1 = k - cnt0;
+                    same = false;
+                } else {
+                    lab = (on && (n1 - 2.0 * s1) < (n0 - 2.0 * s0)) ? 1 : 0;
+                    mk = lab;
+                    int c2[2] = {(on && lab == 0) ? 1 : 0, (on && lab != lab_old) ? 1 : 0};
+                    block_count<2>(c2, sm);
+                    cnt0 = c2[0];
+                    cnt1 = k - cnt0;
+                    same = c2[1] == 0;
+                    if (cnt0 == 0 || cnt1 == 0) {
+                        // _relocate_empty_clusters_dense: the point farthest from its centre founds the empty cluster
+                        const int o = (cnt1 == 0) ? 0 : 1;
+                        double dist = on ? di - 2.0 * (o ? s1 : s0) + (o ? n1 : n0) : -1.0;
+                        int far = i;
+                        block_argmax(dist, far, sm);
+                        if (dist > 0.0) {
+                            if (i == far) mk = 1 - o;
+                            if (o == 0) { cnt0 -= 1; cnt1 = 1; } else { cnt1 -= 1; cnt0 = 1; }
                         }
+                    }
+                    // incremental update of tA with the examples that changed side: the movers are compacted into an
+                    // ascending list (ballot + per-warp offsets) so that every thread walks only them, eight independent
+                    // L2 loads in flight at a time; the additions keep the ascending order (same bits as a full scan)
+                    const int dj = on ? (mk == 0) - (cur == 0) : 0;
+                    const unsigned bal = __ballot_sync(0xffffffffu, dj != 0);
+                    __syncthreads();  // previous readers of sm.moved / sm.wcnt are done
+                    if ((i & 31) == 0) sm.wcnt[i >> 5] = __popc(bal);
+                    __syncthreads();
+                    int base = 0, n_moved = 0;
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            if (e0 + u < n_moved) {
-                                const int j = jj[u] >= 0 ? jj[u] : ~jj[u];
-                                const double gcj = gv[u] - ri - sm.r[j] + m;
-                                tA += jj[u] >= 0 ? gcj : -gcj;
+                    for (int w = 0; w < kWarps; ++w) {
+                        const int c = sm.wcnt[w];
+                        if (w < (i >> 5)) base += c;
+                        n_moved += c;
+                    }
+                    if (dj != 0) sm.moved[base + __popc(bal & ((1u << (i & 31)) - 1u))] = (short)(dj > 0 ? i : ~i);
+                    __syncthreads();
+                    if (on) {
+                        for (int e0 = 0; e0 < n_moved; e0 += 8) {
+                            double gv[8];
+                            int jj[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int e = min(e0 + u, n_moved - 1);
+                                const int code = sm.moved[e];
+                                jj[u] = code;
+                                const int j = code >= 0 ? code : ~code;
+                                gv[u] = gsym(G, sm.trow, i, j);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                if (e0 + u < n_moved) {
+                                    const int j = jj[u] >= 0 ? jj[u] : ~jj[u];
+                                    const double gcj = gv[u] - ri - sm.r[j] + m;
+                                    tA += jj[u] >= 0 ? gcj : -gcj;
+                                }
                             }
                         }
                     }
                 }
+                double s0n, s1n, n0n, n1n, cross0, cross1;
                 cur = mk;
                 if (cnt0 == 0 || cnt1 == 0) {
                     // every point coincides with the surviving centre; sklearn leaves the empty centre at 0
@@ -454,6 +557,7 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
             __syncthreads();
         }
 
+        t1 = clock64(); clk[4] += t1 - t0; t0 = t1;
         // ---- score ----
         int cl[2] = {(on && sm.best_lab[i] == 0) ? 1 : 0, (on && sm.best_mask[i] == 0) ? 1 : 0};
         block_count<2>(cl, sm);
@@ -468,11 +572,9 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
         } else {
             double wa = 0.0, wb = 0.0;
             if (on) {
-#pragma unroll 8
-                for (int j = 0; j < k; ++j) {
-                    const double g = __ldcg(G + (int64_t)j * k + i);
+                sweep_column(G, sm.trow, i, k, [&](int j, double g) {
                     if (sm.best_mask[j] == 0) wa += g; else wb += g;
-                }
+                });
             }
             const bool ina = on && sm.best_mask[i] == 0, inb = on && sm.best_mask[i] == 1;
             double v[4] = {ina ? wa : 0.0, inb ? wa : 0.0, inb ? wb : 0.0, on ? (ca == 0 ? (inb ? ri : 0.0) : (ina ? ri : 0.0)) : 0.0};
@@ -492,16 +594,32 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
         }
         if (i == 0) p.out[neuron] = result;
         __syncthreads();
+        t1 = clock64(); clk[5] += t1 - t0;
+        clk[6] += 1;
     }
+    if (i == 0)
+        for (int c = 0; c < 7; ++c) atomicAdd(&g_phase_clk[c], clk[c]);
 }
 
 int poly_grid(int64_t C) { return (int)std::min<int64_t>(C, (int64_t)slb_sm_count() * 2); }
 
 }  // namespace
 
+extern "C" int slb_polysem_phase_clocks(uint64_t* out7, int reset) {
+    SLB_REQUIRE(out7, SLB_EINVAL, "slb_polysem_phase_clocks: null pointer");
+    unsigned long long host[8] = {0};
+    SLB_CUDA_OK(cudaMemcpyFromSymbol(host, g_phase_clk, sizeof(host)));
+    for (int c = 0; c < 7; ++c) out7[c] = host[c];
+    if (reset) {
+        unsigned long long zero[8] = {0};
+        SLB_CUDA_OK(cudaMemcpyToSymbol(g_phase_clk, zero, sizeof(zero)));
+    }
+    return SLB_OK;
+}
+
 extern "C" size_t slb_polysem_workspace_bytes(int64_t C, int64_t k) {
     if (C <= 0 || k <= 0 || k > kT) return 0;
-    return (size_t)poly_grid(C) * (size_t)k * (size_t)k * sizeof(double);
+    return (size_t)poly_grid(C) * (size_t)slot_doubles(k) * sizeof(double);
 }
 
 extern "C" int slb_polysem_2means(const float* V, int64_t C, int64_t k, int64_t D, const int64_t* first_centers,
@@ -514,7 +632,7 @@ extern "C" int slb_polysem_2means(const float* V, int64_t C, int64_t k, int64_t 
     SLB_REQUIRE(k <= kT, SLB_EUNSUPPORTED, "slb_polysem_2means: at most %d examples per neuron (got %lld)", kT, (long long)k);
     SLB_REQUIRE(D < (1ll << 31), SLB_EUNSUPPORTED, "slb_polysem_2means: D too large");
     SLB_REQUIRE(n_init >= 1 && n_init <= kMaxInit, SLB_EUNSUPPORTED, "slb_polysem_2means: 1 <= n_init <= %d", kMaxInit);
-    SLB_REQUIRE(((uintptr_t)workspace % 8) == 0, SLB_EINVAL, "slb_polysem_2means: workspace must be 8-byte aligned");
+    SLB_REQUIRE(((uintptr_t)workspace % 16) == 0, SLB_EINVAL, "slb_polysem_2means: workspace must be 16-byte aligned");
     const size_t need = slb_polysem_workspace_bytes(C, k);
     SLB_REQUIRE(workspace_bytes >= need, SLB_EWORKSPACE, "slb_polysem_2means: workspace needs %zu bytes, got %zu", need,
                 workspace_bytes);

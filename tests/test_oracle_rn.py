@@ -101,3 +101,52 @@ def test_stride1_bottleneck_matches_torchvision_bottleneck():
         with torch.no_grad():
             want = tv(x)
         assert torch.allclose(rp._bottleneck(x, sd, prefix, stride, ds), want, rtol=1e-12, atol=1e-12)
+
+
+def _spec_for(cfg, sd):
+    from oracle import rn_spec
+
+    return rn_spec.build(cfg.layers, cfg.embed_dim, cfg.heads, cfg.image_size, cfg.width, sd)
+
+
+def test_second_restatement_agrees_on_keys_stem_blocks_and_pool():
+    """oracle/rn_spec.py rebuilds the tower as nn.Modules from the published description; rn_port's state dict must load
+    strictly (names and shapes follow from the module nesting) and every stage must agree: the stem, each bottleneck —
+    including the stride-2 blocks whose stride is an average pool on both paths — and the attention pool."""
+    import pytest
+
+    for name in ("RN-tiny-test", "RN-small-test"):
+        cfg = rp.CONFIGS[name]
+        sd = rp.init_weights(cfg, seed=11)
+        net = _spec_for(cfg, sd)
+        img = torch.randn(2, 3, cfg.image_size, cfg.image_size, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+        taps = {}
+        got = rp.encode_image(sd, cfg, img, dtype=torch.float64, taps=taps)
+        with torch.no_grad():
+            x = net.stem(img)
+            assert torch.allclose(x, taps["stem"], rtol=1e-12, atol=1e-12), f"{name}: stem"
+            strides_seen = set()
+            for prefix, _inpl, _pl, stride, _ds in rp.block_plan(cfg):
+                layer, idx = prefix.split(".")[1:3]
+                x = getattr(net, layer)[int(idx)](x)
+                assert torch.allclose(x, taps[prefix], rtol=1e-11, atol=1e-11), f"{name}: {prefix} (stride {stride})"
+                strides_seen.add(stride)
+            assert strides_seen == {1, 2}
+            want = net.attnpool(x)
+        assert torch.allclose(got, want, rtol=1e-10, atol=1e-11), name
+    # a key the module structure does not produce is rejected
+    bad = dict(sd)
+    bad["visual.layer1.0.downsample.-1.weight"] = torch.zeros(1)
+    with pytest.raises(KeyError, match="published module structure"):
+        _spec_for(cfg, bad)
+
+
+def test_second_restatement_agrees_at_rn50_size():
+    cfg = rp.CONFIGS["RN50"]
+    sd = rp.init_weights(cfg, seed=12)
+    img = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(4), dtype=torch.float64)
+    got = rp.encode_image(sd, cfg, img, dtype=torch.float64)
+    with torch.no_grad():
+        want = _spec_for(cfg, sd)(img)
+    assert got.shape == (1, 1024)
+    assert ((got - want).abs().max() / want.abs().max()).item() < 1e-11
