@@ -158,6 +158,14 @@ int slb_polysem_2means(const float* V, int64_t C, int64_t k, int64_t D, const in
  * scores.redundancy_score's `(sims - 2 I).max(-1)` (scores.py:78-80) without materialising the identity. */
 int slb_rowmax_offdiag(const float* S, int64_t rows, int64_t cols, int64_t row0, float* out, void* stream);
 
+/* K9. redundancy_score (reference scores.py:51-81): out[0] = mean_i max_{j != i} cos(cones_i, cones_j) for cones (n, D)
+ * fp32. The rows are L2-normalised into split planes once and ONE tensor-core GEMM of the planes against themselves keeps
+ * only the running row maxima (diagonal lowered by 2, like `sims - 2 I`) in its epilogue: the n x n cosine matrix is
+ * never written. NaN rows propagate like torch.max. D % 4 == 0, D <= 2048.
+ * workspace: 256-byte aligned device memory >= slb_redundancy_workspace_bytes(n, D). */
+size_t slb_redundancy_workspace_bytes(int64_t n, int64_t D);
+int slb_redundancy(const float* cones, int64_t n, int64_t D, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * embed: the CLIP / SigLIP ViT image tower  (foundation_models/clip.py:103-163 -> open_clip, not vendored)
  * ---------------------------------------------------------------------------------------- */

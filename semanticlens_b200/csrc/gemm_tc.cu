@@ -62,7 +62,22 @@ struct GemmParams {
     int split_acc;  // 1: hi·lo + lo·hi accumulate in their own TMEM columns and meet hi·hi in the epilogue (fp32 add)
     int fmt;     // plane format of A/W and of out_planes
     unsigned int* dbg;  // SLB_GEMM_DEBUG=1: host-mapped words [cta][16] that a timed-out wait reports into (else null)
+    // redundancy_score (scores.py:77-80) fused into the epilogue: nothing is stored; rowmax[m] = max over columns
+    // n < n_valid of (value - 2 [n == m]) is kept with atomics — the n x n cosine matrix never exists in memory
+    float* rowmax;    // [n_valid] pre-filled with -inf, or null
+    int64_t n_valid;  // true problem size (rows and columns past it are zero padding)
 };
+
+// max for floats of either sign through the integer atomics; NaN (stored as the positive quiet NaN) wins over everything
+__device__ __forceinline__ void atomic_max_float(float* addr, float val) {
+    if (val != val) {
+        atomicMax(reinterpret_cast<int*>(addr), 0x7FC00000);
+    } else if (val >= 0.0f) {
+        atomicMax(reinterpret_cast<int*>(addr), __float_as_int(val));
+    } else {
+        atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(val));
+    }
+}
 
 __device__ __forceinline__ float act_apply(float v, int epi) {
     switch (epi) {
@@ -118,6 +133,26 @@ __device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr,
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
     }
     if (nb >= p.N) return;  // warp-uniform
+    if (p.rowmax) {
+        // thread = row m: fold its 32 columns; most chunks do not raise the running maximum, so a plain read filters
+        // the atomics down to ~ln(#chunks) per row
+        const int64_t m = m_warp + lane;
+        if (m < p.n_valid && nb < p.n_valid) {
+            float mx = -INFINITY;
+            bool nan = false;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int64_t n = nb + j;
+                float x = (n == m) ? v[j] - 2.0f : v[j];
+                nan |= (x != x) && n < p.n_valid;
+                mx = (n < p.n_valid) ? fmaxf(mx, x) : mx;
+            }
+            if (nan) mx = __int_as_float(0x7FC00000);  // torch.max propagates NaN
+            const float cur = __ldcg(p.rowmax + m);
+            if (!(mx <= cur)) atomic_max_float(p.rowmax + m, mx);
+        }
+        return;
+    }
     if (p.row_scale) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= rs;
@@ -601,6 +636,8 @@ extern "C" int slb_split_planes(const float* x, int64_t n, int plane_fmt, float 
     return SLB_OK;
 }
 
+static int run_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, GemmParams p, void* stream);
+
 extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, int plane_fmt, int64_t M, int64_t N,
                               int64_t K, float alpha, const float* bias, const float* residual, const float* row_scale,
                               const float* col_scale, int epilogue, int passes, float* out_f32, uint16_t* out_planes,
@@ -612,9 +649,35 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
     SLB_REQUIRE(plane_fmt == SLB_PLANE_F16 || plane_fmt == SLB_PLANE_BF16, SLB_EINVAL, "slb_gemm_split: bad plane format");
     SLB_REQUIRE(passes == 1 || passes == 3 || passes == SLB_PASSES_SPLIT_ACC, SLB_EINVAL,
                 "slb_gemm_split: passes must be 1, 3 or SLB_PASSES_SPLIT_ACC");
+    SLB_REQUIRE(epilogue >= SLB_EPI_NONE && epilogue <= SLB_EPI_ADD_RELU, SLB_EINVAL, "slb_gemm_split: bad epilogue");
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K;
+    p.alpha = alpha;
+    p.bias = bias; p.residual = residual; p.row_scale = row_scale; p.col_scale = col_scale;
+    p.out_f32 = out_f32; p.out_planes = out_planes;
+    p.epilogue = epilogue; p.passes = passes; p.fmt = plane_fmt;
+    return run_gemm_split(a_planes, w_planes, p, stream);
+}
+
+// Fused redundancy row maxima (see GemmParams::rowmax): planes (2, n_pad, K) of the unit-norm rows, rowmax [n] = -inf.
+int slb_gemm_rowmax_offdiag(const uint16_t* planes, int64_t n, int64_t n_pad, int64_t K, float alpha, float* rowmax, void* stream) {
+    GemmParams p{};
+    p.M = n_pad; p.N = n_pad; p.K = K;
+    p.alpha = alpha;
+    p.epilogue = SLB_EPI_NONE; p.passes = 3; p.fmt = SLB_PLANE_F16;
+    p.rowmax = rowmax; p.n_valid = n;
+    return run_gemm_split(planes, planes, p, stream);
+}
+
+static int run_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, GemmParams p, void* stream) {
+    const int64_t M = p.M, N = p.N, K = p.K;
+    int passes = p.passes;
     const int split_acc = passes == SLB_PASSES_SPLIT_ACC;
     if (split_acc) passes = 3;
-    SLB_REQUIRE(epilogue >= SLB_EPI_NONE && epilogue <= SLB_EPI_ADD_RELU, SLB_EINVAL, "slb_gemm_split: bad epilogue");
+    p.passes = passes; p.split_acc = split_acc;
+    float* out_f32 = p.out_f32;
+    uint16_t* out_planes = p.out_planes;
+    const float* residual = p.residual;
     SLB_REQUIRE(K >= BK && K % BK == 0, SLB_EUNSUPPORTED, "slb_gemm_split: K must be a positive multiple of 64 (got %lld)",
                 (long long)K);
     SLB_REQUIRE(N % 8 == 0, SLB_EUNSUPPORTED, "slb_gemm_split: N must be a multiple of 8 (got %lld)", (long long)N);
@@ -624,14 +687,9 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
                     ((uintptr_t)residual % 16) == 0 && ((M * K * 2) % 16) == 0 && ((N * K * 2) % 16) == 0 &&
                     ((M * N * 2) % 16) == 0,
                 SLB_EINVAL, "slb_gemm_split: operands must be 16-byte aligned");
-    SlbProfScope prof("K4 gemm_split (tcgen05)", stream, 2.0 * (double)M * (double)N * (double)K * (double)passes,
+    SlbProfScope prof(p.rowmax ? "K9 cosine row-max (tcgen05)" : "K4 gemm_split (tcgen05)", stream,
+                      2.0 * (double)M * (double)N * (double)K * (double)passes,
                       4.0 * ((double)M * (double)K + (double)N * (double)K) + ((out_f32 ? 4.0 : 0.0) + (out_planes ? 4.0 : 0.0)) * (double)M * (double)N);
-    GemmParams p{};
-    p.M = M; p.N = N; p.K = K;
-    p.alpha = alpha;
-    p.bias = bias; p.residual = residual; p.row_scale = row_scale; p.col_scale = col_scale;
-    p.out_f32 = out_f32; p.out_planes = out_planes;
-    p.epilogue = epilogue; p.passes = passes; p.fmt = plane_fmt; p.split_acc = split_acc;
     // Kernel choice (measured on B200, profiles/r01_gemm_variants.jsonl). One-CTA 128 x 128 tiles read 128 B/clk of shared
     // memory per MMA cycle (the limit); CTA pairs share W: 256 x 128 pair tiles (double-buffered accumulators) win when W
     // is large (cosine GEMM), 256 x 256 pair tiles (single-buffered) when K is long and the tile count fills the machine

@@ -18,8 +18,11 @@ constexpr int kWarpsPerCta = 8;
 
 __device__ __forceinline__ float sumsq4(const float4& v) { return (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w); }
 
-// F.normalize: x / max(||x||_2, eps)
-__device__ __forceinline__ float inv_norm(float ss, float eps) { return 1.0f / fmaxf(sqrtf(ss), eps); }
+// F.normalize: x / max(||x||_2, eps). torch's clamp_min keeps a NaN norm (the whole row becomes NaN); fmaxf would drop it.
+__device__ __forceinline__ float inv_norm(float ss, float eps) {
+    const float nrm = sqrtf(ss);
+    return 1.0f / (nrm != nrm ? nrm : fmaxf(nrm, eps));
+}
 
 // ------------------------------------------------------------------------------------------------
 // one warp per row: inverse norm, then planes of x * inv (zero padded from D up to Kpad columns)
@@ -177,13 +180,36 @@ rowmax_offdiag_kernel(const float* __restrict__ S, int64_t rows, int64_t cols, i
 }
 
 template <int NCH>
-int launch_normalize(const float* x, int64_t rows, int D, int Kpad, float eps, int fmt, float plane_scale, uint16_t* planes,
-                     float* inv, cudaStream_t st) {
+int launch_normalize(const float* x, int64_t rows, int D, int Kpad, float eps, int fmt, float plane_scale, uint16_t* hi,
+                     uint16_t* lo, float* inv, cudaStream_t st) {
     const unsigned grid = (unsigned)slb_ceil_div(rows, kWarpsPerCta);
-    normalize_split_kernel<NCH><<<grid, kWarpsPerCta * 32, 0, st>>>(x, rows, D, Kpad, eps, fmt, plane_scale, planes,
-                                                                   planes ? planes + rows * (int64_t)Kpad : nullptr, inv);
+    normalize_split_kernel<NCH><<<grid, kWarpsPerCta * 32, 0, st>>>(x, rows, D, Kpad, eps, fmt, plane_scale, hi, lo, inv);
     SLB_LAUNCH_OK("normalize_split");
     return SLB_OK;
+}
+
+// mean of n floats in a fixed order (one CTA, float64 accumulation): the last step of redundancy_score
+__global__ void __launch_bounds__(256) mean_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+    __shared__ double part[256];
+    double acc = 0.0;
+    bool nan = false;
+    for (int64_t i = threadIdx.x; i < n; i += 256) {
+        const float v = x[i];
+        nan |= v != v;
+        acc += (double)v;
+    }
+    part[threadIdx.x] = nan ? __longlong_as_double(0x7FF8000000000000ll) : acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = (float)(part[0] / (double)n);
+}
+
+__global__ void fill_kernel(float* __restrict__ x, int64_t n, float v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
 }
 
 template <int NCH>
@@ -201,23 +227,71 @@ int64_t pad64(int64_t d) { return (d + 63) / 64 * 64; }
 
 }  // namespace
 
-extern "C" int slb_normalize_split_rows(const float* x, int64_t rows, int64_t D, float eps, int plane_fmt, float plane_scale,
-                                        uint16_t* planes, float* inv_norms, void* stream) {
+// planes as two explicit pointers: the lo plane need not follow the hi plane directly (padded operands)
+static int normalize_split_rows_2p(const float* x, int64_t rows, int64_t D, float eps, int plane_fmt, float plane_scale,
+                                   uint16_t* hi, uint16_t* lo, float* inv_norms, void* stream) {
     SLB_REQUIRE(plane_scale > 0.0f, SLB_EINVAL, "slb_normalize_split_rows: plane_scale must be positive");
     SLB_REQUIRE(rows >= 0 && D > 0, SLB_EINVAL, "slb_normalize_split_rows: bad size");
     if (rows == 0) return SLB_OK;
-    SLB_REQUIRE(x && (planes || inv_norms), SLB_EINVAL, "slb_normalize_split_rows: null pointer");
+    SLB_REQUIRE(x && (hi || inv_norms), SLB_EINVAL, "slb_normalize_split_rows: null pointer");
     SLB_REQUIRE(plane_fmt == SLB_PLANE_F16 || plane_fmt == SLB_PLANE_BF16, SLB_EINVAL, "slb_normalize_split_rows: bad format");
-    SLB_REQUIRE(D % 4 == 0 && D <= 2048 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)planes % 8) == 0, SLB_EUNSUPPORTED,
-                "slb_normalize_split_rows: D must be a multiple of 4 and <= 2048 (got %lld), x 16-byte aligned", (long long)D);
+    SLB_REQUIRE(D % 4 == 0 && D <= 2048 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)hi % 8) == 0 && ((uintptr_t)lo % 8) == 0,
+                SLB_EUNSUPPORTED, "slb_normalize_split_rows: D must be a multiple of 4 and <= 2048 (got %lld), x 16-byte aligned",
+                (long long)D);
     const int Kpad = (int)pad64(D);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    SlbProfScope prof("K6 normalize_split_rows", stream, 0.0, (double)rows * (4.0 * (double)D + (planes ? 4.0 * Kpad : 0.0)));
+    SlbProfScope prof("K6 normalize_split_rows", stream, 0.0, (double)rows * (4.0 * (double)D + (hi ? 4.0 * Kpad : 0.0)));
     const int nch = (int)slb_ceil_div(Kpad, 128);
-    if (nch <= 2) return launch_normalize<2>(x, rows, (int)D, Kpad, eps, plane_fmt, plane_scale, planes, inv_norms, st);
-    if (nch <= 4) return launch_normalize<4>(x, rows, (int)D, Kpad, eps, plane_fmt, plane_scale, planes, inv_norms, st);
-    if (nch <= 8) return launch_normalize<8>(x, rows, (int)D, Kpad, eps, plane_fmt, plane_scale, planes, inv_norms, st);
-    return launch_normalize<16>(x, rows, (int)D, Kpad, eps, plane_fmt, plane_scale, planes, inv_norms, st);
+    if (nch <= 2) return launch_normalize<2>(x, rows, (int)D, Kpad, eps, plane_fmt, plane_scale, hi, lo, inv_norms, st);
+    if (nch <= 4) return launch_normalize<4>(x, rows, (int)D, Kpad, eps, plane_fmt, plane_scale, hi, lo, inv_norms, st);
+    if (nch <= 8) return launch_normalize<8>(x, rows, (int)D, Kpad, eps, plane_fmt, plane_scale, hi, lo, inv_norms, st);
+    return launch_normalize<16>(x, rows, (int)D, Kpad, eps, plane_fmt, plane_scale, hi, lo, inv_norms, st);
+}
+
+extern "C" int slb_normalize_split_rows(const float* x, int64_t rows, int64_t D, float eps, int plane_fmt, float plane_scale,
+                                        uint16_t* planes, float* inv_norms, void* stream) {
+    return normalize_split_rows_2p(x, rows, D, eps, plane_fmt, plane_scale, planes,
+                                   planes ? planes + rows * pad64(D) : nullptr, inv_norms, stream);
+}
+
+// K9 redundancy_score (scores.py:51-81): mean_i max_{j != i} cos(x_i, x_j). The rows are normalised into split planes
+// once; ONE tensor-core GEMM of the planes against themselves keeps only the row maxima (diagonal lowered by 2) in its
+// epilogue — the n x n cosine matrix (17 GB at n = 65 536) is never written — and a fixed-order mean closes.
+int slb_gemm_rowmax_offdiag(const uint16_t* planes, int64_t n, int64_t n_pad, int64_t K, float alpha, float* rowmax, void* stream);
+
+extern "C" size_t slb_redundancy_workspace_bytes(int64_t n, int64_t D) {
+    if (n <= 0 || D <= 0) return 0;
+    const size_t n_pad = (size_t)((n + 7) / 8 * 8);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    return up((size_t)2 * n_pad * (size_t)pad64(D) * 2) + up((size_t)n * 4);
+}
+
+extern "C" int slb_redundancy(const float* cones, int64_t n, int64_t D, float* out, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+    SLB_REQUIRE(n > 0 && D > 0, SLB_EINVAL, "slb_redundancy: bad size");
+    SLB_REQUIRE(cones && out && workspace, SLB_EINVAL, "slb_redundancy: null pointer");
+    SLB_REQUIRE(((uintptr_t)workspace % 256) == 0, SLB_EINVAL, "slb_redundancy: workspace must be 256-byte aligned");
+    const size_t need = slb_redundancy_workspace_bytes(n, D);
+    SLB_REQUIRE(workspace_bytes >= need, SLB_EWORKSPACE, "slb_redundancy: workspace needs %zu bytes, got %zu", need, workspace_bytes);
+    const int64_t n_pad = (n + 7) / 8 * 8, Kpad = pad64(D);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint16_t* hi = static_cast<uint16_t*>(workspace);
+    uint16_t* lo = hi + n_pad * Kpad;
+    float* rowmax = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + (((size_t)2 * n_pad * Kpad * 2 + 255) & ~(size_t)255));
+    if (n_pad != n) {  // zero rows: cos = 0 against everything, and excluded from the maxima by n_valid
+        SLB_CUDA_OK(cudaMemsetAsync(hi + n * Kpad, 0, (size_t)(n_pad - n) * Kpad * 2, st));
+        SLB_CUDA_OK(cudaMemsetAsync(lo + n * Kpad, 0, (size_t)(n_pad - n) * Kpad * 2, st));
+    }
+    const float sc = 1024.0f;
+    int rc = normalize_split_rows_2p(cones, n, D, 1e-12f, SLB_PLANE_F16, sc, hi, lo, nullptr, stream);
+    if (rc != SLB_OK) return rc;
+    fill_kernel<<<(unsigned)slb_ceil_div(n, 256), 256, 0, st>>>(rowmax, n, -INFINITY);
+    SLB_LAUNCH_OK("fill");
+    rc = slb_gemm_rowmax_offdiag(hi, n, n_pad, Kpad, 1.0f / (sc * sc), rowmax, stream);
+    if (rc != SLB_OK) return rc;
+    mean_kernel<<<1, 256, 0, st>>>(rowmax, n, out);
+    SLB_LAUNCH_OK("mean");
+    return SLB_OK;
 }
 
 extern "C" size_t slb_cosine_gemm_workspace_bytes(int64_t M, int64_t N, int64_t D) {

@@ -189,7 +189,7 @@ __device__ __forceinline__ float slb_from_plane(uint16_t b, int fmt) {
 // s * x ~= hi + lo with hi = rn16(s * x), lo = rn16(s * x - hi); the caller applies the tensor's power-of-two scale s
 // (see slb200.h). 22 (fp16) / 16 (bf16) significant bits in total. fp16 planes saturate at +-65504.
 __device__ __forceinline__ void slb_split2(float v, int fmt, uint16_t& hi, uint16_t& lo) {
-    if (fmt == 0) v = fminf(fmaxf(v, -65504.0f), 65504.0f);
+    if (fmt == 0 && v == v) v = fminf(fmaxf(v, -65504.0f), 65504.0f);  // saturate, but let NaN through (fminf / fmaxf drop it)
     hi = slb_to_plane(v, fmt);
     lo = slb_to_plane(v - slb_from_plane(hi, fmt), fmt);
 }

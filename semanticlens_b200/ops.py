@@ -557,28 +557,22 @@ def polysem_2means(V: torch.Tensor, random_state: int = 123, replace_empty_clust
     return out
 
 
-def redundancy(cones: torch.Tensor, row_block: int = 8192) -> torch.Tensor:
+def redundancy(cones: torch.Tensor) -> torch.Tensor:
     """K9: mean_i max_{j != i} cos(cones_i, cones_j) for a (n, D) fp32 CUDA tensor -> 0-d fp32 tensor.
 
-    The n x n cosine matrix is produced in row blocks by the tensor-core GEMM and reduced by a row-max kernel, so at
-    most row_block x n floats exist at a time."""
+    One call: normalise + split the rows, one tensor-core GEMM whose epilogue keeps only the row maxima (the n x n cosine
+    matrix is never written), fixed-order mean."""
     lib = N.load(require_device=True)
     N.require_cuda(cones, "cones")
     assert cones.ndim == 2
-    cones = cones.detach().to(torch.float32).contiguous()
+    cones = _pad_features(cones.detach().to(torch.float32)).contiguous()
     n, D = cones.shape
-    n_pad = (n + 7) // 8 * 8
-    yp = normalize_split_rows(cones)
-    if n_pad != n:
-        yp = torch.cat([yp, torch.zeros((2, n_pad - n, yp.shape[2]), dtype=yp.dtype, device=yp.device)], 1).contiguous()
-    rowmax = torch.empty((n,), dtype=torch.float32, device=cones.device)
-    for r0 in range(0, n, row_block):
-        r1 = min(n, r0 + row_block)
-        xp = yp[:, r0:r1].contiguous()
-        S, _ = gemm_split(xp, yp, passes=3, alpha=1.0 / (UNIT_ROW_PLANE_SCALE * UNIT_ROW_PLANE_SCALE))
-        with _dev_guard(cones):
-            # padded columns hold cos = 0 and must not take part in the max: pass the true column count via a view
-            Sv = S if n_pad == n else S[:, :n].contiguous()
-            rc = lib.slb_rowmax_offdiag(Sv.data_ptr(), r1 - r0, n, r0, rowmax[r0:r1].data_ptr(), N.stream_ptr(cones.device))
-        N.check(rc, "slb_rowmax_offdiag")
-    return rowmax.mean()
+    out = torch.empty((), dtype=torch.float32, device=cones.device)
+    if n == 0:
+        raise RuntimeError("max(): Expected reduction dim -1 to have non-zero size.")  # what torch raises in the reference
+    need = lib.slb_redundancy_workspace_bytes(n, D)
+    ws = torch.empty(need, dtype=torch.uint8, device=cones.device)
+    with _dev_guard(cones):
+        rc = lib.slb_redundancy(cones.data_ptr(), n, D, out.data_ptr(), ws.data_ptr(), need, N.stream_ptr(cones.device))
+    N.check(rc, "slb_redundancy")
+    return out

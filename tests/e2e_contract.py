@@ -5,10 +5,12 @@ The two backends' fp32 activations differ at the 1e-6 level, which flips the bf1
 its exact value sits next to a rounding midpoint. Instead of a percentage threshold the test ENUMERATES those elements
 from a float64 forward of the model and an a-priori error budget, and demands exactness everywhere else:
 
-  budget   tau[c] = max(SIGMAS * rms_i(a_cpu32[i, c] - a64[i, c]),  REL_FLOOR * mean |summand of channel c|)
-           — the fp32 forward noise of channel c, estimated from the CPU fp32 run against the float64 run (the GPU result
-           is not used, so the budget cannot be inflated by a GPU bug), with an 8-sigma margin for the tail; it grows
-           with the depth of the hooked layer, as the rounding errors of the layers before it accumulate
+  budget   tau[c] = SIGMAS * max(sigma_cpu[c], sigma_gpu[c], REL_FLOOR * scale[c]),  sigma_x[c] = rms_i(a_x32[i, c] - a64[i, c]),
+           scale[c] = mean |summand of channel c| — the fp32 forward noise of channel c on either backend against the
+           float64 run (a per-CHANNEL statistic over all images, 8-sigma margin; cuDNN's Winograd / implicit-GEMM
+           kernels are noisier than oneDNN's direct convolution, and the noise grows with the depth of the hooked layer).
+           sigma_gpu itself must stay fp32-grade (median over channels of sigma_gpu / scale <= GPU_NOISE_CEILING), so a
+           systematic GPU error cannot hide behind its own budget
   excused  element (image i, channel c) iff bf16(a64 - tau) != bf16(a64 + tau)        (a64 = float64 aggregate)
   (1) every (i, c) whose bf16 candidate differs between the two backends is excused — anything else is a bug;
   (2) the GPU state is EXACTLY the canonical top-k of the GPU candidates (values and ids, bit for bit), for every row;
@@ -24,7 +26,8 @@ import torch
 from oracle import collect as oc
 
 SIGMAS = 8.0
-REL_FLOOR = 1e-6
+REL_FLOOR = 1e-7
+GPU_NOISE_CEILING = 2e-5
 
 
 def _tap(model, layers, batches, to):
@@ -60,11 +63,18 @@ def check_collect_contract(net_cpu, layers, batches_cpu, op, kind, k, gpu_state,
         else:
             a64 = (np.abs(flat) if op == "absmax" else flat).max(-1)
         agg_cpu = np.concatenate([oc.aggregate_exact(m, op, kind) for m in maps32[name]])  # (N, C) fp32
-        noise = np.sqrt(((agg_cpu.astype(np.float64) - a64) ** 2).mean(axis=0))[None, :]
-        tau = np.maximum(SIGMAS * noise, REL_FLOOR * np.abs(flat).mean(axis=(0, 2))[None, :])  # (1, C)
+        agg_dev = np.concatenate(agg_gpu[name])
+        scale = np.abs(flat).mean(axis=(0, 2))[None, :]
+        sigma_cpu = np.sqrt(((agg_cpu.astype(np.float64) - a64) ** 2).mean(axis=0))[None, :]
+        sigma_gpu = np.sqrt(((agg_dev.astype(np.float64) - a64) ** 2).mean(axis=0))[None, :]
+        # layer-level sanity (the median over channels: a nearly dead post-ReLU channel has a tiny scale but inherits the
+        # noise of its pre-activation, so single channels can sit far above the typical ratio)
+        ratio = np.median(sigma_gpu / (scale + 1e-30))
+        assert ratio <= GPU_NOISE_CEILING, f"{name}: the GPU forward is not fp32-grade: median noise / scale = {ratio:.2e}"
+        tau = SIGMAS * np.maximum(np.maximum(sigma_cpu, sigma_gpu), REL_FLOOR * scale)  # (1, C)
         excused = oc.f32_to_bf16_bits((a64 - tau).astype(np.float32)) != oc.f32_to_bf16_bits((a64 + tau).astype(np.float32))
         cand_cpu = oc.f32_to_bf16_bits(agg_cpu)
-        cand_gpu = oc.f32_to_bf16_bits(np.concatenate(agg_gpu[name]))
+        cand_gpu = oc.f32_to_bf16_bits(agg_dev)
         differ = ~oc.values_equal(cand_cpu, cand_gpu)
         # (1)
         unexplained = differ & ~excused
@@ -89,6 +99,7 @@ def check_collect_contract(net_cpu, layers, batches_cpu, op, kind, k, gpu_state,
         clean = ~differ.any(axis=0)  # channels whose candidates are identical on both backends
         errs = oc.check_tie_aware(gb[clean], gi[clean], rb[clean], ri[clean], cand_gpu.T[clean])
         assert not errs, f"{name}: GPU vs reference port on rows with identical candidates: {errs[:3]}"
-        report[name] = {"elements": int(differ.size), "excused": int(excused.sum()), "differing": int(differ.sum()),
+        report[name] = {"gpu_noise_over_scale_median": float(ratio),
+                        "cpu_noise_over_scale_median": float(np.median(sigma_cpu / (scale + 1e-30))), "elements": int(differ.size), "excused": int(excused.sum()), "differing": int(differ.sum()),
                         "rows": int(clean.size), "rows_checked_exactly": int(clean.sum())}
     return report

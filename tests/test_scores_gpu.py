@@ -77,6 +77,30 @@ def test_embeddings_in_half_precision_are_gathered(S):
     assert torch.equal(ops.gather_rows(table, idx).cpu(), table.float().cpu()[idx])
 
 
+@pytest.mark.parametrize("n,D", [(1, 8), (2, 64), (131, 96), (1000, 512), (4099, 320)])
+def test_redundancy_fused_rowmax_vs_reference_port(S, n, D):
+    """K9: the row maxima come out of the GEMM epilogue (atomics over column tiles); sizes that are not multiples of the
+    8-row padding or of the tile sizes, a single row (the diagonal alone: cos - 2 = -1), duplicates (maximum = 1)."""
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, D, generator=g)
+    if n > 100:
+        x[7] = 3 * x[90]  # a duplicate direction: row maximum exactly 1 for both
+    want = rp.redundancy_score(x)
+    got = S.redundancy_score(x.cuda())
+    assert got.shape == () and got.dtype == torch.float32
+    maxnorm_close(got.cpu().numpy(), want.numpy())
+
+
+def test_redundancy_nan_and_batched_and_empty(S):
+    x = torch.randn(40, 32, generator=torch.Generator().manual_seed(1))
+    x[3, 5] = float("nan")
+    assert torch.isnan(S.redundancy_score(x.cuda())).item() and torch.isnan(rp.redundancy_score(x)).item()
+    xb = torch.randn(3, 17, 24, generator=torch.Generator().manual_seed(2))
+    maxnorm_close(S.redundancy_score(xb).numpy(), rp.redundancy_score(xb).numpy())
+    with pytest.raises(RuntimeError):
+        S.redundancy_score(torch.empty(0, 16).cuda())
+
+
 def test_golden_clarity_redundancy(golden, S):
     z = np.load(golden / "scores.npz")
     maxnorm_close(S.clarity_score(torch.from_numpy(z["V"]).cuda()).cpu().numpy(), z["clarity"])
