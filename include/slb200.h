@@ -315,9 +315,10 @@ size_t slb_vit_workspace_bytes(const SlbVitWeights* w, int64_t B);
 int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t B, float* out, void* workspace,
                     size_t workspace_bytes, void* stream);
 
-/* The CLIP text tower in one call (open_clip CLIP.encode_text behind clip.py:120-135; reached from Lens.text_probing,
- * lens.py:166-203): token + positional embedding, `layers` pre-LN blocks with a causal mask, ln_final, the end-of-text
- * token's feature times text_projection; un-normalised. head_dim must be 64 and plane_fmt fp16 (tensor-core attention). */
+/* The CLIP / SigLIP text tower in one call (open_clip CLIP.encode_text / CustomTextCLIP.encode_text behind
+ * clip.py:120-135; reached from Lens.text_probing, lens.py:166-203): token + positional embedding, `layers` pre-LN blocks
+ * (causal mask for CLIP, none for SigLIP), ln_final, the pooled token's feature (CLIP: end-of-text; SigLIP: last position)
+ * times text_projection (+ bias for SigLIP); un-normalised. head_dim must be 64 and plane_fmt fp16 (tensor-core attention). */
 typedef struct {
     int32_t context, vocab, width, layers, heads, mlp, embed_dim;
     int32_t act, plane_fmt;
@@ -327,6 +328,11 @@ typedef struct {
     const float* ln_final_g; const float* ln_final_b;
     const uint16_t* proj;  /* planes [2, embed_dim, W] (= text_projection transposed) */
     const SlbVitLayer* layer; /* HOST array */
+    /* SigLIP text towers (open_clip TextTransformer with no_causal_mask, pool_type "last", proj_bias; reached through
+     * clip.py:190-215 SigLipV2.encode_text): bidirectional attention, a biased projection; the caller passes the LAST
+     * position of every sequence as eot_rows. CLIP: non_causal = 0, proj_b = NULL. */
+    int32_t non_causal;
+    const float* proj_b;   /* [embed_dim] or NULL */
 } SlbTextWeights;
 
 size_t slb_text_workspace_bytes(const SlbTextWeights* w, int64_t B);

@@ -326,6 +326,11 @@ class TextConfig:
     embed_dim: int
     act: str = "gelu"
     eps: float = 1e-5
+    # "clip": causal mask, end-of-text (argmax) pooling, bias-free text_projection matrix (W, D).
+    # "siglip": open_clip's TextTransformer as the SigLIP configs set it up (no_causal_mask, pool_type "last",
+    # proj_bias: text_projection is an nn.Linear) — what the reference reaches through SigLipV2.encode_text
+    # (foundation_models/clip.py:190-215). Pinned against HF transformers' SiglipTextModel (tests/test_vit_oracle.py).
+    arch: str = "clip"
 
     @property
     def mlp(self):
@@ -336,6 +341,8 @@ TEXT_CONFIGS = {
     "ViT-B-32": TextConfig("ViT-B-32", 77, 49408, 512, 12, 8, 512),
     "ViT-L-14": TextConfig("ViT-L-14", 77, 49408, 768, 12, 12, 768),
     "text-tiny-test": TextConfig("text-tiny-test", 12, 100, 128, 2, 2, 32),
+    "ViT-B-16-SigLIP": TextConfig("ViT-B-16-SigLIP", 64, 32000, 768, 12, 12, 768, act="gelu_tanh", eps=1e-6, arch="siglip"),
+    "siglip-text-tiny-test": TextConfig("siglip-text-tiny-test", 16, 100, 128, 2, 2, 64, act="gelu_tanh", eps=1e-6, arch="siglip"),
 }
 
 
@@ -350,6 +357,10 @@ def init_text_weights(cfg: TextConfig, seed: int = 1) -> dict[str, torch.Tensor]
         "ln_final.bias": 0.1 * rn(W),
         "text_projection": rn(W, cfg.embed_dim) * W**-0.5,
     }
+    if cfg.arch == "siglip":
+        del sd["text_projection"]
+        sd["text_projection.weight"] = rn(cfg.embed_dim, W) * W**-0.5
+        sd["text_projection.bias"] = 0.02 * rn(cfg.embed_dim)
     proj_std = W**-0.5 * (2 * L) ** -0.5
     for i in range(L):
         p = f"transformer.resblocks.{i}."
@@ -377,6 +388,8 @@ def encode_text(sd: dict, cfg: TextConfig, tokens: torch.Tensor, dtype=torch.flo
     dh = W // H
     x = w["token_embedding.weight"][tokens] + w["positional_embedding"][:T]
     mask = torch.full((T, T), float("-inf"), dtype=dtype, device=tokens.device).triu(1)
+    if cfg.arch == "siglip":
+        mask = torch.zeros_like(mask)
     for i in range(cfg.layers):
         p = f"transformer.resblocks.{i}."
         h = F.layer_norm(x, (W,), w[p + "ln_1.weight"], w[p + "ln_1.bias"], cfg.eps)
@@ -389,4 +402,6 @@ def encode_text(sd: dict, cfg: TextConfig, tokens: torch.Tensor, dtype=torch.flo
         h = _act(F.linear(h, w[p + "mlp.c_fc.weight"], w[p + "mlp.c_fc.bias"]), cfg.act)
         x = x + F.linear(h, w[p + "mlp.c_proj.weight"], w[p + "mlp.c_proj.bias"])
     x = F.layer_norm(x, (W,), w["ln_final.weight"], w["ln_final.bias"], cfg.eps)
+    if cfg.arch == "siglip":
+        return F.linear(x[:, -1], w["text_projection.weight"], w["text_projection.bias"])
     return x[torch.arange(B, device=tokens.device), tokens.argmax(dim=-1)] @ w["text_projection"]

@@ -163,6 +163,7 @@ class SlbTextWeights(ctypes.Structure):
         + [("ln_eps", c_float)]
         + [(n, c_void_p) for n in ("tok_emb", "pos", "ln_final_g", "ln_final_b", "proj")]
         + [("layer", ctypes.POINTER(SlbVitLayer))]
+        + [("non_causal", ctypes.c_int32), ("proj_b", c_void_p)]
     )
 
 

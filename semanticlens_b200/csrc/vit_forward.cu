@@ -231,13 +231,14 @@ extern "C" int slb_text_forward(const SlbTextWeights* w, const int64_t* tokens, 
     if (rc != SLB_OK) return rc;
     rc = slb_assemble_tokens(emb, nullptr, w->pos, B, T, W, 0, x, stream);
     if (rc != SLB_OK) return rc;
-    rc = run_blocks(w->layer, w->layers, x, qkv, pa, pb, B, T, W, w->heads, w->mlp, w->act, w->plane_fmt, w->ln_eps, 1, stream);
+    rc = run_blocks(w->layer, w->layers, x, qkv, pa, pb, B, T, W, w->heads, w->mlp, w->act, w->plane_fmt, w->ln_eps,
+                    w->non_causal ? 0 : 1, stream);
     if (rc != SLB_OK) return rc;
     // ln_final acts per token, so it commutes with picking the end-of-text rows: gather first, normalise B rows
     rc = slb_gather_rows(x, B * T, W, eot_rows, B, head, stream);
     if (rc != SLB_OK) return rc;
     rc = slb_layernorm(head, B, W, W, w->ln_final_g, w->ln_final_b, w->ln_eps, w->plane_fmt, nullptr, pa, stream);
     if (rc != SLB_OK) return rc;
-    return slb_gemm_split(pa, w->proj, w->plane_fmt, B, w->embed_dim, W, kAlpha, nullptr, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3, out,
-                          nullptr, stream);
+    return slb_gemm_split(pa, w->proj, w->plane_fmt, B, w->embed_dim, W, kAlpha, w->proj_b, nullptr, nullptr, nullptr, SLB_EPI_NONE, 3,
+                          out, nullptr, stream);
 }

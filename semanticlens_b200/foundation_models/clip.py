@@ -54,6 +54,7 @@ class OpenClip(AbstractVLM):
         sd = kwargs.pop("state_dict", None)
         given_sd = sd is not None
         bpe_path = kwargs.pop("bpe_path", None)
+        spm_path = kwargs.pop("spm_path", None)
         ckpt = kwargs.pop("checkpoint_path", None)
         seed = kwargs.pop("seed", 1)
         fmt = {"f16": N.PLANE_F16, "bf16": N.PLANE_BF16}[kwargs.pop("plane_format", "f16")]
@@ -81,6 +82,7 @@ class OpenClip(AbstractVLM):
         self._text_sd = {k: v for k, v in sd.items() if not k.startswith("visual.")} if ckpt or given_sd else None
         self._text_seed = seed
         self._bpe_path = bpe_path
+        self._spm_path = spm_path
         self._text: text_mod.TextTower | None = None
         self._tokenizer: text_mod.SimpleTokenizer | None = None
         self._pin: list = [(None, None), (None, None)]  # (pinned staging buffer, event of its last H2D copy)
@@ -183,9 +185,9 @@ class OpenClip(AbstractVLM):
         if self._text is None:
             tcfg = text_mod.TEXT_CONFIGS.get(self.url)
             if tcfg is None:
-                raise NotImplementedError(f"no CLIP text tower is built for '{self.url}' (SigLIP text towers are not built)")
+                raise NotImplementedError(f"no text tower is built for '{self.url}'")
             sd = self._text_sd
-            if not sd or "token_embedding.weight" not in sd:
+            if not sd or not ("token_embedding.weight" in sd or "text.token_embedding.weight" in sd):
                 sd = text_mod.random_text_state_dict(tcfg, self._text_seed)
             self._text = text_mod.TextTower(tcfg, sd, self.device)
         return self._text.to(self.device)
@@ -196,13 +198,18 @@ class OpenClip(AbstractVLM):
             return self._text_tower().forward(text_input)
 
     def tokenize(self, txt, context_length=None):
-        """str or list[str] -> (n, context_length) int64 token ids on ``device`` (reference :165-187). Needs CLIP's BPE
-        merges file: ``OpenClip(..., bpe_path=...)`` or ``SLB_CLIP_BPE``."""
+        """str or list[str] -> (n, context_length) int64 token ids on ``device`` (reference :165-187). Needs the
+        vocabulary file of the model family: CLIP's BPE merges (``bpe_path=`` / ``SLB_CLIP_BPE``) or SigLIP's sentencepiece
+        model (``spm_path=`` / ``SLB_SIGLIP_SPM``)."""
         if self._tokenizer is None:
             tcfg = text_mod.TEXT_CONFIGS.get(self.url)
             if tcfg is None:
                 raise NotImplementedError(f"no tokenizer is built for '{self.url}'")
-            self._tokenizer = text_mod.SimpleTokenizer(self._bpe_path, context_length=tcfg.context)
+            if tcfg.arch == "siglip":
+                self._tokenizer = text_mod.SentencePieceTokenizer(self._spm_path, context_length=tcfg.context,
+                                                                  lower="SigLIP2" not in tcfg.name)
+            else:
+                self._tokenizer = text_mod.SimpleTokenizer(self._bpe_path, context_length=tcfg.context)
         return self._tokenizer(txt, context_length).to(self.device)
 
 

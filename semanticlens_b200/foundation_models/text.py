@@ -1,9 +1,12 @@
-"""Host side of the B200 CLIP text tower and a byte-pair-encoding tokenizer in open_clip's ``SimpleTokenizer`` scheme.
+"""Host side of the B200 CLIP / SigLIP text towers and their tokenizers.
 
-``slb_text_forward`` (csrc/vit_forward.cu) restates open_clip's ``CLIP.encode_text`` — what the reference reaches through
-``OpenClip.encode_text`` (foundation_models/clip.py:120-135) for ``Lens.text_probing`` (lens.py:166-203). The tokenizer
-needs CLIP's BPE merges file (``bpe_simple_vocab_16e6.txt.gz``), which ships with open_clip and cannot be fetched here:
-pass ``bpe_path=`` (or set ``SLB_CLIP_BPE``); without it ``tokenize`` raises and pre-tokenised ids can be fed directly.
+``slb_text_forward`` (csrc/vit_forward.cu) restates open_clip's ``CLIP.encode_text`` and, for the SigLIP models, the
+``TextTransformer`` of ``CustomTextCLIP`` (no causal mask, last-position pooling, biased projection) — what the reference
+reaches through ``OpenClip.encode_text`` / ``SigLipV2.encode_text`` (foundation_models/clip.py:120-135, 190-215) for
+``Lens.text_probing`` (lens.py:166-203). The CLIP tokenizer (open_clip's ``SimpleTokenizer`` scheme) needs CLIP's BPE
+merges file (``bpe_simple_vocab_16e6.txt.gz``), the SigLIP tokenizer a sentencepiece model; both ship with the upstream
+packages / hubs and cannot be fetched here: pass ``bpe_path=`` / ``spm_path=`` (or set ``SLB_CLIP_BPE`` /
+``SLB_SIGLIP_SPM``); without them ``tokenize`` raises and pre-tokenised ids can be fed to ``encode_text`` directly.
 """
 
 from __future__ import annotations
@@ -33,6 +36,7 @@ class TextConfig:
     embed_dim: int
     act: str = "gelu"
     eps: float = 1e-5
+    arch: str = "clip"  # "clip": causal, end-of-text pooling, matrix projection; "siglip": bidirectional, last position, Linear
 
     @property
     def mlp(self) -> int:
@@ -54,8 +58,23 @@ TEXT_CONFIGS = {
 }
 
 
+def _siglip_text(name, vocab, width, layers, heads):
+    return TextConfig(name, 64, vocab, width, layers, heads, width, act="gelu_tanh", eps=1e-6, arch="siglip")
+
+
+# text_cfg of open_clip's SigLIP model configs: context 64, sentencepiece vocabularies (32 000 c4-en for SigLIP, 256 000
+# Gemma for SigLIP 2), no_causal_mask, pool_type "last", proj_bias, LayerNorm eps 1e-6
+TEXT_CONFIGS.update({
+    "ViT-B-16-SigLIP": _siglip_text("ViT-B-16-SigLIP", 32000, 768, 12, 12),
+    "ViT-L-16-SigLIP-256": _siglip_text("ViT-L-16-SigLIP-256", 32000, 1024, 24, 16),
+    "ViT-B-16-SigLIP2": _siglip_text("ViT-B-16-SigLIP2", 256000, 768, 12, 12),
+    "hf-hub:timm/ViT-B-16-SigLIP2": _siglip_text("ViT-B-16-SigLIP2", 256000, 768, 12, 12),
+})
+
+
 def text_state_dict_keys(cfg: TextConfig) -> list[str]:
-    keys = ["token_embedding.weight", "positional_embedding", "ln_final.weight", "ln_final.bias", "text_projection"]
+    keys = ["token_embedding.weight", "positional_embedding", "ln_final.weight", "ln_final.bias"]
+    keys += ["text_projection.weight", "text_projection.bias"] if cfg.arch == "siglip" else ["text_projection"]
     for i in range(cfg.layers):
         p = f"transformer.resblocks.{i}."
         keys += [p + s for s in ("ln_1.weight", "ln_1.bias", "attn.in_proj_weight", "attn.in_proj_bias",
@@ -80,6 +99,9 @@ def random_text_state_dict(cfg: TextConfig, seed: int = 1) -> dict[str, torch.Te
         "ln_final.bias": torch.zeros(W),
         "text_projection": rn(W, cfg.embed_dim) * W**-0.5,
     }
+    if cfg.arch == "siglip":
+        sd["text_projection.weight"] = sd.pop("text_projection").T.contiguous()
+        sd["text_projection.bias"] = torch.zeros(cfg.embed_dim)
     proj_std = W**-0.5 * (2 * L) ** -0.5
     for i in range(L):
         p = f"transformer.resblocks.{i}."
@@ -102,10 +124,20 @@ class TextTower:
     def __init__(self, cfg: TextConfig, state_dict: dict[str, torch.Tensor], device):
         self.cfg = cfg
         keys = text_state_dict_keys(cfg)
+        # open_clip's CustomTextCLIP (the SigLIP models) keeps its text tower under "text."
+        if "text.token_embedding.weight" in state_dict:
+            state_dict = {k[5:]: v for k, v in state_dict.items() if k.startswith("text.")}
         missing = [k for k in keys if k not in state_dict]
         if missing:
             raise KeyError(f"state dict is missing {len(missing)} text-tower tensors, e.g. {missing[:3]}")
         self.state_dict = {k: state_dict[k].detach().to(torch.float32).cpu() for k in keys}
+        want = {"token_embedding.weight": (cfg.vocab, cfg.width), "positional_embedding": (cfg.context, cfg.width),
+                "transformer.resblocks.0.attn.in_proj_weight": (3 * cfg.width, cfg.width)}
+        want.update({"text_projection.weight": (cfg.embed_dim, cfg.width)} if cfg.arch == "siglip"
+                    else {"text_projection": (cfg.width, cfg.embed_dim)})
+        for k, shape in want.items():
+            if k in self.state_dict and tuple(self.state_dict[k].shape) != shape:
+                raise ValueError(f"text tower '{cfg.name}': {k} has shape {tuple(self.state_dict[k].shape)}, expected {shape}")
         self._device = torch.device("cpu")
         self._struct = None
         self._keep: list = []
@@ -157,7 +189,11 @@ class TextTower:
         w.act, w.plane_fmt, w.ln_eps = _ACT[cfg.act], N.PLANE_F16, cfg.eps
         w.tok_emb, w.pos = vec("token_embedding.weight"), vec("positional_embedding")
         w.ln_final_g, w.ln_final_b = vec("ln_final.weight"), vec("ln_final.bias")
-        w.proj = planes(sd["text_projection"].T.contiguous())
+        if cfg.arch == "siglip":
+            w.proj, w.proj_b = planes(sd["text_projection.weight"].contiguous()), vec("text_projection.bias")
+            w.non_causal = 1
+        else:
+            w.proj, w.proj_b, w.non_causal = planes(sd["text_projection"].T.contiguous()), None, 0
         w.layer = layers
         keep.append(layers)
         self._struct = w
@@ -178,8 +214,10 @@ class TextTower:
         out = torch.empty((B, cfg.embed_dim), dtype=torch.float32, device=self._device)
         if B == 0:
             return out
-        # end-of-text position = the largest token id of each sequence (open_clip: text.argmax(dim=-1)); index plumbing
-        eot = tokens.argmax(dim=-1) + torch.arange(B, device=self._device) * cfg.context
+        # pooled position: CLIP = the end-of-text token = the largest id of each sequence (open_clip: text.argmax(dim=-1));
+        # SigLIP = the last position (pool_type "last"; the tokenizer pads to the context length). Index plumbing.
+        pos = tokens.argmax(dim=-1) if cfg.arch == "clip" else torch.full((B,), cfg.context - 1, device=self._device)
+        eot = pos + torch.arange(B, device=self._device) * cfg.context
         need = lib.slb_text_workspace_bytes(ctypes.byref(self._struct), B)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self._device)
@@ -210,6 +248,9 @@ def _pairs(word):
     return set(zip(word[:-1], word[1:]))
 
 
+CLIP_MERGES = 49152 - 256 - 2  # merges CLIP's vocabulary uses (the file's header line excluded; later lines are unused)
+
+
 class SimpleTokenizer:
     """Byte-pair encoding with CLIP's merges file. ``merges``: the list of merge pairs (for tests) or None to read
     ``bpe_path`` (the gzip'ed ``bpe_simple_vocab_16e6.txt.gz`` of open_clip / OpenAI CLIP)."""
@@ -224,8 +265,7 @@ class SimpleTokenizer:
                     "CLIP's BPE merges file (bpe_simple_vocab_16e6.txt.gz, shipped with open_clip) is needed to tokenize "
                     "text; pass OpenClip(..., bpe_path=...) or set SLB_CLIP_BPE, or feed token ids to encode_text directly")
             lines = gzip.open(bpe_path).read().decode("utf-8").split("\n")
-            lines = lines[1 : 49152 - 256 - 2 + 1]
-            merges = [tuple(m.split()) for m in lines]
+            merges = [tuple(m.split()) for m in lines[1 : CLIP_MERGES + 1] if m.strip()]
         self.byte_encoder = _bytes_to_unicode()
         vocab = list(self.byte_encoder.values())
         vocab = vocab + [v + "</w>" for v in vocab]
@@ -299,4 +339,45 @@ class SimpleTokenizer:
                 ids = ids[:T]
                 ids[-1] = self.eot
             out[i, : len(ids)] = torch.tensor(ids)
+        return out
+
+
+class SentencePieceTokenizer:
+    """SigLIP's text tokenizer as open_clip's ``HFTokenizer`` drives it for the SigLIP configs (``clean="canonicalize"``,
+    ``padding="max_length"``, ``truncation=True``): punctuation removed, lower-cased, whitespace collapsed, sentencepiece
+    pieces + ``</s>``, padded with the pad id (1 = ``</s>`` in SigLIP's c4-en vocabulary) up to ``context_length``.
+    ``spm_path``: the sentencepiece ``.model`` file of the checkpoint (``SLB_SIGLIP_SPM``); not available offline, so only
+    the mechanics are tested (tests/test_tokenizer.py trains a toy model). ``lower=False`` for SigLIP 2's Gemma vocabulary
+    keeps the case (its config lower-cases through the tokenizer kwargs instead)."""
+
+    def __init__(self, spm_path: str | None = None, context_length: int = 64, pad_id: int = 1, lower: bool = True):
+        spm_path = spm_path or os.environ.get("SLB_SIGLIP_SPM")
+        if not spm_path or not os.path.exists(spm_path):
+            raise FileNotFoundError(
+                "SigLIP's sentencepiece model (the checkpoint's spiece.model / tokenizer.model) is needed to tokenize text; "
+                "pass OpenClip(..., spm_path=...) or set SLB_SIGLIP_SPM, or feed token ids to encode_text directly")
+        import sentencepiece as spm
+
+        self.sp = spm.SentencePieceProcessor(model_file=spm_path)
+        self.context_length, self.pad_id, self.lower = context_length, pad_id, lower
+        eos = self.sp.eos_id()
+        self.eos = eos if eos >= 0 else pad_id
+        self.vocab_size = self.sp.get_piece_size()
+
+    @staticmethod
+    def canonicalize(text: str, lower: bool = True) -> str:
+        import string
+
+        text = text.translate(str.maketrans("", "", string.punctuation))
+        text = " ".join(text.split())
+        return (text.lower() if lower else text).strip()
+
+    def __call__(self, texts, context_length: int | None = None) -> torch.Tensor:
+        if isinstance(texts, str):
+            texts = [texts]
+        T = context_length or self.context_length
+        out = torch.full((len(texts), T), self.pad_id, dtype=torch.long)
+        for i, text in enumerate(texts):
+            ids = (list(self.sp.encode(self.canonicalize(text, self.lower))) + [self.eos])[:T]
+            out[i, : len(ids)] = torch.tensor(ids, dtype=torch.long)
         return out

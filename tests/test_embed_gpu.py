@@ -299,3 +299,98 @@ def test_text_probing_end_to_end_with_token_ids():
     assert (sim - ref).abs().max() < 1e-5
     with pytest.raises(FileNotFoundError, match="BPE"):
         fm.tokenize(["a photo of a dog"])
+
+
+@pytest.mark.parametrize("name,B", [("siglip-text-tiny-test", 5), ("ViT-B-16-SigLIP", 3)])
+def test_siglip_text_tower_vs_oracle(name, B):
+    """SigLIP text tower (no causal mask, tanh GELU, eps 1e-6, LAST-position pooling, biased projection; reference
+    clip.py:190-215 -> open_clip TextTransformer) against the torch oracle pinned to HF SiglipTextModel. Weights arrive in
+    open_clip's CustomTextCLIP naming ("text." prefix)."""
+    from semanticlens_b200.foundation_models import text as T
+
+    ocfg = vp.TEXT_CONFIGS[name]
+    cfg = T.TextConfig(ocfg.name, ocfg.context, ocfg.vocab, ocfg.width, ocfg.layers, ocfg.heads, ocfg.embed_dim, ocfg.act, ocfg.eps,
+                       arch="siglip")
+    sd = vp.init_text_weights(ocfg, seed=7)
+    tower = T.TextTower(cfg, {"text." + k: v for k, v in sd.items()}, "cuda")
+    g = torch.Generator().manual_seed(11)
+    tokens = torch.ones(B, cfg.context, dtype=torch.int64)  # padded with </s> = 1 like SigLIP's tokenizer
+    for b in range(B):
+        n = int(torch.randint(1, cfg.context + 1, (1,), generator=g))
+        tokens[b, :n] = torch.randint(2, cfg.vocab, (n,), generator=g)
+    want = vp.encode_text(sd, ocfg, tokens, dtype=torch.float64)
+    got = tower.forward(tokens)
+    assert got.shape == (B, cfg.embed_dim) and got.is_cuda
+    assert rel_max(got, want) < 2e-5
+    # a CLIP-style (causal, argmax-pooled) evaluation of the same weights must differ: the flags reach the kernels
+    import dataclasses
+    clip_like = vp.encode_text({**sd, "text_projection": sd["text_projection.weight"].T}, dataclasses.replace(ocfg, arch="clip"),
+                               tokens, dtype=torch.float64)
+    assert rel_max(got, clip_like + sd["text_projection.bias"].double()) > 1e-3
+
+
+def _bpe_file(tmp_path):
+    from test_tokenizer import WORDS, learn_merges, write_bpe_file
+
+    return str(write_bpe_file(tmp_path / "bpe_simple_vocab_16e6.txt.gz", learn_merges(WORDS, 60), trailing=0))
+
+
+def test_text_probing_from_strings_with_templates(tmp_path):
+    """Lens.text_probing driven from STRINGS on the GPU (reference lens.py:59-121, 166-203): tokenizer (merges file in the
+    real format) -> text tower -> template baseline subtraction -> the reference's template-major / (q t) regrouping
+    -> similarity_score. Expected values: the float64 oracle tower on the same token ids, regrouped the reference's way."""
+    import semanticlens_b200 as sl
+    from semanticlens_b200.foundation_models import OpenClip, text as T
+
+    fm = OpenClip("ViT-B-32", device="cuda", load_weights=False, seed=3, bpe_path=_bpe_file(tmp_path))
+    lens = sl.Lens(fm, device="cuda")
+    queries = ["dog", "red car", "blue house"]
+    templates = ["a photo of a {}", "an image of the {}"]
+    db = {"layer4": torch.randn(37, 512, generator=torch.Generator().manual_seed(0)),
+          "layer3": torch.randn(19, 512, generator=torch.Generator().manual_seed(1))}
+    ocfg = vp.TEXT_CONFIGS["ViT-B-32"]
+    sd = T.random_text_state_dict(T.TEXT_CONFIGS["ViT-B-32"], 3)
+
+    def oracle_embed(prompts):
+        return vp.encode_text(sd, ocfg, fm.tokenize(prompts).cpu(), dtype=torch.float64)
+
+    def cos(a, b):
+        return torch.nn.functional.normalize(a, dim=-1) @ torch.nn.functional.normalize(b.double(), dim=-1).T
+
+    # no templates: one embedding per query
+    got = lens.text_probing(queries, db)
+    want = oracle_embed(queries)
+    for layer in db:
+        assert got[layer].shape == (3, db[layer].shape[0])
+        assert (got[layer].double().cpu() - cos(want, db[layer])).abs().max() < 2e-5
+    # templates: prompts are built template-major, regrouped as (query, template) blocks (the reference's quirk), the
+    # embedding of each template formatted with "" is subtracted, mean over the template axis
+    prompts = [t.format(q) for t in templates for q in queries]
+    rows = oracle_embed(prompts).view(len(queries), len(templates), -1)
+    base = oracle_embed([t.format("") for t in templates]).view(1, len(templates), -1)
+    want_t = (rows - base).mean(1)
+    for bs in (None, 4):
+        got_t = lens.text_probing(queries, db["layer4"], templates=templates, batch_size=bs)
+        assert got_t.shape == (3, 37)
+        assert (got_t.double().cpu() - cos(want_t, db["layer4"])).abs().max() < 5e-5
+    # the quirk is observable: the query-major reading gives different numbers
+    sane = (oracle_embed([t.format(q) for q in queries for t in templates]).view(len(queries), len(templates), -1) - base).mean(1)
+    assert (cos(sane, db["layer4"]) - cos(want_t, db["layer4"])).abs().max() > 1e-3
+    # a single string query
+    one = lens.text_probing("dog", db["layer4"], templates=templates)
+    assert one.shape == (1, 37)
+
+
+def test_siglip_wrapper_encodes_text():
+    """SigLipV2.encode_text no longer raises: SigLIP 2 text tower (vocabulary 256 000) from token ids; tokenize needs the
+    sentencepiece model and says so."""
+    from semanticlens_b200.foundation_models import SigLipV2
+
+    fm = SigLipV2(device="cuda", load_weights=False, seed=2)
+    tokens = torch.ones(3, 64, dtype=torch.int64)
+    tokens[:, :5] = torch.arange(15).view(3, 5) + 1000
+    emb = fm.encode_text(tokens)
+    assert emb.shape == (3, 768) and emb.is_cuda and torch.isfinite(emb).all()
+    assert (emb[0] - emb[1]).abs().max() > 0
+    with pytest.raises(FileNotFoundError, match="sentencepiece"):
+        fm.tokenize(["a photo of a dog"])

@@ -50,7 +50,7 @@ def test_text_configs_cover_every_clip_image_tower():
     from semanticlens_b200.foundation_models import rn, text, vit
 
     for url, cfg in list(vit.CONFIGS.items()) + list(rn.CONFIGS.items()):
-        if getattr(cfg, "arch", "") == "siglip":
-            assert url not in text.TEXT_CONFIGS  # SigLIP text towers are not built
-            continue
-        assert text.TEXT_CONFIGS[url].embed_dim == cfg.embed_dim, url
+        tcfg = text.TEXT_CONFIGS[url]
+        assert tcfg.embed_dim == cfg.embed_dim, url
+        assert tcfg.arch == ("siglip" if getattr(cfg, "arch", "") == "siglip" else "clip"), url
+        assert tcfg.width == 64 * tcfg.heads, url  # the tensor-core attention's head_dim

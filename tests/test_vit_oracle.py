@@ -162,6 +162,52 @@ def test_oracle_text_tower_matches_hf_clip_text():
     assert (got - want).abs().max() <= 2e-5 * want.abs().max()
 
 
+def test_oracle_siglip_text_tower_matches_hf_siglip_text():
+    """SigLIP text tower (bidirectional blocks, tanh GELU, eps 1e-6, LAST-position pooling, biased projection) against
+    HF transformers' SiglipTextModel — the executable stand-in for open_clip's TextTransformer with the SigLIP text_cfg."""
+    transformers = pytest.importorskip("transformers")
+    cfg = vp.TEXT_CONFIGS["siglip-text-tiny-test"]
+    sd = vp.init_text_weights(cfg, seed=6)
+    hc = transformers.SiglipTextConfig(
+        vocab_size=cfg.vocab, hidden_size=cfg.width, intermediate_size=cfg.mlp, num_hidden_layers=cfg.layers,
+        num_attention_heads=cfg.heads, max_position_embeddings=cfg.context, projection_size=cfg.embed_dim,
+        hidden_act="gelu_pytorch_tanh", layer_norm_eps=cfg.eps,
+    )
+    m = transformers.SiglipTextModel(hc).eval()
+    W = cfg.width
+    new = {
+        "text_model.embeddings.token_embedding.weight": sd["token_embedding.weight"],
+        "text_model.embeddings.position_embedding.weight": sd["positional_embedding"],
+        "text_model.final_layer_norm.weight": sd["ln_final.weight"],
+        "text_model.final_layer_norm.bias": sd["ln_final.bias"],
+        "text_model.head.weight": sd["text_projection.weight"],
+        "text_model.head.bias": sd["text_projection.bias"],
+    }
+    for i in range(cfg.layers):
+        p, q = f"transformer.resblocks.{i}.", f"text_model.encoder.layers.{i}."
+        wi, bi = sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"]
+        for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
+            new[q + f"self_attn.{n}.weight"] = wi[j * W : (j + 1) * W]
+            new[q + f"self_attn.{n}.bias"] = bi[j * W : (j + 1) * W]
+        new[q + "self_attn.out_proj.weight"], new[q + "self_attn.out_proj.bias"] = sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"]
+        new[q + "layer_norm1.weight"], new[q + "layer_norm1.bias"] = sd[p + "ln_1.weight"], sd[p + "ln_1.bias"]
+        new[q + "layer_norm2.weight"], new[q + "layer_norm2.bias"] = sd[p + "ln_2.weight"], sd[p + "ln_2.bias"]
+        new[q + "mlp.fc1.weight"], new[q + "mlp.fc1.bias"] = sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"]
+        new[q + "mlp.fc2.weight"], new[q + "mlp.fc2.bias"] = sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"]
+    missing, unexpected = m.load_state_dict(new, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    # SigLIP's tokenizer pads with id 1 (= </s>) up to the context length: every position is attended, the last is pooled
+    g = torch.Generator().manual_seed(3)
+    tokens = torch.ones(4, cfg.context, dtype=torch.int64)
+    for b, n in enumerate((3, 7, 15, 1)):
+        tokens[b, :n] = torch.randint(2, cfg.vocab, (n,), generator=g)
+    with torch.no_grad():
+        want = m(input_ids=tokens).pooler_output
+    got = vp.encode_text(sd, cfg, tokens)
+    assert got.shape == (4, cfg.embed_dim)
+    assert (got - want).abs().max() <= 2e-5 * want.abs().max()
+
+
 def test_preprocess_u8_is_totensor_normalize():
     cfg = vp.CONFIGS["ViT-tiny-test"]
     u8 = torch.randint(0, 256, (2, 3, 32, 32), dtype=torch.uint8)
