@@ -24,6 +24,10 @@ ptr = N.load().slb_attention_trace()
 w = (ctypes.c_uint32 * 256).from_address(ptr)
 names = ["tma issue (item)", "mma: K landed (it)", "mma: S issue (it)", "mma: PV issue (blk)", "sm: S visible (it)", "sm: S in regs (it)",
          "sm: exps done (blk)", "sm: P free (blk)", "sm: P published (blk)", "O complete / CTA done"]
+if os.environ.get("SLB_ATTN_TS", "1") != "0":  # the TS-mode kernel's events (attention_ts.cu)
+    names = ["tma issue (item)", "mma: K landed (it)", "mma: S issue (it)", "mma: PV issue (blk)", "sm: S visible (it)",
+             "sm: maxima done (it)", "sm: exps+stores (blk)", "sm: P published (blk)", "mma: V landed (blk)", "O complete / CTA done"]
+    print("SM id of the traced CTA:", w[63])
 nblk = (T + 63) // 64
 for t, nm in enumerate(names):
     vals = [w[64 + 16 * t + i] for i in range(16)]

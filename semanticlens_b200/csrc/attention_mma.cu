@@ -601,6 +601,8 @@ int slb_attention_mma_dh64(const float* q, int64_t q_bs, int64_t q_rs, const flo
     return launch_attn<8>(p, B, st);
 }
 
+int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles,
+                           int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st);  // attention_ts.cu
 int slb_attention_tc_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles,
                            int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st);
 
@@ -631,7 +633,10 @@ extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64
         int n_tiles = (int)(T / 128);
         const int64_t rem = T - 128 * (int64_t)n_tiles;
         if (rem >= 64) n_tiles += 1;
-        int rc = slb_attention_tc_tiles(qkv_planes, B, T, H, scale, n_tiles, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
+        // P as a tensor-memory operand (attention_ts.cu) unless SLB_ATTN_TS=0 asks for the shared-memory-P kernel
+        static const bool no_ts = [] { const char* e = getenv("SLB_ATTN_TS"); return e && e[0] == '0'; }();
+        int rc = no_ts ? slb_attention_tc_tiles(qkv_planes, B, T, H, scale, n_tiles, plane_fmt, out_f32, p.out_hi, p.out_lo, st)
+                       : slb_attention_ts_tiles(qkv_planes, B, T, H, scale, n_tiles, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
         if (rc != SLB_OK) return rc;
         if ((int64_t)n_tiles * 128 >= T) return SLB_OK;
         p.q_row0 = n_tiles * 128;
@@ -1018,13 +1023,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     }
 }
 
-unsigned int* g_attn_trace_host = nullptr;  // SLB_ATTN_TRACE=1 only
-unsigned int* g_attn_trace_dev = nullptr;
+}  // namespace
 
+static unsigned int* g_attn_trace_host = nullptr;  // SLB_ATTN_TRACE=1 only
+static unsigned int* g_attn_trace_dev = nullptr;
+unsigned int* slb_attention_trace_buffer();
+namespace {
 }  // namespace
 
 // the trace words of the last tcgen05 attention launch (null unless SLB_ATTN_TRACE=1): [64 + type * 16 + index] SM clocks
 extern "C" const unsigned int* slb_attention_trace() { return g_attn_trace_host; }
+
+// host-mapped trace words (allocated on first use, zeroed on every call); returns the device alias or null
+unsigned int* slb_attention_trace_buffer() {
+    if (!g_attn_trace_host) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&g_attn_trace_host), 256 * 4, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+        if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_attn_trace_dev), g_attn_trace_host, 0) != cudaSuccess) return nullptr;
+    }
+    for (int i = 0; i < 256; ++i) g_attn_trace_host[i] = 0;
+    return g_attn_trace_dev;
+}
 
 // Full 128-row query tiles of every (image, head) on the tcgen05 path; the caller handles the remaining rows.
 int slb_attention_tc_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles,
@@ -1041,14 +1059,7 @@ int slb_attention_tc_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int
     p.out_f32 = out_f32; p.out_hi = out_hi; p.out_lo = out_lo; p.fmt = plane_fmt;
     p.dbg = nullptr;
     static const bool trace = [] { const char* e = getenv("SLB_ATTN_TRACE"); return e && e[0] == '1'; }();
-    if (trace) {
-        if (!g_attn_trace_host) {
-            SLB_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&g_attn_trace_host), 256 * 4, cudaHostAllocMapped));
-            SLB_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_attn_trace_dev), g_attn_trace_host, 0));
-        }
-        for (int i = 0; i < 256; ++i) g_attn_trace_host[i] = 0;
-        p.dbg = g_attn_trace_dev;
-    }
+    if (trace) p.dbg = slb_attention_trace_buffer();
     SLB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
     dim3 grid((unsigned)(B * H), (unsigned)n_tiles);
     attention_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(tmq, tmkv, p);

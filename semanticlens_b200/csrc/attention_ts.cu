@@ -1,0 +1,487 @@
+// K4 attention, tcgen05 with P as a TENSOR-MEMORY operand (TS-mode MMA) — full 128-row query tiles of the long-sequence
+// towers (T >= 128: ViT-B/16, ViT-L/14, SigLIP; reference foundation_models/clip.py:118 -> open_clip VisionTransformer ->
+// nn.MultiheadAttention). Successor of attention_tc_kernel (attention_mma.cu), which wrote P into shared memory.
+//
+// One CTA = one (image, head, 128-query tile); 320 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 softmax
+// (thread = query row = TMEM lane; two warps per lane quarter, each on 64 of a block's 128 keys). Q and the K / V blocks
+// (128 tokens x 64 dims x {hi, lo} planes = 32 KB) arrive through one 3-D tensor map over the in_proj GEMM's split
+// planes; K and V travel through a ring of two slots. 97 KB of shared memory and 256 TMEM columns per CTA: two CTAs share
+// an SM and fill each other's hand-off bubbles.
+//
+// What changed against the shared-memory-P kernel, and why (its ncu capture: tensor pipe 16 %, the SM's shared-memory
+// port was the limiter — an SS-mode 128x64x16 MMA reads 6 KB of operands for 32 clocks of math):
+//   * key blocks of 128: S = Q K^T runs as N = 128 MMAs (8 KB of operands per 64 clocks = the port's rate);
+//   * P never touches shared memory: the softmax threads convert exp2(S - max) to split fp16 planes in registers and
+//     write them with tcgen05.st INTO THE COLUMNS S OCCUPIED (S fp32 128 columns -> P hi | lo, 16 + 16 columns per 32
+//     keys); O += P V is a TS-mode MMA (A = P from TMEM, B = V from its row-major tile as an MN-major operand: 2 KB of
+//     shared-memory reads per MMA instead of 6) — no P store, no proxy fence, no swizzle arithmetic;
+//   * one S accumulator instead of main + corr: the two cross products (hi.lo, lo.hi) are issued FIRST, so only the four
+//     hi.hi MMAs accumulate onto a large value (the tensor core truncates at every accumulate; same error as before),
+//     and the softmax threads read 512 bytes per row and block instead of 1024;
+//   * the hi plane of P is the fp32 value with its low 13 mantissa bits cleared (exact in fp16), lo the exact
+//     remainder rounded to fp16: one AND + one subtract per element instead of two conversions back to fp32.
+// Two sweeps over the keys as before (no rescaling of O): sweep 1 takes row maxima from hi.hi logits alone (the maximum
+// is only the softmax's stabiliser), double-buffered over the two halves of TMEM (the O columns are idle until sweep 2);
+// sweep 2 recomputes S with all three products. S(j+1) is issued right behind P V(j): MMAs of one thread execute in
+// issue order, so S(j+1) may overwrite the columns P(j) was read from.
+// Accumulators (TMEM columns): [0,128) S / P, [128,192) O main (P hi . V hi), [192,256) O corr (cross terms).
+#include "tc_common.cuh"
+
+#include <stdlib.h>
+
+#include <algorithm>
+
+namespace {
+
+constexpr int kSoftmaxWarps = 8;
+constexpr int kThreads = (2 + kSoftmaxWarps) * 32;
+constexpr int kTile = 128;                       // queries per CTA
+constexpr int kKeys = 128;                       // keys per block
+constexpr int kPlane = kTile * 64 * 2;           // one 128 x 64 fp16 plane tile: 16 KB
+constexpr int kOffQ = 0;                         // Q hi | lo           32 KB
+constexpr int kOffKV = 2 * kPlane;               // two slots of hi | lo  64 KB
+constexpr int kSlots = 2;
+constexpr int kOffXch = kOffKV + kSlots * 2 * kPlane;  // [2][128] floats: row max / row sum exchange between column halves
+constexpr int kOffBars = kOffXch + 2 * kTile * 4;
+constexpr size_t kSmem = (size_t)kOffBars + 128;
+constexpr float kLog2PScale = 10.0f;             // P planes carry 2^10 (hi + lo = 1024 p)
+
+struct AttnTsParams {
+    int T, H, W;
+    float scale_log2;  // scale * log2(e)
+    float* out_f32; uint16_t* out_hi; uint16_t* out_lo; int fmt;
+    int n_tiles, n_items;  // query tiles per (image, head); work items = B * H * n_tiles
+    unsigned int* dbg;     // SLB_ATTN_TRACE=1: host-mapped words; CTA SLB_ATTN_TRACE_CTA records the hand-off timeline of
+    int dbg_cta, dbg_item; // its SLB_ATTN_TRACE_ITEM-th work item
+};
+
+// [64 + type * 16 + index] = SM clocks since the CTA's start (scripts/trace_attention.py)
+#define TS_TRACE(type, idx)                                                                                 \
+    do {                                                                                                    \
+        if (trace_on && (idx) < 16) p.dbg[64 + (type) * 16 + (idx)] = (unsigned int)(clock64() - t_start);  \
+    } while (0)
+
+__device__ __forceinline__ void ts_wait(uint64_t* bar, uint32_t parity) {
+    if (slb_mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!slb_mbar_try_wait(bar, parity))
+        if (clock64() - t0 > 4000000000ll) __trap();  // a lost hand-off must fail the launch, not hang the GPU
+}
+
+// MN-major operand tile (rows = K index, 128 B per row = 64 contiguous MN elements), 128-byte swizzle:
+// SBO = 1024 B between 8-row groups along K; LBO (between 64-element MN atoms) unused for N = 64.
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 8 columns of packed 16-bit pairs (K = 16)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
+// 32 lanes x 16 consecutive columns: thread i of the warp writes row (lane base + i), columns [col, col + 16)
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+    uint64_t* q_full = bars;        // TMA -> MMA
+    uint64_t* q_empty = bars + 1;   // MMA -> TMA: the work item's last S MMAs have read Q
+    uint64_t* kv_full = bars + 2;   // [2] TMA -> MMA
+    uint64_t* kv_empty = bars + 4;  // [2] MMA -> TMA
+    uint64_t* s_full = bars + 6;    // [2] MMA -> softmax, one per S buffer
+    uint64_t* s_free = bars + 8;    // [2] softmax (8 warps) -> MMA: S is in registers
+    uint64_t* p_full = bars + 10;   // softmax (8 warps) -> MMA: P is in tensor memory
+    uint64_t* o_full = bars + 11;   // MMA -> softmax
+    uint64_t* o_free = bars + 12;   // softmax (8 warps) -> MMA: O is in registers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    float* xch = reinterpret_cast<float*>(smem + kOffXch);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nblk = (p.T + kKeys - 1) / kKeys;
+    const int n_iter = 2 * nblk;
+    // S buffer of iteration `it` of a work item (sweep 1 alternates the two buffers, sweep 2 uses buffer 0) and how many
+    // earlier iterations OF THE ITEM used that buffer; a work item uses buffer 0 uses0 times and buffer 1 uses1 times
+    auto s_buf = [&](int it) { return it < nblk ? (it & 1) : 0; };
+    auto s_idx = [&](int it) { return it < nblk ? (it >> 1) : ((nblk + 1) >> 1) + (it - nblk); };
+    const int uses0 = ((nblk + 1) >> 1) + nblk, uses1 = nblk >> 1;
+    auto keys_of = [&](int blk) { return min(kKeys, (p.T - blk * kKeys + 15) & ~15); };  // padded to the MMA N step
+
+    if (warp == 0 && lane == 0) {
+        slb_prefetch_tmap(&tm);
+        if ((slb_smem_u32(smem) & 1023u) != 0) __trap();
+        slb_mbar_init(q_full, 1);
+        slb_mbar_init(q_empty, 1);
+        for (int i = 0; i < kSlots; ++i) {
+            slb_mbar_init(&kv_full[i], 1);
+            slb_mbar_init(&kv_empty[i], 1);
+            slb_mbar_init(&s_full[i], 1);
+            slb_mbar_init(&s_free[i], kSoftmaxWarps);
+        }
+        slb_mbar_init(p_full, kSoftmaxWarps);
+        slb_mbar_init(o_full, 1);
+        slb_mbar_init(o_free, kSoftmaxWarps);
+        slb_fence_mbar_init();
+    }
+    if (warp == 1) slb_tmem_alloc<256>(tmem_slot);
+    slb_tc_fence_before();
+    __syncthreads();
+    slb_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_o = tmem_base + 128;
+    const bool trace_cta = p.dbg != nullptr && (int)blockIdx.x == p.dbg_cta;
+    const long long t_start = clock64();
+    if (trace_cta && warp == 2 && lane == 0) { unsigned int smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); p.dbg[63] = smid; }
+
+    // Persistent: CTA c works on items c, c + gridDim.x, ... (item = (image, head, query tile)); every barrier keeps
+    // running phases across items, so the producer warp prefetches the next item's Q and first K blocks while the softmax
+    // warps are still in the current item's last block and epilogue.
+    if (warp == 0) {
+        if (lane == 0) {
+            int t = 0;  // K / V ring item counter (running)
+            int n = 0;  // work items done by this CTA
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
+                const bool trace_on = trace_cta && n == p.dbg_item;
+                const int bh = item / p.n_tiles, tile = item % p.n_tiles;
+                const int b = bh / p.H, h = bh % p.H;
+                const int row_base = b * p.T;
+                ts_wait(q_empty, (uint32_t)(n & 1) ^ 1u);
+                slb_mbar_arrive_expect_tx(q_full, 2u * kPlane);
+                slb_tma_load_3d(smem + kOffQ, &tm, h * 64, row_base + tile * kTile, 0, q_full);
+                // ring items in consumption order: K_0 .. K_{n-1} (sweep 1), then K_0, V_0, K_1, V_1, ...; item t reuses
+                // the slot of item t - 2. K_{j+1} follows K_j (released by the S MMAs: early), V_{j+1} follows V_j.
+                int t_item = 0;
+                auto load_item = [&](int col, int row) {
+                    const int slot = t % kSlots;
+                    ts_wait(&kv_empty[slot], (uint32_t)((t / kSlots) & 1) ^ 1u);
+                    slb_mbar_arrive_expect_tx(&kv_full[slot], 2u * kPlane);
+                    slb_tma_load_3d(smem + kOffKV + slot * 2 * kPlane, &tm, col, row, 0, &kv_full[slot]);
+                    TS_TRACE(0, t_item);
+                    ++t;
+                    ++t_item;
+                };
+                for (int it = 0; it < n_iter; ++it) {
+                    const int blk = it % nblk;
+                    load_item(p.W + h * 64, row_base + blk * kKeys);
+                    if (it >= nblk) load_item(2 * p.W + h * 64, row_base + blk * kKeys);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t qa = slb_smem_u32(smem + kOffQ);
+            const uint64_t dq_hi = slb_umma_desc_sw128(qa), dq_lo = slb_umma_desc_sw128(qa + kPlane);
+            const uint64_t dk0 = slb_umma_desc_sw128(slb_smem_u32(smem + kOffKV));
+            const uint64_t dv0 = desc_mn_sw128(slb_smem_u32(smem + kOffKV));
+            const uint32_t idesc_o = slb_umma_idesc_f16(0, kTile, 64) | (1u << 16);  // B (= V) is MN-major
+            int t0 = 0;                 // ring items consumed by earlier work items
+            int base[2] = {0, 0};       // S-buffer uses of earlier work items
+            int pblk = 0;               // sweep-2 blocks of earlier work items
+            int n = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
+                const bool trace_on = trace_cta && n == p.dbg_item;
+                auto item_k = [&](int it) { return t0 + (it < nblk ? it : nblk + 2 * (it - nblk)); };
+                auto issue_s = [&](int it) {
+                    const int blk = it % nblk;
+                    const bool sweep2 = it >= nblk;
+                    const int nk = keys_of(blk);
+                    const int t = item_k(it), slot = t % kSlots;
+                    const int buf = s_buf(it), idx = base[buf] + s_idx(it);
+                    ts_wait(&kv_full[slot], (uint32_t)((t / kSlots) & 1));
+                    TS_TRACE(1, it);  // K landed
+                    if (idx > 0) ts_wait(&s_free[buf], (uint32_t)((idx - 1) & 1));  // the buffer's previous S is in registers
+                    slb_tc_fence_after();
+                    TS_TRACE(2, it);  // S issue
+                    const uint64_t dk_hi = dk0 + (uint64_t)(slot * (2 * kPlane >> 4)), dk_lo = dk_hi + (kPlane >> 4);
+                    const uint32_t idesc_s = slb_umma_idesc_f16(0, kTile, nk);
+                    const uint32_t d = tmem_base + (uint32_t)(buf * 128);
+                    if (sweep2) {
+                        // cross terms first: only the four hi.hi MMAs accumulate onto a large value
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) slb_umma_f16(d, dq_hi + 2 * k, dk_lo + 2 * k, idesc_s, k != 0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) slb_umma_f16(d, dq_lo + 2 * k, dk_hi + 2 * k, idesc_s, true);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) slb_umma_f16(d, dq_hi + 2 * k, dk_hi + 2 * k, idesc_s, true);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) slb_umma_f16(d, dq_hi + 2 * k, dk_hi + 2 * k, idesc_s, k != 0);
+                    }
+                    slb_umma_commit(&s_full[buf]);
+                    slb_umma_commit(&kv_empty[slot]);
+                    if (it == n_iter - 1) slb_umma_commit(q_empty);  // the item's last read of Q
+                };
+                auto issue_pv = [&](int it) {
+                    const int blk = it - nblk;
+                    const int nk = keys_of(blk);
+                    const int t = item_k(it) + 1, slot = t % kSlots;
+                    ts_wait(&kv_full[slot], (uint32_t)((t / kSlots) & 1));
+                    TS_TRACE(8, blk);  // V landed
+                    ts_wait(p_full, (uint32_t)((pblk + blk) & 1));
+                    slb_tc_fence_after();
+                    TS_TRACE(3, blk);  // P V issue
+                    const uint64_t dv_hi = dv0 + (uint64_t)(slot * (2 * kPlane >> 4)), dv_lo = dv_hi + (kPlane >> 4);
+                    const int ksteps = nk >> 4;
+                    // k-step s = keys [16 s, 16 s + 16): P hi at column 32 (s / 2) + 8 (s % 2), P lo 16 columns further
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        if (s < ksteps) {
+                            const uint32_t a_hi = tmem_base + (uint32_t)(32 * (s >> 1) + 8 * (s & 1)), a_lo = a_hi + 16;
+                            const uint64_t koff = (uint64_t)((2048 >> 4) * s);
+                            umma_f16_ts(t_o, a_hi, dv_hi + koff, idesc_o, (blk | s) != 0);       // P hi . V hi -> main
+                            umma_f16_ts(t_o + 64, a_hi, dv_lo + koff, idesc_o, (blk | s) != 0);  // P hi . V lo -> corr
+                            umma_f16_ts(t_o + 64, a_lo, dv_hi + koff, idesc_o, true);            // P lo . V hi -> corr
+                        }
+                    }
+                    slb_umma_commit(&kv_empty[slot]);
+                };
+                ts_wait(q_full, (uint32_t)(n & 1));
+                // the previous item's O (columns [128, 256) = S buffer 1) must be in the softmax warps' registers
+                if (n > 0) ts_wait(o_free, (uint32_t)((n - 1) & 1));
+                // sweep 1 runs one block ahead of the softmax warps (two S buffers); sweep 2: S(j), P V(j), S(j+1), ...
+                for (int it = 0; it <= nblk; ++it) issue_s(it);
+                for (int it = nblk; it < n_iter; ++it) {
+                    issue_pv(it);
+                    if (it + 1 < n_iter) issue_s(it + 1);
+                }
+                slb_umma_commit(o_full);
+                t0 += 3 * nblk;
+                base[0] += uses0;
+                base[1] += uses1;
+                pblk += nblk;
+            }
+        }
+        __syncwarp();
+    } else {
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;            // which 64 keys of every 128-key block
+        const int r = quarter * 32 + lane;           // row of the tile = TMEM lane
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        constexpr float kInvAct = 1.0f / SLB_ACT_PLANE_SCALE;
+        const float c_main = p.scale_log2 * kInvAct * kInvAct;
+        int base[2] = {0, 0};
+        int pblk = 0;
+        int n = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
+            const bool trace_on = trace_cta && n == p.dbg_item && warp == 2 && lane == 0;
+            const int bh = item / p.n_tiles, tile = item % p.n_tiles;
+            const int b = bh / p.H, h = bh % p.H;
+            const int row_base = b * p.T;
+            const int row = tile * kTile + r;
+            float m_row = -INFINITY, l_row = 0.f, neg_m = 0.f;
+            for (int it = 0; it < n_iter; ++it) {
+                const int blk = it % nblk;
+                const bool sweep2 = it >= nblk;
+                const int nk = keys_of(blk);
+                const int buf = s_buf(it), idx = base[buf] + s_idx(it);
+                const uint32_t t_s = tmem_base + lane_addr + (uint32_t)(buf * 128);
+                const bool full_block = (blk + 1) * kKeys <= p.T;
+                if (it == nblk) {
+                    // end of sweep 1: the two warps of a row combine their partial maxima (named barrier 1: softmax warps)
+                    if (half) xch[r] = m_row;
+                    asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
+                    if (!half) m_row = fmaxf(m_row, xch[r]);
+                    asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
+                    if (!half) xch[r] = m_row;
+                    asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
+                    m_row = xch[r];
+                    neg_m = kLog2PScale - m_row;  // exp2(s - m + 10) = 1024 p
+                }
+                ts_wait(&s_full[buf], (uint32_t)(idx & 1));
+                slb_tc_fence_after();
+                TS_TRACE(4, it);  // S visible
+                if (!sweep2) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int c = half * 64 + u * 32;
+                        if (c < nk) {  // warp-uniform
+                            uint32_t a[32];
+                            slb_tmem_ld_32x32(t_s + c, a);
+                            slb_tmem_ld_wait();
+                            if (full_block) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) m_row = fmaxf(m_row, __uint_as_float(a[j]) * c_main);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (blk * kKeys + c + j < p.T) m_row = fmaxf(m_row, __uint_as_float(a[j]) * c_main);
+                            }
+                        }
+                    }
+                    slb_tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) slb_mbar_arrive(&s_free[buf]);
+                    TS_TRACE(5, it);  // maxima done
+                    continue;
+                }
+                // sweep 2: 32 keys at a time, S columns [c, c + 32) -> P hi columns [c, c + 16) | P lo columns [c + 16, c + 32)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int c = half * 64 + u * 32;
+                    if (c < nk) {  // warp-uniform
+                        uint32_t a[32];
+                        slb_tmem_ld_32x32(t_s + c, a);
+                        slb_tmem_ld_wait();
+                        uint32_t hh[16], ll[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float x0 = fmaf(__uint_as_float(a[2 * e]), c_main, neg_m);
+                            float x1 = fmaf(__uint_as_float(a[2 * e + 1]), c_main, neg_m);
+                            if (!full_block) {
+                                if (blk * kKeys + c + 2 * e >= p.T) x0 = -INFINITY;
+                                if (blk * kKeys + c + 2 * e + 1 >= p.T) x1 = -INFINITY;
+                            }
+                            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                            l_row += p0 + p1;
+                            // hi = the value with its low 13 mantissa bits cleared (exact in fp16), lo = the exact remainder
+                            const float h0 = __uint_as_float(__float_as_uint(p0) & 0xFFFFE000u);
+                            const float h1 = __uint_as_float(__float_as_uint(p1) & 0xFFFFE000u);
+                            const __half2 hp = __floats2half2_rn(h0, h1);
+                            const __half2 lp = __floats2half2_rn(p0 - h0, p1 - h1);
+                            hh[e] = *reinterpret_cast<const uint32_t*>(&hp);
+                            ll[e] = *reinterpret_cast<const uint32_t*>(&lp);
+                        }
+                        tmem_st_32x16(t_s + c, hh);
+                        tmem_st_32x16(t_s + c + 16, ll);
+                    }
+                }
+                TS_TRACE(6, it - nblk);  // exponentials + stores issued
+                tmem_st_wait();
+                slb_tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    slb_mbar_arrive(&s_free[buf]);
+                    slb_mbar_arrive(p_full);
+                }
+                TS_TRACE(7, it - nblk);  // P published
+            }
+            base[0] += uses0;
+            base[1] += uses1;
+            pblk += nblk;
+            // ---- row sums of the two column halves, then O = (main + corr) / (scales * l); each warp stores 32 of the 64 dims
+            ts_wait(o_full, (uint32_t)(n & 1));
+            slb_tc_fence_after();
+            TS_TRACE(9, 0);  // O complete
+            uint32_t a[32], cr[32];
+            {
+                const int c = half * 32;
+                slb_tmem_ld_32x32(t_o + lane_addr + c, a);
+                slb_tmem_ld_32x32(t_o + lane_addr + 64 + c, cr);
+                slb_tmem_ld_wait();
+            }
+            // O is in registers: the next item's S MMAs may reuse its columns
+            slb_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) slb_mbar_arrive(o_free);
+            if (half) xch[kTile + r] = l_row;
+            asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
+            if (!half) xch[kTile + r] += l_row;
+            asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
+            l_row = xch[kTile + r];
+            const float inv = kInvAct / l_row;  // V planes carry the activation scale, l_row the 2^10 of the P planes
+            const bool ok = row < p.T;
+            const int64_t out_base = ((int64_t)row_base + row) * p.W + (int64_t)h * 64;
+            if (ok) {
+                const int c = half * 32;
+                float o[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(a[j]) + __uint_as_float(cr[j])) * inv;
+                if (p.out_f32) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        reinterpret_cast<float4*>(p.out_f32 + out_base + c)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                }
+                if (p.out_hi) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t hh[4], ll[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            uint16_t h0, l0, h1, l1;
+                            slb_split2_act(o[8 * j + 2 * e], p.fmt, h0, l0);
+                            slb_split2_act(o[8 * j + 2 * e + 1], p.fmt, h1, l1);
+                            hh[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                            ll[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                        }
+                        *reinterpret_cast<uint4*>(p.out_hi + out_base + c + 8 * j) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                        *reinterpret_cast<uint4*>(p.out_lo + out_base + c + 8 * j) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                    }
+                }
+            }
+            TS_TRACE(9, 1);  // item done
+            // the row-sum exchange words are rewritten by the next item's epilogue only after its own barriers; the maxima
+            // words by its sweep 1 -> 2 transition, which follows this epilogue in program order of every warp
+        }
+    }
+
+    slb_tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        slb_tc_fence_after();
+        slb_tmem_dealloc<256>(tmem_base);
+    }
+}
+
+}  // namespace
+
+unsigned int* slb_attention_trace_buffer();  // attention_mma.cu
+
+// Full 128-row query tiles of every (image, head) on the TS-mode tcgen05 path; the caller handles the remaining rows.
+int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles,
+                           int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
+    const int64_t W = H * 64, rows = B * T;
+    CUtensorMap tm;
+    int rc = slb_make_plane_map(&tm, qkv_planes, rows, 3 * W, 2, kTile);
+    if (rc != SLB_OK) return rc;
+    AttnTsParams p{};
+    p.T = (int)T; p.H = (int)H; p.W = (int)W;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.out_f32 = out_f32; p.out_hi = out_hi; p.out_lo = out_lo; p.fmt = plane_fmt;
+    static const bool trace = [] { const char* e = getenv("SLB_ATTN_TRACE"); return e && e[0] == '1'; }();
+    if (trace) {
+        const char* e = getenv("SLB_ATTN_TRACE_CTA");
+        p.dbg = slb_attention_trace_buffer();
+        p.dbg_cta = e ? atoi(e) : 0;
+        e = getenv("SLB_ATTN_TRACE_ITEM");
+        p.dbg_item = e ? atoi(e) : 0;
+    }
+    SLB_CUDA_OK(cudaFuncSetAttribute(attention_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    p.n_tiles = n_tiles;
+    p.n_items = (int)(B * H * n_tiles);
+    int dev = 0, sms = 0;
+    SLB_CUDA_OK(cudaGetDevice(&dev));
+    SLB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = std::min(p.n_items, 2 * sms);  // persistent: two CTAs per SM
+    attention_ts_kernel<<<grid, kThreads, kSmem, st>>>(tm, p);
+    SLB_LAUNCH_OK("attention_ts");
+    return SLB_OK;
+}
