@@ -1,7 +1,6 @@
-"""Time the long-sequence attention kernel on the towers' shapes: python scripts/bench_attention.py  (SLB_ATTN_TS=0 selects
-the shared-memory-P kernel). One JSON line per shape: CUDA-event time per launch, issued TFLOP/s (3 plane products)."""
+"""Time the long-sequence attention kernel on the towers' shapes: python scripts/bench_attention.py
+One JSON line per shape: CUDA-event time per launch (tcgen05 tiles + the mma.sync tail rows), issued TFLOP/s (3 plane products)."""
 import json
-import os
 import sys
 from pathlib import Path
 
@@ -26,5 +25,4 @@ for name, B, T, H in SHAPES:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     flops = 4.0 * B * H * T * T * 64 * 3
-    print(json.dumps({"shape": name, "B": B, "T": T, "H": H, "kernel": "ts" if os.environ.get("SLB_ATTN_TS", "1") != "0" else "smem-P",
-                      "us": round(ms * 1e3, 1), "issued_TFLOP/s": round(flops / ms / 1e9, 1)}), flush=True)
+    print(json.dumps({"shape": name, "B": B, "T": T, "H": H, "us": round(ms * 1e3, 1), "issued_TFLOP/s": round(flops / ms / 1e9, 1)}), flush=True)

@@ -1,4 +1,5 @@
-"""Timeline of one CTA of the tcgen05 attention kernel (SLB_ATTN_TRACE=1): SM-clock offsets of every hand-off.
+"""Timeline of one work item of one CTA of the tcgen05 attention kernel (attention_ts.cu, SLB_ATTN_TRACE=1): SM-clock
+offsets of every hand-off since the CTA started.
 SLB_ATTN_TRACE=1 python scripts/trace_attention.py [T] [B] [H]"""
 import ctypes
 import os
@@ -22,12 +23,9 @@ for _ in range(3):
 torch.cuda.synchronize()
 ptr = N.load().slb_attention_trace()
 w = (ctypes.c_uint32 * 256).from_address(ptr)
-names = ["tma issue (item)", "mma: K landed (it)", "mma: S issue (it)", "mma: PV issue (blk)", "sm: S visible (it)", "sm: S in regs (it)",
-         "sm: exps done (blk)", "sm: P free (blk)", "sm: P published (blk)", "O complete / CTA done"]
-if os.environ.get("SLB_ATTN_TS", "1") != "0":  # the TS-mode kernel's events (attention_ts.cu)
-    names = ["tma issue (item)", "mma: K landed (it)", "mma: S issue (it)", "mma: PV issue (blk)", "sm: S visible (it)",
-             "sm: maxima done (it)", "sm: exps+stores (blk)", "sm: P published (blk)", "mma: V landed (blk)", "O complete / CTA done"]
-    print("SM id of the traced CTA:", w[63])
+names = ["tma issue (ring item)", "mma: K landed (it)", "mma: S issue (it)", "mma: PV issue (blk)", "sm: S visible (it)",
+         "sm: maxima done (it)", "sm: exps+stores (blk)", "sm: P published (blk)", "mma: V landed (blk)", "O complete / item done"]
+print("SM id of the traced CTA:", w[63], "(SLB_ATTN_TRACE_CTA / SLB_ATTN_TRACE_ITEM pick the CTA and its n-th work item)")
 nblk = (T + 63) // 64
 for t, nm in enumerate(names):
     vals = [w[64 + 16 * t + i] for i in range(16)]

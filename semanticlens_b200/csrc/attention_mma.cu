@@ -559,6 +559,118 @@ __global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(AttnPla
     }
 }
 
+// A tail of one to four query rows (the last token left over by the tcgen05 tiles of a 257-token tower) as plain fp32
+// SIMT work: one CTA per (image, head), its 4 warps take the 32-key groups round-robin. Per group a lane first owns two of
+// the 64 dims (coalesced 128-byte reads of the K hi / lo planes), the 32 partial dot products are summed by a transposing
+// butterfly (31 shuffles for 32 keys: lane j ends with key j's logit), then an online-softmax step and the P V update with
+// the lane back on its two dims. The warps' (max, sum, O) merge through shared memory. ~6 k instructions per (image, head)
+// instead of a 16-row tensor-core tile that is 94 % padding and latency-bound (48 -> ~10 us per layer at B = 64, H = 16).
+__global__ void __launch_bounds__(128) attention_rows_kernel(AttnPlanesParams p) {
+    __shared__ float s_m[4], s_l[4], s_o[4][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int64_t ld = 3 * (int64_t)p.W;
+    const int64_t row_base = (int64_t)b * p.T;
+    const uint32_t* khi = reinterpret_cast<const uint32_t*>(p.hi + row_base * ld + p.W + h * 64) + lane;
+    const uint32_t* klo = reinterpret_cast<const uint32_t*>(p.lo + row_base * ld + p.W + h * 64) + lane;
+    const int64_t ldw = ld / 2;  // row pitch in 32-bit words
+    constexpr float kInvAct = 1.0f / SLB_ACT_PLANE_SCALE;
+    const float c_log2 = p.scale * 1.4426950408889634f * kInvAct * kInvAct;
+    const int ngroups = (p.T + 31) >> 5;
+    auto unpack = [](uint32_t hi, uint32_t lo, float& x0, float& x1) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+        x0 = a.x + c.x;
+        x1 = a.y + c.y;
+    };
+    for (int qr = p.q_row0; qr < p.T; ++qr) {
+        float q0, q1;
+        {
+            const int64_t off = (row_base + qr) * ld + h * 64;
+            unpack(reinterpret_cast<const uint32_t*>(p.hi + off)[lane], reinterpret_cast<const uint32_t*>(p.lo + off)[lane], q0, q1);
+        }
+        float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+        // the same trip count for every warp (a data-independent loop keeps the shuffles plain SHFLs); a warp whose last
+        // round has no group left works on keys past T, which are masked
+        for (int g0 = 0; g0 < ngroups; g0 += 4) {
+            const int key0 = (g0 + warp) * 32;
+            float part[32];
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+                // keys past T read the last key again (no branch: the 64 loads of a group stay in flight together); their
+                // logits are masked below
+                const int64_t ko = (int64_t)min(key0 + jj, p.T - 1) * ldw;
+                float k0, k1;
+                unpack(khi[ko], klo[ko], k0, k1);
+                part[jj] = fmaf(q0, k0, q1 * k1);
+            }
+            // transposing butterfly: after the step with stride s a lane keeps the half of its values whose key index has bit
+            // s equal to its own lane bit; lane j ends with the full dot product of key j
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+                for (int i = 0; i < s; ++i) {
+                    const bool up = (lane & s) != 0;
+                    const float keep = up ? part[i + s] : part[i], send = up ? part[i] : part[i + s];
+                    part[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                }
+            }
+            const float logit = key0 + lane < p.T ? part[0] * c_log2 : -INFINITY;
+            float gm = logit;
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, s));
+            const float m_new = fmaxf(m, gm);
+            const float m_use = m_new == -INFINITY ? 0.f : m_new;  // nothing seen yet and an empty group
+            const float alpha = exp2f(m - m_use), pj = exp2f(logit - m_use);
+            l = l * alpha + slb_warp_sum_butterfly(pj);
+            o0 *= alpha;
+            o1 *= alpha;
+            m = m_new;
+            const uint32_t* vhi = khi + p.W / 2;  // V follows K in the packed q | k | v row
+            const uint32_t* vlo = klo + p.W / 2;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+                const float pv = __shfl_sync(0xffffffffu, pj, jj);  // 0 for keys past T
+                const int64_t vo = (int64_t)min(key0 + jj, p.T - 1) * ldw;
+                float v0, v1;
+                unpack(vhi[vo], vlo[vo], v0, v1);
+                o0 = fmaf(pv, v0, o0);
+                o1 = fmaf(pv, v1, o1);
+            }
+        }
+        __syncthreads();  // the previous row's merge has been read
+        if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+        s_o[warp][2 * lane] = o0;
+        s_o[warp][2 * lane + 1] = o1;
+        __syncthreads();
+        if (warp == 0) {
+            float mm = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) mm = fmaxf(mm, s_m[w]);
+            float L = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const float f = s_m[w] == -INFINITY ? 0.f : exp2f(s_m[w] - mm);  // a warp without a key group
+                L += f * s_l[w];
+                a0 += f * s_o[w][2 * lane];
+                a1 += f * s_o[w][2 * lane + 1];
+            }
+            const float inv = kInvAct / L;  // V planes carry the activation scale
+            a0 *= inv;
+            a1 *= inv;
+            const int64_t off = (row_base + qr) * p.W + h * 64 + 2 * lane;
+            if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + off) = make_float2(a0, a1);
+            if (p.out_hi) {
+                uint16_t h0, l0, h1, l1;
+                slb_split2_act(a0, p.fmt, h0, l0);
+                slb_split2_act(a1, p.fmt, h1, l1);
+                *reinterpret_cast<uint32_t*>(p.out_hi + off) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                *reinterpret_cast<uint32_t*>(p.out_lo + off) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+        }
+    }
+}
+
 template <int NW, int MINB, bool kSplit = false>
 int launch_attn_planes(const AttnPlanesParams& p, int64_t B, cudaStream_t st) {
     const size_t smem = (size_t)(p.Tkp > kKeyBlock ? 2 : 1) * 4 * kKeyBlock * kKPad * sizeof(__half);
@@ -603,8 +715,6 @@ int slb_attention_mma_dh64(const float* q, int64_t q_bs, int64_t q_rs, const flo
 
 int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles,
                            int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st);  // attention_ts.cu
-int slb_attention_tc_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles,
-                           int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st);
 
 extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, int64_t dh, float scale,
                                     int causal, int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream) {
@@ -626,410 +736,33 @@ extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64
     p.causal = causal ? 1 : 0;
     p.out_f32 = out_f32; p.out_hi = out_planes; p.out_lo = out_planes ? out_planes + rows * W : nullptr; p.fmt = plane_fmt;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // Long sequences: full 128-query tiles run on tcgen05 (attention_tc_kernel); a tail of fewer than 64 rows (the class
-    // token of a 257-token tower) and short / causal sequences stay on the mma.sync kernel.
+    // Long sequences: full 128-query tiles run on tcgen05 (attention_ts.cu: P as a tensor-memory operand); a tail of fewer
+    // than 64 rows (the last row of a 257-token tower) and short / causal sequences stay on the mma.sync kernel.
     static const bool no_tc = [] { const char* e = getenv("SLB_ATTN_TC"); return e && e[0] == '0'; }();
     if (!causal && !no_tc && T >= 128) {
         int n_tiles = (int)(T / 128);
         const int64_t rem = T - 128 * (int64_t)n_tiles;
         if (rem >= 64) n_tiles += 1;
-        // P as a tensor-memory operand (attention_ts.cu) unless SLB_ATTN_TS=0 asks for the shared-memory-P kernel
-        static const bool no_ts = [] { const char* e = getenv("SLB_ATTN_TS"); return e && e[0] == '0'; }();
-        int rc = no_ts ? slb_attention_tc_tiles(qkv_planes, B, T, H, scale, n_tiles, plane_fmt, out_f32, p.out_hi, p.out_lo, st)
-                       : slb_attention_ts_tiles(qkv_planes, B, T, H, scale, n_tiles, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
+        int rc = slb_attention_ts_tiles(qkv_planes, B, T, H, scale, n_tiles, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
         if (rc != SLB_OK) return rc;
         if ((int64_t)n_tiles * 128 >= T) return SLB_OK;
         p.q_row0 = n_tiles * 128;
-        if (T - p.q_row0 <= 16) return launch_attn_planes<4, 3, true>(p, B, st);  // the class-token row: split the keys
+        if (T - p.q_row0 <= 4) {  // one to four leftover rows (the last token of a 257-token tower): fp32 SIMT rows
+            attention_rows_kernel<<<(unsigned)(B * H), 128, 0, st>>>(p);
+            SLB_LAUNCH_OK("attention_rows");
+            return SLB_OK;
+        }
+        if (T - p.q_row0 <= 16) return launch_attn_planes<4, 3, true>(p, B, st);  // a short tail: split the keys
     }
     return launch_attn_planes<4, 3>(p, B, st);  // 64 query rows per CTA, 3 CTAs / SM (168 registers, <= 72 KB smem)
 }
 
 // =================================================================================================
-// tcgen05 attention for full 128-row query tiles (T >= 128: ViT-B/16, ViT-L/14, SigLIP towers).
-//
-// One CTA = one (image, head, 128-query tile); 320 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 softmax
-// (thread = query row = TMEM lane, two warps per lane quarter, each on 32 of a block's 64 keys). Operands come from the
-// in_proj GEMM's split planes through ONE 3-D tensor map (boxes of 64 cols x 128 / 64 rows x 2 planes, 128B swizzle):
-// the Q tile, and K / V blocks of 64 tokens that travel through one ring of three 16 KB slots. The tiles take 112 KB
-// and the accumulators 256 TMEM columns, so TWO CTAs share an SM and fill each other's hand-off bubbles.
-// Two sweeps over the keys avoid rescaling the output accumulator: sweep 1 computes S = Q K^T (hi.hi only: the row
-// maximum is just the softmax's stabiliser) block by block, sweep 2 recomputes S with all three plane products, writes
-// P = exp2(S - max) as split planes into shared memory (K-major, swizzled by hand) and accumulates O += P V with V
-// consumed straight from its row-major tile as an MN-major operand (no transpose anywhere).
-// Software pipeline: the softmax warps release S as soon as it is in registers and the MMA warp issues S of block j + 1
-// BEFORE P V of block j, so the tensor core computes the next logits under this block's exponentials; V_{j+1} is
-// requested when the S MMAs release K_j's slot (early), K_{j+2} when P V releases V_j's.
-// Accumulators (TMEM): S main | S corr (2 x 64 columns), O main | O corr (2 x 64 columns); hi.hi goes into main and the
-// two cross terms into corr (q, k, v planes share one scale, P planes carry 2^10). Rows of the tile beyond T and keys
-// beyond T are masked / never stored. SLB_ATTN_TRACE=1 records one CTA's hand-off timeline (scripts/trace_attention.py):
-// what remains is the serial chain tmem-load -> exp -> P store -> P V per block (~3500 SM clocks, MUFU- and
-// latency-bound) against ~770 clocks of tensor work; a ping-pong over two query tiles per CTA is the next step.
+// Long sequences (T >= 128): full 128-row query tiles run on tcgen05 with P as a tensor-memory operand — attention_ts.cu.
+// SLB_ATTN_TRACE=1 records one CTA's hand-off timeline into host-mapped words (scripts/trace_attention.py).
 // =================================================================================================
-namespace {
-
-constexpr int kTcSoftmaxWarps = 8;                // two warps per TMEM lane quarter: each takes 32 of a block's 64 keys
-constexpr int kTcThreads = (2 + kTcSoftmaxWarps) * 32;
-constexpr int kTcTile = 128;                      // queries per CTA
-constexpr int kTcKeys = 64;                       // keys per block
-constexpr int kTcPlaneQ = kTcTile * 64 * 2;       // one 128 x 64 fp16 plane tile (Q, P): 16 KB
-constexpr int kTcPlaneK = kTcKeys * 64 * 2;       // one 64 x 64 fp16 plane tile (K, V): 8 KB
-constexpr int kTcQ = 0;                           // Q  hi | lo                       32 KB
-constexpr int kTcKV = 2 * kTcPlaneQ;              // ring of three 16 KB slots (hi | lo planes of 64 tokens) for K and V blocks
-constexpr int kTcSlots = 3;
-constexpr int kTcP = kTcKV + 6 * kTcPlaneK;       // P  hi | lo (128 x 64 each)        32 KB (also the row max / sum exchange)
-constexpr int kTcBars = kTcP + 2 * kTcPlaneQ;     // 112 KB of tiles: two CTAs per SM (2 x (112.1 KB + 1 KB reserved) <= 228 KB)
-constexpr size_t kTcSmem = (size_t)kTcBars + 128 /*barriers*/;
-
-struct AttnTcParams {
-    int T, H, W;
-    float scale_log2;  // scale * log2(e)
-    float* out_f32; uint16_t* out_hi; uint16_t* out_lo; int fmt;
-    unsigned int* dbg;
-};
-
-__device__ __noinline__ void tc_timeout(unsigned int* dbg, int site) {
-    if (dbg) { dbg[(blockIdx.x & 7) * 8 + (site & 7)] = 0xDEAD0000u | (unsigned)site; __threadfence_system(); }
-    __trap();
-}
-__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, int site) {
-    if (slb_mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!slb_mbar_try_wait(bar, parity))
-        if (clock64() - t0 > 4000000000ll) tc_timeout(dbg, site);
-}
-
-// SLB_ATTN_TRACE=1: CTA (0, 0) records SM-clock offsets of its hand-offs into host-mapped words (scripts/trace_attention.py)
-#define TC_TRACE(type, idx)                                                                                  \
-    do {                                                                                                     \
-        if (trace_on && (idx) < 16) p.dbg[64 + (type) * 16 + (idx)] = (unsigned int)(clock64() - t_start);   \
-    } while (0)
-
-// MN-major operand tile (rows = K index, 128 B per row = 64 contiguous MN elements), 128-byte swizzle:
-// SBO = 1024 B between 8-row groups along K; LBO (between 64-element MN atoms) unused for N = 64.
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(1024 >> 4) << 16;    // LBO (not used: a single MN atom)
-    d |= (uint64_t)(1024 >> 4) << 32;    // SBO
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-__global__ void __launch_bounds__(kTcThreads, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv, AttnTcParams p) {
-    // no alignment slack: two CTAs must fit an SM. The declared alignment is honoured for dynamic shared memory (no static
-    // shared memory in this kernel); checked below, a misaligned base traps instead of corrupting swizzled tiles.
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = smem_raw;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcBars);
-    uint64_t* q_full = bars;        // TMA -> MMA
-    uint64_t* kv_full = bars + 1;   // [3] TMA -> MMA, one per slot of the K / V ring
-    uint64_t* kv_empty = bars + 4;  // [3] MMA -> TMA
-    uint64_t* s_full = bars + 7;    // MMA -> softmax
-    uint64_t* s_free = bars + 8;    // softmax (8 warps) -> MMA
-    uint64_t* p_full = bars + 9;    // softmax (8 warps) -> MMA
-    uint64_t* p_free = bars + 10;   // MMA -> softmax
-    uint64_t* o_full = bars + 11;   // MMA -> softmax
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-    // [2][128] partial row max / row sum of the second column half; aliases the P tile, which is idle at both exchanges
-    // (before the first P is written, and after the last P V has completed)
-    float* xch = reinterpret_cast<float*>(smem + kTcP);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-    const int q0 = blockIdx.y * kTcTile;
-    const int row_base = b * p.T;                       // first token row of this image in the planes
-    const int nblk = (p.T + kTcKeys - 1) / kTcKeys;
-    const int n_iter = 2 * nblk;                        // sweep 1 (max) then sweep 2 (P V)
-
-    if (warp == 0 && lane == 0) {
-        slb_prefetch_tmap(&tmq);
-        slb_prefetch_tmap(&tmkv);
-        slb_mbar_init(q_full, 1);
-        if ((slb_smem_u32(smem) & 1023u) != 0) tc_timeout(p.dbg, 15);
-        for (int i = 0; i < kTcSlots; ++i) {
-            slb_mbar_init(&kv_full[i], 1);
-            slb_mbar_init(&kv_empty[i], 1);
-        }
-        slb_mbar_init(s_full, 1);
-        slb_mbar_init(s_free, kTcSoftmaxWarps);
-        slb_mbar_init(p_full, kTcSoftmaxWarps);
-        slb_mbar_init(p_free, 1);
-        slb_mbar_init(o_full, 1);
-        slb_fence_mbar_init();
-    }
-    if (warp == 1) slb_tmem_alloc<256>(tmem_slot);
-    slb_tc_fence_before();
-    __syncthreads();
-    slb_tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const bool trace_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
-    const long long t_start = clock64();
-    const uint32_t t_s = tmem_base;            // S main [0,64), S corr [64,128)
-    const uint32_t t_o = tmem_base + 128;      // O main [128,192), O corr [192,256)
-
-    if (warp == 0) {
-        if (lane == 0) {
-            slb_mbar_arrive_expect_tx(q_full, 2u * kTcPlaneQ);
-            slb_tma_load_3d(smem + kTcQ, &tmq, h * 64, row_base + q0, 0, q_full);
-            // K and V blocks travel through ONE ring of three slots in the order the sweeps consume them: K_0 .. K_{n-1}
-            // (sweep 1, triple-buffered), then K_0, V_0, K_1, V_1, ... Item t may be requested once item t - 3 has been read:
-            // V_{j+1} follows K_j (released by the S MMAs, early), so it lands while the softmax warps still work on block j;
-            // K_{j+2} follows V_j (released by the P V MMAs) and has the whole softmax of block j + 1 to arrive.
-            int t = 0;
-            auto load_item = [&](int col, int row) {
-                const int slot = t % kTcSlots;
-                tc_wait(&kv_empty[slot], (uint32_t)((t / kTcSlots) & 1) ^ 1u, p.dbg, 1);
-                slb_mbar_arrive_expect_tx(&kv_full[slot], 2u * kTcPlaneK);
-                slb_tma_load_3d(smem + kTcKV + slot * 2 * kTcPlaneK, &tmkv, col, row, 0, &kv_full[slot]);
-                TC_TRACE(0, t);
-                ++t;
-            };
-            for (int it = 0; it < n_iter; ++it) {
-                const int blk = it % nblk;
-                load_item(p.W + h * 64, row_base + blk * kTcKeys);
-                if (it >= nblk) load_item(2 * p.W + h * 64, row_base + blk * kTcKeys);
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t qa = slb_smem_u32(smem + kTcQ);
-            const uint32_t pa = slb_smem_u32(smem + kTcP);
-            // loop-invariant operand descriptors (slot 0 of the ring for K / V) and the P V instruction descriptor
-            const uint64_t dq_hi = slb_umma_desc_sw128(qa), dq_lo = slb_umma_desc_sw128(qa + kTcPlaneQ);
-            const uint64_t dp_hi = slb_umma_desc_sw128(pa), dp_lo = slb_umma_desc_sw128(pa + kTcPlaneQ);
-            const uint64_t dk0 = slb_umma_desc_sw128(slb_smem_u32(smem + kTcKV));
-            const uint64_t dv0 = umma_desc_mn_sw128(slb_smem_u32(smem + kTcKV));
-            const uint32_t idesc_o = slb_umma_idesc_f16(0, kTcTile, 64) | (1u << 16);  // B (= V) is MN-major
-            tc_wait(q_full, 0, p.dbg, 2);
-            // S(it) = Q K^T. Sweep 1 only needs row maxima as a softmax stabiliser: hi.hi alone (|error| ~ 2^-11 |s|) is
-            // enough, the exponentials of sweep 2 use the full three products.
-            // item index of block it's K in the ring (the producer's sequence); its V, in sweep 2, is the next item
-            auto item_k = [&](int it) { return it < nblk ? it : nblk + 2 * (it - nblk); };
-            auto issue_s = [&](int it) {
-                const int blk = it % nblk;
-                const bool sweep2 = it >= nblk;
-                const int nk = min(kTcKeys, (p.T - blk * kTcKeys + 15) & ~15);  // keys of this block, padded to the MMA N step
-                const int t = item_k(it), slot = t % kTcSlots;
-                tc_wait(&kv_full[slot], (uint32_t)((t / kTcSlots) & 1), p.dbg, 3);
-                TC_TRACE(1, it);  // K landed
-                tc_wait(s_free, (it & 1) ^ 1u, p.dbg, 4);  // the softmax warps have loaded the previous S into registers
-                slb_tc_fence_after();
-                TC_TRACE(2, it);  // S MMAs issued from here
-                const uint64_t dk_hi = dk0 + (uint64_t)(slot * (2 * kTcPlaneK >> 4)), dk_lo = dk_hi + (kTcPlaneK >> 4);
-                const uint32_t idesc_s = slb_umma_idesc_f16(0, kTcTile, nk);
-                // hi.hi -> S main; hi.lo + lo.hi -> S corr (same scale; summed in fp32 by the softmax warps, so the small
-                // terms are not truncated against the large accumulator: the logits feed an exponential).
-                // One thread issues every MMA: descriptors are base + constant (a descriptor is linear in the address), so
-                // that the issue rate (not ~90 clocks of address arithmetic per MMA) stays below the 32-clock N = 64 MMA.
-#pragma unroll
-                for (int pr = 0; pr < 3; ++pr) {
-                    if (pr == 0 || sweep2) {
-                        const uint64_t da = pr == 2 ? dq_lo : dq_hi, db = pr == 1 ? dk_lo : dk_hi;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            slb_umma_f16(t_s + (pr ? 64 : 0), da + 2 * k, db + 2 * k, idesc_s, pr == 2 ? true : k != 0);
-                    }
-                }
-                slb_umma_commit(s_full);
-                slb_umma_commit(&kv_empty[slot]);  // the K slot is free as soon as these MMAs have read it
-            };
-            // O += P V for block it of sweep 2, once V has landed and the softmax warps have written P
-            auto issue_pv = [&](int it) {
-                const int blk = it - nblk;
-                const int nk = min(kTcKeys, (p.T - blk * kTcKeys + 15) & ~15);
-                const int t = item_k(it) + 1, slot = t % kTcSlots;
-                tc_wait(&kv_full[slot], (uint32_t)((t / kTcSlots) & 1), p.dbg, 8);
-                tc_wait(p_full, (uint32_t)(blk & 1), p.dbg, 5);
-                slb_tc_fence_after();
-                TC_TRACE(3, blk);  // P V MMAs issued from here
-                const uint64_t dv_hi = dv0 + (uint64_t)(slot * (2 * kTcPlaneK >> 4)), dv_lo = dv_hi + (kTcPlaneK >> 4);
-                const int ksteps = nk >> 4;
-#pragma unroll
-                for (int pr = 0; pr < 3; ++pr) {
-                    const uint64_t da = pr == 2 ? dp_lo : dp_hi;   // P hi / lo
-                    const uint64_t db = pr == 1 ? dv_lo : dv_hi;   // V hi / lo
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        // P hi . V hi -> main; the cross terms P hi . V lo + P lo . V hi -> corr (same scale, added in fp32)
-                        if (k < ksteps)
-                            slb_umma_f16(t_o + (pr ? 64 : 0), da + 2 * k, db + (2048 >> 4) * k, idesc_o,
-                                         pr == 2 ? true : (blk | k) != 0);
-                    }
-                }
-                slb_umma_commit(p_free);
-                slb_umma_commit(&kv_empty[slot]);
-            };
-            // software pipeline: S of the next block is issued BEFORE P V of the current one, so the tensor core works on
-            // S(it + 1) while the softmax warps turn S(it) into P(it) (they release S as soon as it is in registers)
-            for (int it = 0; it <= nblk; ++it) issue_s(it);  // sweep 1 and the first block of sweep 2
-            for (int it = nblk; it < n_iter; ++it) {
-                if (it + 1 < n_iter) issue_s(it + 1);
-                issue_pv(it);
-            }
-            slb_umma_commit(o_full);
-        }
-        __syncwarp();
-    } else {
-        const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;            // which 32 keys of every 64-key block
-        const int r = quarter * 32 + lane;           // row of the tile = TMEM lane
-        const int row = q0 + r;
-        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        constexpr float kInvAct = 1.0f / SLB_ACT_PLANE_SCALE;
-        const float c_main = p.scale_log2 * kInvAct * kInvAct;
-        float m_row = -INFINITY, l_row = 0.f;
-        unsigned char* p_hi = smem + kTcP;
-        unsigned char* p_lo = p_hi + kTcPlaneQ;
-        for (int it = 0; it < n_iter; ++it) {
-            const int blk = it % nblk;
-            const bool sweep2 = it >= nblk;
-            const int nk = min(kTcKeys, (p.T - blk * kTcKeys + 15) & ~15);
-            if (it == nblk) {
-                // end of sweep 1: the two warps of a row exchange their partial maxima (named barrier 1: softmax warps only)
-                if (half) xch[r] = m_row;
-                asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
-                if (!half) m_row = fmaxf(m_row, xch[r]);
-                asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
-                if (!half) xch[r] = m_row;
-                asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
-                m_row = xch[r];
-                // xch aliases the P tile: nobody may start writing P before every row has read its maximum
-                asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
-            }
-            tc_wait(s_full, (uint32_t)(it & 1), p.dbg, 6);
-            slb_tc_fence_after();
-            if (warp == 2) TC_TRACE(4, it);    // S visible to the softmax warps
-            const int c = half * 32;           // this warp's 32 keys of the block
-            const bool has_cols = c < nk;      // warp-uniform
-            float v[32];
-            if (has_cols) {
-                uint32_t a[32];
-                slb_tmem_ld_32x32(t_s + lane_addr + c, a);
-                if (sweep2) {
-                    uint32_t sc[32];
-                    slb_tmem_ld_32x32(t_s + lane_addr + 64 + c, sc);
-                    slb_tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        v[j] = (blk * kTcKeys + c + j < p.T) ? (__uint_as_float(a[j]) + __uint_as_float(sc[j])) * c_main : -INFINITY;
-                } else {
-                    slb_tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = (blk * kTcKeys + c + j < p.T) ? __uint_as_float(a[j]) * c_main : -INFINITY;
-                }
-            }
-            // S is in registers: hand the accumulator back so that the next S is computed under this block's exponentials
-            slb_tc_fence_before();
-            __syncwarp();
-            if (lane == 0) slb_mbar_arrive(s_free);
-            if (warp == 2) TC_TRACE(5, it);    // S in registers
-            if (!sweep2) {
-                if (has_cols) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) m_row = fmaxf(m_row, v[j]);
-                }
-                continue;
-            }
-            // p = exp2(s - max) as split planes: 16-byte chunks of hi and of lo per 8 keys, swizzled like TMA would write them
-            uint32_t hh[4][4], ll[4][4];
-            if (has_cols) {
-#pragma unroll
-                for (int q8 = 0; q8 < 4; ++q8) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float p0 = exp2f(v[q8 * 8 + 2 * e] - m_row), p1 = exp2f(v[q8 * 8 + 2 * e + 1] - m_row);
-                        l_row += p0 + p1;
-                        split_pair_unit(p0, p1, hh[q8][e], ll[q8][e]);
-                    }
-                }
-            }
-            if (warp == 2) TC_TRACE(6, it - nblk);  // exponentials done
-            tc_wait(p_free, (uint32_t)((it - nblk) & 1) ^ 1u, p.dbg, 7);  // the previous P has been consumed by its MMAs
-            if (warp == 2) TC_TRACE(7, it - nblk);  // P buffer free
-            if (has_cols) {
-#pragma unroll
-                for (int q8 = 0; q8 < 4; ++q8) {
-                    const int chunk = (c + q8 * 8) >> 3;  // 16-byte chunk of the row holding these 8 keys
-                    const size_t off = (size_t)r * 128 + (size_t)((chunk ^ (r & 7)) << 4);
-                    *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(hh[q8][0], hh[q8][1], hh[q8][2], hh[q8][3]);
-                    *reinterpret_cast<uint4*>(p_lo + off) = make_uint4(ll[q8][0], ll[q8][1], ll[q8][2], ll[q8][3]);
-                }
-            }
-            slb_fence_proxy_async();  // the P tile was written through the generic proxy; the MMA reads it through the async proxy
-            __syncwarp();
-            if (lane == 0) slb_mbar_arrive(p_full);
-            if (warp == 2) TC_TRACE(8, it - nblk);  // P written and published
-        }
-        // ---- row sums of the two column halves, then O = (main + corr) / (scales * l); each warp stores 32 of the 64 dims ----
-        // every P V has completed, hence every warp's P store before it (store -> fence.proxy.async -> p_full -> MMA -> commit
-        // -> o_full): the P tile is idle and can carry the exchange. (compute-sanitizer racecheck does not follow ordering
-        // through mbarriers / tcgen05.commit and reports the store below against the P stores.)
-        tc_wait(o_full, 0, p.dbg, 0);
-        slb_tc_fence_after();
-        if (warp == 2) TC_TRACE(9, 0);  // O complete
-        if (half) xch[128 + r] = l_row;
-        asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
-        if (!half) xch[128 + r] += l_row;
-        asm volatile("bar.sync 1, %0;" ::"n"(kTcSoftmaxWarps * 32) : "memory");
-        l_row = xch[128 + r];
-        const float inv = kInvAct / (kPScale * l_row);  // V planes carry the activation scale, P planes kPScale
-        const bool ok = row < p.T;
-        const int64_t base = ((int64_t)row_base + row) * p.W + (int64_t)h * 64;
-        {
-            const int c = half * 32;
-            uint32_t a[32], cr[32];
-            slb_tmem_ld_32x32(t_o + lane_addr + c, a);
-            slb_tmem_ld_32x32(t_o + lane_addr + 64 + c, cr);
-            slb_tmem_ld_wait();
-            if (ok) {
-                float o[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(a[j]) + __uint_as_float(cr[j])) * inv;
-                if (p.out_f32) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        reinterpret_cast<float4*>(p.out_f32 + base + c)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                }
-                if (p.out_hi) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t hh[4], ll[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            uint16_t h0, l0, h1, l1;
-                            slb_split2_act(o[8 * j + 2 * e], p.fmt, h0, l0);
-                            slb_split2_act(o[8 * j + 2 * e + 1], p.fmt, h1, l1);
-                            hh[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                            ll[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                        }
-                        *reinterpret_cast<uint4*>(p.out_hi + base + c + 8 * j) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-                        *reinterpret_cast<uint4*>(p.out_lo + base + c + 8 * j) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-                    }
-                }
-            }
-        }
-    }
-
-    slb_tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        slb_tc_fence_after();
-        slb_tmem_dealloc<256>(tmem_base);
-        TC_TRACE(9, 1);  // CTA done
-    }
-}
-
-}  // namespace
-
-static unsigned int* g_attn_trace_host = nullptr;  // SLB_ATTN_TRACE=1 only
+static unsigned int* g_attn_trace_host = nullptr;
 static unsigned int* g_attn_trace_dev = nullptr;
-unsigned int* slb_attention_trace_buffer();
-namespace {
-}  // namespace
 
 // the trace words of the last tcgen05 attention launch (null unless SLB_ATTN_TRACE=1): [64 + type * 16 + index] SM clocks
 extern "C" const unsigned int* slb_attention_trace() { return g_attn_trace_host; }
@@ -1042,27 +775,4 @@ unsigned int* slb_attention_trace_buffer() {
     }
     for (int i = 0; i < 256; ++i) g_attn_trace_host[i] = 0;
     return g_attn_trace_dev;
-}
-
-// Full 128-row query tiles of every (image, head) on the tcgen05 path; the caller handles the remaining rows.
-int slb_attention_tc_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles,
-                           int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
-    const int64_t W = H * 64, rows = B * T;
-    CUtensorMap tmq, tmkv;
-    int rc = slb_make_plane_map(&tmq, qkv_planes, rows, 3 * W, 2, kTcTile);
-    if (rc != SLB_OK) return rc;
-    rc = slb_make_plane_map(&tmkv, qkv_planes, rows, 3 * W, 2, kTcKeys);
-    if (rc != SLB_OK) return rc;
-    AttnTcParams p{};
-    p.T = (int)T; p.H = (int)H; p.W = (int)W;
-    p.scale_log2 = scale * 1.4426950408889634f;
-    p.out_f32 = out_f32; p.out_hi = out_hi; p.out_lo = out_lo; p.fmt = plane_fmt;
-    p.dbg = nullptr;
-    static const bool trace = [] { const char* e = getenv("SLB_ATTN_TRACE"); return e && e[0] == '1'; }();
-    if (trace) p.dbg = slb_attention_trace_buffer();
-    SLB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-    dim3 grid((unsigned)(B * H), (unsigned)n_tiles);
-    attention_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(tmq, tmkv, p);
-    SLB_LAUNCH_OK("attention_tc");
-    return SLB_OK;
 }

@@ -41,8 +41,11 @@ constexpr int kPlane = kTile * 64 * 2;           // one 128 x 64 fp16 plane tile
 constexpr int kOffQ = 0;                         // Q hi | lo           32 KB
 constexpr int kOffKV = 2 * kPlane;               // two slots of hi | lo  64 KB
 constexpr int kSlots = 2;
-constexpr int kOffXch = kOffKV + kSlots * 2 * kPlane;  // [2][128] floats: row max / row sum exchange between column halves
-constexpr int kOffBars = kOffXch + 2 * kTile * 4;
+constexpr int kOffStage = kOffKV + kSlots * 2 * kPlane;  // 2 KB per softmax warp: transpose of the output tile
+constexpr int kStageWarp = 2048;
+constexpr int kOffXch = kOffStage + kSoftmaxWarps * kStageWarp;  // [128] floats: row max / row sum exchange of the column halves
+constexpr int kOffBars = kOffXch + kTile * 4;
+static_assert(2 * (kOffBars + 128 + 1024) <= 228 * 1024, "two CTAs must fit an SM");
 constexpr size_t kSmem = (size_t)kOffBars + 128;
 constexpr float kLog2PScale = 10.0f;             // P planes carry 2^10 (hi + lo = 1024 p)
 
@@ -69,11 +72,11 @@ __device__ __forceinline__ void ts_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // MN-major operand tile (rows = K index, 128 B per row = 64 contiguous MN elements), 128-byte swizzle:
-// SBO = 1024 B between 8-row groups along K; LBO (between 64-element MN atoms) unused for N = 64.
-__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr) {
+// SBO = 1024 B between 8-row groups along K; LBO = bytes between 64-element MN atoms (unused for N = 64).
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr, uint32_t lbo) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(1024 >> 4) << 16;
+    d |= (uint64_t)(lbo >> 4) << 16;
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
@@ -103,6 +106,29 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// (x0, x1) -> packed fp16 hi and lo planes of SLB_ACT_PLANE_SCALE * x (fp16 planes): hi = the scaled value with its low
+// 13 mantissa bits cleared (exact in fp16 above the subnormal range), lo = the exact remainder rounded to fp16. Two packed
+// conversions per pair instead of four scalar ones and two back-conversions; saturates like slb_split2, NaN goes through.
+__device__ __forceinline__ void split_pair_act(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    x0 *= SLB_ACT_PLANE_SCALE;
+    x1 *= SLB_ACT_PLANE_SCALE;
+    if (x0 == x0) x0 = fminf(fmaxf(x0, -65504.0f), 65504.0f);
+    if (x1 == x1) x1 = fminf(fmaxf(x1, -65504.0f), 65504.0f);
+    const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+    const float h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+    const __half2 hp = __floats2half2_rn(h0, h1);
+    const __half2 lp = __floats2half2_rn(x0 - h0, x1 - h1);
+    hi = *reinterpret_cast<const uint32_t*>(&hp);
+    lo = *reinterpret_cast<const uint32_t*>(&lp);
+}
+
+// ask the TMA unit to bring a box into L2 (no shared-memory destination): hides the DRAM latency of the next work item
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -123,7 +149,6 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
     uint64_t* o_full = bars + 11;   // MMA -> softmax
     uint64_t* o_free = bars + 12;   // softmax (8 warps) -> MMA: O is in registers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-    float* xch = reinterpret_cast<float*>(smem + kOffXch);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = (p.T + kKeys - 1) / kKeys;
@@ -176,8 +201,20 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
                 ts_wait(q_empty, (uint32_t)(n & 1) ^ 1u);
                 slb_mbar_arrive_expect_tx(q_full, 2u * kPlane);
                 slb_tma_load_3d(smem + kOffQ, &tm, h * 64, row_base + tile * kTile, 0, q_full);
-                // ring items in consumption order: K_0 .. K_{n-1} (sweep 1), then K_0, V_0, K_1, V_1, ...; item t reuses
-                // the slot of item t - 2. K_{j+1} follows K_j (released by the S MMAs: early), V_{j+1} follows V_j.
+                {   // the ring only holds two blocks: start the NEXT item's operands on their way to L2 now
+                    const int nxt = item + (int)gridDim.x;
+                    if (nxt < p.n_items) {
+                        const int bh2 = nxt / p.n_tiles, b2 = bh2 / p.H, h2 = bh2 % p.H, rb2 = b2 * p.T;
+                        tma_prefetch_l2_3d(&tm, h2 * 64, rb2 + (nxt % p.n_tiles) * kTile, 0);
+                        for (int blk = 0; blk < nblk; ++blk) {
+                            tma_prefetch_l2_3d(&tm, p.W + h2 * 64, rb2 + blk * kKeys, 0);
+                            tma_prefetch_l2_3d(&tm, 2 * p.W + h2 * 64, rb2 + blk * kKeys, 0);
+                        }
+                    }
+                }
+                // ring items in consumption order: K_0 .. K_{n-1} (sweep 1), then — sweep 2 walks the blocks BACKWARDS, so
+                // the last K block of sweep 1 is reused in place — V_{n-1}, K_{n-2}, V_{n-2}, ..., K_0, V_0; item t reuses
+                // the slot of item t - 2 (a K slot is released by its S MMAs: early; a V slot by its P V MMAs).
                 int t_item = 0;
                 auto load_item = [&](int col, int row) {
                     const int slot = t % kSlots;
@@ -188,10 +225,11 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
                     ++t;
                     ++t_item;
                 };
-                for (int it = 0; it < n_iter; ++it) {
-                    const int blk = it % nblk;
-                    load_item(p.W + h * 64, row_base + blk * kKeys);
-                    if (it >= nblk) load_item(2 * p.W + h * 64, row_base + blk * kKeys);
+                for (int blk = 0; blk < nblk; ++blk) load_item(p.W + h * 64, row_base + blk * kKeys);  // sweep 1: K
+                for (int j = 0; j < nblk; ++j) {  // sweep 2, blocks in reverse order: K_{n-1} is still resident
+                    const int blk = nblk - 1 - j;
+                    if (j > 0) load_item(p.W + h * 64, row_base + blk * kKeys);
+                    load_item(2 * p.W + h * 64, row_base + blk * kKeys);
                 }
             }
         }
@@ -201,17 +239,19 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
             const uint32_t qa = slb_smem_u32(smem + kOffQ);
             const uint64_t dq_hi = slb_umma_desc_sw128(qa), dq_lo = slb_umma_desc_sw128(qa + kPlane);
             const uint64_t dk0 = slb_umma_desc_sw128(slb_smem_u32(smem + kOffKV));
-            const uint64_t dv0 = desc_mn_sw128(slb_smem_u32(smem + kOffKV));
-            const uint32_t idesc_o = slb_umma_idesc_f16(0, kTile, 64) | (1u << 16);  // B (= V) is MN-major
+            const uint32_t idesc_o = slb_umma_idesc_f16(0, kTile, 64) | (1u << 16);    // B (= V) is MN-major
+            const uint32_t idesc_o2 = slb_umma_idesc_f16(0, kTile, 128) | (1u << 16);  // B = [V hi | V lo]
             int t0 = 0;                 // ring items consumed by earlier work items
             int base[2] = {0, 0};       // S-buffer uses of earlier work items
             int pblk = 0;               // sweep-2 blocks of earlier work items
             int n = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
                 const bool trace_on = trace_cta && n == p.dbg_item;
-                auto item_k = [&](int it) { return t0 + (it < nblk ? it : nblk + 2 * (it - nblk)); };
+                // ring item holding the K block of iteration `it`; sweep 2 (j = it - nblk) reuses item nblk - 1 for j = 0
+                auto item_k = [&](int it) { return t0 + (it < nblk ? it : (it == nblk ? nblk - 1 : nblk + 2 * (it - nblk) - 1)); };
+                auto block_of = [&](int it) { return it < nblk ? it : n_iter - 1 - it; };
                 auto issue_s = [&](int it) {
-                    const int blk = it % nblk;
+                    const int blk = block_of(it);
                     const bool sweep2 = it >= nblk;
                     const int nk = keys_of(blk);
                     const int t = item_k(it), slot = t % kSlots;
@@ -237,29 +277,32 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
                         for (int k = 0; k < 4; ++k) slb_umma_f16(d, dq_hi + 2 * k, dk_hi + 2 * k, idesc_s, k != 0);
                     }
                     slb_umma_commit(&s_full[buf]);
-                    slb_umma_commit(&kv_empty[slot]);
-                    if (it == n_iter - 1) slb_umma_commit(q_empty);  // the item's last read of Q
+                    if (it != nblk - 1) slb_umma_commit(&kv_empty[slot]);  // sweep 1's last K block is read again by sweep 2
+                    if (it == n_iter - 1) slb_umma_commit(q_empty);        // the item's last read of Q
                 };
                 auto issue_pv = [&](int it) {
-                    const int blk = it - nblk;
+                    const int j = it - nblk, blk = block_of(it);
                     const int nk = keys_of(blk);
-                    const int t = item_k(it) + 1, slot = t % kSlots;
+                    const int t = t0 + nblk + 2 * j, slot = t % kSlots;
                     ts_wait(&kv_full[slot], (uint32_t)((t / kSlots) & 1));
-                    TS_TRACE(8, blk);  // V landed
-                    ts_wait(p_full, (uint32_t)((pblk + blk) & 1));
+                    TS_TRACE(8, j);  // V landed
+                    ts_wait(p_full, (uint32_t)((pblk + j) & 1));
                     slb_tc_fence_after();
-                    TS_TRACE(3, blk);  // P V issue
-                    const uint64_t dv_hi = dv0 + (uint64_t)(slot * (2 * kPlane >> 4)), dv_lo = dv_hi + (kPlane >> 4);
+                    TS_TRACE(3, j);  // P V issue
+                    const uint32_t va = slb_smem_u32(smem + kOffKV) + (uint32_t)(slot * 2 * kPlane);
+                    const uint64_t dv_hi = desc_mn_sw128(va, 1024), dv_both = desc_mn_sw128(va, kPlane);
                     const int ksteps = nk >> 4;
-                    // k-step s = keys [16 s, 16 s + 16): P hi at column 32 (s / 2) + 8 (s % 2), P lo 16 columns further
+                    // k-step s = keys [16 s, 16 s + 16): P hi at column 32 (s / 2) + 8 (s % 2), P lo 16 columns further.
+                    // Two MMAs per k-step: P hi . [V hi | V lo] (one N = 128 operand: the lo plane is the second MN atom,
+                    // kPlane bytes after the hi plane) -> [O main | O corr], then P lo . V hi -> O corr. (An N = 64 MMA takes as
+                    // long as an N = 128 one when it is issued from a single stream: scripts/micro/umma_rates.cu.)
 #pragma unroll
                     for (int s = 0; s < 8; ++s) {
                         if (s < ksteps) {
                             const uint32_t a_hi = tmem_base + (uint32_t)(32 * (s >> 1) + 8 * (s & 1)), a_lo = a_hi + 16;
                             const uint64_t koff = (uint64_t)((2048 >> 4) * s);
-                            umma_f16_ts(t_o, a_hi, dv_hi + koff, idesc_o, (blk | s) != 0);       // P hi . V hi -> main
-                            umma_f16_ts(t_o + 64, a_hi, dv_lo + koff, idesc_o, (blk | s) != 0);  // P hi . V lo -> corr
-                            umma_f16_ts(t_o + 64, a_lo, dv_hi + koff, idesc_o, true);            // P lo . V hi -> corr
+                            umma_f16_ts(t_o, a_hi, dv_both + koff, idesc_o2, (j | s) != 0);
+                            umma_f16_ts(t_o + 64, a_lo, dv_hi + koff, idesc_o, true);
                         }
                     }
                     slb_umma_commit(&kv_empty[slot]);
@@ -274,7 +317,7 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
                     if (it + 1 < n_iter) issue_s(it + 1);
                 }
                 slb_umma_commit(o_full);
-                t0 += 3 * nblk;
+                t0 += 3 * nblk - 1;
                 base[0] += uses0;
                 base[1] += uses1;
                 pblk += nblk;
@@ -288,6 +331,11 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         constexpr float kInvAct = 1.0f / SLB_ACT_PLANE_SCALE;
         const float c_main = p.scale_log2 * kInvAct * kInvAct;
+        // 2 KB of staging per warp; the two warps of a lane quarter (column halves 0 and 1) exchange row maxima / sums through
+        // one word per row: half 1 writes, barrier, half 0 combines and writes back, barrier, half 1 reads
+        unsigned char* stage_own = smem + kOffStage + (half * 4 + quarter) * kStageWarp;
+        float* xw = reinterpret_cast<float*>(smem + kOffXch) + r;
+        const int pair_bar = 1 + quarter;  // named barrier of the quarter's two warps
         int base[2] = {0, 0};
         int pblk = 0;
         int n = 0;
@@ -296,24 +344,24 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
             const int bh = item / p.n_tiles, tile = item % p.n_tiles;
             const int b = bh / p.H, h = bh % p.H;
             const int row_base = b * p.T;
-            const int row = tile * kTile + r;
             float m_row = -INFINITY, l_row = 0.f, neg_m = 0.f;
             for (int it = 0; it < n_iter; ++it) {
-                const int blk = it % nblk;
+                const int blk = it < nblk ? it : n_iter - 1 - it;  // sweep 2 walks the blocks backwards
                 const bool sweep2 = it >= nblk;
                 const int nk = keys_of(blk);
                 const int buf = s_buf(it), idx = base[buf] + s_idx(it);
                 const uint32_t t_s = tmem_base + lane_addr + (uint32_t)(buf * 128);
                 const bool full_block = (blk + 1) * kKeys <= p.T;
                 if (it == nblk) {
-                    // end of sweep 1: the two warps of a row combine their partial maxima (named barrier 1: softmax warps)
-                    if (half) xch[r] = m_row;
-                    asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
-                    if (!half) m_row = fmaxf(m_row, xch[r]);
-                    asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
-                    if (!half) xch[r] = m_row;
-                    asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
-                    m_row = xch[r];
+                    // end of sweep 1: the two warps of a row combine their partial maxima
+                    if (half) *xw = m_row;
+                    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                    if (!half) {
+                        m_row = fmaxf(m_row, *xw);
+                        *xw = m_row;
+                    }
+                    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                    if (half) m_row = *xw;
                     neg_m = kLog2PScale - m_row;  // exp2(s - m + 10) = 1024 p
                 }
                 ts_wait(&s_full[buf], (uint32_t)(idx & 1));
@@ -402,44 +450,55 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
             slb_tc_fence_before();
             __syncwarp();
             if (lane == 0) slb_mbar_arrive(o_free);
-            if (half) xch[kTile + r] = l_row;
-            asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
-            if (!half) xch[kTile + r] += l_row;
-            asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
-            l_row = xch[kTile + r];
+            if (half) *xw = l_row;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            if (!half) {
+                l_row += *xw;
+                *xw = l_row;
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            if (half) l_row = *xw;
             const float inv = kInvAct / l_row;  // V planes carry the activation scale, l_row the 2^10 of the P planes
-            const bool ok = row < p.T;
-            const int64_t out_base = ((int64_t)row_base + row) * p.W + (int64_t)h * 64;
-            if (ok) {
-                const int c = half * 32;
-                float o[32];
+            const int c = half * 32;
+            const int64_t tile_base = ((int64_t)row_base + tile * kTile + quarter * 32) * p.W + (int64_t)h * 64 + c;
+            const int rows_ok = p.T - (tile * kTile + quarter * 32);  // rows of this warp's 32 that exist
+            float o[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(a[j]) + __uint_as_float(cr[j])) * inv;
-                if (p.out_f32) {
+            for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(a[j]) + __uint_as_float(cr[j])) * inv;
+            if (p.out_f32 && lane < rows_ok) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        reinterpret_cast<float4*>(p.out_f32 + out_base + c)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                }
-                if (p.out_hi) {
+                for (int j = 0; j < 8; ++j)
+                    reinterpret_cast<float4*>(p.out_f32 + tile_base + (int64_t)lane * p.W)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+            if (p.out_hi) {
+                // thread = row would store 16 bytes to 32 different lines per instruction (the LSU serialises them: the
+                // epilogue was store-bound); the warp transposes through its staging region so that 4 lanes cover the 64
+                // bytes a row owns per plane: 8 rows per instruction. 16-byte chunk ch of row rr lives at
+                // rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4): conflict-free for both access patterns.
+                uint32_t hh[16], ll[16];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t hh[4], ll[4];
+                for (int e = 0; e < 16; ++e) split_pair_act(o[2 * e], o[2 * e + 1], hh[e], ll[e]);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            uint16_t h0, l0, h1, l1;
-                            slb_split2_act(o[8 * j + 2 * e], p.fmt, h0, l0);
-                            slb_split2_act(o[8 * j + 2 * e + 1], p.fmt, h1, l1);
-                            hh[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                            ll[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                        }
-                        *reinterpret_cast<uint4*>(p.out_hi + out_base + c + 8 * j) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-                        *reinterpret_cast<uint4*>(p.out_lo + out_base + c + 8 * j) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                for (int pl = 0; pl < 2; ++pl) {
+                    __syncwarp();  // the region's previous contents (the other plane) have been read
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const uint4 v = pl == 0 ? make_uint4(hh[4 * ch], hh[4 * ch + 1], hh[4 * ch + 2], hh[4 * ch + 3])
+                                                : make_uint4(ll[4 * ch], ll[4 * ch + 1], ll[4 * ch + 2], ll[4 * ch + 3]);
+                        *reinterpret_cast<uint4*>(stage_own + lane * 64 + ((ch ^ ((lane >> 1) & 3)) << 4)) = v;
+                    }
+                    __syncwarp();
+                    uint16_t* dst = pl == 0 ? p.out_hi : p.out_lo;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = i * 8 + (lane >> 2), ch = lane & 3;
+                        const uint4 v = *reinterpret_cast<const uint4*>(stage_own + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+                        if (rr < rows_ok) *reinterpret_cast<uint4*>(dst + tile_base + (int64_t)rr * p.W + ch * 8) = v;
                     }
                 }
+                __syncwarp();
             }
             TS_TRACE(9, 1);  // item done
-            // the row-sum exchange words are rewritten by the next item's epilogue only after its own barriers; the maxima
-            // words by its sweep 1 -> 2 transition, which follows this epilogue in program order of every warp
         }
     }
 

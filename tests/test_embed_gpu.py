@@ -76,7 +76,9 @@ def test_attention_vs_torch(ops, B, T, H, dh, gain):
                                        (2, 128, 2, 1.0), (2, 129, 2, 1.0), (1, 192, 3, 2.0), (1, 255, 1, 1.0), (1, 256, 2, 1.0),
                                        (1, 320, 2, 1.0), (9, 257, 16, 1.0), (2, 577, 2, 1.0),
                                        # tails of <= 16 rows split the keys over the warps; 17 rows do not
-                                       (2, 140, 2, 1.0), (3, 144, 1, 2.0), (1, 145, 2, 1.0), (2, 263, 3, 1.0)])
+                                       (2, 140, 2, 1.0), (3, 144, 1, 2.0), (1, 145, 2, 1.0), (2, 263, 3, 1.0),
+                                       # tails of <= 4 rows run as fp32 SIMT rows (one CTA per image and head)
+                                       (2, 131, 2, 1.0), (1, 260, 3, 2.0), (3, 132, 1, 1.0), (2, 133, 2, 1.0), (5, 385, 4, 1.0)])
 def test_attention_from_planes_vs_torch(ops, B, T, H, gain):
     """The tower's path: attention reads q | k | v from the in_proj GEMM's split planes (cp.async + ldmatrix + mma.sync)."""
     dh = 64
@@ -201,10 +203,8 @@ def test_openclip_wrapper_api():
         OpenClip("not-a-model")
     t = fm.encode_text(torch.zeros(1, 77, dtype=torch.long))  # image and text features share the embedding dimension
     assert t.shape == (1, 512) and torch.isfinite(t).all()
-    from semanticlens_b200.foundation_models import SigLipV2
-
-    with pytest.raises(NotImplementedError):
-        SigLipV2(device="cuda", load_weights=False).encode_text(torch.zeros(1, 64, dtype=torch.long))
+    with pytest.raises(ValueError, match="token ids"):
+        fm.encode_text(torch.zeros(1, 64, dtype=torch.long))  # a SigLIP-length sequence is not a CLIP one
 
 
 def test_preprocess_matches_reference_transform_on_pil():
@@ -330,7 +330,7 @@ def test_siglip_text_tower_vs_oracle(name, B):
 
 
 def _bpe_file(tmp_path):
-    from test_tokenizer import WORDS, learn_merges, write_bpe_file
+    from tests.bpe_fixture import WORDS, learn_merges, write_bpe_file
 
     return str(write_bpe_file(tmp_path / "bpe_simple_vocab_16e6.txt.gz", learn_merges(WORDS, 60), trailing=0))
 
