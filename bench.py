@@ -434,7 +434,7 @@ def run_b200(args):
     torch.cuda.empty_cache()
     sub = {}
     with_cpu = world == 1 and not args.no_cpu
-    for key, short in (("cfg3_step", "cfg3"), ("cfg4_step", "cfg4")):
+    for key, short in (("cfg3_step", "cfg3"), ("cfg4_step", "cfg4"), ("cfg2_accel_step", "cfg2a"), ("cfg4_accel_step", "cfg4a")):
         if short in wanted:
             sub[key] = run_step_config(key, dev, rank, world, pk, pk_src, with_cpu)
     if "cfg5" in wanted:
@@ -479,6 +479,16 @@ STEP_CONFIGS = {
                  "image-tower embed, synthetic 224x224 images",
         probed="resnet50_all_convs", agg="aggregate_conv_mean", fm="ViT-L-14", batch=128, steps=6, warmup=3,
         cpu_images=64, cpu_batch=16),
+    # The same workloads with the OPT-IN accelerated probed forward (semanticlens_b200/probed.py: the ResNet's convolutions
+    # on the package's tcgen05 GEMM instead of cuDNN fp32). Reported beside the strict-fp32 numbers, never instead of them.
+    "cfg2_accel_step": dict(
+        workload="cfg2 with accelerate=True: ResNet-50 probed at conv1,layer1..layer4 (aggregate_conv_mean, k=20) on the "
+                 "package's own convolution kernels + OpenCLIP ViT-B/32 image-tower embed, synthetic 224x224 images",
+        probed="resnet50", agg="aggregate_conv_mean", fm="ViT-B-32", batch=256, steps=10, warmup=3, accelerate=True),
+    "cfg4_accel_step": dict(
+        workload="cfg4 with accelerate=True: ResNet-50 probed at all 53 nn.Conv2d outputs (aggregate_conv_mean, k=20) on the "
+                 "package's own convolution kernels + OpenCLIP ViT-L/14 image-tower embed, synthetic 224x224 images",
+        probed="resnet50_all_convs", agg="aggregate_conv_mean", fm="ViT-L-14", batch=128, steps=6, warmup=3, accelerate=True),
 }
 
 
@@ -539,6 +549,13 @@ def run_step_config(key: str, dev, rank: int, world: int, pk: dict, pk_src: str,
     lib = _native.load(require_device=True)
     model, layers, kind = build_probed(spec["probed"])
     model = model.to(dev)
+    accel = bool(spec.get("accelerate"))
+    if accel:
+        from semanticlens_b200.probed import AcceleratedResNet
+
+        forward = AcceleratedResNet(model, dev)
+    else:
+        forward = model
     agg = getattr(A, spec["agg"])
     fm = OpenClip(spec["fm"], device=dev, load_weights=False, seed=1)
     S_fm = fm.cfg.image_size
@@ -557,7 +574,7 @@ def run_step_config(key: str, dev, rank: int, world: int, pk: dict, pk_src: str,
     collect_bytes = sum(4 * int(torch.tensor(shp[1:]).prod()) for shp in sizes.values())
 
     def step(i):
-        model(ring_f32[i % 3])
+        forward(ring_f32[i % 3])
         fm.encode_image(fm.preprocess(ring_u8[i % 3]))
 
     def sync():
@@ -594,18 +611,25 @@ def run_step_config(key: str, dev, rank: int, world: int, pk: dict, pk_src: str,
         picks = [n for i, n in enumerate(picks) if n not in picks[:i]]
         small = ActMaxCache(picks, agg, K_COLLECT)
         seen = {n: [] for n in picks}
-        taps = [m.register_forward_hook(lambda mod, i, o, n=n: seen[n].append(o.detach().float().cpu().numpy()))
+
+        def as_seen(o):
+            o = o.detach().float()
+            if accel:  # the accelerated forward hands out channels-last maps: K1 folds them in (B, HW, C) order
+                o = o.permute(0, 2, 3, 1).reshape(o.shape[0], -1, o.shape[1])
+            return o.cpu().numpy()
+
+        taps = [m.register_forward_hook(lambda mod, i, o, n=n: seen[n].append(as_seen(o)))
                 for n, m in model.named_modules() if n in picks]
         with torch.no_grad(), small.hook_context(model):
             for j in range(2):
-                model(ring_f32[j][:8])
+                forward(ring_f32[j][:8])
         for t in taps:
             t.remove()
         import numpy as np
 
         exact = True
         for n in picks:
-            st = oc.sweep(seen[n], "mean", kind, K_COLLECT)
+            st = oc.sweep(seen[n], "mean", "tokens" if accel else kind, K_COLLECT)
             got = small.cache[n].activations.view(torch.int16).numpy().view(np.uint16)
             exact &= bool((got == st.bits).all() and (small.cache[n].sample_ids.numpy() == st.ids).all())
         cfg_o, tower_o = _oracle_tower(fm)
@@ -617,6 +641,23 @@ def run_step_config(key: str, dev, rank: int, world: int, pk: dict, pk_src: str,
         parity = {"ok": bool(exact and err < 1e-4), "collect_layers": picks, "collect_values_and_ids_bit_exact": bool(exact),
                   "embed_max_rel_err_vs_fp32_oracle": err, "embed_tolerance": 1e-4,
                   "oracle": "oracle/collect.py (canonical order) + oracle/vit_port.py, same maps / same weights"}
+        if accel:
+            # the accelerated forward's maps against the torch (cuDNN fp32) forward's, same weights, same images
+            ref_maps = {}
+            taps = [m.register_forward_hook(lambda mod, i, o, n=n: ref_maps.__setitem__(n, o.detach().float().cpu()))
+                    for n, m in model.named_modules() if n in picks]
+            with torch.no_grad():
+                model(ring_f32[0][:8])
+            for t in taps:
+                t.remove()
+            worst = 0.0
+            for n in picks:
+                a = torch.from_numpy(seen[n][0])
+                b = ref_maps[n].permute(0, 2, 3, 1).reshape(a.shape)
+                worst = max(worst, float((a - b).abs().max() / b.abs().max()))
+            parity["probed_maps_max_rel_err_vs_torch_fp32"] = worst
+            parity["probed_maps_tolerance"] = 1e-4
+            parity["ok"] = bool(parity["ok"] and worst < 1e-4)
 
     rec = {
         "workload": spec["workload"], "value": world * K * B / (ms / 1e3), "unit": "images/s", "scaling": "weak",
@@ -625,9 +666,11 @@ def run_step_config(key: str, dev, rank: int, world: int, pk: dict, pk_src: str,
         "embed_flops_per_image": _fm_flops(fm), "data": "synthetic, device-resident ring of 3 batches (larger than L2)",
         "roofline": _roofline_from(kt, ms, K, pk, pk_src), "parity": parity,
     }
-    if with_cpu and rank == 0:
+    if with_cpu and rank == 0 and not accel:
         rec["cpu_baseline"] = _cpu_step_sample(spec, fm)
-    del model, fm, cache, ring_f32, ring_u8
+    if accel:
+        rec["probed_forward"] = "semanticlens_b200.probed.AcceleratedResNet (opt-in; default is the torch model)"
+    del model, fm, cache, ring_f32, ring_u8, forward
     torch.cuda.empty_cache()
     return rec
 
@@ -845,8 +888,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     ap.add_argument("--overlap", type=int, default=0, help="1: run the embed tower on a second stream under the sweep")
-    ap.add_argument("--configs", default="cfg3,cfg4,cfg5",
-                    help="sub-records measured after the headline: any of cfg3,cfg4,cfg5, or 'none'")
+    ap.add_argument("--configs", default="cfg3,cfg4,cfg5,cfg2a,cfg4a",
+                    help="sub-records measured after the headline: any of cfg3,cfg4,cfg5,cfg2a,cfg4a (a = opt-in accelerated "
+                         "probed forward), or 'none'")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -364,6 +364,36 @@ int slb_im2col3x3(const uint16_t* in_planes, int64_t B, int64_t H, int64_t W, in
 int slb_avgpool2_planes(const uint16_t* in_planes, int64_t B, int64_t H, int64_t W, int64_t C, int plane_fmt,
                         uint16_t* out_planes, void* stream);
 
+/* ---- accelerated probed-model forward (opt-in; semanticlens_b200/probed.py) -------------------------------------------
+ * The reference runs the user's probed model as `self.model(x)` under forward hooks (activation_based.py:341-358). For
+ * torchvision-style ResNets (Conv2d / BatchNorm2d / ReLU / MaxPool2d: the probed models of BASELINE configs[0..3]) the
+ * same maps can be produced by slb_gemm_split over channels-last planes; these entries are what that needs beyond the
+ * CLIP tower's. Hooked maps leave as channels-last fp32 (B, H*W, C), which slb_agg_reduce reads as SLB_LAYOUT_BTF. */
+
+/* im2col of a ksize x ksize / stride / pad convolution straight from NCHW fp32 images (the 7x7 / 2 / 3 stem):
+ * img (B,C,H,W) -> planes [2, B*Ho*Wo, slb_conv_k(C, ksize)], column (ky*ksize + kx)*C + c, zero outside / past C k k. */
+int slb_im2col_nchw(const float* img, int64_t B, int64_t C, int64_t H, int64_t W, int ksize, int stride, int pad, int plane_fmt,
+                    uint16_t* out_planes, void* stream);
+
+/* slb_im2col3x3 with a stride of 1 or 2 (pad 1): out [2, B*Ho*Wo, slb_conv_k(C, 3)], Ho = (H - 1) / stride + 1. */
+int slb_im2col3x3_strided(const uint16_t* in_planes, int64_t B, int64_t H, int64_t W, int64_t C, int stride, uint16_t* out_planes,
+                          void* stream);
+
+/* Every second pixel of every second row (the operand of a 1x1 / stride 2 convolution): [2, B*H*W, C] ->
+ * [2, B*ceil(H/2)*ceil(W/2), C]. */
+int slb_subsample2_planes(const uint16_t* in_planes, int64_t B, int64_t H, int64_t W, int64_t C, uint16_t* out_planes, void* stream);
+
+/* y = raw * scale[c] + shift[c] (+ residual), optional ReLU, over a channels-last fp32 map [M, C]: the BatchNorm / shortcut
+ * / ReLU that follows a convolution whose RAW output a forward hook has to see. out_f32 [M, C] and / or out_planes
+ * [2, M, C] (nullable); residual may alias out_f32. C % 8 == 0. */
+int slb_affine_act(const float* raw, int64_t M, int64_t C, const float* scale, const float* shift, const float* residual, int relu,
+                   int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream);
+
+/* BatchNorm (scale / shift) + ReLU + MaxPool2d(3, stride 2, pad 1) over a channels-last fp32 map (B, H, W, C) ->
+ * (B, Ho, Wo, C), Ho = (H - 1) / 2 + 1, as fp32 and / or planes (nullable). C % 8 == 0. */
+int slb_bn_relu_maxpool(const float* raw, int64_t B, int64_t H, int64_t W, int64_t C, const float* scale, const float* shift,
+                        int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream);
+
 /* Tokens of open_clip's AttentionPool2d: x (B, HW, C) fp32 channels-last feature map, pos (HW+1, C) ->
  * tok_planes [2, B*(HW+1), C] = [mean over positions; positions] + pos, and query_planes [2, B, C] = token 0 of
  * every image (the only query whose output is kept). */

@@ -96,6 +96,11 @@ _PROTOS = {
     "slb_im2col_stem": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "slb_im2col3x3": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "slb_avgpool2_planes": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "slb_im2col_nchw": (c_int, [c_void_p] + [c_int64] * 4 + [c_int] * 4 + [c_void_p, c_void_p]),
+    "slb_im2col3x3_strided": (c_int, [c_void_p] + [c_int64] * 4 + [c_int, c_void_p, c_void_p]),
+    "slb_subsample2_planes": (c_int, [c_void_p] + [c_int64] * 4 + [c_void_p, c_void_p]),
+    "slb_affine_act": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "slb_bn_relu_maxpool": (c_int, [c_void_p] + [c_int64] * 4 + [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "slb_pool_tokens": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "slb_rn_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "slb_rn_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -162,8 +162,13 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
         device=None,
         aggregate_fn=None,
         cache_dir: str | None = None,
+        accelerate: bool | None = None,
     ):
         self.model = model
+        # opt-in: run a torchvision-style ResNet on the package's own convolution kernels instead of torch's (probed.py).
+        # None = the SLB_ACCEL_FORWARD environment variable. Not part of the cache key: the maps agree to ~1e-5.
+        self.accelerate = accelerate
+        self._accel_forward = None
         self.dataset = dataset_model
         self.dataset_fm = dataset_fm
         self.output_device = "cpu"  # where _compute_concept_db leaves the (C, k, D) tensors
@@ -276,6 +281,17 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
             return self.actmax_cache.cache
         return self._run(batch_size=batch_size, num_workers=num_workers)
 
+    def _probed_forward(self, device):
+        """``self.model`` itself (the reference's ``self.model(x)``), or — opt-in, torchvision-style ResNets only — the
+        B200 forward that produces the hooked maps with the package's convolution kernels (probed.AcceleratedResNet)."""
+        from .. import probed
+
+        if not probed.accel_requested(self.accelerate):
+            return self.model
+        if self._accel_forward is None or self._accel_forward.device != torch.device(device):
+            self._accel_forward = probed.AcceleratedResNet(self.model, device)
+        return self._accel_forward
+
     @torch.no_grad()
     def _run(self, batch_size: int = 64, num_workers: int = 0):
         """The activation sweep (reference :341-358), image-sharded across ranks when distributed."""
@@ -288,12 +304,13 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
             for layer in self.layer_names:
                 self.actmax_cache.cache[layer] = type(self.actmax_cache.cache[layer])(self.actmax_cache.n_collect)
                 self.actmax_cache.sample_idx_counter[layer] = shard.lo
+        forward = self._probed_forward(device)
         with self.actmax_cache.hook_context(self.model):
             for images, _ in tqdm(
                 _DevicePrefetcher(dataloader, device), total=len(dataloader), desc="Collecting ActMax",
                 disable=not self.show_progress,
             ):
-                self.model(images.to(device, non_blocking=True))  # hooks enqueue K1+K2; nothing is copied back
+                forward(images.to(device, non_blocking=True))  # hooks enqueue K1+K2; nothing is copied back
 
         if shard.world > 1:
             sdist.merge_actmax_across_ranks(self.actmax_cache, device)

@@ -403,6 +403,90 @@ def avgpool2_planes(planes: torch.Tensor, B: int, H: int, W: int) -> torch.Tenso
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# accelerated probed-model forward (probed.py): torchvision-style ResNet pieces on channels-last planes
+# ------------------------------------------------------------------------------------------------
+def conv_out(n: int, k: int, stride: int, pad: int) -> int:
+    return (n + 2 * pad - k) // stride + 1
+
+
+def im2col_nchw(img: torch.Tensor, ksize: int, stride: int, pad: int, fmt: int = N.PLANE_F16) -> torch.Tensor:
+    """(B,C,H,W) fp32 -> planes (2, B*Ho*Wo, conv_k(C, ksize)) of a ksize x ksize / stride / pad convolution."""
+    lib = N.load(require_device=True)
+    N.require_cuda(img, "img")
+    img = img.float().contiguous()
+    B, C, H, W = img.shape
+    Ho, Wo = conv_out(H, ksize, stride, pad), conv_out(W, ksize, stride, pad)
+    out = torch.empty((2, B * Ho * Wo, conv_k(C, ksize)), dtype=PLANE_DTYPES[fmt], device=img.device)
+    with _dev_guard(img):
+        N.check(lib.slb_im2col_nchw(img.data_ptr(), B, C, H, W, ksize, stride, pad, fmt, out.data_ptr(), N.stream_ptr(img.device)),
+                "slb_im2col_nchw")
+    return out
+
+
+def im2col3x3_strided(planes: torch.Tensor, B: int, H: int, W: int, stride: int) -> torch.Tensor:
+    """channels-last planes (2, B*H*W, C) -> (2, B*Ho*Wo, conv_k(C, 3)) of a 3x3 / stride 1|2 / pad 1 convolution."""
+    lib = N.load(require_device=True)
+    N.require_cuda(planes, "planes")
+    assert planes.ndim == 3 and planes.shape[0] == 2 and planes.shape[1] == B * H * W and planes.is_contiguous()
+    C = planes.shape[2]
+    Ho, Wo = conv_out(H, 3, stride, 1), conv_out(W, 3, stride, 1)
+    out = torch.empty((2, B * Ho * Wo, conv_k(C, 3)), dtype=planes.dtype, device=planes.device)
+    with _dev_guard(planes):
+        N.check(lib.slb_im2col3x3_strided(planes.data_ptr(), B, H, W, C, stride, out.data_ptr(), N.stream_ptr(planes.device)),
+                "slb_im2col3x3_strided")
+    return out
+
+
+def subsample2_planes(planes: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+    lib = N.load(require_device=True)
+    N.require_cuda(planes, "planes")
+    assert planes.ndim == 3 and planes.shape[0] == 2 and planes.shape[1] == B * H * W and planes.is_contiguous()
+    C = planes.shape[2]
+    out = torch.empty((2, B * ((H + 1) // 2) * ((W + 1) // 2), C), dtype=planes.dtype, device=planes.device)
+    with _dev_guard(planes):
+        N.check(lib.slb_subsample2_planes(planes.data_ptr(), B, H, W, C, out.data_ptr(), N.stream_ptr(planes.device)),
+                "slb_subsample2_planes")
+    return out
+
+
+def affine_act(raw: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, residual: torch.Tensor | None = None, relu: bool = True,
+               fmt: int = N.PLANE_F16, out_f32: torch.Tensor | bool = False, out_planes: torch.Tensor | bool = True):
+    """y = act(raw * scale + shift (+ residual)) over a channels-last fp32 map (M, C). Returns (fp32 | None, planes | None)."""
+    lib = N.load(require_device=True)
+    N.require_cuda(raw, "raw")
+    assert raw.ndim == 2 and raw.dtype == torch.float32 and raw.is_contiguous()
+    M, C = raw.shape
+    if out_f32 is True:
+        out_f32 = torch.empty_like(raw)
+    elif out_f32 is False:
+        out_f32 = None
+    if out_planes is True:
+        out_planes = torch.empty((2, M, C), dtype=PLANE_DTYPES[fmt], device=raw.device)
+    elif out_planes is False:
+        out_planes = None
+    with _dev_guard(raw):
+        N.check(lib.slb_affine_act(raw.data_ptr(), M, C, scale.data_ptr(), shift.data_ptr(), N.ptr(residual), int(relu), fmt,
+                                   N.ptr(out_f32), N.ptr(out_planes), N.stream_ptr(raw.device)), "slb_affine_act")
+    return out_f32, out_planes
+
+
+def bn_relu_maxpool(raw: torch.Tensor, B: int, H: int, W: int, scale: torch.Tensor, shift: torch.Tensor, fmt: int = N.PLANE_F16,
+                    want_f32: bool = False):
+    """BatchNorm + ReLU + MaxPool2d(3, 2, 1) over a channels-last fp32 map (B*H*W, C) -> (fp32 | None, planes) of (B*Ho*Wo, C)."""
+    lib = N.load(require_device=True)
+    N.require_cuda(raw, "raw")
+    assert raw.ndim == 2 and raw.shape[0] == B * H * W and raw.dtype == torch.float32 and raw.is_contiguous()
+    C = raw.shape[1]
+    Mo = B * conv_out(H, 3, 2, 1) * conv_out(W, 3, 2, 1)
+    out32 = torch.empty((Mo, C), dtype=torch.float32, device=raw.device) if want_f32 else None
+    planes = torch.empty((2, Mo, C), dtype=PLANE_DTYPES[fmt], device=raw.device)
+    with _dev_guard(raw):
+        N.check(lib.slb_bn_relu_maxpool(raw.data_ptr(), B, H, W, C, scale.data_ptr(), shift.data_ptr(), fmt, N.ptr(out32),
+                                        planes.data_ptr(), N.stream_ptr(raw.device)), "slb_bn_relu_maxpool")
+    return out32, planes
+
+
 def pool_tokens(x: torch.Tensor, pos: torch.Tensor, fmt: int = N.PLANE_F16):
     """x (B, HW, C) fp32, pos (HW+1, C) -> (token planes (2, B*(HW+1), C), query planes (2, B, C))."""
     lib = N.load(require_device=True)

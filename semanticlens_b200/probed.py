@@ -1,0 +1,235 @@
+"""Opt-in B200 forward for the PROBED model when it is a torchvision-style ResNet.
+
+The reference sweeps the dataset through ``self.model(x)`` under forward hooks
+(``ActivationComponentVisualizer._run``, activation_based.py:341-358); the model is user code and by default this package
+leaves it to PyTorch (cuDNN fp32 — 88 % of the cfg-2 step). For ``torchvision.models.ResNet``
+(BasicBlock or Bottleneck: the probed models of BASELINE.json configs[0..3]) ``AcceleratedResNet`` produces the same maps
+with the package's own kernels: channels-last split planes, every convolution a tcgen05 ``slb_gemm_split`` with eval-mode
+BatchNorm / ReLU / shortcut in its epilogue (csrc/convnet.cu, csrc/gemm_tc.cu) — fp32-grade (22-bit operands, fp32
+accumulate: ~1e-5 of the largest activation after 50 layers, measured in tests/test_probed_gpu.py), not bit-identical to
+cuDNN's fp32, hence opt-in: ``ActivationComponentVisualizer(..., accelerate=True)`` or ``SLB_ACCEL_FORWARD=1``.
+
+Hooks keep working: whatever forward hooks are registered on the model's modules (the ones ``ActMaxCache`` installs) are
+called with the module's output as a ``(B, C, H, W)`` tensor in channels-last memory, which K1 reads in place. Supported
+hook points: every ``nn.Conv2d`` (its raw output, before BatchNorm), ``maxpool``, every residual block and ``layer1..4``.
+The forward stops after the last hooked module (the reference discards the logits).
+"""
+
+from __future__ import annotations
+
+import os
+
+import torch
+from torch import nn
+
+from . import _native as N
+from . import ops
+
+ALPHA = 1.0 / (N.ACT_PLANE_SCALE * N.WEIGHT_PLANE_SCALE)
+
+
+def accel_requested(flag) -> bool:
+    """``accelerate=`` of the visualizer: True / False, or None = the SLB_ACCEL_FORWARD environment variable."""
+    if flag is None:
+        return os.environ.get("SLB_ACCEL_FORWARD", "0") == "1"
+    return bool(flag)
+
+
+class _Conv:
+    """One convolution + its BatchNorm as GEMM operands: weight planes (Cout, conv_k(Cin, k)) with columns ordered
+    (ky, kx, cin) like the im2col kernels, scale = gamma / sqrt(var + eps), shift = beta - mean * scale (folded in float64)."""
+
+    def __init__(self, conv: nn.Conv2d, bn: nn.BatchNorm2d | None, device, fmt: int):
+        k = conv.kernel_size[0]
+        ok = (conv.kernel_size[0] == conv.kernel_size[1] and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
+              and conv.groups == 1 and conv.dilation == (1, 1) and conv.padding_mode == "zeros" and conv.out_channels % 8 == 0)
+        if not ok:
+            raise NotImplementedError(f"accelerated forward: unsupported convolution {conv}")
+        self.module = conv
+        self.k, self.stride, self.pad = k, conv.stride[0], conv.padding[0]
+        self.cin, self.cout = conv.in_channels, conv.out_channels
+        w = conv.weight.detach().to(torch.float32).cpu()
+        kk = ops.conv_k(self.cin, k)
+        mat = torch.zeros((self.cout, kk), dtype=torch.float32)
+        mat[:, : self.cin * k * k] = w.permute(0, 2, 3, 1).reshape(self.cout, -1)
+        self.w = ops.split_planes(mat.to(device), fmt, N.WEIGHT_PLANE_SCALE)
+        self.bias = None if conv.bias is None else conv.bias.detach().to(device=device, dtype=torch.float32).contiguous()
+        if bn is None:
+            scale = torch.ones(self.cout, dtype=torch.float64)
+            shift = torch.zeros(self.cout, dtype=torch.float64)
+        else:
+            if bn.training or bn.running_mean is None:
+                raise NotImplementedError("accelerated forward: BatchNorm2d must be in eval mode with running statistics")
+            gamma = bn.weight.detach().double().cpu() if bn.affine else torch.ones(self.cout, dtype=torch.float64)
+            beta = bn.bias.detach().double().cpu() if bn.affine else torch.zeros(self.cout, dtype=torch.float64)
+            scale = gamma / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
+            shift = beta - bn.running_mean.detach().double().cpu() * scale
+        if conv.bias is not None:
+            shift = shift + conv.bias.detach().double().cpu() * scale
+        self.scale = scale.float().to(device).contiguous()
+        self.shift = shift.float().to(device).contiguous()
+
+
+def _fire(module: nn.Module, out: torch.Tensor) -> None:
+    for hook in list(module._forward_hooks.values()):
+        hook(module, (), out)
+
+
+def _as_nchw(map32: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+    """(B*H*W, C) fp32 -> a (B, C, H, W) view in channels-last memory (what a hook receives; K1 reads it in place)."""
+    return map32.view(B, H, W, map32.shape[1]).permute(0, 3, 1, 2)
+
+
+class AcceleratedResNet:
+    """Runs a ``torchvision.models.ResNet`` (eval mode) on the B200 kernels and calls the forward hooks registered on its
+    modules. ``passes``: ``N.PASSES_SPLIT_ACC`` (default; cross terms in their own accumulator, as the CLIP ResNet tower)
+    or 3 (single accumulator: the faster CTA-pair tiles, ~3x the error)."""
+
+    def __init__(self, model: nn.Module, device=None, plane_format: str = "f16", passes: int | None = None):
+        N.load(require_device=True)
+        need = ("conv1", "bn1", "maxpool", "layer1", "layer2", "layer3", "layer4")
+        if not all(hasattr(model, n) for n in need):
+            raise NotImplementedError("accelerated forward: expected a torchvision-style ResNet (conv1, bn1, maxpool, layer1..4)")
+        if model.training:
+            raise NotImplementedError("accelerated forward: put the model in eval mode (BatchNorm uses running statistics)")
+        mp = model.maxpool
+        if not (isinstance(mp, nn.MaxPool2d) and mp.kernel_size in (3, (3, 3)) and mp.stride in (2, (2, 2))
+                and mp.padding in (1, (1, 1)) and mp.dilation in (1, (1, 1)) and not mp.ceil_mode):
+            raise NotImplementedError(f"accelerated forward: unsupported pooling {mp}")
+        self.model = model
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise N.SlbError("the accelerated forward runs on a CUDA device (there is no CPU fallback)")
+        self.fmt = {"f16": N.PLANE_F16, "bf16": N.PLANE_BF16}[plane_format]
+        self.passes = passes if passes is not None else (3 if os.environ.get("SLB_ACCEL_FAST", "0") == "1" else N.PASSES_SPLIT_ACC)
+        dev, fmt = self.device, self.fmt
+        self.stem = _Conv(model.conv1, model.bn1, dev, fmt)
+        self.blocks = []  # (block module, kind, convs..., downsample | None, owning layer if it is the layer's last block)
+        for lname in ("layer1", "layer2", "layer3", "layer4"):
+            layer = getattr(model, lname)
+            blocks = list(layer.children())
+            for i, blk in enumerate(blocks):
+                ds = None
+                if getattr(blk, "downsample", None) is not None:
+                    d = list(blk.downsample.children())
+                    if len(d) != 2 or not isinstance(d[0], nn.Conv2d) or not isinstance(d[1], nn.BatchNorm2d):
+                        raise NotImplementedError(f"accelerated forward: unsupported shortcut {blk.downsample}")
+                    ds = _Conv(d[0], d[1], dev, fmt)
+                if hasattr(blk, "conv3"):
+                    convs = [_Conv(blk.conv1, blk.bn1, dev, fmt), _Conv(blk.conv2, blk.bn2, dev, fmt), _Conv(blk.conv3, blk.bn3, dev, fmt)]
+                    kind = "bottleneck"
+                elif hasattr(blk, "conv2"):
+                    convs = [_Conv(blk.conv1, blk.bn1, dev, fmt), _Conv(blk.conv2, blk.bn2, dev, fmt)]
+                    kind = "basic"
+                else:
+                    raise NotImplementedError(f"accelerated forward: unsupported block {type(blk).__name__}")
+                self.blocks.append((blk, kind, convs, ds, layer if i == len(blocks) - 1 else None))
+        # modules whose output this forward can hand to a hook
+        self._tappable = {id(self.stem.module), id(model.maxpool)}
+        for blk, _kind, convs, ds, layer in self.blocks:
+            self._tappable.add(id(blk))
+            self._tappable.update(id(c.module) for c in convs)
+            if ds is not None:
+                self._tappable.add(id(ds.module))
+            if layer is not None:
+                self._tappable.add(id(layer))
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _hooked(self, module: nn.Module) -> bool:
+        return len(module._forward_hooks) > 0
+
+    def check_hooks(self) -> None:
+        """Every module carrying a forward hook must be one whose output this forward materialises."""
+        for name, m in self.model.named_modules():
+            if len(m._forward_hooks) and id(m) not in self._tappable:
+                raise NotImplementedError(
+                    f"accelerated forward: cannot expose the output of '{name}' ({type(m).__name__}); hook a Conv2d, maxpool, a "
+                    "residual block or layer1..4, or run with accelerate=False")
+
+    def _conv(self, c: _Conv, a_planes, B, H, W, *, relu, residual=None, want_f32=False, out_f32=None, want_planes=True):
+        """One convolution over operand planes `a_planes` (already im2col'ed / subsampled): BatchNorm + optional shortcut +
+        optional ReLU. Returns (fp32 map | None, planes). A hooked convolution leaves its raw output first."""
+        epi = (N.EPI_ADD_RELU if residual is not None else N.EPI_RELU) if relu else N.EPI_NONE
+        if self._hooked(c.module):
+            raw, _ = ops.gemm_split(a_planes, c.w, bias=c.bias, alpha=ALPHA, epilogue=N.EPI_NONE, passes=self.passes)
+            _fire(c.module, _as_nchw(raw, B, H, W))
+            shift = c.shift if c.bias is None else (c.shift - c.bias * c.scale)  # raw already holds the bias
+            keep32 = out_f32 if out_f32 is not None else bool(want_f32)
+            return ops.affine_act(raw, c.scale, shift, residual=residual, relu=relu, fmt=self.fmt, out_f32=keep32, out_planes=want_planes)
+        if residual is not None and not relu:
+            raise AssertionError("a shortcut add is always followed by the ReLU in a ResNet block")
+        keep32 = out_f32 if out_f32 is not None else bool(want_f32)
+        return ops.gemm_split(a_planes, c.w, bias=c.shift, residual=residual, col_scale=c.scale, alpha=ALPHA, epilogue=epi,
+                              passes=self.passes, out_f32=keep32, out_planes=want_planes)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, logits: bool = False):
+        """x (B, 3, H, W) fp32 on the device. Fires the registered hooks; returns the logits (``logits=True``: the global
+        pool and ``fc`` run in torch on the last map) or None."""
+        self.check_hooks()
+        m = self.model
+        x = x.to(self.device, dtype=torch.float32).contiguous()
+        B, _, H, W = x.shape
+        last = None  # index of the last block that must run
+        if not logits:
+            hooked = {id(mod) for mod in m.modules() if len(mod._forward_hooks)}
+            for i, (blk, _kind, convs, ds, layer) in enumerate(self.blocks):
+                ids = {id(blk)} | {id(c.module) for c in convs} | ({id(ds.module)} if ds else set()) | ({id(layer)} if layer else set())
+                if ids & hooked:
+                    last = i
+        else:
+            last = len(self.blocks) - 1
+        # ---- stem: k x k / stride conv from NCHW, raw map (hook point), BatchNorm + ReLU + MaxPool in one pass ----
+        st = self.stem
+        col = ops.im2col_nchw(x, st.k, st.stride, st.pad, self.fmt)
+        H, W = ops.conv_out(H, st.k, st.stride, st.pad), ops.conv_out(W, st.k, st.stride, st.pad)
+        raw, _ = ops.gemm_split(col, st.w, bias=st.bias, alpha=ALPHA, epilogue=N.EPI_NONE, passes=self.passes)
+        del col
+        if self._hooked(st.module):
+            _fire(st.module, _as_nchw(raw, B, H, W))
+        if last is None and not self._hooked(m.maxpool):
+            return None
+        first_needs_identity = self.blocks[0][3] is None
+        shift = st.shift if st.bias is None else (st.shift - st.bias * st.scale)
+        x32, xpl = ops.bn_relu_maxpool(raw, B, H, W, st.scale, shift, self.fmt, want_f32=first_needs_identity or self._hooked(m.maxpool))
+        del raw
+        H, W = ops.conv_out(H, 3, 2, 1), ops.conv_out(W, 3, 2, 1)
+        if self._hooked(m.maxpool):
+            _fire(m.maxpool, _as_nchw(x32, B, H, W))
+        if last is None:
+            return None
+        # ---- residual blocks ----
+        for i, (blk, kind, convs, ds, layer) in enumerate(self.blocks[: last + 1]):
+            stride = convs[1].stride if kind == "bottleneck" else convs[0].stride
+            Ho, Wo = (ops.conv_out(H, 3, stride, 1), ops.conv_out(W, 3, stride, 1))
+            # shortcut
+            if ds is not None:
+                xs = ops.subsample2_planes(xpl, B, H, W) if ds.stride == 2 else xpl
+                idf, _ = self._conv(ds, xs, B, Ho, Wo, relu=False, want_f32=True, want_planes=False)
+            else:
+                idf = x32
+            if kind == "bottleneck":
+                if convs[0].stride != 1 or convs[2].stride != 1:
+                    raise NotImplementedError("accelerated forward: the stride of a Bottleneck must sit in conv2 (torchvision v1.5)")
+                _, t1 = self._conv(convs[0], xpl, B, H, W, relu=True)
+                col = ops.im2col3x3_strided(t1, B, H, W, stride)
+                _, t2 = self._conv(convs[1], col, B, Ho, Wo, relu=True)
+                del col, t1
+                x32, xpl = self._conv(convs[2], t2, B, Ho, Wo, relu=True, residual=idf, out_f32=idf)
+            else:
+                col = ops.im2col3x3_strided(xpl, B, H, W, stride)
+                _, t1 = self._conv(convs[0], col, B, Ho, Wo, relu=True)
+                col = ops.im2col3x3_strided(t1, B, Ho, Wo, 1)
+                x32, xpl = self._conv(convs[1], col, B, Ho, Wo, relu=True, residual=idf, out_f32=idf)
+                del col, t1
+            H, W = Ho, Wo
+            if self._hooked(blk):
+                _fire(blk, _as_nchw(x32, B, H, W))
+            if layer is not None and self._hooked(layer):
+                _fire(layer, _as_nchw(x32, B, H, W))
+        if not logits:
+            return None
+        feat = x32.view(B, H * W, -1).mean(dim=1)
+        return m.fc(feat) if hasattr(m, "fc") else feat
+
+    __call__ = forward

@@ -30,21 +30,25 @@ REL_FLOOR = 1e-7
 GPU_NOISE_CEILING = 2e-5
 
 
-def _tap(model, layers, batches, to):
+def _tap(model, layers, batches, to, forward=None):
     seen = {n: [] for n in layers}
     mods = dict(model.named_modules())
     taps = [mods[n].register_forward_hook(lambda m, i, o, n=n: seen[n].append(to(o.detach()))) for n in layers]
     with torch.no_grad():
         for x in batches:
-            model(x)
+            (forward or model)(x)
     for t in taps:
         t.remove()
     return seen
 
 
-def check_collect_contract(net_cpu, layers, batches_cpu, op, kind, k, gpu_state, ref_state, device="cuda"):
+def check_collect_contract(net_cpu, layers, batches_cpu, op, kind, k, gpu_state, ref_state, device="cuda", gpu_forward=None,
+                           noise_ceiling=GPU_NOISE_CEILING):
     """net_cpu: the probed model on the CPU (fp32). batches_cpu: list of fp32 input batches in sweep order.
-    gpu_state / ref_state: {layer: (bits uint16 (C,k), ids int64 (C,k))}. Returns a per-layer report."""
+    gpu_state / ref_state: {layer: (bits uint16 (C,k), ids int64 (C,k))}. Returns a per-layer report.
+    gpu_forward: factory(model on the device) -> callable that runs the forward and fires the model's hooks (the opt-in
+    accelerated forward, probed.AcceleratedResNet); default: the torch model itself. noise_ceiling: the fp32-grade bar of
+    the GPU forward (22-bit-operand convolutions sit a little above cuDNN's fp32)."""
     from semanticlens_b200 import _native as N
     from semanticlens_b200 import ops
 
@@ -53,7 +57,8 @@ def check_collect_contract(net_cpu, layers, batches_cpu, op, kind, k, gpu_state,
     maps64 = _tap(net64, layers, [b.double() for b in batches_cpu], lambda o: o.numpy())
     maps32 = _tap(net_cpu, layers, batches_cpu, lambda o: o.numpy())
     net_gpu = copy.deepcopy(net_cpu).to(device)
-    agg_gpu = _tap(net_gpu, layers, [b.to(device) for b in batches_cpu], lambda o: ops.agg_reduce(o, opcode, kind).cpu().numpy())
+    agg_gpu = _tap(net_gpu, layers, [b.to(device) for b in batches_cpu], lambda o: ops.agg_reduce(o, opcode, kind).cpu().numpy(),
+                   forward=gpu_forward(net_gpu) if gpu_forward else None)
     report = {}
     for name in layers:
         m64 = np.concatenate(maps64[name])
@@ -70,7 +75,7 @@ def check_collect_contract(net_cpu, layers, batches_cpu, op, kind, k, gpu_state,
         # layer-level sanity (the median over channels: a nearly dead post-ReLU channel has a tiny scale but inherits the
         # noise of its pre-activation, so single channels can sit far above the typical ratio)
         ratio = np.median(sigma_gpu / (scale + 1e-30))
-        assert ratio <= GPU_NOISE_CEILING, f"{name}: the GPU forward is not fp32-grade: median noise / scale = {ratio:.2e}"
+        assert ratio <= noise_ceiling, f"{name}: the GPU forward is not fp32-grade: median noise / scale = {ratio:.2e}"
         tau = SIGMAS * np.maximum(np.maximum(sigma_cpu, sigma_gpu), REL_FLOOR * scale)  # (1, C)
         excused = oc.f32_to_bf16_bits((a64 - tau).astype(np.float32)) != oc.f32_to_bf16_bits((a64 + tau).astype(np.float32))
         cand_cpu = oc.f32_to_bf16_bits(agg_cpu)
