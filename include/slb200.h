@@ -370,6 +370,15 @@ int slb_avgpool2_planes(const uint16_t* in_planes, int64_t B, int64_t H, int64_t
  * same maps can be produced by slb_gemm_split over channels-last planes; these entries are what that needs beyond the
  * CLIP tower's. Hooked maps leave as channels-last fp32 (B, H*W, C), which slb_agg_reduce reads as SLB_LAYOUT_BTF. */
 
+/* Implicit-GEMM convolution: out[(b, yo, xo), n] = epi(alpha * sum_{ky,kx,c} x[b, yo*stride + ky - pad, xo*stride + kx - pad, c]
+ * * w[n, (ky*ksize + kx)*C + c] * col_scale[n] + bias[n]) (+ residual), the arguments of slb_gemm_split otherwise. x_planes
+ * [2, B*H*W, C] channels-last; w_planes [2, N, ksize*ksize*C]. The im2col matrix is never written: the GEMM's producer warp
+ * fetches (filter tap, 64-channel chunk) k-blocks with TMA im2col-mode loads (zero fill outside the image, stride in the
+ * tensor map's traversal strides). C % 64 == 0, N % 8 == 0, stride 1 or 2, ksize <= 7. */
+int slb_conv_gemm(const uint16_t* x_planes, int64_t B, int64_t H, int64_t W, int64_t C, int ksize, int stride, int pad,
+                  const uint16_t* w_planes, int64_t N, int plane_fmt, float alpha, const float* bias, const float* residual,
+                  const float* col_scale, int epilogue, int passes, float* out_f32, uint16_t* out_planes, void* stream);
+
 /* im2col of a ksize x ksize / stride / pad convolution straight from NCHW fp32 images (the 7x7 / 2 / 3 stem):
  * img (B,C,H,W) -> planes [2, B*Ho*Wo, slb_conv_k(C, ksize)], column (ky*ksize + kx)*C + c, zero outside / past C k k. */
 int slb_im2col_nchw(const float* img, int64_t B, int64_t C, int64_t H, int64_t W, int ksize, int stride, int pad, int plane_fmt,

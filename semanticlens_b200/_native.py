@@ -96,6 +96,8 @@ _PROTOS = {
     "slb_im2col_stem": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "slb_im2col3x3": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "slb_avgpool2_planes": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "slb_conv_gemm": (c_int, [c_void_p] + [c_int64] * 4 + [c_int] * 3 + [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                               c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "slb_im2col_nchw": (c_int, [c_void_p] + [c_int64] * 4 + [c_int] * 4 + [c_void_p, c_void_p]),
     "slb_im2col3x3_strided": (c_int, [c_void_p] + [c_int64] * 4 + [c_int, c_void_p, c_void_p]),
     "slb_subsample2_planes": (c_int, [c_void_p] + [c_int64] * 4 + [c_void_p, c_void_p]),

@@ -6,8 +6,9 @@
 //
 // Data layout: activations are channels-last split planes [2, B*H*W, C] at SLB_ACT_PLANE_SCALE. That makes every 1x1
 // convolution (two thirds of the convolutions, 60 % of the flops) exactly slb_gemm_split over the activation planes —
-// TMA-fed tcgen05 tiles, no data movement — and a 3x3 convolution the same GEMM over im2col planes written by a
-// 16-byte gather kernel (the im2col matrix is 9x the activation but only the narrow bottleneck channels go through it).
+// TMA-fed tcgen05 tiles, no data movement — and a 3x3 convolution of the bottlenecks an IMPLICIT GEMM (slb_conv_gemm: the
+// producer warp fetches (filter tap, 64-channel chunk) k-blocks with TMA im2col-mode loads; the 9x im2col matrix of
+// round 1 — 97 MB per image — is gone). Only the stem's 32-channel 3x3 convolutions still go through im2col planes.
 // Eval-mode BatchNorm, ReLU and the shortcut add are GEMM epilogues (col_scale / bias / SLB_EPI_RELU / SLB_EPI_ADD_RELU);
 // the block output is written both as planes (operand of the next block) and fp32 (its shortcut).
 // No allocation: caller-supplied workspace (slb_rn_workspace_bytes). Nothing synchronises.
@@ -26,6 +27,14 @@ int rn_passes() {
     static const int v = [] {
         const char* e = getenv("SLB_RN_FAST");
         return (e && e[0] == '1') ? 3 : SLB_PASSES_SPLIT_ACC;
+    }();
+    return v;
+}
+
+bool rn_explicit_im2col() {
+    static const bool v = [] {
+        const char* e = getenv("SLB_RN_IM2COL");
+        return e && e[0] == '1';
     }();
     return v;
 }
@@ -374,8 +383,14 @@ extern "C" int slb_rn_forward(const SlbRnWeights* w, const float* img, int64_t B
                             (!ds || (cv[3].cin == inpl && cv[3].cout == 4 * pl && cv[3].ksize == 1)),
                         SLB_EINVAL, "slb_rn_forward: stage %d bottleneck %d has unexpected convolution shapes", li + 1, bi);
             SLB_TRY(conv(cv[0], x_cur, M, SLB_EPI_RELU, nullptr, nullptr, t1));
-            SLB_TRY(slb_im2col3x3(t1, B, H, H, pl, col, stream));
-            SLB_TRY(conv(cv[1], col, M, SLB_EPI_RELU, nullptr, nullptr, t2));
+            // the 3x3 convolution as an implicit GEMM (TMA im2col-mode loads; no 9x matrix); SLB_RN_IM2COL=1: the explicit path
+            if (pl % 64 == 0 && !rn_explicit_im2col()) {
+                SLB_TRY(slb_conv_gemm(t1, B, H, H, pl, 3, 1, 1, cv[1].w, cv[1].cout, fmt, kAlpha, cv[1].shift, nullptr, cv[1].scale,
+                                      SLB_EPI_RELU, kPasses, nullptr, t2, stream));
+            } else {
+                SLB_TRY(slb_im2col3x3(t1, B, H, H, pl, col, stream));
+                SLB_TRY(conv(cv[1], col, M, SLB_EPI_RELU, nullptr, nullptr, t2));
+            }
             const uint16_t* main_in = t2;
             const uint16_t* short_in = x_cur;
             if (stride == 2) {

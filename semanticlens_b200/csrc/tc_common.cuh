@@ -15,6 +15,11 @@ slb_tmap_encode_fn slb_get_tmap_encoder();  // nullptr (+ error string) if the d
 // 3-D map over 16-bit planes [planes][rows][cols] (cols contiguous); box = {64 cols, box_rows, planes}; 128B swizzle.
 int slb_make_plane_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int planes, int box_rows);
 
+// im2col-mode map over ONE channels-last 16-bit plane (B, H, W, C) for a ksize x ksize / stride / pad convolution: a load
+// brings `pixels` consecutive output pixels x 64 channels of one filter tap (128B swizzle, zero fill outside the image).
+int slb_make_im2col_map(CUtensorMap* out, const void* base, int64_t B, int64_t H, int64_t W, int64_t C, int ksize, int stride,
+                        int pad, int pixels);
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // device: TMA
@@ -29,6 +34,17 @@ __device__ __forceinline__ void slb_tma_load_3d(void* smem_dst, const CUtensorMa
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(slb_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2),
         "r"(slb_smem_u32(bar))
+        : "memory");
+}
+
+// im2col-mode load: {c, w, h, n} = channel offset and the coordinates of the FIRST output pixel's window corner in the
+// input (w = column * stride - pad, ...); {off_w, off_h} = the filter tap. The TMA unit steps through the output pixels.
+__device__ __forceinline__ void slb_tma_load_im2col_4d(void* smem_dst, const CUtensorMap* m, int c, int w, int h, int n,
+                                                       uint16_t off_w, uint16_t off_h, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6], {%7, %8};"
+        ::"r"(slb_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c), "r"(w), "r"(h), "r"(n), "r"(slb_smem_u32(bar)),
+        "h"(off_w), "h"(off_h)
         : "memory");
 }
 

@@ -424,6 +424,42 @@ def im2col_nchw(img: torch.Tensor, ksize: int, stride: int, pad: int, fmt: int =
     return out
 
 
+def conv_gemm(x_planes: torch.Tensor, B: int, H: int, W: int, w_planes: torch.Tensor, ksize: int, stride: int, pad: int, *,
+              bias: torch.Tensor | None = None, residual: torch.Tensor | None = None, col_scale: torch.Tensor | None = None,
+              epilogue: int = N.EPI_NONE, passes: int = 3, alpha: float = 1.0, out_f32: torch.Tensor | bool = True,
+              out_planes: torch.Tensor | bool = False):
+    """Implicit-GEMM convolution over channels-last planes (2, B*H*W, C) with weights (2, Cout, ksize*ksize*C), columns
+    ordered (ky, kx, c). No im2col matrix: TMA im2col-mode loads feed the tcgen05 GEMM. Returns (fp32 | None, planes | None)
+    of shape (B*Ho*Wo, Cout)."""
+    lib = N.load(require_device=True)
+    N.require_cuda(x_planes, "x_planes")
+    assert x_planes.ndim == 3 and x_planes.shape[0] == 2 and x_planes.shape[1] == B * H * W and x_planes.is_contiguous()
+    C = x_planes.shape[2]
+    assert w_planes.ndim == 3 and w_planes.shape[0] == 2 and w_planes.shape[2] == ksize * ksize * C and w_planes.is_contiguous()
+    assert w_planes.dtype == x_planes.dtype
+    Nn = w_planes.shape[1]
+    fmt = N.PLANE_F16 if x_planes.dtype == torch.float16 else N.PLANE_BF16
+    M = B * conv_out(H, ksize, stride, pad) * conv_out(W, ksize, stride, pad)
+    dev = x_planes.device
+    if out_f32 is True:
+        out_f32 = torch.empty((M, Nn), dtype=torch.float32, device=dev)
+    elif out_f32 is False:
+        out_f32 = None
+    if out_planes is True:
+        out_planes = torch.empty((2, M, Nn), dtype=x_planes.dtype, device=dev)
+    elif out_planes is False:
+        out_planes = None
+    for t, shape in ((bias, (Nn,)), (residual, (M, Nn)), (col_scale, (Nn,)), (out_f32, (M, Nn))):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape, (t.shape, shape)
+    with _dev_guard(x_planes):
+        rc = lib.slb_conv_gemm(x_planes.data_ptr(), B, H, W, C, ksize, stride, pad, w_planes.data_ptr(), Nn, fmt, float(alpha),
+                               N.ptr(bias), N.ptr(residual), N.ptr(col_scale), epilogue, passes, N.ptr(out_f32), N.ptr(out_planes),
+                               N.stream_ptr(dev))
+    N.check(rc, "slb_conv_gemm")
+    return out_f32, out_planes
+
+
 def im2col3x3_strided(planes: torch.Tensor, B: int, H: int, W: int, stride: int) -> torch.Tensor:
     """channels-last planes (2, B*H*W, C) -> (2, B*Ho*Wo, conv_k(C, 3)) of a 3x3 / stride 1|2 / pad 1 convolution."""
     lib = N.load(require_device=True)

@@ -102,6 +102,7 @@ class AcceleratedResNet:
             raise N.SlbError("the accelerated forward runs on a CUDA device (there is no CPU fallback)")
         self.fmt = {"f16": N.PLANE_F16, "bf16": N.PLANE_BF16}[plane_format]
         self.passes = passes if passes is not None else (3 if os.environ.get("SLB_ACCEL_FAST", "0") == "1" else N.PASSES_SPLIT_ACC)
+        self.explicit_im2col = os.environ.get("SLB_ACCEL_IM2COL", "0") == "1"  # debugging: materialise the im2col matrices
         dev, fmt = self.device, self.fmt
         self.stem = _Conv(model.conv1, model.bn1, dev, fmt)
         self.blocks = []  # (block module, kind, convs..., downsample | None, owning layer if it is the layer's last block)
@@ -146,21 +147,35 @@ class AcceleratedResNet:
                     f"accelerated forward: cannot expose the output of '{name}' ({type(m).__name__}); hook a Conv2d, maxpool, a "
                     "residual block or layer1..4, or run with accelerate=False")
 
-    def _conv(self, c: _Conv, a_planes, B, H, W, *, relu, residual=None, want_f32=False, out_f32=None, want_planes=True):
-        """One convolution over operand planes `a_planes` (already im2col'ed / subsampled): BatchNorm + optional shortcut +
-        optional ReLU. Returns (fp32 map | None, planes). A hooked convolution leaves its raw output first."""
-        epi = (N.EPI_ADD_RELU if residual is not None else N.EPI_RELU) if relu else N.EPI_NONE
+    def _mm(self, c: _Conv, x_planes, B, H, W, **kw):
+        """The convolution's contraction over channels-last planes of a (B, H, W, cin) map, epilogue arguments in ``kw``:
+        1x1 / stride 1 is the GEMM itself; everything else with cin % 64 == 0 is the implicit GEMM (TMA im2col-mode loads,
+        the stride in the tensor map: no im2col matrix, no subsampled copy); narrow 3x3 inputs take the explicit im2col."""
+        if c.k == 1 and c.stride == 1:
+            return ops.gemm_split(x_planes, c.w, alpha=ALPHA, passes=self.passes, **kw)
+        if c.cin % 64 == 0 and not self.explicit_im2col:
+            return ops.conv_gemm(x_planes, B, H, W, c.w, c.k, c.stride, c.pad, alpha=ALPHA, passes=self.passes, **kw)
+        if c.k == 1:
+            return ops.gemm_split(ops.subsample2_planes(x_planes, B, H, W), c.w, alpha=ALPHA, passes=self.passes, **kw)
+        if c.k == 3 and c.pad == 1:
+            return ops.gemm_split(ops.im2col3x3_strided(x_planes, B, H, W, c.stride), c.w, alpha=ALPHA, passes=self.passes, **kw)
+        raise NotImplementedError(f"accelerated forward: unsupported convolution {c.module}")
+
+    def _conv(self, c: _Conv, x_planes, B, H, W, *, relu, residual=None, want_f32=False, out_f32=None, want_planes=True):
+        """One convolution over the planes of a (B, H, W, cin) map: BatchNorm + optional shortcut + optional ReLU. Returns
+        (fp32 map | None, planes | None) of the (B, Ho, Wo, cout) output. A hooked convolution leaves its raw output first."""
+        Ho, Wo = ops.conv_out(H, c.k, c.stride, c.pad), ops.conv_out(W, c.k, c.stride, c.pad)
+        keep32 = out_f32 if out_f32 is not None else bool(want_f32)
         if self._hooked(c.module):
-            raw, _ = ops.gemm_split(a_planes, c.w, bias=c.bias, alpha=ALPHA, epilogue=N.EPI_NONE, passes=self.passes)
-            _fire(c.module, _as_nchw(raw, B, H, W))
+            raw, _ = self._mm(c, x_planes, B, H, W, bias=c.bias, epilogue=N.EPI_NONE)
+            _fire(c.module, _as_nchw(raw, B, Ho, Wo))
             shift = c.shift if c.bias is None else (c.shift - c.bias * c.scale)  # raw already holds the bias
-            keep32 = out_f32 if out_f32 is not None else bool(want_f32)
             return ops.affine_act(raw, c.scale, shift, residual=residual, relu=relu, fmt=self.fmt, out_f32=keep32, out_planes=want_planes)
         if residual is not None and not relu:
             raise AssertionError("a shortcut add is always followed by the ReLU in a ResNet block")
-        keep32 = out_f32 if out_f32 is not None else bool(want_f32)
-        return ops.gemm_split(a_planes, c.w, bias=c.shift, residual=residual, col_scale=c.scale, alpha=ALPHA, epilogue=epi,
-                              passes=self.passes, out_f32=keep32, out_planes=want_planes)
+        epi = (N.EPI_ADD_RELU if residual is not None else N.EPI_RELU) if relu else N.EPI_NONE
+        return self._mm(c, x_planes, B, H, W, bias=c.shift, residual=residual, col_scale=c.scale, epilogue=epi, out_f32=keep32,
+                        out_planes=want_planes)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, logits: bool = False):
@@ -201,27 +216,21 @@ class AcceleratedResNet:
         # ---- residual blocks ----
         for i, (blk, kind, convs, ds, layer) in enumerate(self.blocks[: last + 1]):
             stride = convs[1].stride if kind == "bottleneck" else convs[0].stride
-            Ho, Wo = (ops.conv_out(H, 3, stride, 1), ops.conv_out(W, 3, stride, 1))
-            # shortcut
-            if ds is not None:
-                xs = ops.subsample2_planes(xpl, B, H, W) if ds.stride == 2 else xpl
-                idf, _ = self._conv(ds, xs, B, Ho, Wo, relu=False, want_f32=True, want_planes=False)
-            else:
-                idf = x32
+            Ho, Wo = ops.conv_out(H, 3, stride, 1), ops.conv_out(W, 3, stride, 1)
+            # shortcut: the block's input, or its 1x1 (strided) projection + BatchNorm, as fp32
+            idf = x32 if ds is None else self._conv(ds, xpl, B, H, W, relu=False, want_f32=True, want_planes=False)[0]
             if kind == "bottleneck":
                 if convs[0].stride != 1 or convs[2].stride != 1:
                     raise NotImplementedError("accelerated forward: the stride of a Bottleneck must sit in conv2 (torchvision v1.5)")
                 _, t1 = self._conv(convs[0], xpl, B, H, W, relu=True)
-                col = ops.im2col3x3_strided(t1, B, H, W, stride)
-                _, t2 = self._conv(convs[1], col, B, Ho, Wo, relu=True)
-                del col, t1
+                _, t2 = self._conv(convs[1], t1, B, H, W, relu=True)
+                del t1
                 x32, xpl = self._conv(convs[2], t2, B, Ho, Wo, relu=True, residual=idf, out_f32=idf)
+                del t2
             else:
-                col = ops.im2col3x3_strided(xpl, B, H, W, stride)
-                _, t1 = self._conv(convs[0], col, B, Ho, Wo, relu=True)
-                col = ops.im2col3x3_strided(t1, B, Ho, Wo, 1)
-                x32, xpl = self._conv(convs[1], col, B, Ho, Wo, relu=True, residual=idf, out_f32=idf)
-                del col, t1
+                _, t1 = self._conv(convs[0], xpl, B, H, W, relu=True)
+                x32, xpl = self._conv(convs[1], t1, B, Ho, Wo, relu=True, residual=idf, out_f32=idf)
+                del t1
             H, W = Ho, Wo
             if self._hooked(blk):
                 _fire(blk, _as_nchw(x32, B, H, W))

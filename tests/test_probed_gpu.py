@@ -68,6 +68,34 @@ def test_conv3x3_strided_over_planes(ops, B, H, W, C, s, cout):
         assert torch.equal(col, ops.im2col3x3(planes, B, H, W))
 
 
+@pytest.mark.parametrize("B,H,W,C,k,s,cout", [
+    (2, 14, 14, 64, 3, 1, 64), (2, 14, 14, 64, 3, 2, 128), (3, 56, 56, 64, 3, 1, 64), (1, 7, 9, 128, 3, 1, 32), (2, 15, 13, 64, 3, 2, 72),
+    (5, 7, 7, 512, 3, 1, 512), (2, 28, 28, 256, 1, 2, 512), (1, 9, 7, 64, 1, 2, 8), (2, 8, 8, 64, 1, 1, 256), (3, 5, 5, 64, 3, 1, 64),
+    (2, 57, 55, 128, 3, 2, 128)])
+def test_implicit_gemm_convolution(ops, B, H, W, C, k, s, cout):
+    """slb_conv_gemm (TMA im2col-mode A operand, no im2col matrix) against torch's conv2d in float64 on the values the planes
+    hold, and bit-identical to the explicit im2col + GEMM path it replaces."""
+    pad = k // 2
+    g = torch.Generator().manual_seed(H * 7 + C + s + k)
+    a = torch.randn(B, H, W, C, generator=g)
+    w = torch.randn(cout, C, k, k, generator=g) * (k * k * C) ** -0.5
+    planes = ops.split_planes(a.view(-1, C).cuda(), 0, ACT)
+    x_held = held(planes, ACT).view(B, H, W, C).cpu()
+    wp = weight_planes(ops, w)
+    got, gotp = ops.conv_gemm(planes, B, H, W, wp, k, s, pad, alpha=1.0 / (ACT * WSC), passes=4, out_planes=True)
+    want = F.conv2d(x_held.permute(0, 3, 1, 2), w.double(), stride=s, padding=pad).permute(0, 2, 3, 1).reshape(-1, cout)
+    assert got.shape == want.shape
+    tol = 3e-6 if k * k * C <= 1152 else 1e-5  # the tensor core truncates at every accumulate: 7e-6 at K = 4608
+    assert rel_max(got, want) < tol
+    assert rel_max(held(gotp, ACT), want) < tol
+    if k == 3:
+        col = ops.im2col3x3_strided(planes, B, H, W, s)
+    else:
+        col = ops.subsample2_planes(planes, B, H, W) if s == 2 else planes
+    ref, _ = ops.gemm_split(col, wp, alpha=1.0 / (ACT * WSC), passes=4)
+    assert torch.equal(got, ref)
+
+
 @pytest.mark.parametrize("B,H,W,C", [(2, 8, 8, 16), (1, 7, 9, 24), (3, 56, 56, 256)])
 def test_subsample2_is_a_pure_move(ops, B, H, W, C):
     a = torch.randn(B, H, W, C, generator=torch.Generator().manual_seed(C))
