@@ -443,7 +443,8 @@ def run_b200(args):
     torch.cuda.empty_cache()
     sub = {}
     with_cpu = world == 1 and not args.no_cpu
-    for key, short in (("cfg3_step", "cfg3"), ("cfg4_step", "cfg4"), ("cfg2_accel_step", "cfg2a"), ("cfg4_accel_step", "cfg4a")):
+    for key, short in (("cfg3_step", "cfg3"), ("cfg4_step", "cfg4"), ("cfg2_accel_step", "cfg2a"), ("cfg3_accel_step", "cfg3a"),
+                       ("cfg4_accel_step", "cfg4a")):
         if short in wanted:
             sub[key] = run_step_config(key, dev, rank, world, pk, pk_src, with_cpu)
     if "cfg5" in wanted:
@@ -496,6 +497,11 @@ STEP_CONFIGS = {
         workload="cfg2 with accelerate=True: ResNet-50 probed at conv1,layer1..layer4 (aggregate_conv_mean, k=20) on the "
                  "package's own convolution kernels + OpenCLIP ViT-B/32 image-tower embed, synthetic 224x224 images",
         probed="resnet50", agg="aggregate_conv_mean", fm="ViT-B-32", batch=256, steps=10, warmup=3, accelerate=True),
+    "cfg3_accel_step": dict(
+        workload="cfg3 with accelerate=True: torchvision ViT-B/16 probed at its 12 encoder-block outputs "
+                 "(aggregate_transformer_mean, k=20) on the package's own ViT kernels + SigLIP ViT-L/16-256 image-tower embed, "
+                 "synthetic 224x224 / 256x256 images",
+        probed="vit_b_16", agg="aggregate_transformer_mean", fm="ViT-L-16-SigLIP-256", batch=128, steps=6, warmup=3, accelerate=True),
     "cfg4_accel_step": dict(
         workload="cfg4 with accelerate=True: ResNet-50 probed at all 53 nn.Conv2d outputs (aggregate_conv_mean, k=20) on the "
                  "package's own convolution kernels + OpenCLIP ViT-L/14 image-tower embed, synthetic 224x224 images",
@@ -562,9 +568,9 @@ def run_step_config(key: str, dev, rank: int, world: int, pk: dict, pk_src: str,
     model = model.to(dev)
     accel = bool(spec.get("accelerate"))
     if accel:
-        from semanticlens_b200.probed import AcceleratedResNet
+        from semanticlens_b200.probed import accelerated_forward
 
-        forward = AcceleratedResNet(model, dev)
+        forward = accelerated_forward(model, dev)
     else:
         forward = model
     agg = getattr(A, spec["agg"])
@@ -625,7 +631,7 @@ def run_step_config(key: str, dev, rank: int, world: int, pk: dict, pk_src: str,
 
         def as_seen(o):
             o = o.detach().float()
-            if accel:  # the accelerated forward hands out channels-last maps: K1 folds them in (B, HW, C) order
+            if accel and kind == "conv":  # the accelerated forward hands out channels-last maps: K1 folds them in (B, HW, C) order
                 o = o.permute(0, 2, 3, 1).reshape(o.shape[0], -1, o.shape[1])
             return o.cpu().numpy()
 
@@ -640,7 +646,7 @@ def run_step_config(key: str, dev, rank: int, world: int, pk: dict, pk_src: str,
 
         exact = True
         for n in picks:
-            st = oc.sweep(seen[n], "mean", "tokens" if accel else kind, K_COLLECT)
+            st = oc.sweep(seen[n], "mean", "tokens" if accel else kind, K_COLLECT)  # accelerated conv maps arrive as (B, HW, C)
             got = small.cache[n].activations.view(torch.int16).numpy().view(np.uint16)
             exact &= bool((got == st.bits).all() and (small.cache[n].sample_ids.numpy() == st.ids).all())
         cfg_o, tower_o = _oracle_tower(fm)
@@ -664,7 +670,7 @@ def run_step_config(key: str, dev, rank: int, world: int, pk: dict, pk_src: str,
             worst = 0.0
             for n in picks:
                 a = torch.from_numpy(seen[n][0])
-                b = ref_maps[n].permute(0, 2, 3, 1).reshape(a.shape)
+                b = ref_maps[n].permute(0, 2, 3, 1).reshape(a.shape) if kind == "conv" else ref_maps[n]
                 worst = max(worst, float((a - b).abs().max() / b.abs().max()))
             parity["probed_maps_max_rel_err_vs_torch_fp32"] = worst
             parity["probed_maps_tolerance"] = 1e-4
@@ -899,9 +905,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     ap.add_argument("--overlap", type=int, default=0, help="1: run the embed tower on a second stream under the sweep")
-    ap.add_argument("--configs", default="cfg3,cfg4,cfg5,cfg2a,cfg4a",
-                    help="sub-records measured after the headline: any of cfg3,cfg4,cfg5,cfg2a,cfg4a (a = opt-in accelerated "
-                         "probed forward), or 'none'")
+    ap.add_argument("--configs", default="cfg3,cfg4,cfg5,cfg2a,cfg3a,cfg4a",
+                    help="sub-records measured after the headline: any of cfg3,cfg4,cfg5,cfg2a,cfg3a,cfg4a (a = opt-in "
+                         "accelerated probed forward), or 'none'")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

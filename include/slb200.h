@@ -315,6 +315,13 @@ size_t slb_vit_workspace_bytes(const SlbVitWeights* w, int64_t B);
 int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t B, float* out, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* The trunk of a ViT in slices (the accelerated probed forward: torchvision's VisionTransformer under forward hooks on its
+ * encoder blocks, run by the reference as self.model(x), activation_based.py:341-358). layer_begin == 0 embeds the images
+ * first; then blocks [layer_begin, layer_end) run. The residual stream (B*T, W) fp32 — the output of block layer_end - 1 —
+ * is the first region of the workspace (slb_vit_workspace_bytes). The pooling fields of `w` are not used. */
+int slb_vit_trunk(const SlbVitWeights* w, const float* img, int64_t B, int32_t layer_begin, int32_t layer_end, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
 /* The CLIP / SigLIP text tower in one call (open_clip CLIP.encode_text / CustomTextCLIP.encode_text behind
  * clip.py:120-135; reached from Lens.text_probing, lens.py:166-203): token + positional embedding, `layers` pre-LN blocks
  * (causal mask for CLIP, none for SigLIP), ln_final, the pooled token's feature (CLIP: end-of-text; SigLIP: last position)

@@ -108,6 +108,7 @@ _PROTOS = {
     "slb_rn_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "slb_vit_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "slb_vit_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "slb_vit_trunk": (c_int, [c_void_p, c_void_p, c_int64, ctypes.c_int32, ctypes.c_int32, c_void_p, c_size_t, c_void_p]),
 }
 
 

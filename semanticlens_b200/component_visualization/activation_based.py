@@ -289,7 +289,7 @@ class ActivationComponentVisualizer(AbstractComponentVisualizer):
         if not probed.accel_requested(self.accelerate):
             return self.model
         if self._accel_forward is None or self._accel_forward.device != torch.device(device):
-            self._accel_forward = probed.AcceleratedResNet(self.model, device)
+            self._accel_forward = probed.accelerated_forward(self.model, device)
         return self._accel_forward
 
     @torch.no_grad()

@@ -174,6 +174,52 @@ extern "C" int slb_vit_forward(const SlbVitWeights* w, const float* img, int64_t
     return SLB_OK;
 }
 
+// The trunk of a ViT in slices, for a caller that wants the residual stream between blocks (the accelerated probed
+// forward, semanticlens_b200/probed.py: torchvision's VisionTransformer under forward hooks on its encoder blocks —
+// BASELINE configs[2]). layer_begin == 0 first embeds the images (patch GEMM, class token, positions, ln_pre); then blocks
+// [layer_begin, layer_end) run. The residual stream [B*T, W] fp32 is the FIRST region of the workspace, valid after the call.
+extern "C" int slb_vit_trunk(const SlbVitWeights* w, const float* img, int64_t B, int32_t layer_begin, int32_t layer_end,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+    SLB_REQUIRE(w != nullptr && B >= 0, SLB_EINVAL, "slb_vit_trunk: bad arguments");
+    if (B == 0) return SLB_OK;
+    SLB_REQUIRE(workspace && (img || layer_begin > 0), SLB_EINVAL, "slb_vit_trunk: null pointer");
+    SLB_REQUIRE(0 <= layer_begin && layer_begin <= layer_end && layer_end <= w->layers && (w->layer || w->layers == 0), SLB_EINVAL,
+                "slb_vit_trunk: bad layer range [%d, %d) of %d", layer_begin, layer_end, w->layers);
+    SLB_REQUIRE(w->conv_w && w->pos && (!w->has_cls || w->cls), SLB_EINVAL, "slb_vit_trunk: incomplete weights");
+    SLB_REQUIRE(w->width % 64 == 0 && w->mlp % 64 == 0 && w->heads > 0 && w->width % w->heads == 0 && w->patch % 2 == 0,
+                SLB_EUNSUPPORTED, "slb_vit_trunk: width and mlp must be multiples of 64, the patch size even");
+    WsLayout L;
+    SLB_REQUIRE(layout_for(w, B, &L), SLB_EINVAL, "slb_vit_trunk: image_size must be a multiple of patch");
+    SLB_REQUIRE(L.x == 0, SLB_ECUDA, "slb_vit_trunk: the residual stream must lead the workspace");
+    SLB_REQUIRE(((uintptr_t)workspace % 256) == 0, SLB_EINVAL, "slb_vit_trunk: workspace must be 256-byte aligned");
+    SLB_REQUIRE(workspace_bytes >= L.total, SLB_EWORKSPACE, "slb_vit_trunk: workspace needs %zu bytes, got %zu", L.total, workspace_bytes);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    float* x = reinterpret_cast<float*>(ws + L.x);
+    float* qkv = reinterpret_cast<float*>(ws + L.qkv);
+    uint16_t* pa = reinterpret_cast<uint16_t*>(ws + L.planes_a);
+    uint16_t* pb = reinterpret_cast<uint16_t*>(ws + L.planes_b);
+    float* patch_f32 = reinterpret_cast<float*>(ws + L.patch_f32);
+    const int fmt = w->plane_fmt;
+    const int64_t g = w->image_size / w->patch;
+    const int64_t T = g * g + (w->has_cls ? 1 : 0), W = w->width, rows = B * T;
+    int rc;
+    if (layer_begin == 0) {
+        rc = slb_patchify(img, B, w->image_size, w->patch, fmt, pa, stream);
+        if (rc != SLB_OK) return rc;
+        rc = slb_gemm_split(pa, w->conv_w, fmt, B * g * g, W, slb_patch_k(w->patch), kAlpha, w->conv_b, nullptr, nullptr, nullptr,
+                            SLB_EPI_NONE, 3, patch_f32, nullptr, stream);
+        if (rc != SLB_OK) return rc;
+        rc = slb_assemble_tokens(patch_f32, w->cls, w->pos, B, T, W, w->has_cls ? 1 : 0, x, stream);
+        if (rc != SLB_OK) return rc;
+        if (w->ln_pre_g) {
+            rc = slb_layernorm(x, rows, W, W, w->ln_pre_g, w->ln_pre_b, w->ln_eps, fmt, x, nullptr, stream);
+            if (rc != SLB_OK) return rc;
+        }
+    }
+    return run_blocks(w->layer + layer_begin, layer_end - layer_begin, x, qkv, pa, pb, B, T, W, w->heads, w->mlp, w->act, fmt, w->ln_eps,
+                      0, stream);
+}
+
 // ---------------------------------------------------------------------------------------------
 // CLIP text tower
 // ---------------------------------------------------------------------------------------------

@@ -1,4 +1,4 @@
-"""Opt-in B200 forward for the PROBED model when it is a torchvision-style ResNet.
+"""Opt-in B200 forward for the PROBED model when it is a torchvision-style ResNet or VisionTransformer.
 
 The reference sweeps the dataset through ``self.model(x)`` under forward hooks
 (``ActivationComponentVisualizer._run``, activation_based.py:341-358); the model is user code and by default this package
@@ -9,6 +9,9 @@ BatchNorm / ReLU / shortcut in its epilogue (csrc/convnet.cu, csrc/gemm_tc.cu) â
 accumulate: ~1e-5 of the largest activation after 50 layers, measured in tests/test_probed_gpu.py), not bit-identical to
 cuDNN's fp32, hence opt-in: ``ActivationComponentVisualizer(..., accelerate=True)`` or ``SLB_ACCEL_FORWARD=1``.
 
+``torchvision.models.VisionTransformer`` (BASELINE configs[2]: ViT-B/16 probed at its encoder blocks) runs on the ViT
+tower's kernels the same way (``AcceleratedViT``: ``slb_vit_trunk`` block by block, hooks fired on the residual stream).
+
 Hooks keep working: whatever forward hooks are registered on the model's modules (the ones ``ActMaxCache`` installs) are
 called with the module's output as a ``(B, C, H, W)`` tensor in channels-last memory, which K1 reads in place. Supported
 hook points: every ``nn.Conv2d`` (its raw output, before BatchNorm), ``maxpool``, every residual block and ``layer1..4``.
@@ -17,6 +20,7 @@ The forward stops after the last hooked module (the reference discards the logit
 
 from __future__ import annotations
 
+import ctypes
 import os
 
 import torch
@@ -242,3 +246,137 @@ class AcceleratedResNet:
         return m.fc(feat) if hasattr(m, "fc") else feat
 
     __call__ = forward
+
+
+class AcceleratedViT:
+    """Runs a ``torchvision.models.VisionTransformer`` (eval mode) on the ViT tower's kernels (patch GEMM, LayerNorm,
+    tcgen05 attention, MLP GEMMs with bias / GELU / residual epilogues: csrc/vit_forward.cu ``slb_vit_trunk``) and calls
+    the forward hooks registered on its encoder blocks with the residual stream as a ``(B, T, W)`` fp32 tensor (a view of
+    the workspace: hooks must consume it before the next block runs, which stream order guarantees for K1 / K2).
+    Supported hook points: ``encoder.layers.encoder_layer_<i>`` and ``encoder.layers``."""
+
+    def __init__(self, model: nn.Module, device=None, plane_format: str = "f16"):
+        lib = N.load(require_device=True)
+        need = ("conv_proj", "class_token", "encoder", "image_size", "patch_size", "hidden_dim", "mlp_dim")
+        if not all(hasattr(model, n) for n in need) or not hasattr(model.encoder, "layers"):
+            raise NotImplementedError("accelerated forward: expected a torchvision-style VisionTransformer")
+        if model.training:
+            raise NotImplementedError("accelerated forward: put the model in eval mode (dropout must be off)")
+        self.model = model
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise N.SlbError("the accelerated forward runs on a CUDA device (there is no CPU fallback)")
+        self.fmt = {"f16": N.PLANE_F16, "bf16": N.PLANE_BF16}[plane_format]
+        dev, fmt = self.device, self.fmt
+        self._keep: list = []
+        self._ws = None
+        blocks = list(model.encoder.layers.children())
+        W, P, S = model.hidden_dim, model.patch_size, model.image_size
+        heads = blocks[0].self_attention.num_heads
+        if W % 64 or model.mlp_dim % 64 or P % 2 or S % P:
+            raise NotImplementedError("accelerated forward: width and mlp must be multiples of 64, the patch size even")
+
+        def vec(t):
+            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            self._keep.append(t)
+            return t.data_ptr()
+
+        def planes(mat):
+            t = ops.split_planes(mat.detach().to(device=dev, dtype=torch.float32), fmt, N.WEIGHT_PLANE_SCALE)
+            self._keep.append(t)
+            return t.data_ptr()
+
+        layers = (N.SlbVitLayer * len(blocks))()
+        eps = None
+        for ly, blk in zip(layers, blocks):
+            att, mlp = blk.self_attention, blk.mlp
+            lin = [m for m in mlp.children() if isinstance(m, nn.Linear)]
+            acts = [m for m in mlp.children() if isinstance(m, nn.GELU)]
+            ok = (isinstance(att, nn.MultiheadAttention) and att._qkv_same_embed_dim and att.in_proj_bias is not None and att.batch_first
+                  and att.num_heads == heads and len(lin) == 2 and len(acts) == 1 and acts[0].approximate == "none"
+                  and lin[0].bias is not None and lin[1].bias is not None)
+            if not ok:
+                raise NotImplementedError(f"accelerated forward: unsupported encoder block {blk}")
+            eps = blk.ln_1.eps if eps is None else eps
+            if blk.ln_1.eps != eps or blk.ln_2.eps != eps:
+                raise NotImplementedError("accelerated forward: the LayerNorms must share one eps")
+            ly.ln1_g, ly.ln1_b = vec(blk.ln_1.weight), vec(blk.ln_1.bias)
+            ly.w_qkv, ly.b_qkv = planes(att.in_proj_weight), vec(att.in_proj_bias)
+            ly.w_out, ly.b_out = planes(att.out_proj.weight), vec(att.out_proj.bias)
+            ly.ln2_g, ly.ln2_b = vec(blk.ln_2.weight), vec(blk.ln_2.bias)
+            ly.w_fc, ly.b_fc = planes(lin[0].weight), vec(lin[0].bias)
+            ly.w_proj, ly.b_proj = planes(lin[1].weight), vec(lin[1].bias)
+        kc, kpad = 3 * P * P, lib.slb_patch_k(P)
+        conv = torch.zeros(W, kpad)
+        conv[:, :kc] = model.conv_proj.weight.detach().float().cpu().reshape(W, kc)
+        w = N.SlbVitWeights()
+        w.image_size, w.patch, w.width, w.layers = S, P, W, len(blocks)
+        w.heads, w.mlp, w.embed_dim = heads, model.mlp_dim, W
+        w.act, w.plane_fmt, w.ln_eps = N.EPI_GELU_ERF, fmt, float(eps)
+        w.has_cls, w.pool = 1, N.POOL_CLS
+        w.conv_w = planes(conv)
+        w.conv_b = vec(model.conv_proj.bias) if model.conv_proj.bias is not None else None
+        w.cls = vec(model.class_token.reshape(W))
+        w.pos = vec(model.encoder.pos_embedding.reshape(-1, W))
+        w.ln_pre_g = w.ln_pre_b = None
+        w.layer = layers
+        self._keep.append(layers)
+        self._struct = w
+        self.blocks = blocks
+        self.tokens = (S // P) ** 2 + 1
+        self._tappable = {id(b) for b in blocks} | {id(model.encoder.layers)}
+
+    def check_hooks(self) -> None:
+        for name, m in self.model.named_modules():
+            if len(m._forward_hooks) and id(m) not in self._tappable:
+                raise NotImplementedError(
+                    f"accelerated forward: cannot expose the output of '{name}' ({type(m).__name__}); hook the encoder blocks "
+                    "(encoder.layers.encoder_layer_<i>) or run with accelerate=False")
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, features: bool = False):
+        """x (B, 3, S, S) fp32 on the device. Fires the registered hooks; ``features=True`` returns the final residual stream
+        (B, T, W) (a copy), else None. The trunk stops after the last hooked block."""
+        self.check_hooks()
+        lib = N.load(require_device=True)
+        m, w = self.model, self._struct
+        if x.ndim != 4 or tuple(x.shape[1:]) != (3, w.image_size, w.image_size):
+            raise ValueError(f"expected (B, 3, {w.image_size}, {w.image_size}) images, got {tuple(x.shape)}")
+        x = x.to(self.device, dtype=torch.float32).contiguous()
+        B = x.shape[0]
+        hooked = [i for i, b in enumerate(self.blocks) if len(b._forward_hooks)]
+        seq_hooked = len(m.encoder.layers._forward_hooks) > 0
+        last = len(self.blocks) if (features or seq_hooked) else (hooked[-1] + 1 if hooked else 0)
+        if B == 0 or last == 0:
+            return None
+        need = lib.slb_vit_workspace_bytes(ctypes.byref(w), B)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        stream_x = self._ws[: B * self.tokens * w.width * 4].view(torch.float32).view(B, self.tokens, w.width)
+        cuts = sorted(set(i + 1 for i in hooked if i + 1 <= last) | {last})  # run up to each hooked block, fire, continue
+        begin = 0
+        with torch.cuda.device(x.device):
+            for end in cuts:
+                rc = lib.slb_vit_trunk(ctypes.byref(w), x.data_ptr(), B, begin, end, self._ws.data_ptr(), self._ws.numel(),
+                                       N.stream_ptr(x.device))
+                N.check(rc, "slb_vit_trunk")
+                blk = self.blocks[end - 1]
+                if len(blk._forward_hooks):
+                    _fire(blk, stream_x)
+                begin = end
+        if seq_hooked:
+            _fire(m.encoder.layers, stream_x)
+        return stream_x.clone() if features else None
+
+    __call__ = forward
+
+
+def accelerated_forward(model: nn.Module, device=None):
+    """The accelerated forward that fits ``model`` (a torchvision-style ResNet or VisionTransformer), or NotImplementedError."""
+    if hasattr(model, "layer1") and hasattr(model, "conv1"):
+        return AcceleratedResNet(model, device)
+    if hasattr(model, "conv_proj") and hasattr(model, "encoder"):
+        return AcceleratedViT(model, device)
+    raise NotImplementedError(
+        f"accelerate=True: no accelerated forward for {type(model).__name__} (torchvision-style ResNets and VisionTransformers "
+        "are supported); run with accelerate=False")

@@ -265,3 +265,80 @@ def test_collect_contract_with_the_accelerated_forward(arch, layers, tmp_path):
     print(report)
     for name in layers:
         assert report[name]["rows_checked_exactly"] >= 0.5 * report[name]["rows"], (name, report[name])
+
+
+def test_vit_hooked_blocks_match_float64():
+    """torchvision VisionTransformer on the ViT tower's kernels: the residual stream after every hooked encoder block
+    against a float64 forward of the same model (the torch fp32 forward is measured beside it)."""
+    import torchvision
+
+    from semanticlens_b200.probed import AcceleratedViT, accelerated_forward
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    net = torchvision.models.vit_b_16(weights=None).eval()
+    g = torch.Generator().manual_seed(7)
+    for p_ in net.parameters():  # a random init with non-trivial biases / LayerNorm gains
+        if p_.ndim == 1:
+            p_.data += 0.1 * torch.randn(p_.shape, generator=g)
+    x = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(8))
+    names = [f"encoder.layers.encoder_layer_{i}" for i in (0, 5, 11)]
+
+    def tap(model, inp, forward=None):
+        seen = {}
+        mods = dict(model.named_modules())
+        hs = [mods[n].register_forward_hook(lambda m, i, o, n=n: seen.__setitem__(n, o.detach().clone())) for n in names]
+        with torch.no_grad():
+            (forward or model)(inp)
+        for h in hs:
+            h.remove()
+        return seen
+
+    want = tap(copy.deepcopy(net).double(), x.double())
+    net = net.cuda()
+    t32 = tap(net, x.cuda())
+    fwd = accelerated_forward(net)
+    assert isinstance(fwd, AcceleratedViT)
+    got = tap(net, x.cuda(), fwd)
+    for n in names:
+        assert got[n].shape == (3, 197, 768) and got[n].dtype == torch.float32
+        e_accel, e_torch = rel_max(got[n], want[n]), rel_max(t32[n], want[n])
+        print(f"{n}: accelerated {e_accel:.2e}, torch fp32 {e_torch:.2e} of the largest activation")
+        assert e_accel < 2e-5, n
+    # the trunk stops after the last hooked block; with nothing hooked there is nothing to do
+    assert fwd(x.cuda()) is None
+    feats = fwd(x.cuda(), features=True)
+    assert rel_max(feats, want[names[-1]]) < 2e-5
+    h = net.encoder.ln.register_forward_hook(lambda m, i, o: None)
+    with pytest.raises(NotImplementedError, match="encoder.ln"):
+        fwd(x.cuda())
+    h.remove()
+
+
+def test_vit_collect_with_the_accelerated_forward_matches_the_oracle():
+    """cfg 3's sweep with accelerate=True: the collected state is bit-exact against the canonical oracle fed the maps the
+    hooks saw, and agrees with the torch-forward sweep wherever the candidates' bf16 values agree."""
+    import torchvision
+
+    from oracle import collect as oc
+    from semanticlens_b200.component_visualization import ActivationComponentVisualizer, aggregators
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    net = torchvision.models.vit_b_16(weights=None).eval().cuda()
+    net.name = "vit_b_16"
+    layers = [f"encoder.layers.encoder_layer_{i}" for i in (0, 6, 11)]
+    n, k, bs = 24, 5, 8
+    ds_m, ds_f = _Images(n, "model"), _Images(n, "fm")
+    seen = {name: [] for name in layers}
+    mods = dict(net.named_modules())
+    taps = [mods[name].register_forward_hook(lambda m, i, o, name=name: seen[name].append(o.detach().float().cpu().numpy())) for name in layers]
+    cv = ActivationComponentVisualizer(net, ds_m, ds_f, layers, k, aggregate_fn=aggregators.aggregate_transformer_mean, accelerate=True)
+    cv.show_progress = False
+    cv.run(batch_size=bs)
+    for t in taps:
+        t.remove()
+    for name in layers:
+        st = oc.sweep(seen[name], "mean", "tokens", k)
+        am = cv.actmax_cache.cache[name]
+        assert (bits_of(am.activations) == st.bits).all() and (am.sample_ids.numpy() == st.ids).all(), name
