@@ -386,6 +386,17 @@ int slb_conv_gemm(const uint16_t* x_planes, int64_t B, int64_t H, int64_t W, int
                   const uint16_t* w_planes, int64_t N, int plane_fmt, float alpha, const float* bias, const float* residual,
                   const float* col_scale, int epilogue, int passes, float* out_f32, uint16_t* out_planes, void* stream);
 
+/* slb_gemm_split / slb_conv_gemm that ALSO leave raw_f32 [M, N] = alpha * (A W^T) * row_scale — the value before column
+ * scale, bias, activation and residual: the raw output of a convolution whose BatchNorm / ReLU / shortcut ride in the same
+ * epilogue, for a forward hook registered on the nn.Conv2d itself (BASELINE configs[3]: all 53 convolutions hooked). */
+int slb_gemm_split_raw(const uint16_t* a_planes, const uint16_t* w_planes, int plane_fmt, int64_t M, int64_t N, int64_t K, float alpha,
+                       const float* bias, const float* residual, const float* row_scale, const float* col_scale, int epilogue,
+                       int passes, float* out_f32, uint16_t* out_planes, float* raw_f32, void* stream);
+int slb_conv_gemm_raw(const uint16_t* x_planes, int64_t B, int64_t H, int64_t W, int64_t C, int ksize, int stride, int pad,
+                      const uint16_t* w_planes, int64_t N, int plane_fmt, float alpha, const float* bias, const float* residual,
+                      const float* col_scale, int epilogue, int passes, float* out_f32, uint16_t* out_planes, float* raw_f32,
+                      void* stream);
+
 /* im2col of a ksize x ksize / stride / pad convolution straight from NCHW fp32 images (the 7x7 / 2 / 3 stem):
  * img (B,C,H,W) -> planes [2, B*Ho*Wo, slb_conv_k(C, ksize)], column (ky*ksize + kx)*C + c, zero outside / past C k k. */
 int slb_im2col_nchw(const float* img, int64_t B, int64_t C, int64_t H, int64_t W, int ksize, int stride, int pad, int plane_fmt,

@@ -73,6 +73,8 @@ _PROTOS = {
          c_void_p, c_void_p, c_void_p],
     ),
     "slb_u8_to_f32_norm": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "slb_gemm_split_raw": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "slb_patchify": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "slb_assemble_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "slb_layernorm": (
@@ -98,6 +100,8 @@ _PROTOS = {
     "slb_avgpool2_planes": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "slb_conv_gemm": (c_int, [c_void_p] + [c_int64] * 4 + [c_int] * 3 + [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "slb_conv_gemm_raw": (c_int, [c_void_p] + [c_int64] * 4 + [c_int] * 3 + [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "slb_im2col_nchw": (c_int, [c_void_p] + [c_int64] * 4 + [c_int] * 4 + [c_void_p, c_void_p]),
     "slb_im2col3x3_strided": (c_int, [c_void_p] + [c_int64] * 4 + [c_int, c_void_p, c_void_p]),
     "slb_subsample2_planes": (c_int, [c_void_p] + [c_int64] * 4 + [c_void_p, c_void_p]),

@@ -106,22 +106,6 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// (x0, x1) -> packed fp16 hi and lo planes of SLB_ACT_PLANE_SCALE * x (fp16 planes): hi = the scaled value with its low
-// 13 mantissa bits cleared (exact in fp16 above the subnormal range), lo = the exact remainder rounded to fp16. Two packed
-// conversions per pair instead of four scalar ones and two back-conversions; saturates like slb_split2, NaN goes through.
-__device__ __forceinline__ void split_pair_act(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    x0 *= SLB_ACT_PLANE_SCALE;
-    x1 *= SLB_ACT_PLANE_SCALE;
-    if (x0 == x0) x0 = fminf(fmaxf(x0, -65504.0f), 65504.0f);
-    if (x1 == x1) x1 = fminf(fmaxf(x1, -65504.0f), 65504.0f);
-    const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
-    const float h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
-    const __half2 hp = __floats2half2_rn(h0, h1);
-    const __half2 lp = __floats2half2_rn(x0 - h0, x1 - h1);
-    hi = *reinterpret_cast<const uint32_t*>(&hp);
-    lo = *reinterpret_cast<const uint32_t*>(&lp);
-}
-
 // ask the TMA unit to bring a box into L2 (no shared-memory destination): hides the DRAM latency of the next work item
 __device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)),
@@ -477,7 +461,7 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
                 // rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4): conflict-free for both access patterns.
                 uint32_t hh[16], ll[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) split_pair_act(o[2 * e], o[2 * e + 1], hh[e], ll[e]);
+                for (int e = 0; e < 16; ++e) slb_split_pair_act_f16(o[2 * e], o[2 * e + 1], hh[e], ll[e]);
 #pragma unroll
                 for (int pl = 0; pl < 2; ++pl) {
                     __syncwarp();  // the region's previous contents (the other plane) have been read

@@ -21,6 +21,13 @@ int grid_for(int64_t n, int threads) {
 
 __device__ __forceinline__ void pack8(const float (&v)[8], int fmt, uint4& hi, uint4& lo) {
     uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+    if (fmt == SLB_PLANE_F16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) slb_split_pair_act_f16(v[2 * j], v[2 * j + 1], h[j], l[j]);
+        hi = make_uint4(h[0], h[1], h[2], h[3]);
+        lo = make_uint4(l[0], l[1], l[2], l[3]);
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         uint16_t hh, ll;
@@ -61,6 +68,46 @@ __global__ void __launch_bounds__(256) im2col_nchw_kernel(const float* __restric
         pack8(v, fmt, h4, l4);
         *reinterpret_cast<uint4*>(hi + m * (int64_t)K8 * 8 + kc * 8) = h4;
         *reinterpret_cast<uint4*>(lo + m * (int64_t)K8 * 8 + kc * 8) = l4;
+    }
+}
+
+// The same im2col for the common case of a whole output row per CTA: the k input rows a row of outputs needs are staged in
+// shared memory with coalesced loads (zero padding included), then every thread assembles 16-byte chunks from there. The
+// direct kernel above gathers 4 bytes at a time from up to 32 cache lines per warp instruction and ran at 1 TB/s on the
+// 7x7 / 2 stem of a ResNet (2.5 GB of planes per 256 images); this one is bound by the plane stores.
+__global__ void __launch_bounds__(256) im2col_nchw_rows_kernel(const float* __restrict__ img, int C, int H, int W, int Ho, int Wo, int k,
+                                                               int stride, int pad, int K8, int Wn, int fmt,
+                                                               uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    extern __shared__ float rows[];  // [C][k][Wn]: input column xx - pad of input row y * stride + ky - pad
+    int* tab = reinterpret_cast<int*>(rows + C * k * Wn);  // [8 K8]: column -> offset of its (channel, ky) row + kx, -1 past C k k
+    for (int col = threadIdx.x; col < K8 * 8; col += blockDim.x) {
+        const int tap = col / C, c = col - tap * C;
+        const int ky = tap / k, kx = tap - ky * k;
+        tab[col] = col < C * k * k ? (c * k + ky) * Wn + kx : -1;
+    }
+    const int y = blockIdx.x % Ho;
+    const int64_t b = blockIdx.x / Ho;
+    const float* base = img + b * C * (int64_t)H * W;
+    for (int i = threadIdx.x; i < C * k * Wn; i += blockDim.x) {
+        const int xx = i % Wn, r = i / Wn;
+        const int ky = r % k, c = r / k;
+        const int yy = y * stride + ky - pad, xi = xx - pad;
+        rows[i] = ((unsigned)yy < (unsigned)H && (unsigned)xi < (unsigned)W) ? __ldg(base + ((int64_t)c * H + yy) * W + xi) : 0.f;
+    }
+    __syncthreads();
+    const int64_t m0 = (b * Ho + y) * (int64_t)Wo;
+    for (int q = threadIdx.x; q < Wo * K8; q += blockDim.x) {
+        const int x = q / K8, kc = q - x * K8;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int o = tab[kc * 8 + j];
+            v[j] = o >= 0 ? rows[o + x * stride] : 0.f;
+        }
+        uint4 h4, l4;
+        pack8(v, fmt, h4, l4);
+        *reinterpret_cast<uint4*>(hi + (m0 + x) * (int64_t)K8 * 8 + kc * 8) = h4;
+        *reinterpret_cast<uint4*>(lo + (m0 + x) * (int64_t)K8 * 8 + kc * 8) = l4;
     }
 }
 
@@ -199,8 +246,16 @@ extern "C" int slb_im2col_nchw(const float* img, int64_t B, int64_t C, int64_t H
     SLB_REQUIRE(Ho > 0 && Wo > 0, SLB_EINVAL, "slb_im2col_nchw: empty output");
     const int64_t M = B * Ho * Wo, K = slb_conv_k(C, ksize);
     SlbProfScope prof("conv im2col", stream, 0.0, 4.0 * (double)B * (double)C * (double)H * (double)W + 4.0 * (double)K * (double)M);
-    im2col_nchw_kernel<<<grid_for(M * (K / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        img, M * (K / 8), (int)C, (int)H, (int)W, (int)Ho, (int)Wo, ksize, stride, pad, (int)(K / 8), plane_fmt, out_planes, out_planes + M * K);
+    const int64_t Wn = (Wo - 1) * stride + ksize;  // staged columns per input row (padding included)
+    const size_t smem = (size_t)C * ksize * Wn * sizeof(float) + (size_t)K * sizeof(int);
+    if (smem <= 48 * 1024 && B * Ho < (1ll << 31)) {
+        im2col_nchw_rows_kernel<<<(unsigned)(B * Ho), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+            img, (int)C, (int)H, (int)W, (int)Ho, (int)Wo, ksize, stride, pad, (int)(K / 8), (int)Wn, plane_fmt, out_planes, out_planes + M * K);
+    } else {
+        im2col_nchw_kernel<<<grid_for(M * (K / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            img, M * (K / 8), (int)C, (int)H, (int)W, (int)Ho, (int)Wo, ksize, stride, pad, (int)(K / 8), plane_fmt, out_planes,
+            out_planes + M * K);
+    }
     SLB_LAUNCH_OK("im2col_nchw");
     return SLB_OK;
 }

@@ -57,6 +57,8 @@ struct GemmParams {
     const float* col_scale;  // [N] or null
     float* out_f32;          // [M,N] or null
     uint16_t* out_planes;    // [2,M,N] or null
+    float* raw_f32;          // [M,N] or null: alpha * (A W^T) * row_scale BEFORE column scale / bias / activation / residual —
+                             // the raw output of a convolution whose BatchNorm rides in this epilogue, for a forward hook
     int epilogue;
     int passes;  // 3 or 1
     int split_acc;  // 1: hi·lo + lo·hi accumulate in their own TMEM columns and meet hi·hi in the epilogue (fp32 add)
@@ -186,6 +188,7 @@ __device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr,
             if (m >= p.M) continue;
             const float4 x = *reinterpret_cast<const float4*>(tile + rr * kTileStride + c4);
             float o[4] = {x.x, x.y, x.z, x.w};
+            if (p.raw_f32) *reinterpret_cast<float4*>(p.raw_f32 + m * p.N + n) = x;
             if (p.col_scale) { o[0] *= cs.x; o[1] *= cs.y; o[2] *= cs.z; o[3] *= cs.w; }
             o[0] += bs.x; o[1] += bs.y; o[2] += bs.z; o[3] += bs.w;
             if (p.epilogue != SLB_EPI_NONE && p.epilogue != SLB_EPI_ADD_RELU) {
@@ -714,14 +717,14 @@ extern "C" int slb_split_planes(const float* x, int64_t n, int plane_fmt, float 
 
 static int run_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, GemmParams p, void* stream);
 
-extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, int plane_fmt, int64_t M, int64_t N,
-                              int64_t K, float alpha, const float* bias, const float* residual, const float* row_scale,
-                              const float* col_scale, int epilogue, int passes, float* out_f32, uint16_t* out_planes,
-                              void* stream) {
+static int gemm_split_impl(const uint16_t* a_planes, const uint16_t* w_planes, int plane_fmt, int64_t M, int64_t N,
+                           int64_t K, float alpha, const float* bias, const float* residual, const float* row_scale,
+                           const float* col_scale, int epilogue, int passes, float* out_f32, uint16_t* out_planes, float* raw_f32,
+                           void* stream) {
     SLB_REQUIRE(M >= 0 && N >= 0 && K >= 0, SLB_EINVAL, "slb_gemm_split: negative size");
     if (M == 0 || N == 0) return SLB_OK;
     SLB_REQUIRE(a_planes && w_planes, SLB_EINVAL, "slb_gemm_split: null operand");
-    SLB_REQUIRE(out_f32 || out_planes, SLB_EINVAL, "slb_gemm_split: no output requested");
+    SLB_REQUIRE(out_f32 || out_planes || raw_f32, SLB_EINVAL, "slb_gemm_split: no output requested");
     SLB_REQUIRE(plane_fmt == SLB_PLANE_F16 || plane_fmt == SLB_PLANE_BF16, SLB_EINVAL, "slb_gemm_split: bad plane format");
     SLB_REQUIRE(passes == 1 || passes == 3 || passes == SLB_PASSES_SPLIT_ACC, SLB_EINVAL,
                 "slb_gemm_split: passes must be 1, 3 or SLB_PASSES_SPLIT_ACC");
@@ -732,12 +735,14 @@ extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes
     p.bias = bias; p.residual = residual; p.row_scale = row_scale; p.col_scale = col_scale;
     p.out_f32 = out_f32; p.out_planes = out_planes;
     p.epilogue = epilogue; p.passes = passes; p.fmt = plane_fmt;
+    p.raw_f32 = raw_f32;
     return run_gemm_split(a_planes, w_planes, p, stream);
 }
 
-extern "C" int slb_conv_gemm(const uint16_t* x_planes, int64_t B, int64_t H, int64_t W, int64_t C, int ksize, int stride, int pad,
-                             const uint16_t* w_planes, int64_t N, int plane_fmt, float alpha, const float* bias, const float* residual,
-                             const float* col_scale, int epilogue, int passes, float* out_f32, uint16_t* out_planes, void* stream) {
+static int conv_gemm_impl(const uint16_t* x_planes, int64_t B, int64_t H, int64_t W, int64_t C, int ksize, int stride, int pad,
+                          const uint16_t* w_planes, int64_t N, int plane_fmt, float alpha, const float* bias, const float* residual,
+                          const float* col_scale, int epilogue, int passes, float* out_f32, uint16_t* out_planes, float* raw_f32,
+                          void* stream) {
     SLB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && N >= 0, SLB_EINVAL, "slb_conv_gemm: bad size");
     SLB_REQUIRE(ksize >= 1 && ksize <= 7 && (stride == 1 || stride == 2) && pad >= 0 && pad <= 7, SLB_EUNSUPPORTED,
                 "slb_conv_gemm: filter %d, stride %d, pad %d", ksize, stride, pad);
@@ -746,7 +751,7 @@ extern "C" int slb_conv_gemm(const uint16_t* x_planes, int64_t B, int64_t H, int
     SLB_REQUIRE(Ho > 0 && Wo > 0, SLB_EINVAL, "slb_conv_gemm: empty output");
     const int64_t M = B * Ho * Wo;
     if (M == 0 || N == 0) return SLB_OK;
-    SLB_REQUIRE(x_planes && w_planes && (out_f32 || out_planes), SLB_EINVAL, "slb_conv_gemm: null pointer");
+    SLB_REQUIRE(x_planes && w_planes && (out_f32 || out_planes || raw_f32), SLB_EINVAL, "slb_conv_gemm: null pointer");
     SLB_REQUIRE(plane_fmt == SLB_PLANE_F16 || plane_fmt == SLB_PLANE_BF16, SLB_EINVAL, "slb_conv_gemm: bad plane format");
     SLB_REQUIRE(passes == 1 || passes == 3 || passes == SLB_PASSES_SPLIT_ACC, SLB_EINVAL, "slb_conv_gemm: bad passes");
     SLB_REQUIRE(epilogue >= SLB_EPI_NONE && epilogue <= SLB_EPI_ADD_RELU, SLB_EINVAL, "slb_conv_gemm: bad epilogue");
@@ -759,7 +764,39 @@ extern "C" int slb_conv_gemm(const uint16_t* x_planes, int64_t B, int64_t H, int
     p.conv = 1; p.conv_cc = (int)(C / 64); p.conv_k = ksize; p.conv_stride = stride; p.conv_pad = pad;
     p.conv_ho = (int)Ho; p.conv_wo = (int)Wo;
     p.conv_x = x_planes; p.conv_B = B; p.conv_H = H; p.conv_W = W; p.conv_C = C;
+    p.raw_f32 = raw_f32;
     return run_gemm_split(x_planes, w_planes, p, stream);
+}
+
+extern "C" int slb_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, int plane_fmt, int64_t M, int64_t N, int64_t K,
+                              float alpha, const float* bias, const float* residual, const float* row_scale, const float* col_scale,
+                              int epilogue, int passes, float* out_f32, uint16_t* out_planes, void* stream) {
+    return gemm_split_impl(a_planes, w_planes, plane_fmt, M, N, K, alpha, bias, residual, row_scale, col_scale, epilogue, passes, out_f32,
+                           out_planes, nullptr, stream);
+}
+
+extern "C" int slb_gemm_split_raw(const uint16_t* a_planes, const uint16_t* w_planes, int plane_fmt, int64_t M, int64_t N, int64_t K,
+                                  float alpha, const float* bias, const float* residual, const float* row_scale, const float* col_scale,
+                                  int epilogue, int passes, float* out_f32, uint16_t* out_planes, float* raw_f32, void* stream) {
+    SLB_REQUIRE(raw_f32 != nullptr && ((uintptr_t)raw_f32 % 16) == 0, SLB_EINVAL, "slb_gemm_split_raw: raw_f32 must be a 16-byte aligned buffer");
+    return gemm_split_impl(a_planes, w_planes, plane_fmt, M, N, K, alpha, bias, residual, row_scale, col_scale, epilogue, passes, out_f32,
+                           out_planes, raw_f32, stream);
+}
+
+extern "C" int slb_conv_gemm(const uint16_t* x_planes, int64_t B, int64_t H, int64_t W, int64_t C, int ksize, int stride, int pad,
+                             const uint16_t* w_planes, int64_t N, int plane_fmt, float alpha, const float* bias, const float* residual,
+                             const float* col_scale, int epilogue, int passes, float* out_f32, uint16_t* out_planes, void* stream) {
+    return conv_gemm_impl(x_planes, B, H, W, C, ksize, stride, pad, w_planes, N, plane_fmt, alpha, bias, residual, col_scale, epilogue, passes,
+                          out_f32, out_planes, nullptr, stream);
+}
+
+extern "C" int slb_conv_gemm_raw(const uint16_t* x_planes, int64_t B, int64_t H, int64_t W, int64_t C, int ksize, int stride, int pad,
+                                 const uint16_t* w_planes, int64_t N, int plane_fmt, float alpha, const float* bias, const float* residual,
+                                 const float* col_scale, int epilogue, int passes, float* out_f32, uint16_t* out_planes, float* raw_f32,
+                                 void* stream) {
+    SLB_REQUIRE(raw_f32 != nullptr && ((uintptr_t)raw_f32 % 16) == 0, SLB_EINVAL, "slb_conv_gemm_raw: raw_f32 must be a 16-byte aligned buffer");
+    return conv_gemm_impl(x_planes, B, H, W, C, ksize, stride, pad, w_planes, N, plane_fmt, alpha, bias, residual, col_scale, epilogue, passes,
+                          out_f32, out_planes, raw_f32, stream);
 }
 
 // Fused redundancy row maxima (see GemmParams::rowmax): planes (2, n_pad, K) of the unit-norm rows, rowmax [n] = -inf.

@@ -213,4 +213,20 @@ __device__ __forceinline__ void slb_split2(float v, int fmt, uint16_t& hi, uint1
 __device__ __forceinline__ void slb_split2_act(float v, int fmt, uint16_t& hi, uint16_t& lo) {
     slb_split2(v * SLB_ACT_PLANE_SCALE, fmt, hi, lo);
 }
+// Two values at once, fp16 planes: hi = the scaled value with its low 13 mantissa bits cleared (exact in fp16 above the
+// subnormal range), lo = the exact remainder rounded to fp16 — two packed conversions per pair instead of four scalar ones
+// and two conversions back. hi + lo carries the same 22 bits as slb_split2 (hi is truncated instead of rounded, so the
+// planes differ in the last place of hi while their sum agrees to 2^-22); saturates like slb_split2, NaN goes through.
+__device__ __forceinline__ void slb_split_pair_act_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    x0 *= SLB_ACT_PLANE_SCALE;
+    x1 *= SLB_ACT_PLANE_SCALE;
+    if (x0 == x0) x0 = fminf(fmaxf(x0, -65504.0f), 65504.0f);
+    if (x1 == x1) x1 = fminf(fmaxf(x1, -65504.0f), 65504.0f);
+    const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+    const float h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+    const __half2 hp = __floats2half2_rn(h0, h1);
+    const __half2 lp = __floats2half2_rn(x0 - h0, x1 - h1);
+    hi = *reinterpret_cast<const uint32_t*>(&hp);
+    lo = *reinterpret_cast<const uint32_t*>(&lp);
+}
 #endif  // __CUDACC__

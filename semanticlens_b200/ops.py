@@ -203,8 +203,10 @@ def gemm_split(
     alpha: float = 1.0,
     out_f32: torch.Tensor | bool = True,
     out_planes: torch.Tensor | bool = False,
+    raw_f32: torch.Tensor | None = None,
 ):
     """K4: act(alpha * (A @ W^T) * row_scale * col_scale + bias) + residual from split planes (2, M, K) and (2, N, K).
+    ``raw_f32`` (M, N) fp32: also receives alpha * (A @ W^T) * row_scale, the value before column scale / bias / activation.
 
     ``alpha`` = 1 / (scale of the A planes * scale of the W planes). ``out_planes`` are written at N.ACT_PLANE_SCALE.
 
@@ -234,11 +236,14 @@ def gemm_split(
             assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape, (t.shape, shape)
     if out_planes is not None:
         assert tuple(out_planes.shape) == (2, M, Nn) and out_planes.is_contiguous() and out_planes.dtype == a_planes.dtype
+    args = (a_planes.data_ptr(), w_planes.data_ptr(), fmt, M, Nn, K, float(alpha), N.ptr(bias), N.ptr(residual), N.ptr(row_scale),
+            N.ptr(col_scale), epilogue, passes, N.ptr(out_f32), N.ptr(out_planes))
     with _dev_guard(a_planes):
-        rc = lib.slb_gemm_split(
-            a_planes.data_ptr(), w_planes.data_ptr(), fmt, M, Nn, K, float(alpha), N.ptr(bias), N.ptr(residual), N.ptr(row_scale),
-            N.ptr(col_scale), epilogue, passes, N.ptr(out_f32), N.ptr(out_planes), N.stream_ptr(dev),
-        )
+        if raw_f32 is not None:
+            assert raw_f32.dtype == torch.float32 and raw_f32.is_contiguous() and tuple(raw_f32.shape) == (M, Nn)
+            rc = lib.slb_gemm_split_raw(*args, raw_f32.data_ptr(), N.stream_ptr(dev))
+        else:
+            rc = lib.slb_gemm_split(*args, N.stream_ptr(dev))
     N.check(rc, "slb_gemm_split")
     return out_f32, out_planes
 
@@ -427,7 +432,7 @@ def im2col_nchw(img: torch.Tensor, ksize: int, stride: int, pad: int, fmt: int =
 def conv_gemm(x_planes: torch.Tensor, B: int, H: int, W: int, w_planes: torch.Tensor, ksize: int, stride: int, pad: int, *,
               bias: torch.Tensor | None = None, residual: torch.Tensor | None = None, col_scale: torch.Tensor | None = None,
               epilogue: int = N.EPI_NONE, passes: int = 3, alpha: float = 1.0, out_f32: torch.Tensor | bool = True,
-              out_planes: torch.Tensor | bool = False):
+              out_planes: torch.Tensor | bool = False, raw_f32: torch.Tensor | None = None):
     """Implicit-GEMM convolution over channels-last planes (2, B*H*W, C) with weights (2, Cout, ksize*ksize*C), columns
     ordered (ky, kx, c). No im2col matrix: TMA im2col-mode loads feed the tcgen05 GEMM. Returns (fp32 | None, planes | None)
     of shape (B*Ho*Wo, Cout)."""
@@ -452,10 +457,14 @@ def conv_gemm(x_planes: torch.Tensor, B: int, H: int, W: int, w_planes: torch.Te
     for t, shape in ((bias, (Nn,)), (residual, (M, Nn)), (col_scale, (Nn,)), (out_f32, (M, Nn))):
         if t is not None:
             assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape, (t.shape, shape)
+    args = (x_planes.data_ptr(), B, H, W, C, ksize, stride, pad, w_planes.data_ptr(), Nn, fmt, float(alpha), N.ptr(bias), N.ptr(residual),
+            N.ptr(col_scale), epilogue, passes, N.ptr(out_f32), N.ptr(out_planes))
     with _dev_guard(x_planes):
-        rc = lib.slb_conv_gemm(x_planes.data_ptr(), B, H, W, C, ksize, stride, pad, w_planes.data_ptr(), Nn, fmt, float(alpha),
-                               N.ptr(bias), N.ptr(residual), N.ptr(col_scale), epilogue, passes, N.ptr(out_f32), N.ptr(out_planes),
-                               N.stream_ptr(dev))
+        if raw_f32 is not None:
+            assert raw_f32.dtype == torch.float32 and raw_f32.is_contiguous() and tuple(raw_f32.shape) == (M, Nn)
+            rc = lib.slb_conv_gemm_raw(*args, raw_f32.data_ptr(), N.stream_ptr(dev))
+        else:
+            rc = lib.slb_conv_gemm(*args, N.stream_ptr(dev))
     N.check(rc, "slb_conv_gemm")
     return out_f32, out_planes
 

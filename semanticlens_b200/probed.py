@@ -170,7 +170,16 @@ class AcceleratedResNet:
         (fp32 map | None, planes | None) of the (B, Ho, Wo, cout) output. A hooked convolution leaves its raw output first."""
         Ho, Wo = ops.conv_out(H, c.k, c.stride, c.pad), ops.conv_out(W, c.k, c.stride, c.pad)
         keep32 = out_f32 if out_f32 is not None else bool(want_f32)
-        if self._hooked(c.module):
+        if self._hooked(c.module) and c.bias is None and not (residual is not None and not relu):
+            # the hook wants the RAW convolution output: the GEMM leaves it (raw_f32) next to the BatchNorm / ReLU / shortcut
+            # result of the same epilogue — one pass over the accumulator, no second kernel
+            raw = torch.empty((B * Ho * Wo, c.cout), dtype=torch.float32, device=x_planes.device)
+            epi = (N.EPI_ADD_RELU if residual is not None else N.EPI_RELU) if relu else N.EPI_NONE
+            out = self._mm(c, x_planes, B, H, W, bias=c.shift, residual=residual, col_scale=c.scale, epilogue=epi, out_f32=keep32,
+                           out_planes=want_planes, raw_f32=raw)
+            _fire(c.module, _as_nchw(raw, B, Ho, Wo))
+            return out
+        if self._hooked(c.module):  # a convolution with its own bias: raw output first, then the affine + activation pass
             raw, _ = self._mm(c, x_planes, B, H, W, bias=c.bias, epilogue=N.EPI_NONE)
             _fire(c.module, _as_nchw(raw, B, Ho, Wo))
             shift = c.shift if c.bias is None else (c.shift - c.bias * c.scale)  # raw already holds the bias

@@ -96,6 +96,24 @@ def test_implicit_gemm_convolution(ops, B, H, W, C, k, s, cout):
     assert torch.equal(got, ref)
 
 
+@pytest.mark.parametrize("M,K,N", [(300, 64, 64), (128, 576, 256), (1000, 256, 72)])
+def test_raw_output_rides_along_with_the_fused_epilogue(ops, M, K, N):
+    """raw_f32 = the GEMM before column scale / bias / activation / residual, bit-identical to a plain GEMM, while the fused
+    outputs are bit-identical to the same call without it (a hooked nn.Conv2d sees its raw output at no extra pass)."""
+    g = torch.Generator().manual_seed(M + K)
+    a = ops.split_planes(torch.randn(M, K, generator=g).cuda(), 0, ACT)
+    w = ops.split_planes((torch.randn(N, K, generator=g) * K**-0.5).cuda(), 0, WSC)
+    sc, sh = (torch.rand(N, generator=g) + 0.5).cuda(), torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda()
+    kw = dict(alpha=1.0 / (ACT * WSC), passes=4)
+    plain, _ = ops.gemm_split(a, w, **kw)
+    for epi, r in ((4, None), (5, res), (0, None)):
+        want32, wantp = ops.gemm_split(a, w, bias=sh, col_scale=sc, residual=r, epilogue=epi, out_planes=True, **kw)
+        raw = torch.full((M, N), float("nan"), device="cuda")
+        got32, gotp = ops.gemm_split(a, w, bias=sh, col_scale=sc, residual=r, epilogue=epi, out_planes=True, raw_f32=raw, **kw)
+        assert torch.equal(raw, plain) and torch.equal(got32, want32) and torch.equal(gotp, wantp)
+
+
 @pytest.mark.parametrize("B,H,W,C", [(2, 8, 8, 16), (1, 7, 9, 24), (3, 56, 56, 256)])
 def test_subsample2_is_a_pure_move(ops, B, H, W, C):
     a = torch.randn(B, H, W, C, generator=torch.Generator().manual_seed(C))
