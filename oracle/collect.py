@@ -122,10 +122,14 @@ def aggregate_canonical(x: np.ndarray, op: str, kind: str, token: int = 0) -> np
         n = L
         r = r.reshape(B, C)
     else:
+        # two-level order: blocks of 64 tokens folded sequentially from the identity, block partials folded in block order
         B, T, F = xf.shape
         acc = np.full((B, F), ident, dtype=np.float32)
-        for t_ in range(T):
-            acc = _fold(acc, xf[:, t_], is_max)
+        for t0 in range(0, T, 64):
+            part = np.full((B, F), ident, dtype=np.float32)
+            for t_ in range(t0, min(t0 + 64, T)):
+                part = _fold(part, xf[:, t_], is_max)
+            acc = _fold(acc, part, is_max)
         r, n = acc, T
     if not is_max:
         r = (r / np.float32(n)).astype(np.float32)

@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent.parent))
 from semanticlens_b200 import ops
 C = 296 * 8
 g = torch.Generator(device="cuda").manual_seed(2)

@@ -10,7 +10,8 @@
 //   element e goes to accumulator (ws, lane) = ((e / 32) % 8, e % 32), each accumulator folds its elements in
 //   increasing e starting from the identity (+0.0f / -inf); the 8 ws-accumulators of a lane are combined as
 //   ((a0+a1)+(a2+a3))+((a4+a5)+(a6+a7)); the 32 lanes by an xor butterfly 16,8,4,2,1.
-// Canonical order (BTF): plain sequential fold over t = 0..T-1 per (b, f).
+// Canonical order (BTF): the T tokens of a chain (b, f) are cut into blocks of 64; each block is folded sequentially from
+//   the identity, the block partials are folded sequentially in block order (T <= 64: one plain sequential fold).
 // mean = sum / (float)L (IEEE division), then rounded once to the input dtype (no-op for fp32).
 #include "slb_common.cuh"
 
@@ -460,88 +461,147 @@ __global__ void __launch_bounds__(kThreads) agg_rows_direct_cta_kernel(const T* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// BTF: x (B, T, F) -> out (B, F); CTA = (b, slab of up to 256 features); tiles of TC tokens staged by
-// one bulk copy per token row; thread i folds feature f0+i sequentially over t.
+// BTF: x (B, T, F) -> out (B, F) — token maps of transformers and the channels-last maps (B, H*W, C) of the accelerated
+// probed forward. A chain (b, f) walks T rows that lie F elements apart, so the parallelism of a strictly sequential
+// fold is B*F chains — 8192 for a 64-channel 112x112 map, far too few loads in flight for HBM. The canonical order is
+// therefore two-level (shape-only, so still invariant to batch size / grid / code path):
+//   the tokens are cut into blocks of 64; a block is folded sequentially from the identity, the block partials are
+//   folded sequentially in block order (T <= 64: one plain sequential fold).
+// CTA = (image, group of 32*VEC features), 4 warps; lane = VEC adjacent features (one 4..16-byte load per row, a warp reads
+// 128..512 contiguous bytes of every row); warp w owns blocks w, w+4, ... and keeps 4 KB of rows
+// in flight in registers (8..32 independent loads per lane, five CTAs per SM) before folding them in order; the partials meet in
+// shared memory and warp 0 folds them in block order. No staging ring: every byte is read once, straight into registers.
 // ------------------------------------------------------------------------------------------------
+constexpr int kBtfThreads = 128;
+constexpr int kBtfWarps = 4;
+constexpr int kBtfBlock = 64;          // tokens per canonical block
+constexpr int kBtfChunkFloats = 8192;  // partials staged per in-order combine (32 KB)
+
 struct BtfParams {
     const void* x;
     float* out;
     int64_t B;
     int T;
     int64_t F;
-    int slabs;       // ceil(F / 256)
-    int tok_per_tile;
-    int use_bulk;
+    int groups;  // ceil(F / (32 * VEC)) feature groups per image
 };
 
-struct __align__(16) BtfSmem {
-    uint64_t full[kStages];
+// raw per-lane load of BYTES bytes kept as 32-bit words (so that the rows in flight provably stay in registers)
+template <int BYTES>
+struct BtfRaw;
+template <>
+struct BtfRaw<2> {
+    uint32_t w[1];
+    __device__ __forceinline__ void load(const void* q) { w[0] = *static_cast<const uint16_t*>(q); }
+};
+template <>
+struct BtfRaw<4> {
+    uint32_t w[1];
+    __device__ __forceinline__ void load(const void* q) { w[0] = *static_cast<const uint32_t*>(q); }
+};
+template <>
+struct BtfRaw<8> {
+    uint32_t w[2];
+    __device__ __forceinline__ void load(const void* q) {
+        const uint2 t = *static_cast<const uint2*>(q);
+        w[0] = t.x; w[1] = t.y;
+    }
+};
+template <>
+struct BtfRaw<16> {
+    uint32_t w[4];
+    __device__ __forceinline__ void load(const void* q) {
+        const uint4 t = *static_cast<const uint4*>(q);
+        w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+    }
 };
 
-template <typename T, int OP>
-__global__ void __launch_bounds__(kThreads, 2) agg_btf_kernel(BtfParams p) {
+template <typename T>
+__device__ __forceinline__ float btf_elem(const uint32_t* w, int e);
+template <>
+__device__ __forceinline__ float btf_elem<float>(const uint32_t* w, int e) { return __uint_as_float(w[e]); }
+template <>
+__device__ __forceinline__ float btf_elem<__half>(const uint32_t* w, int e) {
+    return __half2float(__ushort_as_half((unsigned short)(w[e >> 1] >> (16 * (e & 1)))));
+}
+template <>
+__device__ __forceinline__ float btf_elem<__nv_bfloat16>(const uint32_t* w, int e) {
+    return __uint_as_float((w[e >> 1] >> (16 * (e & 1))) << 16);
+}
+
+template <typename T, int OP, int VEC>
+__global__ void __launch_bounds__(kBtfThreads, 5) agg_btf_kernel(BtfParams p) {
     using A = Agg<OP>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* stage_base = smem_raw;
-    BtfSmem* ss = reinterpret_cast<BtfSmem*>(smem_raw + kStages * kStageBytes);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const T* x = static_cast<const T*>(p.x);
+    constexpr int kBytes = (int)sizeof(T) * VEC;
+    using Raw = BtfRaw<kBytes>;
+    constexpr int kRows = kBytes <= 4 ? 32 : 128 / kBytes;  // rows in flight per lane: 32 / 16 / 8 (32 registers, 4 KB per warp)
+    constexpr int kChunkBlocks = kBtfChunkFloats / (32 * VEC);
+    extern __shared__ __align__(16) float btf_part[];  // [min(n_blocks, kChunkBlocks)][32 * VEC]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b = blockIdx.x / p.groups;
+    const int grp = (int)(blockIdx.x % p.groups);
+    const int64_t f = (int64_t)grp * (32 * VEC) + (int64_t)lane * VEC;
+    const bool active = f < p.F;  // F % VEC == 0: a lane's features are all inside or all outside
+    const T* src = static_cast<const T*>(p.x) + (b * p.T) * p.F + (active ? f : 0);
+    const int n_blocks = (p.T + kBtfBlock - 1) / kBtfBlock;
 
-    const int64_t b = blockIdx.x / p.slabs;
-    const int slab = (int)(blockIdx.x % p.slabs);
-    const int64_t f0 = (int64_t)slab * 256;
-    const int fs = (int)min((int64_t)256, p.F - f0);
-    const T* src0 = x + (b * p.T) * p.F + f0;
-    const int n_tiles = (p.T + p.tok_per_tile - 1) / p.tok_per_tile;
-    const uint32_t row_bytes = (uint32_t)(fs * sizeof(T));
+    float total[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) total[e] = A::identity();
 
-    float acc = A::identity();
-
-    if (p.use_bulk) {
-        if (tid == 0) {
-            for (int s = 0; s < kStages; ++s) slb_mbar_init(&ss->full[s], 1);
-            slb_fence_mbar_init();
+    for (int c0 = 0; c0 < n_blocks; c0 += kChunkBlocks) {
+        const int nb = min(kChunkBlocks, n_blocks - c0);
+        for (int j = warp; j < nb; j += kBtfWarps) {
+            const int t0 = (c0 + j) * kBtfBlock;
+            float acc[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] = A::identity();
+            if (active) {
+                const T* q = src + (int64_t)t0 * p.F;
+                if (t0 + kBtfBlock <= p.T) {
+#pragma unroll 1
+                    for (int h = 0; h < kBtfBlock / kRows; ++h) {
+                        Raw v[kRows];
+#pragma unroll
+                        for (int u = 0; u < kRows; ++u) v[u].load(q + (int64_t)(h * kRows + u) * p.F);
+#pragma unroll
+                        for (int u = 0; u < kRows; ++u)
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) acc[e] = A::fold(acc[e], A::pre(btf_elem<T>(v[u].w, e)));
+                    }
+                } else {  // the last, partial block: the bound is uniform over the warp
+                    const int nt = p.T - t0;
+#pragma unroll 1
+                    for (int h = 0; h * kRows < nt; ++h) {
+                        Raw v[kRows];
+#pragma unroll
+                        for (int u = 0; u < kRows; ++u)
+                            if (h * kRows + u < nt) v[u].load(q + (int64_t)(h * kRows + u) * p.F);
+#pragma unroll
+                        for (int u = 0; u < kRows; ++u)
+                            if (h * kRows + u < nt) {
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) acc[e] = A::fold(acc[e], A::pre(btf_elem<T>(v[u].w, e)));
+                            }
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) btf_part[(size_t)j * (32 * VEC) + lane * VEC + e] = acc[e];
         }
         __syncthreads();
-        // warp 0 is the producer: lane j issues the copy of token row j of the tile
-        auto issue = [&](int i) {
-            int s = i % kStages;
-            int t0 = i * p.tok_per_tile;
-            int nt = min(p.tok_per_tile, p.T - t0);
-            unsigned char* dst = stage_base + (size_t)s * kStageBytes;
-            if (lane == 0) slb_mbar_arrive_expect_tx(&ss->full[s], row_bytes * (uint32_t)nt);
-            __syncwarp();
-            for (int j = lane; j < nt; j += 32)
-                slb_bulk_g2s(dst + (size_t)j * row_bytes, src0 + (int64_t)(t0 + j) * p.F, row_bytes, &ss->full[s]);
-        };
-        if (warp == 0)
-            for (int i = 0; i < kStages && i < n_tiles; ++i) issue(i);
-        for (int i = 0; i < n_tiles; ++i) {
-            const int s = i % kStages;
-            slb_mbar_wait(&ss->full[s], (uint32_t)((i / kStages) & 1));
-            const T* tile = reinterpret_cast<const T*>(stage_base + (size_t)s * kStageBytes);
-            const int nt = min(p.tok_per_tile, p.T - i * p.tok_per_tile);
-            if (tid < fs) {
-                for (int t = 0; t < nt; ++t) acc = A::fold(acc, A::pre(to_f32<T>(tile[(size_t)t * fs + tid])));
-            }
-            __syncthreads();
-            if (warp == 0 && i + kStages < n_tiles) issue(i + kStages);
-        }
-    } else {
-        if (tid < fs) {
-            const T* q = src0 + tid;
-            int t = 0;
-            for (; t + 8 <= p.T; t += 8) {
-                float v[8];
+        if (warp == 0) {
+            for (int j = 0; j < nb; ++j) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = A::pre(to_f32<T>(q[(int64_t)(t + j) * p.F]));
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc = A::fold(acc, v[j]);
+                for (int e = 0; e < VEC; ++e) total[e] = A::fold(total[e], btf_part[(size_t)j * (32 * VEC) + lane * VEC + e]);
             }
-            for (; t < p.T; ++t) acc = A::fold(acc, A::pre(to_f32<T>(q[(int64_t)t * p.F])));
         }
+        __syncthreads();
     }
-    if (tid < fs) p.out[b * p.F + f0 + tid] = round_to_input<T>(A::finish(acc, p.T));
+    if (warp == 0 && active) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) p.out[b * p.F + f + e] = round_to_input<T>(A::finish(total[e], p.T));
+    }
 }
 
 template <typename T>
@@ -664,26 +724,39 @@ int launch_rows(const void* x, float* out, int64_t n_rows, int64_t L, cudaStream
     return SLB_OK;
 }
 
+template <typename T, int OP, int VEC>
+int launch_btf_vec(const BtfParams& p0, cudaStream_t st) {
+    BtfParams p = p0;
+    p.groups = (int)slb_ceil_div(p.F, (int64_t)32 * VEC);
+    const int64_t grid = p.B * p.groups;
+    SLB_REQUIRE(grid <= 0x7FFFFFFF, SLB_EUNSUPPORTED, "agg_btf: grid too large");
+    const int n_blocks = (p.T + kBtfBlock - 1) / kBtfBlock;
+    const size_t smem = (size_t)std::min(n_blocks, kBtfChunkFloats / (32 * VEC)) * (32 * VEC) * sizeof(float);
+    agg_btf_kernel<T, OP, VEC><<<(int)grid, kBtfThreads, smem, st>>>(p);
+    SLB_LAUNCH_OK("agg_btf");
+    return SLB_OK;
+}
+
 template <typename T, int OP>
 int launch_btf(const void* x, float* out, int64_t B, int64_t T_, int64_t F, cudaStream_t st) {
     BtfParams p{};
     p.x = x; p.out = out; p.B = B; p.T = (int)T_; p.F = F;
-    p.slabs = (int)slb_ceil_div(F, 256);
-    const size_t esz = sizeof(T);
-    // bulk rows need 16-byte aligned starts and sizes for every (b, t, slab)
-    bool ok = ((uintptr_t)x % 16) == 0 && ((F * (int64_t)esz) % 16) == 0 && ((256 * esz) % 16) == 0 &&
-              (((F % 256) * (int64_t)esz) % 16) == 0 && !force_direct();
-    p.use_bulk = ok ? 1 : 0;
-    int64_t slab_row_bytes = std::min<int64_t>(F, 256) * (int64_t)esz;
-    p.tok_per_tile = (int)std::max<int64_t>(1, std::min<int64_t>(kStageBytes / slab_row_bytes, 64));
-    const size_t smem = (size_t)kStages * kStageBytes + sizeof(BtfSmem);
-    auto kern = agg_btf_kernel<T, OP>;
-    SLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t grid = B * p.slabs;
-    SLB_REQUIRE(grid <= 0x7FFFFFFF, SLB_EUNSUPPORTED, "agg_btf: grid too large");
-    kern<<<(int)grid, kThreads, smem, st>>>(p);
-    SLB_LAUNCH_OK("agg_btf");
-    return SLB_OK;
+    // widest per-lane vector (16 bytes at most) that divides F, keeps every row start aligned and still leaves at least
+    // two CTAs per SM; narrower vectors mean more, smaller CTAs
+    const int64_t want = 2 * (int64_t)slb_sm_count();
+    constexpr int kMaxVec = 16 / (int)sizeof(T);
+    int vec = 1;
+    for (int v = kMaxVec; v > 1; v >>= 1) {
+        const bool fits = (F % v) == 0 && ((uintptr_t)x % (v * sizeof(T))) == 0;
+        if (fits && B * slb_ceil_div(F, (int64_t)32 * v) >= want) { vec = v; break; }
+    }
+    switch (vec) {
+        case 8:
+            if constexpr (kMaxVec >= 8) return launch_btf_vec<T, OP, 8>(p, st);
+        case 4: return launch_btf_vec<T, OP, 4>(p, st);
+        case 2: return launch_btf_vec<T, OP, 2>(p, st);
+        default: return launch_btf_vec<T, OP, 1>(p, st);
+    }
 }
 
 template <typename T>

@@ -85,9 +85,11 @@ def test_gemm_epilogues(ops, epi):
            2: lambda t: t * torch.sigmoid(1.702 * t), 3: lambda t: torch.nn.functional.gelu(t, approximate="tanh")}[epi]
     want = act(z) + res.double()
     assert rel_err(out, want) < 3e-6
-    # the planes output is the split of the fp32 output
-    ref_planes = ops.split_planes(out, 0, SA)  # out_planes carry the activation scale
-    assert torch.equal(planes, ref_planes)
+    # the planes output is the packed truncating split of the fp32 output at the activation scale (tc_common.cuh,
+    # slb_split_pair_act_f16): hi = the value with its low 13 mantissa bits cleared, lo = fp16(value - hi)
+    x = (out * SA).clamp(-65504.0, 65504.0)
+    h = (x.view(torch.int32) & -8192).view(torch.float32)
+    assert torch.equal(planes[0], h.half()) and torch.equal(planes[1], (x - h).half())
     assert rel_err((planes[0].double() + planes[1].double()) / SA, out.double()) < 1e-6
 
 
