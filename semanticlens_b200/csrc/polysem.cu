@@ -59,7 +59,10 @@ struct Smem {
     int ired[kWarps * 2];
     short moved[kT];   // examples that changed side this iteration, ascending; ~j encodes "left cluster 0"
     unsigned short in0[kThreads];  // bit `it`: the example starts restart `it` in cluster 0
-    int trow[kT];                  // row offsets of the packed upper triangle
+    int fb[kT / 8 + 1];            // first fragment of every 8-row band of the Gram slot
+    double red10[kWarps][kMaxInit];
+    double scan10[kWarps][kMaxInit / 2];
+    int ired10[kWarps][kMaxInit];
     int seed0[kMaxInit];           // second seed of every restart (the first is PolyParams::first)
     int cnt0[kMaxInit];            // size of cluster 0 after the first assignment
     int wcnt[kWarps];
@@ -91,6 +94,80 @@ __device__ __forceinline__ void block_sum(double (&v)[N], Smem& sm) {
     }
 }
 
+// N-wide versions (N <= kMaxInit): several restarts' reductions behind ONE pair of barriers — phase B is a chain of
+// block-wide reductions, each costing two barrier latencies, so the restarts are reduced together wherever they are independent
+template <int N>
+__device__ __forceinline__ void block_sumN(double (&v)[N], Smem& sm) {
+    static_assert(N <= kMaxInit, "red10 holds kMaxInit values per warp");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[n] += __shfl_xor_sync(0xffffffffu, v[n], o);
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) sm.red10[warp][n] = v[n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += sm.red10[w][n];
+        v[n] = t;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void block_countN(int (&v)[N], Smem& sm) {
+    static_assert(N <= kMaxInit, "ired10 holds kMaxInit values per warp");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int n = 0; n < N; ++n) v[n] = __reduce_add_sync(0xffffffffu, v[n]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) sm.ired10[warp][n] = v[n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += sm.ired10[w][n];
+        v[n] = t;
+    }
+}
+
+// N inclusive prefix sums over the threads (np.cumsum of N independent vectors)
+template <int N>
+__device__ __forceinline__ void block_scanN(double (&x)[N], Smem& sm) {
+    static_assert(N <= kMaxInit / 2, "scan10 holds kMaxInit / 2 values per warp");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, x[n], o);
+            if (lane >= o) x[n] += y;
+        }
+    }
+    __syncthreads();
+    if (lane == 31) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) sm.scan10[warp][n] = x[n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        double base = 0.0;
+        for (int w = 0; w < warp; ++w) base += sm.scan10[w][n];
+        x[n] += base;
+    }
+}
+
 __device__ __forceinline__ double block_sum1(double x, Smem& sm) {
     double v[1] = {x};
     block_sum<1>(v, sm);
@@ -117,22 +194,6 @@ __device__ __forceinline__ void block_count(int (&v)[N], Smem& sm) {
     }
 }
 
-// inclusive prefix sum over the threads (np.cumsum)
-__device__ __forceinline__ double block_scan(double x, Smem& sm) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-    }
-    __syncthreads();
-    if (lane == 31) sm.scan[warp] = x;
-    __syncthreads();
-    double base = 0.0;
-    for (int w = 0; w < warp; ++w) base += sm.scan[w];
-    return base + x;
-}
-
 // (max value, first index attaining it) over threads
 __device__ __forceinline__ void block_argmax(double& val, int& idx, Smem& sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -154,41 +215,26 @@ __device__ __forceinline__ void block_argmax(double& val, int& idx, Smem& sm) {
     }
 }
 
-// ---- Gram storage: packed upper triangle -----------------------------------------------------------
-// G0 is symmetric; a slot keeps rows a = 0..k-1 of the upper triangle back to back (row a holds columns a..k-1), i.e.
-// k(k+1)/2 doubles = 263 KB at k = 256. Two CTAs per SM keep 296 slots live: 78 MB, which stays inside the 126 MB L2 —
-// the full mirrored matrix (152 MB) did not, and every phase-B read went to DRAM (ncu: 30 % L2 hit rate, 7x the
-// algorithmic DRAM traffic). Thread i reads "column i": entries above the diagonal come from row j (coalesced over i),
-// entries below it from the thread's own row i (consecutive j -> consecutive addresses, served by L1 after the first touch).
-__host__ __device__ __forceinline__ int64_t slot_doubles(int64_t k) { return (k * (k + 1) / 2 + 1) & ~(int64_t)1; }  // even
-__device__ __forceinline__ int tri_row(int a, int k) { return a * k - (a * (a - 1)) / 2 - a; }  // + column; k <= 256: fits int
-// trow = the k row offsets, precomputed in shared memory: phase B is a latency-bound scalar loop at two warps per scheduler,
-// so every instruction saved per element shortens it (an on-the-fly tri_row cost ~10 integer instructions per load)
-__device__ __forceinline__ double gsym(const double* __restrict__ U, const int* __restrict__ trow, int i, int j) {
-    const int lo = min(i, j), hi = max(i, j);
-    return U[trow[lo] + hi];
+// ---- Gram storage: upper triangle packed as DMMA fragments --------------------------------------------------
+// G0 is symmetric. A slot keeps, for every band R of 8 rows and every group Kq >= 2R of 4 columns, the 8 x 4 block
+// G0[8R + g][4Kq + t] as 32 doubles in lane order g * 4 + t — exactly one A fragment of mma.m8n8k4.f64 — bands back to
+// back: 1056 fragments = 270 KB at k = 256. Two CTAs per SM keep 296 slots live: 80 MB, inside the 126 MB L2.
+// Every full pass over the matrix in phase B is a product G0 * W with a thin weight matrix W (ones -> row means; the
+// ten restarts' first memberships; the final membership) and runs on the FP64 tensor cores straight from this layout:
+// an A fragment on or above the diagonal is one 256-byte contiguous load for the warp; a fragment below the diagonal
+// is the transpose of half an 8 x 8 block stored above it, which in lane order is two contiguous 128-byte pieces. The
+// earlier layout (plain packed rows, thread i sweeping "column i" with scalar loads) touched 32 different lines per
+// warp instruction on the half of the sweep that ran along a thread's own row: ncu showed 18.5 sectors per request and the
+// sweeps bound by L1 tag throughput (35-40 % of the kernel's samples).
+__host__ __device__ __forceinline__ int frag_base(int R, int KQ) { return R * KQ - R * (R - 1); }  // fragments before band R
+__host__ __device__ __forceinline__ int64_t slot_doubles(int64_t k) {
+    const int NB = (int)((k + 7) >> 3), KQ = (int)((k + 3) >> 2);
+    return (int64_t)frag_base(NB, KQ) * 32;
 }
-
-// Sweep over "column i" of the symmetric Gram matrix by thread i, eight independent loads in flight (a load block
-// followed by a use block: left to itself the compiler interleaves one load with the arithmetic of the previous
-// element and every load pays the full L2 latency). f(j, G0[i][j]) is called in ascending j.
-// Two alternatives were measured and were slower at two warps per scheduler (scripts/time_polysem.py, r02 notes in
-// DESIGN.md): warp-cooperative row sums (more sequential round trips) and streaming the triangle through shared memory
-// with bulk copies (the CTA waits on the copies, 8 chunk hand-offs per sweep).
-template <typename F>
-__device__ __forceinline__ void sweep_column(const double* __restrict__ U, const int* __restrict__ trow, int i, int k, F&& f) {
-    const double* own = U + trow[i];  // row i of the packed triangle (+ column)
-    for (int j0 = 0; j0 < k; j0 += 8) {
-        double gv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int j = min(j0 + u, k - 1);
-            gv[u] = j < i ? U[trow[j] + i] : own[j];
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (j0 + u < k) f(j0 + u, gv[u]);
-    }
+// element (i, j) of the symmetric matrix; fb = the band offsets (in fragments) in shared memory
+__device__ __forceinline__ int frag_elem(const int* __restrict__ fb, int i, int j) {
+    const int lo = min(i, j), hi = max(i, j), R = lo >> 3;
+    return ((fb[R] + (hi >> 2) - 2 * R) << 5) + ((lo & 7) << 2) + (hi & 3);
 }
 
 // ---- phase A: G0 = X X^T (float64, DMMA) -----------------------------------------------------------
@@ -296,21 +342,143 @@ __device__ void gram_f64(const float* __restrict__ X, int k, int D, double* __re
             if (s + kStages < n_stage) request_stage(sm, ring, X, k, D, (s + kStages) * kStageCols, bulk, pol);
         }
         if (live) {
+            // accumulator (a, b) of lane (g, t) holds G0[32 bi + 8a + g][32 bj + 8b + 2t + {0, 1}]: two adjacent doubles of
+            // fragment (band 4 bi + a, group 8 bj + 2b + t / 2) — one 16-byte store; fragments below the diagonal are not kept
+            const int NB = (k + 7) >> 3, KQ = (k + 3) >> 2;
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    const int i = bi * 32 + a * 8 + g, j = bj * 32 + b * 8 + 2 * t;
-                    if (i < k) {
-                        double* row = G + tri_row(i, k);  // (phase A: once per tile row, not worth a table lookup)
-                        if (j >= i && j < k) row[j] = acc[a][b][0];
-                        if (j + 1 >= i && j + 1 < k) row[j + 1] = acc[a][b][1];
-                    }
+                    const int R = bi * 4 + a, Kq = bj * 8 + 2 * b + (t >> 1);
+                    if ((bi < bj || b >= a) && R < NB && Kq < KQ)
+                        *reinterpret_cast<double2*>(G + (((sm.fb[R] + Kq - 2 * R) << 5) + (g << 2) + ((t & 1) << 1))) =
+                            make_double2(acc[a][b][0], acc[a][b][1]);
                 }
             }
         }
     }
     __syncthreads();
+}
+
+// ---- phase B building block: Y = G0 * W on the FP64 tensor cores -------------------------------------------
+// W is k x (8 NT), given as wf(j, n); Y[row][n] is handed to out(row, n, y_n, y_n+1) two columns at a time. Warps 0..7 each
+// own four bands of 8 rows (warp w: bands w, w + 8, w + 16, w + 24) and walk the 4-column groups with 16 fragment loads
+// in flight per lane; the B fragments (weights) are shared by a warp's four bands. Warp 8 has no rows.
+template <int NT, typename WF, typename OUT>
+__device__ __forceinline__ void gram_times(const double* __restrict__ U, const int* __restrict__ fb, int k, WF&& wf, OUT&& out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp >= 8) return;
+    const int g = lane >> 2, t = lane & 3;
+    const int NB = (k + 7) >> 3, KQ = (k + 3) >> 2;
+    int band[4], base[4];
+    bool live[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        band[m] = warp + 8 * m;
+        live[m] = band[m] < NB;
+        base[m] = live[m] ? fb[band[m]] - 2 * band[m] : 0;
+    }
+    const int lo_off = (t << 2) + (g & 3);  // lane offset inside the half fragment that holds a transposed block
+    double acc[4][NT][2];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+    for (int q0 = 0; q0 < KQ; q0 += 4) {
+        double a[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int Kq = min(q0 + u, KQ - 1);  // a clamped group is loaded but not used
+            const int Rp = Kq >> 1;
+            const int tbase = ((fb[Rp] - 2 * Rp + (g >> 2)) << 5) + ((Kq & 1) << 4) + lo_off;  // + 2 * band * 32
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                // on / above the diagonal: fragment (band, Kq) as stored; below: rows 4 (Kq & 1) .. +3 of the two fragments
+                // (Kq / 2, 2 band) and (Kq / 2, 2 band + 1), read transposed — G0[8 band + g][4 Kq + t] either way
+                const int idx = (Kq >= 2 * band[m]) ? ((base[m] + Kq) << 5) + lane : tbase + (band[m] << 6);
+                a[u][m] = live[m] ? U[idx] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int Kq = q0 + u;
+            if (Kq < KQ) {
+                double bw[NT];
+#pragma unroll
+                for (int n = 0; n < NT; ++n) bw[n] = wf(4 * Kq + t, n * 8 + g);
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) dmma884(acc[m][n][0], acc[m][n][1], a[u][m], bw[n]);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+        if (live[m]) {
+#pragma unroll
+            for (int n = 0; n < NT; ++n) out(band[m] * 8 + g, n * 8 + 2 * t, acc[m][n][0], acc[m][n][1]);
+        }
+}
+
+// The same walk for one or two weight columns on the plain FP64 pipe: a DMMA spends 8 columns of work on them, and the
+// tensor pipe is what the other CTA's phase A is bound by. Lane (g, t) multiplies its fragment element by w[4 Kq + t] and
+// the four t-lanes of a row are added at the end. 32 loads in flight per lane.
+template <int NV, typename WF, typename OUT>
+__device__ __forceinline__ void gram_times_vec(const double* __restrict__ U, const int* __restrict__ fb, int k, WF&& wf, OUT&& out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp >= 8) return;
+    const int g = lane >> 2, t = lane & 3;
+    const int NB = (k + 7) >> 3, KQ = (k + 3) >> 2;
+    int band[4], base[4];
+    bool live[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        band[m] = warp + 8 * m;
+        live[m] = band[m] < NB;
+        base[m] = live[m] ? fb[band[m]] - 2 * band[m] : 0;
+    }
+    const int lo_off = (t << 2) + (g & 3);
+    double acc[4][NV];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[m][v] = 0.0;
+    for (int q0 = 0; q0 < KQ; q0 += 8) {
+        double a[8][4];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int Kq = min(q0 + u, KQ - 1);
+            const int Rp = Kq >> 1;
+            const int tbase = ((fb[Rp] - 2 * Rp + (g >> 2)) << 5) + ((Kq & 1) << 4) + lo_off;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int idx = (Kq >= 2 * band[m]) ? ((base[m] + Kq) << 5) + lane : tbase + (band[m] << 6);
+                a[u][m] = live[m] ? U[idx] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int Kq = q0 + u;
+            if (Kq < KQ) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const double w = wf(4 * Kq + t, v);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) acc[m][v] = fma(a[u][m], w, acc[m][v]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            double y = acc[m][v];
+            y += __shfl_xor_sync(0xffffffffu, y, 1);
+            y += __shfl_xor_sync(0xffffffffu, y, 2);
+            if (live[m] && t == 0) out(band[m] * 8 + g, v, y);
+        }
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
@@ -326,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
     const bool on = i < k;
     double* G = p.G + (int64_t)blockIdx.x * slot_doubles(k);
     for (int e = i; e < kStages * kT * kPitch; e += kThreads) (&sm.stage[0][0][0])[e] = 0.f;
-    if (i < kT) sm.trow[i] = tri_row(min(i, k - 1), k);
+    if (i <= kT / 8) sm.fb[i] = frag_base(i, (k + 3) >> 2);
     if (i == 0) {
         for (int s = 0; s < kStages; ++s) slb_mbar_init(&sm.full[s], kT);
         slb_fence_mbar_init();
@@ -344,13 +512,12 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
         t1 = clock64(); clk[0] += t1 - t0; t0 = t1;
 
         // row means, grand mean, centred diagonal, tolerance
-        double ri = 0.0;
-        if (on) {
-            sweep_column(G, sm.trow, i, k, [&](int, double g) { ri += g; });
-            ri /= (double)k;
-        }
-        const double m = block_sum1(on ? ri : 0.0, sm) / (double)k;
-        const double g_ii = on ? gsym(G, sm.trow, i, i) : 0.0;
+        gram_times_vec<1>(G, sm.fb, k, [&](int j, int) { return j < k ? 1.0 : 0.0; },
+                          [&](int row, int, double y) { sm.r[row] = y / (double)k; });
+        __syncthreads();
+        const double ri = on ? sm.r[i] : 0.0;
+        const double m = block_sum1(ri, sm) / (double)k;
+        const double g_ii = on ? G[frag_elem(sm.fb, i, i)] : 0.0;
         const double di = on ? g_ii - 2.0 * ri + m : 0.0;
         sm.r[i] = ri;
         sm.diag[i] = di;
@@ -358,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
 
         t1 = clock64(); clk[1] += t1 - t0; t0 = t1;
         auto gc = [&](int j) -> double {  // Gc[i][j] from the packed upper triangle
-            return gsym(G, sm.trow, i, j) - ri - sm.r[j] + m;
+            return G[frag_elem(sm.fb, i, j)] - ri - sm.r[j] + m;
         };
 
         double best_inertia = 0.0;
@@ -369,62 +536,102 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
         // restart. The first assignments only depend on the seeds, so they are all taken first and ONE sweep over the
         // Gram matrix then serves every restart (each entry is loaded once and added into up to n_init independent sums).
         unsigned labw = 0, in0w = 0;  // bit `it`: first label of example i / example i starts in cluster 0 (after relocation)
-        for (int it = 0; it < p.n_init; ++it) {
+        // the restarts are independent here, so five at a time share every block-wide reduction (one pair of barriers each)
+        constexpr int GS = 5;
+        for (int q0 = 0; q0 < p.n_init; q0 += GS) {
             // k-means++ (sklearn _kmeans_plusplus, n_local_trials = 2)
-            const int i0 = p.first[it];
-            const double gi0 = on ? gc(i0) : 0.0;
-            const double closest = on ? fmax(di - 2.0 * gi0 + sm.diag[i0], 0.0) : 0.0;
-            const double pot = block_sum1(closest, sm);
-            const double cum = block_scan(closest, sm);
-            int cnts[2] = {(on && cum < p.rand[2 * it] * pot) ? 1 : 0, (on && cum < p.rand[2 * it + 1] * pot) ? 1 : 0};
-            block_count<2>(cnts, sm);
-            const int cand0 = min(cnts[0], k - 1), cand1 = min(cnts[1], k - 1);
-            const double gc0 = on ? gc(cand0) : 0.0, gc1 = on ? gc(cand1) : 0.0;
-            double pots[2] = {on ? fmin(closest, fmax(di - 2.0 * gc0 + sm.diag[cand0], 0.0)) : 0.0,
-                              on ? fmin(closest, fmax(di - 2.0 * gc1 + sm.diag[cand1], 0.0)) : 0.0};
-            block_sum<2>(pots, sm);
-            const int i1 = (pots[1] < pots[0]) ? cand1 : cand0;
-            // first E-step (+ empty-cluster relocation) from the two seeds
-            const double s0 = gi0, s1 = (i1 == cand1) ? gc1 : gc0;
-            const double n0 = sm.diag[i0], n1 = sm.diag[i1];
-            const int lab = (on && (n1 - 2.0 * s1) < (n0 - 2.0 * s0)) ? 1 : 0;
-            int mk = lab;
-            int c1[1] = {(on && lab == 0) ? 1 : 0};
-            block_count<1>(c1, sm);
-            int cnt0 = c1[0], cnt1 = k - cnt0;
-            if (cnt0 == 0 || cnt1 == 0) {
-                const int o = (cnt1 == 0) ? 0 : 1;
-                double dist = on ? di - 2.0 * (o ? s1 : s0) + (o ? n1 : n0) : -1.0;
-                int far = i;
-                block_argmax(dist, far, sm);
-                if (dist > 0.0) {
-                    if (i == far) mk = 1 - o;
-                    if (o == 0) { cnt0 -= 1; } else { cnt0 = 1; }
+            double gi0[GS], closest[GS], pot[GS], cum[GS];
+#pragma unroll
+            for (int q = 0; q < GS; ++q) {
+                const bool act = on && q0 + q < p.n_init;
+                const int i0 = p.first[min(q0 + q, p.n_init - 1)];
+                gi0[q] = act ? gc(i0) : 0.0;
+                closest[q] = act ? fmax(di - 2.0 * gi0[q] + sm.diag[i0], 0.0) : 0.0;
+                pot[q] = cum[q] = closest[q];
+            }
+            block_sumN<GS>(pot, sm);
+            block_scanN<GS>(cum, sm);
+            int cnts[2 * GS];
+#pragma unroll
+            for (int q = 0; q < GS; ++q) {
+                const int it = min(q0 + q, p.n_init - 1);
+                const bool act = on && q0 + q < p.n_init;
+                cnts[2 * q] = (act && cum[q] < p.rand[2 * it] * pot[q]) ? 1 : 0;
+                cnts[2 * q + 1] = (act && cum[q] < p.rand[2 * it + 1] * pot[q]) ? 1 : 0;
+            }
+            block_countN<2 * GS>(cnts, sm);
+            double gcand[2 * GS], pots[2 * GS];
+#pragma unroll
+            for (int q = 0; q < 2 * GS; ++q) {
+                const int cand = min(cnts[q], k - 1);
+                const bool act = on && q0 + (q >> 1) < p.n_init;
+                gcand[q] = act ? gc(cand) : 0.0;
+                pots[q] = act ? fmin(closest[q >> 1], fmax(di - 2.0 * gcand[q] + sm.diag[cand], 0.0)) : 0.0;
+            }
+            block_sumN<2 * GS>(pots, sm);
+            // first E-step from the two seeds
+            int lab[GS], c1[GS], i1s[GS];
+            double s1s[GS];
+#pragma unroll
+            for (int q = 0; q < GS; ++q) {
+                const bool act = on && q0 + q < p.n_init;
+                const int i0 = p.first[min(q0 + q, p.n_init - 1)];
+                const bool second = pots[2 * q + 1] < pots[2 * q];
+                i1s[q] = min(second ? cnts[2 * q + 1] : cnts[2 * q], k - 1);
+                s1s[q] = second ? gcand[2 * q + 1] : gcand[2 * q];
+                lab[q] = (act && (sm.diag[i1s[q]] - 2.0 * s1s[q]) < (sm.diag[i0] - 2.0 * gi0[q])) ? 1 : 0;
+                c1[q] = (act && lab[q] == 0) ? 1 : 0;
+            }
+            block_countN<GS>(c1, sm);
+#pragma unroll
+            for (int q = 0; q < GS; ++q) {
+                const int it = q0 + q;
+                if (it < p.n_init) {  // uniform over the CTA
+                    int mk = lab[q];
+                    int cnt0 = c1[q];
+                    const int cnt1 = k - cnt0;
+                    if (cnt0 == 0 || cnt1 == 0) {  // empty-cluster relocation (rare; uniform)
+                        const int i0 = p.first[it];
+                        const int o = (cnt1 == 0) ? 0 : 1;
+                        double dist = on ? di - 2.0 * (o ? s1s[q] : gi0[q]) + (o ? sm.diag[i1s[q]] : sm.diag[i0]) : -1.0;
+                        int far = i;
+                        block_argmax(dist, far, sm);
+                        if (dist > 0.0) {
+                            if (i == far) mk = 1 - o;
+                            if (o == 0) { cnt0 -= 1; } else { cnt0 = 1; }
+                        }
+                    }
+                    labw |= (unsigned)lab[q] << it;
+                    in0w |= (unsigned)(on && mk == 0) << it;
+                    if (i == 0) { sm.seed0[it] = i1s[q]; sm.cnt0[it] = cnt0; }
                 }
             }
-            labw |= (unsigned)lab << it;
-            in0w |= (unsigned)(on && mk == 0) << it;
-            if (i == 0) { sm.seed0[it] = i1; sm.cnt0[it] = cnt0; }
         }
         __syncthreads();
         sm.in0[i] = (unsigned short)in0w;
         __syncthreads();
         t1 = clock64(); clk[2] += t1 - t0; t0 = t1;
-        // groups of 5 restarts: the default n_init = 10 is two sweeps with no idle accumulator
-        for (int q0 = 0; q0 < p.n_init; q0 += 5) {
-            double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        // Y[i][q] = sum over the first members j of restart q of G0[i][j], all restarts in one product; centring:
+        //   sum_j w_j Gc[i][j] = Y[i] - r_i c - S + m c,   c = |members|,   S = sum_j w_j r_j = (1/k) sum_i Y[i]  (G0 symmetric)
+        gram_times<2>(G, sm.fb, k, [&](int j, int n) { return (((unsigned)sm.in0[j] >> n) & 1u) ? 1.0 : 0.0; },
+                      [&](int row, int col, double y0, double y1) {
+                          if (col < p.n_init) sm.tA0[col][row] = y0;
+                          if (col + 1 < p.n_init) sm.tA0[col + 1][row] = y1;
+                      });
+        __syncthreads();
+        {
+            double tot[kMaxInit];
+#pragma unroll
+            for (int q = 0; q < kMaxInit; ++q) tot[q] = (on && q < p.n_init) ? sm.tA0[q][i] : 0.0;
+            block_sumN<kMaxInit>(tot, sm);
             if (on) {
-                sweep_column(G, sm.trow, i, k, [&](int j, double g) {
-                    const double gcj = g - ri - sm.r[j] + m;
-                    const unsigned w = (unsigned)sm.in0[j] >> q0;  // the same j for the whole warp: no divergence
 #pragma unroll
-                    for (int q = 0; q < 5; ++q)
-                        if ((w >> q) & 1u) acc[q] += gcj;
-                });
+                for (int q = 0; q < kMaxInit; ++q)
+                    if (q < p.n_init) {
+                        const double c = (double)sm.cnt0[q];
+                        sm.tA0[q][i] = sm.tA0[q][i] - ri * c - tot[q] / (double)k + m * c;
+                    }
             }
-#pragma unroll
-            for (int q = 0; q < 5; ++q)
-                if (q0 + q < p.n_init && i < kT) sm.tA0[q0 + q][i] = acc[q];
         }
         __syncthreads();
         t1 = clock64(); clk[3] += t1 - t0; t0 = t1;
@@ -492,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
                                 const int code = sm.moved[e];
                                 jj[u] = code;
                                 const int j = code >= 0 ? code : ~code;
-                                gv[u] = gsym(G, sm.trow, i, j);
+                                gv[u] = G[frag_elem(sm.fb, i, j)];
                             }
 #pragma unroll
                             for (int u = 0; u < 8; ++u) {
@@ -570,12 +777,10 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
             const double c = (on && i < ns) ? ri / (fmax(sqrt(m), 1e-12) * fmax(sqrt(g_ii), 1e-12)) : 0.0;
             result = 1.0 - block_sum1(c, sm) / (double)ns;
         } else {
-            double wa = 0.0, wb = 0.0;
-            if (on) {
-                sweep_column(G, sm.trow, i, k, [&](int j, double g) {
-                    if (sm.best_mask[j] == 0) wa += g; else wb += g;
-                });
-            }
+            gram_times_vec<2>(G, sm.fb, k, [&](int j, int v) { return (j < k && (int)sm.best_mask[j] == v) ? 1.0 : 0.0; },
+                              [&](int row, int v, double y) { sm.tA0[v][row] = y; });
+            __syncthreads();
+            const double wa = on ? sm.tA0[0][i] : 0.0, wb = on ? sm.tA0[1][i] : 0.0;
             const bool ina = on && sm.best_mask[i] == 0, inb = on && sm.best_mask[i] == 1;
             double v[4] = {ina ? wa : 0.0, inb ? wa : 0.0, inb ? wb : 0.0, on ? (ca == 0 ? (inb ? ri : 0.0) : (ina ? ri : 0.0)) : 0.0};
             block_sum<4>(v, sm);
