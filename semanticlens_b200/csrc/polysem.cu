@@ -61,8 +61,6 @@ struct Smem {
     unsigned short in0[kThreads];  // bit `it`: the example starts restart `it` in cluster 0
     int fb[kT / 8 + 1];            // first fragment of every 8-row band of the Gram slot
     double red10[kWarps][kMaxInit];
-    double scan10[kWarps][kMaxInit / 2];
-    int ired10[kWarps][kMaxInit];
     int seed0[kMaxInit];           // second seed of every restart (the first is PolyParams::first)
     int cnt0[kMaxInit];            // size of cluster 0 after the first assignment
     int wcnt[kWarps];
@@ -94,8 +92,7 @@ __device__ __forceinline__ void block_sum(double (&v)[N], Smem& sm) {
     }
 }
 
-// N-wide versions (N <= kMaxInit): several restarts' reductions behind ONE pair of barriers — phase B is a chain of
-// block-wide reductions, each costing two barrier latencies, so the restarts are reduced together wherever they are independent
+// N-wide version (N <= kMaxInit): the restarts' sums behind one pair of barriers
 template <int N>
 __device__ __forceinline__ void block_sumN(double (&v)[N], Smem& sm) {
     static_assert(N <= kMaxInit, "red10 holds kMaxInit values per warp");
@@ -117,54 +114,6 @@ __device__ __forceinline__ void block_sumN(double (&v)[N], Smem& sm) {
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) t += sm.red10[w][n];
         v[n] = t;
-    }
-}
-
-template <int N>
-__device__ __forceinline__ void block_countN(int (&v)[N], Smem& sm) {
-    static_assert(N <= kMaxInit, "ired10 holds kMaxInit values per warp");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int n = 0; n < N; ++n) v[n] = __reduce_add_sync(0xffffffffu, v[n]);
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-        for (int n = 0; n < N; ++n) sm.ired10[warp][n] = v[n];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-        int t = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) t += sm.ired10[w][n];
-        v[n] = t;
-    }
-}
-
-// N inclusive prefix sums over the threads (np.cumsum of N independent vectors)
-template <int N>
-__device__ __forceinline__ void block_scanN(double (&x)[N], Smem& sm) {
-    static_assert(N <= kMaxInit / 2, "scan10 holds kMaxInit / 2 values per warp");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double y = __shfl_up_sync(0xffffffffu, x[n], o);
-            if (lane >= o) x[n] += y;
-        }
-    }
-    __syncthreads();
-    if (lane == 31) {
-#pragma unroll
-        for (int n = 0; n < N; ++n) sm.scan10[warp][n] = x[n];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-        double base = 0.0;
-        for (int w = 0; w < warp; ++w) base += sm.scan10[w][n];
-        x[n] += base;
     }
 }
 
@@ -192,6 +141,22 @@ __device__ __forceinline__ void block_count(int (&v)[N], Smem& sm) {
         for (int w = 0; w < kWarps; ++w) t += sm.ired[w * 2 + n];
         v[n] = t;
     }
+}
+
+// inclusive prefix sum over the threads (np.cumsum)
+__device__ __forceinline__ double block_scan(double x, Smem& sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();
+    if (lane == 31) sm.scan[warp] = x;
+    __syncthreads();
+    double base = 0.0;
+    for (int w = 0; w < warp; ++w) base += sm.scan[w];
+    return base + x;
 }
 
 // (max value, first index attaining it) over threads
@@ -244,6 +209,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// (Measured and dropped: widening fp32 -> f64 with integer shifts instead of cvt.f64.f32. The conversions run on the XU
+// pipe, which ncu shows busy, but phase A is bound by the DMMA sub-pipe itself — 84 % active while a CTA is in phase A —
+// and the extra integer instructions cost more issue slots than the XU conversions: 300 -> 330 us per neuron and CTA.)
 __device__ __forceinline__ uint64_t evict_first_policy() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -421,66 +389,6 @@ __device__ __forceinline__ void gram_times(const double* __restrict__ U, const i
         }
 }
 
-// The same walk for one or two weight columns on the plain FP64 pipe: a DMMA spends 8 columns of work on them, and the
-// tensor pipe is what the other CTA's phase A is bound by. Lane (g, t) multiplies its fragment element by w[4 Kq + t] and
-// the four t-lanes of a row are added at the end. 32 loads in flight per lane.
-template <int NV, typename WF, typename OUT>
-__device__ __forceinline__ void gram_times_vec(const double* __restrict__ U, const int* __restrict__ fb, int k, WF&& wf, OUT&& out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp >= 8) return;
-    const int g = lane >> 2, t = lane & 3;
-    const int NB = (k + 7) >> 3, KQ = (k + 3) >> 2;
-    int band[4], base[4];
-    bool live[4];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        band[m] = warp + 8 * m;
-        live[m] = band[m] < NB;
-        base[m] = live[m] ? fb[band[m]] - 2 * band[m] : 0;
-    }
-    const int lo_off = (t << 2) + (g & 3);
-    double acc[4][NV];
-#pragma unroll
-    for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int v = 0; v < NV; ++v) acc[m][v] = 0.0;
-    for (int q0 = 0; q0 < KQ; q0 += 8) {
-        double a[8][4];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int Kq = min(q0 + u, KQ - 1);
-            const int Rp = Kq >> 1;
-            const int tbase = ((fb[Rp] - 2 * Rp + (g >> 2)) << 5) + ((Kq & 1) << 4) + lo_off;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int idx = (Kq >= 2 * band[m]) ? ((base[m] + Kq) << 5) + lane : tbase + (band[m] << 6);
-                a[u][m] = live[m] ? U[idx] : 0.0;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int Kq = q0 + u;
-            if (Kq < KQ) {
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    const double w = wf(4 * Kq + t, v);
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) acc[m][v] = fma(a[u][m], w, acc[m][v]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            double y = acc[m][v];
-            y += __shfl_xor_sync(0xffffffffu, y, 1);
-            y += __shfl_xor_sync(0xffffffffu, y, 2);
-            if (live[m] && t == 0) out(band[m] * 8 + g, v, y);
-        }
-}
-
 // ---- the kernel ------------------------------------------------------------------------------------
 // SM-clock totals of thread 0 of every CTA per phase (slb_polysem_phase_clocks): Gram, row means, k-means++ and first
 // assignments, first-iteration sums, Lloyd restarts, score. A handful of clock reads per neuron.
@@ -512,8 +420,8 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
         t1 = clock64(); clk[0] += t1 - t0; t0 = t1;
 
         // row means, grand mean, centred diagonal, tolerance
-        gram_times_vec<1>(G, sm.fb, k, [&](int j, int) { return j < k ? 1.0 : 0.0; },
-                          [&](int row, int, double y) { sm.r[row] = y / (double)k; });
+        gram_times<1>(G, sm.fb, k, [&](int j, int) { return j < k ? 1.0 : 0.0; },
+                      [&](int row, int col, double y0, double) { if (col == 0) sm.r[row] = y0 / (double)k; });
         __syncthreads();
         const double ri = on ? sm.r[i] : 0.0;
         const double m = block_sum1(ri, sm) / (double)k;
@@ -521,7 +429,10 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
         const double di = on ? g_ii - 2.0 * ri + m : 0.0;
         sm.r[i] = ri;
         sm.diag[i] = di;
-        const double tol = block_sum1(di, sm) / ((double)k * (double)p.D) * 1e-4;  // also publishes sm.r / sm.diag
+        double tv[2] = {di, g_ii};
+        block_sum<2>(tv, sm);  // also publishes sm.r / sm.diag
+        const double tol = tv[0] / ((double)k * (double)p.D) * 1e-4;
+        const bool nonfinite = !(tv[1] < 0x1p255);  // an Inf / NaN example, or a true overflow: sklearn raises on such input
 
         t1 = clock64(); clk[1] += t1 - t0; t0 = t1;
         auto gc = [&](int j) -> double {  // Gc[i][j] from the packed upper triangle
@@ -536,76 +447,42 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
         // restart. The first assignments only depend on the seeds, so they are all taken first and ONE sweep over the
         // Gram matrix then serves every restart (each entry is loaded once and added into up to n_init independent sums).
         unsigned labw = 0, in0w = 0;  // bit `it`: first label of example i / example i starts in cluster 0 (after relocation)
-        // the restarts are independent here, so five at a time share every block-wide reduction (one pair of barriers each)
-        constexpr int GS = 5;
-        for (int q0 = 0; q0 < p.n_init; q0 += GS) {
+        for (int it = 0; it < p.n_init; ++it) {
             // k-means++ (sklearn _kmeans_plusplus, n_local_trials = 2)
-            double gi0[GS], closest[GS], pot[GS], cum[GS];
-#pragma unroll
-            for (int q = 0; q < GS; ++q) {
-                const bool act = on && q0 + q < p.n_init;
-                const int i0 = p.first[min(q0 + q, p.n_init - 1)];
-                gi0[q] = act ? gc(i0) : 0.0;
-                closest[q] = act ? fmax(di - 2.0 * gi0[q] + sm.diag[i0], 0.0) : 0.0;
-                pot[q] = cum[q] = closest[q];
-            }
-            block_sumN<GS>(pot, sm);
-            block_scanN<GS>(cum, sm);
-            int cnts[2 * GS];
-#pragma unroll
-            for (int q = 0; q < GS; ++q) {
-                const int it = min(q0 + q, p.n_init - 1);
-                const bool act = on && q0 + q < p.n_init;
-                cnts[2 * q] = (act && cum[q] < p.rand[2 * it] * pot[q]) ? 1 : 0;
-                cnts[2 * q + 1] = (act && cum[q] < p.rand[2 * it + 1] * pot[q]) ? 1 : 0;
-            }
-            block_countN<2 * GS>(cnts, sm);
-            double gcand[2 * GS], pots[2 * GS];
-#pragma unroll
-            for (int q = 0; q < 2 * GS; ++q) {
-                const int cand = min(cnts[q], k - 1);
-                const bool act = on && q0 + (q >> 1) < p.n_init;
-                gcand[q] = act ? gc(cand) : 0.0;
-                pots[q] = act ? fmin(closest[q >> 1], fmax(di - 2.0 * gcand[q] + sm.diag[cand], 0.0)) : 0.0;
-            }
-            block_sumN<2 * GS>(pots, sm);
-            // first E-step from the two seeds
-            int lab[GS], c1[GS], i1s[GS];
-            double s1s[GS];
-#pragma unroll
-            for (int q = 0; q < GS; ++q) {
-                const bool act = on && q0 + q < p.n_init;
-                const int i0 = p.first[min(q0 + q, p.n_init - 1)];
-                const bool second = pots[2 * q + 1] < pots[2 * q];
-                i1s[q] = min(second ? cnts[2 * q + 1] : cnts[2 * q], k - 1);
-                s1s[q] = second ? gcand[2 * q + 1] : gcand[2 * q];
-                lab[q] = (act && (sm.diag[i1s[q]] - 2.0 * s1s[q]) < (sm.diag[i0] - 2.0 * gi0[q])) ? 1 : 0;
-                c1[q] = (act && lab[q] == 0) ? 1 : 0;
-            }
-            block_countN<GS>(c1, sm);
-#pragma unroll
-            for (int q = 0; q < GS; ++q) {
-                const int it = q0 + q;
-                if (it < p.n_init) {  // uniform over the CTA
-                    int mk = lab[q];
-                    int cnt0 = c1[q];
-                    const int cnt1 = k - cnt0;
-                    if (cnt0 == 0 || cnt1 == 0) {  // empty-cluster relocation (rare; uniform)
-                        const int i0 = p.first[it];
-                        const int o = (cnt1 == 0) ? 0 : 1;
-                        double dist = on ? di - 2.0 * (o ? s1s[q] : gi0[q]) + (o ? sm.diag[i1s[q]] : sm.diag[i0]) : -1.0;
-                        int far = i;
-                        block_argmax(dist, far, sm);
-                        if (dist > 0.0) {
-                            if (i == far) mk = 1 - o;
-                            if (o == 0) { cnt0 -= 1; } else { cnt0 = 1; }
-                        }
-                    }
-                    labw |= (unsigned)lab[q] << it;
-                    in0w |= (unsigned)(on && mk == 0) << it;
-                    if (i == 0) { sm.seed0[it] = i1s[q]; sm.cnt0[it] = cnt0; }
+            const int i0 = p.first[it];
+            const double gi0 = on ? gc(i0) : 0.0;
+            const double closest = on ? fmax(di - 2.0 * gi0 + sm.diag[i0], 0.0) : 0.0;
+            const double pot = block_sum1(closest, sm);
+            const double cum = block_scan(closest, sm);
+            int cnts[2] = {(on && cum < p.rand[2 * it] * pot) ? 1 : 0, (on && cum < p.rand[2 * it + 1] * pot) ? 1 : 0};
+            block_count<2>(cnts, sm);
+            const int cand0 = min(cnts[0], k - 1), cand1 = min(cnts[1], k - 1);
+            const double gc0 = on ? gc(cand0) : 0.0, gc1 = on ? gc(cand1) : 0.0;
+            double pots[2] = {on ? fmin(closest, fmax(di - 2.0 * gc0 + sm.diag[cand0], 0.0)) : 0.0,
+                              on ? fmin(closest, fmax(di - 2.0 * gc1 + sm.diag[cand1], 0.0)) : 0.0};
+            block_sum<2>(pots, sm);
+            const int i1 = (pots[1] < pots[0]) ? cand1 : cand0;
+            // first E-step (+ empty-cluster relocation) from the two seeds
+            const double s0 = gi0, s1 = (i1 == cand1) ? gc1 : gc0;
+            const double n0 = sm.diag[i0], n1 = sm.diag[i1];
+            const int lab = (on && (n1 - 2.0 * s1) < (n0 - 2.0 * s0)) ? 1 : 0;
+            int mk = lab;
+            int c1[1] = {(on && lab == 0) ? 1 : 0};
+            block_count<1>(c1, sm);
+            int cnt0 = c1[0], cnt1 = k - cnt0;
+            if (cnt0 == 0 || cnt1 == 0) {
+                const int o = (cnt1 == 0) ? 0 : 1;
+                double dist = on ? di - 2.0 * (o ? s1 : s0) + (o ? n1 : n0) : -1.0;
+                int far = i;
+                block_argmax(dist, far, sm);
+                if (dist > 0.0) {
+                    if (i == far) mk = 1 - o;
+                    if (o == 0) { cnt0 -= 1; } else { cnt0 = 1; }
                 }
             }
+            labw |= (unsigned)lab << it;
+            in0w |= (unsigned)(on && mk == 0) << it;
+            if (i == 0) { sm.seed0[it] = i1; sm.cnt0[it] = cnt0; }
         }
         __syncthreads();
         sm.in0[i] = (unsigned short)in0w;
@@ -777,8 +654,11 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
             const double c = (on && i < ns) ? ri / (fmax(sqrt(m), 1e-12) * fmax(sqrt(g_ii), 1e-12)) : 0.0;
             result = 1.0 - block_sum1(c, sm) / (double)ns;
         } else {
-            gram_times_vec<2>(G, sm.fb, k, [&](int j, int v) { return (j < k && (int)sm.best_mask[j] == v) ? 1.0 : 0.0; },
-                              [&](int row, int v, double y) { sm.tA0[v][row] = y; });
+            gram_times<1>(G, sm.fb, k,
+                          [&](int j, int n) { return (j < k && n < 2 && (int)sm.best_mask[j] == n) ? 1.0 : 0.0; },
+                          [&](int row, int col, double y0, double y1) {
+                              if (col == 0) { sm.tA0[0][row] = y0; sm.tA0[1][row] = y1; }
+                          });
             __syncthreads();
             const double wa = on ? sm.tA0[0][i] : 0.0, wb = on ? sm.tA0[1][i] : 0.0;
             const bool ina = on && sm.best_mask[i] == 0, inb = on && sm.best_mask[i] == 1;
@@ -797,7 +677,7 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
                 result = 1.0 - sab / (fmax(sqrt(saa), 1e-12) * fmax(sqrt(sbb), 1e-12));
             }
         }
-        if (i == 0) p.out[neuron] = result;
+        if (i == 0) p.out[neuron] = nonfinite ? __longlong_as_double(0x7FF8000000000000ll) : result;
         __syncthreads();
         t1 = clock64(); clk[5] += t1 - t0;
         clk[6] += 1;

@@ -153,6 +153,26 @@ def test_polysemanticity_many_neurons_vs_oracle(S):
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9)
 
 
+def test_polysemanticity_zeros_subnormals_and_non_finite_examples(S):
+    """Zeros, signed zeros and subnormals are ordinary values; an Inf / NaN example makes that neuron's score NaN (sklearn
+    raises on such input) and leaves the neighbouring neurons alone."""
+    rng = np.random.default_rng(5)
+    V = rng.standard_normal((6, 32, 48)).astype(np.float32)
+    V[:, ::2] += 2 * rng.standard_normal((6, 1, 48)).astype(np.float32)
+    V[0, :, ::3] = 0.0                    # exact zeros (a ReLU'd embedding)
+    V[1, 3, 5] = np.float32(1e-41)        # a subnormal
+    V[1, 4, :8] = -0.0
+    ref = P.polysemanticity_gram(V)
+    bad = V.copy()
+    bad[2, 7, 1] = np.inf
+    bad[4, 0, 0] = np.nan
+    got = S.polysemanticity_score(torch.from_numpy(V).cuda()).cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9)
+    got_bad = S.polysemanticity_score(torch.from_numpy(bad).cuda()).cpu().numpy()
+    assert np.isnan(got_bad[[2, 4]]).all()
+    np.testing.assert_allclose(got_bad[[0, 1, 3, 5]], ref[[0, 1, 3, 5]], rtol=0, atol=1e-9)
+
+
 def test_cosine_gemm_shapes_vs_port(S):
     g = torch.Generator().manual_seed(3)
     for (Q, C, D) in ((1, 10, 128), (7, 1000, 512), (300, 129, 768), (130, 260, 100)):
