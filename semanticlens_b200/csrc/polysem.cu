@@ -23,6 +23,7 @@
 //          oracle/polysem.py::kmeans2_gram is the line-by-line CPU statement of this phase.
 #include "slb_common.cuh"
 
+#include <stdlib.h>
 #include <algorithm>
 
 namespace {
@@ -209,6 +210,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// (Measured and dropped: ONE 2-D TMA box per stage behind a 4-slot full / empty mbarrier ring instead of a bulk copy per row
+// and a block barrier per stage: phase A of a lone CTA 238 -> 234 us, the whole kernel 130 -> 136 ms — the copies and
+// barriers were not the bound. With SLB_POLYSEM_CTAS_PER_SM=1 a lone CTA needs 238 us per Gram matrix where the DMMA
+// sub-pipe would allow ~150: one warp issues a DMMA only every ~56 clocks, and it takes both CTAs' 18 warps in phase A
+// to fill the pipe. The same run shows phase B at 117 us alone against 230 us next to a neighbour's phase A.)
 // (Measured and dropped: widening fp32 -> f64 with integer shifts instead of cvt.f64.f32. The conversions run on the XU
 // pipe, which ncu shows busy, but phase A is bound by the DMMA sub-pipe itself — 84 % active while a CTA is in phase A —
 // and the extra integer instructions cost more issue slots than the XU conversions: 300 -> 330 us per neuron and CTA.)
@@ -686,7 +692,16 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
         for (int c = 0; c < 7; ++c) atomicAdd(&g_phase_clk[c], clk[c]);
 }
 
-int poly_grid(int64_t C) { return (int)std::min<int64_t>(C, (int64_t)slb_sm_count() * 2); }
+// SLB_POLYSEM_CTAS_PER_SM=1 (diagnostic): one CTA per SM, to time the phases without a neighbour on the SM
+int poly_ctas_per_sm() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("SLB_POLYSEM_CTAS_PER_SM");
+        v = (e && e[0] == '1') ? 1 : 2;
+    }
+    return v;
+}
+int poly_grid(int64_t C) { return (int)std::min<int64_t>(C, (int64_t)slb_sm_count() * poly_ctas_per_sm()); }
 
 }  // namespace
 
@@ -732,7 +747,7 @@ extern "C" int slb_polysem_2means(const float* V, int64_t C, int64_t k, int64_t 
     }
     p.G = static_cast<double*>(workspace);
     p.out = out;
-    const size_t smem = sizeof(Smem);
+    const size_t smem = poly_ctas_per_sm() == 1 ? std::max(sizeof(Smem), (size_t)120 * 1024) : sizeof(Smem);
     SLB_CUDA_OK(cudaFuncSetAttribute(polysem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     polysem_kernel<<<poly_grid(C), kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     SLB_LAUNCH_OK("polysem_2means");
