@@ -154,6 +154,17 @@ int slb_polysem_2means(const float* V, int64_t C, int64_t k, int64_t D, const in
                        const double* local_trial_uniforms, int n_init, int replace_empty_clusters, double* out,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* K8g. The general form of K8: any n_clusters in [2, 8] and any number of examples per neuron (scores.py:132-185 called with
+ * n_clusters != 2, or a concept DB with more than 256 examples per neuron): sklearn KMeans(n_clusters, n_init,
+ * random_state).fit per neuron in float64 in sample space, then 1 - clarity of the centres (or the fallback when a cluster
+ * has fewer than 2 members). first_centers [n_init] and local_trial_uniforms [n_init][n_clusters - 1][n_local_trials] are
+ * HOST arrays (n_local_trials = 2 + int(log n_clusters), sklearn _kmeans.py:226); they are copied on `stream`.
+ * k >= n_clusters (sklearn raises otherwise). workspace >= slb_polysem_kmeans_workspace_bytes(...), 16-byte aligned. */
+size_t slb_polysem_kmeans_workspace_bytes(int64_t C, int64_t k, int64_t D, int n_clusters, int n_init);
+int slb_polysem_kmeans(const float* V, int64_t C, int64_t k, int64_t D, int n_clusters, const int64_t* first_centers,
+                       const double* local_trial_uniforms, int n_local_trials, int n_init, int replace_empty_clusters,
+                       double* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* K9 (part). out[i] = max_j (S[i, j] - 2 * (j == row0 + i)) for a row block S (rows, cols) of the cosine matrix —
  * scores.redundancy_score's `(sims - 2 I).max(-1)` (scores.py:78-80) without materialising the identity. */
 int slb_rowmax_offdiag(const float* S, int64_t rows, int64_t cols, int64_t row0, float* out, void* stream);

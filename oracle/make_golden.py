@@ -12,6 +12,7 @@ Fixtures (inputs + the reference's outputs):
   actmax_kat.npz        the reference's own known-answer test (tests/component_visualization/test_activation_caching.py:14-30)
   scores.npz            clarity / similarity (all shape branches) / polysemanticity (incl. the small-cluster fallback)
   scores_poly.npz       reference polysemanticity / clarity of the seeded cases of tests/polysem_cases.py (outputs only)
+  scores_poly_general.npz  the same for n_clusters = 2..8 and up to 520 examples per neuron (GENERAL_CASES, outputs only)
   cache_format/         one ActMaxCache.store() directory written by the reference (file names, keys, metadata)
   collect_large.npz     full-size hook fixture: 3 batches of (256, 2048, 7, 7) post-ReLU maps (regenerated from a seed by
                         tests/collect_cases.py; only a checksum of the inputs and the reference's outputs are stored), k = 20
@@ -209,6 +210,23 @@ def gen_scores_poly():
     np.savez_compressed(GOLD / "scores_poly.npz", **out)
 
 
+def gen_scores_poly_general():
+    """polysemanticity_score with n_clusters != 2 and / or more than 256 examples per neuron (the general kernel K8g)."""
+    import warnings
+
+    from semanticlens import scores as S
+    from tests.polysem_cases import GENERAL_CASES, make_general_case
+
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name, spec in GENERAL_CASES.items():
+            V = torch.from_numpy(make_general_case(name))
+            out[f"{name}.poly"] = S.polysemanticity_score(V, n_clusters=spec[4]).numpy()
+            out[f"{name}.poly_noreplace"] = S.polysemanticity_score(V, replace_empty_clusters=False, n_clusters=spec[4]).numpy()
+    np.savez_compressed(GOLD / "scores_poly_general.npz", **out)
+
+
 def gen_collect_large():
     """k = 20, batch 256, C = 2048 (ResNet-50 layer4 geometry) through the reference's hooks."""
     from semanticlens.component_visualization import aggregators as A
@@ -243,6 +261,7 @@ def main():
     gen_cache_format()
     gen_scores()
     gen_scores_poly()
+    gen_scores_poly_general()
     gen_collect_large()
     gen_text_probe()
     for f in sorted(GOLD.rglob("*")):

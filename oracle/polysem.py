@@ -15,6 +15,9 @@ random_state=123)`` per neuron (third-party arithmetic: scikit-learn, pinned 1.6
   centres that are means of subsets, centre shifts, inertia, tolerance, the final cosine of the two un-centred centres)
   is a function of G0.
 
+* :func:`kmeans_direct` / :func:`polysemanticity_general` — the sample-space form for any ``n_clusters`` and any number of
+  examples (the general kernel ``slb_polysem_kmeans``), pinned against sklearn for 2-5 clusters and 300+ examples.
+
 Pinned: tests/test_oracle_polysem.py checks both against sklearn itself (labels identical, centres / scores to 1e-9)
 and against tests/golden/scores.npz recorded from the imported reference.
 """
@@ -242,6 +245,130 @@ def polysemanticity_direct(V, seed: int = 123, replace_empty_clusters: bool = Tr
         cn = centers / np.maximum(np.linalg.norm(centers, axis=1, keepdims=True), 1e-12)
         out[c] = 1.0 - (((cn.mean(0) ** 2).sum() - 0.5) / 1.0 * 2.0)
         cnt = np.bincount(labels, minlength=2)
+        if replace_empty_clusters and cnt.min() < 2:
+            ns = min(10, v.shape[0])
+            mean = v.mean(0)
+            acc = np.float32(0)
+            for i in range(ns):
+                pair = np.stack([mean, v[i]]).astype(np.float32)
+                pn = pair / np.maximum(np.linalg.norm(pair, axis=1, keepdims=True), np.float32(1e-12))
+                acc = acc + np.float32(((pn.mean(0) ** 2).sum() - np.float32(0.5)) * 2)
+            out[c] = 1.0 - float(acc) / ns
+    return out
+
+# ------------------------------------------------------------------------------------------------
+# general restatement: any number of clusters, any number of examples (what slb_polysem_kmeans runs)
+# ------------------------------------------------------------------------------------------------
+def n_local_trials(n_clusters: int) -> int:
+    """sklearn _kmeans.py:226  (2 + int(log(n_clusters)))"""
+    return 2 + int(np.log(n_clusters))
+
+
+def kmeanspp_draws_general(k: int, n_clusters: int, seed: int = 123, n_init: int = N_INIT):
+    """The data-independent part of sklearn's RandomState stream for any n_clusters: per init the first centre
+    (``random_state.choice(k, p=1/k)``) and, for each further centre, ``n_local_trials`` uniforms (``_kmeans_plusplus``).
+    -> first (n_init,) int64, rand (n_init, n_clusters - 1, n_local_trials) float64."""
+    rs = np.random.RandomState(seed)
+    L = n_local_trials(n_clusters)
+    first = np.empty(n_init, dtype=np.int64)
+    rand = np.empty((n_init, max(n_clusters - 1, 0), L), dtype=np.float64)
+    p = np.ones(k, dtype=np.float64)
+    p = p / p.sum()
+    for i in range(n_init):
+        first[i] = rs.choice(k, p=p)
+        for c in range(1, n_clusters):
+            rand[i, c - 1] = rs.uniform(size=L)
+    return first, rand
+
+
+def kmeans_direct(X, n_clusters: int, seed: int = 123):
+    """sklearn KMeans(n_clusters, n_init=10, random_state=seed).fit(X) in float64, sample space.
+    -> (labels (k,), centres (n_clusters, D) un-centred, inertia). Several empty clusters in one iteration take the
+    farthest points in descending order of distance (sklearn: np.argpartition's order, unspecified among them)."""
+    X = np.array(X, dtype=np.float64)
+    k, D = X.shape
+    m = n_clusters
+    if k < m:
+        raise ValueError(f"n_samples={k} should be >= n_clusters={m}.")
+    tol = np.mean(np.var(X, axis=0)) * TOL
+    mean = X.mean(axis=0)
+    X = X - mean
+    xsq = (X * X).sum(1)
+    first, rand = kmeanspp_draws_general(k, m, seed)
+
+    def d2(c):
+        return np.maximum(xsq - 2.0 * (X @ c) + c @ c, 0.0)
+
+    def e_step(centers):
+        pd = (centers * centers).sum(1)[None, :] - 2.0 * (X @ centers.T)
+        return np.argmin(pd, axis=1)  # first minimum, like the strict `<` scan of _update_chunk_dense
+
+    best = None
+    for it in range(N_INIT):
+        idx = [int(first[it])]
+        closest = d2(X[idx[0]])
+        pot = closest.sum()
+        for c in range(1, m):
+            cand = np.minimum(np.searchsorted(np.cumsum(closest), rand[it, c - 1] * pot), k - 1)
+            dist_c = np.stack([np.minimum(closest, d2(X[j])) for j in cand])
+            pots = dist_c.sum(1)
+            b = int(np.argmin(pots))
+            pot, closest = pots[b], dist_c[b]
+            idx.append(int(cand[b]))
+        centers = X[idx].copy()
+        labels_old = np.full(k, -1)
+        strict = False
+        for _ in range(MAX_ITER):
+            labels = e_step(centers)
+            sums = np.stack([X[labels == a].sum(0) for a in range(m)])
+            w = np.array([(labels == a).sum() for a in range(m)], dtype=np.float64)
+            empty = np.where(w == 0)[0]
+            if len(empty):
+                dist = ((X - centers[labels]) ** 2).sum(1)
+                if dist.max() > 0:
+                    order = np.lexsort((np.arange(k), -dist))[: len(empty)]  # farthest first, lower index on ties
+                    for e, far in zip(empty, order):
+                        o = labels[far]
+                        sums[o] -= X[far]
+                        sums[e] = X[far]
+                        w[e] = 1
+                        w[o] -= 1
+            # _average_centers (_k_means_common.pyx, sklearn 1.9): a cluster that is still empty goes to "the location of the
+            # biggest cluster" — read in index order, i.e. the biggest cluster's raw SUM if it has not been averaged yet
+            new = sums.copy()
+            amax = int(np.argmax(w))
+            for j in range(m):
+                if w[j] > 0:
+                    new[j] = new[j] / w[j]
+                else:
+                    new[j] = new[amax]
+            shift = ((new - centers) ** 2).sum()
+            centers = new
+            if np.array_equal(labels, labels_old):
+                strict = True
+                break
+            if shift <= tol:
+                break
+            labels_old = labels
+        if not strict:
+            labels = e_step(centers)
+        inertia = ((X - centers[labels]) ** 2).sum()
+        if best is None or (inertia < best[2] and not _same_clustering(labels, best[0])):
+            best = (labels, centers, inertia)
+    return best[0], best[1] + mean, best[2]
+
+
+def polysemanticity_general(V, n_clusters: int = 2, seed: int = 123, replace_empty_clusters: bool = True):
+    """scores.py:132-185 for any n_clusters: 1 - clarity of the cluster centres (float64), with the reference's fallback
+    for neurons whose smallest cluster has fewer than 2 members (or that miss a cluster altogether)."""
+    V32 = np.asarray(V, dtype=np.float32)
+    m = n_clusters
+    out = np.empty(len(V32))
+    for c, v in enumerate(V32):
+        labels, centers, _ = kmeans_direct(v, m, seed)
+        cn = centers / np.maximum(np.linalg.norm(centers, axis=1, keepdims=True), 1e-12)
+        out[c] = 1.0 - (((cn.mean(0) ** 2).sum() - 1.0 / m) / (m - 1) * m)
+        cnt = np.bincount(labels, minlength=m)
         if replace_empty_clusters and cnt.min() < 2:
             ns = min(10, v.shape[0])
             mean = v.mean(0)

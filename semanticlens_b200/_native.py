@@ -63,6 +63,12 @@ _PROTOS = {
         c_int,
         [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
+    "slb_polysem_kmeans_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int]),
+    "slb_polysem_kmeans": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+         c_void_p],
+    ),
     "slb_rowmax_offdiag": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "slb_redundancy_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "slb_redundancy": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),

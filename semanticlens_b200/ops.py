@@ -686,6 +686,57 @@ def polysem_2means(V: torch.Tensor, random_state: int = 123, replace_empty_clust
     return out
 
 
+POLYSEM_FAST_MAX_EXAMPLES = 256  # K8's Gram-matrix kernel: one thread per example
+POLYSEM_MAX_CLUSTERS = 8
+
+
+def kmeanspp_draws_general(k: int, n_clusters: int, seed: int, n_init: int = 10):
+    """The data-independent draws of sklearn's k-means++ for any n_clusters: per init ``choice(k, p=uniform)`` (first
+    centre), then for every further centre ``uniform(size=2 + int(log(n_clusters)))`` (the local trials, _kmeans.py:226,249).
+    -> first (n_init,) int64, rand (n_init, n_clusters - 1, n_local_trials) float64, n_local_trials."""
+    import numpy as np
+
+    L = 2 + int(np.log(n_clusters))
+    rs = np.random.RandomState(seed)
+    p = np.ones(k, dtype=np.float64)
+    p = p / p.sum()
+    first = np.empty(n_init, dtype=np.int64)
+    rand = np.empty((n_init, n_clusters - 1, L), dtype=np.float64)
+    for i in range(n_init):
+        first[i] = rs.choice(k, p=p)
+        for c in range(1, n_clusters):
+            rand[i, c - 1] = rs.uniform(size=L)
+    return first, rand, L
+
+
+def polysem_kmeans(V: torch.Tensor, n_clusters: int = 2, random_state: int = 123, replace_empty_clusters: bool = True,
+                   n_init: int = 10) -> torch.Tensor:
+    """K8g: polysemanticity for any n_clusters in [2, 8] and any number of examples: (C, k, D) fp32 CUDA -> (C,) float64."""
+    lib = N.load(require_device=True)
+    N.require_cuda(V, "V")
+    assert V.ndim == 3
+    V = V.detach().to(torch.float32).contiguous()
+    C, k, D = V.shape
+    out = torch.empty((C,), dtype=torch.float64, device=V.device)
+    if C == 0:
+        return out
+    if k == 0 or D == 0:
+        raise ValueError("polysemanticity_score needs at least one sample and one feature per neuron")
+    if k < n_clusters:
+        raise ValueError(f"n_samples={k} should be >= n_clusters={n_clusters}.")  # sklearn's message
+    if not 2 <= n_clusters <= POLYSEM_MAX_CLUSTERS:
+        raise N.SlbError(f"polysemanticity kernel supports 2..{POLYSEM_MAX_CLUSTERS} clusters (got {n_clusters})")
+    first, rand, L = kmeanspp_draws_general(k, n_clusters, random_state, n_init)
+    need = lib.slb_polysem_kmeans_workspace_bytes(C, k, D, n_clusters, n_init)
+    ws = torch.empty(need, dtype=torch.uint8, device=V.device)
+    with _dev_guard(V):
+        rc = lib.slb_polysem_kmeans(V.data_ptr(), C, k, D, n_clusters, first.ctypes.data, rand.ctypes.data, L, n_init,
+                                    1 if replace_empty_clusters else 0, out.data_ptr(), ws.data_ptr(), need,
+                                    N.stream_ptr(V.device))
+    N.check(rc, "slb_polysem_kmeans")
+    return out
+
+
 def redundancy(cones: torch.Tensor) -> torch.Tensor:
     """K9: mean_i max_{j != i} cos(cones_i, cones_j) for a (n, D) fp32 CUDA tensor -> 0-d fp32 tensor.
 

@@ -107,18 +107,21 @@ def redundancy_score(cones: torch.Tensor) -> torch.Tensor:
 @torch.inference_mode()
 def polysemanticity_score(V: torch.Tensor, replace_empty_clusters: bool = True, random_state: int = 123,
                           n_clusters: int = 2) -> torch.Tensor:
-    """1 - clarity of the 2-means cluster centres of each neuron's examples (reference scores.py:132-185).
+    """1 - clarity of the k-means cluster centres of each neuron's examples (reference scores.py:132-185).
 
-    The reference fits ``sklearn.cluster.KMeans(n_clusters=2, n_init=10, random_state=123)`` per neuron in a Python
-    loop; K8 runs the same algorithm (k-means++ with sklearn's RandomState stream, Lloyd to strict convergence or
+    The reference fits ``sklearn.cluster.KMeans(n_clusters, n_init=10, random_state=123)`` per neuron in a Python
+    loop; K8 runs the same algorithm for the default ``n_clusters=2`` with up to 256 examples per neuron (k-means++ with sklearn's RandomState stream, Lloyd to strict convergence or
     tolerance, best of 10 by inertia) for every neuron on the GPU from the neuron's Gram matrix. Returns float64
     like the reference. Neurons whose smaller cluster has fewer than 2 members take the reference's fallback
     ``1 - mean_{i<10} clarity([mean(V), V[:, i]])`` when ``replace_empty_clusters``.
     """
-    if n_clusters != 2:
-        raise NotImplementedError("the B200 polysemanticity kernel implements the reference default n_clusters=2")
     if V.ndim != 3:
         raise ValueError("polysemanticity_score expects (n_neurons, n_samples, n_features)")
     dev = V.device
-    out = ops.polysem_2means(_to_gpu(V), random_state=random_state, replace_empty_clusters=replace_empty_clusters)
+    if n_clusters == 2 and V.shape[1] <= ops.POLYSEM_FAST_MAX_EXAMPLES:
+        out = ops.polysem_2means(_to_gpu(V), random_state=random_state, replace_empty_clusters=replace_empty_clusters)
+    else:
+        # any number of clusters (2..8) / of examples: the same sklearn fit in sample space (K8g)
+        out = ops.polysem_kmeans(_to_gpu(V), n_clusters=n_clusters, random_state=random_state,
+                                 replace_empty_clusters=replace_empty_clusters)
     return out.to(dev) if out.device != dev else out

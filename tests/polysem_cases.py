@@ -45,3 +45,36 @@ def hash_name(name: str) -> int:
     for ch in name.encode():
         h = ((h ^ ch) * 16777619) & 0xFFFFFFFF
     return h
+
+
+# Cases for the general kernel (K8g): (C, k, D, kind, n_clusters) — more than two clusters and / or more than 256 examples.
+# Reference outputs: tests/golden/scores_poly_general.npz (oracle/make_golden.py::gen_scores_poly_general).
+GENERAL_CASES = {
+    "g3_gauss_k40": (10, 40, 24, "gauss", 3),
+    "g4_planted_k64": (8, 64, 16, "planted3", 4),
+    "g3_planted_k300": (6, 300, 32, "planted3", 3),
+    "g2_gauss_k300": (6, 300, 48, "gauss", 2),
+    "g2_planted_k520": (4, 520, 24, "planted", 2),
+    "g5_k30_d5": (10, 30, 5, "gauss", 5),
+    "g3_dups_k24": (12, 24, 8, "dups", 3),
+    "g8_gauss_k100": (4, 100, 12, "gauss", 8),
+    "g2_outlier_k300": (6, 300, 16, "outlier", 2),
+}
+
+
+def make_general_case(name: str) -> np.ndarray:
+    C, k, D, kind, _ = GENERAL_CASES[name]
+    rng = np.random.default_rng(abs(hash_name(name)))
+    V = rng.standard_normal((C, k, D)).astype(np.float32)
+    if kind == "planted":
+        V[:, ::2] += 2.0 * rng.standard_normal((C, 1, D)).astype(np.float32)
+    elif kind == "planted3":
+        V[:, ::3] += 3.0 * rng.standard_normal((C, 1, D)).astype(np.float32)
+        V[:, 1::3] -= 3.0 * rng.standard_normal((C, 1, D)).astype(np.float32)
+    elif kind == "dups":
+        V[:, 1:] = V[:, :1]          # two or three distinct points only: clusters stay empty / get relocated
+        V[4:, 8] += 1.0
+        V[8:, 9] += 2.0
+    elif kind == "outlier":
+        V[:, 0] += 40.0              # one far example: a single-member cluster -> the "< 2 members" fallback
+    return V

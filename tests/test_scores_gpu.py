@@ -173,6 +173,42 @@ def test_polysemanticity_zeros_subnormals_and_non_finite_examples(S):
     np.testing.assert_allclose(got_bad[[0, 1, 3, 5]], ref[[0, 1, 3, 5]], rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize("name", list(__import__("tests.polysem_cases", fromlist=["GENERAL_CASES"]).GENERAL_CASES))
+def test_polysemanticity_general_cases_match_reference(golden, S, name):
+    """n_clusters = 2..8 and more than 256 examples per neuron (K8g, slb_polysem_kmeans) against outputs recorded from the
+    imported reference (sklearn KMeans per neuron), and against the sample-space oracle."""
+    from tests.polysem_cases import GENERAL_CASES, make_general_case
+
+    z = np.load(golden / "scores_poly_general.npz")
+    m = GENERAL_CASES[name][4]
+    V = make_general_case(name)
+    got = S.polysemanticity_score(torch.from_numpy(V).cuda(), n_clusters=m).cpu().numpy()
+    np.testing.assert_allclose(got, z[f"{name}.poly"], rtol=0, atol=2e-6)
+    got_nr = S.polysemanticity_score(torch.from_numpy(V).cuda(), replace_empty_clusters=False, n_clusters=m).cpu().numpy()
+    np.testing.assert_allclose(got_nr, z[f"{name}.poly_noreplace"], rtol=0, atol=1e-9)
+
+
+def test_polysemanticity_general_kernel_agrees_with_the_fast_kernel(S):
+    """Two clusters, <= 256 examples: both kernels implement the same fit."""
+    from semanticlens_b200 import ops
+
+    rng = np.random.default_rng(21)
+    V = rng.standard_normal((40, 48, 32)).astype(np.float32)
+    V[::2, ::2] += 2 * rng.standard_normal((20, 1, 32)).astype(np.float32)
+    Vg = torch.from_numpy(V).cuda()
+    np.testing.assert_allclose(ops.polysem_kmeans(Vg, 2).cpu().numpy(), ops.polysem_2means(Vg).cpu().numpy(), rtol=0, atol=1e-9)
+
+
+def test_polysemanticity_general_errors(S):
+    V = torch.randn(2, 3, 8).cuda()
+    with pytest.raises(ValueError, match="n_samples=3 should be >= n_clusters=4"):
+        S.polysemanticity_score(V, n_clusters=4)
+    bad = torch.randn(3, 300, 8)
+    bad[1, 5, 2] = float("nan")
+    got = S.polysemanticity_score(bad.cuda()).cpu()
+    assert torch.isnan(got[1]) and torch.isfinite(got[[0, 2]]).all()
+
+
 def test_cosine_gemm_shapes_vs_port(S):
     g = torch.Generator().manual_seed(3)
     for (Q, C, D) in ((1, 10, 128), (7, 1000, 512), (300, 129, 768), (130, 260, 100)):
