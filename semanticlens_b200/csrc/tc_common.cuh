@@ -13,7 +13,9 @@ typedef CUresult (*slb_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint
 slb_tmap_encode_fn slb_get_tmap_encoder();  // nullptr (+ error string) if the driver does not provide it
 
 // 3-D map over 16-bit planes [planes][rows][cols] (cols contiguous); box = {64 cols, box_rows, planes}; 128B swizzle.
+// (cached per host thread by its arguments; slb_encode_plane_map always calls the driver)
 int slb_make_plane_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int planes, int box_rows);
+int slb_encode_plane_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int planes, int box_rows);
 
 // im2col-mode map over ONE channels-last 16-bit plane (B, H, W, C) for a ksize x ksize / stride / pad convolution: a load
 // brings `pixels` consecutive output pixels x 64 channels of one filter tap (128B swizzle, zero fill outside the image).

@@ -117,6 +117,30 @@ def test_k1_tokens_bitexact_vs_canonical_oracle(ops, shape, op):
     assert_f32_bitexact(got, oc.aggregate_canonical(x.numpy(), op, "tokens"))
 
 
+# the (B, T, F) kernel picks its per-lane vector width from F, the alignment and the CTA count, and stages block partials in
+# chunks: long chains (several chunks), wide batches (16-byte lanes), odd widths (scalar lanes), 16-bit inputs, unaligned bases
+@pytest.mark.parametrize("shape,dtype,offset", [
+    ((1, 17000, 32), torch.float32, 0),      # 266 blocks of 64 tokens: two partial chunks at one element per lane
+    ((2, 12544, 64), torch.float32, 0),      # the channels-last conv1 map of ResNet-50
+    ((320, 70, 128), torch.float32, 0),      # enough CTAs for 16-byte lanes
+    ((320, 130, 130), torch.float32, 0),     # F % 4 != 0: 8-byte lanes, a partial feature group
+    ((3, 100, 37), torch.float32, 0),        # odd width: scalar lanes
+    ((40, 90, 64), torch.float32, 1),        # base pointer 4-byte aligned only
+    ((700, 66, 256), torch.float16, 0),      # 16-byte lanes of eight halves
+    ((5, 200, 30), torch.float16, 0),
+    ((6, 129, 72), torch.float16, 1),        # 2-byte aligned base
+])
+@pytest.mark.parametrize("op", ["mean", "absmax"])
+def test_k1_tokens_vector_widths_and_chunks(ops, shape, dtype, offset, op):
+    g = torch.Generator().manual_seed(hash((shape, op)) % 2**31)
+    x = torch.randn(*shape, generator=g).to(dtype)
+    buf = torch.empty(x.numel() + 8, dtype=dtype, device="cuda")
+    xd = buf[offset : offset + x.numel()].view(shape)
+    xd.copy_(x)
+    got = ops.agg_reduce(xd, OPS[op], "tokens").cpu().numpy()
+    assert_f32_bitexact(got, oc.aggregate_canonical(x.numpy(), op, "tokens"))
+
+
 @pytest.mark.parametrize("pos", [0, 3, -1])
 def test_k1_special_token(ops, pos):
     x = torch.randn(4, 9, 33)
