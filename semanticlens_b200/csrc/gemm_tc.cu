@@ -33,7 +33,7 @@ constexpr int kEpiWarps = 8;  // two warps per TMEM lane quarter, interleaved ov
 constexpr int kThreads = (2 + kEpiWarps) * 32;
 // per-warp transpose tile of the epilogue (see drain_chunk)
 constexpr int kTileStride = 20;                // floats per tile row: 16 columns + 4 pad (float4-aligned, conflict-free writes)
-constexpr int kTileFloats = 32 * kTileStride;  // per epilogue warp
+constexpr int kTileFloats = 1024;              // per epilogue warp: the 32 x 20 transpose tile, or two 2 KB TMA-store boxes
 constexpr int kEpiTileBytes = kEpiWarps * kTileFloats * 4;
 
 template <int BN>
@@ -45,7 +45,7 @@ struct Cfg {
     static constexpr int kWBytes = 2 * BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kWBytes;
     static constexpr int kTmemCols = 4 * BN;  // [buffer][main | cross][BN]: the cross half is used by SLB_PASSES_SPLIT_ACC only
-    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiTileBytes;
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kEpiTileBytes;
 };
 
 struct GemmParams {
@@ -71,6 +71,9 @@ struct GemmParams {
     // implicit-GEMM convolution (slb_conv_gemm): A is never materialised — row m of the GEMM is output pixel m of a
     // k x k / stride / pad convolution over channels-last planes and k-block kb is (filter tap, 64-channel chunk); the
     // producer fetches it with TMA im2col-mode loads (one per plane). One-CTA kernel only.
+    // TMA-store epilogue (host decides): 0 = per-lane global stores; 1 = the fp32 output, 2 = the plane output leave through
+    // cp.async.bulk.tensor stores of 32-row x 16-column boxes that each epilogue warp stages in its shared-memory tile
+    int tma_store;
     int conv;                       // 0 = plain GEMM
     int conv_cc, conv_k;            // 64-channel chunks per tap, filter size
     int conv_stride, conv_pad;
@@ -98,6 +101,12 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float val) {
 // fp32, + the 2-ulp ex2.approx), and Phi(x) = 1 - Phi(-x) for x > 0. Beyond |x| = 6 Phi is 1e-9 from 0 / 1. The error
 // that matters for GELU is the absolute error of Phi (GELU error = |x| times it), i.e. this is as good as the fp32 erff
 // formula's own rounding of 1 + erf. NaN goes through (fminf drops it from t, the final product restores it).
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float gelu_erf_fast(float x) {
     const float t = fminf(fabsf(x), 6.0f);
     float q = 2.8350232241791673e-06f;
@@ -117,11 +126,13 @@ __device__ __forceinline__ float act_apply(float v, int epi) {
     switch (epi) {
         case SLB_EPI_GELU_ERF:
             return gelu_erf_fast(v);
-        case SLB_EPI_QUICKGELU:
-            return v / (1.0f + __expf(-1.702f * v));
+        case SLB_EPI_QUICKGELU:  // x sigmoid(1.702 x)
+            return __fdividef(v, 1.0f + ex2_approx(-1.702f * 1.4426950408889634f * v));
         case SLB_EPI_GELU_TANH: {
-            float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
-            return 0.5f * v * (1.0f + tanhf(u));
+            // 0.5 x (1 + tanh u) = x - x / (1 + e^(2u)), u = sqrt(2/pi) (x + 0.044715 x^3): one ex2 and one fast division
+            // instead of tanhf (~30 instructions with its own branch); |error| ~ 1e-7 |x|
+            const float u2 = 2.0f * 0.7978845608028654f * 1.4426950408889634f * fmaf(0.044715f * v * v, v, v);
+            return v - __fdividef(v, 1.0f + ex2_approx(fminf(u2, 88.0f)));
         }
         case SLB_EPI_RELU:
             return fmaxf(v, 0.0f);
@@ -288,6 +299,128 @@ __device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr,
     }
 }
 
+// ---- TMA-store epilogue ---------------------------------------------------------------------------------------
+// For outputs without a shortcut (in_proj, fc, the convolutions that are not a block tail, the cosine GEMM) the thread that
+// drained row r from TMEM keeps all 32 columns of the chunk: column scale / bias arrive as broadcast loads, the activation
+// runs on 32 independent values, and the results are written ONCE to the warp's shared-memory tile in the layout a tensor-map
+// store expects (32 rows x 16 columns, 64-byte rows for fp32 / 32-byte rows per plane, hardware swizzle so that a
+// quarter-warp's 16-byte writes hit distinct banks). One lane then issues cp.async.bulk.tensor stores (UTMASTG): no
+// transpose read-back, no per-lane global addresses, and partial tiles are clipped by the TMA unit.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(slb_smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(slb_smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void drain_chunk_tma(const GemmParams& p, const CUtensorMap* tmO, uint32_t taddr, int64_t m_warp, int lane,
+                                                float rs, int64_t nb, int fmt, float* tile, uint32_t cross_off, uint32_t& n_stores) {
+    uint32_t raw[32];
+    float v[32];
+    slb_tmem_ld_32x32(taddr, raw);
+    if (cross_off) {
+        uint32_t cr[32];
+        slb_tmem_ld_32x32(taddr + cross_off, cr);
+        slb_tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(raw[j]) + __uint_as_float(cr[j])) * p.alpha;
+    } else {
+        slb_tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+    }
+    if (nb >= p.N || m_warp >= p.M) return;  // warp-uniform
+    if (p.row_scale) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= rs;
+    }
+    if (p.col_scale || p.bias) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int64_t n = nb + 4 * q;  // N % 8 == 0: four columns are inside together
+            float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < p.N) {
+                if (p.col_scale) cs = __ldg(reinterpret_cast<const float4*>(p.col_scale + n));
+                if (p.bias) bs = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            }
+            v[4 * q] = fmaf(v[4 * q], cs.x, bs.x);
+            v[4 * q + 1] = fmaf(v[4 * q + 1], cs.y, bs.y);
+            v[4 * q + 2] = fmaf(v[4 * q + 2], cs.z, bs.z);
+            v[4 * q + 3] = fmaf(v[4 * q + 3], cs.w, bs.w);
+        }
+    }
+    if (p.epilogue == SLB_EPI_GELU_ERF) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+    } else if (p.epilogue != SLB_EPI_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], p.epilogue);
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int64_t n0 = nb + half * 16;
+        if (n0 >= p.N) break;  // warp-uniform
+        // two 2 KB boxes per warp, used alternately: a box is free once the store before the previous one has finished READING it
+        unsigned char* tb = reinterpret_cast<unsigned char*>(tile) + ((n_stores & 1u) << 11);
+        if (n_stores >= 2) {
+            if (lane == 0) bulk_wait_read1();
+            __syncwarp();
+        }
+        if (p.tma_store == 1) {
+            // 64-byte rows, 64B swizzle: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)
+            const int sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<float4*>(tb + lane * 64 + ((c ^ sw) << 4)) =
+                    make_float4(v[half * 16 + 4 * c], v[half * 16 + 4 * c + 1], v[half * 16 + 4 * c + 2], v[half * 16 + 4 * c + 3]);
+        } else {
+            // hi rows at the tile base, lo rows 1 KB above; 32-byte rows, 32B swizzle: chunk c of row r at c ^ ((r >> 2) & 1)
+            uint32_t hp[8], lp[8];
+            if (fmt == 0) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) slb_split_pair_act_f16(v[half * 16 + 2 * e], v[half * 16 + 2 * e + 1], hp[e], lp[e]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    uint16_t h0, l0, h1, l1;
+                    slb_split2_act(v[half * 16 + 2 * e], fmt, h0, l0);
+                    slb_split2_act(v[half * 16 + 2 * e + 1], fmt, h1, l1);
+                    hp[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                    lp[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                }
+            }
+            const int sw = (lane >> 2) & 1;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                *reinterpret_cast<uint4*>(tb + lane * 32 + ((c ^ sw) << 4)) = make_uint4(hp[4 * c], hp[4 * c + 1], hp[4 * c + 2], hp[4 * c + 3]);
+                *reinterpret_cast<uint4*>(tb + 1024 + lane * 32 + ((c ^ sw) << 4)) =
+                    make_uint4(lp[4 * c], lp[4 * c + 1], lp[4 * c + 2], lp[4 * c + 3]);
+            }
+        }
+        // generic-proxy writes -> visible to the async proxy (TMA) before the store is issued
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            if (p.tma_store == 1) {
+                tma_store_2d(tmO, tb, (int)n0, (int)m_warp);
+            } else {
+                tma_store_3d(tmO, tb, (int)n0, (int)m_warp, 0);
+                tma_store_3d(tmO, tb + 1024, (int)n0, (int)m_warp, 1);
+            }
+            bulk_commit();
+        }
+        ++n_stores;
+    }
+}
+
 // a lost hand-off (a TMA load that never completes its bytes) must fail the launch, not hang the GPU
 __device__ __forceinline__ void gemm_wait(uint64_t* bar, uint32_t parity) {
     if (slb_mbar_try_wait(bar, parity)) return;
@@ -299,7 +432,7 @@ __device__ __forceinline__ void gemm_wait(uint64_t* bar, uint32_t parity) {
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                  const __grid_constant__ CUtensorMap tmW, GemmParams p) {
+                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, GemmParams p) {
     using C = Cfg<BN>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -418,7 +551,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int acc = 0;
         uint32_t acc_phase = 0;
         const int fmt = p.fmt;
-        float* tile = reinterpret_cast<float*>(smem + (size_t)C::kStages * C::kStageBytes + 256) + (warp - 2) * kTileFloats;
+        uint32_t n_stores = 0;  // TMA-store epilogue: boxes this warp has handed to the TMA unit
+        float* tile = reinterpret_cast<float*>(smem + (size_t)C::kStages * C::kStageBytes + 512) + (warp - 2) * kTileFloats;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
             gemm_wait(&tfull[acc], acc_phase);
@@ -428,13 +562,18 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll 1
             for (int c = chunk0; c < BN / 32; c += kEpiWarps / 4) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
-                drain_chunk(p, taddr, (int64_t)m0 + quarter * 32, lane, rs, (int64_t)n0 + c * 32, fmt, tile, p.split_acc ? BN : 0);
+                if (p.tma_store)
+                    drain_chunk_tma(p, &tmO, taddr, (int64_t)m0 + quarter * 32, lane, rs, (int64_t)n0 + c * 32, fmt, tile,
+                                    p.split_acc ? BN : 0, n_stores);
+                else
+                    drain_chunk(p, taddr, (int64_t)m0 + quarter * 32, lane, rs, (int64_t)n0 + c * 32, fmt, tile, p.split_acc ? BN : 0);
             }
             slb_tc_fence_before();
             __syncwarp();
             if (lane == 0) slb_mbar_arrive(&tempty[acc]);
             if (++acc == C::kAccBufs) { acc = 0; acc_phase ^= 1u; }
         }
+        if (n_stores && lane == 0) bulk_wait0();  // the stores read this CTA's shared memory: finish before it goes away
     }
 
     slb_tc_fence_before();
@@ -472,7 +611,7 @@ struct CfgPair {
     static constexpr int kWBytes = 2 * (BN / 2) * BK * 2;  // this CTA's half of the W rows, both planes
     static constexpr int kStageBytes = kABytes + kWBytes;  // 48 / 56 / 64 KB
     static constexpr int kTmemCols = PBN == 192 ? 512 : 2 * PBN;  // [buffer][BN]; allocations are powers of two
-    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 + 256 + kEpiTileBytes;
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 + 512 + kEpiTileBytes;
 };
 
 // bounded wait: a protocol error must abort the kernel (trap -> CUDA error), never hang the device. On timeout
@@ -497,7 +636,8 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
 
 template <int PBN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmParams p) {
+gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                       const __grid_constant__ CUtensorMap tmO, GemmParams p) {
     using C = CfgPair<PBN>;
     constexpr int BN = C::BN;
     extern __shared__ unsigned char smem_raw[];
@@ -599,7 +739,8 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int acc = 0;
         uint32_t acc_phase = 0;
         const int fmt = p.fmt;
-        float* tile = reinterpret_cast<float*>(smem + (size_t)C::kStages * C::kStageBytes + 256) + (warp - 2) * kTileFloats;
+        uint32_t n_stores = 0;  // TMA-store epilogue: boxes this warp has handed to the TMA unit
+        float* tile = reinterpret_cast<float*>(smem + (size_t)C::kStages * C::kStageBytes + 512) + (warp - 2) * kTileFloats;
         for (int t = cluster_id; t < total; t += num_clusters) {
             const int m0 = (t / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (t % tiles_n) * BN;
             mbar_wait_bounded(&tfull[acc], acc_phase, p.dbg, 4, t, -1, acc);
@@ -609,13 +750,17 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll 1
             for (int c = chunk0; c < BN / 32; c += kEpiWarps / 4) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32);
-                drain_chunk(p, taddr, (int64_t)m0 + quarter * 32, lane, rs, (int64_t)n0 + c * 32, fmt, tile);
+                if (p.tma_store)
+                    drain_chunk_tma(p, &tmO, taddr, (int64_t)m0 + quarter * 32, lane, rs, (int64_t)n0 + c * 32, fmt, tile, 0, n_stores);
+                else
+                    drain_chunk(p, taddr, (int64_t)m0 + quarter * 32, lane, rs, (int64_t)n0 + c * 32, fmt, tile);
             }
             slb_tc_fence_before();
             __syncwarp();
             if (lane == 0) slb_mbar_arrive_cluster(slb_mapa(slb_smem_u32(&tempty[acc]), 0));
             if (++acc == C::kAccBufs) { acc = 0; acc_phase ^= 1u; }
         }
+        if (n_stores && lane == 0) bulk_wait0();
     }
 
     // neither CTA may exit (or free tensor memory) while its partner can still touch its shared / tensor memory
@@ -646,13 +791,14 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 }
 
 template <int BN>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW, const GemmParams& p, cudaStream_t st) {
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
+                cudaStream_t st) {
     using C = Cfg<BN>;
     auto kern = gemm_split_kernel<BN>;
     SLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
     const int64_t tiles = slb_ceil_div(p.M, BM) * slb_ceil_div(p.N, BN);
     const int grid = (int)std::min<int64_t>(tiles, slb_sm_count());
-    kern<<<grid, kThreads, C::kSmem, st>>>(tmA, tmA2, tmW, p);
+    kern<<<grid, kThreads, C::kSmem, st>>>(tmA, tmA2, tmW, tmO, p);
     SLB_LAUNCH_OK("gemm_split");
     return SLB_OK;
 }
@@ -661,7 +807,7 @@ unsigned int* g_dbg_host = nullptr;  // SLB_GEMM_DEBUG=1 only
 unsigned int* g_dbg_dev = nullptr;
 
 template <int PBN>
-int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p_in, cudaStream_t st) {
+int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p_in, cudaStream_t st) {
     using C = CfgPair<PBN>;
     GemmParams p = p_in;
     static const bool debug = [] { const char* e = getenv("SLB_GEMM_DEBUG"); return e && e[0] == '1'; }();
@@ -676,7 +822,7 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmP
     SLB_CUDA_OK(cudaFuncSetAttribute(gemm_split_pair_kernel<PBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
     const int64_t tiles = slb_ceil_div(p.M, 2 * BM) * slb_ceil_div(p.N, C::BN);
     const int clusters = (int)std::min<int64_t>(tiles, slb_sm_count() / 2);
-    gemm_split_pair_kernel<PBN><<<2 * clusters, kThreads, C::kSmem, st>>>(tmA, tmW, p);
+    gemm_split_pair_kernel<PBN><<<2 * clusters, kThreads, C::kSmem, st>>>(tmA, tmW, tmO, p);
     SLB_LAUNCH_OK("gemm_split_pair");
     if (debug) {
         cudaError_t e = cudaStreamSynchronize(st);
@@ -771,6 +917,44 @@ int slb_encode_plane_map(CUtensorMap* out, const void* base, int64_t rows, int64
                       (long long)cols, box_rows);
         return SLB_ECUDA;
     }
+    return SLB_OK;
+}
+
+// Output map for the TMA-store epilogue: planes == 0 -> fp32 (M, N), box 16 columns x 32 rows, 64B swizzle;
+// planes == 2 -> 16-bit planes (2, M, N), box 16 columns x 32 rows x 1 plane, 32B swizzle. Cached like the plane maps.
+int slb_make_store_map(CUtensorMap* out, const void* base, int64_t M, int64_t N, int planes) {
+    static thread_local PlaneMapCache cache;
+    const PlaneMapKey key{base, M, N, planes, -1};
+    const size_t slot = plane_map_slot(key);
+    if (cache.used[slot] && cache.key[slot] == key) {
+        *out = cache.map[slot];
+        return SLB_OK;
+    }
+    slb_tmap_encode_fn enc = slb_get_tmap_encoder();
+    if (!enc) return SLB_ECUDA;
+    CUresult r;
+    if (planes == 0) {
+        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+        cuuint64_t strides[1] = {(cuuint64_t)N * 4};
+        cuuint32_t box[2] = {16, 32};
+        cuuint32_t estr[2] = {1, 1};
+        r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, 2};
+        cuuint64_t strides[2] = {(cuuint64_t)N * 2, (cuuint64_t)M * (cuuint64_t)N * 2};
+        cuuint32_t box[3] = {16, 32, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) {
+        slb_set_error("cuTensorMapEncodeTiled (store map) failed with %d (M=%lld N=%lld planes=%d)", (int)r, (long long)M, (long long)N, planes);
+        return SLB_ECUDA;
+    }
+    cache.key[slot] = key;
+    cache.map[slot] = *out;
+    cache.used[slot] = true;
     return SLB_OK;
 }
 
@@ -989,9 +1173,25 @@ static int run_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, Ge
     if (rc != SLB_OK) return rc;
     rc = slb_make_plane_map(&tmW, w_planes, N, K, 2, kind == 2 ? 64 : (kind == 4 ? 96 : 128));  // W rows staged per CTA
     if (rc != SLB_OK) return rc;
+    // TMA-store epilogue: exactly one output, nothing that needs a second operand per element (shortcut, raw hook output,
+    // fused row maximum). Measured on one box (r2 A/B, towers): CTA-pair kernels 5.68 -> 5.50 ms (ViT-B/32), 23.87 -> 23.58 ms
+    // (ViT-L/14); the one-CTA kernel's convolutions 7.47 -> 8.69 ms (RN50: boxes of 32-byte plane rows are a poor fit for the
+    // TMA unit, and those GEMMs are pure epilogue) — so the pair kernels use it and the one-CTA kernel keeps per-lane stores.
+    // SLB_GEMM_TMA_STORE = 0 (never) | 1 (pair kernels with K < 1024, default) | 2 (all kernels).
+    static const int tma_store_mode = [] { const char* e = getenv("SLB_GEMM_TMA_STORE"); return e ? atoi(e) : 1; }();
+    // (K >= 1024: the main loop hides the epilogue either way and the stores' bookkeeping costs 1-3 %: cfg 3 A/B 41.0 vs 42.3 ms)
+    const bool tma_store_on = tma_store_mode == 2 || (tma_store_mode == 1 && kind != 1 && K < 1024);
+    CUtensorMap tmO;
+    memset(&tmO, 0, sizeof(tmO));
+    p.tma_store = 0;
+    if (tma_store_on && !p.residual && !p.raw_f32 && !p.rowmax && p.epilogue != SLB_EPI_ADD_RELU && ((out_f32 != nullptr) != (out_planes != nullptr))) {
+        rc = slb_make_store_map(&tmO, out_f32 ? (const void*)out_f32 : (const void*)out_planes, M, N, out_f32 ? 0 : 2);
+        if (rc != SLB_OK) return rc;
+        p.tma_store = out_f32 ? 1 : 2;
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (kind == 4) return launch_gemm_pair<192>(tmA, tmW, p, st);
-    if (kind == 3) return launch_gemm_pair<256>(tmA, tmW, p, st);
-    if (kind == 2) return launch_gemm_pair<128>(tmA, tmW, p, st);
-    return launch_gemm<128>(tmA, tmA2, tmW, p, st);
+    if (kind == 4) return launch_gemm_pair<192>(tmA, tmW, tmO, p, st);
+    if (kind == 3) return launch_gemm_pair<256>(tmA, tmW, tmO, p, st);
+    if (kind == 2) return launch_gemm_pair<128>(tmA, tmW, tmO, p, st);
+    return launch_gemm<128>(tmA, tmA2, tmW, tmO, p, st);
 }

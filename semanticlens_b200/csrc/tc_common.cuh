@@ -16,6 +16,8 @@ slb_tmap_encode_fn slb_get_tmap_encoder();  // nullptr (+ error string) if the d
 // (cached per host thread by its arguments; slb_encode_plane_map always calls the driver)
 int slb_make_plane_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int planes, int box_rows);
 int slb_encode_plane_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int planes, int box_rows);
+// output map of the GEMM's TMA-store epilogue: planes == 0 -> fp32 (M, N); planes == 2 -> 16-bit planes (2, M, N)
+int slb_make_store_map(CUtensorMap* out, const void* base, int64_t M, int64_t N, int planes);
 
 // im2col-mode map over ONE channels-last 16-bit plane (B, H, W, C) for a ksize x ksize / stride / pad convolution: a load
 // brings `pixels` consecutive output pixels x 64 channels of one filter tap (128B swizzle, zero fill outside the image).
