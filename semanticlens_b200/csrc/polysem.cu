@@ -210,6 +210,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// (Measured and dropped: TWO kernels per chunk of 8192 neurons — a Gram kernel whose two resident CTAs per SM are always in
+// phase A and a k-means kernel among its own kind, the Gram slots making one round trip through HBM. Phase A then takes
+// 346 us per neuron and CTA = 173 us per neuron and SM = 31.6 TFLOP/s of FP64 tensor work, 79 % of B200's 40 TFLOP/s, and
+// phase B 143 us per neuron and CTA (248 us at three CTAs per SM: the G0 x W products contend for the same pipe): 130 ms for
+// 65 536 neurons, the same as the fused kernel, for 2.2 GB of workspace instead of 80 MB. So the fused kernel's overlap
+// already hides phase B about as well as a split can; what is left is the FP64 tensor throughput itself.)
 // (Measured and dropped: ONE 2-D TMA box per stage behind a 4-slot full / empty mbarrier ring instead of a bulk copy per row
 // and a block barrier per stage: phase A of a lone CTA 238 -> 234 us, the whole kernel 130 -> 136 ms — the copies and
 // barriers were not the bound. With SLB_POLYSEM_CTAS_PER_SM=1 a lone CTA needs 238 us per Gram matrix where the DMMA
