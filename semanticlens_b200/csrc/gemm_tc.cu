@@ -1110,7 +1110,13 @@ int slb_gemm_rowmax_offdiag(const uint16_t* planes, int64_t n, int64_t n_pad, in
 static int run_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, GemmParams p, void* stream) {
     const int64_t M = p.M, N = p.N, K = p.K;
     int passes = p.passes;
-    const int split_acc = passes == SLB_PASSES_SPLIT_ACC;
+    // The second accumulator exists to keep the one-sided truncation of long accumulations out of the result (the error
+    // grows with the number of MMA steps per output). With K <= 256 an output sees at most 48 steps — less than a ViT-B
+    // projection through one accumulator — while such GEMMs (the 1 x 1 convolutions of the first ResNet stages) are pure
+    // epilogue, where the second TMEM load per chunk is paid in full. SLB_GEMM_SPLIT_ACC_MIN_K overrides the threshold.
+    static const int64_t split_min_k = [] { const char* e = getenv("SLB_GEMM_SPLIT_ACC_MIN_K"); return e ? (int64_t)atoll(e) : (int64_t)257; }();
+    const int split_acc = passes == SLB_PASSES_SPLIT_ACC && K >= split_min_k;
+    if (passes == SLB_PASSES_SPLIT_ACC && !split_acc) passes = 3;
     if (split_acc) passes = 3;
     p.passes = passes; p.split_acc = split_acc;
     float* out_f32 = p.out_f32;

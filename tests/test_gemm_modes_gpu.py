@@ -1,0 +1,23 @@
+"""The GEMM's two epilogues (per-lane stores after a shared-memory transpose / TMA stores of swizzled boxes) are chosen
+per launch by the host; SLB_GEMM_TMA_STORE forces one for every eligible launch. The env var is read once per process, so
+each mode runs the GEMM and tower parity tests in a child interpreter."""
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_gemm_and_tower_parity_with_the_store_path_forced(mode):
+    env = dict(os.environ, SLB_GEMM_TMA_STORE=mode)
+    r = subprocess.run(
+        [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "tests/test_gemm_gpu.py",
+         "tests/test_rn_gpu.py", "tests/test_embed_gpu.py::test_vit_tower_vs_oracle", "tests/test_embed_gpu.py::test_siglip_tower_vs_oracle"],
+        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
