@@ -201,6 +201,9 @@ int slb_split_planes(const float* x, int64_t n, int plane_fmt, float scale, uint
 #define SLB_EPI_GELU_TANH 3 /* nn.GELU("tanh")       (SigLIP / timm towers) */
 #define SLB_EPI_RELU 4      /* max(z, 0)             (conv + BatchNorm + ReLU of the CLIP ModifiedResNet) */
 #define SLB_EPI_ADD_RELU 5  /* max(z + residual, 0)  (the tail of a ResNet bottleneck: the ReLU follows the shortcut add) */
+#define SLB_EPI_ADD_RELU_PLANES 6 /* the same, but `residual` points at the shortcut as split planes: const uint16_t [2][M][N] in the
+                                   * GEMM's plane format at the activation scale (what out_planes of the previous block holds), cast to
+                                   * const float*. A residual stream kept as planes never needs an fp32 copy of a block's output. */
 
 #define SLB_PASSES_SPLIT_ACC 4 /* `passes` selector of slb_gemm_split, see below */
 
@@ -390,9 +393,10 @@ int slb_avgpool2_planes(const uint16_t* in_planes, int64_t B, int64_t H, int64_t
 
 /* Implicit-GEMM convolution: out[(b, yo, xo), n] = epi(alpha * sum_{ky,kx,c} x[b, yo*stride + ky - pad, xo*stride + kx - pad, c]
  * * w[n, (ky*ksize + kx)*C + c] * col_scale[n] + bias[n]) (+ residual), the arguments of slb_gemm_split otherwise. x_planes
- * [2, B*H*W, C] channels-last; w_planes [2, N, ksize*ksize*C]. The im2col matrix is never written: the GEMM's producer warp
- * fetches (filter tap, 64-channel chunk) k-blocks with TMA im2col-mode loads (zero fill outside the image, stride in the
- * tensor map's traversal strides). C % 64 == 0, N % 8 == 0, stride 1 or 2, ksize <= 7. */
+ * [2, B*H*W, C] channels-last; w_planes [2, N, slb_conv_k(C, ksize)]. The im2col matrix is never written: the GEMM's producer
+ * warp fetches (filter tap, 64-channel chunk) k-blocks with TMA im2col-mode loads (zero fill outside the image, stride in the
+ * tensor map's traversal strides). C % 64 == 0, or C == 32 (a k-block is then one whole tap: 64-byte rows under the 64-byte
+ * swizzle, two MMA steps — the 3x3 convolutions of the CLIP ModifiedResNet stem); N % 8 == 0, stride 1 or 2, ksize <= 7. */
 int slb_conv_gemm(const uint16_t* x_planes, int64_t B, int64_t H, int64_t W, int64_t C, int ksize, int stride, int pad,
                   const uint16_t* w_planes, int64_t N, int plane_fmt, float alpha, const float* bias, const float* residual,
                   const float* col_scale, int epilogue, int passes, float* out_f32, uint16_t* out_planes, void* stream);

@@ -19,7 +19,7 @@ _lib = None
 DT_F32, DT_F16, DT_BF16 = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_BTF = 0, 1
 AGG_MEAN, AGG_MAX, AGG_ABSMEAN, AGG_ABSMAX, AGG_TOKEN = 0, 1, 2, 3, 4
-EPI_NONE, EPI_GELU_ERF, EPI_QUICKGELU, EPI_GELU_TANH, EPI_RELU, EPI_ADD_RELU = 0, 1, 2, 3, 4, 5
+EPI_NONE, EPI_GELU_ERF, EPI_QUICKGELU, EPI_GELU_TANH, EPI_RELU, EPI_ADD_RELU, EPI_ADD_RELU_PLANES = 0, 1, 2, 3, 4, 5, 6
 POOL_CLS, POOL_MAP = 0, 1
 PASSES_SPLIT_ACC = 4  # SLB_PASSES_SPLIT_ACC
 PLANE_F16, PLANE_BF16 = 0, 1

@@ -36,16 +36,23 @@ constexpr int kTileStride = 20;                // floats per tile row: 16 column
 constexpr int kTileFloats = 1024;              // per epilogue warp: the 32 x 20 transpose tile, or two 2 KB TMA-store boxes
 constexpr int kEpiTileBytes = kEpiWarps * kTileFloats * 4;
 
-template <int BN>
+// EW = epilogue warps of the one-CTA kernel: 8 (two per TMEM lane quarter, three stages) or 16 (four per quarter, two
+// stages). GEMMs with K <= 512 are pure epilogue — one to eight k-blocks per tile against a 64 KB accumulator drain that is
+// a chain of TMEM / shared-memory / global latencies — and sixteen warps hide twice as much of that chain; the registers
+// they need come out of the per-thread budget (576 threads: 113 registers), the shared memory out of the third stage.
+template <int BN, int EW = 8>
 struct Cfg {
     static_assert(BN == 128, "one-CTA tiles are 128 x 128");
+    static_assert(EW == 8 || EW == 16, "two or four epilogue warps per TMEM lane quarter");
+    static constexpr int kEW = EW;
+    static constexpr int kThreadsC = (2 + EW) * 32;
     static constexpr int kAccBufs = 2;
-    static constexpr int kStages = 3;
+    static constexpr int kStages = EW == 8 ? 3 : 2;
     static constexpr int kABytes = 2 * BM * BK * 2;  // both planes
     static constexpr int kWBytes = 2 * BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kWBytes;
     static constexpr int kTmemCols = 4 * BN;  // [buffer][main | cross][BN]: the cross half is used by SLB_PASSES_SPLIT_ACC only
-    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kEpiTileBytes;
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/ + (size_t)EW * kTileFloats * 4;
 };
 
 struct GemmParams {
@@ -57,6 +64,7 @@ struct GemmParams {
     const float* col_scale;  // [N] or null
     float* out_f32;          // [M,N] or null
     uint16_t* out_planes;    // [2,M,N] or null
+    const uint16_t* residual_planes;  // the shortcut as split planes [2][M][N] at the activation scale (SLB_EPI_ADD_RELU_PLANES), or null
     float* raw_f32;          // [M,N] or null: alpha * (A W^T) * row_scale BEFORE column scale / bias / activation / residual —
                              // the raw output of a convolution whose BatchNorm rides in this epilogue, for a forward hook
     int epilogue;
@@ -75,6 +83,8 @@ struct GemmParams {
     // cp.async.bulk.tensor stores of 32-row x 16-column boxes that each epilogue warp stages in its shared-memory tile
     int tma_store;
     int conv;                       // 0 = plain GEMM
+    int bk;                         // elements of K per k-block: 64, or 32 for a convolution over 32-channel maps (a k-block =
+                                    // one filter tap, 64-byte rows under the 64-byte swizzle, two MMA steps per product)
     int conv_cc, conv_k;            // 64-channel chunks per tap, filter size
     int conv_stride, conv_pad;
     int conv_ho, conv_wo;           // output height / width
@@ -153,6 +163,7 @@ __device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr,
     // the shortcut values are fetched first (8 independent 16-byte loads per lane): their latency hides behind the
     // TMEM load and the transpose, and no store of this chunk can be ordered before them (residual may alias out_f32)
     float4 res[2][4];
+    const bool has_res = p.residual != nullptr || p.residual_planes != nullptr;
     if (p.residual && nb < p.N) {
 #pragma unroll
         for (int half = 0; half < 2; ++half)
@@ -162,6 +173,43 @@ __device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr,
                 res[half][it] = (m < p.M && n < p.N) ? *reinterpret_cast<const float4*>(p.residual + m * p.N + n)
                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+    } else if (p.residual_planes && nb < p.N) {
+        // the shortcut kept as planes (22 bits): same bytes to read as fp32, and the block never writes an fp32 copy of its output
+        uint2 rh[2][4], rl[2][4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int64_t m = m_warp + it * 8 + r8, n = nb + half * 16 + c4;
+                const bool ok = m < p.M && n < p.N;
+                rh[half][it] = ok ? *reinterpret_cast<const uint2*>(p.residual_planes + m * p.N + n) : make_uint2(0u, 0u);
+                rl[half][it] = ok ? *reinterpret_cast<const uint2*>(p.residual_planes + p.M * p.N + m * p.N + n) : make_uint2(0u, 0u);
+            }
+        constexpr float kInv = 1.0f / SLB_ACT_PLANE_SCALE;
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const uint2 h = rh[half][it], l = rl[half][it];
+                res[half][it] = make_float4(
+                    (slb_from_plane((uint16_t)(h.x & 0xFFFFu), p.fmt) + slb_from_plane((uint16_t)(l.x & 0xFFFFu), p.fmt)) * kInv,
+                    (slb_from_plane((uint16_t)(h.x >> 16), p.fmt) + slb_from_plane((uint16_t)(l.x >> 16), p.fmt)) * kInv,
+                    (slb_from_plane((uint16_t)(h.y & 0xFFFFu), p.fmt) + slb_from_plane((uint16_t)(l.y & 0xFFFFu), p.fmt)) * kInv,
+                    (slb_from_plane((uint16_t)(h.y >> 16), p.fmt) + slb_from_plane((uint16_t)(l.y >> 16), p.fmt)) * kInv);
+            }
+    }
+    // column scale / bias of both halves too: fetched right before their first use they cost a full load latency per half
+    // (ncu source page: 20 % of a short-K convolution's samples sat on the first FFMA that consumes them)
+    float4 cs2[2], bs2[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int64_t n = nb + half * 16 + c4;
+        cs2[half] = make_float4(1.f, 1.f, 1.f, 1.f);
+        bs2[half] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < p.N) {
+            if (p.col_scale) cs2[half] = __ldg(reinterpret_cast<const float4*>(p.col_scale + n));
+            if (p.bias) bs2[half] = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        }
     }
     uint32_t raw[32];
     float v[32];
@@ -216,9 +264,7 @@ __device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr,
         __syncwarp();
         const int64_t n = nb + half * 16 + c4;  // N % 8 == 0 and n % 4 == 0: the 4 columns are valid together
         if (n >= p.N) continue;
-        float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.col_scale) cs = __ldg(reinterpret_cast<const float4*>(p.col_scale + n));
-        if (p.bias) bs = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        const float4 cs = cs2[half], bs = bs2[half];
         float o[4][4];
         bool ok[4];
         int64_t off[4];
@@ -253,7 +299,7 @@ __device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr,
 #pragma unroll
                 for (int j = 0; j < 4; ++j) o[it][j] = act_apply(o[it][j], p.epilogue);
         }
-        if (p.residual) {
+        if (has_res) {
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 const float4 r = res[half][it];
@@ -429,11 +475,11 @@ __device__ __forceinline__ void gemm_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 8000000000ll) __trap();
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int EW>
+__global__ void __launch_bounds__((2 + EW) * 32, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, GemmParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, EW>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::kStages * C::kStageBytes);
@@ -455,7 +501,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             slb_mbar_init(&tfull[a], 1);
-            slb_mbar_init(&tempty[a], kEpiWarps);
+            slb_mbar_init(&tempty[a], EW);
         }
         slb_fence_mbar_init();
     }
@@ -465,10 +511,12 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     slb_tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_kb = (int)(p.K / BK);
+    const int bk = p.bk;  // 64, or 32 (narrow implicit convolution: half-filled stages, same offsets scaled by bk)
+    const int num_kb = (int)(p.K / bk);
     const int tiles_n = (int)((p.N + BN - 1) / BN);
     const int tiles_m = (int)((p.M + BM - 1) / BM);
     const int total = tiles_m * tiles_n;
+    const uint32_t a_plane = (uint32_t)(BM * bk * 2), w_plane = (uint32_t)(BN * bk * 2);  // bytes of one plane of a k-block
 
     if (warp == 0) {
         if (lane == 0) {
@@ -490,16 +538,16 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int kb = 0; kb < num_kb; ++kb) {
                     gemm_wait(&empty[stage], phase ^ 1u);
                     unsigned char* st = smem + (size_t)stage * C::kStageBytes;
-                    slb_mbar_arrive_expect_tx(&full[stage], (uint32_t)C::kStageBytes);
+                    slb_mbar_arrive_expect_tx(&full[stage], 2u * (a_plane + w_plane));
                     if (p.conv) {
                         const int tap = kb / p.conv_cc, c0 = (kb - tap * p.conv_cc) * BK;
                         const int ky = tap / p.conv_k, kx = tap - ky * p.conv_k;
                         slb_tma_load_im2col_4d(st, &tmA, c0, cw, ch, cn, (uint16_t)kx, (uint16_t)ky, &full[stage]);
-                        slb_tma_load_im2col_4d(st + BM * BK * 2, &tmA2, c0, cw, ch, cn, (uint16_t)kx, (uint16_t)ky, &full[stage]);
+                        slb_tma_load_im2col_4d(st + a_plane, &tmA2, c0, cw, ch, cn, (uint16_t)kx, (uint16_t)ky, &full[stage]);
                     } else {
                         slb_tma_load_3d(st, &tmA, kb * BK, m0, 0, &full[stage]);
                     }
-                    slb_tma_load_3d(st + C::kABytes, &tmW, kb * BK, n0, 0, &full[stage]);
+                    slb_tma_load_3d(st + C::kABytes, &tmW, kb * bk, n0, 0, &full[stage]);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -507,7 +555,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = slb_umma_idesc_f16(p.fmt, BM, BN);
-            const uint64_t desc0 = slb_umma_desc_sw128(slb_smem_u32(smem));  // stage 0, A hi plane
+            const uint64_t desc0 = bk == 32 ? slb_umma_desc_sw64(slb_smem_u32(smem)) : slb_umma_desc_sw128(slb_smem_u32(smem));  // stage 0, A hi plane
+            const int ksteps = bk / 16;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -528,13 +577,13 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                     for (int pr = 0; pr < 3; ++pr) {
                         if (pr < p.passes) {
-                            const uint64_t da = da0 + (pr == 2 ? (BM * BK * 2) >> 4 : 0);
-                            const uint64_t dw = dw0 + (pr == 1 ? (BN * BK * 2) >> 4 : 0);
+                            const uint64_t da = da0 + (pr == 2 ? a_plane >> 4 : 0);
+                            const uint64_t dw = dw0 + (pr == 1 ? w_plane >> 4 : 0);
                             // first write of an accumulator overwrites: main at (kb, pr, k) = 0, the cross columns at pr = 1
                             const int first = p.split_acc ? (pr == 2 ? 1 : kb) : (kb | pr);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
-                                slb_umma_f16(pr ? d_cross : d_tmem, da + 2 * k, dw + 2 * k, idesc, (first | k) != 0);
+                                if (k < ksteps) slb_umma_f16(pr ? d_cross : d_tmem, da + 2 * k, dw + 2 * k, idesc, (first | k) != 0);
                         }
                     }
                     slb_umma_commit(&empty[stage]);
@@ -560,7 +609,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int64_t m = (int64_t)m0 + quarter * 32 + lane;  // the TMEM lane (= output row) this thread drains
             const float rs = (p.row_scale && m < p.M) ? p.row_scale[m] : 1.0f;
 #pragma unroll 1
-            for (int c = chunk0; c < BN / 32; c += kEpiWarps / 4) {
+            for (int c = chunk0; c < BN / 32; c += EW / 4) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
                 if (p.tma_store)
                     drain_chunk_tma(p, &tmO, taddr, (int64_t)m0 + quarter * 32, lane, rs, (int64_t)n0 + c * 32, fmt, tile,
@@ -790,15 +839,15 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
     }
 }
 
-template <int BN>
+template <int BN, int EW>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
                 cudaStream_t st) {
-    using C = Cfg<BN>;
-    auto kern = gemm_split_kernel<BN>;
+    using C = Cfg<BN, EW>;
+    auto kern = gemm_split_kernel<BN, EW>;
     SLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
     const int64_t tiles = slb_ceil_div(p.M, BM) * slb_ceil_div(p.N, BN);
     const int grid = (int)std::min<int64_t>(tiles, slb_sm_count());
-    kern<<<grid, kThreads, C::kSmem, st>>>(tmA, tmA2, tmW, tmO, p);
+    kern<<<grid, C::kThreadsC, C::kSmem, st>>>(tmA, tmA2, tmW, tmO, p);
     SLB_LAUNCH_OK("gemm_split");
     return SLB_OK;
 }
@@ -920,6 +969,25 @@ int slb_encode_plane_map(CUtensorMap* out, const void* base, int64_t rows, int64
     return SLB_OK;
 }
 
+// W of a 32-channel convolution: planes [2][rows][cols] with cols = the padded row length in storage; box = {32 columns (one
+// filter tap), box_rows, 2 planes} under the 64-byte swizzle. Not cached (two such launches per tower forward).
+static int encode_plane_map_bk32(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int box_rows) {
+    slb_tmap_encode_fn enc = slb_get_tmap_encoder();
+    if (!enc) return SLB_ECUDA;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * (cuuint64_t)cols * 2};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        slb_set_error("cuTensorMapEncodeTiled (32-column W map) failed with %d (rows=%lld cols=%lld)", (int)r, (long long)rows, (long long)cols);
+        return SLB_ECUDA;
+    }
+    return SLB_OK;
+}
+
 // Output map for the TMA-store epilogue: planes == 0 -> fp32 (M, N), box 16 columns x 32 rows, 64B swizzle;
 // planes == 2 -> 16-bit planes (2, M, N), box 16 columns x 32 rows x 1 plane, 32B swizzle. Cached like the plane maps.
 int slb_make_store_map(CUtensorMap* out, const void* base, int64_t M, int64_t N, int planes) {
@@ -982,9 +1050,12 @@ int slb_make_im2col_map(CUtensorMap* out, const void* base, int64_t B, int64_t H
     int lower[2] = {-pad, -pad};
     int upper[2] = {pad - (ksize - 1), pad - (ksize - 1)};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, lower, upper, (cuuint32_t)BK,
-                    (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // C == 32 (narrow maps): a tap is one 64-byte row per pixel, staged under the 64-byte swizzle
+    const bool narrow = C == 32;
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
+                    (cuuint32_t)(narrow ? 32 : BK), (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    narrow ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         slb_set_error("cuTensorMapEncodeIm2col failed with %d (B=%lld H=%lld W=%lld C=%lld k=%d stride=%d pad=%d)", (int)r, (long long)B,
                       (long long)H, (long long)W, (long long)C, ksize, stride, pad);
@@ -1026,11 +1097,17 @@ static int gemm_split_impl(const uint16_t* a_planes, const uint16_t* w_planes, i
     SLB_REQUIRE(plane_fmt == SLB_PLANE_F16 || plane_fmt == SLB_PLANE_BF16, SLB_EINVAL, "slb_gemm_split: bad plane format");
     SLB_REQUIRE(passes == 1 || passes == 3 || passes == SLB_PASSES_SPLIT_ACC, SLB_EINVAL,
                 "slb_gemm_split: passes must be 1, 3 or SLB_PASSES_SPLIT_ACC");
-    SLB_REQUIRE(epilogue >= SLB_EPI_NONE && epilogue <= SLB_EPI_ADD_RELU, SLB_EINVAL, "slb_gemm_split: bad epilogue");
+    SLB_REQUIRE(epilogue >= SLB_EPI_NONE && epilogue <= SLB_EPI_ADD_RELU_PLANES, SLB_EINVAL, "slb_gemm_split: bad epilogue");
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.alpha = alpha;
     p.bias = bias; p.residual = residual; p.row_scale = row_scale; p.col_scale = col_scale;
+    if (epilogue == SLB_EPI_ADD_RELU_PLANES) {  // `residual` points at planes [2][M][N] (see slb200.h)
+        SLB_REQUIRE(residual, SLB_EINVAL, "slb_gemm_split: SLB_EPI_ADD_RELU_PLANES needs the shortcut planes");
+        p.residual_planes = reinterpret_cast<const uint16_t*>(residual);
+        p.residual = nullptr;
+        epilogue = SLB_EPI_ADD_RELU;
+    }
     p.out_f32 = out_f32; p.out_planes = out_planes;
     p.epilogue = epilogue; p.passes = passes; p.fmt = plane_fmt;
     p.raw_f32 = raw_f32;
@@ -1044,7 +1121,7 @@ static int conv_gemm_impl(const uint16_t* x_planes, int64_t B, int64_t H, int64_
     SLB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && N >= 0, SLB_EINVAL, "slb_conv_gemm: bad size");
     SLB_REQUIRE(ksize >= 1 && ksize <= 7 && (stride == 1 || stride == 2) && pad >= 0 && pad <= 7, SLB_EUNSUPPORTED,
                 "slb_conv_gemm: filter %d, stride %d, pad %d", ksize, stride, pad);
-    SLB_REQUIRE(C % 64 == 0, SLB_EUNSUPPORTED, "slb_conv_gemm: channels must be a multiple of 64 (got %lld)", (long long)C);
+    SLB_REQUIRE(C % 64 == 0 || C == 32, SLB_EUNSUPPORTED, "slb_conv_gemm: channels must be 32 or a multiple of 64 (got %lld)", (long long)C);
     const int64_t Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
     SLB_REQUIRE(Ho > 0 && Wo > 0, SLB_EINVAL, "slb_conv_gemm: empty output");
     const int64_t M = B * Ho * Wo;
@@ -1052,14 +1129,21 @@ static int conv_gemm_impl(const uint16_t* x_planes, int64_t B, int64_t H, int64_
     SLB_REQUIRE(x_planes && w_planes && (out_f32 || out_planes || raw_f32), SLB_EINVAL, "slb_conv_gemm: null pointer");
     SLB_REQUIRE(plane_fmt == SLB_PLANE_F16 || plane_fmt == SLB_PLANE_BF16, SLB_EINVAL, "slb_conv_gemm: bad plane format");
     SLB_REQUIRE(passes == 1 || passes == 3 || passes == SLB_PASSES_SPLIT_ACC, SLB_EINVAL, "slb_conv_gemm: bad passes");
-    SLB_REQUIRE(epilogue >= SLB_EPI_NONE && epilogue <= SLB_EPI_ADD_RELU, SLB_EINVAL, "slb_conv_gemm: bad epilogue");
+    SLB_REQUIRE(epilogue >= SLB_EPI_NONE && epilogue <= SLB_EPI_ADD_RELU_PLANES, SLB_EINVAL, "slb_conv_gemm: bad epilogue");
     GemmParams p{};
     p.M = M; p.N = N; p.K = (int64_t)ksize * ksize * C;
     p.alpha = alpha;
     p.bias = bias; p.residual = residual; p.col_scale = col_scale;
+    if (epilogue == SLB_EPI_ADD_RELU_PLANES) {
+        SLB_REQUIRE(residual, SLB_EINVAL, "slb_conv_gemm: SLB_EPI_ADD_RELU_PLANES needs the shortcut planes");
+        p.residual_planes = reinterpret_cast<const uint16_t*>(residual);
+        p.residual = nullptr;
+        epilogue = SLB_EPI_ADD_RELU;
+    }
     p.out_f32 = out_f32; p.out_planes = out_planes;
     p.epilogue = epilogue; p.passes = passes; p.fmt = plane_fmt;
-    p.conv = 1; p.conv_cc = (int)(C / 64); p.conv_k = ksize; p.conv_stride = stride; p.conv_pad = pad;
+    p.bk = C == 32 ? 32 : BK;
+    p.conv = 1; p.conv_cc = C == 32 ? 1 : (int)(C / 64); p.conv_k = ksize; p.conv_stride = stride; p.conv_pad = pad;
     p.conv_ho = (int)Ho; p.conv_wo = (int)Wo;
     p.conv_x = x_planes; p.conv_B = B; p.conv_H = H; p.conv_W = W; p.conv_C = C;
     p.raw_f32 = raw_f32;
@@ -1109,6 +1193,8 @@ int slb_gemm_rowmax_offdiag(const uint16_t* planes, int64_t n, int64_t n_pad, in
 
 static int run_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, GemmParams p, void* stream) {
     const int64_t M = p.M, N = p.N, K = p.K;
+    if (p.bk == 0) p.bk = BK;
+    const bool narrow = p.bk == 32;  // implicit convolution over 32-channel maps (conv_gemm_impl)
     int passes = p.passes;
     // The second accumulator exists to keep the one-sided truncation of long accumulations out of the result (the error
     // grows with the number of MMA steps per output). With K <= 256 an output sees at most 48 steps — less than a ViT-B
@@ -1122,13 +1208,13 @@ static int run_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, Ge
     float* out_f32 = p.out_f32;
     uint16_t* out_planes = p.out_planes;
     const float* residual = p.residual;
-    SLB_REQUIRE(K >= BK && K % BK == 0, SLB_EUNSUPPORTED, "slb_gemm_split: K must be a positive multiple of 64 (got %lld)",
+    SLB_REQUIRE(K >= p.bk && K % p.bk == 0, SLB_EUNSUPPORTED, "slb_gemm_split: K must be a positive multiple of 64 (got %lld)",
                 (long long)K);
     SLB_REQUIRE(N % 8 == 0, SLB_EUNSUPPORTED, "slb_gemm_split: N must be a multiple of 8 (got %lld)", (long long)N);
     SLB_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), SLB_EUNSUPPORTED, "slb_gemm_split: size too large");
     SLB_REQUIRE(((uintptr_t)a_planes % 16) == 0 && ((uintptr_t)w_planes % 16) == 0 &&
                     ((uintptr_t)out_f32 % 16) == 0 && ((uintptr_t)out_planes % 16) == 0 &&
-                    ((uintptr_t)residual % 16) == 0 && (p.conv || ((M * K * 2) % 16) == 0) && ((N * K * 2) % 16) == 0 &&
+                    ((uintptr_t)residual % 16) == 0 && ((uintptr_t)p.residual_planes % 16) == 0 && (p.conv || ((M * K * 2) % 16) == 0) && ((N * slb_conv_k(K, 1) * 2) % 16) == 0 &&
                     ((M * N * 2) % 16) == 0,
                 SLB_EINVAL, "slb_gemm_split: operands must be 16-byte aligned");
     // algorithmic bytes of the A operand: the activation itself for an implicit convolution (each pixel once), M x K otherwise
@@ -1177,7 +1263,10 @@ static int run_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, Ge
         tmA2 = tmA;
     }
     if (rc != SLB_OK) return rc;
-    rc = slb_make_plane_map(&tmW, w_planes, N, K, 2, kind == 2 ? 64 : (kind == 4 ? 96 : 128));  // W rows staged per CTA
+    if (narrow)  // W rows keep their padded length in storage (slb_conv_k); a k-block is one 32-column tap
+        rc = encode_plane_map_bk32(&tmW, w_planes, N, slb_conv_k(K, 1), 128);
+    else
+        rc = slb_make_plane_map(&tmW, w_planes, N, K, 2, kind == 2 ? 64 : (kind == 4 ? 96 : 128));  // W rows staged per CTA
     if (rc != SLB_OK) return rc;
     // TMA-store epilogue: exactly one output, nothing that needs a second operand per element (shortcut, raw hook output,
     // fused row maximum). Measured on one box (r2 A/B, towers): CTA-pair kernels 5.68 -> 5.50 ms (ViT-B/32), 23.87 -> 23.58 ms
@@ -1190,7 +1279,7 @@ static int run_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, Ge
     CUtensorMap tmO;
     memset(&tmO, 0, sizeof(tmO));
     p.tma_store = 0;
-    if (tma_store_on && !p.residual && !p.raw_f32 && !p.rowmax && p.epilogue != SLB_EPI_ADD_RELU && ((out_f32 != nullptr) != (out_planes != nullptr))) {
+    if (tma_store_on && !p.residual && !p.residual_planes && !p.raw_f32 && !p.rowmax && p.epilogue != SLB_EPI_ADD_RELU && ((out_f32 != nullptr) != (out_planes != nullptr))) {
         rc = slb_make_store_map(&tmO, out_f32 ? (const void*)out_f32 : (const void*)out_planes, M, N, out_f32 ? 0 : 2);
         if (rc != SLB_OK) return rc;
         p.tma_store = out_f32 ? 1 : 2;
@@ -1199,5 +1288,11 @@ static int run_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, Ge
     if (kind == 4) return launch_gemm_pair<192>(tmA, tmW, tmO, p, st);
     if (kind == 3) return launch_gemm_pair<256>(tmA, tmW, tmO, p, st);
     if (kind == 2) return launch_gemm_pair<128>(tmA, tmW, tmO, p, st);
-    return launch_gemm<128>(tmA, tmA2, tmW, tmO, p, st);
+    // Sixteen epilogue warps (SLB_GEMM_EPI_WARPS=16, short K, one accumulator) are an experiment kept for measurement only:
+    // on the RN50 tower they were SLOWER than eight (12.4 k vs 13.2 k img/s, same box, alternating runs) — the third stage
+    // they give up costs more than the extra latency hiding buys — so eight is the default everywhere.
+    static const int forced_ew = [] { const char* e = getenv("SLB_GEMM_EPI_WARPS"); return e ? atoi(e) : 0; }();
+    const bool wide = forced_ew == 16 && K <= 512;
+    if (wide && !split_acc) return launch_gemm<128, 16>(tmA, tmA2, tmW, tmO, p, st);
+    return launch_gemm<128, 8>(tmA, tmA2, tmW, tmO, p, st);
 }

@@ -31,6 +31,14 @@ int rn_passes() {
     return v;
 }
 
+bool rn_f32_stream() {
+    static const bool v = [] {
+        const char* e = getenv("SLB_RN_F32_STREAM");
+        return e && atoi(e) != 0;
+    }();
+    return v;
+}
+
 bool rn_explicit_im2col() {
     static const bool v = [] {
         const char* e = getenv("SLB_RN_IM2COL");
@@ -337,8 +345,9 @@ extern "C" int slb_rn_forward(const SlbRnWeights* w, const float* img, int64_t B
     uint16_t* t2 = reinterpret_cast<uint16_t*>(ws + L.t2);
     uint16_t* t3 = reinterpret_cast<uint16_t*>(ws + L.t3);
     uint16_t* xp = reinterpret_cast<uint16_t*>(ws + L.xp);
-    float* f = reinterpret_cast<float*>(ws + L.f);
+    uint16_t* sc = reinterpret_cast<uint16_t*>(ws + L.f);  // a projected shortcut as planes (same 4 bytes per element as fp32)
     uint16_t* col = reinterpret_cast<uint16_t*>(ws + L.col);
+    float* f = reinterpret_cast<float*>(ws + L.col);  // the last block's fp32 map: read by the pool before k | v land in `col`
     const int fmt = w->plane_fmt;
     const int kPasses = rn_passes();
     int rc;
@@ -362,10 +371,20 @@ extern "C" int slb_rn_forward(const SlbRnWeights* w, const float* img, int64_t B
     int64_t H = S / 2, M = B * H * H;
     SLB_TRY(slb_im2col_stem(img, B, S, fmt, col, stream));
     SLB_TRY(conv(cv[0], col, M, SLB_EPI_RELU, nullptr, nullptr, t1));
-    SLB_TRY(slb_im2col3x3(t1, B, H, H, wd / 2, col, stream));
-    SLB_TRY(conv(cv[1], col, M, SLB_EPI_RELU, nullptr, nullptr, t2));
-    SLB_TRY(slb_im2col3x3(t2, B, H, H, wd / 2, col, stream));
-    SLB_TRY(conv(cv[2], col, M, SLB_EPI_RELU, nullptr, nullptr, x_nxt));
+    // the two 3x3 convolutions over wd/2 channels: implicit GEMMs too (32 channels = one tap per k-block); at 112 x 112 their
+    // im2col matrices were 2 GB each per 128 images — 15 % of the RN50 tower's time went into writing and re-reading them
+    const int64_t hw_ = wd / 2;
+    if ((hw_ % 64 == 0 || hw_ == 32) && !rn_explicit_im2col()) {
+        SLB_TRY(slb_conv_gemm(t1, B, H, H, hw_, 3, 1, 1, cv[1].w, cv[1].cout, fmt, kAlpha, cv[1].shift, nullptr, cv[1].scale, SLB_EPI_RELU,
+                              kPasses, nullptr, t2, stream));
+        SLB_TRY(slb_conv_gemm(t2, B, H, H, hw_, 3, 1, 1, cv[2].w, cv[2].cout, fmt, kAlpha, cv[2].shift, nullptr, cv[2].scale, SLB_EPI_RELU,
+                              kPasses, nullptr, x_nxt, stream));
+    } else {
+        SLB_TRY(slb_im2col3x3(t1, B, H, H, hw_, col, stream));
+        SLB_TRY(conv(cv[1], col, M, SLB_EPI_RELU, nullptr, nullptr, t2));
+        SLB_TRY(slb_im2col3x3(t2, B, H, H, hw_, col, stream));
+        SLB_TRY(conv(cv[2], col, M, SLB_EPI_RELU, nullptr, nullptr, x_nxt));
+    }
     SLB_TRY(slb_avgpool2_planes(x_nxt, B, H, H, wd, fmt, x_cur, stream));
     H /= 2;
     M /= 4;
@@ -401,9 +420,28 @@ extern "C" int slb_rn_forward(const SlbRnWeights* w, const float* img, int64_t B
                 H /= 2;
                 M /= 4;
             }
-            if (ds) SLB_TRY(conv(cv[3], short_in, M, SLB_EPI_NONE, nullptr, f, nullptr));
-            // main + shortcut, ReLU: the shortcut is read from and the fp32 output written to the same buffer
-            SLB_TRY(conv(cv[2], main_in, M, SLB_EPI_ADD_RELU, f, f, x_nxt));
+            // The residual stream lives as split planes (22 bits per value, 2^-22 relative per block): the shortcut is the
+            // block's input planes or its projection written as planes, and the tail reads it through
+            // SLB_EPI_ADD_RELU_PLANES. Same bytes to read as an fp32 shortcut, but no block writes an fp32 copy of its
+            // output (a third of the tail convolution's traffic) — except the last one, whose fp32 map feeds the pool.
+            const bool last = li == 3 && bi == w->blocks[3] - 1;
+            if (rn_f32_stream()) {  // SLB_RN_F32_STREAM=1: the round-1 arrangement (fp32 shortcut buffer), kept for A/B runs
+                float* f0 = reinterpret_cast<float*>(sc);
+                if (ds) SLB_TRY(conv(cv[3], short_in, M, SLB_EPI_NONE, nullptr, f0, nullptr));
+                SLB_TRY(conv(cv[2], main_in, M, SLB_EPI_ADD_RELU, f0, f0, x_nxt));
+                if (last) SLB_CUDA_OK(cudaMemcpyAsync(f, f0, (size_t)M * 4 * pl * 4, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+                std::swap(x_cur, x_nxt);
+                cv += ds ? 4 : 3;
+                inpl = 4 * pl;
+                continue;
+            }
+            const uint16_t* shortcut = x_cur;
+            if (ds) {
+                SLB_TRY(conv(cv[3], short_in, M, SLB_EPI_NONE, nullptr, nullptr, sc));
+                shortcut = sc;
+            }
+            SLB_TRY(conv(cv[2], main_in, M, SLB_EPI_ADD_RELU_PLANES, reinterpret_cast<const float*>(shortcut), last ? f : nullptr,
+                         last ? nullptr : x_nxt));
             std::swap(x_cur, x_nxt);
             cv += ds ? 4 : 3;
             inpl = 4 * pl;

@@ -84,6 +84,18 @@ __device__ __forceinline__ uint64_t slb_umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// The same for rows of 32 16-bit elements (64 B) under the 64-byte swizzle: 8-row atoms of 512 B. Used by the implicit
+// convolution over 32-channel maps, whose k-block is one filter tap = 32 channels (CLIP ModifiedResNet stem).
+__device__ __forceinline__ uint64_t slb_umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;     // SBO: 8 rows * 64 B between row groups
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;              // SWIZZLE_64B
+    return d;
+}
+
 // kind::f16 instruction descriptor: D fp32, A/B both `fmt` (0 = fp16, 1 = bf16), both K-major, shape M x N x 16.
 __device__ __forceinline__ uint32_t slb_umma_idesc_f16(int fmt, int M, int N) {
     uint32_t d = 0;

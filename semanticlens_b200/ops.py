@@ -190,6 +190,21 @@ def split_planes(x: torch.Tensor, fmt: int = N.PLANE_F16, scale: float = 1.0) ->
     return planes
 
 
+def _plane_residual(epilogue: int, residual, plane_dtype, M: int, Nn: int):
+    """A shortcut handed over as split planes (2, M, N) in the GEMM's plane dtype selects SLB_EPI_ADD_RELU_PLANES (the only
+    epilogue with a plane shortcut: the tail of a residual block)."""
+    if residual is None or residual.dtype == torch.float32:
+        return epilogue, residual
+    assert epilogue in (N.EPI_ADD_RELU, N.EPI_ADD_RELU_PLANES), "a plane shortcut goes with the add + ReLU epilogue"
+    assert residual.dtype == plane_dtype and tuple(residual.shape) == (2, M, Nn) and residual.is_contiguous(), residual.shape
+    return N.EPI_ADD_RELU_PLANES, residual
+
+
+def planes_to_f32(planes: torch.Tensor) -> torch.Tensor:
+    """(2, M, N) activation planes -> the fp32 values they carry (hi + lo) / ACT_PLANE_SCALE."""
+    return (planes[0].float() + planes[1].float()) / N.ACT_PLANE_SCALE
+
+
 def gemm_split(
     a_planes: torch.Tensor,
     w_planes: torch.Tensor,
@@ -231,7 +246,9 @@ def gemm_split(
         out_planes = torch.empty((2, M, Nn), dtype=a_planes.dtype, device=dev)
     elif out_planes is False:
         out_planes = None
-    for t, shape in ((bias, (Nn,)), (residual, (M, Nn)), (row_scale, (M,)), (col_scale, (Nn,)), (out_f32, (M, Nn))):
+    epilogue, residual = _plane_residual(epilogue, residual, a_planes.dtype, M, Nn)
+    for t, shape in ((bias, (Nn,)), (residual if epilogue != N.EPI_ADD_RELU_PLANES else None, (M, Nn)), (row_scale, (M,)),
+                     (col_scale, (Nn,)), (out_f32, (M, Nn))):
         if t is not None:
             assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape, (t.shape, shape)
     if out_planes is not None:
@@ -440,7 +457,7 @@ def conv_gemm(x_planes: torch.Tensor, B: int, H: int, W: int, w_planes: torch.Te
     N.require_cuda(x_planes, "x_planes")
     assert x_planes.ndim == 3 and x_planes.shape[0] == 2 and x_planes.shape[1] == B * H * W and x_planes.is_contiguous()
     C = x_planes.shape[2]
-    assert w_planes.ndim == 3 and w_planes.shape[0] == 2 and w_planes.shape[2] == ksize * ksize * C and w_planes.is_contiguous()
+    assert w_planes.ndim == 3 and w_planes.shape[0] == 2 and w_planes.shape[2] == conv_k(C, ksize) and w_planes.is_contiguous()
     assert w_planes.dtype == x_planes.dtype
     Nn = w_planes.shape[1]
     fmt = N.PLANE_F16 if x_planes.dtype == torch.float16 else N.PLANE_BF16
@@ -454,7 +471,9 @@ def conv_gemm(x_planes: torch.Tensor, B: int, H: int, W: int, w_planes: torch.Te
         out_planes = torch.empty((2, M, Nn), dtype=x_planes.dtype, device=dev)
     elif out_planes is False:
         out_planes = None
-    for t, shape in ((bias, (Nn,)), (residual, (M, Nn)), (col_scale, (Nn,)), (out_f32, (M, Nn))):
+    epilogue, residual = _plane_residual(epilogue, residual, x_planes.dtype, M, Nn)
+    for t, shape in ((bias, (Nn,)), (residual if epilogue != N.EPI_ADD_RELU_PLANES else None, (M, Nn)), (col_scale, (Nn,)),
+                     (out_f32, (M, Nn))):
         if t is not None:
             assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape, (t.shape, shape)
     args = (x_planes.data_ptr(), B, H, W, C, ksize, stride, pad, w_planes.data_ptr(), Nn, fmt, float(alpha), N.ptr(bias), N.ptr(residual),

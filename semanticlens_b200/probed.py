@@ -183,6 +183,8 @@ class AcceleratedResNet:
             raw, _ = self._mm(c, x_planes, B, H, W, bias=c.bias, epilogue=N.EPI_NONE)
             _fire(c.module, _as_nchw(raw, B, Ho, Wo))
             shift = c.shift if c.bias is None else (c.shift - c.bias * c.scale)  # raw already holds the bias
+            if residual is not None and residual.dtype != torch.float32:
+                residual = ops.planes_to_f32(residual)  # (rare path: a hooked convolution with its own bias at a block tail)
             return ops.affine_act(raw, c.scale, shift, residual=residual, relu=relu, fmt=self.fmt, out_f32=keep32, out_planes=want_planes)
         if residual is not None and not relu:
             raise AssertionError("a shortcut add is always followed by the ReLU in a ResNet block")
@@ -217,9 +219,8 @@ class AcceleratedResNet:
             _fire(st.module, _as_nchw(raw, B, H, W))
         if last is None and not self._hooked(m.maxpool):
             return None
-        first_needs_identity = self.blocks[0][3] is None
         shift = st.shift if st.bias is None else (st.shift - st.bias * st.scale)
-        x32, xpl = ops.bn_relu_maxpool(raw, B, H, W, st.scale, shift, self.fmt, want_f32=first_needs_identity or self._hooked(m.maxpool))
+        x32, xpl = ops.bn_relu_maxpool(raw, B, H, W, st.scale, shift, self.fmt, want_f32=self._hooked(m.maxpool))
         del raw
         H, W = ops.conv_out(H, 3, 2, 1), ops.conv_out(W, 3, 2, 1)
         if self._hooked(m.maxpool):
@@ -230,20 +231,25 @@ class AcceleratedResNet:
         for i, (blk, kind, convs, ds, layer) in enumerate(self.blocks[: last + 1]):
             stride = convs[1].stride if kind == "bottleneck" else convs[0].stride
             Ho, Wo = ops.conv_out(H, 3, stride, 1), ops.conv_out(W, 3, stride, 1)
-            # shortcut: the block's input, or its 1x1 (strided) projection + BatchNorm, as fp32
-            idf = x32 if ds is None else self._conv(ds, xpl, B, H, W, relu=False, want_f32=True, want_planes=False)[0]
+            # The residual stream lives as split planes (22 bits): the shortcut is the block's input planes, or its 1x1
+            # (strided) projection + BatchNorm written as planes, and the tail reads it through SLB_EPI_ADD_RELU_PLANES —
+            # the same bytes as an fp32 shortcut, but a block whose output nobody hooks never writes an fp32 copy of it
+            # (a third of the tail convolution's HBM traffic, the largest single item of the forward).
+            idf = xpl if ds is None else self._conv(ds, xpl, B, H, W, relu=False, want_f32=False, want_planes=True)[1]
+            need32 = self._hooked(blk) or (layer is not None and self._hooked(layer)) or (logits and i == last)
             if kind == "bottleneck":
                 if convs[0].stride != 1 or convs[2].stride != 1:
                     raise NotImplementedError("accelerated forward: the stride of a Bottleneck must sit in conv2 (torchvision v1.5)")
                 _, t1 = self._conv(convs[0], xpl, B, H, W, relu=True)
                 _, t2 = self._conv(convs[1], t1, B, H, W, relu=True)
                 del t1
-                x32, xpl = self._conv(convs[2], t2, B, Ho, Wo, relu=True, residual=idf, out_f32=idf)
+                x32, xpl = self._conv(convs[2], t2, B, Ho, Wo, relu=True, residual=idf, want_f32=need32)
                 del t2
             else:
                 _, t1 = self._conv(convs[0], xpl, B, H, W, relu=True)
-                x32, xpl = self._conv(convs[1], t1, B, Ho, Wo, relu=True, residual=idf, out_f32=idf)
+                x32, xpl = self._conv(convs[1], t1, B, Ho, Wo, relu=True, residual=idf, want_f32=need32)
                 del t1
+            del idf
             H, W = Ho, Wo
             if self._hooked(blk):
                 _fire(blk, _as_nchw(x32, B, H, W))

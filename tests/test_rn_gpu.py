@@ -95,6 +95,29 @@ def test_gemm_relu_epilogues(ops):
     assert (out >= 0).all() and rel_max(held(planes), want) < 3e-6
 
 
+@pytest.mark.parametrize("M,Nn,K,passes", [(200, 72, 128, 3), (1000, 256, 64, 4), (260, 2048, 512, 4), (37, 8, 576, 4)])
+def test_shortcut_as_planes(ops, M, Nn, K, passes):
+    """SLB_EPI_ADD_RELU_PLANES: the shortcut handed over as split planes (the residual stream of the ResNet paths) gives exactly
+    what the fp32 shortcut holding the same values gives, with and without the fp32 copy of the output."""
+    from semanticlens_b200 import _native as N
+
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    a, w = torch.randn(M, K, device="cuda", generator=g), torch.randn(Nn, K, device="cuda", generator=g) * 0.1
+    bias, res = torch.randn(Nn, device="cuda", generator=g), torch.randn(M, Nn, device="cuda", generator=g)
+    cs = torch.rand(Nn, device="cuda", generator=g) + 0.5
+    ap, wp, rp_ = ops.split_planes(a, 0, ACT), ops.split_planes(w, 0, WSC), ops.split_planes(res, 0, ACT)
+    res_held = ops.planes_to_f32(rp_)
+    assert rel_max(res_held, res) < 1e-6 and torch.equal(res_held.double().cpu(), held(rp_).cpu())
+    kw = dict(bias=bias, col_scale=cs, alpha=1 / (ACT * WSC), passes=passes)
+    want32, wantp = ops.gemm_split(ap, wp, residual=res_held, epilogue=N.EPI_ADD_RELU, out_planes=True, **kw)
+    got32, gotp = ops.gemm_split(ap, wp, residual=rp_, epilogue=N.EPI_ADD_RELU, out_planes=True, **kw)
+    assert torch.equal(got32, want32) and torch.equal(gotp, wantp)
+    none32, onlyp = ops.gemm_split(ap, wp, residual=rp_, epilogue=N.EPI_ADD_RELU, out_f32=False, out_planes=True, **kw)
+    assert none32 is None and torch.equal(onlyp, wantp)
+    z = (a.double() @ w.double().T) * cs.double() + bias.double()
+    assert rel_max(got32, torch.relu(z + res.double())) < 3e-6
+
+
 @pytest.mark.parametrize("cin,cout,k,H", [(64, 256, 1, 14), (32, 32, 3, 16), (128, 128, 3, 7)])
 def test_conv_bn_relu_as_gemm(ops, cin, cout, k, H):
     """One convolution + eval BatchNorm + ReLU the way slb_rn_forward runs it, against F.conv2d in float64."""
