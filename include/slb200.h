@@ -375,6 +375,13 @@ int64_t slb_conv_k(int64_t cin, int64_t ksize);
  * img (B,3,S,S) fp32 NCHW -> planes [2, B*(S/2)^2, 64], column (ky*3 + kx)*3 + c, zero past 27. S must be even. */
 int slb_im2col_stem(const float* img, int64_t B, int64_t S, int plane_fmt, uint16_t* out_planes, void* stream);
 
+/* The stem's first convolution computed directly (27 products per output do not pay for an im2col matrix and a tensor-core
+ * pass): img (B,3,S,S) fp32 NCHW, w_planes [2, cout, 64] (columns (ky*3 + kx)*3 + c, at SLB_WEIGHT_PLANE_SCALE), 3x3 / stride 2 /
+ * pad 1, then max(z * scale[n] + shift[n], 0) (eval BatchNorm + ReLU) -> out_planes [2, B*(S/2)^2, cout] at
+ * SLB_ACT_PLANE_SCALE. fp32 accumulation in (ky, kx, c) order. cout = 32 or 64, S even. (open_clip ModifiedResNet.conv1/bn1/act1) */
+int slb_stem_conv3x3s2(const float* img, int64_t B, int64_t S, const uint16_t* w_planes, int64_t cout, int plane_fmt,
+                       const float* scale, const float* shift, uint16_t* out_planes, void* stream);
+
 /* im2col of a 3x3, stride 1, pad 1 convolution over channels-last planes: in [2, B*H*W, C] ->
  * out [2, B*H*W, slb_conv_k(C, 3)], column (ky*3 + kx)*C + c (weights are laid out (cout, ky, kx, cin) to match),
  * zero outside the image and past 9C. C must be a multiple of 8. Plane bits are moved untouched. */

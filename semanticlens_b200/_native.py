@@ -102,6 +102,7 @@ _PROTOS = {
     "slb_resize_bicubic_u8": (c_int, [c_void_p] + [c_int64] * 8 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     "slb_conv_k": (c_int64, [c_int64, c_int64]),
     "slb_im2col_stem": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "slb_stem_conv3x3s2": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "slb_im2col3x3": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "slb_avgpool2_planes": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "slb_conv_gemm": (c_int, [c_void_p] + [c_int64] * 4 + [c_int] * 3 + [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p,

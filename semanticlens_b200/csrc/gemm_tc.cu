@@ -345,6 +345,139 @@ __device__ __forceinline__ void drain_chunk(const GemmParams& p, uint32_t taddr,
     }
 }
 
+// The same epilogue for a 32-row x 16-column half chunk, for the sixteen-warp kernel (short-K GEMMs: one to eight k-blocks
+// against a 64 KB accumulator drain that is a chain of TMEM / shared-memory / global latencies, where twice the warps hide
+// twice the chain). Half the columns per call keeps a thread under the 113 registers that 576 threads leave (the 32-column
+// form needs 167: as a sixteen-warp kernel it spilled 160 bytes and lost 6 %). One accumulator, no fused row maximum, no
+// TMA store: the host selects this kernel only for such launches.
+__device__ __forceinline__ void drain_half(const GemmParams& p, uint32_t taddr, int64_t m_warp, int lane, float rs, int64_t nb,
+                                           int fmt, float* tile) {
+    const int c4 = (lane & 3) * 4;
+    const int r8 = lane >> 2;
+    const int64_t n = nb + c4;  // N % 8 == 0 and n % 4 == 0: the 4 columns are valid together
+    const bool col_ok = n < p.N;
+    float4 res[4];
+    const bool has_res = p.residual != nullptr || p.residual_planes != nullptr;
+    if (p.residual) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int64_t m = m_warp + it * 8 + r8;
+            res[it] = (m < p.M && col_ok) ? *reinterpret_cast<const float4*>(p.residual + m * p.N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else if (p.residual_planes) {
+        uint2 rh[4], rl[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int64_t m = m_warp + it * 8 + r8;
+            const bool ok = m < p.M && col_ok;
+            rh[it] = ok ? *reinterpret_cast<const uint2*>(p.residual_planes + m * p.N + n) : make_uint2(0u, 0u);
+            rl[it] = ok ? *reinterpret_cast<const uint2*>(p.residual_planes + p.M * p.N + m * p.N + n) : make_uint2(0u, 0u);
+        }
+        constexpr float kInv = 1.0f / SLB_ACT_PLANE_SCALE;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const uint2 h = rh[it], l = rl[it];
+            res[it] = make_float4(
+                (slb_from_plane((uint16_t)(h.x & 0xFFFFu), p.fmt) + slb_from_plane((uint16_t)(l.x & 0xFFFFu), p.fmt)) * kInv,
+                (slb_from_plane((uint16_t)(h.x >> 16), p.fmt) + slb_from_plane((uint16_t)(l.x >> 16), p.fmt)) * kInv,
+                (slb_from_plane((uint16_t)(h.y & 0xFFFFu), p.fmt) + slb_from_plane((uint16_t)(l.y & 0xFFFFu), p.fmt)) * kInv,
+                (slb_from_plane((uint16_t)(h.y >> 16), p.fmt) + slb_from_plane((uint16_t)(l.y >> 16), p.fmt)) * kInv);
+        }
+    }
+    float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col_ok) {
+        if (p.col_scale) cs = __ldg(reinterpret_cast<const float4*>(p.col_scale + n));
+        if (p.bias) bs = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    }
+    uint32_t raw[16];
+    slb_tmem_ld_32x16(taddr, raw);
+    slb_tmem_ld_wait();
+    if (nb >= p.N) return;  // warp-uniform
+    __syncwarp();  // the previous half has been read
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        // alpha, then the row scale: the same two roundings as the 32-column form
+        float x0 = __uint_as_float(raw[4 * q]) * p.alpha, x1 = __uint_as_float(raw[4 * q + 1]) * p.alpha;
+        float x2 = __uint_as_float(raw[4 * q + 2]) * p.alpha, x3 = __uint_as_float(raw[4 * q + 3]) * p.alpha;
+        if (p.row_scale) { x0 *= rs; x1 *= rs; x2 *= rs; x3 *= rs; }
+        *reinterpret_cast<float4*>(tile + lane * kTileStride + 4 * q) = make_float4(x0, x1, x2, x3);
+    }
+    __syncwarp();
+    if (!col_ok) return;
+    float o[4][4];
+    bool ok[4];
+    int64_t off[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + r8;
+        const float4 x = *reinterpret_cast<const float4*>(tile + rr * kTileStride + c4);
+        o[it][0] = x.x; o[it][1] = x.y; o[it][2] = x.z; o[it][3] = x.w;
+        ok[it] = m_warp + rr < p.M;
+        off[it] = (m_warp + rr) * p.N + n;
+    }
+    if (p.raw_f32) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+            if (ok[it]) *reinterpret_cast<float4*>(p.raw_f32 + off[it]) = make_float4(o[it][0], o[it][1], o[it][2], o[it][3]);
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        o[it][0] = fmaf(o[it][0], cs.x, bs.x);
+        o[it][1] = fmaf(o[it][1], cs.y, bs.y);
+        o[it][2] = fmaf(o[it][2], cs.z, bs.z);
+        o[it][3] = fmaf(o[it][3], cs.w, bs.w);
+    }
+    if (p.epilogue != SLB_EPI_NONE && p.epilogue != SLB_EPI_ADD_RELU) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[it][j] = act_apply(o[it][j], p.epilogue);
+    }
+    if (has_res) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const float4 r = res[it];
+            o[it][0] += r.x; o[it][1] += r.y; o[it][2] += r.z; o[it][3] += r.w;
+        }
+    }
+    if (p.epilogue == SLB_EPI_ADD_RELU) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[it][j] = fmaxf(o[it][j], 0.0f);
+    }
+    if (p.out_f32) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+            if (ok[it]) *reinterpret_cast<float4*>(p.out_f32 + off[it]) = make_float4(o[it][0], o[it][1], o[it][2], o[it][3]);
+    }
+    if (p.out_planes) {
+        uint2 hp[4], lp[4];
+        if (fmt == 0) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                slb_split_pair_act_f16(o[it][0], o[it][1], hp[it].x, lp[it].x);
+                slb_split_pair_act_f16(o[it][2], o[it][3], hp[it].y, lp[it].y);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                uint16_t h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) slb_split2_act(o[it][j], fmt, h[j], l[j]);
+                hp[it] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+                lp[it] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+            if (ok[it]) {
+                *reinterpret_cast<uint2*>(p.out_planes + off[it]) = hp[it];
+                *reinterpret_cast<uint2*>(p.out_planes + p.M * p.N + off[it]) = lp[it];
+            }
+    }
+}
+
 // ---- TMA-store epilogue ---------------------------------------------------------------------------------------
 // For outputs without a shortcut (in_proj, fc, the convolutions that are not a block tail, the cosine GEMM) the thread that
 // drained row r from TMEM keeps all 32 columns of the chunk: column scale / bias arrive as broadcast loads, the activation
@@ -611,7 +744,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll 1
             for (int c = chunk0; c < BN / 32; c += EW / 4) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
-                if (p.tma_store)
+                if constexpr (EW == 16) {  // one 32-column chunk per warp, drained as two 16-column halves (register budget)
+                    drain_half(p, taddr, (int64_t)m0 + quarter * 32, lane, rs, (int64_t)n0 + c * 32, fmt, tile);
+                    drain_half(p, taddr + 16, (int64_t)m0 + quarter * 32, lane, rs, (int64_t)n0 + c * 32 + 16, fmt, tile);
+                } else if (p.tma_store)
                     drain_chunk_tma(p, &tmO, taddr, (int64_t)m0 + quarter * 32, lane, rs, (int64_t)n0 + c * 32, fmt, tile,
                                     p.split_acc ? BN : 0, n_stores);
                 else
@@ -1288,11 +1424,10 @@ static int run_gemm_split(const uint16_t* a_planes, const uint16_t* w_planes, Ge
     if (kind == 4) return launch_gemm_pair<192>(tmA, tmW, tmO, p, st);
     if (kind == 3) return launch_gemm_pair<256>(tmA, tmW, tmO, p, st);
     if (kind == 2) return launch_gemm_pair<128>(tmA, tmW, tmO, p, st);
-    // Sixteen epilogue warps (SLB_GEMM_EPI_WARPS=16, short K, one accumulator) are an experiment kept for measurement only:
-    // on the RN50 tower they were SLOWER than eight (12.4 k vs 13.2 k img/s, same box, alternating runs) — the third stage
-    // they give up costs more than the extra latency hiding buys — so eight is the default everywhere.
+    // Sixteen epilogue warps for the pure-epilogue shapes (K <= 512, one accumulator): each warp drains its 32-column chunk
+    // as two 16-column halves (drain_half). SLB_GEMM_EPI_WARPS=8 forces the eight-warp kernel.
     static const int forced_ew = [] { const char* e = getenv("SLB_GEMM_EPI_WARPS"); return e ? atoi(e) : 0; }();
-    const bool wide = forced_ew == 16 && K <= 512;
-    if (wide && !split_acc) return launch_gemm<128, 16>(tmA, tmA2, tmW, tmO, p, st);
+    const bool wide = forced_ew != 8 && K <= 512 && !split_acc && !p.tma_store && !p.rowmax;
+    if (wide) return launch_gemm<128, 16>(tmA, tmA2, tmW, tmO, p, st);
     return launch_gemm<128, 8>(tmA, tmA2, tmW, tmO, p, st);
 }

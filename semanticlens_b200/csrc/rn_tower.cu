@@ -84,6 +84,98 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restric
     }
 }
 
+// ---- the stem's first convolution computed directly (fp32 FMAs): 3 -> 8 G channels, 3x3, stride 2, pad 1 ---------------------
+// 27 products per output are not worth a tensor-core pass: as a GEMM this layer cost an im2col kernel (0.29 ms per 128
+// images: 411 MB of zero-padded K = 64 rows) plus a GEMM that is pure epilogue (0.33 ms), against ~0.1 ms of HBM time for
+// reading the images and writing the planes once. Thread = (output pixel, 8 adjacent output channels); the G threads of a
+// pixel share its 27 inputs (same addresses: one transaction), a warp stores 32/G pixels x 16 G bytes = 512 contiguous bytes
+// per plane. Weights are the 22-bit values the planes hold (hi + lo, descaled), accumulation is fp32 in tap order (ky, kx, c):
+// batch-invariant and at least as accurate as the split GEMM. BatchNorm + ReLU + plane split as in the GEMM epilogue.
+template <int G>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ img, int64_t n_work, int S, int fmt,
+                                                        const uint16_t* __restrict__ w_hi, const uint16_t* __restrict__ w_lo,
+                                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    constexpr int CO = 8 * G;
+    __shared__ float4 wsm[27][CO / 4];
+    __shared__ float sc[CO], sh[CO];
+    for (int t = threadIdx.x; t < 27 * CO; t += 256) {
+        const int k = t / CO, n = t - k * CO;
+        reinterpret_cast<float*>(wsm)[t] =
+            (slb_from_plane(w_hi[n * 64 + k], fmt) + slb_from_plane(w_lo[n * 64 + k], fmt)) * (1.0f / SLB_WEIGHT_PLANE_SCALE);
+    }
+    if (threadIdx.x < CO) {
+        sc[threadIdx.x] = scale[threadIdx.x];
+        sh[threadIdx.x] = shift[threadIdx.x];
+    }
+    __syncthreads();
+    // thread = (4 horizontally adjacent output pixels, 8 adjacent output channels): a weight fetched from shared memory feeds
+    // four FMAs (one pixel per thread made the kernel shared-memory bound: 54 16-byte reads per 216 FMAs), and the 9 input
+    // columns of a row serve all four pixels
+    const int Ho = S >> 1, Q = (Ho + 3) >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_work; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % G);
+        const int64_t q = i / G;
+        const int xq = (int)(q % Q);
+        const int y = (int)((q / Q) % Ho);
+        const int64_t b = q / ((int64_t)Q * Ho);
+        const int x0 = xq * 4;
+        const float* base = img + b * 3 * (int64_t)S * S;
+        float acc[4][8];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = 2 * y + ky - 1;
+            const bool row_in = yy >= 0 && yy < S;
+            float v[3][9];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* row = base + ((int64_t)c * S + (row_in ? yy : 0)) * S;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int xx = 2 * x0 + t - 1;
+                    v[c][t] = (row_in && xx >= 0 && xx < S) ? __ldg(row + xx) : 0.f;
+                }
+            }
+            // same accumulation order per output as the one-pixel form: (ky, kx, c)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int k = (ky * 3 + kx) * 3 + c;
+                    const float4 w0 = wsm[k][g * 2], w1 = wsm[k][g * 2 + 1];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float a = v[c][2 * p + kx];
+                        acc[p][0] = fmaf(a, w0.x, acc[p][0]); acc[p][1] = fmaf(a, w0.y, acc[p][1]);
+                        acc[p][2] = fmaf(a, w0.z, acc[p][2]); acc[p][3] = fmaf(a, w0.w, acc[p][3]);
+                        acc[p][4] = fmaf(a, w1.x, acc[p][4]); acc[p][5] = fmaf(a, w1.y, acc[p][5]);
+                        acc[p][6] = fmaf(a, w1.z, acc[p][6]); acc[p][7] = fmaf(a, w1.w, acc[p][7]);
+                    }
+                }
+        }
+        const int64_t m0 = (b * Ho + y) * (int64_t)Ho + x0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            if (x0 + p >= Ho) break;
+            uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float z = fmaxf(fmaf(acc[p][j], sc[g * 8 + j], sh[g * 8 + j]), 0.0f);
+                uint16_t hh, ll;
+                slb_split2_act(z, fmt, hh, ll);
+                h[j >> 1] |= (uint32_t)hh << ((j & 1) * 16);
+                l[j >> 1] |= (uint32_t)ll << ((j & 1) * 16);
+            }
+            *reinterpret_cast<uint4*>(hi + (m0 + p) * CO + g * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(lo + (m0 + p) * CO + g * 8) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+    }
+}
+
 // ---- 3x3 / stride 1 / pad 1 im2col over channels-last planes: pure 16-byte moves ------------------------------------
 // grid.y = plane. One warp owns an output pixel (row of the im2col matrix) at a time: the pixel is decoded once, the
 // lanes sweep the row's 16-byte chunks (tap-major, channels contiguous), so stores are fully coalesced and loads are
@@ -260,6 +352,31 @@ extern "C" int slb_im2col_stem(const float* img, int64_t B, int64_t S, int plane
     return SLB_OK;
 }
 
+extern "C" int slb_stem_conv3x3s2(const float* img, int64_t B, int64_t S, const uint16_t* w_planes, int64_t cout, int plane_fmt,
+                                  const float* scale, const float* shift, uint16_t* out_planes, void* stream) {
+    SLB_REQUIRE(B >= 0 && S > 0, SLB_EINVAL, "slb_stem_conv3x3s2: bad size");
+    if (B == 0) return SLB_OK;
+    SLB_REQUIRE(img && w_planes && scale && shift && out_planes, SLB_EINVAL, "slb_stem_conv3x3s2: null pointer");
+    SLB_REQUIRE(S % 2 == 0, SLB_EUNSUPPORTED, "slb_stem_conv3x3s2: the image size must be even");
+    SLB_REQUIRE(cout == 32 || cout == 64, SLB_EUNSUPPORTED, "slb_stem_conv3x3s2: 32 or 64 output channels (got %lld)", (long long)cout);
+    SLB_REQUIRE(plane_fmt == SLB_PLANE_F16 || plane_fmt == SLB_PLANE_BF16, SLB_EINVAL, "slb_stem_conv3x3s2: bad plane format");
+    SLB_REQUIRE(((uintptr_t)out_planes % 16) == 0, SLB_EINVAL, "slb_stem_conv3x3s2: misaligned output");
+    const int64_t M = B * (S / 2) * (S / 2);
+    SlbProfScope prof("K4 stem conv (direct)", stream, 2.0 * 27.0 * (double)cout * (double)M,
+                      12.0 * (double)B * (double)S * (double)S + 4.0 * (double)cout * (double)M);
+    const int64_t n_work = B * (S / 2) * ((S / 2 + 3) / 4) * (cout / 8);  // (pixel quad, 8-channel group) items
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(slb_ceil_div(n_work, 256), (int64_t)slb_sm_count() * 32));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint16_t* w_lo = w_planes + cout * 64;
+    uint16_t* lo = out_planes + M * cout;
+    if (cout == 32)
+        stem_conv_kernel<4><<<grid, 256, 0, st>>>(img, n_work, (int)S, plane_fmt, w_planes, w_lo, scale, shift, out_planes, lo);
+    else
+        stem_conv_kernel<8><<<grid, 256, 0, st>>>(img, n_work, (int)S, plane_fmt, w_planes, w_lo, scale, shift, out_planes, lo);
+    SLB_LAUNCH_OK("stem_conv");
+    return SLB_OK;
+}
+
 extern "C" int slb_im2col3x3(const uint16_t* in_planes, int64_t B, int64_t H, int64_t W, int64_t C, uint16_t* out_planes,
                              void* stream) {
     SLB_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0, SLB_EINVAL, "slb_im2col3x3: bad size");
@@ -369,8 +486,12 @@ extern "C" int slb_rn_forward(const SlbRnWeights* w, const float* img, int64_t B
 
     // ---- stem ----
     int64_t H = S / 2, M = B * H * H;
-    SLB_TRY(slb_im2col_stem(img, B, S, fmt, col, stream));
-    SLB_TRY(conv(cv[0], col, M, SLB_EPI_RELU, nullptr, nullptr, t1));
+    if ((cv[0].cout == 32 || cv[0].cout == 64) && !rn_explicit_im2col()) {
+        SLB_TRY(slb_stem_conv3x3s2(img, B, S, cv[0].w, cv[0].cout, fmt, cv[0].scale, cv[0].shift, t1, stream));
+    } else {
+        SLB_TRY(slb_im2col_stem(img, B, S, fmt, col, stream));
+        SLB_TRY(conv(cv[0], col, M, SLB_EPI_RELU, nullptr, nullptr, t1));
+    }
     // the two 3x3 convolutions over wd/2 channels: implicit GEMMs too (32 channels = one tap per k-block); at 112 x 112 their
     // im2col matrices were 2 GB each per 128 images — 15 % of the RN50 tower's time went into writing and re-reading them
     const int64_t hw_ = wd / 2;

@@ -20,24 +20,35 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // K3: u8 planar image -> normalised fp32   out = (u8/255 - mean[c]) / std[c]   (torch's op order)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) u8_norm_kernel(const uint8_t* __restrict__ img, int64_t n16, int64_t plane16, int Cc,
-                                                      float3 mean, float3 stdv, float* __restrict__ out) {
-    // one thread = 16 pixels of one channel plane (planes are multiples of 16 pixels)
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)((i / plane16) % Cc);
-        const float m = c == 0 ? mean.x : (c == 1 ? mean.y : mean.z);
-        const float s = c == 0 ? stdv.x : (c == 1 ? stdv.y : stdv.z);
-        const uint4 raw = reinterpret_cast<const uint4*>(img)[i];
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-        float4* o = reinterpret_cast<float4*>(out) + i * 4;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float4 v;
-            v.x = __fdiv_rn(__fdiv_rn((float)(w[q] & 0xFF), 255.0f) - m, s);
-            v.y = __fdiv_rn(__fdiv_rn((float)((w[q] >> 8) & 0xFF), 255.0f) - m, s);
-            v.z = __fdiv_rn(__fdiv_rn((float)((w[q] >> 16) & 0xFF), 255.0f) - m, s);
-            v.w = __fdiv_rn(__fdiv_rn((float)(w[q] >> 24), 255.0f) - m, s);
-            o[q] = v;
+// Only 256 x Cc different results exist, so the host computes them (the same two IEEE divisions torch performs) and the
+// kernel is a table look-up: the two divisions per pixel were half of the old kernel's time (58 us per 256 images = 0.52 of
+// the HBM peak). The table is replicated 16 times in shared memory — entry (c, v) of lane l sits in bank 16 (v & 1) + (l & 15) —
+// so a warp's 32 data-dependent look-ups conflict at most two-way (one shared copy: ~3.5-way on random bytes, 47 us; 32
+// copies leave room for only two CTAs per SM, 53 us). Persistent CTAs (four per SM) fill their Cc x 16 KB copy once; thread = 4
+// pixels per step: a warp reads 128 contiguous bytes and writes 512.
+struct U8Lut {
+    float v[3 * 256];
+};
+constexpr int kU8Threads = 512;
+
+__global__ void __launch_bounds__(kU8Threads) u8_norm_kernel(const uint8_t* __restrict__ img, int64_t planes, int words, int slices, int Cc,
+                                                             const __grid_constant__ U8Lut lut_in, float* __restrict__ out) {
+    extern __shared__ float lut[];  // [Cc][256][16]
+    for (int t = threadIdx.x; t < Cc * 256 * 16; t += kU8Threads) lut[t] = lut_in.v[t >> 4];
+    __syncthreads();
+    const int lane = threadIdx.x & 15;
+    const int per = (words + slices - 1) / slices;  // 4-pixel words of a plane handled per job
+    for (int64_t job = blockIdx.x; job < planes * slices; job += gridDim.x) {
+        const int64_t plane = job / slices;
+        const int sl = (int)(job - plane * slices);
+        const float* tab = lut + (int)(plane % Cc) * (256 * 16) + lane;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(img) + plane * words;
+        float4* dst = reinterpret_cast<float4*>(out) + plane * words;
+        const int end = min(words, (sl + 1) * per);
+#pragma unroll 4
+        for (int i = sl * per + threadIdx.x; i < end; i += kU8Threads) {
+            const uint32_t w = __ldg(src + i);
+            dst[i] = make_float4(tab[(w & 0xFF) << 4], tab[((w >> 8) & 0xFF) << 4], tab[((w >> 16) & 0xFF) << 4], tab[(w >> 24) << 4]);
         }
     }
 }
@@ -350,11 +361,27 @@ extern "C" int slb_u8_to_f32_norm(const uint8_t* img, int64_t B, int64_t Cc, int
     SLB_REQUIRE(img && out && mean3 && std3, SLB_EINVAL, "slb_u8_to_f32_norm: null pointer (mean3/std3 are HOST arrays)");
     SLB_REQUIRE(n_pix % 16 == 0 && ((uintptr_t)img % 16) == 0 && ((uintptr_t)out % 16) == 0, SLB_EUNSUPPORTED,
                 "slb_u8_to_f32_norm: planes must be multiples of 16 pixels and 16-byte aligned");
-    const int64_t n16 = B * Cc * n_pix / 16;
+    SLB_REQUIRE(n_pix / 4 < (1ll << 31), SLB_EUNSUPPORTED, "slb_u8_to_f32_norm: plane too large");
     SlbProfScope prof("K3 u8_to_f32_norm", stream, 0.0, 5.0 * (double)B * (double)Cc * (double)n_pix);
-    float3 m = make_float3(mean3[0], Cc > 1 ? mean3[1] : 0.f, Cc > 2 ? mean3[2] : 0.f);
-    float3 s = make_float3(std3[0], Cc > 1 ? std3[1] : 1.f, Cc > 2 ? std3[2] : 1.f);
-    u8_norm_kernel<<<grid_for(n16, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, n16, n_pix / 16, (int)Cc, m, s, out);
+    U8Lut lut;
+    for (int c = 0; c < (int)Cc; ++c) {
+        // volatile: keeps the compiler from folding the two divisions into anything but two IEEE divisions
+        volatile float m = mean3[c], sd = std3[c];
+        for (int v = 0; v < 256; ++v) {
+            volatile float t = (float)v / 255.0f;
+            volatile float u = t - m;
+            lut.v[c * 256 + v] = u / sd;
+        }
+    }
+    for (int i = (int)Cc * 256; i < 3 * 256; ++i) lut.v[i] = 0.f;
+    const int words = (int)(n_pix / 4);
+    // jobs of ~2048 words (4 per thread) over four persistent CTAs per SM
+    const int slices = (int)std::max<int64_t>(1, slb_ceil_div(words, 2048));
+    const int64_t jobs = B * Cc * slices;
+    const int grid = (int)std::min<int64_t>(jobs, (int64_t)slb_sm_count() * 4);
+    const size_t smem = (size_t)Cc * 256 * 16 * sizeof(float);
+    SLB_CUDA_OK(cudaFuncSetAttribute(u8_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 256 * 16 * (int)sizeof(float)));
+    u8_norm_kernel<<<grid, kU8Threads, smem, static_cast<cudaStream_t>(stream)>>>(img, B * Cc, words, slices, (int)Cc, lut, out);
     SLB_LAUNCH_OK("u8_norm");
     return SLB_OK;
 }

@@ -400,6 +400,25 @@ def im2col_stem(img: torch.Tensor, fmt: int = N.PLANE_F16) -> torch.Tensor:
     return out
 
 
+def stem_conv3x3s2(img: torch.Tensor, w_planes: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
+    """(B,3,S,S) fp32 -> planes (2, B*(S/2)^2, cout) of relu(conv3x3 / stride 2 / pad 1 * scale + shift), computed directly
+    (fp32 FMAs) from the weight planes (2, cout, 64)."""
+    lib = N.load(require_device=True)
+    N.require_cuda(img, "img")
+    img = img.float().contiguous()
+    B, _, S, _ = img.shape
+    assert w_planes.ndim == 3 and w_planes.shape[0] == 2 and w_planes.shape[2] == 64 and w_planes.is_contiguous()
+    cout = w_planes.shape[1]
+    fmt = N.PLANE_F16 if w_planes.dtype == torch.float16 else N.PLANE_BF16
+    for t in (scale, shift):
+        assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (cout,)
+    out = torch.empty((2, B * (S // 2) ** 2, cout), dtype=w_planes.dtype, device=img.device)
+    with _dev_guard(img):
+        N.check(lib.slb_stem_conv3x3s2(img.data_ptr(), B, S, w_planes.data_ptr(), cout, fmt, scale.data_ptr(), shift.data_ptr(),
+                                       out.data_ptr(), N.stream_ptr(img.device)), "slb_stem_conv3x3s2")
+    return out
+
+
 def im2col3x3(planes: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
     """channels-last planes (2, B*H*W, C) -> (2, B*H*W, conv_k(C, 3)) of a 3x3 / stride 1 / pad 1 convolution."""
     lib = N.load(require_device=True)

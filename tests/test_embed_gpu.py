@@ -32,6 +32,19 @@ def test_k3_u8_norm_bitexact_vs_totensor_normalize(ops):
     assert torch.equal(got, vp.preprocess_u8(cfg, u8))
 
 
+@pytest.mark.parametrize("B,C,H,W", [(1, 1, 4, 4), (2, 3, 16, 16), (5, 2, 48, 36), (3, 3, 256, 256), (2, 3, 384, 384), (7, 3, 20, 12)])
+def test_k3_u8_norm_shapes_and_every_byte_value(ops, B, C, H, W):
+    """The table look-up kernel on planes of several sizes (one or several slices per plane) and channel counts, with every
+    byte value present, against torch's two divisions, bit for bit."""
+    g = torch.Generator().manual_seed(H + C)
+    u8 = torch.randint(0, 256, (B, C, H, W), dtype=torch.uint8, generator=g)
+    u8.view(-1)[: min(256, u8.numel())] = torch.arange(min(256, u8.numel()), dtype=torch.uint8)
+    mean, std = (0.48145466, 0.4578275, 0.40821073)[:C], (0.26862954, 0.26130258, 0.27577711)[:C]
+    got = ops.u8_to_f32_norm(u8.cuda(), mean, std).cpu()
+    want = (u8.float().div(255) - torch.tensor(mean).view(1, C, 1, 1)) / torch.tensor(std).view(1, C, 1, 1)
+    assert torch.equal(got, want)
+
+
 @pytest.mark.parametrize("B,S,P", [(2, 64, 32), (3, 48, 16), (2, 28, 14), (1, 32, 8), (2, 12, 4), (1, 224, 32)])
 def test_patchify_bitexact_vs_unfold(ops, B, S, P):
     """The patch-embedding im2col (8 pixels per thread when P % 8 == 0, 2 otherwise) against F.unfold, bit for bit."""

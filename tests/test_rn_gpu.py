@@ -41,6 +41,32 @@ def test_im2col_stem_bitexact(ops, B, S):
     assert torch.equal(got.cpu(), ops.split_planes(want.cuda(), 0, ACT).cpu())
 
 
+@pytest.mark.parametrize("B,S,cout", [(2, 32, 32), (1, 64, 64), (3, 18, 32), (2, 224, 32)])
+def test_stem_conv_direct(ops, B, S, cout):
+    """slb_stem_conv3x3s2 (the stem's first convolution + BatchNorm + ReLU as fp32 FMAs) against F.conv2d in float64 on the
+    weights the planes hold, and against the im2col + GEMM path it replaces."""
+    from semanticlens_b200 import _native as N
+
+    g = torch.Generator().manual_seed(S + cout)
+    img = torch.randn(B, 3, S, S, generator=g)
+    wt = torch.randn(cout, 3, 3, 3, generator=g) * (2.0 / 27) ** 0.5
+    scale, shift = 1 + 0.1 * torch.randn(cout, generator=g), 0.1 * torch.randn(cout, generator=g)
+    mat = torch.zeros(cout, 64)
+    mat[:, :27] = wt.permute(0, 2, 3, 1).reshape(cout, -1)
+    wp = ops.split_planes(mat.cuda(), 0, WSC)
+    w_held = ((wp[0].double() + wp[1].double()) / WSC)[:, :27].view(cout, 3, 3, 3).permute(0, 3, 1, 2).cpu()
+    want = torch.relu(F.conv2d(img.double(), w_held, stride=2, padding=1) * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1))
+    got = ops.stem_conv3x3s2(img.cuda(), wp, scale.cuda(), shift.cuda())
+    assert got.shape == (2, B * (S // 2) ** 2, cout)
+    assert rel_max(held(got), nhwc_rows(want)) < 1e-6
+    via_gemm, _ = ops.gemm_split(ops.im2col_stem(img.cuda()), wp, bias=shift.cuda(), col_scale=scale.cuda(), epilogue=N.EPI_RELU,
+                                 alpha=1 / (ACT * WSC), passes=N.PASSES_SPLIT_ACC)
+    assert rel_max(held(got), via_gemm) < 3e-6
+    parts = torch.cat([ops.stem_conv3x3s2(img[:1].cuda(), wp, scale.cuda(), shift.cuda()),
+                       ops.stem_conv3x3s2(img[1:].cuda(), wp, scale.cuda(), shift.cuda())], 1) if B > 1 else got
+    assert torch.equal(parts, got)
+
+
 @pytest.mark.parametrize("B,H,W,C", [(2, 8, 8, 32), (1, 7, 7, 64), (3, 5, 9, 8), (1, 14, 14, 256)])
 def test_im2col3x3_moves_plane_bits(ops, B, H, W, C):
     x = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(C + H))
