@@ -365,23 +365,16 @@ __device__ __forceinline__ void drain_half(const GemmParams& p, uint32_t taddr, 
             res[it] = (m < p.M && col_ok) ? *reinterpret_cast<const float4*>(p.residual + m * p.N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     } else if (p.residual_planes) {
-        uint2 rh[4], rl[4];
+        // the raw plane words stay in the float4's registers (hi in x / y, lo in z / w) until the add: unpacking them here
+        // would make the warp wait for these loads before it has even issued its TMEM load (ncu: 37 % of the samples of a
+        // block-tail convolution sat on the first PRMT of the unpack)
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             const int64_t m = m_warp + it * 8 + r8;
             const bool ok = m < p.M && col_ok;
-            rh[it] = ok ? *reinterpret_cast<const uint2*>(p.residual_planes + m * p.N + n) : make_uint2(0u, 0u);
-            rl[it] = ok ? *reinterpret_cast<const uint2*>(p.residual_planes + p.M * p.N + m * p.N + n) : make_uint2(0u, 0u);
-        }
-        constexpr float kInv = 1.0f / SLB_ACT_PLANE_SCALE;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const uint2 h = rh[it], l = rl[it];
-            res[it] = make_float4(
-                (slb_from_plane((uint16_t)(h.x & 0xFFFFu), p.fmt) + slb_from_plane((uint16_t)(l.x & 0xFFFFu), p.fmt)) * kInv,
-                (slb_from_plane((uint16_t)(h.x >> 16), p.fmt) + slb_from_plane((uint16_t)(l.x >> 16), p.fmt)) * kInv,
-                (slb_from_plane((uint16_t)(h.y & 0xFFFFu), p.fmt) + slb_from_plane((uint16_t)(l.y & 0xFFFFu), p.fmt)) * kInv,
-                (slb_from_plane((uint16_t)(h.y >> 16), p.fmt) + slb_from_plane((uint16_t)(l.y >> 16), p.fmt)) * kInv);
+            const uint2 h = ok ? *reinterpret_cast<const uint2*>(p.residual_planes + m * p.N + n) : make_uint2(0u, 0u);
+            const uint2 l = ok ? *reinterpret_cast<const uint2*>(p.residual_planes + p.M * p.N + m * p.N + n) : make_uint2(0u, 0u);
+            res[it] = make_float4(__uint_as_float(h.x), __uint_as_float(h.y), __uint_as_float(l.x), __uint_as_float(l.y));
         }
     }
     float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -433,7 +426,18 @@ __device__ __forceinline__ void drain_half(const GemmParams& p, uint32_t taddr, 
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[it][j] = act_apply(o[it][j], p.epilogue);
     }
-    if (has_res) {
+    if (p.residual_planes) {
+        constexpr float kInv = 1.0f / SLB_ACT_PLANE_SCALE;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const uint32_t hx = __float_as_uint(res[it].x), hy = __float_as_uint(res[it].y);
+            const uint32_t lx = __float_as_uint(res[it].z), ly = __float_as_uint(res[it].w);
+            o[it][0] += (slb_from_plane((uint16_t)(hx & 0xFFFFu), p.fmt) + slb_from_plane((uint16_t)(lx & 0xFFFFu), p.fmt)) * kInv;
+            o[it][1] += (slb_from_plane((uint16_t)(hx >> 16), p.fmt) + slb_from_plane((uint16_t)(lx >> 16), p.fmt)) * kInv;
+            o[it][2] += (slb_from_plane((uint16_t)(hy & 0xFFFFu), p.fmt) + slb_from_plane((uint16_t)(ly & 0xFFFFu), p.fmt)) * kInv;
+            o[it][3] += (slb_from_plane((uint16_t)(hy >> 16), p.fmt) + slb_from_plane((uint16_t)(ly >> 16), p.fmt)) * kInv;
+        }
+    } else if (has_res) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             const float4 r = res[it];
@@ -609,9 +613,8 @@ __device__ __forceinline__ void gemm_wait(uint64_t* bar, uint32_t parity) {
 }
 
 template <int BN, int EW>
-__global__ void __launch_bounds__((2 + EW) * 32, 1)
-gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, GemmParams p) {
+__device__ __forceinline__ void gemm_split_body(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmW,
+                                                const CUtensorMap& tmO, const GemmParams& p) {
     using C = Cfg<BN, EW>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -741,6 +744,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             slb_tc_fence_after();
             const int64_t m = (int64_t)m0 + quarter * 32 + lane;  // the TMEM lane (= output row) this thread drains
             const float rs = (p.row_scale && m < p.M) ? p.row_scale[m] : 1.0f;
+            // (An L2 prefetch of the next tile's shortcut from here — no registers held — was measured SLOWER: RN50 tower
+            // GEMMs 7.41 -> 7.85 ms; the DRAM queue is already full and the prefetches only reorder it.)
 #pragma unroll 1
             for (int c = chunk0; c < BN / 32; c += EW / 4) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
@@ -768,6 +773,16 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         slb_tmem_dealloc<C::kTmemCols>(tmem_base);
     }
 }
+
+template <int BN, int EW>
+__global__ void __launch_bounds__((2 + EW) * 32, 1)
+gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const __grid_constant__ GemmParams p) {
+    gemm_split_body<BN, EW>(tmA, tmA2, tmW, tmO, p);
+}
+
+// (The sixteen-warp instantiation gets 96 registers per thread: 18 warps put five on one SM sub-partition, 16384 / (5 x 32) = 102,
+// rounded down to the allocation unit. __maxnreg__(112) compiles without spills but cannot launch.)
 
 // ---------------------------------------------------------------------------------------------
 // CTA-pair kernel (cta_group::2): one 256 x 128 output tile per cluster of two CTAs on neighbouring SMs.

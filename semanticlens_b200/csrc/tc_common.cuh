@@ -28,6 +28,9 @@ int slb_make_im2col_map(CUtensorMap* out, const void* base, int64_t B, int64_t H
 // ---------------------------------------------------------------------------------------------
 // device: TMA
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void slb_prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(p)));
+}
 __device__ __forceinline__ void slb_prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
