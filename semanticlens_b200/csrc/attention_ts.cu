@@ -50,7 +50,11 @@ constexpr size_t kSmem = (size_t)kOffBars + 128;
 constexpr float kLog2PScale = 10.0f;             // P planes carry 2^10 (hi + lo = 1024 p)
 
 struct AttnTsParams {
-    int T, H, W;
+    int T, H, W;   // T = keys of a work item: the sequence length, or pack * Tseq in packed mode
+    // Packed mode (short sequences, Tseq < 128): a work item is (group of `pack` = 128 / Tseq consecutive images, head); the
+    // group's pack * Tseq rows are contiguous in the qkv matrix and form ONE query tile and ONE key block, and the softmax
+    // masks the logits block-diagonally (a query sees the keys of its own image only). pack = 0: one image per item.
+    int pack, Tseq, B;
     float scale_log2;  // scale * log2(e)
     float* out_f32; uint16_t* out_hi; uint16_t* out_lo; int fmt;
     int n_tiles, n_items;  // query tiles per (image, head); work items = B * H * n_tiles
@@ -136,6 +140,7 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = (p.T + kKeys - 1) / kKeys;
+    const int item_rows = p.T;  // rows of the qkv matrix per item index b (an image, or a group of images in packed mode)
     const int n_iter = 2 * nblk;
     // S buffer of iteration `it` of a work item (sweep 1 alternates the two buffers, sweep 2 uses buffer 0) and how many
     // earlier iterations OF THE ITEM used that buffer; a work item uses buffer 0 uses0 times and buffer 1 uses1 times
@@ -181,14 +186,14 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
                 const bool trace_on = trace_cta && n == p.dbg_item;
                 const int bh = item / p.n_tiles, tile = item % p.n_tiles;
                 const int b = bh / p.H, h = bh % p.H;
-                const int row_base = b * p.T;
+                const int row_base = b * item_rows;
                 ts_wait(q_empty, (uint32_t)(n & 1) ^ 1u);
                 slb_mbar_arrive_expect_tx(q_full, 2u * kPlane);
                 slb_tma_load_3d(smem + kOffQ, &tm, h * 64, row_base + tile * kTile, 0, q_full);
                 {   // the ring only holds two blocks: start the NEXT item's operands on their way to L2 now
                     const int nxt = item + (int)gridDim.x;
                     if (nxt < p.n_items) {
-                        const int bh2 = nxt / p.n_tiles, b2 = bh2 / p.H, h2 = bh2 % p.H, rb2 = b2 * p.T;
+                        const int bh2 = nxt / p.n_tiles, b2 = bh2 / p.H, h2 = bh2 % p.H, rb2 = b2 * item_rows;
                         tma_prefetch_l2_3d(&tm, h2 * 64, rb2 + (nxt % p.n_tiles) * kTile, 0);
                         for (int blk = 0; blk < nblk; ++blk) {
                             tma_prefetch_l2_3d(&tm, p.W + h2 * 64, rb2 + blk * kKeys, 0);
@@ -327,7 +332,15 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
             const bool trace_on = trace_cta && n == p.dbg_item && warp == 2 && lane == 0;
             const int bh = item / p.n_tiles, tile = item % p.n_tiles;
             const int b = bh / p.H, h = bh % p.H;
-            const int row_base = b * p.T;
+            const int row_base = b * item_rows;
+            // keys this thread's query row may see: [k_lo, k_lo + k_span); rows of the item that exist: rows_item
+            int k_lo = 0, rows_item = p.T;
+            const int k_span = p.pack ? p.Tseq : p.T;
+            if (p.pack) {
+                const int img = min(r / p.Tseq, p.pack - 1);
+                k_lo = img * p.Tseq;
+                rows_item = min(p.pack, p.B - b * p.pack) * p.Tseq;
+            }
             float m_row = -INFINITY, l_row = 0.f, neg_m = 0.f;
             for (int it = 0; it < n_iter; ++it) {
                 const int blk = it < nblk ? it : n_iter - 1 - it;  // sweep 2 walks the blocks backwards
@@ -335,7 +348,7 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
                 const int nk = keys_of(blk);
                 const int buf = s_buf(it), idx = base[buf] + s_idx(it);
                 const uint32_t t_s = tmem_base + lane_addr + (uint32_t)(buf * 128);
-                const bool full_block = (blk + 1) * kKeys <= p.T;
+                const bool full_block = !p.pack && (blk + 1) * kKeys <= p.T;
                 if (it == nblk) {
                     // end of sweep 1: the two warps of a row combine their partial maxima
                     if (half) *xw = m_row;
@@ -365,7 +378,7 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j)
-                                    if (blk * kKeys + c + j < p.T) m_row = fmaxf(m_row, __uint_as_float(a[j]) * c_main);
+                                    if ((unsigned)(blk * kKeys + c + j - k_lo) < (unsigned)k_span) m_row = fmaxf(m_row, __uint_as_float(a[j]) * c_main);
                             }
                         }
                     }
@@ -389,8 +402,8 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
                             float x0 = fmaf(__uint_as_float(a[2 * e]), c_main, neg_m);
                             float x1 = fmaf(__uint_as_float(a[2 * e + 1]), c_main, neg_m);
                             if (!full_block) {
-                                if (blk * kKeys + c + 2 * e >= p.T) x0 = -INFINITY;
-                                if (blk * kKeys + c + 2 * e + 1 >= p.T) x1 = -INFINITY;
+                                if ((unsigned)(blk * kKeys + c + 2 * e - k_lo) >= (unsigned)k_span) x0 = -INFINITY;
+                                if ((unsigned)(blk * kKeys + c + 2 * e + 1 - k_lo) >= (unsigned)k_span) x1 = -INFINITY;
                             }
                             const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
                             l_row += p0 + p1;
@@ -445,7 +458,7 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
             const float inv = kInvAct / l_row;  // V planes carry the activation scale, l_row the 2^10 of the P planes
             const int c = half * 32;
             const int64_t tile_base = ((int64_t)row_base + tile * kTile + quarter * 32) * p.W + (int64_t)h * 64 + c;
-            const int rows_ok = p.T - (tile * kTile + quarter * 32);  // rows of this warp's 32 that exist
+            const int rows_ok = rows_item - (tile * kTile + quarter * 32);  // rows of this warp's 32 that exist
             float o[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(a[j]) + __uint_as_float(cr[j])) * inv;
@@ -499,6 +512,7 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
 unsigned int* slb_attention_trace_buffer();  // attention_mma.cu
 
 // Full 128-row query tiles of every (image, head) on the TS-mode tcgen05 path; the caller handles the remaining rows.
+// T < 128 (n_tiles must be 1): packed mode — 128 / T images per tile, block-diagonal softmax mask, every row is covered.
 int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles,
                            int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
     const int64_t W = H * 64, rows = B * T;
@@ -507,6 +521,13 @@ int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int
     if (rc != SLB_OK) return rc;
     AttnTsParams p{};
     p.T = (int)T; p.H = (int)H; p.W = (int)W;
+    int64_t n_batch = B;  // item indices b
+    if (T < kTile) {
+        SLB_REQUIRE(n_tiles == 1, SLB_EINVAL, "slb_attention_ts_tiles: a short sequence is one tile");
+        p.pack = (int)(kTile / T); p.Tseq = (int)T; p.B = (int)B;
+        p.T = p.pack * (int)T;
+        n_batch = (B + p.pack - 1) / p.pack;
+    }
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out_f32 = out_f32; p.out_hi = out_hi; p.out_lo = out_lo; p.fmt = plane_fmt;
     static const bool trace = [] { const char* e = getenv("SLB_ATTN_TRACE"); return e && e[0] == '1'; }();
@@ -519,7 +540,7 @@ int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int
     }
     SLB_CUDA_OK(cudaFuncSetAttribute(attention_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     p.n_tiles = n_tiles;
-    p.n_items = (int)(B * H * n_tiles);
+    p.n_items = (int)(n_batch * H * n_tiles);
     int dev = 0, sms = 0;
     SLB_CUDA_OK(cudaGetDevice(&dev));
     SLB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

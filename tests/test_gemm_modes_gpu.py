@@ -21,3 +21,25 @@ def test_gemm_and_tower_parity_with_the_store_path_forced(mode):
          "tests/test_rn_gpu.py", "tests/test_embed_gpu.py::test_vit_tower_vs_oracle", "tests/test_embed_gpu.py::test_siglip_tower_vs_oracle"],
         cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_short_k_gemms_with_eight_epilogue_warps():
+    """K <= 512 one-CTA GEMMs default to the sixteen-warp epilogue (16-column drains); SLB_GEMM_EPI_WARPS=8 keeps the
+    eight-warp kernel (32-column drains). Both must pass the same parity suites."""
+    env = dict(os.environ, SLB_GEMM_EPI_WARPS="8")
+    r = subprocess.run(
+        [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "tests/test_gemm_gpu.py", "tests/test_rn_gpu.py",
+         "tests/test_probed_gpu.py::test_implicit_gemm_convolution", "tests/test_probed_gpu.py::test_raw_output_rides_along_with_the_fused_epilogue"],
+        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_short_sequences_packed_on_the_tcgen05_attention():
+    """SLB_ATTN_PACK=1 (opt-in: it trades the batch-composition invariance away) runs T < 128 bidirectional attention on the
+    tcgen05 kernel, 128 // T images per tile under a block-diagonal mask: same numerics contract, whole towers included."""
+    env = dict(os.environ, SLB_ATTN_PACK="1")
+    r = subprocess.run(
+        [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+         "tests/test_embed_gpu.py::test_attention_from_planes_vs_torch", "tests/test_embed_gpu.py::test_vit_tower_vs_oracle"],
+        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
