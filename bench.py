@@ -109,6 +109,39 @@ class HostImages:
         return (self.f32[a:b], self.labels[a:b]) if self.kind == "model" else self.u8[a:b]
 
 
+class RingImages:
+    """A dataset of ``n_total`` images whose item i is image ``(i - lo) % ring`` of a ring of pinned host batches: the full-size
+    run (1.28 M images over 8 ranks) streams real host -> device copies every step without holding 193 GB of pixels.
+    Index ranges must not wrap (shards and batches are multiples of the batch size)."""
+
+    def __init__(self, n_total: int, lo: int, hi: int, seed: int, gen_device, kind: str, batch: int, ring_batches: int = 8, store=None):
+        self.n_total, self.lo, self.hi, self.kind = n_total, lo, hi, kind
+        self.ring = batch * ring_batches
+        self.name = f"synthetic-ring-{kind}-{n_total}-seed{seed}"
+        if store is not None:
+            self.u8 = store
+        else:
+            self.u8 = torch.cat([synth_u8(batch, seed * 1_000_003 + lo + a, gen_device).cpu() for a in range(ring_batches)]).pin_memory()
+        if kind == "model":
+            self.f32 = torch.empty(self.u8.shape, dtype=torch.float32, pin_memory=True)
+            for a in range(0, self.ring, batch):
+                self.f32[a : a + batch] = normalise(self.u8[a : a + batch])
+            self.labels = torch.zeros(self.ring, dtype=torch.int64)
+
+    def __len__(self):
+        return self.n_total
+
+    def __getitem__(self, i):
+        j = (i - self.lo) % self.ring
+        return (self.f32[j], 0) if self.kind == "model" else self.u8[j]
+
+    def get_batch(self, lo, hi):
+        a = (lo - self.lo) % self.ring
+        b = a + (hi - lo)
+        assert self.lo <= lo <= hi <= self.hi and b <= self.ring, "index range outside this rank's shard or wrapping the ring"
+        return (self.f32[a:b], self.labels[a:b]) if self.kind == "model" else self.u8[a:b]
+
+
 # ---------------------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi, exact PID is killed)
 # ---------------------------------------------------------------------------------------------------
@@ -408,6 +441,39 @@ def run_b200(args):
                      "all_runs": [round(world * K_e2e * B / (r[0] / 1e3), 1) for r in runs_a],
                      "api": "Lens.compute_concept_db(cv, batch_size=256) with ActivationComponentVisualizer(..., accelerate=True)"}
 
+    # ---- the full-size run: this rank's share of the 1.28 M-image, 8-GPU target through the public API ----
+    full_run = None
+    if not args.no_e2e and fm is not None and "full" in args.configs.split(","):
+        from semanticlens_b200.lens import Lens
+
+        per_rank = (args.full_images // 8) // B * B  # 160 000 images per GPU: at N = 8 the job IS the 1.28 M-image run
+        n_total, lo, hi = world * per_rank, rank * per_rank, (rank + 1) * per_rank
+        ds_model = RingImages(n_total, lo, hi, 31, dev, "model", B)
+        ds_fm = RingImages(n_total, lo, hi, 31, dev, "fm", B, store=ds_model.u8)
+        cv = ActivationComponentVisualizer(model, ds_model, ds_fm, LAYERS, K_COLLECT, device=dev, aggregate_fn=A.aggregate_conv_mean)
+        cv.show_progress = False
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        db = Lens(fm, device=dev).compute_concept_db(cv, batch_size=B)
+        b.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item()) / 1e3
+        full_run = {
+            "workload": f"cfg2 at full size through Lens.compute_concept_db: {n_total} images ({per_rank} per GPU = 1/8 of the 1.28 M-image "
+                        "8-GPU target), host-resident ring of 8 pinned batches per rank, H2D every step, concept DB read back",
+            "value": n_total / secs, "unit": "images/s", "seconds": secs, "wall_seconds": wall, "images": n_total, "scaling": "weak",
+            "h2d_bytes_per_step": int(h2d), "concept_db_bytes": int(sum(v.numel() * v.element_size() for v in db.values())),
+            "projected_1p28M_seconds_at_this_rate": 1_280_000 / (n_total / secs),
+        }
+        del db, cv, ds_model, ds_fm
+        torch.cuda.empty_cache()
+
     # ---- roofline of the dominant libslb200 kernel (live CUDA-event times of the timed region) ------------
     traffic_file = ROOT / "profiles" / "dram_traffic.json"  # per-launch DRAM bytes from the committed ncu capture
     traffic = json.loads(traffic_file.read_text()) if traffic_file.exists() else {}
@@ -451,6 +517,8 @@ def run_b200(args):
         sub["cfg5_scores"] = run_cfg5(dev, rank, world, pk, pk_src, with_cpu)
     if e2e_accel is not None and "cfg2_accel_step" in sub:
         sub["cfg2_accel_step"]["e2e"] = e2e_accel
+    if full_run is not None:
+        sub["cfg2_full_run"] = full_run
 
     if rank == 0:
         line = {
@@ -917,9 +985,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     ap.add_argument("--overlap", type=int, default=0, help="1: run the embed tower on a second stream under the sweep")
-    ap.add_argument("--configs", default="cfg3,cfg4,cfg5,cfg2a,cfg3a,cfg4a",
+    ap.add_argument("--full-images", type=int, default=1_280_000, help="size of the 8-GPU full run; each rank sweeps 1/8 of it")
+    ap.add_argument("--configs", default="cfg3,cfg4,cfg5,cfg2a,cfg3a,cfg4a,full",
                     help="sub-records measured after the headline: any of cfg3,cfg4,cfg5,cfg2a,cfg3a,cfg4a (a = opt-in "
-                         "accelerated probed forward), or 'none'")
+                         "accelerated probed forward), full (this rank's 1/8 of the 1.28 M-image run through the public API), or 'none'")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
