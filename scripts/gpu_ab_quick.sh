@@ -1,7 +1,5 @@
 #!/bin/bash
 TAG=${1:-ab}
 O=gpurun_out; mkdir -p $O
-timeout 400 python -m pytest tests/test_embed_gpu.py -m gpu -q -x -p no:cacheprovider > $O/${TAG}_pytest.log 2>&1; echo "exit $?" >> $O/${TAG}_pytest.log; tail -12 $O/${TAG}_pytest.log | cut -c1-300
-for m in 0 1 0 1; do
-    echo "SLB_ATTN_PACK=$m"; SLB_ATTN_PACK=$m timeout 120 python scripts/profile_tower.py ViT-B-32 256 2>&1 | tail -1 | tee -a $O/${TAG}_vitb32.jsonl | cut -c1-420
-done
+timeout 300 python -m pytest tests/test_scores_gpu.py tests/test_cfg5_gpu.py -m gpu -q -x -p no:cacheprovider > $O/${TAG}_pytest.log 2>&1; echo "exit $?" >> $O/${TAG}_pytest.log; tail -3 $O/${TAG}_pytest.log | cut -c1-300
+timeout 300 python scripts/time_polysem.py 65536 2>&1 | tee $O/${TAG}_polysem_split.jsonl | cut -c1-400

@@ -312,10 +312,18 @@ __device__ void gram_f64(const float* __restrict__ X, int k, int D, double* __re
                     for (int a = 0; a < 4; ++a) av[a] = (double)ra[a * 8 * kPitch + kk * 4];
 #pragma unroll
                     for (int b = 0; b < 4; ++b) bv[b] = (double)rb[b * 8 * kPitch + kk * 4];
+                    if (bi == bj) {  // a diagonal tile keeps its upper 8x8 blocks only: 10 of 16 DMMAs (warp-uniform)
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+                        for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], av[a], bv[b]);
+                            for (int b = 0; b < 4; ++b)
+                                if (b >= a) dmma884(acc[a][b][0], acc[a][b][1], av[a], bv[b]);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], av[a], bv[b]);
+                    }
                 }
             }
             __syncthreads();  // the slot is free again
