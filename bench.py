@@ -900,12 +900,13 @@ def run_cfg5(dev, rank: int, world: int, pk: dict, pk_src: str, with_cpu: bool, 
                          "frac": by / ms_po / 1e6 / pk["hbm_gbs"], "traffic": tr("K8 polysem_2means"),
                          "note": "algorithmic bytes = the k x D examples of every neuron read once; the kernel is bound by "
                                  "its float64 Gram matrix on the FP64 tensor cores (DMMA) and the on-chip Lloyd iterations",
-                         # what actually bounds it: the 36 upper-triangle 32x32 tiles of G0 = X X^T in float64 per neuron
-                         "fp64_tensor": {"flops_per_neuron": 36 * 2.0 * 32 * 32 * D if k == 256 else 2.0 * k * k * D,
-                                         "achieved_TFLOP/s": C * (36 * 2.0 * 32 * 32 * D if k == 256 else 2.0 * k * k * D) / ms_po / 1e9,
+                         # what actually bounds it: G0 = X X^T in float64 per neuron, issued as the 528 upper 8x8 blocks of the
+                         # 36 upper-triangle 32x32 tiles (the diagonal tiles skip their lower blocks): 528 * 2 * 8 * 8 * D flops
+                         "fp64_tensor": {"flops_per_neuron": 528 * 2.0 * 8 * 8 * D if k == 256 else 2.0 * k * k * D,
+                                         "achieved_TFLOP/s": C * (528 * 2.0 * 8 * 8 * D if k == 256 else 2.0 * k * k * D) / ms_po / 1e9,
                                          "peak_TFLOP/s": 40.0, "peak_source": "nominal B200 FP64 tensor (no measured figure "
-                                         "in MEASURED_PEAKS.json); the Gram phase alone runs at 31.6 (profiles/r02_polysem_split.jsonl)",
-                                         "frac": C * (36 * 2.0 * 32 * 32 * D if k == 256 else 2.0 * k * k * D) / ms_po / 1e9 / 40.0}}},
+                                         "in MEASURED_PEAKS.json); the Gram phase alone ran at 31.6 in the split-kernel experiment (DESIGN.md, K8)",
+                                         "frac": C * (528 * 2.0 * 8 * 8 * D if k == 256 else 2.0 * k * k * D) / ms_po / 1e9 / 40.0}}},
     }
     total_ms = ms_sim + ms_cl + ms_po
     dom = max(scores, key=lambda n: scores[n]["ms"])
