@@ -330,6 +330,38 @@ __device__ void gram_f64(const float* __restrict__ X, int k, int D, double* __re
             if (s + kStages < n_stage) request_stage(sm, ring, X, k, D, (s + kStages) * kStageCols, bulk, pol);
         }
         if (live) {
+            // Row sums of G0 while the tile is still in registers (they were a separate G0 x 1 product over the stored slot:
+            // 20 us per neuron and CTA). psum[tile][0..31] = sums of the tile's rows -> rows of block bi; psum[tile][32..63] = sums
+            // of its columns -> by symmetry, rows of block bj. A diagonal tile holds its upper 8x8 blocks only: the column sums of
+            // the strictly upper blocks are folded into its row part. Fixed shuffle order: deterministic.
+            double* ps = &sm.tA0[0][0] + tile * 64;
+            const bool diag = bi == bj;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                double rs = 0.0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) rs += acc[a][b][0] + acc[a][b][1];  // (skipped blocks of a diagonal tile are zero)
+                rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+                rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+                if (t == 0 && !diag) ps[8 * a + g] = rs;
+                // diagonal tile: row part of rows 8a + g, completed below with the column sums of blocks (a' < a, a)
+                double c0 = 0.0, c1 = 0.0;  // columns 8a + 2t, 8a + 2t + 1 of block column a
+#pragma unroll
+                for (int a2 = 0; a2 < 4; ++a2)
+                    if (!diag || a2 < a) { c0 += acc[a2][a][0]; c1 += acc[a2][a][1]; }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+                    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+                }
+                if (!diag) {
+                    if (g == 0) { ps[32 + 8 * a + 2 * t] = c0; ps[32 + 8 * a + 2 * t + 1] = c1; }
+                } else {
+                    // row 8a + g's share is the sum of column g of block column a: component g % 2 of any lane with t = g / 2
+                    const double pick0 = __shfl_sync(0xffffffffu, c0, g >> 1), pick1 = __shfl_sync(0xffffffffu, c1, g >> 1);
+                    if (t == 0) ps[8 * a + g] = rs + ((g & 1) ? pick1 : pick0);
+                }
+            }
             // accumulator (a, b) of lane (g, t) holds G0[32 bi + 8a + g][32 bj + 8b + 2t + {0, 1}]: two adjacent doubles of
             // fragment (band 4 bi + a, group 8 bj + 2b + t / 2) — one 16-byte store; fragments below the diagonal are not kept
             const int NB = (k + 7) >> 3, KQ = (k + 3) >> 2;
@@ -440,10 +472,16 @@ __global__ void __launch_bounds__(kThreads, 2) polysem_kernel(PolyParams p) {
         t1 = clock64(); clk[0] += t1 - t0; t0 = t1;
 
         // row means, grand mean, centred diagonal, tolerance
-        gram_times<1>(G, sm.fb, k, [&](int j, int) { return j < k ? 1.0 : 0.0; },
-                      [&](int row, int col, double y0, double) { if (col == 0) sm.r[row] = y0 / (double)k; });
-        __syncthreads();
-        const double ri = on ? sm.r[i] : 0.0;
+        // row means from the per-tile sums phase A left in sm.tA0 (fixed order: blocks left of the diagonal, then the row's own)
+        double ri = 0.0;
+        if (on) {
+            const int B = i >> 5, o = i & 31, nb = (k + 31) >> 5;
+            const double* ps = &sm.tA0[0][0];
+            for (int b2 = 0; b2 < B; ++b2) ri += ps[(b2 * 8 - b2 * (b2 - 1) / 2 + (B - b2)) * 64 + 32 + o];
+            for (int b2 = B; b2 < nb; ++b2) ri += ps[(B * 8 - B * (B - 1) / 2 + (b2 - B)) * 64 + o];
+            ri /= (double)k;
+        }
+        __syncthreads();  // sm.tA0 is free again
         const double m = block_sum1(ri, sm) / (double)k;
         const double g_ii = on ? G[frag_elem(sm.fb, i, i)] : 0.0;
         const double di = on ? g_ii - 2.0 * ri + m : 0.0;
