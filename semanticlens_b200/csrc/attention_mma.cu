@@ -713,7 +713,7 @@ int slb_attention_mma_dh64(const float* q, int64_t q_bs, int64_t q_rs, const flo
     return launch_attn<8>(p, B, st);
 }
 
-int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles,
+int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles, int tail_keys,
                            int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st);  // attention_ts.cu
 
 extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, int64_t dh, float scale,
@@ -747,12 +747,16 @@ extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64
     // (every image padded to a multiple of 16 keys, one TMA box per image) would restore the invariance.
     static const bool pack = [] { const char* e = getenv("SLB_ATTN_PACK"); return e && e[0] == '1'; }();
     if (pack && !causal && !no_tc && T < 128 && T >= 16)
-        return slb_attention_ts_tiles(qkv_planes, B, T, H, scale, 1, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
+        return slb_attention_ts_tiles(qkv_planes, B, T, H, scale, 1, 0, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
     if (!causal && !no_tc && T >= 128) {
         int n_tiles = (int)(T / 128);
         const int64_t rem = T - 128 * (int64_t)n_tiles;
         if (rem >= 64) n_tiles += 1;
-        int rc = slb_attention_ts_tiles(qkv_planes, B, T, H, scale, n_tiles, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
+        // T = 128 n + 1..4 (ViT-L/14's 257 tokens): the tail keys ride in the softmax threads instead of a key block of their
+        // own (SLB_ATTN_KEY_TAIL=0: the old arrangement, a third block holding one key)
+        static const bool no_tail = [] { const char* e = getenv("SLB_ATTN_KEY_TAIL"); return e && e[0] == '0'; }();
+        const int tail_keys = (!no_tail && rem >= 1 && rem <= 4) ? (int)rem : 0;
+        int rc = slb_attention_ts_tiles(qkv_planes, B, T, H, scale, n_tiles, tail_keys, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
         if (rc != SLB_OK) return rc;
         if ((int64_t)n_tiles * 128 >= T) return SLB_OK;
         p.q_row0 = n_tiles * 128;
