@@ -43,3 +43,13 @@ def test_short_sequences_packed_on_the_tcgen05_attention():
          "tests/test_embed_gpu.py::test_attention_from_planes_vs_torch", "tests/test_embed_gpu.py::test_vit_tower_vs_oracle"],
         cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_key_tail_as_a_block_of_its_own():
+    """SLB_ATTN_KEY_TAIL=0: T = 128 n + 1..4 runs the tail keys as one more key block (the arrangement before the SIMT tail)."""
+    env = dict(os.environ, SLB_ATTN_KEY_TAIL="0")
+    r = subprocess.run(
+        [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+         "tests/test_embed_gpu.py::test_attention_from_planes_vs_torch"],
+        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
