@@ -121,9 +121,11 @@ class RingImages:
         if store is not None:
             self.u8 = store
         else:
-            self.u8 = torch.cat([synth_u8(batch, seed * 1_000_003 + lo + a, gen_device).cpu() for a in range(ring_batches)]).pin_memory()
+            self.u8 = torch.cat([synth_u8(batch, seed * 1_000_003 + lo + a, gen_device).cpu() for a in range(ring_batches)])
+            if torch.cuda.is_available():
+                self.u8 = self.u8.pin_memory()
         if kind == "model":
-            self.f32 = torch.empty(self.u8.shape, dtype=torch.float32, pin_memory=True)
+            self.f32 = torch.empty(self.u8.shape, dtype=torch.float32, pin_memory=torch.cuda.is_available())
             for a in range(0, self.ring, batch):
                 self.f32[a : a + batch] = normalise(self.u8[a : a + batch])
             self.labels = torch.zeros(self.ring, dtype=torch.int64)

@@ -31,3 +31,32 @@ def test_stdout_is_reserved_for_the_result_line():
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.strip() == '{"ok": 1}'
     assert "banner" in r.stderr and "chatter" in r.stderr
+
+
+def test_ring_dataset_of_the_full_run_maps_global_ids_onto_the_host_ring():
+    """bench.RingImages (the dataset of the cfg2_full_run sub-record): item i of a rank's shard is image (i - lo) % ring of a
+    small host ring, batch-aligned ranges never wrap, ranges outside the shard are refused, both views share the pixels."""
+    import pytest
+    import torch
+
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    B, ring_batches = 4, 3
+    lo, hi, n_total = 40, 40 + 7 * B, 200
+    dm = bench.RingImages(n_total, lo, hi, 5, "cpu", "model", B, ring_batches)
+    df = bench.RingImages(n_total, lo, hi, 5, "cpu", "fm", B, ring_batches, store=dm.u8)
+    assert len(dm) == len(df) == n_total and dm.ring == B * ring_batches and dm.u8.shape == (dm.ring, 3, 224, 224)
+    assert dm.name != df.name and str(n_total) in dm.name
+    for step in range(7):
+        a = lo + step * B
+        x, y = dm.get_batch(a, a + B)
+        u = df.get_batch(a, a + B)
+        j = (step * B) % dm.ring
+        assert torch.equal(u, dm.u8[j : j + B]) and x.shape == (B, 3, 224, 224) and y.shape == (B,)
+        assert torch.equal(x, bench.normalise(u))
+        assert torch.equal(df[a + 1], dm.u8[(j + 1) % dm.ring]) and torch.equal(dm[a + 1][0], x[1])
+    with pytest.raises(AssertionError):
+        dm.get_batch(lo - B, lo)  # outside this rank's shard
+    with pytest.raises(AssertionError):
+        dm.get_batch(lo + 2, lo + 2 + dm.ring)  # would wrap the ring
