@@ -714,7 +714,7 @@ int slb_attention_mma_dh64(const float* q, int64_t q_bs, int64_t q_rs, const flo
 }
 
 int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles, int tail_keys,
-                           int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st);  // attention_ts.cu
+                           int causal, int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st);  // attention_ts.cu
 
 extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, int64_t dh, float scale,
                                     int causal, int plane_fmt, float* out_f32, uint16_t* out_planes, void* stream) {
@@ -739,15 +739,14 @@ extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64
     // Long sequences: full 128-query tiles run on tcgen05 (attention_ts.cu: P as a tensor-memory operand); a tail of fewer
     // than 64 rows (the last row of a 257-token tower) and short / causal sequences stay on the mma.sync kernel.
     static const bool no_tc = [] { const char* e = getenv("SLB_ATTN_TC"); return e && e[0] == '0'; }();
-    // Short bidirectional sequences (ViT-B/32's 50 tokens, SigLIP text's 64) CAN run on the tcgen05 kernel, 128 / T images per
-    // tile under a block-diagonal softmax mask (SLB_ATTN_PACK=1). Measured (ViT-B/32, 256 images): attention 0.91 -> 0.75 ms per
-    // tower, tower time unchanged within noise (6.93 / 7.12 vs 7.02 / 7.05 ms) — and an image's bits then depend on its
-    // position in the tile (its keys fall into different 16-key MMA steps), which breaks the batch-composition invariance
-    // the sharded sweep relies on (rank-count independent concept DBs). Off by default for that reason; slot-aligned packing
-    // (every image padded to a multiple of 16 keys, one TMA box per image) would restore the invariance.
-    static const bool pack = [] { const char* e = getenv("SLB_ATTN_PACK"); return e && e[0] == '1'; }();
-    if (pack && !causal && !no_tc && T < 128 && T >= 16)
-        return slb_attention_ts_tiles(qkv_planes, B, T, H, scale, 1, 0, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
+    // Short sequences (ViT-B/32's 50 tokens, the text towers' 77 / 64, causal or not) run on the tcgen05 kernel too: every image
+    // gets a slot of 16 / 32 / 64 / 128 tile rows (two 50-token images per tile), the softmax masks block-diagonally. Slots
+    // start on multiples of 16 keys, so an image's bits do not depend on its neighbours or its position (the batch-composition
+    // invariance the sharded sweep relies on; a first version that packed images back to back did not have it).
+    // SLB_ATTN_PACK=0 keeps short sequences on the mma.sync kernel.
+    static const bool no_pack = [] { const char* e = getenv("SLB_ATTN_PACK"); return e && e[0] == '0'; }();
+    if (!no_pack && !no_tc && T < 128)
+        return slb_attention_ts_tiles(qkv_planes, B, T, H, scale, 1, 0, causal, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
     if (!causal && !no_tc && T >= 128) {
         int n_tiles = (int)(T / 128);
         const int64_t rem = T - 128 * (int64_t)n_tiles;
@@ -756,7 +755,7 @@ extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64
         // own (SLB_ATTN_KEY_TAIL=0: the old arrangement, a third block holding one key)
         static const bool no_tail = [] { const char* e = getenv("SLB_ATTN_KEY_TAIL"); return e && e[0] == '0'; }();
         const int tail_keys = (!no_tail && rem >= 1 && rem <= 4) ? (int)rem : 0;
-        int rc = slb_attention_ts_tiles(qkv_planes, B, T, H, scale, n_tiles, tail_keys, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
+        int rc = slb_attention_ts_tiles(qkv_planes, B, T, H, scale, n_tiles, tail_keys, 0, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
         if (rc != SLB_OK) return rc;
         if ((int64_t)n_tiles * 128 >= T) return SLB_OK;
         p.q_row0 = n_tiles * 128;

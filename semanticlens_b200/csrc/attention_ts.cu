@@ -50,11 +50,14 @@ constexpr size_t kSmem = (size_t)kOffBars + 128;
 constexpr float kLog2PScale = 10.0f;             // P planes carry 2^10 (hi + lo = 1024 p)
 
 struct AttnTsParams {
-    int T, H, W;   // T = keys of a work item: the sequence length, or pack * Tseq in packed mode
-    // Packed mode (short sequences, Tseq < 128): a work item is (group of `pack` = 128 / Tseq consecutive images, head); the
-    // group's pack * Tseq rows are contiguous in the qkv matrix and form ONE query tile and ONE key block, and the softmax
-    // masks the logits block-diagonally (a query sees the keys of its own image only). pack = 0: one image per item.
-    int pack, Tseq, B;
+    int T, H, W;   // T = keys of a work item: the sequence length, or 128 in packed mode
+    // Packed mode (short sequences, Tseq < 128): a work item is (group of `pack` consecutive images, head). Every image gets a
+    // SLOT of 2^slot_shift >= Tseq rows of the tile (16, 32, 64 or 128; pack = 128 / slot), loaded by its own TMA boxes; the tile
+    // is ONE query tile and ONE key block and the softmax masks the logits block-diagonally (a query sees the keys of its own
+    // image only; `causal`: and no later token). Slots start on multiples of 16 keys, so an image's keys fall into the same MMA
+    // k-steps and the same summation order wherever it sits in the tile: results are bit-identical for any batch composition.
+    // pack = 0: one image per item.
+    int pack, slot_shift, Tseq, B, causal;
     // Key tail (T = 128 n + 1..4: the class token on top of a power-of-two patch grid, ViT-L/14's 257): the last `tail` keys do
     // not get a key block of their own (a block costs the same hand-offs whether it holds 1 key or 128: 91 -> 136 us per layer)
     // — the softmax threads take them in fp32 SIMT: logit from the Q row in shared memory, probability into the row sum, p v
@@ -130,7 +133,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
-attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
+attention_ts_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_hi,
+                    const __grid_constant__ CUtensorMap tm_lo, AttnTsParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
     uint64_t* q_full = bars;        // TMA -> MMA
@@ -146,7 +150,8 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = (p.T + kKeys - 1) / kKeys;
-    const int item_rows = p.tail ? p.rows_seq : p.T;  // rows of the qkv matrix per item index b (an image, or a packed group)
+    // rows of the qkv matrix per item index b (an image, or a packed group of images)
+    const int item_rows = p.pack ? p.pack * p.Tseq : (p.tail ? p.rows_seq : p.T);
     const int n_iter = 2 * nblk;
     // S buffer of iteration `it` of a work item (sweep 1 alternates the two buffers, sweep 2 uses buffer 0) and how many
     // earlier iterations OF THE ITEM used that buffer; a work item uses buffer 0 uses0 times and buffer 1 uses1 times
@@ -194,8 +199,22 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
                 const int b = bh / p.H, h = bh % p.H;
                 const int row_base = b * item_rows;
                 ts_wait(q_empty, (uint32_t)(n & 1) ^ 1u);
+                // one 128-row box of both planes, or (packed mode) one box per image and plane into the image's slot; images past
+                // the batch repeat the last one (their rows are never stored)
+                auto load_tile = [&](unsigned char* dst, int col, int row, uint64_t* bar) {
+                    if (!p.pack) {
+                        slb_tma_load_3d(dst, &tm, col, row, 0, bar);
+                        return;
+                    }
+                    for (int im = 0; im < p.pack; ++im) {
+                        const int g_img = min(b * p.pack + im, p.B - 1);
+                        unsigned char* d = dst + ((im << p.slot_shift) << 7);
+                        slb_tma_load_3d(d, &tm_hi, col, g_img * p.Tseq, 0, bar);
+                        slb_tma_load_3d(d + kPlane, &tm_lo, col, g_img * p.Tseq, 0, bar);
+                    }
+                };
                 slb_mbar_arrive_expect_tx(q_full, 2u * kPlane);
-                slb_tma_load_3d(smem + kOffQ, &tm, h * 64, row_base + tile * kTile, 0, q_full);
+                load_tile(smem + kOffQ, h * 64, row_base + tile * kTile, q_full);
                 {   // the ring only holds two blocks: start the NEXT item's operands on their way to L2 now
                     const int nxt = item + (int)gridDim.x;
                     if (nxt < p.n_items) {
@@ -215,7 +234,7 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
                     const int slot = t % kSlots;
                     ts_wait(&kv_empty[slot], (uint32_t)((t / kSlots) & 1) ^ 1u);
                     slb_mbar_arrive_expect_tx(&kv_full[slot], 2u * kPlane);
-                    slb_tma_load_3d(smem + kOffKV + slot * 2 * kPlane, &tm, col, row, 0, &kv_full[slot]);
+                    load_tile(smem + kOffKV + slot * 2 * kPlane, col, row, &kv_full[slot]);
                     TS_TRACE(0, t_item);
                     ++t;
                     ++t_item;
@@ -340,13 +359,10 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
             const int b = bh / p.H, h = bh % p.H;
             const int row_base = b * item_rows;
             // keys this thread's query row may see: [k_lo, k_lo + k_span); rows of the item that exist: rows_item
-            int k_lo = 0, rows_item = p.T;
-            const int k_span = p.pack ? p.Tseq : p.T;
-            if (p.pack) {
-                const int img = min(r / p.Tseq, p.pack - 1);
-                k_lo = img * p.Tseq;
-                rows_item = min(p.pack, p.B - b * p.pack) * p.Tseq;
-            }
+            int k_lo = 0;
+            int k_span = p.pack ? p.Tseq : p.T;
+            if (p.pack) k_lo = (r >> p.slot_shift) << p.slot_shift;
+            if (p.causal) k_span = min(k_span, r - k_lo + 1);  // causal: keys up to the query's own position
             if (p.tail && warp == 2 && lane < 4 * p.tail) {
                 // the tail keys' K and V rows (hi / lo: four 128-byte lines per key) into L1 now: the softmax threads read them
                 // between the sweeps and in the epilogue, where a trip to L2 would sit on every warp's critical path
@@ -527,8 +543,14 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
             }
             const float inv = kInvAct / l_row;  // V planes carry the activation scale, l_row the 2^10 of the P planes
             const int c = half * 32;
-            const int64_t tile_base = ((int64_t)row_base + tile * kTile + quarter * 32) * p.W + (int64_t)h * 64 + c;
-            const int rows_ok = rows_item - (tile * kTile + quarter * 32);  // rows of this warp's 32 that exist
+            // tile row rt (0..127) -> row of the output matrix, or -1 when the row does not exist (past the sequence / the batch)
+            auto out_row = [&](int rt) -> int64_t {
+                if (!p.pack) return tile * kTile + rt < p.T + p.tail ? (int64_t)row_base + tile * kTile + rt : -1;
+                const int im = rt >> p.slot_shift, tok = rt & ((1 << p.slot_shift) - 1);
+                const int g_img = b * p.pack + im;
+                return (tok < p.Tseq && g_img < p.B) ? (int64_t)g_img * p.Tseq + tok : -1;
+            };
+            const int64_t col_base = (int64_t)h * 64 + c;
             float o[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(a[j]) + __uint_as_float(cr[j]);
@@ -556,10 +578,11 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] *= inv;
-            if (p.out_f32 && lane < rows_ok) {
+            const int64_t my_row = out_row(quarter * 32 + lane);
+            if (p.out_f32 && my_row >= 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    reinterpret_cast<float4*>(p.out_f32 + tile_base + (int64_t)lane * p.W)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    reinterpret_cast<float4*>(p.out_f32 + my_row * p.W + col_base)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             }
             if (p.out_hi) {
                 // thread = row would store 16 bytes to 32 different lines per instruction (the LSU serialises them: the
@@ -584,7 +607,8 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
                     for (int i = 0; i < 4; ++i) {
                         const int rr = i * 8 + (lane >> 2), ch = lane & 3;
                         const uint4 v = *reinterpret_cast<const uint4*>(stage_own + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
-                        if (rr < rows_ok) *reinterpret_cast<uint4*>(dst + tile_base + (int64_t)rr * p.W + ch * 8) = v;
+                        const int64_t orow = out_row(quarter * 32 + rr);
+                        if (orow >= 0) *reinterpret_cast<uint4*>(dst + orow * p.W + col_base + ch * 8) = v;
                     }
                 }
                 __syncwarp();
@@ -606,10 +630,11 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, AttnTsParams p) {
 unsigned int* slb_attention_trace_buffer();  // attention_mma.cu
 
 // Full 128-row query tiles of every (image, head) on the TS-mode tcgen05 path; the caller handles the remaining rows.
-// T < 128 (n_tiles must be 1): packed mode — 128 / T images per tile, block-diagonal softmax mask, every row is covered.
+// T < 128 (n_tiles must be 1): packed mode — every image in a slot of 16 / 32 / 64 / 128 rows of the tile, block-diagonal (and,
+// with `causal`, lower-triangular) softmax mask, every row is covered.
 // tail_keys (0..4, only with T = 128 n_tiles + tail_keys): the last keys are taken by the softmax threads in fp32 (no key block).
 int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles, int tail_keys,
-                           int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
+                           int causal, int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
     const int64_t W = H * 64, rows = B * T;
     CUtensorMap tm;
     int rc = slb_make_plane_map(&tm, qkv_planes, rows, 3 * W, 2, kTile);
@@ -623,11 +648,21 @@ int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int
         p.qkv = qkv_planes; p.plane_stride = rows * 3 * W;
     }
     int64_t n_batch = B;  // item indices b
+    CUtensorMap tm_hi = tm, tm_lo = tm;
     if (T < kTile) {
-        SLB_REQUIRE(n_tiles == 1, SLB_EINVAL, "slb_attention_ts_tiles: a short sequence is one tile");
-        p.pack = (int)(kTile / T); p.Tseq = (int)T; p.B = (int)B;
-        p.T = p.pack * (int)T;
+        SLB_REQUIRE(n_tiles == 1 && tail_keys == 0, SLB_EINVAL, "slb_attention_ts_tiles: a short sequence is one tile");
+        int shift = 4;
+        while ((1 << shift) < T) ++shift;
+        p.slot_shift = shift; p.pack = kTile >> shift; p.Tseq = (int)T; p.B = (int)B; p.causal = causal ? 1 : 0;
+        p.T = kTile;
         n_batch = (B + p.pack - 1) / p.pack;
+        // one plane, slot rows per box: an image's Q / K / V rows go to its slot of the tile
+        rc = slb_make_plane_map(&tm_hi, qkv_planes, rows, 3 * W, 1, 1 << shift);
+        if (rc != SLB_OK) return rc;
+        rc = slb_make_plane_map(&tm_lo, qkv_planes + rows * 3 * W, rows, 3 * W, 1, 1 << shift);
+        if (rc != SLB_OK) return rc;
+    } else {
+        SLB_REQUIRE(!causal, SLB_EUNSUPPORTED, "slb_attention_ts_tiles: causal masks on short sequences only");
     }
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out_f32 = out_f32; p.out_hi = out_hi; p.out_lo = out_lo; p.fmt = plane_fmt;
@@ -646,7 +681,7 @@ int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int
     SLB_CUDA_OK(cudaGetDevice(&dev));
     SLB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = std::min(p.n_items, 2 * sms);  // persistent: two CTAs per SM
-    attention_ts_kernel<<<grid, kThreads, kSmem, st>>>(tm, p);
+    attention_ts_kernel<<<grid, kThreads, kSmem, st>>>(tm, tm_hi, tm_lo, p);
     SLB_LAUNCH_OK("attention_ts");
     return SLB_OK;
 }

@@ -259,7 +259,27 @@ def test_preprocess_staging_buffers_do_not_race_the_copy_engine():
         assert torch.equal(o.cpu(), (b.float() / 255.0 - mean) / std)
 
 
-@pytest.mark.parametrize("B,T,H", [(3, 77, 8), (2, 12, 2), (1, 64, 1), (2, 130, 2)])
+@pytest.mark.parametrize("T,H,causal", [(50, 2, False), (64, 1, False), (17, 3, False), (77, 2, True), (12, 2, True), (100, 1, False),
+                                        (257, 2, False), (129, 1, False)])
+def test_attention_bits_do_not_depend_on_the_batch_composition(ops, T, H, causal):
+    """Short sequences share a tcgen05 tile (one slot of 16 / 32 / 64 / 128 rows per image); an image's output must be the same
+    bits whichever images it shares the tile with and whichever slot it lands in (the sharded sweep relies on it)."""
+    B, W = 7, H * 64
+    qkv = torch.randn(B, T, 3 * W, generator=torch.Generator().manual_seed(T + 31 * H))
+    planes = ops.split_planes(qkv.view(B * T, 3 * W).cuda(), 0, ACT).view(2, B, T, 3 * W)
+
+    def run(lo, hi):
+        sub = planes[:, lo:hi].reshape(2, (hi - lo) * T, 3 * W).contiguous()
+        return ops.attention_planes(sub, hi - lo, H, causal=causal).view(hi - lo, T, W)
+
+    whole = run(0, B)
+    parts = torch.cat([run(0, 1), run(1, 4), run(4, 6), run(6, 7)])
+    assert torch.equal(whole, parts)
+    shifted = torch.cat([run(0, 3), run(3, 7)])
+    assert torch.equal(whole, shifted)
+
+
+@pytest.mark.parametrize("B,T,H", [(3, 77, 8), (2, 12, 2), (1, 64, 1), (2, 130, 2), (5, 33, 2), (9, 16, 1), (4, 127, 1)])
 def test_causal_attention_from_planes_vs_torch(ops, B, T, H):
     dh = 64
     W = H * dh

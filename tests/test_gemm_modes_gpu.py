@@ -34,13 +34,14 @@ def test_short_k_gemms_with_eight_epilogue_warps():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
-def test_short_sequences_packed_on_the_tcgen05_attention():
-    """SLB_ATTN_PACK=1 (opt-in: it trades the batch-composition invariance away) runs T < 128 bidirectional attention on the
-    tcgen05 kernel, 128 // T images per tile under a block-diagonal mask: same numerics contract, whole towers included."""
-    env = dict(os.environ, SLB_ATTN_PACK="1")
+def test_short_sequences_on_the_mma_sync_attention():
+    """SLB_ATTN_PACK=0 keeps T < 128 attention (ViT-B/32, the text towers) on the mma.sync kernel instead of packing the images
+    into slots of a tcgen05 tile: same numerics contract, whole towers and the causal text tower included."""
+    env = dict(os.environ, SLB_ATTN_PACK="0")
     r = subprocess.run(
         [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
-         "tests/test_embed_gpu.py::test_attention_from_planes_vs_torch", "tests/test_embed_gpu.py::test_vit_tower_vs_oracle"],
+         "tests/test_embed_gpu.py::test_attention_from_planes_vs_torch", "tests/test_embed_gpu.py::test_vit_tower_vs_oracle",
+         "tests/test_embed_gpu.py::test_vit_tower_batch_composition_invariance", "tests/test_embed_gpu.py", "-k", "attention or tower or text"],
         cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
