@@ -133,8 +133,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
-attention_ts_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_hi,
-                    const __grid_constant__ CUtensorMap tm_lo, AttnTsParams p) {
+attention_ts_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_pack, AttnTsParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
     uint64_t* q_full = bars;        // TMA -> MMA
@@ -199,19 +198,14 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
                 const int b = bh / p.H, h = bh % p.H;
                 const int row_base = b * item_rows;
                 ts_wait(q_empty, (uint32_t)(n & 1) ^ 1u);
-                // one 128-row box of both planes, or (packed mode) one box per image and plane into the image's slot; images past
-                // the batch repeat the last one (their rows are never stored)
+                // one 128-row box of both planes; packed mode: ONE 4-D box {64 columns, slot tokens, pack images, 2 planes} over the
+                // planes seen as (plane, image, token, column) — it lands as [plane][image][token] = the slot layout, tokens past
+                // the sequence and images past the batch zero-filled by the TMA unit
                 auto load_tile = [&](unsigned char* dst, int col, int row, uint64_t* bar) {
-                    if (!p.pack) {
+                    if (!p.pack)
                         slb_tma_load_3d(dst, &tm, col, row, 0, bar);
-                        return;
-                    }
-                    for (int im = 0; im < p.pack; ++im) {
-                        const int g_img = min(b * p.pack + im, p.B - 1);
-                        unsigned char* d = dst + ((im << p.slot_shift) << 7);
-                        slb_tma_load_3d(d, &tm_hi, col, g_img * p.Tseq, 0, bar);
-                        slb_tma_load_3d(d + kPlane, &tm_lo, col, g_img * p.Tseq, 0, bar);
-                    }
+                    else
+                        slb_tma_load_4d(dst, &tm_pack, col, 0, b * p.pack, 0, bar);
                 };
                 slb_mbar_arrive_expect_tx(q_full, 2u * kPlane);
                 load_tile(smem + kOffQ, h * 64, row_base + tile * kTile, q_full);
@@ -648,7 +642,7 @@ int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int
         p.qkv = qkv_planes; p.plane_stride = rows * 3 * W;
     }
     int64_t n_batch = B;  // item indices b
-    CUtensorMap tm_hi = tm, tm_lo = tm;
+    CUtensorMap tm_pack = tm;
     if (T < kTile) {
         SLB_REQUIRE(n_tiles == 1 && tail_keys == 0, SLB_EINVAL, "slb_attention_ts_tiles: a short sequence is one tile");
         int shift = 4;
@@ -656,11 +650,21 @@ int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int
         p.slot_shift = shift; p.pack = kTile >> shift; p.Tseq = (int)T; p.B = (int)B; p.causal = causal ? 1 : 0;
         p.T = kTile;
         n_batch = (B + p.pack - 1) / p.pack;
-        // one plane, slot rows per box: an image's Q / K / V rows go to its slot of the tile
-        rc = slb_make_plane_map(&tm_hi, qkv_planes, rows, 3 * W, 1, 1 << shift);
-        if (rc != SLB_OK) return rc;
-        rc = slb_make_plane_map(&tm_lo, qkv_planes + rows * 3 * W, rows, 3 * W, 1, 1 << shift);
-        if (rc != SLB_OK) return rc;
+        // the planes as (plane, image, token, column); box = {64 columns, slot tokens, pack images, both planes}
+        slb_tmap_encode_fn enc = slb_get_tmap_encoder();
+        if (!enc) return SLB_ECUDA;
+        cuuint64_t dims[4] = {(cuuint64_t)(3 * W), (cuuint64_t)T, (cuuint64_t)B, 2};
+        cuuint64_t strides[3] = {(cuuint64_t)(3 * W) * 2, (cuuint64_t)T * (cuuint64_t)(3 * W) * 2, (cuuint64_t)rows * (cuuint64_t)(3 * W) * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(1 << shift), (cuuint32_t)p.pack, 2};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tm_pack, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<uint16_t*>(qkv_planes), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            slb_set_error("cuTensorMapEncodeTiled (packed attention map) failed with %d (B=%lld T=%lld W=%lld)", (int)r, (long long)B,
+                          (long long)T, (long long)W);
+            return SLB_ECUDA;
+        }
     } else {
         SLB_REQUIRE(!causal, SLB_EUNSUPPORTED, "slb_attention_ts_tiles: causal masks on short sequences only");
     }
@@ -681,7 +685,7 @@ int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int
     SLB_CUDA_OK(cudaGetDevice(&dev));
     SLB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = std::min(p.n_items, 2 * sms);  // persistent: two CTAs per SM
-    attention_ts_kernel<<<grid, kThreads, kSmem, st>>>(tm, tm_hi, tm_lo, p);
+    attention_ts_kernel<<<grid, kThreads, kSmem, st>>>(tm, tm_pack, p);
     SLB_LAUNCH_OK("attention_ts");
     return SLB_OK;
 }

@@ -44,6 +44,14 @@ __device__ __forceinline__ void slb_tma_load_3d(void* smem_dst, const CUtensorMa
         : "memory");
 }
 
+__device__ __forceinline__ void slb_tma_load_4d(void* smem_dst, const CUtensorMap* m, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(slb_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(slb_smem_u32(bar))
+        : "memory");
+}
+
 // im2col-mode load: {c, w, h, n} = channel offset and the coordinates of the FIRST output pixel's window corner in the
 // input (w = column * stride - pad, ...); {off_w, off_h} = the filter tap. The TMA unit steps through the output pixels.
 __device__ __forceinline__ void slb_tma_load_im2col_4d(void* smem_dst, const CUtensorMap* m, int c, int w, int h, int n,
