@@ -1,4 +1,5 @@
 #!/bin/bash
+# Two-GPU validation (gpurun --gpus 2): the two-rank NCCL equality tests and the bench with all sub-records under torchrun.
 TAG=${1:-val2}
 O=gpurun_out; mkdir -p $O
 timeout 600 python -m pytest tests/test_multigpu_gpu.py -m gpu -q -p no:cacheprovider > $O/${TAG}_pytest.log 2>&1; echo "exit $?" >> $O/${TAG}_pytest.log; tail -3 $O/${TAG}_pytest.log | cut -c1-300

@@ -1,3 +1,4 @@
+"""One launch of the polysemanticity kernel at cfg-5 neuron shape for ncu: python scripts/ncu_polysem.py"""
 import sys, torch
 sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent.parent))
 from semanticlens_b200 import ops
