@@ -58,3 +58,49 @@ def test_probability_planes_of_the_attention_kernels():
     assert np.max(np.abs(back - p)[p > 2.0**-10] / p[p > 2.0**-10]) < 2.0**-21
     tiny = p < 2.0**-14  # below the normal range of the lo plane the absolute error keeps shrinking with the hi plane's ulp
     assert np.max(np.abs(back - p)[tiny]) < 2.0**-34
+
+
+def test_a_residual_stream_kept_as_planes_loses_one_22_bit_rounding_per_block():
+    """SLB_EPI_ADD_RELU_PLANES (the ResNet paths): the shortcut is re-read from the previous block's output planes instead of
+    an fp32 copy. hi + lo is exact in fp32 (11 + 11 bits), so the only difference to an fp32 stream is the 2^-22 relative
+    truncation per block; over the 16 blocks of a ResNet-50 it stays two orders of magnitude under the 1e-4 parity bar."""
+    rng = np.random.default_rng(3)
+    x32 = np.abs(rng.standard_normal(100_000)).astype(np.float32)
+    x64 = x32.astype(np.float64)
+    xp = x32.copy()
+    for _ in range(16):
+        upd = (rng.standard_normal(x32.shape) * 0.5).astype(np.float32)
+        x64 = np.maximum(x64 + upd, 0.0)
+        x32 = np.maximum(x32 + upd, np.float32(0))
+        hi, lo = split(xp, ACT)
+        held = (hi.astype(np.float32) + lo.astype(np.float32)) / np.float32(ACT)  # what the epilogue reconstructs: exact
+        assert np.array_equal(held.astype(np.float64), (hi.astype(np.float64) + lo.astype(np.float64)) / ACT)
+        xp = np.maximum(held + upd, np.float32(0))
+    scale = np.abs(x64).max()
+    assert np.abs(x32 - x64).max() / scale < 1e-6
+    assert np.abs(xp - x64).max() / scale < 4e-6
+
+
+def test_ops_helpers_for_plane_shortcuts_on_the_host():
+    """ops.planes_to_f32 / ops._plane_residual: pure host logic (which epilogue a shortcut selects, shape checks)."""
+    import pytest
+    import torch
+
+    from semanticlens_b200 import _native as N
+    from semanticlens_b200 import ops
+
+    x = torch.randn(5, 8)
+    v = x * ACT
+    hi = v.half()
+    lo = (v - hi.float()).half()
+    planes = torch.stack([hi, lo])
+    assert torch.allclose(ops.planes_to_f32(planes), x, rtol=0, atol=2.0**-20 * x.abs().max().item())
+    assert ops._plane_residual(N.EPI_RELU, None, torch.float16, 5, 8) == (N.EPI_RELU, None)
+    f32 = torch.zeros(5, 8)
+    assert ops._plane_residual(N.EPI_ADD_RELU, f32, torch.float16, 5, 8) == (N.EPI_ADD_RELU, f32)
+    epi, res = ops._plane_residual(N.EPI_ADD_RELU, planes, torch.float16, 5, 8)
+    assert epi == N.EPI_ADD_RELU_PLANES and res is planes
+    with pytest.raises(AssertionError):
+        ops._plane_residual(N.EPI_RELU, planes, torch.float16, 5, 8)  # a plane shortcut only goes with add + ReLU
+    with pytest.raises(AssertionError):
+        ops._plane_residual(N.EPI_ADD_RELU, planes, torch.float16, 6, 8)  # wrong shape
