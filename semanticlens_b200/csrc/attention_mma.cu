@@ -751,10 +751,10 @@ extern "C" int slb_attention_planes(const uint16_t* qkv_planes, int64_t B, int64
         int n_tiles = (int)(T / 128);
         const int64_t rem = T - 128 * (int64_t)n_tiles;
         if (rem >= 64) n_tiles += 1;
-        // T = 128 n + 1..4 (ViT-L/14's 257 tokens): the tail keys ride in the softmax threads instead of a key block of their
-        // own (SLB_ATTN_KEY_TAIL=0: the old arrangement, a third block holding one key)
+        // T = 128 n + 1 (ViT-L/14's 257 tokens): the last key rides in the softmax threads instead of a key block of its own
+        // (SLB_ATTN_KEY_TAIL=0: the old arrangement, a third block holding one key)
         static const bool no_tail = [] { const char* e = getenv("SLB_ATTN_KEY_TAIL"); return e && e[0] == '0'; }();
-        const int tail_keys = (!no_tail && rem >= 1 && rem <= 4) ? (int)rem : 0;
+        const int tail_keys = (!no_tail && rem == 1) ? 1 : 0;  // (2..4 leftover keys: a block of their own, as before)
         int rc = slb_attention_ts_tiles(qkv_planes, B, T, H, scale, n_tiles, tail_keys, 0, plane_fmt, out_f32, p.out_hi, p.out_lo, st);
         if (rc != SLB_OK) return rc;
         if ((int64_t)n_tiles * 128 >= T) return SLB_OK;

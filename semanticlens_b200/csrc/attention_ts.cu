@@ -58,7 +58,7 @@ struct AttnTsParams {
     // k-steps and the same summation order wherever it sits in the tile: results are bit-identical for any batch composition.
     // pack = 0: one image per item.
     int pack, slot_shift, Tseq, B, causal;
-    // Key tail (T = 128 n + 1..4: the class token on top of a power-of-two patch grid, ViT-L/14's 257): the last `tail` keys do
+    // Key tail (T = 128 n + 1: the class token on top of a power-of-two patch grid, ViT-L/14's 257): the last key (tail = 1) does
     // not get a key block of their own (a block costs the same hand-offs whether it holds 1 key or 128: 91 -> 136 us per layer)
     // — the softmax threads take them in fp32 SIMT: logit from the Q row in shared memory, probability into the row sum, p v
     // added to O in the epilogue. T then counts the keys that go through the tensor cores; rows_seq is the real length.
@@ -357,16 +357,16 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
             int k_span = p.pack ? p.Tseq : p.T;
             if (p.pack) k_lo = (r >> p.slot_shift) << p.slot_shift;
             if (p.causal) k_span = min(k_span, r - k_lo + 1);  // causal: keys up to the query's own position
-            if (p.tail && warp == 2 && lane < 4 * p.tail) {
+            if (p.tail && warp == 2 && lane < 4) {
                 // the tail keys' K and V rows (hi / lo: four 128-byte lines per key) into L1 now: the softmax threads read them
                 // between the sweeps and in the epilogue, where a trip to L2 would sit on every warp's critical path
-                const int jt = lane >> 2, which = lane & 3;
-                const uint16_t* a = p.qkv + ((int64_t)row_base + p.T + jt) * (3 * p.W) + ((which & 1) ? 2 : 1) * p.W + h * 64 +
+                const int which = lane & 3;
+                const uint16_t* a = p.qkv + ((int64_t)row_base + p.T) * (3 * p.W) + ((which & 1) ? 2 : 1) * p.W + h * 64 +
                                     ((which & 2) ? p.plane_stride : 0);
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
             }
             float m_row = -INFINITY, l_row = 0.f, neg_m = 0.f;
-            float s_tail[4] = {0.f, 0.f, 0.f, 0.f};
+            float s_tail = 0.f;
             for (int it = 0; it < n_iter; ++it) {
                 const int blk = it < nblk ? it : n_iter - 1 - it;  // sweep 2 walks the blocks backwards
                 const bool sweep2 = it >= nblk;
@@ -376,48 +376,34 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
                 const bool full_block = !p.pack && (blk + 1) * kKeys <= p.T;
                 if (it == nblk) {
                     if (p.tail) {
-                        // the tail keys' logits for this thread's query row, fp32: q from the Q tile (both planes, 128-byte
-                        // swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)), k from the planes in global memory
+                        // the tail key's logit for this thread's query row, fp32: q from the Q tile (both planes, 128-byte
+                        // swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)), k from the planes in global memory.
+                        // (Rolled loop, one key: the first version unrolled four keys and grew the kernel from 79 to 126 KB of
+                        // code — ncu then showed 23 % of the samples waiting for instructions.)
                         ts_wait(q_full, (uint32_t)(n & 1));  // (long complete: makes the TMA's writes visible to this thread)
                         const unsigned char* qrow = smem + kOffQ + r * 128;
-                        float dot[4] = {0.f, 0.f, 0.f, 0.f};
-                        const int64_t krow = ((int64_t)row_base + p.T) * (3 * p.W) + p.W + h * 64;
-#pragma unroll
+                        const uint16_t* kh = p.qkv + ((int64_t)row_base + p.T) * (3 * p.W) + p.W + h * 64;
+                        float dot = 0.f;
+#pragma unroll 1
                         for (int ch = 0; ch < 8; ++ch) {
                             const uint4 qh = *reinterpret_cast<const uint4*>(qrow + ((ch ^ (r & 7)) << 4));
                             const uint4 ql = *reinterpret_cast<const uint4*>(qrow + kPlane + ((ch ^ (r & 7)) << 4));
+                            const uint4 kh4 = __ldg(reinterpret_cast<const uint4*>(kh + ch * 8));
+                            const uint4 kl4 = __ldg(reinterpret_cast<const uint4*>(kh + p.plane_stride + ch * 8));
                             const uint32_t qhw[4] = {qh.x, qh.y, qh.z, qh.w}, qlw[4] = {ql.x, ql.y, ql.z, ql.w};
-                            float qf[8];
+                            const uint32_t khw[4] = {kh4.x, kh4.y, kh4.z, kh4.w}, klw[4] = {kl4.x, kl4.y, kl4.z, kl4.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&qhw[e]));
-                                const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&qlw[e]));
-                                qf[2 * e] = a2.x + b2.x;
-                                qf[2 * e + 1] = a2.y + b2.y;
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                if (j >= p.tail) break;
-                                const uint16_t* kh = p.qkv + krow + (int64_t)j * (3 * p.W) + ch * 8;
-                                const uint4 kh4 = __ldg(reinterpret_cast<const uint4*>(kh));
-                                const uint4 kl4 = __ldg(reinterpret_cast<const uint4*>(kh + p.plane_stride));
-                                const uint32_t khw[4] = {kh4.x, kh4.y, kh4.z, kh4.w}, klw[4] = {kl4.x, kl4.y, kl4.z, kl4.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&khw[e]));
-                                    const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&klw[e]));
-                                    dot[j] = fmaf(qf[2 * e], a2.x + b2.x, dot[j]);
-                                    dot[j] = fmaf(qf[2 * e + 1], a2.y + b2.y, dot[j]);
-                                }
+                                const float2 qa = __half22float2(*reinterpret_cast<const __half2*>(&qhw[e]));
+                                const float2 qb = __half22float2(*reinterpret_cast<const __half2*>(&qlw[e]));
+                                const float2 ka = __half22float2(*reinterpret_cast<const __half2*>(&khw[e]));
+                                const float2 kb = __half22float2(*reinterpret_cast<const __half2*>(&klw[e]));
+                                dot = fmaf(qa.x + qb.x, ka.x + kb.x, dot);
+                                dot = fmaf(qa.y + qb.y, ka.y + kb.y, dot);
                             }
                         }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (j < p.tail) {
-                                s_tail[j] = dot[j] * c_main;  // planes carry the activation scale on both sides, like S
-                                m_row = fmaxf(m_row, s_tail[j]);
-                            }
-                        }
+                        s_tail = dot * c_main;  // planes carry the activation scale on both sides, like S
+                        m_row = fmaxf(m_row, s_tail);
                     }
                     // end of sweep 1: the two warps of a row combine their partial maxima
                     if (half) *xw = m_row;
@@ -524,16 +510,10 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
             }
             asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             if (half) l_row = *xw;
-            float p_tail[4] = {0.f, 0.f, 0.f, 0.f};
-            if (p.tail) {
-                // (l_row is complete except for the tail: every half-warp pair adds the same p, once)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j < p.tail) {
-                        p_tail[j] = ex2_approx(s_tail[j] + neg_m);
-                        l_row += p_tail[j];
-                    }
-                }
+            float p_tail = 0.f;
+            if (p.tail) {  // (l_row is complete except for the tail key: both warps of the row add the same p, once each)
+                p_tail = ex2_approx(s_tail + neg_m);
+                l_row += p_tail;
             }
             const float inv = kInvAct / l_row;  // V planes carry the activation scale, l_row the 2^10 of the P planes
             const int c = half * 32;
@@ -549,24 +529,20 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(a[j]) + __uint_as_float(cr[j]);
             if (p.tail) {
-                // O += p v for the tail keys: v = hi + lo of this head's 32 dims [c, c + 32) (planes at the activation scale, as
-                // the accumulated P V is)
+                // O += p v for the tail key: v = hi + lo of this head's 32 dims [c, c + 32) (planes at the activation scale, as the
+                // accumulated P V is)
+                const uint16_t* vh = p.qkv + ((int64_t)row_base + p.T) * (3 * p.W) + 2 * p.W + h * 64 + c;
 #pragma unroll
-                for (int jt = 0; jt < 4; ++jt) {
-                    if (jt >= p.tail) break;
-                    const uint16_t* vh = p.qkv + ((int64_t)row_base + p.T + jt) * (3 * p.W) + 2 * p.W + h * 64 + c;
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(vh + q4 * 8));
+                    const uint4 l4 = __ldg(reinterpret_cast<const uint4*>(vh + p.plane_stride + q4 * 8));
+                    const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(vh + q4 * 8));
-                        const uint4 l4 = __ldg(reinterpret_cast<const uint4*>(vh + p.plane_stride + q4 * 8));
-                        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
-                            const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
-                            o[q4 * 8 + 2 * e] = fmaf(p_tail[jt], a2.x + b2.x, o[q4 * 8 + 2 * e]);
-                            o[q4 * 8 + 2 * e + 1] = fmaf(p_tail[jt], a2.y + b2.y, o[q4 * 8 + 2 * e + 1]);
-                        }
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+                        const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+                        o[q4 * 8 + 2 * e] = fmaf(p_tail, a2.x + b2.x, o[q4 * 8 + 2 * e]);
+                        o[q4 * 8 + 2 * e + 1] = fmaf(p_tail, a2.y + b2.y, o[q4 * 8 + 2 * e + 1]);
                     }
                 }
             }
@@ -626,7 +602,7 @@ unsigned int* slb_attention_trace_buffer();  // attention_mma.cu
 // Full 128-row query tiles of every (image, head) on the TS-mode tcgen05 path; the caller handles the remaining rows.
 // T < 128 (n_tiles must be 1): packed mode — every image in a slot of 16 / 32 / 64 / 128 rows of the tile, block-diagonal (and,
 // with `causal`, lower-triangular) softmax mask, every row is covered.
-// tail_keys (0..4, only with T = 128 n_tiles + tail_keys): the last keys are taken by the softmax threads in fp32 (no key block).
+// tail_keys (0 or 1, only with T = 128 n_tiles + 1): the last key is taken by the softmax threads in fp32 (no key block).
 int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int64_t H, float scale, int n_tiles, int tail_keys,
                            int causal, int plane_fmt, float* out_f32, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
     const int64_t W = H * 64, rows = B * T;
@@ -636,8 +612,8 @@ int slb_attention_ts_tiles(const uint16_t* qkv_planes, int64_t B, int64_t T, int
     AttnTsParams p{};
     p.T = (int)T; p.H = (int)H; p.W = (int)W;
     if (tail_keys) {
-        SLB_REQUIRE(tail_keys > 0 && tail_keys <= 4 && T == (int64_t)n_tiles * kTile + tail_keys, SLB_EINVAL,
-                    "slb_attention_ts_tiles: a key tail is 1..4 keys past the last full block");
+        SLB_REQUIRE(tail_keys == 1 && T == (int64_t)n_tiles * kTile + 1, SLB_EINVAL,
+                    "slb_attention_ts_tiles: the key tail is the one key past the last full block");
         p.tail = tail_keys; p.rows_seq = (int)T; p.T = (int)(T - tail_keys);
         p.qkv = qkv_planes; p.plane_stride = rows * 3 * W;
     }

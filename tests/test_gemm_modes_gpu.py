@@ -47,7 +47,7 @@ def test_short_sequences_on_the_mma_sync_attention():
 
 
 def test_key_tail_as_a_block_of_its_own():
-    """SLB_ATTN_KEY_TAIL=0: T = 128 n + 1..4 runs the tail keys as one more key block (the arrangement before the SIMT tail)."""
+    """SLB_ATTN_KEY_TAIL=0: T = 128 n + 1 runs the last key as one more key block (the arrangement before the SIMT tail)."""
     env = dict(os.environ, SLB_ATTN_KEY_TAIL="0")
     r = subprocess.run(
         [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
