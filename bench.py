@@ -863,7 +863,9 @@ def run_cfg5(dev, rank: int, world: int, pk: dict, pk_src: str, with_cpu: bool, 
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        out = None
         for _ in range(iters):
+            out = None  # release the previous result first: two live 2.6 GB outputs would put a cudaMalloc inside the timed region
             out = fn()
         b.record()
         torch.cuda.synchronize()
